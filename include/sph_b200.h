@@ -1,0 +1,174 @@
+/*
+ * sph_b200.h — C-ABI of the B200-native SPH step engine.
+ *
+ * This is the drop-in boundary for the per-step hot path of the Fortran code
+ * graves-andrew-02/SUMMERSPH.  The reference has no FFI of its own (no bind(C),
+ * SURVEY.md §8(b)); the seam is cut at the body of `simulate`'s time loop:
+ *     fixed h    : SUMMER_SPH.f90:886-928            (mode SPH_MODE_FIXED_H)
+ *     variable h : "SUMMER_SPH - Variable.f90":1120-1162 (mode SPH_MODE_VARIABLE_H)
+ * The host (Fortran via ISO_C_BINDING, the C++ twin in host/, or Python ctypes)
+ * keeps `program run_sph`, file I/O, the `do while (t < end_time)` shell, the
+ * per-step print and the save cadence; everything inside the loop is one call.
+ *
+ * Conventions
+ *   - every entry point returns 0 on success, <0 on error (SPH_ERR_*); the text
+ *     of the last error is available from sph_last_error();
+ *   - plain pointers and sizes only; the caller owns its host arrays for the
+ *     duration of a call; the context owns all device memory and the
+ *     authoritative particle state between calls;
+ *   - particle arrays are SoA, FP64; rows come back in ascending `number`
+ *     order (the reference's array order after pack, SUMMER_SPH.f90:481,554);
+ *   - one host thread drives a context; calls are synchronous at return;
+ *   - there is NO CPU fallback: without a CUDA device sph_create fails with
+ *     SPH_ERR_NO_DEVICE.
+ */
+#ifndef SPH_B200_H
+#define SPH_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPH_MODE_FIXED_H     0   /* SUMMER_SPH.f90                     */
+#define SPH_MODE_VARIABLE_H  1   /* "SUMMER_SPH - Variable.f90"        */
+#define SPH_FLAG_SOFT_USES_HI 2  /* "(test new)" softening 0.001*h_i (T:298), OR-ed into mode */
+
+#define SPH_OK               0
+#define SPH_ERR_ARG         -1
+#define SPH_ERR_NO_DEVICE   -2
+#define SPH_ERR_CUDA        -3
+#define SPH_ERR_OOM         -4
+#define SPH_ERR_STATE       -5
+#define SPH_ERR_DEPTH       -6   /* particles closer than the key resolution while max_depth exceeds it */
+#define SPH_ERR_COMM        -7
+
+/* evaluation phases (sph_evaluate mask); a full reference evaluation is SPH_EVAL_ALL */
+#define SPH_EVAL_TREE     1   /* create_tree            F:795-816  V:999-1020 */
+#define SPH_EVAL_DENSITY  2   /* get_density + EOS      F:398-468  V:440-512  */
+#define SPH_EVAL_GRAVITY  4   /* particle_gravforces    F:249-290  V:270-311  */
+#define SPH_EVAL_SINKS    8   /* sink_gravforces        F:559-591  V:691-726  */
+#define SPH_EVAL_SPH     16   /* get_SPH                F:295-395  V:324-432  */
+#define SPH_EVAL_ALL     31
+
+/* Mirrors V's type(param) (Variable.f90:54-64, file order Variable.f90:899) plus the
+ * constants that are compile-time in F (SUMMER_SPH.f90:7-11, 694, 873). */
+typedef struct sph_params {
+  int32_t mode;                 /* SPH_MODE_* | SPH_FLAG_*                              */
+  int32_t max_depth;            /* F:8 (1000) | params%max_depth                        */
+  int32_t nq;                   /* kernel-table samples: 5000 (F:8) | 2500 (V:8)        */
+  int32_t n_ranks;              /* informational; multi-GPU is set up by sph_comm_init  */
+  double  h_fixed;              /* F:11 `smoothing` (2.5). Also the 0.001*smoothing gravity
+                                   softening add-on in BOTH modes (F:275, V:296)         */
+  double  bounding_size;        /* F:11 (1500) | params%bounding_size                   */
+  double  theta;                /* read but unused by the reference (V:1029); the BH
+                                   opening angle is the literal 0.5 unless theta_override */
+  double  gamma;                /* F:465-466 (1.4) | params%gamma                       */
+  double  eta;                  /* V:527                                                */
+  double  convergence_criteria; /* V:529                                                */
+  double  max_length;           /* V:528                                                */
+  double  timestep_scale;       /* F:851 (0.25) | params%timestep_scale                 */
+  double  end_time;             /* F:873 (1000) | params%end_time (host loop only)      */
+  double  sink_radius;          /* F:694 (3.5) | V:830 (5.0): radius given to IC sinks  */
+  int32_t theta_override;       /* 0: use literal 0.5 like the reference; 1: use .theta */
+  int32_t reserved;
+} sph_params;
+
+/* Interaction counters of the most recent evaluation (for flop rooflines). */
+typedef struct sph_counts {
+  int64_t n_gas;
+  int64_t n_nodes;               /* octree nodes incl. leaves                           */
+  int64_t density_candidates;    /* leaf box tests passed (F:443 | V:479)               */
+  int64_t density_contributing;  /* of those, q <= 2                                    */
+  int64_t sph_pairs;             /* unordered pairs reaching F:355 | V:384              */
+  int64_t grav_opened;           /* nodes opened (recursed)   F:284                     */
+  int64_t grav_accepted;         /* nodes accepted/leaf       F:279                     */
+  int64_t h_iterations;          /* calc_smoothing inner re-walks, summed over particles */
+} sph_counts;
+
+typedef struct sph_ctx sph_ctx;
+
+/* Fill `p` with the reference's defaults for `mode` (F's compile-time constants, or the
+ * values a typical parameters.txt carries for V). */
+int sph_default_params(int32_t mode, sph_params* p);
+
+/* Create / destroy a context on CUDA device `device` (use 0; under torchrun LOCAL_RANK). */
+int sph_create(const sph_params* p, int32_t device, sph_ctx** out);
+int sph_destroy(sph_ctx* ctx);
+const char* sph_last_error(const sph_ctx* ctx);   /* ctx may be NULL for create errors */
+
+/* Optional multi-GPU: `unique_id` is the 128-byte ncclUniqueId obtained from
+ * sph_comm_unique_id() on rank 0 and broadcast by the host (MPI / torch.distributed). */
+int sph_comm_unique_id(void* unique_id_128);
+int sph_comm_init(sph_ctx* ctx, int32_t rank, int32_t n_ranks, const void* unique_id_128);
+
+/* Replace the particle state (what read_data_from_file produces, F:594-716 | V:729-852).
+ * alpha may be NULL (=0, F:681); h may be NULL in fixed-h mode. n_sink may be 0: the
+ * reference's dummy zero-mass sink (F:698-707) is then created internally. */
+int sph_upload(sph_ctx* ctx, int64_t n_gas,
+               const double* x, const double* y, const double* z,
+               const double* vx, const double* vy, const double* vz,
+               const double* u, const double* m, const double* alpha, const double* h,
+               int32_t n_sink,
+               const double* sx, const double* sy, const double* sz,
+               const double* svx, const double* svy, const double* svz,
+               const double* sm, const double* srad);
+
+/* One evaluation (tree + density + EOS + find_forces) on the current state, no integration:
+ * the parity hook. `mask` selects phases (SPH_EVAL_*); rates are zeroed first (F:824). */
+int sph_evaluate(sph_ctx* ctx, int32_t mask);
+
+/* One body of the reference loop (F:886-928 | V:1120-1162): two evaluations, two half kicks,
+ * drift, t += dt, dt ladder, (V) h Newton-Raphson + sink creation, accretion, bounds cull. */
+int sph_step(sph_ctx* ctx, double* dt_inout, double* t_inout,
+             int64_t* n_gas_out, int32_t* n_sink_out);
+
+/* Device-resident loop: step until t >= t_stop or max_steps (<=0: unlimited) steps. */
+int sph_run_until(sph_ctx* ctx, double t_stop, int64_t max_steps,
+                  double* dt_inout, double* t_inout, int64_t* steps_out,
+                  int64_t* n_gas_out, int32_t* n_sink_out);
+
+int sph_sizes(sph_ctx* ctx, int64_t* n_gas, int32_t* n_sink);
+
+/* Download the state in ascending `number` order; any pointer may be NULL. Capacity of each
+ * array must be >= the current n_gas (resp. n_sink). */
+int sph_download(sph_ctx* ctx,
+                 double* x, double* y, double* z, double* vx, double* vy, double* vz,
+                 double* u, double* m, double* alpha, double* h,
+                 double* sx, double* sy, double* sz, double* svx, double* svy, double* svz,
+                 double* sm, double* srad);
+
+/* Per-evaluation quantities the reference never saves (parity hooks), ascending `number`. */
+int sph_download_diag(sph_ctx* ctx, double* rho, double* omega, double* pressure, double* sound,
+                      double* ax, double* ay, double* az, double* udot, double* alphadot,
+                      double* sink_ax, double* sink_ay, double* sink_az);
+
+/* Tree of the most recent evaluation: `order[k]` = number (0-based) of the k-th leaf in the
+ * reference's depth-first (Morton) order; per particle (ascending number): 63-bit descent key,
+ * leaf level (root=0), leaf cell centre and size. Any pointer may be NULL. */
+int sph_download_tree(sph_ctx* ctx, int32_t* order, uint64_t* key, int32_t* level,
+                      double* cx, double* cy, double* cz, double* size);
+
+/* Neighbour sets of the most recent evaluation, ascending `number`:
+ * count[i]  = #{ j : leaf box test of j passes for x_i }  (self included; F:443 | V:479),
+ * hash[i]   = sum over that set of mix64(number_j) (order independent),
+ * if list != NULL: CSR with offsets[i] (n_gas+1 entries, caller-provided) and list capacity
+ * `list_cap` entries, each row sorted ascending. */
+int sph_download_neighbours(sph_ctx* ctx, int32_t* count, uint64_t* hash,
+                            int64_t* offsets, int32_t* list, int64_t list_cap);
+
+int sph_counters(sph_ctx* ctx, sph_counts* out);
+
+/* Per-stage device time of the most recent sph_step / sph_evaluate in milliseconds:
+ * [0]=bbox+keys [1]=sort+reorder [2]=tree build [3]=density+EOS [4]=gravity(+sinks)
+ * [5]=SPH pair [6]=integrate+dt [7]=h iteration [8]=accretion+cull ; n <= 16 */
+int sph_stage_times(sph_ctx* ctx, double* ms, int32_t n);
+
+/* Number of CUDA kernel launches issued by this context so far. */
+int64_t sph_launch_count(sph_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPH_B200_H */
