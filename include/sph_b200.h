@@ -168,6 +168,16 @@ int sph_stage_times(sph_ctx* ctx, double* ms, int32_t n);
 /* Number of CUDA kernel launches issued by this context so far. */
 int64_t sph_launch_count(sph_ctx* ctx);
 
+/* Number of walk groups (cell-aligned runs of <= 32 particles) in the most recent tree. */
+int64_t sph_group_count(sph_ctx* ctx);
+
+/* CUDA-event timer on the context's own stream (bench.py: torch events cannot see this stream). */
+int sph_timer_start(sph_ctx* ctx);
+int sph_timer_stop(sph_ctx* ctx, double* elapsed_ms);
+
+/* FP64 FMA throughput of the device in TFLOP/s, measured with a register-resident FMA kernel. */
+int sph_fp64_peak(sph_ctx* ctx, double* tflops);
+
 #ifdef __cplusplus
 }
 #endif

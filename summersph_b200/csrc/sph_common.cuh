@@ -1,0 +1,89 @@
+// sph_common.cuh — shared device/host definitions of the B200 SPH step engine.
+//
+// Data layout in HBM (all FP64 SoA, particle arrays kept physically in the Morton order of the most
+// recent evaluation; `id` carries the reference's `number`, SUMMER_SPH.f90:15,886-888):
+//   state   : x y z vx vy vz u m alpha h            (10 x 8 B)  + id (4 B)     double-buffered for the re-order
+//   derived : rho omega P c PoR2                    ( 5 x 8 B)
+//   rates   : ax ay az udot alphadot                ( 5 x 8 B)
+//   tree    : key (8 B) level (4 B) leaf centre cx cy cz (24 B) reach R = 2h + size/2 (8 B)
+//   BVH     : per 32-particle chunk and per 8-ary group of chunks: position box + reach box, 12 floats
+//   octree  : compressed Barnes-Hut octree in depth-first preorder, 48 B per node (COM, M, size, next)
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#define SPH_KEY_LEVELS 21          // 3 bits per level in a 63-bit descent key
+#define SPH_CHUNK 32               // particles per BVH leaf chunk = one warp of targets
+#define SPH_BVH_FAN 8
+#define SPH_MAX_SINKS 64
+#define FULL_MASK 0xffffffffu
+
+struct DevParams {
+  int    variable_h;     // V mode
+  int    soft_hi;        // T:298 softening
+  int    nq;
+  int    lmax;           // min(max_depth, SPH_KEY_LEVELS)
+  int    depth_unbounded;// max_depth > SPH_KEY_LEVELS: equal keys are an error instead of a depth-limited leaf
+  double dq, inv_dq;
+  double h_fixed;
+  double pi_norm;        // F:125 3.14159265359_dp | V:7 real(4) pi
+  double gamma, gm1;
+  double theta;
+  double G;              // real(4) literal 39.478416442871094 (F:7)
+  double eta, conv, max_length, tscale, bounding;
+  double lit_001, lit_015, lit_01, lit_1em4;   // real(4) literals (SURVEY §8(a'))
+};
+
+// root cube of the current tree (device resident)
+struct RootBox { double cx, cy, cz, size; double mn[3], mx[3]; };
+
+// Barnes-Hut node, depth-first preorder; leaves are nodes too.
+struct __align__(16) GNode {
+  double cx, cy, cz, m;   // centre of mass, total mass
+  double size;            // cell edge at the node's own (branching / leaf) level
+  int    next;            // preorder index just past this node's subtree
+  int    flags;           // bit0: childless (leaf or depth-limited multi-particle node)
+};
+
+// float AABBs rounded outward; pos = particle positions, reach = union of leaf boxes expanded by 2h
+struct __align__(16) BvhBox { float plo[3], phi[3], rlo[3], rhi[3]; };
+
+__host__ __device__ inline uint64_t mix64(uint64_t z) {   // splitmix64 finaliser (same in oracle)
+  z += 0x9E3779B97F4A7C15ull; z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+#ifdef __CUDACC__
+// number of leading octal digits (levels) two 63-bit keys share, capped at lmax
+__device__ __forceinline__ int lcp_levels(uint64_t a, uint64_t b, int lmax) {
+  uint64_t x = a ^ b;
+  if (x == 0) return lmax;
+  int l = (__clzll((long long)x) - 1) / 3;
+  return l < lmax ? l : lmax;
+}
+
+__device__ __forceinline__ double warp_min(double v) {
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(FULL_MASK, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL_MASK, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_minf(float v) {
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(FULL_MASK, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_maxf(float v) {
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL_MASK, v, o));
+  return v;
+}
+__device__ __forceinline__ long long warp_sum_ll(long long v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+  return v;
+}
+#endif

@@ -1,0 +1,830 @@
+// sph_engine.cu — context, step orchestration and the C-ABI of include/sph_b200.h.
+//
+// One context = one CUDA device + one stream.  All particle data live in HBM between calls; the host
+// sees them only through sph_upload / sph_download.  There is no CPU code path for any stage.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include <dlfcn.h>
+#include <cub/cub.cuh>
+
+#include "../../include/sph_b200.h"
+#include "sph_common.cuh"
+#include "sph_tree.cuh"
+#include "sph_walk.cuh"
+#include "sph_gravity.cuh"
+#include "sph_integrate.cuh"
+
+namespace {
+
+thread_local std::string g_create_error;
+
+enum Stage { ST_KEYS = 0, ST_SORT, ST_TREE, ST_DENSITY, ST_GRAVITY, ST_SPH, ST_INTEGRATE, ST_HITER, ST_CULL, ST_COUNT };
+
+// x**n in libgcc __powidf2 order (kernel tables, SUMMER_SPH.f90:63-100)
+inline double powi(double x, int n) { double y = (n % 2) ? x : 1.0; while (n >>= 1) { x = x * x; if (n % 2) y *= x; } return y; }
+
+struct NcclUid { char b[128]; };
+struct NcclApi {   // resolved at run time from the already-loaded (torch-bundled) or system libnccl
+  void* lib = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, NcclUid /*ncclUniqueId by value*/, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  int (*Broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+
+}  // namespace
+
+struct sph_ctx {
+  sph_params p; DevParams dp; int device = 0; cudaStream_t stream = nullptr;
+  std::string err;
+  int64_t n = 0, cap = 0, n_upload = 0; int n_sink = 0;
+  // particle state, double buffered for the Morton re-order / compaction
+  double* st[2][10] = {}; int* id[2] = {}; int cur = 0;
+  double *rho = nullptr, *omega = nullptr, *prs = nullptr, *cs = nullptr, *por2 = nullptr;
+  double *ax = nullptr, *ay = nullptr, *az = nullptr, *udot = nullptr, *adot = nullptr;
+  // tree
+  uint64_t* key[2] = {}; int* perm[2] = {}; int* level = nullptr;
+  double *lcx = nullptr, *lcy = nullptr, *lcz = nullptr, *reach = nullptr;
+  BvhBox* bvh = nullptr; size_t bvh_cap = 0; BvhInfo bi;
+  int *node_count = nullptr, *gsize = nullptr, *gfirst = nullptr; int2* groups = nullptr; int n_groups = 0;
+  GNode* nodes = nullptr; int *node_part = nullptr, *parent = nullptr, *nchild = nullptr, *arrive = nullptr, *cnt = nullptr, *off = nullptr;
+  RootBox* root = nullptr; double* partial = nullptr; int n_partial = 0;
+  void* cub_tmp = nullptr; size_t cub_bytes = 0;
+  double *d_wt = nullptr, *d_dwt = nullptr, *d_gt = nullptr;
+  SinkArrays S = {}; double* sink_buf = nullptr; double* sink_partial = nullptr; size_t sink_partial_cap = 0;
+  SimScalars* sc = nullptr; SimScalars* h_sc = nullptr;     // device + pinned host mirror
+  WalkCounters* ctr = nullptr; WalkCounters* h_ctr = nullptr;
+  unsigned char* keep = nullptr; unsigned long long* acc_key[2] = {}; int* acc_val[2] = {}; int* d_nsel = nullptr;
+  int* pos = nullptr;           // ascending-number position of each sorted particle (downloads)
+  double* stage_d = nullptr;    // device staging for ordered downloads
+  bool tree_valid = false;
+  sph_counts counts; double stage_ms[ST_COUNT] = {};
+  std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> ev_used; std::vector<cudaEvent_t> ev_pool;
+  int64_t launches = 0;
+  cudaEvent_t tm0 = nullptr, tm1 = nullptr;
+  // multi-GPU
+  NcclApi nccl; void* comm = nullptr; int rank = 0, n_ranks = 1;
+};
+
+namespace {
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { c->err = std::string(#call) + ": " + cudaGetErrorString(e_); return SPH_ERR_CUDA; } } while (0)
+#define LAUNCH(kern, grid, block, smem, ...) do { kern<<<(grid), (block), (smem), c->stream>>>(__VA_ARGS__); ++c->launches; } while (0)
+
+inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+StateArrays state_of(sph_ctx* c, int which) {
+  double** s = c->st[which];
+  return StateArrays{s[0], s[1], s[2], s[3], s[4], s[5], s[6], s[7], s[8], s[9], c->id[which]};
+}
+RateArrays rates_of(sph_ctx* c) { return RateArrays{c->ax, c->ay, c->az, c->udot, c->adot}; }
+
+void stage_begin(sph_ctx* c, int st) {
+  cudaEvent_t a, b;
+  auto get = [&]() { cudaEvent_t e; if (!c->ev_pool.empty()) { e = c->ev_pool.back(); c->ev_pool.pop_back(); } else cudaEventCreate(&e); return e; };
+  a = get(); b = get();
+  cudaEventRecord(a, c->stream);
+  c->ev_used.push_back({st, {a, b}});
+}
+void stage_end(sph_ctx* c) { cudaEventRecord(c->ev_used.back().second.second, c->stream); }
+void stage_collect(sph_ctx* c, bool reset) {   // call after a stream sync
+  if (reset) for (int i = 0; i < ST_COUNT; ++i) c->stage_ms[i] = 0.0;
+  for (auto& e : c->ev_used) {
+    float ms = 0.f; cudaEventElapsedTime(&ms, e.second.first, e.second.second);
+    c->stage_ms[e.first] += ms;
+    c->ev_pool.push_back(e.second.first); c->ev_pool.push_back(e.second.second);
+  }
+  c->ev_used.clear();
+}
+
+template <class T> int dalloc(sph_ctx* c, T** p, size_t count) {
+  if (*p) { cudaFree(*p); *p = nullptr; }
+  if (count == 0) count = 1;
+  cudaError_t e = cudaMalloc((void**)p, count * sizeof(T));
+  if (e != cudaSuccess) { c->err = std::string("cudaMalloc: ") + cudaGetErrorString(e); cudaGetLastError(); return SPH_ERR_OOM; }
+  return SPH_OK;
+}
+#define DA(ptr, count) do { int r_ = dalloc(c, &(ptr), (size_t)(count)); if (r_) return r_; } while (0)
+
+int ensure_capacity(sph_ctx* c, int64_t n) {
+  if (n <= c->cap) return SPH_OK;
+  const int64_t cap = n + n / 64 + 1024;
+  for (int b = 0; b < 2; ++b) { for (int f = 0; f < 10; ++f) DA(c->st[b][f], cap); DA(c->id[b], cap); DA(c->key[b], cap); DA(c->perm[b], cap); DA(c->acc_key[b], cap); DA(c->acc_val[b], cap); }
+  DA(c->rho, cap); DA(c->omega, cap); DA(c->prs, cap); DA(c->cs, cap); DA(c->por2, cap);
+  DA(c->ax, cap); DA(c->ay, cap); DA(c->az, cap); DA(c->udot, cap); DA(c->adot, cap);
+  DA(c->level, cap); DA(c->lcx, cap); DA(c->lcy, cap); DA(c->lcz, cap); DA(c->reach, cap);
+  DA(c->node_count, 2 * cap); DA(c->gsize, cap); DA(c->gfirst, cap); DA(c->groups, cap);
+  DA(c->nodes, 2 * cap); DA(c->node_part, 2 * cap); DA(c->parent, 2 * cap); DA(c->nchild, 2 * cap); DA(c->arrive, 2 * cap);
+  DA(c->cnt, cap + 1); DA(c->off, cap + 1);
+  DA(c->keep, cap); DA(c->pos, cap); DA(c->stage_d, cap);
+  // CUB temp: radix sort pairs (u64,int), exclusive scan, select
+  size_t b1 = 0, b2 = 0, b3 = 0, b4 = 0;
+  cub::DeviceSelect::Flagged(nullptr, b4, cub::CountingInputIterator<int>(0), c->gsize, c->gfirst, c->d_nsel, (int)cap, c->stream);
+  cub::DoubleBuffer<uint64_t> dk(c->key[0], c->key[1]); cub::DoubleBuffer<int> dv(c->perm[0], c->perm[1]);
+  cub::DeviceRadixSort::SortPairs(nullptr, b1, dk, dv, (int)cap, 0, 64, c->stream);
+  cub::DeviceScan::ExclusiveSum(nullptr, b2, c->cnt, c->off, (int)cap + 1, c->stream);
+  cub::DeviceSelect::Flagged(nullptr, b3, c->perm[0], c->keep, c->perm[1], c->d_nsel, (int)cap, c->stream);
+  c->cub_bytes = std::max(std::max(b1, b4), std::max(b2, b3)) + 256;
+  if (c->cub_tmp) { cudaFree(c->cub_tmp); c->cub_tmp = nullptr; }
+  if (cudaMalloc(&c->cub_tmp, c->cub_bytes) != cudaSuccess) { c->err = "cudaMalloc(cub temp)"; cudaGetLastError(); return SPH_ERR_OOM; }
+  c->cap = cap;
+  return SPH_OK;
+}
+
+void make_dev_params(sph_ctx* c) {
+  const sph_params& p = c->p; DevParams& d = c->dp;
+  d.variable_h = (p.mode & SPH_MODE_VARIABLE_H) ? 1 : 0;
+  d.soft_hi = (p.mode & SPH_FLAG_SOFT_USES_HI) ? 1 : 0;
+  d.nq = p.nq;
+  d.lmax = p.max_depth < SPH_KEY_LEVELS ? p.max_depth : SPH_KEY_LEVELS;
+  d.depth_unbounded = p.max_depth > SPH_KEY_LEVELS;
+  d.dq = 2.0 / p.nq; d.inv_dq = 1.0 / d.dq;
+  d.h_fixed = p.h_fixed;
+  d.pi_norm = d.variable_h ? (double)3.1415926535897932f : 3.14159265359;      // V:7 | F:125
+  d.gamma = d.variable_h ? p.gamma : 1.4;                                      // F:466
+  d.gm1 = d.variable_h ? (p.gamma - 1.0) : 0.4;                                // F:465
+  d.theta = p.theta_override ? p.theta : 0.5;                                  // F:825
+  d.G = (double)39.47841760435743f;                                            // F:7
+  d.eta = p.eta; d.conv = p.convergence_criteria; d.max_length = p.max_length;
+  d.tscale = d.variable_h ? p.timestep_scale : 0.25;                           // F:851
+  d.bounding = p.bounding_size;
+  d.lit_001 = (double)0.01f; d.lit_015 = (double)0.15f; d.lit_01 = (double)0.1f; d.lit_1em4 = (double)0.0001f;
+}
+
+int upload_tables(sph_ctx* c) {
+  const int nq = c->p.nq; const double dq = 2.0 / nq;
+  std::vector<double> w(nq + 1), dw(nq + 1), g(nq + 1);
+  for (int i = 0; i <= nq; ++i) {
+    volatile double q = i * dq;
+    if (q >= 0.0 && q <= 1.0) {
+      w[i] = 1.0 - 1.5 * powi(q, 2) + 0.75 * powi(q, 3);
+      dw[i] = -3.0 * q + 2.25 * powi(q, 2);
+      g[i] = ((40.0 * powi(q, 3)) - (36.0 * powi(q, 5)) + (15.0 * powi(q, 6))) / 30.0;
+    } else if (q > 1.0 && q <= 2.0) {
+      w[i] = 0.25 * powi(2.0 - q, 3);
+      dw[i] = -0.75 * powi(2.0 - q, 2);
+      g[i] = ((80.0 * powi(q, 3)) - (90.0 * powi(q, 4)) + (36.0 * powi(q, 5)) - (5.0 * powi(q, 6)) - 2.0) / 30.0;
+    } else { w[i] = 0.0; dw[i] = 0.0; g[i] = 1.0; }
+  }
+  DA(c->d_wt, nq + 2); DA(c->d_dwt, nq + 2); DA(c->d_gt, nq + 2);
+  CK(cudaMemcpy(c->d_wt, w.data(), (nq + 1) * 8, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->d_dwt, dw.data(), (nq + 1) * 8, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->d_gt, g.data(), (nq + 1) * 8, cudaMemcpyHostToDevice));
+  return SPH_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// tree
+// ---------------------------------------------------------------------------------------------------
+int build_tree(sph_ctx* c) {
+  const int n = (int)c->n;
+  const int T = 256;
+  stage_begin(c, ST_KEYS);
+  {
+    StateArrays s = state_of(c, c->cur);
+    int nb = std::min(cdiv(n, T), c->n_partial);
+    LAUNCH(k_bbox_partial, nb, T, 0, n, s.x, s.y, s.z, c->partial);
+    // multi-GPU: particles are replicated, every rank sees the same box (no exchange needed)
+    LAUNCH(k_bbox_final, 1, 32, 0, nb, c->partial, c->root);
+    LAUNCH(k_keys, cdiv(n, T), T, 0, n, s.x, s.y, s.z, c->root, c->dp.lmax, c->key[0], c->perm[0]);
+  }
+  stage_end(c);
+  stage_begin(c, ST_SORT);
+  {
+    cub::DoubleBuffer<uint64_t> dk(c->key[0], c->key[1]); cub::DoubleBuffer<int> dv(c->perm[0], c->perm[1]);
+    size_t bytes = c->cub_bytes;
+    CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp, bytes, dk, dv, n, 0, 63, c->stream));
+    if (dk.Current() != c->key[0]) { std::swap(c->key[0], c->key[1]); }
+    if (dv.Current() != c->perm[0]) { std::swap(c->perm[0], c->perm[1]); }
+    PermuteArgs pa;
+    for (int f = 0; f < 10; ++f) { pa.src[f] = c->st[c->cur][f]; pa.dst[f] = c->st[c->cur ^ 1][f]; }
+    pa.id_src = c->id[c->cur]; pa.id_dst = c->id[c->cur ^ 1];
+    LAUNCH(k_permute, cdiv(n, T), T, 0, n, c->perm[0], pa);
+    c->cur ^= 1;
+  }
+  stage_end(c);
+  stage_begin(c, ST_TREE);
+  {
+    StateArrays s = state_of(c, c->cur);
+    LAUNCH(k_leaf, cdiv(n, T), T, 0, n, c->key[0], s.h, c->root, c->dp, c->level, c->lcx, c->lcy, c->lcz, c->reach, &c->sc->err);
+    // octree
+    LAUNCH(k_oct_nodes<false>, cdiv(n, T), T, 0, n, c->key[0], c->dp.lmax, c->root, c->cnt, c->off, 0, c->nodes, c->node_part, c->node_count);
+    CK(cudaMemsetAsync(c->cnt + n, 0, sizeof(int), c->stream));
+    size_t bytes = c->cub_bytes;
+    CK(cub::DeviceScan::ExclusiveSum(c->cub_tmp, bytes, c->cnt, c->off, n + 1, c->stream));
+    // node count is needed on the host for launch sizes of the per-node passes
+    int n_int = 0;
+    CK(cudaMemcpyAsync(&n_int, c->off + n, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    const int nn = n + n_int;
+    c->counts.n_nodes = nn;
+    LAUNCH(k_oct_nodes<true>, cdiv(n, T), T, 0, n, c->key[0], c->dp.lmax, c->root, c->cnt, c->off, nn, c->nodes, c->node_part, c->node_count);
+    LAUNCH(k_oct_link, cdiv(nn, T), T, 0, nn, c->nodes, c->node_part, c->parent, c->nchild);
+    CK(cudaMemsetAsync(c->arrive, 0, sizeof(int) * (size_t)nn, c->stream));
+    LAUNCH(k_oct_up, cdiv(n, T), T, 0, n, c->off, c->cnt, s.x, s.y, s.z, s.m, s.h, c->level, c->root, c->nodes, c->parent, c->nchild, c->arrive);
+    LAUNCH(k_oct_finalize, cdiv(nn, T), T, 0, nn, c->nodes);
+    // walk groups (cell-aligned buckets) and the implicit 8-ary BVH over them
+    CK(cudaMemsetAsync(c->gsize, 0, sizeof(int) * (size_t)n, c->stream));
+    LAUNCH(k_group_mark, cdiv(nn, T), T, 0, nn, c->nodes, c->node_part, c->node_count, c->gsize);
+    bytes = c->cub_bytes;
+    CK(cub::DeviceSelect::Flagged(c->cub_tmp, bytes, cub::CountingInputIterator<int>(0), c->gsize, c->gfirst, c->d_nsel, n, c->stream));
+    int ng = 0;
+    CK(cudaMemcpyAsync(&ng, c->d_nsel, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->n_groups = ng;
+    if ((size_t)ng + ng / 7 + 64 > c->bvh_cap) { c->bvh_cap = (size_t)(ng + ng / 7 + 64) * 5 / 4; DA(c->bvh, c->bvh_cap); }
+    LAUNCH(k_group_pack, cdiv(ng, T), T, 0, ng, c->gfirst, c->gsize, c->groups);
+    BvhInfo& bi = c->bi;
+    int cntl = ng, offl = 0, l = 0;
+    bi.off[0] = 0; bi.cnt[0] = cntl;
+    LAUNCH(k_bvh_leaf, cdiv((int64_t)cntl * 32, T), T, 0, ng, c->groups, s.x, s.y, s.z, c->lcx, c->lcy, c->lcz, c->reach, c->bvh);
+    while (cntl > 32) {
+      int np = cdiv(cntl, SPH_BVH_FAN);
+      bi.off[l + 1] = offl + cntl; bi.cnt[l + 1] = np;
+      LAUNCH(k_bvh_up, cdiv(np, T), T, 0, cntl, c->bvh + offl, c->bvh + offl + cntl);
+      offl += cntl; cntl = np; ++l;
+    }
+    bi.nlev = l + 1;
+  }
+  stage_end(c);
+  c->tree_valid = true;
+  return SPH_OK;
+}
+
+size_t density_smem(const sph_ctx* c, int nwarp) { return (size_t)2 * (c->p.nq + 1) * 8 + (size_t)nwarp * 8 * WALK_TILE * 8 + (size_t)nwarp * (WALK_STACK + WALK_CQ) * 4; }
+size_t force_smem(const sph_ctx* c, int nwarp) {
+  size_t t = (size_t)((c->p.nq + 1) + ((c->p.nq + 1) & 1)) * 8;
+  return t + (size_t)nwarp * FORCE_FIELDS * WALK_TILE * 8 + (size_t)nwarp * WALK_TILE * 4 + (size_t)nwarp * (WALK_STACK + WALK_CQ) * 4;
+}
+int walk_grid(const sph_ctx* c, int nwarp) {
+  const int nchunk = c->n_groups;
+  int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+  return std::max(1, std::min(cdiv(nchunk, nwarp), sms));
+}
+
+DensityArrays dens_arrays(sph_ctx* c) {
+  StateArrays s = state_of(c, c->cur);
+  return DensityArrays{s.x, s.y, s.z, s.m, c->lcx, c->lcy, c->lcz, c->reach};
+}
+
+int run_density(sph_ctx* c) {
+  const int n = (int)c->n, W = 16;
+  stage_begin(c, ST_DENSITY);
+  StateArrays s = state_of(c, c->cur);
+  LAUNCH(k_density<false>, walk_grid(c, W), W * 32, density_smem(c, W), c->n_groups, c->groups, c->dp, dens_arrays(c), c->bvh, c->bi, c->d_wt, c->d_dwt,
+         s.u, s.h, c->rho, c->omega, c->prs, c->cs, c->por2, c->ctr);
+  stage_end(c);
+  return SPH_OK;
+}
+int run_hiter(sph_ctx* c) {
+  const int n = (int)c->n, W = 16;
+  stage_begin(c, ST_HITER);
+  StateArrays s = state_of(c, c->cur);
+  LAUNCH(k_density<true>, walk_grid(c, W), W * 32, density_smem(c, W), c->n_groups, c->groups, c->dp, dens_arrays(c), c->bvh, c->bi, c->d_wt, c->d_dwt,
+         s.u, s.h, c->rho, c->omega, c->prs, c->cs, c->por2, c->ctr);
+  stage_end(c);
+  return SPH_OK;
+}
+int run_force(sph_ctx* c) {
+  const int n = (int)c->n, W = 16;
+  stage_begin(c, ST_SPH);
+  StateArrays s = state_of(c, c->cur);
+  ForceArrays A{s.x, s.y, s.z, s.vx, s.vy, s.vz, s.m, s.h, c->rho, c->cs, s.alpha, c->por2, c->lcx, c->lcy, c->lcz, c->reach, s.id};
+  LAUNCH(k_force, walk_grid(c, W), W * 32, force_smem(c, W), c->n_groups, c->groups, c->dp, A, c->bvh, c->bi, c->d_dwt, c->ax, c->ay, c->az, c->udot, c->adot, c->ctr);
+  stage_end(c);
+  return SPH_OK;
+}
+int run_gravity(sph_ctx* c, int do_grav, int do_sinks) {
+  const int n = (int)c->n, T = 256;
+  stage_begin(c, ST_GRAVITY);
+  StateArrays s = state_of(c, c->cur);
+  const int nb = cdiv(n, T);
+  const int ns = do_sinks ? c->n_sink : 0;
+  if ((size_t)nb * std::max(ns, 1) * 3 > c->sink_partial_cap) {
+    c->sink_partial_cap = (size_t)nb * std::max(ns, 1) * 3 * 2;
+    DA(c->sink_partial, c->sink_partial_cap);
+  }
+  LAUNCH(k_gravity, nb, T, (size_t)(c->p.nq + 1) * 8, n, c->dp, c->nodes, (int)c->counts.n_nodes, s.x, s.y, s.z, s.h, s.m, c->d_gt,
+         c->ax, c->ay, c->az, do_grav, ns, c->S, c->sink_partial, c->ctr);
+  LAUNCH(k_sink_finalize, 1, 32, 0, nb, c->n_sink, c->sink_partial, c->S, c->dp.G, do_sinks);
+  stage_end(c);
+  return SPH_OK;
+}
+
+int evaluate(sph_ctx* c, int mask) {
+  if (c->n < 2) { c->err = "need at least 2 gas particles"; return SPH_ERR_STATE; }
+  const size_t nb = (size_t)c->n * 8;
+  CK(cudaMemsetAsync(c->ax, 0, nb, c->stream)); CK(cudaMemsetAsync(c->ay, 0, nb, c->stream)); CK(cudaMemsetAsync(c->az, 0, nb, c->stream));
+  CK(cudaMemsetAsync(c->udot, 0, nb, c->stream)); CK(cudaMemsetAsync(c->adot, 0, nb, c->stream));     // F:824
+  CK(cudaMemsetAsync(c->ctr, 0, sizeof(WalkCounters), c->stream));
+  int r;
+  if (mask & SPH_EVAL_TREE) { if ((r = build_tree(c))) return r; }
+  else if (!c->tree_valid) { c->err = "no tree: evaluate with SPH_EVAL_TREE first"; return SPH_ERR_STATE; }
+  if (mask & SPH_EVAL_DENSITY) { if ((r = run_density(c))) return r; }
+  if ((r = run_gravity(c, (mask & SPH_EVAL_GRAVITY) ? 1 : 0, (mask & SPH_EVAL_SINKS) ? 1 : 0))) return r;
+  if (mask & SPH_EVAL_SPH) { if ((r = run_force(c))) return r; }
+  return SPH_OK;
+}
+
+int fetch_counters(sph_ctx* c) {
+  CK(cudaMemcpyAsync(c->h_ctr, c->ctr, sizeof(WalkCounters), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  c->counts.n_gas = c->n;
+  c->counts.density_candidates = (int64_t)c->h_ctr->dens_cand;
+  c->counts.density_contributing = (int64_t)c->h_ctr->dens_contrib;
+  c->counts.sph_pairs = (int64_t)(c->h_ctr->sph_pairs / 2);
+  c->counts.grav_opened = (int64_t)c->h_ctr->grav_opened;
+  c->counts.grav_accepted = (int64_t)c->h_ctr->grav_accepted;
+  return SPH_OK;
+}
+
+int check_device_error(sph_ctx* c) {
+  if (c->h_sc->err) {
+    c->err = "particles share a full 63-bit descent key (closer than root_size/2^21) while max_depth > 21";
+    return SPH_ERR_DEPTH;
+  }
+  return SPH_OK;
+}
+
+// compaction after accretion / bounds: order preserving (pack, F:481,554)
+int compact(sph_ctx* c) {
+  const int n = (int)c->n, T = 256;
+  LAUNCH(k_iota, cdiv(n, T), T, 0, n, c->perm[0]);
+  size_t bytes = c->cub_bytes;
+  CK(cub::DeviceSelect::Flagged(c->cub_tmp, bytes, c->perm[0], c->keep, c->perm[1], c->d_nsel, n, c->stream));
+  int nsel = 0;
+  CK(cudaMemcpyAsync(&nsel, c->d_nsel, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  PermuteArgs pa;
+  for (int f = 0; f < 10; ++f) { pa.src[f] = c->st[c->cur][f]; pa.dst[f] = c->st[c->cur ^ 1][f]; }
+  pa.id_src = c->id[c->cur]; pa.id_dst = c->id[c->cur ^ 1];
+  if (nsel > 0) LAUNCH(k_permute, cdiv(nsel, T), T, 0, nsel, c->perm[1], pa);
+  c->cur ^= 1;
+  c->n = nsel;
+  c->tree_valid = false;
+  return SPH_OK;
+}
+
+int step(sph_ctx* c) {
+  const int T = 256;
+  int r;
+  int n = (int)c->n;
+  if ((r = evaluate(c, SPH_EVAL_ALL))) return r;                              // F:894-898
+  stage_begin(c, ST_INTEGRATE);
+  LAUNCH(k_kick<true>, cdiv(n, T), T, 0, n, state_of(c, c->cur), rates_of(c), c->sc);       // F:900,903
+  LAUNCH(k_kick_sinks<true>, 1, SPH_MAX_SINKS, 0, c->S, c->sc);
+  stage_end(c);
+  if ((r = evaluate(c, SPH_EVAL_ALL))) return r;                              // F:905-910
+  stage_begin(c, ST_INTEGRATE);
+  LAUNCH(k_kick<false>, cdiv(n, T), T, 0, n, state_of(c, c->cur), rates_of(c), c->sc);      // F:912
+  LAUNCH(k_kick_sinks<false>, 1, SPH_MAX_SINKS, 0, c->S, c->sc);
+  {
+    int nb = std::min(cdiv(n, T), c->n_partial);
+    LAUNCH(k_dt_partial, nb, T, 0, n, c->dp, state_of(c, c->cur), rates_of(c), c->cs, c->partial);   // F:916
+    LAUNCH(k_dt_final, 1, 32, 0, nb, c->partial, c->dp, c->sc, 1);                                   // F:914
+  }
+  stage_end(c);
+  if (c->dp.variable_h) {
+    if ((r = run_hiter(c))) return r;                                         // V:1152
+    stage_begin(c, ST_CULL);
+    LAUNCH(k_create_scan, cdiv(n, T), T, 0, n, c->dp, state_of(c, c->cur), c->sc);          // V:1155
+    LAUNCH(k_create_apply, 1, 32, 0, state_of(c, c->cur), c->S, c->sc);
+    stage_end(c);
+  }
+  stage_begin(c, ST_CULL);
+  LAUNCH(k_any_sink_mass, 1, 32, 0, c->S, c->sc);                             // F:919
+  LAUNCH(k_flags, cdiv(n, T), T, 0, n, c->dp, state_of(c, c->cur), c->key[0], c->level, c->lcx, c->lcy, c->lcz, c->reach, c->root,
+         c->S, c->sc, c->keep, c->acc_key[0], c->acc_val[0], (int)c->cap);
+  CK(cudaMemcpyAsync(c->h_sc, c->sc, sizeof(SimScalars), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  if ((r = check_device_error(c))) return r;
+  int n_acc = std::min(c->h_sc->n_accreted, (int)c->cap);
+  if (n_acc > 1) {
+    cub::DoubleBuffer<unsigned long long> dk(c->acc_key[0], c->acc_key[1]); cub::DoubleBuffer<int> dv(c->acc_val[0], c->acc_val[1]);
+    size_t bytes = c->cub_bytes;
+    CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp, bytes, dk, dv, n_acc, 0, 64, c->stream));
+    if (dk.Current() != c->acc_key[0]) std::swap(c->acc_key[0], c->acc_key[1]);
+    if (dv.Current() != c->acc_val[0]) std::swap(c->acc_val[0], c->acc_val[1]);
+  }
+  LAUNCH(k_accrete_apply, 1, SPH_MAX_SINKS, 0, n_acc, c->acc_key[0], c->acc_val[0], state_of(c, c->cur), c->S, c->sc);
+  if (c->dp.variable_h) LAUNCH(k_cull_sinks, 1, 32, 0, c->dp, c->S, c->sc);   // V:613
+  const int n_removed = c->h_sc->n_removed;
+  // reset per-step device counters
+  CK(cudaMemsetAsync(&c->sc->n_removed, 0, sizeof(int) * 2, c->stream));
+  if (n_removed > 0) { if ((r = compact(c))) return r; }
+  CK(cudaMemcpyAsync(c->h_sc, c->sc, sizeof(SimScalars), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  c->n_sink = c->h_sc->n_sink;
+  stage_end(c);
+  return SPH_OK;
+}
+
+// ascending-number position of every sorted particle: rank of its id among the surviving ids
+int compute_pos(sph_ctx* c) {
+  const int n = (int)c->n;
+  std::vector<int> ids(n), pos(n);
+  CK(cudaMemcpyAsync(ids.data(), c->id[c->cur], (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  if ((int64_t)n == c->n_upload) { pos = ids; }
+  else {
+    std::vector<int> present((size_t)c->n_upload + 1, 0);
+    for (int i = 0; i < n; ++i) present[ids[i]] = 1;
+    int acc = 0; for (int64_t k = 0; k < c->n_upload; ++k) { int p = present[k]; present[k] = acc; acc += p; }
+    for (int i = 0; i < n; ++i) pos[i] = present[ids[i]];
+  }
+  CK(cudaMemcpyAsync(c->pos, pos.data(), (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return SPH_OK;
+}
+int fetch_ordered(sph_ctx* c, const double* src, double* dst_host) {
+  if (!dst_host) return SPH_OK;
+  const int n = (int)c->n, T = 256;
+  LAUNCH(k_scatter_d, cdiv(n, T), T, 0, n, c->pos, src, c->stage_d);
+  CK(cudaMemcpyAsync(dst_host, c->stage_d, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return SPH_OK;
+}
+int fetch_sink(sph_ctx* c, const double* src, double* dst_host) {
+  if (!dst_host || c->n_sink == 0) return SPH_OK;
+  CK(cudaMemcpyAsync(dst_host, src, (size_t)c->n_sink * 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return SPH_OK;
+}
+
+bool load_nccl(sph_ctx* c) {
+  if (c->nccl.lib) return true;
+  const char* names[] = {"libnccl.so.2", "libnccl.so", nullptr};
+  void* h = nullptr;
+  for (int i = 0; names[i] && !h; ++i) h = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+  if (!h) { c->err = std::string("dlopen libnccl: ") + dlerror(); return false; }
+  c->nccl.lib = h;
+  *(void**)&c->nccl.GetUniqueId = dlsym(h, "ncclGetUniqueId");
+  *(void**)&c->nccl.CommInitRank = dlsym(h, "ncclCommInitRank");
+  *(void**)&c->nccl.CommDestroy = dlsym(h, "ncclCommDestroy");
+  *(void**)&c->nccl.AllReduce = dlsym(h, "ncclAllReduce");
+  *(void**)&c->nccl.AllGather = dlsym(h, "ncclAllGather");
+  *(void**)&c->nccl.Broadcast = dlsym(h, "ncclBroadcast");
+  *(void**)&c->nccl.GetErrorString = dlsym(h, "ncclGetErrorString");
+  if (!c->nccl.CommInitRank || !c->nccl.AllGather) { c->err = "libnccl: missing symbols"; return false; }
+  return true;
+}
+
+}  // namespace
+
+// =====================================================================================================
+extern "C" {
+
+int sph_default_params(int32_t mode, sph_params* p) {
+  if (!p) return SPH_ERR_ARG;
+  std::memset(p, 0, sizeof(*p));
+  p->mode = mode; p->n_ranks = 1; p->h_fixed = 2.5; p->theta = 0.5; p->theta_override = 0;
+  p->max_depth = 1000; p->bounding_size = 1500.0; p->gamma = 1.4; p->eta = 1.2;
+  p->convergence_criteria = 1e-3; p->max_length = 50.0; p->timestep_scale = 0.25;
+  if (mode & SPH_MODE_VARIABLE_H) { p->nq = 2500; p->end_time = 0.1; p->sink_radius = 5.0; }
+  else { p->nq = 5000; p->end_time = 1000.0; p->sink_radius = 3.5; }
+  return SPH_OK;
+}
+
+const char* sph_last_error(const sph_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int sph_create(const sph_params* p, int32_t device, sph_ctx** out) {
+  if (!p || !out) { g_create_error = "null argument"; return SPH_ERR_ARG; }
+  if (p->nq < 2 || p->nq > 12000 || p->max_depth < 1) { g_create_error = "bad nq / max_depth"; return SPH_ERR_ARG; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { cudaGetLastError(); g_create_error = "no CUDA device (there is no CPU fallback)"; return SPH_ERR_NO_DEVICE; }
+  if (device < 0 || device >= ndev) { g_create_error = "bad device index"; return SPH_ERR_ARG; }
+  sph_ctx* c = new sph_ctx();
+  c->p = *p; c->device = device;
+  std::memset(&c->counts, 0, sizeof(c->counts));
+  auto fail = [&](int code) { g_create_error = c->err; sph_destroy(c); return code; };
+  if (cudaSetDevice(device) != cudaSuccess) { c->err = "cudaSetDevice failed"; return fail(SPH_ERR_CUDA); }
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { c->err = "stream create failed"; return fail(SPH_ERR_CUDA); }
+  make_dev_params(c);
+  int r;
+  if ((r = upload_tables(c))) return fail(r);
+  c->n_partial = 4096;
+  if ((r = dalloc(c, &c->partial, (size_t)c->n_partial * 6))) return fail(r);
+  if ((r = dalloc(c, &c->root, 1))) return fail(r);
+  if ((r = dalloc(c, &c->sc, 1))) return fail(r);
+  if ((r = dalloc(c, &c->ctr, 1))) return fail(r);
+  if ((r = dalloc(c, &c->d_nsel, 1))) return fail(r);
+  if ((r = dalloc(c, &c->sink_buf, (size_t)SPH_MAX_SINKS * 11))) return fail(r);
+  { double* b = c->sink_buf; const int M = SPH_MAX_SINKS;
+    c->S = SinkArrays{b, b + M, b + 2 * M, b + 3 * M, b + 4 * M, b + 5 * M, b + 6 * M, b + 7 * M, b + 8 * M, b + 9 * M, b + 10 * M}; }
+  cudaMemset(c->sink_buf, 0, (size_t)SPH_MAX_SINKS * 11 * 8);
+  if (cudaMallocHost((void**)&c->h_sc, sizeof(SimScalars)) != cudaSuccess || cudaMallocHost((void**)&c->h_ctr, sizeof(WalkCounters)) != cudaSuccess) { c->err = "cudaMallocHost failed"; return fail(SPH_ERR_OOM); }
+  std::memset(c->h_sc, 0, sizeof(SimScalars)); c->h_sc->create_cand = ~0ull; c->h_sc->dt = 1.0e-2;
+  cudaMemcpy(c->sc, c->h_sc, sizeof(SimScalars), cudaMemcpyHostToDevice);
+  cudaMemset(c->ctr, 0, sizeof(WalkCounters));
+  // opt in to large dynamic shared memory
+  int maxsm = 0; cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  size_t need = std::max(density_smem(c, 16), force_smem(c, 16));
+  if ((size_t)maxsm < need) { c->err = "device shared memory too small for the walk kernels"; return fail(SPH_ERR_CUDA); }
+  cudaFuncSetAttribute(k_density<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)density_smem(c, 16));
+  cudaFuncSetAttribute(k_density<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)density_smem(c, 16));
+  cudaFuncSetAttribute(k_force, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)force_smem(c, 16));
+  cudaFuncSetAttribute(k_gravity, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((c->p.nq + 1) * 8));
+  cudaFuncSetAttribute(k_neighbours, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  if (cudaGetLastError() != cudaSuccess) { c->err = "cudaFuncSetAttribute failed (was the library built for this GPU's architecture?)"; return fail(SPH_ERR_CUDA); }
+  *out = c;
+  return SPH_OK;
+}
+
+int sph_destroy(sph_ctx* c) {
+  if (!c) return SPH_OK;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->comm && c->nccl.CommDestroy) c->nccl.CommDestroy(c->comm);
+  auto F = [](void* p) { if (p) cudaFree(p); };
+  for (int b = 0; b < 2; ++b) { for (int f = 0; f < 10; ++f) F(c->st[b][f]); F(c->id[b]); F(c->key[b]); F(c->perm[b]); F(c->acc_key[b]); F(c->acc_val[b]); }
+  F(c->rho); F(c->omega); F(c->prs); F(c->cs); F(c->por2); F(c->ax); F(c->ay); F(c->az); F(c->udot); F(c->adot);
+  F(c->node_count); F(c->gsize); F(c->gfirst); F(c->groups); F(c->level); F(c->lcx); F(c->lcy); F(c->lcz); F(c->reach); F(c->bvh); F(c->nodes); F(c->node_part); F(c->parent); F(c->nchild);
+  F(c->arrive); F(c->cnt); F(c->off); F(c->root); F(c->partial); F(c->cub_tmp); F(c->d_wt); F(c->d_dwt); F(c->d_gt);
+  F(c->sink_buf); F(c->sink_partial); F(c->sc); F(c->ctr); F(c->keep); F(c->d_nsel); F(c->pos); F(c->stage_d);
+  if (c->h_sc) cudaFreeHost(c->h_sc);
+  if (c->h_ctr) cudaFreeHost(c->h_ctr);
+  for (auto& e : c->ev_used) { cudaEventDestroy(e.second.first); cudaEventDestroy(e.second.second); }
+  for (auto e : c->ev_pool) cudaEventDestroy(e);
+  if (c->tm0) { cudaEventDestroy(c->tm0); cudaEventDestroy(c->tm1); }
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return SPH_OK;
+}
+
+int sph_comm_unique_id(void* uid) {
+  sph_ctx tmp; sph_ctx* c = &tmp;
+  if (!uid) return SPH_ERR_ARG;
+  if (!load_nccl(c)) { g_create_error = c->err; return SPH_ERR_COMM; }
+  int r = c->nccl.GetUniqueId(uid);
+  return r == 0 ? SPH_OK : SPH_ERR_COMM;
+}
+
+int sph_comm_init(sph_ctx* c, int32_t rank, int32_t n_ranks, const void* uid) {
+  if (!c || !uid || n_ranks < 1 || rank < 0 || rank >= n_ranks) return SPH_ERR_ARG;
+  cudaSetDevice(c->device);
+  if (!load_nccl(c)) return SPH_ERR_COMM;
+  NcclUid id; std::memcpy(&id, uid, 128);
+  int r = c->nccl.CommInitRank(&c->comm, n_ranks, id, rank);
+  if (r != 0) { c->err = std::string("ncclCommInitRank: ") + (c->nccl.GetErrorString ? c->nccl.GetErrorString(r) : "?"); return SPH_ERR_COMM; }
+  c->rank = rank; c->n_ranks = n_ranks;
+  return SPH_OK;
+}
+
+int sph_upload(sph_ctx* c, int64_t n, const double* x, const double* y, const double* z,
+               const double* vx, const double* vy, const double* vz, const double* u, const double* m,
+               const double* alpha, const double* h, int32_t ns,
+               const double* sx, const double* sy, const double* sz, const double* svx, const double* svy, const double* svz,
+               const double* sm, const double* srad) {
+  if (!c) return SPH_ERR_ARG;
+  if (n < 2 || n > 0x0fffffff * (int64_t)SPH_CHUNK || !x || !y || !z || !vx || !vy || !vz || !u || !m) { c->err = "bad particle arrays"; return SPH_ERR_ARG; }
+  if (ns < 0 || ns > SPH_MAX_SINKS - 8) { c->err = "too many sinks"; return SPH_ERR_ARG; }
+  if (c->dp.variable_h && !h) { c->err = "variable-h mode needs the smoothing-length column"; return SPH_ERR_ARG; }
+  cudaSetDevice(c->device);
+  int r = ensure_capacity(c, n); if (r) return r;
+  c->n = n; c->n_upload = n; c->cur = 0; c->tree_valid = false;
+  const double* src[10] = {x, y, z, vx, vy, vz, u, m, alpha, c->dp.variable_h ? h : nullptr};   // F ignores column 10
+  for (int f = 0; f < 10; ++f) {
+    if (src[f]) CK(cudaMemcpyAsync(c->st[0][f], src[f], (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+    else if (f == 8) CK(cudaMemsetAsync(c->st[0][f], 0, (size_t)n * 8, c->stream));            // alpha := 0, F:681
+    else { std::vector<double> hv((size_t)n, c->p.h_fixed); CK(cudaMemcpyAsync(c->st[0][f], hv.data(), (size_t)n * 8, cudaMemcpyHostToDevice, c->stream)); CK(cudaStreamSynchronize(c->stream)); }
+  }
+  LAUNCH(k_iota, cdiv(n, 256), 256, 0, (int)n, c->id[0]);
+  // sinks (dummy zero sink if none: F:698-707)
+  std::vector<double> hb((size_t)SPH_MAX_SINKS * 11, 0.0);
+  const int M = SPH_MAX_SINKS;
+  const double* ssrc[7] = {sx, sy, sz, svx, svy, svz, sm};
+  for (int k = 0; k < 7; ++k) for (int s = 0; s < ns; ++s) hb[(size_t)k * M + s] = ssrc[k] ? ssrc[k][s] : 0.0;
+  for (int s = 0; s < ns; ++s) hb[(size_t)7 * M + s] = (srad && srad[s] == srad[s]) ? srad[s] : c->p.sink_radius;
+  c->n_sink = ns > 0 ? ns : 1;
+  CK(cudaMemcpyAsync(c->sink_buf, hb.data(), hb.size() * 8, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  c->h_sc->n_sink = c->n_sink; c->h_sc->n_removed = 0; c->h_sc->n_accreted = 0; c->h_sc->err = 0; c->h_sc->create_cand = ~0ull;
+  CK(cudaMemcpyAsync(c->sc, c->h_sc, sizeof(SimScalars), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return SPH_OK;
+}
+
+int sph_evaluate(sph_ctx* c, int32_t mask) {
+  if (!c) return SPH_ERR_ARG;
+  if (c->n <= 0) { c->err = "no particles uploaded"; return SPH_ERR_STATE; }
+  cudaSetDevice(c->device);
+  int r = evaluate(c, mask); if (r) return r;
+  CK(cudaMemcpyAsync(c->h_sc, c->sc, sizeof(SimScalars), cudaMemcpyDeviceToHost, c->stream));
+  if ((r = fetch_counters(c))) return r;
+  stage_collect(c, true);
+  CK(cudaGetLastError());
+  return check_device_error(c);
+}
+
+int sph_step(sph_ctx* c, double* dt, double* t, int64_t* n_out, int32_t* ns_out) {
+  if (!c || !dt || !t) return SPH_ERR_ARG;
+  if (c->n <= 0) { c->err = "no particles uploaded"; return SPH_ERR_STATE; }
+  cudaSetDevice(c->device);
+  c->h_sc->dt = *dt; c->h_sc->t = *t;
+  CK(cudaMemcpyAsync(c->sc, c->h_sc, 2 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  int r = step(c); if (r) return r;
+  if ((r = fetch_counters(c))) return r;
+  c->counts.h_iterations = (int64_t)c->h_ctr->h_iters;
+  stage_collect(c, true);
+  CK(cudaGetLastError());
+  *dt = c->h_sc->dt; *t = c->h_sc->t;
+  if (n_out) *n_out = c->n;
+  if (ns_out) *ns_out = c->n_sink;
+  return SPH_OK;
+}
+
+int sph_run_until(sph_ctx* c, double t_stop, int64_t max_steps, double* dt, double* t, int64_t* steps_out,
+                  int64_t* n_out, int32_t* ns_out) {
+  if (!c || !dt || !t) return SPH_ERR_ARG;
+  if (c->n <= 0) { c->err = "no particles uploaded"; return SPH_ERR_STATE; }
+  cudaSetDevice(c->device);
+  c->h_sc->dt = *dt; c->h_sc->t = *t;
+  CK(cudaMemcpyAsync(c->sc, c->h_sc, 2 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  int64_t steps = 0; int r = SPH_OK;
+  bool first = true;
+  while (c->h_sc->t < t_stop && (max_steps <= 0 || steps < max_steps) && c->n >= 2) {      // F:879
+    if ((r = step(c))) break;
+    stage_collect(c, first); first = false;
+    ++steps;
+  }
+  if (!r) { r = fetch_counters(c); c->counts.h_iterations = (int64_t)c->h_ctr->h_iters; }
+  *dt = c->h_sc->dt; *t = c->h_sc->t;
+  if (steps_out) *steps_out = steps;
+  if (n_out) *n_out = c->n;
+  if (ns_out) *ns_out = c->n_sink;
+  return r;
+}
+
+int sph_sizes(sph_ctx* c, int64_t* n, int32_t* ns) {
+  if (!c) return SPH_ERR_ARG;
+  if (n) *n = c->n;
+  if (ns) *ns = c->n_sink;
+  return SPH_OK;
+}
+
+int sph_download(sph_ctx* c, double* x, double* y, double* z, double* vx, double* vy, double* vz,
+                 double* u, double* m, double* alpha, double* h,
+                 double* sx, double* sy, double* sz, double* svx, double* svy, double* svz, double* sm, double* srad) {
+  if (!c) return SPH_ERR_ARG;
+  cudaSetDevice(c->device);
+  int r;
+  if (c->n > 0) {
+    if ((r = compute_pos(c))) return r;
+    double* dst[10] = {x, y, z, vx, vy, vz, u, m, alpha, h};
+    for (int f = 0; f < 10; ++f) if ((r = fetch_ordered(c, c->st[c->cur][f], dst[f]))) return r;
+  }
+  double* sd[8] = {sx, sy, sz, svx, svy, svz, sm, srad};
+  const double* ss[8] = {c->S.x, c->S.y, c->S.z, c->S.vx, c->S.vy, c->S.vz, c->S.m, c->S.radius};
+  for (int k = 0; k < 8; ++k) if ((r = fetch_sink(c, ss[k], sd[k]))) return r;
+  return SPH_OK;
+}
+
+int sph_download_diag(sph_ctx* c, double* rho, double* omega, double* pressure, double* sound,
+                      double* ax, double* ay, double* az, double* udot, double* alphadot,
+                      double* sax, double* say, double* saz) {
+  if (!c) return SPH_ERR_ARG;
+  if (c->n <= 0) { c->err = "no particles"; return SPH_ERR_STATE; }
+  cudaSetDevice(c->device);
+  int r; if ((r = compute_pos(c))) return r;
+  const double* src[9] = {c->rho, c->omega, c->prs, c->cs, c->ax, c->ay, c->az, c->udot, c->adot};
+  double* dst[9] = {rho, omega, pressure, sound, ax, ay, az, udot, alphadot};
+  for (int f = 0; f < 9; ++f) if ((r = fetch_ordered(c, src[f], dst[f]))) return r;
+  if ((r = fetch_sink(c, c->S.ax, sax))) return r;
+  if ((r = fetch_sink(c, c->S.ay, say))) return r;
+  if ((r = fetch_sink(c, c->S.az, saz))) return r;
+  return SPH_OK;
+}
+
+int sph_download_tree(sph_ctx* c, int32_t* order, uint64_t* key, int32_t* level,
+                      double* cx, double* cy, double* cz, double* size) {
+  if (!c) return SPH_ERR_ARG;
+  if (!c->tree_valid) { c->err = "no tree"; return SPH_ERR_STATE; }
+  cudaSetDevice(c->device);
+  const int n = (int)c->n, T = 256;
+  int r; if ((r = compute_pos(c))) return r;
+  if (order) { CK(cudaMemcpy(order, c->pos, (size_t)n * 4, cudaMemcpyDeviceToHost)); }
+  if (key) {
+    LAUNCH(k_scatter_u64, cdiv(n, T), T, 0, n, c->pos, (const unsigned long long*)c->key[0], (unsigned long long*)c->stage_d);
+    CK(cudaMemcpyAsync(key, c->stage_d, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream));
+  }
+  std::vector<int> lev(n);
+  if (level || size) {
+    LAUNCH(k_scatter_i, cdiv(n, T), T, 0, n, c->pos, c->level, (int*)c->stage_d);
+    CK(cudaMemcpyAsync(lev.data(), c->stage_d, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream));
+    if (level) std::memcpy(level, lev.data(), (size_t)n * 4);
+  }
+  if ((r = fetch_ordered(c, c->lcx, cx))) return r;
+  if ((r = fetch_ordered(c, c->lcy, cy))) return r;
+  if ((r = fetch_ordered(c, c->lcz, cz))) return r;
+  if (size) {
+    RootBox rb; CK(cudaMemcpy(&rb, c->root, sizeof(rb), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; ++i) { double s = rb.size; for (int q = 0; q < lev[i]; ++q) s *= 0.5; size[i] = s; }
+  }
+  return SPH_OK;
+}
+
+int sph_download_neighbours(sph_ctx* c, int32_t* count, uint64_t* hash, int64_t* offsets, int32_t* list, int64_t list_cap) {
+  if (!c) return SPH_ERR_ARG;
+  if (!c->tree_valid) { c->err = "no tree"; return SPH_ERR_STATE; }
+  cudaSetDevice(c->device);
+  const int n = (int)c->n, T = 256, W = 8;
+  int r; if ((r = compute_pos(c))) return r;
+  int* d_count = nullptr; unsigned long long* d_hash = nullptr; long long* d_off = nullptr; int* d_list = nullptr;
+  DA(d_count, n); DA(d_hash, n);
+  size_t smem = (size_t)W * 4 * WALK_TILE * 8 + (size_t)W * WALK_TILE * 4 + (size_t)W * (WALK_STACK + WALK_CQ) * 4;
+  LAUNCH(k_neighbours, walk_grid(c, W), W * 32, smem, c->n_groups, c->groups, dens_arrays(c), c->pos, c->bvh, c->bi, d_count, d_hash, nullptr, nullptr);
+  std::vector<int> cnt_sorted(n), pos(n), cnt_num(n);
+  std::vector<unsigned long long> hash_sorted(n);
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaMemcpy(cnt_sorted.data(), d_count, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(hash_sorted.data(), d_hash, (size_t)n * 8, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(pos.data(), c->pos, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < n; ++i) { cnt_num[pos[i]] = cnt_sorted[i]; if (hash) hash[pos[i]] = hash_sorted[i]; }
+  if (count) std::memcpy(count, cnt_num.data(), (size_t)n * 4);
+  std::vector<long long> off_num(n + 1, 0);
+  for (int i = 0; i < n; ++i) off_num[i + 1] = off_num[i] + cnt_num[i];
+  if (offsets) for (int i = 0; i <= n; ++i) offsets[i] = off_num[i];
+  int rc = SPH_OK;
+  if (list) {
+    const long long tot = off_num[n];
+    if (tot > list_cap) { c->err = "neighbour list capacity too small: need " + std::to_string(tot) + " have " + std::to_string((long long)list_cap); rc = SPH_ERR_ARG; }
+    else {
+      std::vector<long long> off_sorted(n);
+      for (int i = 0; i < n; ++i) off_sorted[i] = off_num[pos[i]];
+      DA(d_off, n); DA(d_list, std::max<long long>(tot, 1));
+      CK(cudaMemcpyAsync(d_off, off_sorted.data(), (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+      LAUNCH(k_neighbours, walk_grid(c, W), W * 32, smem, c->n_groups, c->groups, dens_arrays(c), c->pos, c->bvh, c->bi, d_count, d_hash, d_off, d_list);
+      CK(cudaMemcpyAsync(list, d_list, (size_t)tot * 4, cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream));
+      for (int i = 0; i < n; ++i) std::sort(list + off_num[i], list + off_num[i + 1]);
+    }
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  cudaFree(d_count); cudaFree(d_hash); if (d_off) cudaFree(d_off); if (d_list) cudaFree(d_list);
+  return rc;
+}
+
+int sph_counters(sph_ctx* c, sph_counts* out) {
+  if (!c || !out) return SPH_ERR_ARG;
+  *out = c->counts;
+  return SPH_OK;
+}
+
+int sph_stage_times(sph_ctx* c, double* ms, int32_t n) {
+  if (!c || !ms) return SPH_ERR_ARG;
+  for (int i = 0; i < n && i < 16; ++i) ms[i] = i < ST_COUNT ? c->stage_ms[i] : 0.0;
+  return SPH_OK;
+}
+
+int64_t sph_launch_count(sph_ctx* c) { return c ? c->launches : 0; }
+int64_t sph_group_count(sph_ctx* c) { return c ? c->n_groups : 0; }
+
+int sph_timer_start(sph_ctx* c) {
+  if (!c) return SPH_ERR_ARG;
+  cudaSetDevice(c->device);
+  if (!c->tm0) { CK(cudaEventCreate(&c->tm0)); CK(cudaEventCreate(&c->tm1)); }
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaEventRecord(c->tm0, c->stream));
+  return SPH_OK;
+}
+
+int sph_timer_stop(sph_ctx* c, double* ms) {
+  if (!c || !ms || !c->tm0) return SPH_ERR_ARG;
+  cudaSetDevice(c->device);
+  CK(cudaEventRecord(c->tm1, c->stream));
+  CK(cudaEventSynchronize(c->tm1));
+  float f = 0.f; CK(cudaEventElapsedTime(&f, c->tm0, c->tm1));
+  *ms = f;
+  return SPH_OK;
+}
+
+int sph_fp64_peak(sph_ctx* c, double* tflops) {
+  if (!c || !tflops) return SPH_ERR_ARG;
+  cudaSetDevice(c->device);
+  int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+  double* out = nullptr; DA(out, 1);
+  const int iters = 1 << 14, blocks = sms * 8, threads = 256;
+  cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {
+    CK(cudaEventRecord(a, c->stream));
+    LAUNCH(k_fp64_peak, blocks, threads, 0, iters, 1.0000001, out);
+    CK(cudaEventRecord(b, c->stream));
+    CK(cudaEventSynchronize(b));
+    float ms = 0.f; CK(cudaEventElapsedTime(&ms, a, b));
+    const double fl = 2.0 * 8.0 * (double)iters * (double)blocks * threads;
+    best = std::max(best, fl / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(out);
+  *tflops = best;
+  return SPH_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,485 @@
+// sph_walk.cuh — neighbour walks: density(+Omega)+EOS, h Newton-Raphson, SPH pair forces, diagnostics.
+//
+// Replaces density_tree_search / get_density (SUMMER_SPH.f90:398-457 | Variable.f90:440-496),
+// get_pressure_and_sound_speed (F:459-468 | V:502-512), calc_smoothing (V:515-546) and
+// SPH_tree_search / get_SPH (F:295-395 | V:324-432).
+//
+// Membership is the reference's, bit for bit: j is a candidate of i iff the leaf box test
+//     all_k |x_i,k - c_leaf(j),k| < 2 h_j + size_leaf(j)/2          (F:443 | V:479)
+// passes (h_j = the value in the tree = at build time; F: the global smoothing), evaluated in FP64 with
+// the same operations.  HOW candidates are found is free: one warp owns a chunk of 32 Morton-adjacent
+// targets (lane = target), walks the implicit 8-ary BVH of chunk boxes with a shared-memory stack (8 child
+// boxes per popped node tested by 8 lanes, coalesced), stages the surviving source particles of each hit
+// chunk into a shared-memory tile, and every lane then runs the exact box test against the tile and the
+// kernel arithmetic for its own hits.  The pair force is evaluated in gather form:
+// each particle sums its own side, no atomics, every term equal to the reference's term.
+#pragma once
+#include "sph_common.cuh"
+
+struct BvhInfo { int nlev; int off[12]; int cnt[12]; };
+
+#define WALK_STACK 224      // node stack entries per warp
+#define WALK_CQ    96       // chunk queue entries per warp
+#define WALK_TILE  32       // staged source particles per warp
+
+struct WalkCounters { unsigned long long dens_cand, dens_contrib, sph_pairs, grav_opened, grav_accepted, h_iters; };
+
+__device__ __forceinline__ bool box_overlap(const float* alo, const float* ahi, const float* blo, const float* bhi) {
+  return alo[0] <= bhi[0] && ahi[0] >= blo[0] && alo[1] <= bhi[1] && ahi[1] >= blo[1] && alo[2] <= bhi[2] && ahi[2] >= blo[2];
+}
+
+// Generic warp walk. OP interface:
+//   static const bool SYMMETRIC;                     // also accept sources lying inside the group's reach box
+//   bool   source_filter(int j)                      // per-source prefilter against the group (lane = source)
+//   void   stage(int slot, int j)                    // copy source j into tile slot
+//   void   consume(int count)                        // all lanes process tile[0..count)
+template <class OP>
+__device__ void neighbour_walk(OP& op, const int2* __restrict__ groups, int chunk, const BvhBox* __restrict__ box, const BvhInfo& bi,
+                               unsigned* stack, unsigned* cq) {
+  const int lane = threadIdx.x & 31;
+  const BvhBox g = box[bi.off[0] + chunk];
+  int sn = 0, qn = 0, tn = 0;
+
+  auto hit = [&](const BvhBox& b) -> bool {
+    bool r = box_overlap(g.plo, g.phi, b.rlo, b.rhi);
+    if (OP::SYMMETRIC) r = r || box_overlap(g.rlo, g.rhi, b.plo, b.phi);
+    return r;
+  };
+  auto drain_chunks = [&]() {
+    for (int q = 0; q < qn; ++q) {
+      const int2 sg = groups[cq[q]];
+      const int j = sg.x + lane;
+      bool ok = (lane < sg.y) && op.source_filter(j);
+      unsigned bal = __ballot_sync(FULL_MASK, ok);
+      int cntc = __popc(bal);
+      if (cntc == 0) continue;
+      if (tn + cntc > WALK_TILE) { __syncwarp(); op.consume(tn); tn = 0; __syncwarp(); }
+      if (ok) op.stage(tn + __popc(bal & ((1u << lane) - 1u)), j);
+      tn += cntc;
+    }
+    qn = 0;
+  };
+
+  const int top = bi.nlev - 1;
+  {
+    bool ok = lane < bi.cnt[top];
+    if (ok) ok = hit(box[bi.off[top] + lane]);
+    unsigned bal = __ballot_sync(FULL_MASK, ok);
+    int pos = __popc(bal & ((1u << lane) - 1u));
+    if (ok) { if (top == 0) cq[pos] = (unsigned)lane; else stack[pos] = ((unsigned)top << 28) | (unsigned)lane; }
+    if (top == 0) qn = __popc(bal); else sn = __popc(bal);
+    __syncwarp();
+  }
+  while (sn > 0) {
+    const int npop = sn < 4 ? sn : 4;
+    const int grp = lane >> 3;
+    bool valid = grp < npop;
+    unsigned e = valid ? stack[sn - 1 - grp] : 0u;
+    __syncwarp();
+    sn -= npop;
+    const int lev = (int)(e >> 28), idx = (int)(e & 0x0fffffffu);
+    const int clev = lev - 1;
+    const int child = idx * SPH_BVH_FAN + (lane & 7);
+    bool ok = valid && child < bi.cnt[clev > 0 ? clev : 0];
+    if (ok) ok = hit(box[bi.off[clev] + child]);
+    bool ok0 = ok && clev == 0, okn = ok && clev > 0;
+    unsigned b0 = __ballot_sync(FULL_MASK, ok0), bn = __ballot_sync(FULL_MASK, okn);
+    if (ok0) cq[qn + __popc(b0 & ((1u << lane) - 1u))] = (unsigned)child;
+    if (okn) stack[sn + __popc(bn & ((1u << lane) - 1u))] = ((unsigned)clev << 28) | (unsigned)child;
+    qn += __popc(b0); sn += __popc(bn);
+    __syncwarp();
+    if (qn > WALK_CQ - 32) { drain_chunks(); }
+  }
+  drain_chunks();
+  __syncwarp();
+  if (tn > 0) op.consume(tn);
+  __syncwarp();
+}
+
+// shared kernel-table lookup: returns table-space (w, dw) at q (<= 2 assumed), F:113-118
+__device__ __forceinline__ void table_lerp(const double* __restrict__ wt, const double* __restrict__ dwt,
+                                           int nq, double dq, double inv_dq, double q, double& w, double& dw) {
+  int i = (int)(q * inv_dq); i = i < nq - 1 ? i : nq - 1;
+  double a = (q - i * dq) * inv_dq;
+  double b = 1.0 - a;
+  w = b * wt[i] + a * wt[i + 1];
+  dw = b * dwt[i] + a * dwt[i + 1];
+}
+__device__ __forceinline__ double table_lerp1(const double* __restrict__ t, int nq, double dq, double inv_dq, double q) {
+  int i = (int)(q * inv_dq); i = i < nq - 1 ? i : nq - 1;
+  double a = (q - i * dq) * inv_dq;
+  return (1.0 - a) * t[i] + a * t[i + 1];
+}
+
+// ------------------------------------------------------------------------------------------------------
+// density (+ Omega) operator, also used by the h iteration
+// ------------------------------------------------------------------------------------------------------
+struct DensityArrays {
+  const double *x, *y, *z, *m, *lcx, *lcy, *lcz, *reach;
+};
+
+struct DensityOp {
+  static const bool SYMMETRIC = false;
+  // tile (per warp, shared memory): 8 arrays of WALK_TILE doubles
+  double *sx, *sy, *sz, *sm, *scx, *scy, *scz, *sR;
+  const DensityArrays& A;
+  const double *wt, *dwt;            // shared-memory tables
+  int nq; double dq, inv_dq;
+  float gplo[3], gphi[3];            // group position box (for the per-source prefilter)
+  // lane state
+  double xi, yi, zi, inv_h;
+  bool active;
+  double accW, accB;                 // sum m_j w(q), sum m_j r dw(q)
+  unsigned cand, contrib;
+
+  __device__ DensityOp(const DensityArrays& a) : A(a) {}
+
+  __device__ __forceinline__ bool source_filter(int j) const {
+    double R = A.reach[j];
+    if (!(R > 0.0)) return false;
+    double cx = A.lcx[j], cy = A.lcy[j], cz = A.lcz[j];
+    return (cx - R <= (double)gphi[0]) && (cx + R >= (double)gplo[0]) &&
+           (cy - R <= (double)gphi[1]) && (cy + R >= (double)gplo[1]) &&
+           (cz - R <= (double)gphi[2]) && (cz + R >= (double)gplo[2]);
+  }
+  __device__ __forceinline__ void stage(int s, int j) {
+    sx[s] = A.x[j]; sy[s] = A.y[j]; sz[s] = A.z[j]; sm[s] = A.m[j];
+    scx[s] = A.lcx[j]; scy[s] = A.lcy[j]; scz[s] = A.lcz[j]; sR[s] = A.reach[j];
+  }
+  __device__ __forceinline__ void consume(int count) {
+    unsigned mask = 0;
+    if (active) {
+      for (int k = 0; k < count; ++k) {
+        double R = sR[k];
+        bool in = (fabs(xi - scx[k]) < R) && (fabs(yi - scy[k]) < R) && (fabs(zi - scz[k]) < R);   // F:443 | V:479
+        mask |= (in ? 1u : 0u) << k;
+      }
+    }
+    cand += __popc(mask);
+    while (mask) {
+      int k = __ffs(mask) - 1; mask &= mask - 1;
+      double dx = xi - sx[k], dy = yi - sy[k], dz = zi - sz[k];
+      double r = sqrt(dx * dx + dy * dy + dz * dz);
+      double q = r * inv_h;
+      if (q <= 2.0) {
+        double w, dw; table_lerp(wt, dwt, nq, dq, inv_dq, q, w, dw);
+        double mj = sm[k];
+        accW += mj * w;
+        accB += mj * (r * dw);
+        ++contrib;
+      }
+    }
+  }
+};
+
+// dynamic shared memory layout: [tables: 2*(nq+1) doubles][per warp: tile 8*WALK_TILE doubles][per warp: stack+cq]
+template <bool HITER>
+__global__ void __launch_bounds__(512, 1)
+k_density(int n_groups, const int2* __restrict__ groups, DevParams P, DensityArrays A, const BvhBox* __restrict__ box, BvhInfo bi,
+          const double* __restrict__ g_wt, const double* __restrict__ g_dwt,
+          const double* __restrict__ u, double* __restrict__ h,
+          double* __restrict__ rho, double* __restrict__ omega, double* __restrict__ prs, double* __restrict__ cs,
+          double* __restrict__ por2, WalkCounters* ctr) {
+  extern __shared__ double smem[];
+  const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* wt = smem; double* dwt = smem + (P.nq + 1);
+  double* tiles = dwt + (P.nq + 1);
+  unsigned* ws = reinterpret_cast<unsigned*>(tiles + (size_t)nwarp * 8 * WALK_TILE);
+  for (int i = threadIdx.x; i <= P.nq; i += blockDim.x) { wt[i] = g_wt[i]; dwt[i] = g_dwt[i]; }
+  __syncthreads();
+  double* tile = tiles + (size_t)warp * 8 * WALK_TILE;
+  unsigned* stack = ws + (size_t)warp * (WALK_STACK + WALK_CQ);
+  unsigned* cq = stack + WALK_STACK;
+  const int nchunk = n_groups;
+  unsigned long long tot_cand = 0, tot_contrib = 0, tot_iter = 0;
+
+  for (int chunk = blockIdx.x * nwarp + warp; chunk < nchunk; chunk += gridDim.x * nwarp) {
+    const int2 tg = groups[chunk];
+    const int i = tg.x + lane;
+    const bool live = lane < tg.y;
+    DensityOp op(A);
+    op.sx = tile; op.sy = tile + WALK_TILE; op.sz = tile + 2 * WALK_TILE; op.sm = tile + 3 * WALK_TILE;
+    op.scx = tile + 4 * WALK_TILE; op.scy = tile + 5 * WALK_TILE; op.scz = tile + 6 * WALK_TILE; op.sR = tile + 7 * WALK_TILE;
+    op.wt = wt; op.dwt = dwt; op.nq = P.nq; op.dq = P.dq; op.inv_dq = P.inv_dq;
+    const BvhBox g = box[bi.off[0] + chunk];
+    for (int k = 0; k < 3; ++k) { op.gplo[k] = g.plo[k]; op.gphi[k] = g.phi[k]; }
+    op.xi = live ? A.x[i] : 0.0; op.yi = live ? A.y[i] : 0.0; op.zi = live ? A.z[i] : 0.0;
+    op.cand = 0; op.contrib = 0;
+    double hi = live ? (P.variable_h ? h[i] : P.h_fixed) : 1.0;
+    const double mi = live ? A.m[i] : 0.0;
+
+    if (!HITER) {
+      op.active = live; op.inv_h = 1.0 / hi; op.accW = 0.0; op.accB = 0.0;
+      neighbour_walk(op, groups, chunk, box, bi, stack, cq);
+      if (live) {
+        // W/(pi h^3), dW/(pi h^4): F:125-126 (global smoothing) | V:139-140
+        const double hn = P.variable_h ? hi : P.h_fixed;
+        const double n3 = P.pi_norm * ((hn * hn) * hn), n4 = P.pi_norm * ((hn * hn) * (hn * hn));
+        const double r = op.accW / n3;
+        double om = 1.0;
+        if (P.variable_h) {
+          // Omega = 1 + h/(3 rho) * sum m_j (3W - r dW)/h                                   V:455,487
+          const double s = (3.0 * op.accW / n3 - op.accB / n4) / hi;
+          om = 1.0 + (hi / (3.0 * r)) * s;
+        }
+        const double p = P.gm1 * u[i] * r;                               // F:465 | V:509
+        const double c = sqrt(P.gamma * p / r);                          // F:466 | V:510
+        rho[i] = r; omega[i] = om; prs[i] = p; cs[i] = c;
+        por2[i] = P.variable_h ? p / ((om * r) * r) : p / (r * r);       // V:413 | F:381
+      }
+      tot_cand += op.cand; tot_contrib += op.contrib;
+    } else {
+      // calc_smoothing V:515-546 for the 32 targets of this chunk; lanes iterate while growing by > conv
+      double r = live ? rho[i] : 1.0, om = live ? omega[i] : 1.0;
+      double old_len = hi;
+      bool iter = false;
+      if (live) {
+        const double e3 = P.eta / hi;
+        hi = hi * (1.0 + ((mi * ((e3 * e3) * e3) / r) - 1.0) / (3.0 * om));                   // V:527
+        if (hi < P.max_length && hi > P.lit_001) iter = (((hi - old_len) / old_len) > P.conv) && (hi < 10.0);   // V:528-529
+        else hi = old_len;                                                                   // V:541
+      }
+      while (__any_sync(FULL_MASK, iter)) {
+        op.active = iter; op.inv_h = 1.0 / hi; op.accW = 0.0; op.accB = 0.0;
+        if (iter) old_len = hi;
+        neighbour_walk(op, groups, chunk, box, bi, stack, cq);
+        if (iter) {
+          const double n3 = P.pi_norm * ((hi * hi) * hi), n4 = P.pi_norm * ((hi * hi) * (hi * hi));
+          r = op.accW / n3;
+          const double s = (3.0 * op.accW / n3 - op.accB / n4) / hi;
+          om = 1.0 + (hi / (3.0 * r)) * s;                                                   // V:535
+          const double e3 = P.eta / hi;
+          hi = hi * (1.0 + ((mi * ((e3 * e3) * e3)) / r - 1.0) / (3.0 * om));                 // V:538
+          ++tot_iter;
+          iter = (((hi - old_len) / old_len) > P.conv) && (hi < 10.0);
+        }
+      }
+      if (live) { h[i] = hi; rho[i] = r; omega[i] = om; }
+    }
+  }
+  if (!HITER) {
+    tot_cand = (unsigned long long)warp_sum_ll((long long)tot_cand);
+    tot_contrib = (unsigned long long)warp_sum_ll((long long)tot_contrib);
+    if (lane == 0) { atomicAdd(&ctr->dens_cand, tot_cand); atomicAdd(&ctr->dens_contrib, tot_contrib); }
+  } else {
+    tot_iter = (unsigned long long)warp_sum_ll((long long)tot_iter);
+    if (lane == 0) atomicAdd(&ctr->h_iters, tot_iter);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// SPH pair force operator (gather form)
+// ------------------------------------------------------------------------------------------------------
+struct ForceArrays {
+  const double *x, *y, *z, *vx, *vy, *vz, *m, *h, *rho, *c, *alpha, *por2, *lcx, *lcy, *lcz, *reach;
+  const int* id;
+};
+#define FORCE_FIELDS 17
+
+struct ForceOp {
+  static const bool SYMMETRIC = true;
+  double* t;             // tile: FORCE_FIELDS arrays of WALK_TILE doubles
+  int* tid;              // tile ids
+  const ForceArrays& A;
+  const double* dwt; int nq; double dq, inv_dq;
+  float gplo[3], gphi[3], grlo[3], grhi[3];
+  int variable_h; double h_fixed, pi_norm, lit_001;
+  // lane state
+  bool live;
+  double xi, yi, zi, vxi, vyi, vzi, hi, inv_hi, inv_n4i, rhoi, ci, alphai, por2i, cxi, cyi, czi, Ri;
+  int idi;
+  double ax, ay, az, ud, ad;
+  unsigned pairs;
+
+  __device__ ForceOp(const ForceArrays& a) : A(a) {}
+
+  __device__ __forceinline__ bool source_filter(int j) const {
+    double R = A.reach[j];
+    if (!(R > 0.0)) return false;
+    double cx = A.lcx[j], cy = A.lcy[j], cz = A.lcz[j];
+    bool a = (cx - R <= (double)gphi[0]) && (cx + R >= (double)gplo[0]) &&
+             (cy - R <= (double)gphi[1]) && (cy + R >= (double)gplo[1]) &&
+             (cz - R <= (double)gphi[2]) && (cz + R >= (double)gplo[2]);
+    if (a) return true;
+    double px = A.x[j], py = A.y[j], pz = A.z[j];
+    return px >= (double)grlo[0] && px <= (double)grhi[0] && py >= (double)grlo[1] && py <= (double)grhi[1] &&
+           pz >= (double)grlo[2] && pz <= (double)grhi[2];
+  }
+  __device__ __forceinline__ void stage(int s, int j) {
+    const double hj = variable_h ? A.h[j] : h_fixed;
+    t[0 * WALK_TILE + s] = A.x[j];  t[1 * WALK_TILE + s] = A.y[j];  t[2 * WALK_TILE + s] = A.z[j];
+    t[3 * WALK_TILE + s] = A.vx[j]; t[4 * WALK_TILE + s] = A.vy[j]; t[5 * WALK_TILE + s] = A.vz[j];
+    t[6 * WALK_TILE + s] = A.m[j];  t[7 * WALK_TILE + s] = hj;
+    t[8 * WALK_TILE + s] = 1.0 / (pi_norm * ((hj * hj) * (hj * hj)));
+    t[9 * WALK_TILE + s] = A.rho[j]; t[10 * WALK_TILE + s] = A.c[j]; t[11 * WALK_TILE + s] = A.alpha[j];
+    t[12 * WALK_TILE + s] = A.por2[j];
+    t[13 * WALK_TILE + s] = A.lcx[j]; t[14 * WALK_TILE + s] = A.lcy[j]; t[15 * WALK_TILE + s] = A.lcz[j];
+    t[16 * WALK_TILE + s] = A.reach[j];
+    tid[s] = A.id[j];
+  }
+  __device__ __forceinline__ void consume(int count) {
+    unsigned mask = 0;
+    if (live) {
+      for (int k = 0; k < count; ++k) {
+        const int idj = tid[k];
+        bool in;
+        if (idj < idi) {          // i is the higher-numbered `body`: is x_i inside Box(j)?   F:351-354 | V:380-383
+          const double R = t[16 * WALK_TILE + k];
+          in = (fabs(xi - t[13 * WALK_TILE + k]) < R) && (fabs(yi - t[14 * WALK_TILE + k]) < R) && (fabs(zi - t[15 * WALK_TILE + k]) < R);
+        } else if (idj > idi) {   // j is the `body` that visits i: is x_j inside Box(i)?
+          in = (Ri > 0.0) && (fabs(t[0 * WALK_TILE + k] - cxi) < Ri) && (fabs(t[1 * WALK_TILE + k] - cyi) < Ri) && (fabs(t[2 * WALK_TILE + k] - czi) < Ri);
+        } else in = false;
+        mask |= (in ? 1u : 0u) << k;
+      }
+    }
+    pairs += __popc(mask);
+    while (mask) {
+      const int k = __ffs(mask) - 1; mask &= mask - 1;
+      const double nx = xi - t[0 * WALK_TILE + k], ny = yi - t[1 * WALK_TILE + k], nz = zi - t[2 * WALK_TILE + k];   // F:356
+      const double wx = vxi - t[3 * WALK_TILE + k], wy = vyi - t[4 * WALK_TILE + k], wz = vzi - t[5 * WALK_TILE + k]; // F:358
+      const double r2 = nx * nx + ny * ny + nz * nz;
+      const double dr = sqrt(r2);
+      const double rv = wx * nx + wy * ny + wz * nz;
+      const double vdotr = rv >= 0.0 ? 0.0 : rv;                          // F:361
+      const double inv_dr = 1.0 / dr;                                     // dr == 0 -> NaN like F:363
+      const double mj = t[6 * WALK_TILE + k], hj = t[7 * WALK_TILE + k];
+      // kernel gradient magnitudes dW/dr at h_i and h_j                                   F:366 | V:395-396
+      double dWi = 0.0, dWj = 0.0;
+      {
+        const double q = dr * inv_hi;
+        if (q <= 2.0) dWi = table_lerp1(dwt, nq, dq, inv_dq, q) * inv_n4i;
+      }
+      if (variable_h) {
+        const double q = dr / hj;
+        if (q <= 2.0) dWj = table_lerp1(dwt, nq, dq, inv_dq, q) * t[8 * WALK_TILE + k];
+      } else dWj = dWi;
+      const double hbar = variable_h ? (hi + hj) / 2.0 : hi;              // V:402
+      const double nu = (hbar * vdotr) / (r2 + lit_001 * hbar * hbar);    // F:373 | V:405
+      const double cbar = 0.5 * (ci + t[10 * WALK_TILE + k]);
+      const double abar = 0.5 * (alphai + t[11 * WALK_TILE + k]);
+      const double visc = (-abar * cbar * nu + 2.0 * abar * nu * nu) / (0.5 * (rhoi + t[9 * WALK_TILE + k]));   // F:378 | V:410
+      const double por2j = t[12 * WALK_TILE + k];
+      const double rvn = rv * inv_dr;                                     // n_hat . v_ij
+      double scal, vdg;
+      if (variable_h) {
+        vdg = (dWi * rvn + dWj * rvn) / 2.0;                              // V:401
+        scal = (por2i * dWi + por2j * dWj) + visc * (dWi + dWj) / 2.0;    // V:413-414
+      } else {
+        vdg = dWi * rvn;                                                  // F:370
+        scal = ((por2i + por2j) + visc) * dWi;                            // F:381-382
+      }
+      const double f = mj * scal * inv_dr;
+      ax -= f * nx; ay -= f * ny; az -= f * nz;                           // F:383 (own side)
+      ud += mj * vdg * (por2i + 0.5 * visc);                              // F:387 | V:419-421
+      ad += mj * vdg;                                                     // F:390
+    }
+  }
+};
+
+__global__ void __launch_bounds__(512, 1)
+k_force(int n_groups, const int2* __restrict__ groups, DevParams P, ForceArrays A, const BvhBox* __restrict__ box, BvhInfo bi, const double* __restrict__ g_dwt,
+        double* __restrict__ ax, double* __restrict__ ay, double* __restrict__ az, double* __restrict__ udot,
+        double* __restrict__ adot, WalkCounters* ctr) {
+  extern __shared__ double smem[];
+  const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* dwt = smem;
+  double* tiles = dwt + (P.nq + 1) + ((P.nq + 1) & 1);
+  int* tids = reinterpret_cast<int*>(tiles + (size_t)nwarp * FORCE_FIELDS * WALK_TILE);
+  unsigned* ws = reinterpret_cast<unsigned*>(tids + (size_t)nwarp * WALK_TILE);
+  for (int i = threadIdx.x; i <= P.nq; i += blockDim.x) dwt[i] = g_dwt[i];
+  __syncthreads();
+  double* tile = tiles + (size_t)warp * FORCE_FIELDS * WALK_TILE;
+  unsigned* stack = ws + (size_t)warp * (WALK_STACK + WALK_CQ);
+  unsigned* cq = stack + WALK_STACK;
+  const int nchunk = n_groups;
+  unsigned long long tot_pairs = 0;
+  for (int chunk = blockIdx.x * nwarp + warp; chunk < nchunk; chunk += gridDim.x * nwarp) {
+    const int2 tg = groups[chunk];
+    const int i = tg.x + lane;
+    const bool live = lane < tg.y;
+    ForceOp op(A);
+    op.t = tile; op.tid = tids + warp * WALK_TILE;
+    op.dwt = dwt; op.nq = P.nq; op.dq = P.dq; op.inv_dq = P.inv_dq;
+    op.variable_h = P.variable_h; op.h_fixed = P.h_fixed; op.pi_norm = P.pi_norm; op.lit_001 = P.lit_001;
+    const BvhBox g = box[bi.off[0] + chunk];
+    for (int k = 0; k < 3; ++k) { op.gplo[k] = g.plo[k]; op.gphi[k] = g.phi[k]; op.grlo[k] = g.rlo[k]; op.grhi[k] = g.rhi[k]; }
+    op.live = live;
+    const int ii = live ? i : 0;
+    op.xi = A.x[ii]; op.yi = A.y[ii]; op.zi = A.z[ii]; op.vxi = A.vx[ii]; op.vyi = A.vy[ii]; op.vzi = A.vz[ii];
+    op.hi = P.variable_h ? A.h[ii] : P.h_fixed; op.inv_hi = 1.0 / op.hi;
+    op.inv_n4i = 1.0 / (P.pi_norm * ((op.hi * op.hi) * (op.hi * op.hi)));
+    op.rhoi = A.rho[ii]; op.ci = A.c[ii]; op.alphai = A.alpha[ii]; op.por2i = A.por2[ii];
+    op.cxi = A.lcx[ii]; op.cyi = A.lcy[ii]; op.czi = A.lcz[ii]; op.Ri = A.reach[ii]; op.idi = A.id[ii];
+    op.ax = op.ay = op.az = op.ud = op.ad = 0.0; op.pairs = 0;
+    neighbour_walk(op, groups, chunk, box, bi, stack, cq);
+    if (live) {
+      ax[i] += op.ax; ay[i] += op.ay; az[i] += op.az;
+      udot[i] += op.ud;
+      // alpha-rate clean-up F:316-318 | V:345-347
+      adot[i] = fmax(op.ad / op.rhoi, 0.0) + P.lit_015 * ((0.1 - op.alphai) * op.ci / op.hi);
+    }
+    tot_pairs += op.pairs;
+  }
+  tot_pairs = (unsigned long long)warp_sum_ll((long long)tot_pairs);
+  if (lane == 0) atomicAdd(&ctr->sph_pairs, tot_pairs);    // each unordered pair is seen from both sides
+}
+
+// ------------------------------------------------------------------------------------------------------
+// neighbour diagnostics: per-target candidate count + order-independent hash, optional CSR list
+// ------------------------------------------------------------------------------------------------------
+struct NgbOp {
+  static const bool SYMMETRIC = false;
+  double *scx, *scy, *scz, *sR; int* sid;
+  const DensityArrays& A; const int* id;
+  float gplo[3], gphi[3];
+  double xi, yi, zi; bool live;
+  unsigned count; unsigned long long hash;
+  int* out;              // CSR row start for this lane or nullptr
+  __device__ NgbOp(const DensityArrays& a) : A(a) {}
+  __device__ __forceinline__ bool source_filter(int j) const {
+    double R = A.reach[j];
+    if (!(R > 0.0)) return false;
+    double cx = A.lcx[j], cy = A.lcy[j], cz = A.lcz[j];
+    return (cx - R <= (double)gphi[0]) && (cx + R >= (double)gplo[0]) && (cy - R <= (double)gphi[1]) && (cy + R >= (double)gplo[1]) &&
+           (cz - R <= (double)gphi[2]) && (cz + R >= (double)gplo[2]);
+  }
+  __device__ __forceinline__ void stage(int s, int j) {
+    scx[s] = A.lcx[j]; scy[s] = A.lcy[j]; scz[s] = A.lcz[j]; sR[s] = A.reach[j]; sid[s] = id[j];
+  }
+  __device__ __forceinline__ void consume(int cnt) {
+    if (!live) return;
+    for (int k = 0; k < cnt; ++k) {
+      double R = sR[k];
+      bool in = (fabs(xi - scx[k]) < R) && (fabs(yi - scy[k]) < R) && (fabs(zi - scz[k]) < R);
+      if (in) { if (out) out[count] = sid[k]; ++count; hash += mix64((unsigned long long)sid[k]); }
+    }
+  }
+};
+
+__global__ void __launch_bounds__(256)
+k_neighbours(int n_groups, const int2* __restrict__ groups, DensityArrays A, const int* __restrict__ id, const BvhBox* __restrict__ box, BvhInfo bi,
+             int* __restrict__ count, unsigned long long* __restrict__ hash, const long long* __restrict__ offsets,
+             int* __restrict__ list) {
+  extern __shared__ double smem[];
+  const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* tile = smem + (size_t)warp * 4 * WALK_TILE;
+  int* sid = reinterpret_cast<int*>(smem + (size_t)nwarp * 4 * WALK_TILE) + warp * WALK_TILE;
+  unsigned* ws = reinterpret_cast<unsigned*>(reinterpret_cast<int*>(smem + (size_t)nwarp * 4 * WALK_TILE) + nwarp * WALK_TILE);
+  unsigned* stack = ws + (size_t)warp * (WALK_STACK + WALK_CQ);
+  unsigned* cq = stack + WALK_STACK;
+  const int nchunk = n_groups;
+  for (int chunk = blockIdx.x * nwarp + warp; chunk < nchunk; chunk += gridDim.x * nwarp) {
+    const int2 tg = groups[chunk];
+    const int i = tg.x + lane;
+    NgbOp op(A);
+    op.scx = tile; op.scy = tile + WALK_TILE; op.scz = tile + 2 * WALK_TILE; op.sR = tile + 3 * WALK_TILE; op.sid = sid; op.id = id;
+    const BvhBox g = box[bi.off[0] + chunk];
+    for (int k = 0; k < 3; ++k) { op.gplo[k] = g.plo[k]; op.gphi[k] = g.phi[k]; }
+    op.live = lane < tg.y;
+    op.xi = op.live ? A.x[i] : 0.0; op.yi = op.live ? A.y[i] : 0.0; op.zi = op.live ? A.z[i] : 0.0;
+    op.count = 0; op.hash = 0;
+    op.out = (list && op.live) ? list + offsets[i] : nullptr;
+    neighbour_walk(op, groups, chunk, box, bi, stack, cq);
+    if (op.live) { count[i] = (int)op.count; hash[i] = op.hash; }
+  }
+}

@@ -1,0 +1,206 @@
+"""ctypes binding of the C-ABI engine (include/sph_b200.h -> libsph_b200.so).
+
+This is the reference-facing call path a Python host uses; tests and bench go through it, so every
+number they report crosses the same `extern "C"` boundary a Fortran ISO_C_BINDING host would.
+No CPU fallback: a missing library or CUDA device raises.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+from ._abi import SphParams, SphCounts, EVAL_ALL, ERRORS
+from .state import Bodies, Sinks
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsph_b200.so")
+_LIB = None
+
+STAGES = ("keys", "sort", "tree", "density", "gravity", "sph", "integrate", "h_iter", "cull")
+
+
+class SphError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"sph_b200 error {code} ({ERRORS.get(code, '?')}): {msg}")
+        self.code = code
+
+
+def load_library(path=None):
+    """Load libsph_b200.so (built in-tree by summersph_b200.build). Fails loudly if it is missing."""
+    global _LIB
+    if _LIB is not None and path is None:
+        return _LIB
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise FileNotFoundError(f"{p} not found: build it with `python -m summersph_b200.build` "
+                                "(there is no CPU fallback for the SPH step)")
+    lib = C.CDLL(p)
+    vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+    lib.sph_last_error.restype = C.c_char_p
+    lib.sph_last_error.argtypes = [vp]
+    lib.sph_default_params.argtypes = [i32, C.POINTER(SphParams)]
+    lib.sph_create.argtypes = [C.POINTER(SphParams), i32, C.POINTER(vp)]
+    lib.sph_destroy.argtypes = [vp]
+    lib.sph_comm_unique_id.argtypes = [vp]
+    lib.sph_comm_init.argtypes = [vp, i32, i32, vp]
+    lib.sph_upload.argtypes = [vp, i64] + [vp] * 10 + [i32] + [vp] * 8
+    lib.sph_evaluate.argtypes = [vp, i32]
+    lib.sph_step.argtypes = [vp, C.POINTER(dbl), C.POINTER(dbl), C.POINTER(i64), C.POINTER(i32)]
+    lib.sph_run_until.argtypes = [vp, dbl, i64, C.POINTER(dbl), C.POINTER(dbl), C.POINTER(i64), C.POINTER(i64), C.POINTER(i32)]
+    lib.sph_sizes.argtypes = [vp, C.POINTER(i64), C.POINTER(i32)]
+    lib.sph_download.argtypes = [vp] + [vp] * 18
+    lib.sph_download_diag.argtypes = [vp] + [vp] * 12
+    lib.sph_download_tree.argtypes = [vp] + [vp] * 7
+    lib.sph_download_neighbours.argtypes = [vp, vp, vp, vp, vp, i64]
+    lib.sph_counters.argtypes = [vp, C.POINTER(SphCounts)]
+    lib.sph_stage_times.argtypes = [vp, vp, i32]
+    lib.sph_launch_count.argtypes = [vp]
+    lib.sph_launch_count.restype = i64
+    lib.sph_group_count.argtypes = [vp]
+    lib.sph_group_count.restype = i64
+    lib.sph_timer_start.argtypes = [vp]
+    lib.sph_timer_stop.argtypes = [vp, C.POINTER(dbl)]
+    lib.sph_fp64_peak.argtypes = [vp, C.POINTER(dbl)]
+    if path is None:
+        _LIB = lib
+    return lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Engine:
+    """One engine context on one CUDA device (`sph_ctx`)."""
+
+    def __init__(self, params: SphParams, device=0):
+        self._l = load_library()
+        self.params = params
+        self._c = C.c_void_p()
+        rc = self._l.sph_create(C.byref(params), int(device), C.byref(self._c))
+        if rc != 0:
+            msg = self._l.sph_last_error(None)
+            self._c = None
+            raise SphError(rc, (msg or b"").decode())
+
+    def close(self):
+        if getattr(self, "_c", None):
+            self._l.sph_destroy(self._c)
+            self._c = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise SphError(rc, (self._l.sph_last_error(self._c) or b"").decode())
+
+    # -- multi-GPU ---------------------------------------------------------------------------------
+    def unique_id(self):
+        buf = (C.c_char * 128)()
+        rc = self._l.sph_comm_unique_id(buf)
+        if rc != 0:
+            raise SphError(rc, (self._l.sph_last_error(None) or b"").decode())
+        return bytes(buf)
+
+    def comm_init(self, rank, n_ranks, unique_id: bytes):
+        buf = (C.c_char * 128).from_buffer_copy(unique_id)
+        self._ck(self._l.sph_comm_init(self._c, int(rank), int(n_ranks), buf))
+
+    # -- state -------------------------------------------------------------------------------------
+    def upload(self, b: Bodies, s: Sinks):
+        rad = s.radius
+        self._ck(self._l.sph_upload(self._c, len(b), _p(b.x), _p(b.y), _p(b.z), _p(b.vx), _p(b.vy), _p(b.vz),
+                                    _p(b.u), _p(b.m), _p(b.alpha), _p(b.h), len(s),
+                                    _p(s.x), _p(s.y), _p(s.z), _p(s.vx), _p(s.vy), _p(s.vz), _p(s.m), _p(rad)))
+
+    def sizes(self):
+        n, ns = C.c_int64(), C.c_int32()
+        self._ck(self._l.sph_sizes(self._c, C.byref(n), C.byref(ns)))
+        return n.value, ns.value
+
+    def evaluate(self, mask=EVAL_ALL):
+        self._ck(self._l.sph_evaluate(self._c, int(mask)))
+
+    def step(self, dt, t):
+        cdt, ct, n, ns = C.c_double(dt), C.c_double(t), C.c_int64(), C.c_int32()
+        self._ck(self._l.sph_step(self._c, C.byref(cdt), C.byref(ct), C.byref(n), C.byref(ns)))
+        return cdt.value, ct.value
+
+    def run_until(self, t_stop, dt, t, max_steps=0):
+        cdt, ct, steps, n, ns = C.c_double(dt), C.c_double(t), C.c_int64(), C.c_int64(), C.c_int32()
+        self._ck(self._l.sph_run_until(self._c, float(t_stop), int(max_steps), C.byref(cdt), C.byref(ct),
+                                       C.byref(steps), C.byref(n), C.byref(ns)))
+        return cdt.value, ct.value, steps.value
+
+    def download(self, into=None):
+        n, ns = self.sizes()
+        b, s = (into if into is not None else (Bodies.empty(n), Sinks.empty(ns)))
+        self._ck(self._l.sph_download(self._c, _p(b.x), _p(b.y), _p(b.z), _p(b.vx), _p(b.vy), _p(b.vz), _p(b.u), _p(b.m),
+                                      _p(b.alpha), _p(b.h), _p(s.x), _p(s.y), _p(s.z), _p(s.vx), _p(s.vy), _p(s.vz),
+                                      _p(s.m), _p(s.radius)))
+        return b, s
+
+    def diag(self):
+        n, ns = self.sizes()
+        keys = ("rho", "omega", "P", "c", "ax", "ay", "az", "udot", "alphadot")
+        d = {k: np.zeros(n) for k in keys}
+        d.update({k: np.zeros(ns) for k in ("sink_ax", "sink_ay", "sink_az")})
+        self._ck(self._l.sph_download_diag(self._c, *[_p(d[k]) for k in keys + ("sink_ax", "sink_ay", "sink_az")]))
+        return d
+
+    def tree(self):
+        n, _ = self.sizes()
+        t = {"order": np.zeros(n, np.int32), "key": np.zeros(n, np.uint64), "level": np.zeros(n, np.int32),
+             "cx": np.zeros(n), "cy": np.zeros(n), "cz": np.zeros(n), "size": np.zeros(n)}
+        self._ck(self._l.sph_download_tree(self._c, *[_p(t[k]) for k in ("order", "key", "level", "cx", "cy", "cz", "size")]))
+        return t
+
+    def neighbours(self, with_list=True):
+        n, _ = self.sizes()
+        count = np.zeros(n, np.int32); hsh = np.zeros(n, np.uint64); off = np.zeros(n + 1, np.int64)
+        self._ck(self._l.sph_download_neighbours(self._c, _p(count), _p(hsh), _p(off), None, 0))
+        lst = None
+        if with_list:
+            tot = int(off[-1])
+            lst = np.zeros(max(tot, 1), np.int32)
+            self._ck(self._l.sph_download_neighbours(self._c, _p(count), _p(hsh), _p(off), _p(lst), tot))
+            lst = lst[:tot]
+        return count, hsh, off, lst
+
+    def counters(self):
+        c = SphCounts()
+        self._ck(self._l.sph_counters(self._c, C.byref(c)))
+        return c.as_dict()
+
+    def stage_times(self):
+        ms = np.zeros(16)
+        self._ck(self._l.sph_stage_times(self._c, _p(ms), 16))
+        return dict(zip(STAGES, ms[:len(STAGES)].tolist()))
+
+    def launch_count(self):
+        return int(self._l.sph_launch_count(self._c))
+
+    def timer_start(self):
+        self._ck(self._l.sph_timer_start(self._c))
+
+    def timer_stop(self):
+        ms = C.c_double()
+        self._ck(self._l.sph_timer_stop(self._c, C.byref(ms)))
+        return ms.value
+
+    def fp64_peak(self):
+        v = C.c_double()
+        self._ck(self._l.sph_fp64_peak(self._c, C.byref(v)))
+        return v.value
+
+    def group_count(self):
+        return int(self._l.sph_group_count(self._c))
