@@ -1,0 +1,131 @@
+// run_sph.cpp — C++ twin of the reference's `program run_sph` + `simulate` shell
+// (SUMMER_SPH.f90:863-955 | "SUMMER_SPH - Variable.f90":1076-1191), driving the CUDA engine through the
+// C-ABI of include/sph_b200.h.  It exists because this image has no Fortran compiler; the Fortran host
+// host/run_sph_b200.f90 binds the same entry points with ISO_C_BINDING.
+//
+//   run_sph [--variable] [--params parameters.txt] [--end-time T] [--max-steps N] [--save-dir DIR] ics.txt
+//
+// Surface kept from the reference: header + whitespace rows, 8 columns read in fixed-h mode (alpha := 0),
+// 10 in variable-h mode, u == 0 marks a sink, dummy sink if none, save<k>.txt cadence t > k*end_time/1000,
+// per-step "SPH Particles: N dt : dt time : t" line, loop ends at the first step with t >= end_time.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <fstream>
+#include <sstream>
+#include <sys/stat.h>
+
+#include "../include/sph_b200.h"
+
+struct Table { std::vector<double> c[10]; std::vector<double> s[8]; };
+
+static bool read_data_from_file(const std::string& fn, const sph_params& p, Table& t) {    // F:594-716
+  std::ifstream f(fn);
+  if (!f) { std::fprintf(stderr, " Error opening file: %s\n", fn.c_str()); return false; }
+  std::string line;
+  std::getline(f, line);                                                                   // header, F:617
+  const bool variable = p.mode & SPH_MODE_VARIABLE_H;
+  size_t row = 0;
+  while (std::getline(f, line)) {
+    std::istringstream is(line);
+    double v[10]; int k = 0;
+    while (k < 10 && (is >> v[k])) ++k;
+    if (k == 0) break;
+    ++row;
+    if (k < 8) { std::fprintf(stderr, " Error reading line %zu\n", row); return false; }
+    if (v[6] == 0.0) {                                                                     // sink, F:659
+      const double sv[8] = {v[0], v[1], v[2], v[3], v[4], v[5], v[7], p.sink_radius};
+      for (int q = 0; q < 8; ++q) t.s[q].push_back(sv[q]);
+    } else {
+      if (variable && k < 10) { std::fprintf(stderr, " Error reading line %zu\n", row); return false; }
+      for (int q = 0; q < 8; ++q) t.c[q].push_back(v[q]);
+      t.c[8].push_back(variable ? v[8] : 0.0);                                             // F:681
+      t.c[9].push_back(variable ? v[9] : p.h_fixed);
+    }
+  }
+  if (row == 0) { std::fprintf(stderr, " No data found in file: %s\n", fn.c_str()); return false; }
+  std::printf(" Successfully read %zu bodies and %zu sinks from %s.\n", t.c[0].size(), t.s[0].empty() ? (size_t)1 : t.s[0].size(), fn.c_str());
+  return true;
+}
+
+static bool read_params_from_file(const std::string& fn, sph_params& p) {                  // V:854-919
+  std::ifstream f(fn);
+  if (!f) { std::fprintf(stderr, " Error opening file: %s\n", fn.c_str()); return false; }
+  std::string line; std::getline(f, line);
+  bool any = false;
+  while (std::getline(f, line)) {
+    std::istringstream is(line);
+    double b, th, g, e, cv, ml, ts, et; double md;
+    if (!(is >> b >> md >> th >> g >> e >> cv >> ml >> ts >> et)) break;
+    p.bounding_size = b; p.max_depth = (int)md; p.theta = th; p.gamma = g; p.eta = e;
+    p.convergence_criteria = cv; p.max_length = ml; p.timestep_scale = ts; p.end_time = et;
+    any = true;
+  }
+  if (any) std::printf(" Successfully read parameters from%s.\n", fn.c_str());
+  return any;
+}
+
+static bool make_save(sph_ctx* ctx, const sph_params& p, int number, const std::string& dir) {   // F:719-738
+  int64_t n; int32_t ns; sph_sizes(ctx, &n, &ns);
+  std::vector<double> c[10], s[8];
+  for (auto& v : c) v.resize(n);
+  for (auto& v : s) v.resize(ns);
+  if (sph_download(ctx, c[0].data(), c[1].data(), c[2].data(), c[3].data(), c[4].data(), c[5].data(), c[6].data(), c[7].data(),
+                   c[8].data(), c[9].data(), s[0].data(), s[1].data(), s[2].data(), s[3].data(), s[4].data(), s[5].data(),
+                   s[6].data(), s[7].data())) return false;
+  const std::string fn = dir + "/save" + std::to_string(number) + ".txt";
+  struct stat st;
+  if (stat(fn.c_str(), &st) == 0) { std::fprintf(stderr, "%s exists (status=\"new\")\n", fn.c_str()); return false; }   // F:728
+  FILE* f = std::fopen(fn.c_str(), "w");
+  if (!f) return false;
+  const bool variable = p.mode & SPH_MODE_VARIABLE_H;
+  std::fprintf(f, " x  y  z  vx  vy vz energy mass  alpha  %s\n", variable ? "smoothing" : "");
+  const int nc = variable ? 10 : 9;
+  for (int64_t i = 0; i < n; ++i) { for (int q = 0; q < nc; ++q) std::fprintf(f, "%25.17E", c[q][i]); std::fputc('\n', f); }
+  for (int i = 0; i < ns; ++i)
+    std::fprintf(f, "%25.17E%25.17E%25.17E%25.17E%25.17E%25.17E%25.17E%25.17E\n", s[0][i], s[1][i], s[2][i], s[3][i], s[4][i], s[5][i], 0.0, s[6][i]);
+  std::fclose(f);
+  return true;
+}
+
+int main(int argc, char** argv) {
+  int mode = SPH_MODE_FIXED_H; std::string params_file, save_dir, ics; double end_override = -1; long max_steps = -1;
+  for (int i = 1; i < argc; ++i) {
+    std::string a = argv[i];
+    if (a == "--variable") mode = SPH_MODE_VARIABLE_H;
+    else if (a == "--params" && i + 1 < argc) { params_file = argv[++i]; mode = SPH_MODE_VARIABLE_H; }
+    else if (a == "--end-time" && i + 1 < argc) end_override = std::atof(argv[++i]);
+    else if (a == "--max-steps" && i + 1 < argc) max_steps = std::atol(argv[++i]);
+    else if (a == "--save-dir" && i + 1 < argc) save_dir = argv[++i];
+    else ics = a;
+  }
+  if (ics.empty()) { std::fprintf(stderr, "usage: run_sph [--variable] [--params parameters.txt] [--end-time T] [--max-steps N] [--save-dir DIR] ics.txt\n"); return 2; }
+  sph_params p; sph_default_params(mode, &p);
+  if (!params_file.empty() && !read_params_from_file(params_file, p)) return 1;
+  if (end_override >= 0) p.end_time = end_override;
+  Table t;
+  if (!read_data_from_file(ics, p, t)) return 1;
+  sph_ctx* ctx = nullptr;
+  if (sph_create(&p, 0, &ctx)) { std::fprintf(stderr, "sph_create: %s\n", sph_last_error(nullptr)); return 1; }
+  if (sph_upload(ctx, (int64_t)t.c[0].size(), t.c[0].data(), t.c[1].data(), t.c[2].data(), t.c[3].data(), t.c[4].data(), t.c[5].data(),
+                 t.c[6].data(), t.c[7].data(), t.c[8].data(), t.c[9].data(), (int32_t)t.s[0].size(), t.s[0].data(), t.s[1].data(),
+                 t.s[2].data(), t.s[3].data(), t.s[4].data(), t.s[5].data(), t.s[6].data(), t.s[7].data())) {
+    std::fprintf(stderr, "sph_upload: %s\n", sph_last_error(ctx)); return 1;
+  }
+  double tt = 0.0, dt = 1.0e-2;                                                            // F:872,875
+  int t_test = 0; long steps = 0; int64_t n = (int64_t)t.c[0].size(); int32_t ns = 0;
+  while (tt < p.end_time) {                                                                // F:879
+    if (!save_dir.empty() && tt > t_test * p.end_time / 1000.0) {                          // F:881
+      if (!make_save(ctx, p, t_test, save_dir)) return 1;
+      ++t_test;
+    }
+    std::printf(" SPH Particles: %lld dt :   %.17g time :    %.17g\n", (long long)n, dt, tt);   // F:891
+    std::fflush(stdout);
+    if (sph_step(ctx, &dt, &tt, &n, &ns)) { std::fprintf(stderr, "sph_step: %s\n", sph_last_error(ctx)); return 1; }
+    if (max_steps >= 0 && ++steps >= max_steps) break;
+  }
+  sph_destroy(ctx);
+  return 0;
+}

@@ -1,6 +1,6 @@
 """ctypes mirror of include/sph_b200.h (struct layouts and constants only; no library loading).
 
-Shared by the engine binding (engine.py) and by the test-only oracle wrapper (oracle/oracle.py).
+Shared by the engine binding (engine.py) and by test infrastructure.
 """
 import ctypes as C
 

@@ -1,0 +1,43 @@
+"""Host-side `simulate` shell (SUMMER_SPH.f90:863-930 | "SUMMER_SPH - Variable.f90":1076-1164).
+
+The loop shell, save cadence and per-step print stay on the host exactly as in the reference; the loop
+body (F:886-928 | V:1120-1162) is one call into the CUDA engine through the C-ABI (`sph_step`).
+"""
+from ._abi import SphParams
+from .state import Bodies, Sinks
+from .io import make_save
+
+
+def simulate(bodies: Bodies, sinks: Sinks, params: SphParams, engine=None, save_dir=None, max_steps=None,
+             log=print, device=0):
+    """Run until t >= params.end_time (no final-step clipping, no final save: F:879).
+
+    `engine` defaults to a new CUDA `Engine` (there is no CPU fallback). Saves `save<k>.txt` into
+    `save_dir` when `t > k*end_time/1000` (F:874,881; the reference reads t_list(0) out of bounds on
+    the first pass, here t_list(0) := 0 so save0 is written at the first step with t > 0).
+    Returns (bodies, sinks, t, dt, steps)."""
+    own = engine is None
+    if own:
+        from .engine import Engine
+        engine = Engine(params, device=device)
+    try:
+        engine.upload(bodies, sinks)
+        t, dt = 0.0, 1.0e-2                                                  # F:872,875
+        end_time = params.end_time
+        t_test, steps = 0, 0
+        while t < end_time:                                                  # F:879
+            if save_dir is not None and t > t_test * end_time / 1000.0:      # F:881
+                b, s = engine.download()
+                make_save(b, s, t_test, params, save_dir)
+                t_test += 1
+            n, _ = engine.sizes()
+            log(f" SPH Particles: {n} dt : {dt!r} time :  {t!r}")            # F:891
+            dt, t = engine.step(dt, t)
+            steps += 1
+            if max_steps is not None and steps >= max_steps:
+                break
+        b, s = engine.download()
+        return b, s, t, dt, steps
+    finally:
+        if own:
+            engine.close()

@@ -1,0 +1,289 @@
+"""Parity of the CUDA engine (through the C-ABI) against the CPU oracle on the same seeded inputs.
+
+Bit-exact: Morton (DFS leaf) order, leaf levels and cells, neighbour sets, dt ladder, interaction counts.
+FP64 fields: 1e-10 relative (north_star), scale = max(|value|, field RMS) — SURVEY.md §8(c)."""
+import numpy as np
+import pytest
+
+from summersph_b200 import (default_params, MODE_FIXED_H, MODE_VARIABLE_H, FLAG_SOFT_USES_HI, ics, Bodies, Sinks,
+                            EVAL_ALL, EVAL_TREE, EVAL_DENSITY, EVAL_GRAVITY, EVAL_SINKS, EVAL_SPH)
+from summersph_b200.state import GAS_FIELDS
+from conftest import relerr
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def E(built_engine):
+    from summersph_b200.engine import Engine
+    return Engine
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle.oracle import Oracle
+    return Oracle
+
+
+def compare_eval(o, e, check_ngb=True, tol=TOL):
+    to, te = o.tree(), e.tree()
+    assert np.array_equal(to["order"], te["order"])
+    assert np.array_equal(to["level"], te["level"])
+    for k in ("cx", "cy", "cz", "size"):
+        assert np.array_equal(to[k], te[k]), k
+    if check_ngb:
+        co, ho, _, _ = o.neighbours(with_list=False); ce, he, _, _ = e.neighbours(with_list=False)
+        assert np.array_equal(co, ce) and np.array_equal(ho, he)
+    do, de = o.diag(), e.diag()
+    for k in do:
+        assert relerr(de[k], do[k]) < tol, f"{k}: {relerr(de[k], do[k]):.3e}"
+    co, ce = o.counters(), e.counters()
+    for k in ("density_candidates", "density_contributing", "sph_pairs", "grav_accepted"):
+        assert co[k] == ce[k], k
+
+
+def compare_state(o, e, tol=TOL):
+    bo, so = o.download(); be, se = e.download()
+    assert len(bo) == len(be) and len(so) == len(se)
+    for k in GAS_FIELDS:
+        assert relerr(getattr(be, k), getattr(bo, k)) < tol, f"{k}: {relerr(getattr(be, k), getattr(bo, k)):.3e}"
+    for k in ("x", "y", "z", "vx", "vy", "vz", "m", "radius"):
+        assert relerr(getattr(se, k), getattr(so, k)) < tol, f"sink {k}"
+
+
+@pytest.mark.parametrize("mode", [MODE_FIXED_H, MODE_VARIABLE_H, MODE_VARIABLE_H | FLAG_SOFT_USES_HI])
+def test_disc_10k_evaluation(mode, E, O):
+    """config 1: Keplerian disc, 10k gas + 1 central sink."""
+    p = default_params(mode)
+    b, s = ics.keplerian_disc(10_000)
+    o = O(p); o.record_neighbours(True); o.upload(b, s); o.evaluate()
+    with E(p) as e:
+        e.upload(b, s); e.evaluate()
+        compare_eval(o, e)
+        # neighbour lists row by row
+        _, _, oo, lo = o.neighbours(); _, _, oe, le = e.neighbours()
+        assert np.array_equal(oo, oe) and np.array_equal(lo, le)
+
+
+@pytest.mark.parametrize("mode", [MODE_FIXED_H, MODE_VARIABLE_H])
+def test_disc_10k_phases(mode, E, O):
+    p = default_params(mode)
+    b, s = ics.keplerian_disc(10_000, seed=77)
+    o = O(p); o.upload(b, s)
+    with E(p) as e:
+        e.upload(b, s)
+        for mask in (EVAL_TREE | EVAL_DENSITY | EVAL_GRAVITY, EVAL_TREE | EVAL_DENSITY | EVAL_SINKS, EVAL_TREE | EVAL_DENSITY | EVAL_SPH):
+            o.evaluate(mask); e.evaluate(mask)
+            do, de = o.diag(), e.diag()
+            for k in do:
+                assert relerr(de[k], do[k]) < TOL, (mask, k)
+
+
+@pytest.mark.parametrize("mode", [MODE_FIXED_H, MODE_VARIABLE_H])
+def test_disc_10k_steps(mode, E, O):
+    """config 1 to its end time (0.1 yr ~ 6 steps on the dt ladder): state, dt and t track the oracle."""
+    p = default_params(mode)
+    b, s = ics.keplerian_disc(10_000)
+    o = O(p); o.upload(b, s)
+    with E(p) as e:
+        e.upload(b, s)
+        dto = dte = 0.01; to = te = 0.0
+        while to < 0.1:
+            dto, to = o.step(dto, to); dte, te = e.step(dte, te)
+            assert dto == dte and to == te
+            assert o.sizes() == e.sizes()
+            if mode & MODE_VARIABLE_H:
+                assert o.counters()["h_iterations"] == e.counters()["h_iterations"]
+        compare_state(o, e)
+
+
+def test_sod_tube_variable(E, O):
+    """config 2 (reduced to ~20k for the CPU oracle): lattice ICs, no sink -> dummy sink, alpha = 1."""
+    p = default_params(MODE_VARIABLE_H)
+    b, s = ics.sod_tube(20_000, width=6)
+    o = O(p); o.record_neighbours(True); o.upload(b, s); o.evaluate()
+    with E(p) as e:
+        e.upload(b, s); e.evaluate()
+        compare_eval(o, e)
+        o.record_neighbours(False)
+        o.upload(b, s); e.upload(b, s)
+        dto = dte = 0.01; to = te = 0.0
+        for _ in range(3):
+            dto, to = o.step(dto, to); dte, te = e.step(dte, te)
+            assert dto == dte and to == te
+        compare_state(o, e)
+
+
+def test_sod_tube_fixed(E, O):
+    b, s = ics.sod_tube(20_000, width=6)
+    p = default_params(MODE_FIXED_H, h_fixed=float(1.2 * np.max(b.h) / 1.2))
+    o = O(p); o.record_neighbours(True); o.upload(b, s); o.evaluate()
+    with E(p) as e:
+        e.upload(b, s); e.evaluate()
+        compare_eval(o, e)
+
+
+def test_thin_ring_50k(E, O):
+    """config 3 geometry at 50k (the oracle's comfortable range), variable h, 2 steps."""
+    p = default_params(MODE_VARIABLE_H)
+    b, s = ics.thin_ring(50_000)
+    o = O(p, threads=1); o.record_neighbours(True); o.upload(b, s); o.evaluate()
+    with E(p) as e:
+        e.upload(b, s); e.evaluate()
+        compare_eval(o, e)
+        o.record_neighbours(False)
+        o.upload(b, s); e.upload(b, s)
+        dto = dte = 0.01; to = te = 0.0
+        for _ in range(2):
+            dto, to = o.step(dto, to); dte, te = e.step(dte, te)
+            assert dto == dte and to == te
+        compare_state(o, e)
+
+
+@pytest.mark.parametrize("mode", [MODE_FIXED_H, MODE_VARIABLE_H])
+def test_accretion_and_bounds(mode, E, O):
+    """Sinks that accrete (two of them, overlapping reach) and a tight bounding cube: removals, renumbering,
+    sink mass/position/velocity updates and the order-preserving pack (F:484-556 | V:616-688, F:471-482)."""
+    p = default_params(mode, bounding_size=85.0)
+    b, _ = ics.keplerian_disc(8_000, seed=9)
+    s = Sinks([0.0, 40.0], [0.0, 0.0], [0.0, 0.0], [0.0, 0.0], [0.0, 6.0], [0.0, 0.0], [1.0, 0.01], [13.0, 6.0])
+    o = O(p); o.upload(b, s)
+    with E(p) as e:
+        e.upload(b, s)
+        dto = dte = 0.01; to = te = 0.0
+        for k in range(3):
+            dto, to = o.step(dto, to); dte, te = e.step(dte, te)
+            assert o.sizes() == e.sizes(), k
+            assert dto == dte and to == te
+        assert o.sizes()[0] < 8_000
+        compare_state(o, e)
+
+
+def test_sink_creation(E, O):
+    """V:549-597: the first over-dense particle (m (eta/h)^3 > 0.5) far from every sink spawns a sink
+    (mass 1e-11, radius 2h), which then accretes its own seed particle in the same step (V:1155-1157).
+    max_length below the Newton-Raphson proposal keeps the seed's h (V:528,541)."""
+    p = default_params(MODE_VARIABLE_H, max_length=0.21)
+    b, s = ics.keplerian_disc(4_000, seed=21)
+    b.m[1234] = 5e-3; b.h[1234] = 0.2
+    o = O(p); o.upload(b, s)
+    with E(p) as e:
+        e.upload(b, s)
+        dto, to = o.step(0.01, 0.0); dte, te = e.step(0.01, 0.0)
+        assert o.sizes() == e.sizes() == (3999, 2)
+        assert (dto, to) == (dte, te)
+        compare_state(o, e)
+        dto, to = o.step(dto, to); dte, te = e.step(dte, te)
+        assert o.sizes() == e.sizes()
+        compare_state(o, e)
+
+
+@pytest.mark.parametrize("max_depth", [4, 7])
+def test_depth_limited_tree(max_depth, E, O):
+    """max_depth below the natural leaf depth: multi-particle childless nodes are skipped by the density /
+    SPH walks and taken whole by gravity (F:182,431,443)."""
+    p = default_params(MODE_VARIABLE_H, max_depth=max_depth)
+    b, s = ics.keplerian_disc(6_000, seed=4)
+    o = O(p); o.record_neighbours(True); o.upload(b, s); o.evaluate(EVAL_TREE | EVAL_DENSITY | EVAL_GRAVITY | EVAL_SINKS)
+    with E(p) as e:
+        e.upload(b, s); e.evaluate(EVAL_TREE | EVAL_DENSITY | EVAL_GRAVITY | EVAL_SINKS)
+        to, te = o.tree(), e.tree()
+        assert np.array_equal(to["level"], te["level"]) and np.max(te["level"]) == max_depth
+        assert np.any(to["n_in_leaf"] > 1)
+        co, ho, _, _ = o.neighbours(with_list=False); ce, he, _, _ = e.neighbours(with_list=False)
+        assert np.array_equal(co, ce) and np.array_equal(ho, he)
+        do, de = o.diag(), e.diag()
+        ok = do["rho"] > 0
+        assert relerr(de["rho"][ok], do["rho"][ok]) < TOL
+        assert np.array_equal(de["rho"] == 0, do["rho"] == 0)
+        for k in ("ax", "ay", "az"):
+            assert relerr(de[k], do[k]) < TOL, k
+
+
+def test_key_depth_error_is_loud(E):
+    """Two coincident particles with max_depth = 1000: the 63-bit key cannot separate them -> SPH_ERR_DEPTH."""
+    from summersph_b200.engine import SphError
+    p = default_params(MODE_VARIABLE_H)
+    b, s = ics.keplerian_disc(2_000, seed=2)
+    for k in ("x", "y", "z"):
+        getattr(b, k)[1] = getattr(b, k)[0]
+    with E(p) as e:
+        e.upload(b, s)
+        with pytest.raises(SphError) as ei:
+            e.evaluate()
+        assert ei.value.code == -6
+
+
+def test_ragged_and_tiny_inputs(E, O):
+    """Sizes that do not fill a warp / a walk group, and the smallest legal input (2 particles)."""
+    from summersph_b200.engine import SphError
+    p = default_params(MODE_VARIABLE_H)
+    for n in (2, 3, 31, 33, 65, 1000):
+        b, s = ics.keplerian_disc(n, seed=n)
+        o = O(p); o.record_neighbours(True); o.upload(b, s); o.evaluate()
+        with E(p) as e:
+            e.upload(b, s); e.evaluate()
+            compare_eval(o, e)
+    b, s = ics.keplerian_disc(1, seed=1)
+    with E(p) as e:
+        with pytest.raises(SphError):
+            e.upload(b, s)
+
+
+def test_run_until_matches_stepping(E):
+    """sph_run_until (device-resident loop) == repeated sph_step."""
+    p = default_params(MODE_VARIABLE_H)
+    b, s = ics.keplerian_disc(5_000, seed=8)
+    with E(p) as e1, E(p) as e2:
+        e1.upload(b, s); e2.upload(b, s)
+        dt, t, steps = e1.run_until(0.05, 0.01, 0.0)
+        dt2, t2, n2 = 0.01, 0.0, 0
+        while t2 < 0.05:
+            dt2, t2 = e2.step(dt2, t2); n2 += 1
+        assert (dt, t, steps) == (dt2, t2, n2)
+        b1, _ = e1.download(); b2, _ = e2.download()
+        for k in GAS_FIELDS:
+            assert np.array_equal(getattr(b1, k), getattr(b2, k)), k       # deterministic kernels
+
+
+def test_million_particle_properties(E):
+    """Size-independent properties at 1M particles (beyond the oracle's comfortable range): keys sorted,
+    every particle is its own neighbour, SPH pair forces conserve momentum, downloads come back in
+    ascending number order, repeat evaluations are bit-identical."""
+    p = default_params(MODE_VARIABLE_H)
+    n = 1_000_000
+    b, s = ics.keplerian_disc(n, seed=5)
+    with E(p) as e:
+        e.upload(b, s)
+        e.evaluate(EVAL_TREE | EVAL_DENSITY | EVAL_SPH)
+        t = e.tree()
+        assert np.array_equal(np.sort(t["order"]), np.arange(n))
+        sorted_keys = t["key"][t["order"]]                                # keys along the DFS leaf order
+        assert np.all(sorted_keys[1:] > sorted_keys[:-1])
+        d = e.diag()
+        assert np.all(d["rho"] >= b.m / (float(np.float32(np.pi)) * b.h ** 3) * (1 - 1e-12))   # self term
+        for k in ("ax", "ay", "az"):
+            tot = np.sum(b.m * d[k]); scale = np.sum(np.abs(b.m * d[k]))
+            assert abs(tot) < 1e-11 * scale
+        bb, _ = e.download()
+        assert np.array_equal(bb.x, b.x) and np.array_equal(bb.h, b.h)
+        e.evaluate(EVAL_TREE | EVAL_DENSITY | EVAL_SPH)
+        d2 = e.diag()
+        for k in ("rho", "ax", "udot"):
+            assert np.array_equal(d[k], d2[k]), k
+
+
+def test_disc_200k_vs_threaded_oracle(E, O):
+    """200k disc against the oracle with OpenMP on its race-free loops (density, gravity, h iteration);
+    the SPH pair loop stays serial in the oracle's parity path only when threads == 1, so compare the
+    density / gravity phases here."""
+    import os
+    p = default_params(MODE_VARIABLE_H)
+    b, s = ics.keplerian_disc(200_000, seed=6)
+    o = O(p, threads=min(8, os.cpu_count() or 1)); o.upload(b, s)
+    mask = EVAL_TREE | EVAL_DENSITY | EVAL_GRAVITY | EVAL_SINKS
+    o.evaluate(mask)
+    with E(p) as e:
+        e.upload(b, s); e.evaluate(mask)
+        compare_eval(o, e, check_ngb=False)
