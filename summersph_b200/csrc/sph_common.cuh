@@ -62,6 +62,26 @@ __device__ __forceinline__ int lcp_levels(uint64_t a, uint64_t b, int lmax) {
   return l < lmax ? l : lmax;
 }
 
+// Reciprocal / square root without the IEEE slow-path subroutine: MUFU seed (~2^-20) + two FMA Newton /
+// Goldschmidt steps (~1 ulp).  Used only where the result feeds FP64 sums compared at 1e-10; every
+// membership / ordering decision uses the correctly rounded __d*_rn intrinsics instead.
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0); r = fma(r, e, r);
+  e = fma(-x, r, 1.0); r = fma(r, e, r);
+  return r;
+}
+// s = sqrt(x), rs = 1/sqrt(x) for x > 0 (x == 0 gives NaN in both, callers guard where 0 is legal)
+__device__ __forceinline__ void fast_sqrt_rsqrt(double x, double& s, double& rs) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double g = x * y, h = 0.5 * y;
+  double r = fma(-h, g, 0.5); g = fma(g, r, g); h = fma(h, r, h);
+  r = fma(-h, g, 0.5); g = fma(g, r, g); h = fma(h, r, h);
+  s = g; rs = 2.0 * h;
+}
+
 __device__ __forceinline__ double warp_min(double v) {
   for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(FULL_MASK, v, o));
   return v;

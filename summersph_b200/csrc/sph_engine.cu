@@ -61,7 +61,7 @@ struct sph_ctx {
   double *d_wt = nullptr, *d_dwt = nullptr, *d_gt = nullptr;
   SinkArrays S = {}; double* sink_buf = nullptr; double* sink_partial = nullptr; size_t sink_partial_cap = 0;
   SimScalars* sc = nullptr; SimScalars* h_sc = nullptr;     // device + pinned host mirror
-  WalkCounters* ctr = nullptr; WalkCounters* h_ctr = nullptr;
+  WalkCounters* ctr = nullptr; WalkCounters* h_ctr = nullptr; int* work = nullptr;
   unsigned char* keep = nullptr; unsigned long long* acc_key[2] = {}; int* acc_val[2] = {}; int* d_nsel = nullptr;
   int* pos = nullptr;           // ascending-number position of each sorted particle (downloads)
   double* stage_d = nullptr;    // device staging for ordered downloads
@@ -279,8 +279,9 @@ int run_density(sph_ctx* c) {
   const int n = (int)c->n, W = 16;
   stage_begin(c, ST_DENSITY);
   StateArrays s = state_of(c, c->cur);
+  CK(cudaMemsetAsync(c->work, 0, sizeof(int), c->stream));
   LAUNCH(k_density<false>, walk_grid(c, W), W * 32, density_smem(c, W), c->n_groups, c->groups, c->dp, dens_arrays(c), c->bvh, c->bi, c->d_wt, c->d_dwt,
-         s.u, s.h, c->rho, c->omega, c->prs, c->cs, c->por2, c->ctr);
+         s.u, s.h, c->rho, c->omega, c->prs, c->cs, c->por2, c->ctr, c->work);
   stage_end(c);
   return SPH_OK;
 }
@@ -288,8 +289,9 @@ int run_hiter(sph_ctx* c) {
   const int n = (int)c->n, W = 16;
   stage_begin(c, ST_HITER);
   StateArrays s = state_of(c, c->cur);
+  CK(cudaMemsetAsync(c->work, 0, sizeof(int), c->stream));
   LAUNCH(k_density<true>, walk_grid(c, W), W * 32, density_smem(c, W), c->n_groups, c->groups, c->dp, dens_arrays(c), c->bvh, c->bi, c->d_wt, c->d_dwt,
-         s.u, s.h, c->rho, c->omega, c->prs, c->cs, c->por2, c->ctr);
+         s.u, s.h, c->rho, c->omega, c->prs, c->cs, c->por2, c->ctr, c->work);
   stage_end(c);
   return SPH_OK;
 }
@@ -298,7 +300,8 @@ int run_force(sph_ctx* c) {
   stage_begin(c, ST_SPH);
   StateArrays s = state_of(c, c->cur);
   ForceArrays A{s.x, s.y, s.z, s.vx, s.vy, s.vz, s.m, s.h, c->rho, c->cs, s.alpha, c->por2, c->lcx, c->lcy, c->lcz, c->reach, s.id};
-  LAUNCH(k_force, walk_grid(c, W), W * 32, force_smem(c, W), c->n_groups, c->groups, c->dp, A, c->bvh, c->bi, c->d_dwt, c->ax, c->ay, c->az, c->udot, c->adot, c->ctr);
+  CK(cudaMemsetAsync(c->work, 0, sizeof(int), c->stream));
+  LAUNCH(k_force, walk_grid(c, W), W * 32, force_smem(c, W), c->n_groups, c->groups, c->dp, A, c->bvh, c->bi, c->d_dwt, c->ax, c->ay, c->az, c->udot, c->adot, c->ctr, c->work);
   stage_end(c);
   return SPH_OK;
 }
@@ -515,6 +518,7 @@ int sph_create(const sph_params* p, int32_t device, sph_ctx** out) {
   if ((r = dalloc(c, &c->root, 1))) return fail(r);
   if ((r = dalloc(c, &c->sc, 1))) return fail(r);
   if ((r = dalloc(c, &c->ctr, 1))) return fail(r);
+  if ((r = dalloc(c, &c->work, 4))) return fail(r);
   if ((r = dalloc(c, &c->d_nsel, 1))) return fail(r);
   if ((r = dalloc(c, &c->sink_buf, (size_t)SPH_MAX_SINKS * 11))) return fail(r);
   { double* b = c->sink_buf; const int M = SPH_MAX_SINKS;
@@ -548,7 +552,7 @@ int sph_destroy(sph_ctx* c) {
   F(c->rho); F(c->omega); F(c->prs); F(c->cs); F(c->por2); F(c->ax); F(c->ay); F(c->az); F(c->udot); F(c->adot);
   F(c->node_count); F(c->gsize); F(c->gfirst); F(c->groups); F(c->level); F(c->lcx); F(c->lcy); F(c->lcz); F(c->reach); F(c->bvh); F(c->nodes); F(c->node_part); F(c->parent); F(c->nchild);
   F(c->arrive); F(c->cnt); F(c->off); F(c->root); F(c->partial); F(c->cub_tmp); F(c->d_wt); F(c->d_dwt); F(c->d_gt);
-  F(c->sink_buf); F(c->sink_partial); F(c->sc); F(c->ctr); F(c->keep); F(c->d_nsel); F(c->pos); F(c->stage_d);
+  F(c->sink_buf); F(c->sink_partial); F(c->sc); F(c->ctr); F(c->work); F(c->keep); F(c->d_nsel); F(c->pos); F(c->stage_d);
   if (c->h_sc) cudaFreeHost(c->h_sc);
   if (c->h_ctr) cudaFreeHost(c->h_ctr);
   for (auto& e : c->ev_used) { cudaEventDestroy(e.second.first); cudaEventDestroy(e.second.second); }

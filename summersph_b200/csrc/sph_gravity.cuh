@@ -64,11 +64,11 @@ k_gravity(int n, DevParams P, const GNode* __restrict__ nodes, int n_nodes,
           ++accepted;
           skip = nf.x;
           if (a.w > 0.0 && d2 > 0.0) {                                        // F:279
-            const double dist = sqrt(d2);
+            double dist, rs; fast_sqrt_rsqrt(d2, dist, rs);
             const double q = dist * inv_h;
             double W = 1.0;
             if (q <= 2.0) W = table_lerp1(gt, P.nq, P.dq, P.inv_dq, q);       // F:129-146
-            const double f = (P.G * a.w * W) / (dist * dist * dist);          // F:281
+            const double f = (P.G * a.w * W) * (rs * rs * rs);                // F:281
             gx -= f * dx; gy -= f * dy; gz -= f * dz;
           }
         } else { open = true; ++opened; }

@@ -159,7 +159,9 @@ struct DensityOp {
     while (mask) {
       int k = __ffs(mask) - 1; mask &= mask - 1;
       double dx = xi - sx[k], dy = yi - sy[k], dz = zi - sz[k];
-      double r = sqrt(dx * dx + dy * dy + dz * dz);
+      const double r2 = dx * dx + dy * dy + dz * dz;
+      double r, rs; fast_sqrt_rsqrt(r2, r, rs);
+      if (r2 == 0.0) r = 0.0;                                            // self term, W(0)
       double q = r * inv_h;
       if (q <= 2.0) {
         double w, dw; table_lerp(wt, dwt, nq, dq, inv_dq, q, w, dw);
@@ -179,7 +181,7 @@ k_density(int n_groups, const int2* __restrict__ groups, DevParams P, DensityArr
           const double* __restrict__ g_wt, const double* __restrict__ g_dwt,
           const double* __restrict__ u, double* __restrict__ h,
           double* __restrict__ rho, double* __restrict__ omega, double* __restrict__ prs, double* __restrict__ cs,
-          double* __restrict__ por2, WalkCounters* ctr) {
+          double* __restrict__ por2, WalkCounters* ctr, int* work) {
   extern __shared__ double smem[];
   const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double* wt = smem; double* dwt = smem + (P.nq + 1);
@@ -193,7 +195,11 @@ k_density(int n_groups, const int2* __restrict__ groups, DevParams P, DensityArr
   const int nchunk = n_groups;
   unsigned long long tot_cand = 0, tot_contrib = 0, tot_iter = 0;
 
-  for (int chunk = blockIdx.x * nwarp + warp; chunk < nchunk; chunk += gridDim.x * nwarp) {
+  for (;;) {
+    int chunk = 0;
+    if (lane == 0) chunk = atomicAdd(work, 1);
+    chunk = __shfl_sync(FULL_MASK, chunk, 0);
+    if (chunk >= nchunk) break;
     const int2 tg = groups[chunk];
     const int i = tg.x + lane;
     const bool live = lane < tg.y;
@@ -274,7 +280,7 @@ struct ForceArrays {
   const double *x, *y, *z, *vx, *vy, *vz, *m, *h, *rho, *c, *alpha, *por2, *lcx, *lcy, *lcz, *reach;
   const int* id;
 };
-#define FORCE_FIELDS 17
+#define FORCE_FIELDS 18
 
 struct ForceOp {
   static const bool SYMMETRIC = true;
@@ -311,6 +317,7 @@ struct ForceOp {
     t[3 * WALK_TILE + s] = A.vx[j]; t[4 * WALK_TILE + s] = A.vy[j]; t[5 * WALK_TILE + s] = A.vz[j];
     t[6 * WALK_TILE + s] = A.m[j];  t[7 * WALK_TILE + s] = hj;
     t[8 * WALK_TILE + s] = 1.0 / (pi_norm * ((hj * hj) * (hj * hj)));
+    t[17 * WALK_TILE + s] = 1.0 / hj;
     t[9 * WALK_TILE + s] = A.rho[j]; t[10 * WALK_TILE + s] = A.c[j]; t[11 * WALK_TILE + s] = A.alpha[j];
     t[12 * WALK_TILE + s] = A.por2[j];
     t[13 * WALK_TILE + s] = A.lcx[j]; t[14 * WALK_TILE + s] = A.lcy[j]; t[15 * WALK_TILE + s] = A.lcz[j];
@@ -338,10 +345,9 @@ struct ForceOp {
       const double nx = xi - t[0 * WALK_TILE + k], ny = yi - t[1 * WALK_TILE + k], nz = zi - t[2 * WALK_TILE + k];   // F:356
       const double wx = vxi - t[3 * WALK_TILE + k], wy = vyi - t[4 * WALK_TILE + k], wz = vzi - t[5 * WALK_TILE + k]; // F:358
       const double r2 = nx * nx + ny * ny + nz * nz;
-      const double dr = sqrt(r2);
+      double dr, inv_dr; fast_sqrt_rsqrt(r2, dr, inv_dr);                 // dr == 0 -> NaN like F:363
       const double rv = wx * nx + wy * ny + wz * nz;
       const double vdotr = rv >= 0.0 ? 0.0 : rv;                          // F:361
-      const double inv_dr = 1.0 / dr;                                     // dr == 0 -> NaN like F:363
       const double mj = t[6 * WALK_TILE + k], hj = t[7 * WALK_TILE + k];
       // kernel gradient magnitudes dW/dr at h_i and h_j                                   F:366 | V:395-396
       double dWi = 0.0, dWj = 0.0;
@@ -350,14 +356,14 @@ struct ForceOp {
         if (q <= 2.0) dWi = table_lerp1(dwt, nq, dq, inv_dq, q) * inv_n4i;
       }
       if (variable_h) {
-        const double q = dr / hj;
+        const double q = dr * t[17 * WALK_TILE + k];
         if (q <= 2.0) dWj = table_lerp1(dwt, nq, dq, inv_dq, q) * t[8 * WALK_TILE + k];
       } else dWj = dWi;
       const double hbar = variable_h ? (hi + hj) / 2.0 : hi;              // V:402
-      const double nu = (hbar * vdotr) / (r2 + lit_001 * hbar * hbar);    // F:373 | V:405
+      const double nu = (hbar * vdotr) * fast_rcp(r2 + lit_001 * hbar * hbar);   // F:373 | V:405
       const double cbar = 0.5 * (ci + t[10 * WALK_TILE + k]);
       const double abar = 0.5 * (alphai + t[11 * WALK_TILE + k]);
-      const double visc = (-abar * cbar * nu + 2.0 * abar * nu * nu) / (0.5 * (rhoi + t[9 * WALK_TILE + k]));   // F:378 | V:410
+      const double visc = (-abar * cbar * nu + 2.0 * abar * nu * nu) * fast_rcp(0.5 * (rhoi + t[9 * WALK_TILE + k]));   // F:378 | V:410
       const double por2j = t[12 * WALK_TILE + k];
       const double rvn = rv * inv_dr;                                     // n_hat . v_ij
       double scal, vdg;
@@ -379,7 +385,7 @@ struct ForceOp {
 __global__ void __launch_bounds__(512, 1)
 k_force(int n_groups, const int2* __restrict__ groups, DevParams P, ForceArrays A, const BvhBox* __restrict__ box, BvhInfo bi, const double* __restrict__ g_dwt,
         double* __restrict__ ax, double* __restrict__ ay, double* __restrict__ az, double* __restrict__ udot,
-        double* __restrict__ adot, WalkCounters* ctr) {
+        double* __restrict__ adot, WalkCounters* ctr, int* work) {
   extern __shared__ double smem[];
   const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double* dwt = smem;
@@ -393,7 +399,11 @@ k_force(int n_groups, const int2* __restrict__ groups, DevParams P, ForceArrays 
   unsigned* cq = stack + WALK_STACK;
   const int nchunk = n_groups;
   unsigned long long tot_pairs = 0;
-  for (int chunk = blockIdx.x * nwarp + warp; chunk < nchunk; chunk += gridDim.x * nwarp) {
+  for (;;) {
+    int chunk = 0;
+    if (lane == 0) chunk = atomicAdd(work, 1);
+    chunk = __shfl_sync(FULL_MASK, chunk, 0);
+    if (chunk >= nchunk) break;
     const int2 tg = groups[chunk];
     const int i = tg.x + lane;
     const bool live = lane < tg.y;
