@@ -310,14 +310,15 @@ int run_gravity(sph_ctx* c, int do_grav, int do_sinks) {
   stage_begin(c, ST_GRAVITY);
   StateArrays s = state_of(c, c->cur);
   const int nb = cdiv(n, T);
+  const int nw = cdiv(n, 32);
   const int ns = do_sinks ? c->n_sink : 0;
-  if ((size_t)nb * std::max(ns, 1) * 3 > c->sink_partial_cap) {
-    c->sink_partial_cap = (size_t)nb * std::max(ns, 1) * 3 * 2;
+  if ((size_t)(nw + 8) * std::max(ns, 1) * 3 > c->sink_partial_cap) {
+    c->sink_partial_cap = (size_t)(nw + 8) * std::max(ns, 1) * 3 * 2;
     DA(c->sink_partial, c->sink_partial_cap);
   }
   LAUNCH(k_gravity, nb, T, (size_t)(c->p.nq + 1) * 8, n, c->dp, c->nodes, (int)c->counts.n_nodes, s.x, s.y, s.z, s.h, s.m, c->d_gt,
          c->ax, c->ay, c->az, do_grav, ns, c->S, c->sink_partial, c->ctr);
-  LAUNCH(k_sink_finalize, 1, 32, 0, nb, c->n_sink, c->sink_partial, c->S, c->dp.G, do_sinks);
+  LAUNCH(k_sink_finalize, 1, 256, 0, nw, c->n_sink, c->sink_partial, c->S, c->dp.G, do_sinks);
   stage_end(c);
   return SPH_OK;
 }

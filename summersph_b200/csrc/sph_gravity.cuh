@@ -17,8 +17,17 @@
 
 struct SinkArrays { double *x, *y, *z, *vx, *vy, *vz, *m, *radius, *ax, *ay, *az; };
 
+struct NodeRegs { double cx, cy, cz, m, size; int next, flags; };
+__device__ __forceinline__ NodeRegs load_node(const GNode* __restrict__ nodes, int v) {
+  const double2* p = reinterpret_cast<const double2*>(nodes + v);
+  const double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+  NodeRegs r; r.cx = a.x; r.cy = a.y; r.cz = b.x; r.m = b.y; r.size = c.x;
+  r.next = __double2loint(c.y); r.flags = __double2hiint(c.y);
+  return r;
+}
+
 // layout of dynamic smem: grav table (nq+1 doubles)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 k_gravity(int n, DevParams P, const GNode* __restrict__ nodes, int n_nodes,
           const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
           const double* __restrict__ h, const double* __restrict__ m, const double* __restrict__ g_gt,
@@ -41,44 +50,40 @@ k_gravity(int n, DevParams P, const GNode* __restrict__ nodes, int n_nodes,
     int cur = 0;
     int skip = live ? 0 : 0x7fffffff;
     while (cur < n_nodes) {
-      const GNode* nd = nodes + cur;
-      const double4 a = *reinterpret_cast<const double4*>(nd);
-      const double size = nd->size;
-      const int2 nf = *reinterpret_cast<const int2*>(&nd->next);
+      const NodeRegs N = load_node(nodes, cur);
       bool open = false;
       if (cur >= skip) {
-        const double dx = xi - a.x, dy = yi - a.y, dz = zi - a.z;            // F:274
-        double d2 = dx * dx + dy * dy + dz * dz + soft;
+        const double dx = xi - N.cx, dy = yi - N.cy, dz = zi - N.cz;          // F:274
+        const double d2 = dx * dx + dy * dy + dz * dz + soft;
         bool accept;
-        if (nf.y & 1) accept = true;                                          // .not. allocated(children)
+        if (N.flags & 1) accept = true;                                       // .not. allocated(children)
         else {
-          const double s2 = size * size, t2 = theta2 * d2;
+          const double s2 = N.size * N.size, t2 = theta2 * d2;
           if (s2 < t2 * (1.0 - 1e-12)) accept = true;
           else if (s2 > t2 * (1.0 + 1e-12)) accept = false;
           else {   // borderline: redo the reference's arithmetic exactly (no contraction)       F:275-278
             double e2 = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)), soft);
-            accept = __ddiv_rn(size, __dsqrt_rn(e2)) < theta;
+            accept = __ddiv_rn(N.size, __dsqrt_rn(e2)) < theta;
           }
         }
         if (accept) {
           ++accepted;
-          skip = nf.x;
-          if (a.w > 0.0 && d2 > 0.0) {                                        // F:279
+          skip = N.next;
+          if (N.m > 0.0 && d2 > 0.0) {                                        // F:279
             double dist, rs; fast_sqrt_rsqrt(d2, dist, rs);
             const double q = dist * inv_h;
             double W = 1.0;
             if (q <= 2.0) W = table_lerp1(gt, P.nq, P.dq, P.inv_dq, q);       // F:129-146
-            const double f = (P.G * a.w * W) * (rs * rs * rs);                // F:281
+            const double f = (P.G * N.m * W) * (rs * rs * rs);                // F:281
             gx -= f * dx; gy -= f * dy; gz -= f * dz;
           }
         } else { open = true; ++opened; }
       }
-      cur = __any_sync(FULL_MASK, open) ? cur + 1 : nf.x;
+      cur = __any_sync(FULL_MASK, open) ? cur + 1 : N.next;
     }
   }
-  // direct sink <-> gas (unsoftened) F:567-576; per-block partial sums of the sink side
-  __shared__ double red[8][3];
-  const int warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  // direct sink <-> gas (unsoftened) F:567-576; per-warp partial sums of the sink side (no block barrier)
+  const int gwarp = i >> 5;
   for (int s = 0; s < n_sink; ++s) {
     const double vx_ = xi - S.x[s], vy_ = yi - S.y[s], vz_ = zi - S.z[s];
     const double dr = sqrt(vx_ * vx_ + vy_ * vy_ + vz_ * vz_);
@@ -92,33 +97,31 @@ k_gravity(int n, DevParams P, const GNode* __restrict__ nodes, int n_nodes,
       px = mi * wx; py = mi * wy; pz = mi * wz;                               // F:573
     }
     px = warp_sum(px); py = warp_sum(py); pz = warp_sum(pz);
-    if (lane == 0) { red[warp][0] = px; red[warp][1] = py; red[warp][2] = pz; }
-    __syncthreads();
-    if (threadIdx.x < 3) {
-      double t = 0.0;
-      for (int w = 0; w < nwarp; ++w) t += red[w][threadIdx.x];
-      sink_partial[((size_t)blockIdx.x * n_sink + s) * 3 + threadIdx.x] = t;
+    if (lane == 0) {
+      double* o = sink_partial + ((size_t)gwarp * n_sink + s) * 3;
+      o[0] = px; o[1] = py; o[2] = pz;
     }
-    __syncthreads();
   }
   if (live) { ax[i] = gx; ay[i] = gy; az[i] = gz; }
   opened = (unsigned)warp_sum_ll(opened); accepted = (unsigned)warp_sum_ll(accepted);
   if (lane == 0 && do_grav) { atomicAdd(&ctr->grav_opened, (unsigned long long)opened); atomicAdd(&ctr->grav_accepted, (unsigned long long)accepted); }
 }
 
-// fold per-block sink partials in block order (deterministic) and add sink-sink pairs F:578-590
-__global__ void k_sink_finalize(int n_blocks, int n_sink, const double* __restrict__ partial, SinkArrays S, double G, int do_sinks) {
+// fold per-warp sink partials in a fixed order (deterministic) and add sink-sink pairs F:578-590. One block of 256.
+__global__ void k_sink_finalize(int n_parts, int n_sink, const double* __restrict__ partial, SinkArrays S, double G, int do_sinks) {
+  __shared__ double red[256];
   __shared__ double acc[SPH_MAX_SINKS][3];
-  const int t = threadIdx.x;           // one warp per launch; lanes stride over blocks
-  for (int s = 0; s < n_sink; ++s) {
-    double v[3] = {0.0, 0.0, 0.0};
-    if (do_sinks)
-      for (int b = t; b < n_blocks; b += 32)
-        for (int k = 0; k < 3; ++k) v[k] += partial[((size_t)b * n_sink + s) * 3 + k];
-    for (int k = 0; k < 3; ++k) v[k] = warp_sum(v[k]);
-    if (t == 0) for (int k = 0; k < 3; ++k) acc[s][k] = v[k];
-  }
-  __syncwarp();
+  const int t = threadIdx.x;
+  for (int s = 0; s < n_sink; ++s)
+    for (int k = 0; k < 3; ++k) {
+      double v = 0.0;
+      if (do_sinks) for (int b = t; b < n_parts; b += 256) v += partial[((size_t)b * n_sink + s) * 3 + k];
+      red[t] = v;
+      __syncthreads();
+      for (int o = 128; o > 0; o >>= 1) { if (t < o) red[t] += red[t + o]; __syncthreads(); }
+      if (t == 0) acc[s][k] = red[0];
+      __syncthreads();
+    }
   if (t == 0) {
     if (do_sinks && n_sink >= 2) {
       for (int i = 0; i < n_sink; ++i)
