@@ -166,9 +166,8 @@ def main():
 
     e = Engine(p, device=local)
     if world > 1:
-        uid = [e.unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        e.comm_init(rank, world, uid[0])
+        from summersph_b200.parallel import init_comm, torch_broadcast_bytes
+        init_comm(e, rank, world, torch_broadcast_bytes)
 
     def barrier():
         if world > 1:

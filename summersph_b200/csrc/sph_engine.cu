@@ -38,7 +38,10 @@ struct NcclApi {   // resolved at run time from the already-loaded (torch-bundle
   int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
   int (*Broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
 };
+enum { NC_UINT64 = 5, NC_FLOAT64 = 8, NC_SUM = 0, NC_MIN = 3 };
 
 }  // namespace
 
@@ -72,6 +75,8 @@ struct sph_ctx {
   cudaEvent_t tm0 = nullptr, tm1 = nullptr;
   // multi-GPU
   NcclApi nccl; void* comm = nullptr; int rank = 0, n_ranks = 1;
+  std::vector<int> rank_g, rank_p;   // per-rank first group / first particle of its target slice (size n_ranks + 1)
+  int g0 = 0, g1 = 0, p0 = 0, p1 = 0;
 };
 
 namespace {
@@ -182,6 +187,48 @@ int upload_tables(sph_ctx* c) {
 }
 
 // ---------------------------------------------------------------------------------------------------
+// multi-GPU: particles are replicated on every rank, target work is sharded by contiguous group slices;
+// results travel with an all-gather-v (one in-place ncclBroadcast per owner inside a group call).
+// ---------------------------------------------------------------------------------------------------
+#define NC(call) do { int r_ = (call); if (r_ != 0) { c->err = std::string(#call) + ": " + (c->nccl.GetErrorString ? c->nccl.GetErrorString(r_) : "nccl error"); return SPH_ERR_COMM; } } while (0)
+
+int allgatherv(sph_ctx* c, double* const* bufs, int nbufs) {
+  if (c->n_ranks <= 1) return SPH_OK;
+  NC(c->nccl.GroupStart());
+  for (int b = 0; b < nbufs; ++b)
+    for (int r = 0; r < c->n_ranks; ++r) {
+      const int cnt = c->rank_p[r + 1] - c->rank_p[r];
+      if (cnt <= 0) continue;
+      double* p = bufs[b] + c->rank_p[r];
+      NC(c->nccl.Broadcast(p, p, (size_t)cnt, NC_FLOAT64, r, c->comm, c->stream));
+    }
+  NC(c->nccl.GroupEnd());
+  return SPH_OK;
+}
+int allreduce(sph_ctx* c, void* buf, size_t count, int dtype, int op) {
+  if (c->n_ranks <= 1) return SPH_OK;
+  NC(c->nccl.AllReduce(buf, buf, count, dtype, op, c->comm, c->stream));
+  return SPH_OK;
+}
+
+__global__ void k_set_int(int* p, int v) { *p = v; }
+
+int compute_slices(sph_ctx* c) {
+  const int R = c->n_ranks, ng = c->n_groups, n = (int)c->n;
+  c->rank_g.assign(R + 1, 0); c->rank_p.assign(R + 1, 0);
+  for (int r = 0; r <= R; ++r) c->rank_g[r] = (int)((int64_t)ng * r / R);
+  c->rank_p[R] = n;
+  if (R > 1) {
+    for (int r = 1; r < R; ++r)
+      CK(cudaMemcpyAsync(&c->rank_p[r], c->gfirst + c->rank_g[r], sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  c->g0 = c->rank_g[c->rank]; c->g1 = c->rank_g[c->rank + 1];
+  c->p0 = c->rank_p[c->rank]; c->p1 = c->rank_p[c->rank + 1];
+  return SPH_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // tree
 // ---------------------------------------------------------------------------------------------------
 int build_tree(sph_ctx* c) {
@@ -253,11 +300,13 @@ int build_tree(sph_ctx* c) {
       offl += cntl; cntl = np; ++l;
     }
     bi.nlev = l + 1;
+    { int r_ = compute_slices(c); if (r_) return r_; }
   }
   stage_end(c);
   c->tree_valid = true;
   return SPH_OK;
 }
+
 
 size_t density_smem(const sph_ctx* c, int nwarp) { return (size_t)2 * (c->p.nq + 1) * 8 + (size_t)nwarp * 8 * WALK_TILE * 8 + (size_t)nwarp * (WALK_STACK + WALK_CQ) * 4; }
 size_t force_smem(const sph_ctx* c, int nwarp) {
@@ -265,7 +314,7 @@ size_t force_smem(const sph_ctx* c, int nwarp) {
   return t + (size_t)nwarp * FORCE_FIELDS * WALK_TILE * 8 + (size_t)nwarp * WALK_TILE * 4 + (size_t)nwarp * (WALK_STACK + WALK_CQ) * 4;
 }
 int walk_grid(const sph_ctx* c, int nwarp) {
-  const int nchunk = c->n_groups;
+  const int nchunk = c->g1 - c->g0;
   int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
   return std::max(1, std::min(cdiv(nchunk, nwarp), sms));
 }
@@ -279,9 +328,10 @@ int run_density(sph_ctx* c) {
   const int n = (int)c->n, W = 16;
   stage_begin(c, ST_DENSITY);
   StateArrays s = state_of(c, c->cur);
-  CK(cudaMemsetAsync(c->work, 0, sizeof(int), c->stream));
-  LAUNCH(k_density<false>, walk_grid(c, W), W * 32, density_smem(c, W), c->n_groups, c->groups, c->dp, dens_arrays(c), c->bvh, c->bi, c->d_wt, c->d_dwt,
+  LAUNCH(k_set_int, 1, 1, 0, c->work, c->g0);
+  LAUNCH(k_density<false>, walk_grid(c, W), W * 32, density_smem(c, W), c->g1, c->groups, c->dp, dens_arrays(c), c->bvh, c->bi, c->d_wt, c->d_dwt,
          s.u, s.h, c->rho, c->omega, c->prs, c->cs, c->por2, c->ctr, c->work);
+  { double* bufs[5] = {c->rho, c->omega, c->prs, c->cs, c->por2}; int r_ = allgatherv(c, bufs, 5); if (r_) return r_; }
   stage_end(c);
   return SPH_OK;
 }
@@ -289,9 +339,10 @@ int run_hiter(sph_ctx* c) {
   const int n = (int)c->n, W = 16;
   stage_begin(c, ST_HITER);
   StateArrays s = state_of(c, c->cur);
-  CK(cudaMemsetAsync(c->work, 0, sizeof(int), c->stream));
-  LAUNCH(k_density<true>, walk_grid(c, W), W * 32, density_smem(c, W), c->n_groups, c->groups, c->dp, dens_arrays(c), c->bvh, c->bi, c->d_wt, c->d_dwt,
+  LAUNCH(k_set_int, 1, 1, 0, c->work, c->g0);
+  LAUNCH(k_density<true>, walk_grid(c, W), W * 32, density_smem(c, W), c->g1, c->groups, c->dp, dens_arrays(c), c->bvh, c->bi, c->d_wt, c->d_dwt,
          s.u, s.h, c->rho, c->omega, c->prs, c->cs, c->por2, c->ctr, c->work);
+  { double* bufs[1] = {s.h}; int r_ = allgatherv(c, bufs, 1); if (r_) return r_; }
   stage_end(c);
   return SPH_OK;
 }
@@ -300,25 +351,30 @@ int run_force(sph_ctx* c) {
   stage_begin(c, ST_SPH);
   StateArrays s = state_of(c, c->cur);
   ForceArrays A{s.x, s.y, s.z, s.vx, s.vy, s.vz, s.m, s.h, c->rho, c->cs, s.alpha, c->por2, c->lcx, c->lcy, c->lcz, c->reach, s.id};
-  CK(cudaMemsetAsync(c->work, 0, sizeof(int), c->stream));
-  LAUNCH(k_force, walk_grid(c, W), W * 32, force_smem(c, W), c->n_groups, c->groups, c->dp, A, c->bvh, c->bi, c->d_dwt, c->ax, c->ay, c->az, c->udot, c->adot, c->ctr, c->work);
+  LAUNCH(k_set_int, 1, 1, 0, c->work, c->g0);
+  LAUNCH(k_force, walk_grid(c, W), W * 32, force_smem(c, W), c->g1, c->groups, c->dp, A, c->bvh, c->bi, c->d_dwt, c->ax, c->ay, c->az, c->udot, c->adot, c->ctr, c->work);
+  { double* bufs[5] = {c->ax, c->ay, c->az, c->udot, c->adot}; int r_ = allgatherv(c, bufs, 5); if (r_) return r_; }
   stage_end(c);
   return SPH_OK;
 }
 int run_gravity(sph_ctx* c, int do_grav, int do_sinks) {
-  const int n = (int)c->n, T = 256;
+  const int T = 256;
   stage_begin(c, ST_GRAVITY);
   StateArrays s = state_of(c, c->cur);
-  const int nb = cdiv(n, T);
-  const int nw = cdiv(n, 32);
+  const int nloc = c->p1 - c->p0;
+  const int nb = cdiv(nloc, T);
+  const int nw = cdiv(nloc, 32);
   const int ns = do_sinks ? c->n_sink : 0;
   if ((size_t)(nw + 8) * std::max(ns, 1) * 3 > c->sink_partial_cap) {
     c->sink_partial_cap = (size_t)(nw + 8) * std::max(ns, 1) * 3 * 2;
     DA(c->sink_partial, c->sink_partial_cap);
   }
-  LAUNCH(k_gravity, nb, T, (size_t)(c->p.nq + 1) * 8, n, c->dp, c->nodes, (int)c->counts.n_nodes, s.x, s.y, s.z, s.h, s.m, c->d_gt,
-         c->ax, c->ay, c->az, do_grav, ns, c->S, c->sink_partial, c->ctr);
-  LAUNCH(k_sink_finalize, 1, 256, 0, nw, c->n_sink, c->sink_partial, c->S, c->dp.G, do_sinks);
+  if (nb > 0)
+    LAUNCH(k_gravity, nb, T, (size_t)(c->p.nq + 1) * 8, c->p0, c->p1, c->dp, c->nodes, (int)c->counts.n_nodes, s.x, s.y, s.z, s.h, s.m, c->d_gt,
+           c->ax, c->ay, c->az, do_grav, ns, c->S, c->sink_partial, c->ctr);
+  LAUNCH(k_sink_reduce, 1, 256, 0, nw, c->n_sink, c->sink_partial, c->S, do_sinks);
+  { int r_ = allreduce(c, c->S.ax, (size_t)3 * SPH_MAX_SINKS, NC_FLOAT64, NC_SUM); if (r_) return r_; }
+  LAUNCH(k_sink_pairs, 1, 32, 0, c->n_sink, c->S, c->dp.G, do_sinks);
   stage_end(c);
   return SPH_OK;
 }
@@ -335,10 +391,12 @@ int evaluate(sph_ctx* c, int mask) {
   if (mask & SPH_EVAL_DENSITY) { if ((r = run_density(c))) return r; }
   if ((r = run_gravity(c, (mask & SPH_EVAL_GRAVITY) ? 1 : 0, (mask & SPH_EVAL_SINKS) ? 1 : 0))) return r;
   if (mask & SPH_EVAL_SPH) { if ((r = run_force(c))) return r; }
+  else { double* bufs[3] = {c->ax, c->ay, c->az}; if ((r = allgatherv(c, bufs, 3))) return r; }
   return SPH_OK;
 }
 
 int fetch_counters(sph_ctx* c) {
+  { int r_ = allreduce(c, c->ctr, sizeof(WalkCounters) / 8, NC_UINT64, NC_SUM); if (r_) return r_; }
   CK(cudaMemcpyAsync(c->h_ctr, c->ctr, sizeof(WalkCounters), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   c->counts.n_gas = c->n;
@@ -391,9 +449,11 @@ int step(sph_ctx* c) {
   LAUNCH(k_kick<false>, cdiv(n, T), T, 0, n, state_of(c, c->cur), rates_of(c), c->sc);      // F:912
   LAUNCH(k_kick_sinks<false>, 1, SPH_MAX_SINKS, 0, c->S, c->sc);
   {
-    int nb = std::min(cdiv(n, T), c->n_partial);
-    LAUNCH(k_dt_partial, nb, T, 0, n, c->dp, state_of(c, c->cur), rates_of(c), c->cs, c->partial);   // F:916
-    LAUNCH(k_dt_final, 1, 32, 0, nb, c->partial, c->dp, c->sc, 1);                                   // F:914
+    int nb = std::max(1, std::min(cdiv(c->p1 - c->p0, T), c->n_partial));
+    LAUNCH(k_dt_partial, nb, T, 0, c->p0, c->p1, c->dp, state_of(c, c->cur), rates_of(c), c->cs, c->partial);   // F:916
+    LAUNCH(k_dt_fold, 1, 32, 0, nb, c->partial, c->sc);
+    { int r_ = allreduce(c, &c->sc->dt_min, 1, NC_FLOAT64, NC_MIN); if (r_) return r_; }
+    LAUNCH(k_dt_ladder, 1, 1, 0, c->dp, c->sc, 1);                                                   // F:914,855-859
   }
   stage_end(c);
   if (c->dp.variable_h) {
@@ -477,7 +537,9 @@ bool load_nccl(sph_ctx* c) {
   *(void**)&c->nccl.AllGather = dlsym(h, "ncclAllGather");
   *(void**)&c->nccl.Broadcast = dlsym(h, "ncclBroadcast");
   *(void**)&c->nccl.GetErrorString = dlsym(h, "ncclGetErrorString");
-  if (!c->nccl.CommInitRank || !c->nccl.AllGather) { c->err = "libnccl: missing symbols"; return false; }
+  *(void**)&c->nccl.GroupStart = dlsym(h, "ncclGroupStart");
+  *(void**)&c->nccl.GroupEnd = dlsym(h, "ncclGroupEnd");
+  if (!c->nccl.CommInitRank || !c->nccl.Broadcast || !c->nccl.AllReduce || !c->nccl.GroupStart || !c->nccl.GroupEnd) { c->err = "libnccl: missing symbols"; return false; }
   return true;
 }
 
@@ -579,7 +641,7 @@ int sph_comm_init(sph_ctx* c, int32_t rank, int32_t n_ranks, const void* uid) {
   NcclUid id; std::memcpy(&id, uid, 128);
   int r = c->nccl.CommInitRank(&c->comm, n_ranks, id, rank);
   if (r != 0) { c->err = std::string("ncclCommInitRank: ") + (c->nccl.GetErrorString ? c->nccl.GetErrorString(r) : "?"); return SPH_ERR_COMM; }
-  c->rank = rank; c->n_ranks = n_ranks;
+  c->rank = rank; c->n_ranks = n_ranks; c->tree_valid = false;
   return SPH_OK;
 }
 

@@ -28,7 +28,7 @@ __device__ __forceinline__ NodeRegs load_node(const GNode* __restrict__ nodes, i
 
 // layout of dynamic smem: grav table (nq+1 doubles)
 __global__ void __launch_bounds__(256, 4)
-k_gravity(int n, DevParams P, const GNode* __restrict__ nodes, int n_nodes,
+k_gravity(int p_begin, int p_end, DevParams P, const GNode* __restrict__ nodes, int n_nodes,
           const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
           const double* __restrict__ h, const double* __restrict__ m, const double* __restrict__ g_gt,
           double* __restrict__ ax, double* __restrict__ ay, double* __restrict__ az,
@@ -36,9 +36,9 @@ k_gravity(int n, DevParams P, const GNode* __restrict__ nodes, int n_nodes,
   extern __shared__ double gt[];
   for (int i = threadIdx.x; i <= P.nq; i += blockDim.x) gt[i] = g_gt[i];
   __syncthreads();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = p_begin + blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
-  const bool live = i < n;
+  const bool live = i < p_end;
   const double xi = live ? x[i] : 0.0, yi = live ? y[i] : 0.0, zi = live ? z[i] : 0.0;
   const double hi = live ? (P.variable_h ? h[i] : P.h_fixed) : 1.0;
   const double inv_h = 1.0 / hi;
@@ -83,7 +83,7 @@ k_gravity(int n, DevParams P, const GNode* __restrict__ nodes, int n_nodes,
     }
   }
   // direct sink <-> gas (unsoftened) F:567-576; per-warp partial sums of the sink side (no block barrier)
-  const int gwarp = i >> 5;
+  const int gwarp = (i - p_begin) >> 5;
   for (int s = 0; s < n_sink; ++s) {
     const double vx_ = xi - S.x[s], vy_ = yi - S.y[s], vz_ = zi - S.z[s];
     const double dr = sqrt(vx_ * vx_ + vy_ * vy_ + vz_ * vz_);
@@ -107,10 +107,9 @@ k_gravity(int n, DevParams P, const GNode* __restrict__ nodes, int n_nodes,
   if (lane == 0 && do_grav) { atomicAdd(&ctr->grav_opened, (unsigned long long)opened); atomicAdd(&ctr->grav_accepted, (unsigned long long)accepted); }
 }
 
-// fold per-warp sink partials in a fixed order (deterministic) and add sink-sink pairs F:578-590. One block of 256.
-__global__ void k_sink_finalize(int n_parts, int n_sink, const double* __restrict__ partial, SinkArrays S, double G, int do_sinks) {
+// fold per-warp sink partials in a fixed order (deterministic). One block of 256.
+__global__ void k_sink_reduce(int n_parts, int n_sink, const double* __restrict__ partial, SinkArrays S, int do_sinks) {
   __shared__ double red[256];
-  __shared__ double acc[SPH_MAX_SINKS][3];
   const int t = threadIdx.x;
   for (int s = 0; s < n_sink; ++s)
     for (int k = 0; k < 3; ++k) {
@@ -119,23 +118,23 @@ __global__ void k_sink_finalize(int n_parts, int n_sink, const double* __restric
       red[t] = v;
       __syncthreads();
       for (int o = 128; o > 0; o >>= 1) { if (t < o) red[t] += red[t + o]; __syncthreads(); }
-      if (t == 0) acc[s][k] = red[0];
+      if (t == 0) { double* a = (k == 0) ? S.ax : (k == 1) ? S.ay : S.az; a[s] = red[0]; }
       __syncthreads();
     }
-  if (t == 0) {
-    if (do_sinks && n_sink >= 2) {
-      for (int i = 0; i < n_sink; ++i)
-        for (int j = 0; j < i; ++j) {
-          double v[3] = {S.x[j] - S.x[i], S.y[j] - S.y[i], S.z[j] - S.z[i]};
-          double dr = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
-          double d3 = dr * dr * dr;
-          for (int k = 0; k < 3; ++k) {
-            double w = G * v[k] / d3;
-            acc[i][k] += S.m[j] * w;
-            acc[j][k] -= S.m[i] * w;
-          }
-        }
+}
+// sink-sink pairs F:578-590 (after the cross-rank sum of the gas contributions)
+__global__ void k_sink_pairs(int n_sink, SinkArrays S, double G, int do_sinks) {
+  if (threadIdx.x != 0 || !do_sinks || n_sink < 2) return;
+  for (int i = 0; i < n_sink; ++i)
+    for (int j = 0; j < i; ++j) {
+      double v[3] = {S.x[j] - S.x[i], S.y[j] - S.y[i], S.z[j] - S.z[i]};
+      double dr = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+      double d3 = dr * dr * dr;
+      double* A[3] = {S.ax, S.ay, S.az};
+      for (int k = 0; k < 3; ++k) {
+        double w = G * v[k] / d3;
+        A[k][i] += S.m[j] * w;
+        A[k][j] -= S.m[i] * w;
+      }
     }
-    for (int s = 0; s < n_sink; ++s) { S.ax[s] = acc[s][0]; S.ay[s] = acc[s][1]; S.az[s] = acc[s][2]; }
-  }
 }

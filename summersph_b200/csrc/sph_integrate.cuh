@@ -49,10 +49,10 @@ __global__ void k_kick_sinks(SinkArrays S, const SimScalars* sc) {
 }
 
 // timestep candidates: F:845-851. fmin drops NaNs like gfortran's MINVAL.
-__global__ void k_dt_partial(int n, DevParams P, StateArrays s, RateArrays r, const double* __restrict__ cs,
+__global__ void k_dt_partial(int p_begin, int p_end, DevParams P, StateArrays s, RateArrays r, const double* __restrict__ cs,
                              double* __restrict__ partial) {
   double mn = INFINITY;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+  for (int i = p_begin + blockIdx.x * blockDim.x + threadIdx.x; i < p_end; i += gridDim.x * blockDim.x) {
     const double vx = s.vx[i], vy = s.vy[i], vz = s.vz[i];
     const double ax = r.ax[i], ay = r.ay[i], az = r.az[i];
     const double vv = __dadd_rn(__dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy)), __dmul_rn(vz, vz));
@@ -76,20 +76,21 @@ __global__ void k_dt_partial(int n, DevParams P, StateArrays s, RateArrays r, co
   }
 }
 
-// fold + the x1.5 / x0.5 ladder F:855-859; also t = t + dt (F:914). One warp.
-__global__ void k_dt_final(int nblocks, const double* __restrict__ partial, DevParams P, SimScalars* sc, int advance_time) {
+// fold the block minima of this rank's slice. One warp.
+__global__ void k_dt_fold(int nblocks, const double* __restrict__ partial, SimScalars* sc) {
   double mn = INFINITY;
   for (int b = threadIdx.x; b < nblocks; b += 32) mn = fmin(mn, partial[b]);
   mn = warp_min(mn);
-  if (threadIdx.x == 0) {
-    sc->dt_min = mn;
-    double dt = sc->dt;
-    if (advance_time) sc->t = sc->t + dt;
-    const double cand = mn * P.tscale;
-    if (cand > 2.0 * dt && 1.5 * dt < P.lit_01) dt = 1.5 * dt;
-    else if (cand < 0.5 * dt && dt * 0.5 > P.lit_1em4) dt = 0.5 * dt;
-    sc->dt = dt;
-  }
+  if (threadIdx.x == 0) sc->dt_min = mn;
+}
+// the x1.5 / x0.5 ladder F:855-859 on the global minimum; also t = t + dt (F:914)
+__global__ void k_dt_ladder(DevParams P, SimScalars* sc, int advance_time) {
+  double dt = sc->dt;
+  if (advance_time) sc->t = sc->t + dt;
+  const double cand = sc->dt_min * P.tscale;
+  if (cand > 2.0 * dt && 1.5 * dt < P.lit_01) dt = 1.5 * dt;
+  else if (cand < 0.5 * dt && dt * 0.5 > P.lit_1em4) dt = 0.5 * dt;
+  sc->dt = dt;
 }
 
 // V:559-560 first (lowest number) particle with m (eta/h)^3 > 0.5

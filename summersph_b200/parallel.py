@@ -1,0 +1,33 @@
+"""Multi-GPU plumbing: one process (or thread) per GPU, NCCL communicator owned by the engine.
+
+Design: the particle set is replicated on every rank (64M particles need ~26 GB of
+the 180 GB), the tree is built redundantly, and the expensive target work — density, gravity, SPH pair
+forces, h iteration — is sharded by contiguous Morton slices of walk groups; results travel with an
+all-gather-v over NVLink, the sink sums and the dt minimum with all-reduces.  Every rank therefore holds
+bit-identical state after each step, and an N-rank run is bit-identical to the 1-rank run.
+"""
+
+
+def slice_bounds(n_groups, rank, world):
+    """Group slice [g0, g1) of `rank` — the same integer arithmetic as compute_slices() in sph_engine.cu."""
+    return (n_groups * rank) // world, (n_groups * (rank + 1)) // world
+
+
+def init_comm(engine, rank, world, broadcast_bytes):
+    """Create the engine's NCCL communicator. `broadcast_bytes(b: bytes|None) -> bytes` must return rank 0's
+    payload on every rank (torch.distributed, MPI, a pipe ...)."""
+    if world <= 1:
+        return
+    uid = engine.unique_id() if rank == 0 else None
+    uid = broadcast_bytes(uid)
+    if not isinstance(uid, (bytes, bytearray)) or len(uid) != 128:
+        raise ValueError("unique id broadcast failed")
+    engine.comm_init(rank, world, bytes(uid))
+
+
+def torch_broadcast_bytes(payload, src=0):
+    """broadcast_bytes implementation on top of an initialised torch.distributed process group."""
+    import torch.distributed as dist
+    box = [payload]
+    dist.broadcast_object_list(box, src=src)
+    return box[0]
