@@ -1,0 +1,195 @@
+! run_sph_b200.f90 -- Fortran host for the B200 SPH step engine (ISO_C_BINDING over include/sph_b200.h).
+!
+! Keeps the reference's program shell: `program run_sph`, read_data_from_file, read_params_from_file,
+! make_save, the `do while (t < end_time)` loop, the per-step print and the save cadence
+! (SUMMER_SPH.f90:594-738, 863-955 | "SUMMER_SPH - Variable.f90":729-942, 1076-1191).  The loop body
+! (F:886-928 | V:1120-1162) is ONE call: sph_step.
+!
+! NOT COMPILED IN THE BUILD IMAGE (no gfortran/flang/nvfortran there, SURVEY.md 8(c)); the C++ twin
+! host/run_sph.cpp exercises the same entry points.  Build where a compiler exists:
+!     make -C host run_sph_b200
+module sph_b200_c
+  use, intrinsic :: iso_c_binding
+  implicit none
+
+  integer(c_int32_t), parameter :: SPH_MODE_FIXED_H = 0, SPH_MODE_VARIABLE_H = 1
+
+  type, bind(C) :: sph_params          ! mirrors `struct sph_params` (and V's type(param), V:54-64)
+    integer(c_int32_t) :: mode, max_depth, nq, n_ranks
+    real(c_double)     :: h_fixed, bounding_size, theta, gamma, eta, convergence_criteria
+    real(c_double)     :: max_length, timestep_scale, end_time, sink_radius
+    integer(c_int32_t) :: theta_override, reserved
+  end type sph_params
+
+  interface
+    integer(c_int) function sph_default_params(mode, p) bind(C, name="sph_default_params")
+      import :: c_int, c_int32_t, sph_params
+      integer(c_int32_t), value :: mode
+      type(sph_params), intent(out) :: p
+    end function
+    integer(c_int) function sph_create(p, device, ctx) bind(C, name="sph_create")
+      import :: c_int, c_int32_t, c_ptr, sph_params
+      type(sph_params), intent(in) :: p
+      integer(c_int32_t), value :: device
+      type(c_ptr), intent(out) :: ctx
+    end function
+    integer(c_int) function sph_destroy(ctx) bind(C, name="sph_destroy")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: ctx
+    end function
+    function sph_last_error(ctx) result(msg) bind(C, name="sph_last_error")
+      import :: c_ptr
+      type(c_ptr), value :: ctx
+      type(c_ptr) :: msg
+    end function
+    integer(c_int) function sph_upload(ctx, n_gas, x, y, z, vx, vy, vz, u, m, alpha, h, n_sink, &
+                                       sx, sy, sz, svx, svy, svz, sm, srad) bind(C, name="sph_upload")
+      import :: c_int, c_int32_t, c_int64_t, c_double, c_ptr
+      type(c_ptr), value :: ctx
+      integer(c_int64_t), value :: n_gas
+      real(c_double), intent(in) :: x(*), y(*), z(*), vx(*), vy(*), vz(*), u(*), m(*), alpha(*), h(*)
+      integer(c_int32_t), value :: n_sink
+      real(c_double), intent(in) :: sx(*), sy(*), sz(*), svx(*), svy(*), svz(*), sm(*), srad(*)
+    end function
+    integer(c_int) function sph_step(ctx, dt, t, n_gas, n_sink) bind(C, name="sph_step")
+      import :: c_int, c_int32_t, c_int64_t, c_double, c_ptr
+      type(c_ptr), value :: ctx
+      real(c_double), intent(inout) :: dt, t
+      integer(c_int64_t), intent(out) :: n_gas
+      integer(c_int32_t), intent(out) :: n_sink
+    end function
+    integer(c_int) function sph_sizes(ctx, n_gas, n_sink) bind(C, name="sph_sizes")
+      import :: c_int, c_int32_t, c_int64_t, c_ptr
+      type(c_ptr), value :: ctx
+      integer(c_int64_t), intent(out) :: n_gas
+      integer(c_int32_t), intent(out) :: n_sink
+    end function
+    integer(c_int) function sph_download(ctx, x, y, z, vx, vy, vz, u, m, alpha, h, &
+                                         sx, sy, sz, svx, svy, svz, sm, srad) bind(C, name="sph_download")
+      import :: c_int, c_double, c_ptr
+      type(c_ptr), value :: ctx
+      real(c_double), intent(out) :: x(*), y(*), z(*), vx(*), vy(*), vz(*), u(*), m(*), alpha(*), h(*)
+      real(c_double), intent(out) :: sx(*), sy(*), sz(*), svx(*), svy(*), svz(*), sm(*), srad(*)
+    end function
+  end interface
+end module sph_b200_c
+
+program run_sph
+  use, intrinsic :: iso_c_binding
+  use sph_b200_c
+  implicit none
+  integer, parameter :: dp = kind(1.0d0)
+  character(len=256) :: filename, header_line
+  type(sph_params) :: p
+  type(c_ptr) :: ctx
+  real(dp), allocatable :: x(:), y(:), z(:), vx(:), vy(:), vz(:), u(:), m(:), alpha(:), h(:)
+  real(dp), allocatable :: sx(:), sy(:), sz(:), svx(:), svy(:), svz(:), sm(:), srad(:)
+  real(dp), allocatable :: row(:,:)
+  real(dp) :: t, dt, v(10)
+  integer :: status, num_lines, i, nb, ns, t_test, rc, ncol
+  integer(c_int64_t) :: n_gas
+  integer(c_int32_t) :: n_sink
+  logical :: variable
+
+  variable = (command_argument_count() >= 1)          ! any argument selects the variable-h reference
+  filename = merge('disc_20k_low_vel.txt', 'disc_12000_2.txt    ', variable)     ! V:1181 | F:946
+  rc = sph_default_params(merge(SPH_MODE_VARIABLE_H, SPH_MODE_FIXED_H, variable), p)
+  ncol = merge(10, 8, variable)
+
+  ! ---- read_data_from_file (F:594-716): header skipped, first pass counts records, second pass reads
+  open(unit=10, file=trim(filename), status='old', action='read', iostat=status)
+  if (status /= 0) then
+    write(*,*) 'Error opening file: ', trim(filename); stop 1
+  end if
+  read(10, '(A)', iostat=status) header_line
+  num_lines = 0
+  do
+    read(10, *, iostat=status)
+    if (status /= 0) exit
+    num_lines = num_lines + 1
+  end do
+  close(10)
+  allocate(row(10, num_lines)); row = 0.0_dp
+  open(unit=10, file=trim(filename), status='old', action='read')
+  read(10, '(A)') header_line
+  do i = 1, num_lines
+    v = 0.0_dp
+    read(10, *, iostat=status) v(1:ncol)
+    row(:, i) = v
+    if (status /= 0) exit                              ! trailing 8-column sink rows in V (SURVEY.md 5)
+  end do
+  close(10)
+  nb = count(row(7, :) /= 0.0_dp); ns = count(row(7, :) == 0.0_dp)
+  allocate(x(nb), y(nb), z(nb), vx(nb), vy(nb), vz(nb), u(nb), m(nb), alpha(nb), h(nb))
+  allocate(sx(max(ns,1)), sy(max(ns,1)), sz(max(ns,1)), svx(max(ns,1)), svy(max(ns,1)), svz(max(ns,1)), sm(max(ns,1)), srad(max(ns,1)))
+  nb = 0; ns = 0
+  do i = 1, num_lines
+    if (row(7, i) /= 0.0_dp) then
+      nb = nb + 1
+      x(nb) = row(1, i); y(nb) = row(2, i); z(nb) = row(3, i)
+      vx(nb) = row(4, i); vy(nb) = row(5, i); vz(nb) = row(6, i)
+      u(nb) = row(7, i); m(nb) = row(8, i)
+      alpha(nb) = merge(row(9, i), 0.0_dp, variable)   ! F:681
+      h(nb) = merge(row(10, i), p%h_fixed, variable)
+    else
+      ns = ns + 1
+      sx(ns) = row(1, i); sy(ns) = row(2, i); sz(ns) = row(3, i)
+      svx(ns) = row(4, i); svy(ns) = row(5, i); svz(ns) = row(6, i)
+      sm(ns) = row(8, i); srad(ns) = p%sink_radius      ! F:694 | V:830
+    end if
+  end do
+  write(*,*) 'Successfully read ', nb, ' bodies and ', max(ns, 1), ' sinks from ', trim(filename), '.'
+
+  ! ---- simulate (F:863-930): the loop body is one call into the engine
+  rc = sph_create(p, 0_c_int32_t, ctx)
+  if (rc /= 0) stop 'sph_create failed (no CUDA device? there is no CPU fallback)'
+  rc = sph_upload(ctx, int(nb, c_int64_t), x, y, z, vx, vy, vz, u, m, alpha, h, int(ns, c_int32_t), &
+                  sx, sy, sz, svx, svy, svz, sm, srad)
+  if (rc /= 0) stop 'sph_upload failed'
+  t = 0.0_dp; dt = 1.0e-2_dp; t_test = 0                 ! F:871-875
+  n_gas = nb
+  do while (t < p%end_time)                              ! F:879
+    if (t > t_test * p%end_time / 1000) then             ! F:881 (t_list(0) := 0)
+      call make_save(t_test)
+      t_test = t_test + 1
+    end if
+    print *, "SPH Particles:", n_gas, "dt :", dt, "time : ", t      ! F:891
+    rc = sph_step(ctx, dt, t, n_gas, n_sink)
+    if (rc /= 0) stop 'sph_step failed'
+  end do
+  rc = sph_destroy(ctx)
+
+contains
+
+  subroutine make_save(number)                           ! F:719-738 | V:921-942
+    integer, intent(in) :: number
+    integer :: io, k
+    integer(c_int64_t) :: ng
+    integer(c_int32_t) :: nsk
+    character(len=256) :: savename
+    real(dp), allocatable :: a(:,:), s(:,:)
+    rc = sph_sizes(ctx, ng, nsk)
+    allocate(a(ng, 10), s(max(nsk, 1), 8))
+    rc = sph_download(ctx, a(:,1), a(:,2), a(:,3), a(:,4), a(:,5), a(:,6), a(:,7), a(:,8), a(:,9), a(:,10), &
+                      s(:,1), s(:,2), s(:,3), s(:,4), s(:,5), s(:,6), s(:,7), s(:,8))
+    write(savename, '(A,I0,A)') 'save', number, '.txt'
+    open(newunit=io, file=savename, status="new", action="write")
+    if (variable) then
+      write(io, *) 'x  ','y  ','z  ','vx  ','vy ','vz ','energy ','mass  ','alpha  ', 'smoothing'
+    else
+      write(io, *) 'x  ','y  ','z  ','vx  ','vy ','vz ','energy ','mass  ','alpha  '
+    end if
+    do k = 1, int(ng)
+      if (variable) then
+        write(io, *) a(k, 1:10)
+      else
+        write(io, *) a(k, 1:9)
+      end if
+    end do
+    do k = 1, nsk
+      write(io, *) s(k, 1:6), 0.0_dp, s(k, 7)
+    end do
+    close(io)
+  end subroutine make_save
+
+end program run_sph
