@@ -149,28 +149,37 @@ struct DensityOp {
   __device__ __forceinline__ void consume(int count) {
     unsigned mask = 0;
     if (active) {
+#pragma unroll 4
       for (int k = 0; k < count; ++k) {
-        double R = sR[k];
-        bool in = (fabs(xi - scx[k]) < R) && (fabs(yi - scy[k]) < R) && (fabs(zi - scz[k]) < R);   // F:443 | V:479
+        const double R = sR[k];
+        const bool in = (fabs(xi - scx[k]) < R) & (fabs(yi - scy[k]) < R) & (fabs(zi - scz[k]) < R);   // F:443 | V:479
         mask |= (in ? 1u : 0u) << k;
       }
     }
     cand += __popc(mask);
+    // two hits per trip, branch-free, so two independent dependency chains are in flight per lane
+    double w2 = 0.0, b2 = 0.0;
     while (mask) {
-      int k = __ffs(mask) - 1; mask &= mask - 1;
-      double dx = xi - sx[k], dy = yi - sy[k], dz = zi - sz[k];
-      const double r2 = dx * dx + dy * dy + dz * dz;
-      double r, rs; fast_sqrt_rsqrt(r2, r, rs);
-      if (r2 == 0.0) r = 0.0;                                            // self term, W(0)
-      double q = r * inv_h;
-      if (q <= 2.0) {
-        double w, dw; table_lerp(wt, dwt, nq, dq, inv_dq, q, w, dw);
-        double mj = sm[k];
-        accW += mj * w;
-        accB += mj * (r * dw);
-        ++contrib;
-      }
+      const int k0 = __ffs(mask) - 1; mask &= mask - 1;
+      const bool v1 = mask != 0;
+      const int k1 = v1 ? __ffs(mask) - 1 : k0; mask &= mask - 1;
+      term(k0, true, accW, accB);
+      term(k1, v1, w2, b2);
     }
+    accW += w2; accB += b2;
+  }
+  __device__ __forceinline__ void term(int k, bool valid, double& aW, double& aB) {
+    const double dx = xi - sx[k], dy = yi - sy[k], dz = zi - sz[k];
+    const double r2 = dx * dx + dy * dy + dz * dz;
+    double r, rs; fast_sqrt_rsqrt(r2, r, rs);
+    r = (r2 == 0.0) ? 0.0 : r;                                           // self term, W(0)
+    const double q = r * inv_h;
+    const bool in = valid & (q <= 2.0);
+    double w, dw; table_lerp(wt, dwt, nq, dq, inv_dq, in ? q : 0.0, w, dw);
+    const double mj = in ? sm[k] : 0.0;
+    aW += mj * w;
+    aB += mj * (r * dw);
+    contrib += in ? 1u : 0u;
   }
 };
 
@@ -327,58 +336,67 @@ struct ForceOp {
   __device__ __forceinline__ void consume(int count) {
     unsigned mask = 0;
     if (live) {
+#pragma unroll 4
       for (int k = 0; k < count; ++k) {
+        // idj < idi: i is the higher-numbered `body`: is x_i inside Box(j)?   F:351-354 | V:380-383
+        // idj > idi: j is the `body` that visits i: is x_j inside Box(i)?   (Box(i) is empty when R_i = -1)
         const int idj = tid[k];
-        bool in;
-        if (idj < idi) {          // i is the higher-numbered `body`: is x_i inside Box(j)?   F:351-354 | V:380-383
-          const double R = t[16 * WALK_TILE + k];
-          in = (fabs(xi - t[13 * WALK_TILE + k]) < R) && (fabs(yi - t[14 * WALK_TILE + k]) < R) && (fabs(zi - t[15 * WALK_TILE + k]) < R);
-        } else if (idj > idi) {   // j is the `body` that visits i: is x_j inside Box(i)?
-          in = (Ri > 0.0) && (fabs(t[0 * WALK_TILE + k] - cxi) < Ri) && (fabs(t[1 * WALK_TILE + k] - cyi) < Ri) && (fabs(t[2 * WALK_TILE + k] - czi) < Ri);
-        } else in = false;
+        const bool lt = idj < idi;
+        const double px = lt ? xi : t[0 * WALK_TILE + k], py = lt ? yi : t[1 * WALK_TILE + k], pz = lt ? zi : t[2 * WALK_TILE + k];
+        const double cx = lt ? t[13 * WALK_TILE + k] : cxi, cy = lt ? t[14 * WALK_TILE + k] : cyi, cz = lt ? t[15 * WALK_TILE + k] : czi;
+        const double R = lt ? t[16 * WALK_TILE + k] : Ri;
+        const bool in = (idj != idi) & (fabs(px - cx) < R) & (fabs(py - cy) < R) & (fabs(pz - cz) < R);
         mask |= (in ? 1u : 0u) << k;
       }
     }
     pairs += __popc(mask);
     while (mask) {
       const int k = __ffs(mask) - 1; mask &= mask - 1;
-      const double nx = xi - t[0 * WALK_TILE + k], ny = yi - t[1 * WALK_TILE + k], nz = zi - t[2 * WALK_TILE + k];   // F:356
-      const double wx = vxi - t[3 * WALK_TILE + k], wy = vyi - t[4 * WALK_TILE + k], wz = vzi - t[5 * WALK_TILE + k]; // F:358
-      const double r2 = nx * nx + ny * ny + nz * nz;
-      double dr, inv_dr; fast_sqrt_rsqrt(r2, dr, inv_dr);                 // dr == 0 -> NaN like F:363
-      const double rv = wx * nx + wy * ny + wz * nz;
-      const double vdotr = rv >= 0.0 ? 0.0 : rv;                          // F:361
-      const double mj = t[6 * WALK_TILE + k], hj = t[7 * WALK_TILE + k];
-      // kernel gradient magnitudes dW/dr at h_i and h_j                                   F:366 | V:395-396
-      double dWi = 0.0, dWj = 0.0;
-      {
-        const double q = dr * inv_hi;
-        if (q <= 2.0) dWi = table_lerp1(dwt, nq, dq, inv_dq, q) * inv_n4i;
-      }
-      if (variable_h) {
-        const double q = dr * t[17 * WALK_TILE + k];
-        if (q <= 2.0) dWj = table_lerp1(dwt, nq, dq, inv_dq, q) * t[8 * WALK_TILE + k];
-      } else dWj = dWi;
-      const double hbar = variable_h ? (hi + hj) / 2.0 : hi;              // V:402
-      const double nu = (hbar * vdotr) * fast_rcp(r2 + lit_001 * hbar * hbar);   // F:373 | V:405
-      const double cbar = 0.5 * (ci + t[10 * WALK_TILE + k]);
-      const double abar = 0.5 * (alphai + t[11 * WALK_TILE + k]);
-      const double visc = (-abar * cbar * nu + 2.0 * abar * nu * nu) * fast_rcp(0.5 * (rhoi + t[9 * WALK_TILE + k]));   // F:378 | V:410
-      const double por2j = t[12 * WALK_TILE + k];
-      const double rvn = rv * inv_dr;                                     // n_hat . v_ij
-      double scal, vdg;
-      if (variable_h) {
-        vdg = (dWi * rvn + dWj * rvn) / 2.0;                              // V:401
-        scal = (por2i * dWi + por2j * dWj) + visc * (dWi + dWj) / 2.0;    // V:413-414
-      } else {
-        vdg = dWi * rvn;                                                  // F:370
-        scal = ((por2i + por2j) + visc) * dWi;                            // F:381-382
-      }
-      const double f = mj * scal * inv_dr;
-      ax -= f * nx; ay -= f * ny; az -= f * nz;                           // F:383 (own side)
-      ud += mj * vdg * (por2i + 0.5 * visc);                              // F:387 | V:419-421
-      ad += mj * vdg;                                                     // F:390
+      double f, u, a;
+      pair(k, f, u, a);
+      ax -= f * (xi - t[0 * WALK_TILE + k]);                            // F:383 (own side)
+      ay -= f * (yi - t[1 * WALK_TILE + k]);
+      az -= f * (zi - t[2 * WALK_TILE + k]);
+      ud += u; ad += a;
     }
+  }
+  // one pair (i, slot k): f = m_j * A / dr  (a_i -= f * (x_i - x_j)), u = du/dt term, a = alpha-rate term
+  __device__ __forceinline__ void pair(int k, double& f, double& u, double& a) const {
+    const double nx = xi - t[0 * WALK_TILE + k], ny = yi - t[1 * WALK_TILE + k], nz = zi - t[2 * WALK_TILE + k];   // F:356
+    const double wx = vxi - t[3 * WALK_TILE + k], wy = vyi - t[4 * WALK_TILE + k], wz = vzi - t[5 * WALK_TILE + k]; // F:358
+    const double r2 = nx * nx + ny * ny + nz * nz;
+    double dr, inv_dr; fast_sqrt_rsqrt(r2, dr, inv_dr);                 // dr == 0 -> NaN like F:363
+    const double rv = wx * nx + wy * ny + wz * nz;
+    const double vdotr = rv >= 0.0 ? 0.0 : rv;                          // F:361
+    const double mj = t[6 * WALK_TILE + k], hj = t[7 * WALK_TILE + k];
+    // kernel gradient magnitudes dW/dr at h_i and h_j                                   F:366 | V:395-396
+    const double qi = dr * inv_hi;
+    const bool ini = qi <= 2.0;
+    const double dWi = ini ? table_lerp1(dwt, nq, dq, inv_dq, qi) * inv_n4i : ((qi != qi) ? qi : 0.0);
+    double dWj = dWi;
+    if (variable_h) {
+      const double qj = dr * t[17 * WALK_TILE + k];
+      const bool inj = qj <= 2.0;
+      dWj = inj ? table_lerp1(dwt, nq, dq, inv_dq, qj) * t[8 * WALK_TILE + k] : 0.0;
+    }
+    const double hbar = variable_h ? (hi + hj) / 2.0 : hi;              // V:402
+    const double nu = (hbar * vdotr) * fast_rcp(r2 + lit_001 * hbar * hbar);   // F:373 | V:405
+    const double cbar = 0.5 * (ci + t[10 * WALK_TILE + k]);
+    const double abar = 0.5 * (alphai + t[11 * WALK_TILE + k]);
+    const double visc = (-abar * cbar * nu + 2.0 * abar * nu * nu) * fast_rcp(0.5 * (rhoi + t[9 * WALK_TILE + k]));   // F:378 | V:410
+    const double por2j = t[12 * WALK_TILE + k];
+    const double rvn = rv * inv_dr;                                     // n_hat . v_ij
+    double scal, vdg;
+    if (variable_h) {
+      vdg = (dWi * rvn + dWj * rvn) / 2.0;                              // V:401
+      scal = (por2i * dWi + por2j * dWj) + visc * (dWi + dWj) / 2.0;    // V:413-414
+    } else {
+      vdg = dWi * rvn;                                                  // F:370
+      scal = ((por2i + por2j) + visc) * dWi;                            // F:381-382
+    }
+    f = mj * scal * inv_dr;
+    u = mj * vdg * (por2i + 0.5 * visc);                                // F:387 | V:419-421
+    a = mj * vdg;                                                       // F:390
   }
 };
 
