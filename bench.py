@@ -132,6 +132,7 @@ def main():
     ap.add_argument("--ref-particles", type=int, default=200_000)
     ap.add_argument("--cpu-baseline-particles", type=int, default=100_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (large multi-GPU sizing runs)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -197,13 +198,21 @@ def main():
     counters = e.counters()
     n_now, ns_now = e.sizes()
     tm = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    per_rank = [ms]
     if world > 1:
+        allms = [torch.zeros_like(tm) for _ in range(world)]
+        dist.all_gather(allms, tm)
+        per_rank = [float(x.item()) for x in allms]
+        walk = torch.tensor([stage_acc.get("density", 0) + stage_acc.get("gravity", 0) + stage_acc.get("sph", 0)], dtype=torch.float64, device="cuda")
+        allw = [torch.zeros_like(walk) for _ in range(world)]
+        dist.all_gather(allw, walk)
+        per_rank_walk = [float(x.item()) / args.steps for x in allw]
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
     ms = float(tm.item())
     value = n * args.steps / (ms * 1e-3)
 
     # ---- end to end through the C-ABI with host buffers ("e2e") -----------------------------------------
-    e2e_steps = max(1, min(args.steps, 3))
+    e2e_steps = 0 if args.no_e2e else max(1, min(args.steps, 3))
     barrier()
     t0 = time.perf_counter()
     dt2, t2 = 0.01, 0.0
@@ -216,7 +225,7 @@ def main():
     te = torch.tensor([e2e_sec], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = n * e2e_steps / float(te.item())
+    e2e_value = n * e2e_steps / float(te.item()) if e2e_steps else None
     h2d = 10 * 8 * n + 8 * 8 * len(s)
     d2h = 10 * 8 * n + 8 * 8 * len(s) + 4 * n        # + the id array used to restore ascending-number order
 
@@ -227,8 +236,15 @@ def main():
         per_launch = {"sph": (BYTES_SPH_PER_LAUNCH, "k_force"), "density": (BYTES_DENSITY_PER_LAUNCH, "k_density"), "gravity": (BYTES_GRAVITY_PER_LAUNCH, "k_gravity")}
         dom = max(per_launch, key=lambda k: stage_acc.get(k, 0.0))
         dom_ms = stage_acc[dom] / (2 * args.steps)           # two launches per step
-        achieved = per_launch[dom][0] * n / (dom_ms * 1e-3) / 1e9
-        fp64_peak = e.fp64_peak()
+        achieved = per_launch[dom][0] * (n / world) / (dom_ms * 1e-3) / 1e9       # per-rank launch processes n/world targets
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+            # ncu capture was taken at tr["particles"]; DRAM traffic of the walk kernels scales with N
+            traffic = tr["dram_bytes_per_launch"][per_launch[dom][1]] / tr["particles"] * n / max(world, 1)
+        except Exception:
+            pass
+        fp64_peak = e.fp64_peak() * world
         flops_eval = (counters["density_candidates"] * FLOPS["density_candidate"] + counters["sph_pairs"] * FLOPS["sph_pair"]
                       + counters["grav_opened"] * FLOPS["grav_opened"] + counters["grav_accepted"] * FLOPS["grav_accepted"]
                       + n * ns_now * FLOPS["sink_gas"])
@@ -245,7 +261,7 @@ def main():
                     "steps": e2e_steps, "what": "sph_upload (pinned host SoA) + sph_step + sph_download (ascending number order) per step"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": per_launch[dom][1], "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / hbm_peak, "traffic": traffic, "traffic_note": "bytes/launch; dram__bytes_read+write from the 2M-particle ncu capture scaled linearly to this N", "peak_source": peak_src,
                          "algorithmic_bytes_per_particle_per_launch": per_launch[dom][0], "launch_ms": dom_ms,
                          "note": "walk kernels are FP64-pipe / latency bound (SURVEY.md §8(d)); see fp64"},
             "fp64": {"achieved_tflops": step_flops / (ms / args.steps * 1e-3) / 1e12, "peak_tflops": fp64_peak,
@@ -254,8 +270,11 @@ def main():
             "hbm_step": {"achieved": BYTES_PER_PARTICLE_STEP * n / (ms / args.steps * 1e-3) / 1e9, "peak": hbm_peak,
                          "frac": BYTES_PER_PARTICLE_STEP * n / (ms / args.steps * 1e-3) / 1e9 / hbm_peak, "unit": "GB/s"},
             "stage_ms_per_step": {k: v / args.steps for k, v in stage_acc.items()},
+            "per_rank_ms_per_step": [v / args.steps for v in per_rank],
             "counters": counters,
         }
+        if world > 1:
+            line["per_rank_walk_ms_per_step"] = per_rank_walk
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1
             nb = args.cpu_baseline_particles

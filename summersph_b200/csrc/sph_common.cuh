@@ -12,7 +12,8 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
-#define SPH_KEY_LEVELS 21          // 3 bits per level in a 63-bit descent key
+#define SPH_KEY_LEVELS 21          // 3 bits per level in a 63-bit descent key word
+#define SPH_KEY_LEVELS2 42         // two key words: levels 22..42 live in the second word (slow path)
 #define SPH_CHUNK 32               // particles per BVH leaf chunk = one warp of targets
 #define SPH_BVH_FAN 8
 #define SPH_MAX_SINKS 64
@@ -22,8 +23,8 @@ struct DevParams {
   int    variable_h;     // V mode
   int    soft_hi;        // T:298 softening
   int    nq;
-  int    lmax;           // min(max_depth, SPH_KEY_LEVELS)
-  int    depth_unbounded;// max_depth > SPH_KEY_LEVELS: equal keys are an error instead of a depth-limited leaf
+  int    lmax;           // min(max_depth, levels the key can hold: 21, or 42 on the two-word slow path)
+  int    depth_unbounded;// max_depth > lmax: particles sharing a full key are NOT a depth-limited leaf of the reference
   double dq, inv_dq;
   double h_fixed;
   double pi_norm;        // F:125 3.14159265359_dp | V:7 real(4) pi
@@ -60,6 +61,24 @@ __device__ __forceinline__ int lcp_levels(uint64_t a, uint64_t b, int lmax) {
   if (x == 0) return lmax;
   int l = (__clzll((long long)x) - 1) / 3;
   return l < lmax ? l : lmax;
+}
+
+// two-word keys: `lo` may be null (single-word fast path)
+__device__ __forceinline__ int lcp_levels2(uint64_t ha, uint64_t la, uint64_t hb, uint64_t lb, int lmax) {
+  uint64_t x = ha ^ hb;
+  int l;
+  if (x != 0) l = (__clzll((long long)x) - 1) / 3;
+  else {
+    uint64_t y = la ^ lb;
+    if (y == 0) return lmax;
+    l = SPH_KEY_LEVELS + (__clzll((long long)y) - 1) / 3;
+  }
+  return l < lmax ? l : lmax;
+}
+// octal digit of descent level l (0-based: l = 0 is the root's split)
+__device__ __forceinline__ int key_digit(uint64_t hi, uint64_t lo, int l) {
+  return l < SPH_KEY_LEVELS ? (int)((hi >> (3 * (SPH_KEY_LEVELS - 1 - l))) & 7)
+                            : (int)((lo >> (3 * (SPH_KEY_LEVELS2 - 1 - l))) & 7);
 }
 
 // Reciprocal / square root without the IEEE slow-path subroutine: MUFU seed (~2^-20) + two FMA Newton /

@@ -54,7 +54,7 @@ struct sph_ctx {
   double *rho = nullptr, *omega = nullptr, *prs = nullptr, *cs = nullptr, *por2 = nullptr;
   double *ax = nullptr, *ay = nullptr, *az = nullptr, *udot = nullptr, *adot = nullptr;
   // tree
-  uint64_t* key[2] = {}; int* perm[2] = {}; int* level = nullptr;
+  uint64_t* key[2] = {}; uint64_t* key_lo[2] = {}; bool two_word = false; int* perm[2] = {}; int* level = nullptr;
   double *lcx = nullptr, *lcy = nullptr, *lcz = nullptr, *reach = nullptr;
   BvhBox* bvh = nullptr; size_t bvh_cap = 0; BvhInfo bi;
   int *node_count = nullptr, *gsize = nullptr, *gfirst = nullptr; int2* groups = nullptr; int n_groups = 0;
@@ -140,6 +140,7 @@ int ensure_capacity(sph_ctx* c, int64_t n) {
   c->cub_bytes = std::max(std::max(b1, b4), std::max(b2, b3)) + 256;
   if (c->cub_tmp) { cudaFree(c->cub_tmp); c->cub_tmp = nullptr; }
   if (cudaMalloc(&c->cub_tmp, c->cub_bytes) != cudaSuccess) { c->err = "cudaMalloc(cub temp)"; cudaGetLastError(); return SPH_ERR_OOM; }
+  for (int b = 0; b < 2; ++b) if (c->key_lo[b]) { cudaFree(c->key_lo[b]); c->key_lo[b] = nullptr; }
   c->cap = cap;
   return SPH_OK;
 }
@@ -149,8 +150,9 @@ void make_dev_params(sph_ctx* c) {
   d.variable_h = (p.mode & SPH_MODE_VARIABLE_H) ? 1 : 0;
   d.soft_hi = (p.mode & SPH_FLAG_SOFT_USES_HI) ? 1 : 0;
   d.nq = p.nq;
-  d.lmax = p.max_depth < SPH_KEY_LEVELS ? p.max_depth : SPH_KEY_LEVELS;
-  d.depth_unbounded = p.max_depth > SPH_KEY_LEVELS;
+  const int key_cap = c->two_word ? SPH_KEY_LEVELS2 : SPH_KEY_LEVELS;
+  d.lmax = p.max_depth < key_cap ? p.max_depth : key_cap;
+  d.depth_unbounded = p.max_depth > key_cap;
   d.dq = 2.0 / p.nq; d.inv_dq = 1.0 / d.dq;
   d.h_fixed = p.h_fixed;
   d.pi_norm = d.variable_h ? (double)3.1415926535897932f : 3.14159265359;      // V:7 | F:125
@@ -231,9 +233,28 @@ int compute_slices(sph_ctx* c) {
 // ---------------------------------------------------------------------------------------------------
 // tree
 // ---------------------------------------------------------------------------------------------------
+int build_tree_impl(sph_ctx* c, bool* retry_two_word);
+
+// Single-word (63-bit, 21-level) keys are the fast path.  If two particles share a full key while the
+// reference's max_depth is deeper, the build is repeated (and stays) on the two-word path: 42 levels,
+// sorted with two stable radix passes (low word, then high word).
 int build_tree(sph_ctx* c) {
+  bool retry = false;
+  int r = build_tree_impl(c, &retry);
+  if (r == SPH_OK && retry) {
+    c->two_word = true;
+    make_dev_params(c);
+    for (int b = 0; b < 2; ++b) DA(c->key_lo[b], c->cap);
+    r = build_tree_impl(c, &retry);
+  }
+  return r;
+}
+
+int build_tree_impl(sph_ctx* c, bool* retry_two_word) {
   const int n = (int)c->n;
   const int T = 256;
+  *retry_two_word = false;
+  if (c->two_word && !c->key_lo[0]) { for (int b = 0; b < 2; ++b) DA(c->key_lo[b], c->cap); }
   stage_begin(c, ST_KEYS);
   {
     StateArrays s = state_of(c, c->cur);
@@ -241,13 +262,21 @@ int build_tree(sph_ctx* c) {
     LAUNCH(k_bbox_partial, nb, T, 0, n, s.x, s.y, s.z, c->partial);
     // multi-GPU: particles are replicated, every rank sees the same box (no exchange needed)
     LAUNCH(k_bbox_final, 1, 32, 0, nb, c->partial, c->root);
-    LAUNCH(k_keys, cdiv(n, T), T, 0, n, s.x, s.y, s.z, c->root, c->dp.lmax, c->key[0], c->perm[0]);
+    LAUNCH(k_keys, cdiv(n, T), T, 0, n, s.x, s.y, s.z, c->root, c->dp.lmax, c->key[0], c->two_word ? c->key_lo[0] : nullptr, c->perm[0]);
   }
   stage_end(c);
   stage_begin(c, ST_SORT);
   {
-    cub::DoubleBuffer<uint64_t> dk(c->key[0], c->key[1]); cub::DoubleBuffer<int> dv(c->perm[0], c->perm[1]);
     size_t bytes = c->cub_bytes;
+    if (c->two_word) {     // stable LSD order: low word first
+      cub::DoubleBuffer<uint64_t> dl(c->key_lo[0], c->key_lo[1]); cub::DoubleBuffer<int> dv(c->perm[0], c->perm[1]);
+      CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp, bytes, dl, dv, n, 0, 63, c->stream));
+      if (dv.Current() != c->perm[0]) std::swap(c->perm[0], c->perm[1]);
+      LAUNCH(k_gather_u64, cdiv(n, T), T, 0, n, c->perm[0], c->key[0], c->key[1]);
+      std::swap(c->key[0], c->key[1]);
+      bytes = c->cub_bytes;
+    }
+    cub::DoubleBuffer<uint64_t> dk(c->key[0], c->key[1]); cub::DoubleBuffer<int> dv(c->perm[0], c->perm[1]);
     CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp, bytes, dk, dv, n, 0, 63, c->stream));
     if (dk.Current() != c->key[0]) { std::swap(c->key[0], c->key[1]); }
     if (dv.Current() != c->perm[0]) { std::swap(c->perm[0], c->perm[1]); }
@@ -256,24 +285,36 @@ int build_tree(sph_ctx* c) {
     pa.id_src = c->id[c->cur]; pa.id_dst = c->id[c->cur ^ 1];
     LAUNCH(k_permute, cdiv(n, T), T, 0, n, c->perm[0], pa);
     c->cur ^= 1;
+    if (c->two_word) {     // regenerate both key words in the final order from the re-ordered positions
+      StateArrays s = state_of(c, c->cur);
+      LAUNCH(k_keys, cdiv(n, T), T, 0, n, s.x, s.y, s.z, c->root, c->dp.lmax, c->key[0], c->key_lo[0], c->perm[1]);
+    }
   }
   stage_end(c);
   stage_begin(c, ST_TREE);
   {
     StateArrays s = state_of(c, c->cur);
-    LAUNCH(k_leaf, cdiv(n, T), T, 0, n, c->key[0], s.h, c->root, c->dp, c->level, c->lcx, c->lcy, c->lcz, c->reach, &c->sc->err);
+    const uint64_t* klo = c->two_word ? c->key_lo[0] : nullptr;
+    LAUNCH(k_leaf, cdiv(n, T), T, 0, n, c->key[0], klo, s.h, c->root, c->dp, c->level, c->lcx, c->lcy, c->lcz, c->reach, &c->sc->err);
     // octree
-    LAUNCH(k_oct_nodes<false>, cdiv(n, T), T, 0, n, c->key[0], c->dp.lmax, c->root, c->cnt, c->off, 0, c->nodes, c->node_part, c->node_count);
+    LAUNCH(k_oct_nodes<false>, cdiv(n, T), T, 0, n, c->key[0], klo, c->dp.lmax, c->root, c->cnt, c->off, 0, c->nodes, c->node_part, c->node_count);
     CK(cudaMemsetAsync(c->cnt + n, 0, sizeof(int), c->stream));
     size_t bytes = c->cub_bytes;
     CK(cub::DeviceScan::ExclusiveSum(c->cub_tmp, bytes, c->cnt, c->off, n + 1, c->stream));
     // node count is needed on the host for launch sizes of the per-node passes
-    int n_int = 0;
+    int n_int = 0, key_err = 0;
     CK(cudaMemcpyAsync(&n_int, c->off + n, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(&key_err, &c->sc->err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    if (key_err && !c->two_word) {            // a 63-bit key collision: redo this build with two-word keys
+      CK(cudaMemsetAsync(&c->sc->err, 0, sizeof(int), c->stream));
+      stage_end(c);
+      *retry_two_word = true;
+      return SPH_OK;
+    }
     const int nn = n + n_int;
     c->counts.n_nodes = nn;
-    LAUNCH(k_oct_nodes<true>, cdiv(n, T), T, 0, n, c->key[0], c->dp.lmax, c->root, c->cnt, c->off, nn, c->nodes, c->node_part, c->node_count);
+    LAUNCH(k_oct_nodes<true>, cdiv(n, T), T, 0, n, c->key[0], klo, c->dp.lmax, c->root, c->cnt, c->off, nn, c->nodes, c->node_part, c->node_count);
     LAUNCH(k_oct_link, cdiv(nn, T), T, 0, nn, c->nodes, c->node_part, c->parent, c->nchild);
     CK(cudaMemsetAsync(c->arrive, 0, sizeof(int) * (size_t)nn, c->stream));
     LAUNCH(k_oct_up, cdiv(n, T), T, 0, n, c->off, c->cnt, s.x, s.y, s.z, s.m, s.h, c->level, c->root, c->nodes, c->parent, c->nchild, c->arrive);
@@ -410,7 +451,7 @@ int fetch_counters(sph_ctx* c) {
 
 int check_device_error(sph_ctx* c) {
   if (c->h_sc->err) {
-    c->err = "particles share a full 63-bit descent key (closer than root_size/2^21) while max_depth > 21";
+    c->err = "particles share a full 126-bit descent key (closer than root_size/2^42) while max_depth > 42";
     return SPH_ERR_DEPTH;
   }
   return SPH_OK;
@@ -465,7 +506,7 @@ int step(sph_ctx* c) {
   }
   stage_begin(c, ST_CULL);
   LAUNCH(k_any_sink_mass, 1, 32, 0, c->S, c->sc);                             // F:919
-  LAUNCH(k_flags, cdiv(n, T), T, 0, n, c->dp, state_of(c, c->cur), c->key[0], c->level, c->lcx, c->lcy, c->lcz, c->reach, c->root,
+  LAUNCH(k_flags, cdiv(n, T), T, 0, n, c->dp, state_of(c, c->cur), c->key[0], c->two_word ? c->key_lo[0] : nullptr, c->level, c->lcx, c->lcy, c->lcz, c->reach, c->root,
          c->S, c->sc, c->keep, c->acc_key[0], c->acc_val[0], (int)c->cap);
   CK(cudaMemcpyAsync(c->h_sc, c->sc, sizeof(SimScalars), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
@@ -611,7 +652,7 @@ int sph_destroy(sph_ctx* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->comm && c->nccl.CommDestroy) c->nccl.CommDestroy(c->comm);
   auto F = [](void* p) { if (p) cudaFree(p); };
-  for (int b = 0; b < 2; ++b) { for (int f = 0; f < 10; ++f) F(c->st[b][f]); F(c->id[b]); F(c->key[b]); F(c->perm[b]); F(c->acc_key[b]); F(c->acc_val[b]); }
+  for (int b = 0; b < 2; ++b) { for (int f = 0; f < 10; ++f) F(c->st[b][f]); F(c->id[b]); F(c->key[b]); F(c->key_lo[b]); F(c->perm[b]); F(c->acc_key[b]); F(c->acc_val[b]); }
   F(c->rho); F(c->omega); F(c->prs); F(c->cs); F(c->por2); F(c->ax); F(c->ay); F(c->az); F(c->udot); F(c->adot);
   F(c->node_count); F(c->gsize); F(c->gfirst); F(c->groups); F(c->level); F(c->lcx); F(c->lcy); F(c->lcz); F(c->reach); F(c->bvh); F(c->nodes); F(c->node_part); F(c->parent); F(c->nchild);
   F(c->arrive); F(c->cnt); F(c->off); F(c->root); F(c->partial); F(c->cub_tmp); F(c->d_wt); F(c->d_dwt); F(c->d_gt);

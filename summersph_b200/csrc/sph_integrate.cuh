@@ -126,7 +126,7 @@ __global__ void k_create_apply(StateArrays s, SinkArrays S, SimScalars* sc) {
 // The tree walk of sink2gasdists is replayed per particle along its own root-to-leaf path: every ancestor
 // cell must pass `all |c - x_s| < R_s + size/2` (F:529), the leaf `< 2 R_s + size/2` (F:536) | `< R_s + size/2`
 // (V:668), then dr = sum sqrt(c^2 - x_s^2) on the leaf cell centre (F:537) | sum sqrt((x - x_s)^2) (V:669).
-__global__ void k_flags(int n, DevParams P, StateArrays s, const uint64_t* __restrict__ key, const int* __restrict__ level,
+__global__ void k_flags(int n, DevParams P, StateArrays s, const uint64_t* __restrict__ key, const uint64_t* __restrict__ key_lo, const int* __restrict__ level,
                         const double* __restrict__ lcx, const double* __restrict__ lcy, const double* __restrict__ lcz,
                         const double* __restrict__ reach, const RootBox* __restrict__ rb, SinkArrays S, SimScalars* sc,
                         unsigned char* __restrict__ keep, unsigned long long* __restrict__ acc_key,
@@ -157,12 +157,12 @@ __global__ void k_flags(int n, DevParams P, StateArrays s, const uint64_t* __res
       if (!(dr < R)) continue;
       // ancestors along the path (levels 0 .. lev-1)
       double ax = rb->cx, ay = rb->cy, az = rb->cz, as = rb->size;
-      const uint64_t k = key[i];
+      const uint64_t k = key[i], k2 = key_lo ? key_lo[i] : 0;
       bool pass = true;
       for (int l = 0; l < lev; ++l) {
         const double al = R + as / 2.0;
         if (!(fabs(ax - sx) < al && fabs(ay - sy) < al && fabs(az - sz) < al)) { pass = false; break; }
-        const int dg = (int)((k >> (3 * (SPH_KEY_LEVELS - 1 - l))) & 7);
+        const int dg = key_digit(k, k2, l);
         const double q = 0.25 * as;
         ax = __dadd_rn(ax, (dg & 1) ? q : -q); ay = __dadd_rn(ay, (dg & 2) ? q : -q); az = __dadd_rn(az, (dg & 4) ? q : -q);
         as = as * 0.5;

@@ -60,23 +60,32 @@ __global__ void k_bbox_final(int nblocks, const double* __restrict__ partial, Ro
 // descent keys: replay of F:190-214 for lmax levels. Digit = [x>cx] + 2[y>cy] + 4[z>cz] (strict >).
 // ------------------------------------------------------------------------------------------------------
 __global__ void k_keys(int n, const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
-                       const RootBox* __restrict__ rb, int lmax, uint64_t* __restrict__ key, int* __restrict__ idx) {
+                       const RootBox* __restrict__ rb, int lmax, uint64_t* __restrict__ key, uint64_t* __restrict__ key_lo,
+                       int* __restrict__ idx) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double px = x[i], py = y[i], pz = z[i];
   double cx = rb->cx, cy = rb->cy, cz = rb->cz, s = rb->size;
-  uint64_t k = 0;
+  uint64_t k = 0, k2 = 0;
   for (int l = 0; l < lmax; ++l) {
     int bx = px > cx, by = py > cy, bz = pz > cz;
-    k = (k << 3) | (uint64_t)(bx | (by << 1) | (bz << 2));
+    const uint64_t dg = (uint64_t)(bx | (by << 1) | (bz << 2));
+    if (l < SPH_KEY_LEVELS) k = (k << 3) | dg; else k2 = (k2 << 3) | dg;
     double q = 0.25 * s;                                                 // F:195 (exact scaling)
     cx = __dadd_rn(cx, bx ? q : -q);                                     // F:199
     cy = __dadd_rn(cy, by ? q : -q);
     cz = __dadd_rn(cz, bz ? q : -q);
     s = s * 0.5;                                                         // F:191
   }
-  key[i] = k << (3 * (SPH_KEY_LEVELS - lmax));
+  const int l1 = lmax < SPH_KEY_LEVELS ? lmax : SPH_KEY_LEVELS;
+  key[i] = k << (3 * (SPH_KEY_LEVELS - l1));
+  if (key_lo) key_lo[i] = k2 << (3 * (SPH_KEY_LEVELS2 - (lmax > SPH_KEY_LEVELS ? lmax : SPH_KEY_LEVELS)));
   idx[i] = i;
+}
+
+__global__ void k_gather_u64(int n, const int* __restrict__ perm, const uint64_t* __restrict__ src, uint64_t* __restrict__ dst) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[perm[i]];
 }
 
 // physical re-order of the state into sorted order
@@ -96,21 +105,21 @@ __global__ void k_permute(int n, const int* __restrict__ perm, PermuteArgs a) {
 // A particle that shares its full key with a neighbour sits in a depth-limited multi-particle childless
 // node, which the density / SPH / accretion walks skip (neither branch of F:431,443 fires): R = -1.
 // ------------------------------------------------------------------------------------------------------
-__global__ void k_leaf(int n, const uint64_t* __restrict__ key, const double* __restrict__ h, const RootBox* __restrict__ rb,
-                       DevParams P, int* __restrict__ level, double* __restrict__ lcx, double* __restrict__ lcy,
-                       double* __restrict__ lcz, double* __restrict__ reach, int* __restrict__ err_flag) {
+__global__ void k_leaf(int n, const uint64_t* __restrict__ key, const uint64_t* __restrict__ key_lo, const double* __restrict__ h,
+                       const RootBox* __restrict__ rb, DevParams P, int* __restrict__ level, double* __restrict__ lcx,
+                       double* __restrict__ lcy, double* __restrict__ lcz, double* __restrict__ reach, int* __restrict__ err_flag) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  uint64_t k = key[i];
-  int d = (i > 0) ? lcp_levels(key[i - 1], k, P.lmax) : -1;
-  int e = (i < n - 1) ? lcp_levels(k, key[i + 1], P.lmax) : -1;
+  const uint64_t k = key[i], k2 = key_lo ? key_lo[i] : 0;
+  int d = (i > 0) ? lcp_levels2(key[i - 1], key_lo ? key_lo[i - 1] : 0, k, k2, P.lmax) : -1;
+  int e = (i < n - 1) ? lcp_levels2(k, k2, key[i + 1], key_lo ? key_lo[i + 1] : 0, P.lmax) : -1;
   int m = d > e ? d : e;
   bool multi = (m >= P.lmax);
   int lev = multi ? P.lmax : m + 1;
   if (multi && P.depth_unbounded) atomicExch(err_flag, 1);
   double cx = rb->cx, cy = rb->cy, cz = rb->cz, s = rb->size;
   for (int l = 0; l < lev; ++l) {
-    int dg = (int)((k >> (3 * (SPH_KEY_LEVELS - 1 - l))) & 7);
+    const int dg = key_digit(k, k2, l);
     double q = 0.25 * s;
     cx = __dadd_rn(cx, (dg & 1) ? q : -q);
     cy = __dadd_rn(cy, (dg & 2) ? q : -q);
@@ -216,40 +225,53 @@ __global__ void k_bvh_up(int n_child, const BvhBox* __restrict__ child, BvhBox* 
 // SURVEY.md Appendix B).  cnt[i] = number of branching nodes starting at i; preorder slot of the k-th
 // (ascending level) = i + off[i] + k; leaf i sits at i + off[i] + cnt[i].
 // ------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int cell_last(const uint64_t* __restrict__ key, int n, int lo, uint64_t kmax) {
-  // largest r >= lo with key[r] <= kmax, given key[lo] <= kmax; gallop then bisect
+__device__ __forceinline__ bool key_le(const uint64_t* __restrict__ key, const uint64_t* __restrict__ key_lo, int r,
+                                       uint64_t kmax, uint64_t kmax_lo) {
+  const uint64_t a = key[r];
+  if (a != kmax) return a < kmax;
+  return key_lo ? key_lo[r] <= kmax_lo : true;
+}
+__device__ __forceinline__ int cell_last(const uint64_t* __restrict__ key, const uint64_t* __restrict__ key_lo, int n, int lo,
+                                         uint64_t kmax, uint64_t kmax_lo) {
+  // largest r >= lo with key[r] <= kmax (two-word compare), given key[lo] <= kmax; gallop then bisect
   int step = 1, hi = lo;
   while (true) {
     int probe = lo + step;
     if (probe >= n) { hi = n - 1; break; }
-    if (key[probe] <= kmax) { lo = probe; step <<= 1; } else { hi = probe - 1; break; }
+    if (key_le(key, key_lo, probe, kmax, kmax_lo)) { lo = probe; step <<= 1; } else { hi = probe - 1; break; }
   }
   while (lo < hi) {
     int mid = (lo + hi + 1) >> 1;
-    if (key[mid] <= kmax) lo = mid; else hi = mid - 1;
+    if (key_le(key, key_lo, mid, kmax, kmax_lo)) lo = mid; else hi = mid - 1;
   }
   return lo;
 }
 
 template <bool EMIT>
-__global__ void k_oct_nodes(int n, const uint64_t* __restrict__ key, int lmax, const RootBox* __restrict__ rb,
-                            int* __restrict__ cnt, const int* __restrict__ off, int n_nodes,
+__global__ void k_oct_nodes(int n, const uint64_t* __restrict__ key, const uint64_t* __restrict__ key_lo, int lmax,
+                            const RootBox* __restrict__ rb, int* __restrict__ cnt, const int* __restrict__ off, int n_nodes,
                             GNode* __restrict__ nodes, int* __restrict__ node_part, int* __restrict__ node_count) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  uint64_t k = key[i];
-  int d = (i > 0) ? lcp_levels(key[i - 1], k, lmax) : -1;
-  int e = (i < n - 1) ? lcp_levels(k, key[i + 1], lmax) : -1;
+  const uint64_t k = key[i], k2 = key_lo ? key_lo[i] : 0;
+  int d = (i > 0) ? lcp_levels2(key[i - 1], key_lo ? key_lo[i - 1] : 0, k, k2, lmax) : -1;
+  int e = (i < n - 1) ? lcp_levels2(k, k2, key[i + 1], key_lo ? key_lo[i + 1] : 0, lmax) : -1;
   int count = 0;
   int total = EMIT ? cnt[i] : 0;
   int base = EMIT ? i + off[i] : 0;
   int r = i;
   double root_size = EMIT ? rb->size : 0.0;
   for (int L = e; L > d; --L) {            // smallest cell first; cells nest so r only grows
-    int shift = 3 * (SPH_KEY_LEVELS - L);
-    uint64_t kmax = (shift >= 63) ? ~0ull : (k | ((1ull << shift) - 1ull));
-    r = cell_last(key, n, r, kmax);
-    if (lcp_levels(k, key[r], lmax) == L) {
+    uint64_t kmax, kmax_lo;
+    if (L <= SPH_KEY_LEVELS) {
+      const int shift = 3 * (SPH_KEY_LEVELS - L);
+      kmax = (shift >= 63) ? ~0ull : (k | ((1ull << shift) - 1ull)); kmax_lo = ~0ull;
+    } else {
+      const int shift = 3 * (SPH_KEY_LEVELS2 - L);
+      kmax = k; kmax_lo = k2 | ((1ull << shift) - 1ull);
+    }
+    r = cell_last(key, key_lo, n, r, kmax, kmax_lo);
+    if (lcp_levels2(k, k2, key[r], key_lo ? key_lo[r] : 0, lmax) == L) {
       if (EMIT) {
         int slot = base + (total - 1 - count);
         double s = root_size;

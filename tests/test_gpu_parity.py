@@ -201,8 +201,49 @@ def test_depth_limited_tree(max_depth, E, O):
             assert relerr(de[k], do[k]) < TOL, k
 
 
+def test_two_word_keys(E, O):
+    """Pairs closer than root_size/2^21 overflow the 63-bit key: the engine switches to two-word (42-level)
+    keys and still reproduces the reference tree (leaf levels > 21) and everything downstream."""
+    p = default_params(MODE_VARIABLE_H)
+    b, s = ics.keplerian_disc(5_000, seed=31)
+    for a_, c_, eps in ((10, 11, 3e-7), (200, 201, 5e-9), (3000, 3001, 2e-10)):
+        b.x[c_] = b.x[a_] + eps; b.y[c_] = b.y[a_] - 0.5 * eps; b.z[c_] = b.z[a_] + 0.25 * eps
+    o = O(p); o.record_neighbours(True); o.upload(b, s); o.evaluate()
+    assert np.max(o.tree()["level"]) > 21
+    with E(p) as e:
+        e.upload(b, s); e.evaluate()
+        compare_eval(o, e)
+        o.record_neighbours(False)
+        o.upload(b, s); e.upload(b, s)
+        dto = dte = 0.01; to = te = 0.0
+        for _ in range(2):
+            dto, to = o.step(dto, to); dte, te = e.step(dte, te)
+            assert dto == dte and to == te
+        compare_state(o, e)
+
+
+def test_depth_limit_between_one_and_two_words(E, O):
+    """max_depth = 30 with coincident particles: a depth-limited multi-particle leaf at level 30."""
+    p = default_params(MODE_VARIABLE_H, max_depth=30)
+    b, s = ics.keplerian_disc(3_000, seed=32)
+    for k in ("x", "y", "z"):
+        getattr(b, k)[7] = getattr(b, k)[6]
+    mask = EVAL_TREE | EVAL_DENSITY | EVAL_GRAVITY | EVAL_SINKS
+    o = O(p); o.record_neighbours(True); o.upload(b, s); o.evaluate(mask)
+    with E(p) as e:
+        e.upload(b, s); e.evaluate(mask)
+        to, te = o.tree(), e.tree()
+        assert np.array_equal(to["order"], te["order"]) and np.array_equal(to["level"], te["level"])
+        assert te["level"][6] == 30 and te["level"][7] == 30
+        co, ho, _, _ = o.neighbours(with_list=False); ce, he, _, _ = e.neighbours(with_list=False)
+        assert np.array_equal(co, ce) and np.array_equal(ho, he)
+        do, de = o.diag(), e.diag()
+        for k in ("ax", "ay", "az"):
+            assert relerr(de[k], do[k]) < TOL, k
+
+
 def test_key_depth_error_is_loud(E):
-    """Two coincident particles with max_depth = 1000: the 63-bit key cannot separate them -> SPH_ERR_DEPTH."""
+    """Two coincident particles with max_depth = 1000: not even the 126-bit key separates them -> SPH_ERR_DEPTH."""
     from summersph_b200.engine import SphError
     p = default_params(MODE_VARIABLE_H)
     b, s = ics.keplerian_disc(2_000, seed=2)
