@@ -67,7 +67,7 @@ struct sph_ctx {
   WalkCounters* ctr = nullptr; WalkCounters* h_ctr = nullptr; int* work = nullptr;
   unsigned char* keep = nullptr; unsigned long long* acc_key[2] = {}; int* acc_val[2] = {}; int* d_nsel = nullptr;
   int* pos = nullptr;           // ascending-number position of each sorted particle (downloads)
-  double* stage_d = nullptr;    // device staging for ordered downloads
+  double* stage_d = nullptr; double* stage_d2 = nullptr; int stage_flip = 0;   // device staging for ordered downloads
   bool tree_valid = false;
   sph_counts counts; double stage_ms[ST_COUNT] = {};
   std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> ev_used; std::vector<cudaEvent_t> ev_pool;
@@ -129,7 +129,7 @@ int ensure_capacity(sph_ctx* c, int64_t n) {
   DA(c->node_count, 2 * cap); DA(c->gsize, cap); DA(c->gfirst, cap); DA(c->groups, cap);
   DA(c->nodes, 2 * cap); DA(c->node_part, 2 * cap); DA(c->parent, 2 * cap); DA(c->nchild, 2 * cap); DA(c->arrive, 2 * cap);
   DA(c->cnt, cap + 1); DA(c->off, cap + 1);
-  DA(c->keep, cap); DA(c->pos, cap); DA(c->stage_d, cap);
+  DA(c->keep, cap); DA(c->pos, cap); DA(c->stage_d, cap); DA(c->stage_d2, cap);
   // CUB temp: radix sort pairs (u64,int), exclusive scan, select
   size_t b1 = 0, b2 = 0, b3 = 0, b4 = 0;
   cub::DeviceSelect::Flagged(nullptr, b4, cub::CountingInputIterator<int>(0), c->gsize, c->gfirst, c->d_nsel, (int)cap, c->stream);
@@ -403,8 +403,8 @@ int run_gravity(sph_ctx* c, int do_grav, int do_sinks) {
   stage_begin(c, ST_GRAVITY);
   StateArrays s = state_of(c, c->cur);
   const int nloc = c->p1 - c->p0;
-  const int nb = cdiv(nloc, T);
   const int nw = cdiv(nloc, 32);
+  const int nb = cdiv(nloc, T);
   const int ns = do_sinks ? c->n_sink : 0;
   if ((size_t)(nw + 8) * std::max(ns, 1) * 3 > c->sink_partial_cap) {
     c->sink_partial_cap = (size_t)(nw + 8) * std::max(ns, 1) * 3 * 2;
@@ -532,35 +532,41 @@ int step(sph_ctx* c) {
   return SPH_OK;
 }
 
-// ascending-number position of every sorted particle: rank of its id among the surviving ids
+// ascending-number position of every sorted particle: rank of its id among the surviving ids (all on device)
+__global__ void k_mark_present(int n, const int* __restrict__ id, int* __restrict__ present) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) present[id[i]] = 1;
+}
+__global__ void k_rank_of(int n, const int* __restrict__ id, const int* __restrict__ rank, int* __restrict__ pos) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) pos[i] = rank[id[i]];
+}
 int compute_pos(sph_ctx* c) {
-  const int n = (int)c->n;
-  std::vector<int> ids(n), pos(n);
-  CK(cudaMemcpyAsync(ids.data(), c->id[c->cur], (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
-  if ((int64_t)n == c->n_upload) { pos = ids; }
-  else {
-    std::vector<int> present((size_t)c->n_upload + 1, 0);
-    for (int i = 0; i < n; ++i) present[ids[i]] = 1;
-    int acc = 0; for (int64_t k = 0; k < c->n_upload; ++k) { int p = present[k]; present[k] = acc; acc += p; }
-    for (int i = 0; i < n; ++i) pos[i] = present[ids[i]];
+  const int n = (int)c->n, T = 256;
+  if ((int64_t)n == c->n_upload) {         // nothing was ever removed: number == upload index
+    CK(cudaMemcpyAsync(c->pos, c->id[c->cur], (size_t)n * 4, cudaMemcpyDeviceToDevice, c->stream));
+    return SPH_OK;
   }
-  CK(cudaMemcpyAsync(c->pos, pos.data(), (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
+  const int nu = (int)c->n_upload;          // <= cap: cnt/off (cap + 1 ints) are only read while the octree is being built
+  CK(cudaMemsetAsync(c->cnt, 0, sizeof(int) * (size_t)(nu + 1), c->stream));
+  LAUNCH(k_mark_present, cdiv(n, T), T, 0, n, c->id[c->cur], c->cnt);
+  size_t bytes = c->cub_bytes;
+  CK(cub::DeviceScan::ExclusiveSum(c->cub_tmp, bytes, c->cnt, c->off, nu + 1, c->stream));
+  LAUNCH(k_rank_of, cdiv(n, T), T, 0, n, c->id[c->cur], c->off, c->pos);
   return SPH_OK;
 }
+// scatter into ascending-number order on the device, then one D2H per field; two staging buffers let the
+// scatter of field f+1 overlap nothing it depends on (stream order protects the buffers), one sync at the end
 int fetch_ordered(sph_ctx* c, const double* src, double* dst_host) {
   if (!dst_host) return SPH_OK;
   const int n = (int)c->n, T = 256;
-  LAUNCH(k_scatter_d, cdiv(n, T), T, 0, n, c->pos, src, c->stage_d);
-  CK(cudaMemcpyAsync(dst_host, c->stage_d, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
+  double* stage = c->stage_flip ? c->stage_d2 : c->stage_d;
+  c->stage_flip ^= 1;
+  LAUNCH(k_scatter_d, cdiv(n, T), T, 0, n, c->pos, src, stage);
+  CK(cudaMemcpyAsync(dst_host, stage, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
   return SPH_OK;
 }
 int fetch_sink(sph_ctx* c, const double* src, double* dst_host) {
   if (!dst_host || c->n_sink == 0) return SPH_OK;
   CK(cudaMemcpyAsync(dst_host, src, (size_t)c->n_sink * 8, cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
   return SPH_OK;
 }
 
@@ -656,7 +662,7 @@ int sph_destroy(sph_ctx* c) {
   F(c->rho); F(c->omega); F(c->prs); F(c->cs); F(c->por2); F(c->ax); F(c->ay); F(c->az); F(c->udot); F(c->adot);
   F(c->node_count); F(c->gsize); F(c->gfirst); F(c->groups); F(c->level); F(c->lcx); F(c->lcy); F(c->lcz); F(c->reach); F(c->bvh); F(c->nodes); F(c->node_part); F(c->parent); F(c->nchild);
   F(c->arrive); F(c->cnt); F(c->off); F(c->root); F(c->partial); F(c->cub_tmp); F(c->d_wt); F(c->d_dwt); F(c->d_gt);
-  F(c->sink_buf); F(c->sink_partial); F(c->sc); F(c->ctr); F(c->work); F(c->keep); F(c->d_nsel); F(c->pos); F(c->stage_d);
+  F(c->sink_buf); F(c->sink_partial); F(c->sc); F(c->ctr); F(c->work); F(c->keep); F(c->d_nsel); F(c->pos); F(c->stage_d); F(c->stage_d2);
   if (c->h_sc) cudaFreeHost(c->h_sc);
   if (c->h_ctr) cudaFreeHost(c->h_ctr);
   for (auto& e : c->ev_used) { cudaEventDestroy(e.second.first); cudaEventDestroy(e.second.second); }
@@ -792,6 +798,7 @@ int sph_download(sph_ctx* c, double* x, double* y, double* z, double* vx, double
   double* sd[8] = {sx, sy, sz, svx, svy, svz, sm, srad};
   const double* ss[8] = {c->S.x, c->S.y, c->S.z, c->S.vx, c->S.vy, c->S.vz, c->S.m, c->S.radius};
   for (int k = 0; k < 8; ++k) if ((r = fetch_sink(c, ss[k], sd[k]))) return r;
+  CK(cudaStreamSynchronize(c->stream));
   return SPH_OK;
 }
 
@@ -808,6 +815,7 @@ int sph_download_diag(sph_ctx* c, double* rho, double* omega, double* pressure, 
   if ((r = fetch_sink(c, c->S.ax, sax))) return r;
   if ((r = fetch_sink(c, c->S.ay, say))) return r;
   if ((r = fetch_sink(c, c->S.az, saz))) return r;
+  CK(cudaStreamSynchronize(c->stream));
   return SPH_OK;
 }
 
@@ -818,7 +826,7 @@ int sph_download_tree(sph_ctx* c, int32_t* order, uint64_t* key, int32_t* level,
   cudaSetDevice(c->device);
   const int n = (int)c->n, T = 256;
   int r; if ((r = compute_pos(c))) return r;
-  if (order) { CK(cudaMemcpy(order, c->pos, (size_t)n * 4, cudaMemcpyDeviceToHost)); }
+  if (order) { CK(cudaMemcpyAsync(order, c->pos, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream)); }
   if (key) {
     LAUNCH(k_scatter_u64, cdiv(n, T), T, 0, n, c->pos, (const unsigned long long*)c->key[0], (unsigned long long*)c->stage_d);
     CK(cudaMemcpyAsync(key, c->stage_d, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream));
@@ -832,6 +840,7 @@ int sph_download_tree(sph_ctx* c, int32_t* order, uint64_t* key, int32_t* level,
   if ((r = fetch_ordered(c, c->lcx, cx))) return r;
   if ((r = fetch_ordered(c, c->lcy, cy))) return r;
   if ((r = fetch_ordered(c, c->lcz, cz))) return r;
+  CK(cudaStreamSynchronize(c->stream));
   if (size) {
     RootBox rb; CK(cudaMemcpy(&rb, c->root, sizeof(rb), cudaMemcpyDeviceToHost));
     for (int i = 0; i < n; ++i) { double s = rb.size; for (int q = 0; q < lev[i]; ++q) s *= 0.5; size[i] = s; }
