@@ -207,6 +207,10 @@ def main():
         allw = [torch.zeros_like(walk) for _ in range(world)]
         dist.all_gather(allw, walk)
         per_rank_walk = [float(x.item()) / args.steps for x in allw]
+        comm = torch.tensor([stage_acc.get("comm", 0)], dtype=torch.float64, device="cuda")
+        allc = [torch.zeros_like(comm) for _ in range(world)]
+        dist.all_gather(allc, comm)
+        per_rank_comm = [float(x.item()) / args.steps for x in allc]
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
     ms = float(tm.item())
     value = n * args.steps / (ms * 1e-3)
@@ -283,6 +287,7 @@ def main():
         }
         if world > 1:
             line["per_rank_walk_ms_per_step"] = per_rank_walk
+            line["per_rank_comm_ms_per_step"] = per_rank_comm
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1
             nb = args.cpu_baseline_particles

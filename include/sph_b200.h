@@ -162,7 +162,8 @@ int sph_counters(sph_ctx* ctx, sph_counts* out);
 
 /* Per-stage device time of the most recent sph_step / sph_evaluate in milliseconds:
  * [0]=bbox+keys [1]=sort+reorder [2]=tree build [3]=density+EOS [4]=gravity(+sinks)
- * [5]=SPH pair [6]=integrate+dt [7]=h iteration [8]=accretion+cull ; n <= 16 */
+ * [5]=SPH pair [6]=integrate+dt [7]=h iteration [8]=accretion+cull [9]=NCCL exchanges (incl. waiting
+ * for the slowest rank) ; n <= 16 */
 int sph_stage_times(sph_ctx* ctx, double* ms, int32_t n);
 
 /* Number of CUDA kernel launches issued by this context so far. */

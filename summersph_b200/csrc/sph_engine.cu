@@ -23,7 +23,7 @@ namespace {
 
 thread_local std::string g_create_error;
 
-enum Stage { ST_KEYS = 0, ST_SORT, ST_TREE, ST_DENSITY, ST_GRAVITY, ST_SPH, ST_INTEGRATE, ST_HITER, ST_CULL, ST_COUNT };
+enum Stage { ST_KEYS = 0, ST_SORT, ST_TREE, ST_DENSITY, ST_GRAVITY, ST_SPH, ST_INTEGRATE, ST_HITER, ST_CULL, ST_COMM, ST_COUNT };
 
 // x**n in libgcc __powidf2 order (kernel tables, SUMMER_SPH.f90:63-100)
 inline double powi(double x, int n) { double y = (n % 2) ? x : 1.0; while (n >>= 1) { x = x * x; if (n % 2) y *= x; } return y; }
@@ -372,8 +372,8 @@ int run_density(sph_ctx* c) {
   LAUNCH(k_set_int, 1, 1, 0, c->work, c->g0);
   LAUNCH(k_density<false>, walk_grid(c, W), W * 32, density_smem(c, W), c->g1, c->groups, c->dp, dens_arrays(c), c->bvh, c->bi, c->d_wt, c->d_dwt,
          s.u, s.h, c->rho, c->omega, c->prs, c->cs, c->por2, c->ctr, c->work);
-  { double* bufs[5] = {c->rho, c->omega, c->prs, c->cs, c->por2}; int r_ = allgatherv(c, bufs, 5); if (r_) return r_; }
   stage_end(c);
+  if (c->n_ranks > 1) { stage_begin(c, ST_COMM); double* bufs[5] = {c->rho, c->omega, c->prs, c->cs, c->por2}; int r_ = allgatherv(c, bufs, 5); if (r_) return r_; stage_end(c); }
   return SPH_OK;
 }
 int run_hiter(sph_ctx* c) {
@@ -383,8 +383,8 @@ int run_hiter(sph_ctx* c) {
   LAUNCH(k_set_int, 1, 1, 0, c->work, c->g0);
   LAUNCH(k_density<true>, walk_grid(c, W), W * 32, density_smem(c, W), c->g1, c->groups, c->dp, dens_arrays(c), c->bvh, c->bi, c->d_wt, c->d_dwt,
          s.u, s.h, c->rho, c->omega, c->prs, c->cs, c->por2, c->ctr, c->work);
-  { double* bufs[1] = {s.h}; int r_ = allgatherv(c, bufs, 1); if (r_) return r_; }
   stage_end(c);
+  if (c->n_ranks > 1) { stage_begin(c, ST_COMM); double* bufs[1] = {s.h}; int r_ = allgatherv(c, bufs, 1); if (r_) return r_; stage_end(c); }
   return SPH_OK;
 }
 int run_force(sph_ctx* c) {
@@ -394,8 +394,8 @@ int run_force(sph_ctx* c) {
   ForceArrays A{s.x, s.y, s.z, s.vx, s.vy, s.vz, s.m, s.h, c->rho, c->cs, s.alpha, c->por2, c->lcx, c->lcy, c->lcz, c->reach, s.id};
   LAUNCH(k_set_int, 1, 1, 0, c->work, c->g0);
   LAUNCH(k_force, walk_grid(c, W), W * 32, force_smem(c, W), c->g1, c->groups, c->dp, A, c->bvh, c->bi, c->d_dwt, c->ax, c->ay, c->az, c->udot, c->adot, c->ctr, c->work);
-  { double* bufs[5] = {c->ax, c->ay, c->az, c->udot, c->adot}; int r_ = allgatherv(c, bufs, 5); if (r_) return r_; }
   stage_end(c);
+  if (c->n_ranks > 1) { stage_begin(c, ST_COMM); double* bufs[5] = {c->ax, c->ay, c->az, c->udot, c->adot}; int r_ = allgatherv(c, bufs, 5); if (r_) return r_; stage_end(c); }
   return SPH_OK;
 }
 int run_gravity(sph_ctx* c, int do_grav, int do_sinks) {
@@ -414,7 +414,9 @@ int run_gravity(sph_ctx* c, int do_grav, int do_sinks) {
     LAUNCH(k_gravity, nb, T, (size_t)(c->p.nq + 1) * 8, c->p0, c->p1, c->dp, c->nodes, (int)c->counts.n_nodes, s.x, s.y, s.z, s.h, s.m, c->d_gt,
            c->ax, c->ay, c->az, do_grav, ns, c->S, c->sink_partial, c->ctr);
   LAUNCH(k_sink_reduce, 1, 256, 0, nw, c->n_sink, c->sink_partial, c->S, do_sinks);
-  { int r_ = allreduce(c, c->S.ax, (size_t)3 * SPH_MAX_SINKS, NC_FLOAT64, NC_SUM); if (r_) return r_; }
+  stage_end(c);
+  if (c->n_ranks > 1) { stage_begin(c, ST_COMM); int r_ = allreduce(c, c->S.ax, (size_t)3 * SPH_MAX_SINKS, NC_FLOAT64, NC_SUM); if (r_) return r_; stage_end(c); }
+  stage_begin(c, ST_GRAVITY);
   LAUNCH(k_sink_pairs, 1, 32, 0, c->n_sink, c->S, c->dp.G, do_sinks);
   stage_end(c);
   return SPH_OK;

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsph_b200.so")
 _LIB = None
 
-STAGES = ("keys", "sort", "tree", "density", "gravity", "sph", "integrate", "h_iter", "cull")
+STAGES = ("keys", "sort", "tree", "density", "gravity", "sph", "integrate", "h_iter", "cull", "comm")
 
 
 class SphError(RuntimeError):
