@@ -46,6 +46,15 @@ struct __align__(16) GNode {
   int    flags;           // bit0: childless (leaf or depth-limited multi-particle node)
 };
 
+// The same node in the gravity walk layout: children contiguous at [child, child + nchild); nchild == 0 for
+// leaves and depth-limited childless nodes.
+struct __align__(16) WNode {
+  double cx, cy, cz, m;
+  double size;
+  int    child;
+  int    nchild;
+};
+
 // float AABBs rounded outward; pos = particle positions, reach = union of leaf boxes expanded by 2h
 struct __align__(16) BvhBox { float plo[3], phi[3], rlo[3], rhi[3]; };
 

@@ -46,7 +46,7 @@ enum { NC_UINT64 = 5, NC_FLOAT64 = 8, NC_SUM = 0, NC_MIN = 3 };
 }  // namespace
 
 struct sph_ctx {
-  sph_params p; DevParams dp; int device = 0; cudaStream_t stream = nullptr;
+  sph_params p; DevParams dp; int device = 0; int n_sm = 148; cudaStream_t stream = nullptr;
   std::string err;
   int64_t n = 0, cap = 0, n_upload = 0; int n_sink = 0;
   // particle state, double buffered for the Morton re-order / compaction
@@ -59,6 +59,7 @@ struct sph_ctx {
   BvhBox* bvh = nullptr; size_t bvh_cap = 0; BvhInfo bi;
   int *node_count = nullptr, *gsize = nullptr, *gfirst = nullptr; int2* groups = nullptr; int n_groups = 0;
   GNode* nodes = nullptr; int *node_part = nullptr, *parent = nullptr, *nchild = nullptr, *arrive = nullptr, *cnt = nullptr, *off = nullptr;
+  WNode* wnodes = nullptr; int *wcount = nullptr, *wstart = nullptr, *widx = nullptr; int2* grav_spill = nullptr;   // gravity walk layout
   RootBox* root = nullptr; double* partial = nullptr; int n_partial = 0;
   void* cub_tmp = nullptr; size_t cub_bytes = 0;
   double *d_wt = nullptr, *d_dwt = nullptr, *d_gt = nullptr;
@@ -129,15 +130,17 @@ int ensure_capacity(sph_ctx* c, int64_t n) {
   DA(c->node_count, 2 * cap); DA(c->gsize, cap); DA(c->gfirst, cap); DA(c->groups, cap);
   DA(c->nodes, 2 * cap); DA(c->node_part, 2 * cap); DA(c->parent, 2 * cap); DA(c->nchild, 2 * cap); DA(c->arrive, 2 * cap);
   DA(c->cnt, cap + 1); DA(c->off, cap + 1);
+  DA(c->wnodes, 2 * cap); DA(c->wcount, 2 * cap); DA(c->wstart, 2 * cap); DA(c->widx, 2 * cap);
   DA(c->keep, cap); DA(c->pos, cap); DA(c->stage_d, cap); DA(c->stage_d2, cap);
   // CUB temp: radix sort pairs (u64,int), exclusive scan, select
-  size_t b1 = 0, b2 = 0, b3 = 0, b4 = 0;
+  size_t b1 = 0, b2 = 0, b3 = 0, b4 = 0, b5 = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, b5, c->wcount, c->wstart, (int)(2 * cap), c->stream);
   cub::DeviceSelect::Flagged(nullptr, b4, cub::CountingInputIterator<int>(0), c->gsize, c->gfirst, c->d_nsel, (int)cap, c->stream);
   cub::DoubleBuffer<uint64_t> dk(c->key[0], c->key[1]); cub::DoubleBuffer<int> dv(c->perm[0], c->perm[1]);
   cub::DeviceRadixSort::SortPairs(nullptr, b1, dk, dv, (int)cap, 0, 64, c->stream);
   cub::DeviceScan::ExclusiveSum(nullptr, b2, c->cnt, c->off, (int)cap + 1, c->stream);
   cub::DeviceSelect::Flagged(nullptr, b3, c->perm[0], c->keep, c->perm[1], c->d_nsel, (int)cap, c->stream);
-  c->cub_bytes = std::max(std::max(b1, b4), std::max(b2, b3)) + 256;
+  c->cub_bytes = std::max(std::max(std::max(b1, b4), std::max(b2, b3)), b5) + 256;
   if (c->cub_tmp) { cudaFree(c->cub_tmp); c->cub_tmp = nullptr; }
   if (cudaMalloc(&c->cub_tmp, c->cub_bytes) != cudaSuccess) { c->err = "cudaMalloc(cub temp)"; cudaGetLastError(); return SPH_ERR_OOM; }
   for (int b = 0; b < 2; ++b) if (c->key_lo[b]) { cudaFree(c->key_lo[b]); c->key_lo[b] = nullptr; }
@@ -315,10 +318,14 @@ int build_tree_impl(sph_ctx* c, bool* retry_two_word) {
     const int nn = n + n_int;
     c->counts.n_nodes = nn;
     LAUNCH(k_oct_nodes<true>, cdiv(n, T), T, 0, n, c->key[0], klo, c->dp.lmax, c->root, c->cnt, c->off, nn, c->nodes, c->node_part, c->node_count);
-    LAUNCH(k_oct_link, cdiv(nn, T), T, 0, nn, c->nodes, c->node_part, c->parent, c->nchild);
+    LAUNCH(k_oct_link, cdiv(nn, T), T, 0, nn, c->nodes, c->node_part, c->parent, c->nchild, c->wcount);
+    bytes = c->cub_bytes;
+    CK(cub::DeviceScan::ExclusiveSum(c->cub_tmp, bytes, c->wcount, c->wstart, nn, c->stream));
+    CK(cudaMemsetAsync(c->widx, 0xff, sizeof(int) * (size_t)nn, c->stream));
+    LAUNCH(k_oct_widx, cdiv(nn, T), T, 0, nn, c->nodes, c->wcount, c->wstart, c->widx);
     CK(cudaMemsetAsync(c->arrive, 0, sizeof(int) * (size_t)nn, c->stream));
     LAUNCH(k_oct_up, cdiv(n, T), T, 0, n, c->off, c->cnt, s.x, s.y, s.z, s.m, s.h, c->level, c->root, c->nodes, c->parent, c->nchild, c->arrive);
-    LAUNCH(k_oct_finalize, cdiv(nn, T), T, 0, nn, c->nodes);
+    LAUNCH(k_oct_finalize, cdiv(nn, T), T, 0, nn, c->nodes, c->wcount, c->wstart, c->widx, c->wnodes);
     // walk groups (cell-aligned buckets) and the implicit 8-ary BVH over them
     CK(cudaMemsetAsync(c->gsize, 0, sizeof(int) * (size_t)n, c->stream));
     LAUNCH(k_group_mark, cdiv(nn, T), T, 0, nn, c->nodes, c->node_part, c->node_count, c->gsize);
@@ -356,8 +363,7 @@ size_t force_smem(const sph_ctx* c, int nwarp) {
 }
 int walk_grid(const sph_ctx* c, int nwarp) {
   const int nchunk = c->g1 - c->g0;
-  int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
-  return std::max(1, std::min(cdiv(nchunk, nwarp), sms));
+  return std::max(1, std::min(cdiv(nchunk, nwarp), c->n_sm));
 }
 
 DensityArrays dens_arrays(sph_ctx* c) {
@@ -398,22 +404,30 @@ int run_force(sph_ctx* c) {
   if (c->n_ranks > 1) { stage_begin(c, ST_COMM); double* bufs[5] = {c->ax, c->ay, c->az, c->udot, c->adot}; int r_ = allgatherv(c, bufs, 5); if (r_) return r_; stage_end(c); }
   return SPH_OK;
 }
+size_t gravity_smem(const sph_ctx* c, int nwarp) { return (size_t)((c->p.nq + 1) + ((c->p.nq + 1) & 1)) * 8 + (size_t)nwarp * sizeof(GravWarpSmem); }
 int run_gravity(sph_ctx* c, int do_grav, int do_sinks) {
-  const int T = 256;
   stage_begin(c, ST_GRAVITY);
   StateArrays s = state_of(c, c->cur);
-  const int nloc = c->p1 - c->p0;
-  const int nw = cdiv(nloc, 32);
-  const int nb = cdiv(nloc, T);
+  const int ng = c->g1 - c->g0;
   const int ns = do_sinks ? c->n_sink : 0;
-  if ((size_t)(nw + 8) * std::max(ns, 1) * 3 > c->sink_partial_cap) {
-    c->sink_partial_cap = (size_t)(nw + 8) * std::max(ns, 1) * 3 * 2;
+  if ((size_t)(ng + 8) * std::max(ns, 1) * 3 > c->sink_partial_cap) {
+    c->sink_partial_cap = (size_t)(ng + 8) * std::max(ns, 1) * 3 * 2;
     DA(c->sink_partial, c->sink_partial_cap);
   }
-  if (nb > 0)
-    LAUNCH(k_gravity, nb, T, (size_t)(c->p.nq + 1) * 8, c->p0, c->p1, c->dp, c->nodes, (int)c->counts.n_nodes, s.x, s.y, s.z, s.h, s.m, c->d_gt,
-           c->ax, c->ay, c->az, do_grav, ns, c->S, c->sink_partial, c->ctr);
-  LAUNCH(k_sink_reduce, 1, 256, 0, nw, c->n_sink, c->sink_partial, c->S, do_sinks);
+  if (ng > 0) {
+    const int grid = walk_grid(c, GW_WARPS);
+    if (!c->grav_spill) DA(c->grav_spill, (size_t)c->n_sm * GW_WARPS * GW_SPILL);
+    LAUNCH(k_set_int, 1, 1, 0, c->work, c->g0);
+    LAUNCH(k_gravity, grid, GW_WARPS * 32, gravity_smem(c, GW_WARPS), c->g0, c->g1, c->groups, c->bvh, c->dp, c->wnodes, s.x, s.y, s.z, s.h, s.m, c->d_gt,
+           c->ax, c->ay, c->az, do_grav, ns, c->S, c->sink_partial, c->ctr, c->work, c->grav_spill, &c->sc->err);
+  }
+#ifdef GW_DEBUG
+  { unsigned long long d[16]; cudaStreamSynchronize(c->stream); cudaMemcpyFromSymbol(d, gw_dbg, sizeof(d)); unsigned long long z[16] = {}; cudaMemcpyToSymbol(gw_dbg, z, sizeof(z));
+    fprintf(stderr, "GWDBG trips %llu popped %llu A %llu O %llu M %llu evals %llu entries %llu lanework %llu spills %llu maxsn %llu mixacc %llu mixopen %llu\n", d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7], d[8], d[9], d[10], d[11]);
+    unsigned long long hh[33]; cudaMemcpyFromSymbol(hh, gw_hist, sizeof(hh)); unsigned long long zz[33] = {}; cudaMemcpyToSymbol(gw_hist, zz, sizeof(zz));
+    fprintf(stderr, "GWHIST"); for (int i = 0; i < 33; ++i) fprintf(stderr, " %llu", hh[i]); fprintf(stderr, "\n"); }
+#endif
+  LAUNCH(k_sink_reduce, 1, 256, 0, ng, c->n_sink, c->sink_partial, c->S, do_sinks);
   stage_end(c);
   if (c->n_ranks > 1) { stage_begin(c, ST_COMM); int r_ = allreduce(c, c->S.ax, (size_t)3 * SPH_MAX_SINKS, NC_FLOAT64, NC_SUM); if (r_) return r_; stage_end(c); }
   stage_begin(c, ST_GRAVITY);
@@ -452,6 +466,7 @@ int fetch_counters(sph_ctx* c) {
 }
 
 int check_device_error(sph_ctx* c) {
+  if (c->h_sc->err == 2) { c->err = "gravity walk: node stack overflow (GW_SPILL)"; return SPH_ERR_STATE; }
   if (c->h_sc->err) {
     c->err = "particles share a full 126-bit descent key (closer than root_size/2^42) while max_depth > 42";
     return SPH_ERR_DEPTH;
@@ -642,12 +657,13 @@ int sph_create(const sph_params* p, int32_t device, sph_ctx** out) {
   cudaMemset(c->ctr, 0, sizeof(WalkCounters));
   // opt in to large dynamic shared memory
   int maxsm = 0; cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
-  size_t need = std::max(density_smem(c, 16), force_smem(c, 16));
+  cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, device);
+  size_t need = std::max(std::max(density_smem(c, 16), force_smem(c, 16)), gravity_smem(c, GW_WARPS));
   if ((size_t)maxsm < need) { c->err = "device shared memory too small for the walk kernels"; return fail(SPH_ERR_CUDA); }
   cudaFuncSetAttribute(k_density<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)density_smem(c, 16));
   cudaFuncSetAttribute(k_density<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)density_smem(c, 16));
   cudaFuncSetAttribute(k_force, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)force_smem(c, 16));
-  cudaFuncSetAttribute(k_gravity, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((c->p.nq + 1) * 8));
+  cudaFuncSetAttribute(k_gravity, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gravity_smem(c, GW_WARPS));
   cudaFuncSetAttribute(k_neighbours, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   if (cudaGetLastError() != cudaSuccess) { c->err = "cudaFuncSetAttribute failed (was the library built for this GPU's architecture?)"; return fail(SPH_ERR_CUDA); }
   *out = c;
@@ -663,6 +679,7 @@ int sph_destroy(sph_ctx* c) {
   for (int b = 0; b < 2; ++b) { for (int f = 0; f < 10; ++f) F(c->st[b][f]); F(c->id[b]); F(c->key[b]); F(c->key_lo[b]); F(c->perm[b]); F(c->acc_key[b]); F(c->acc_val[b]); }
   F(c->rho); F(c->omega); F(c->prs); F(c->cs); F(c->por2); F(c->ax); F(c->ay); F(c->az); F(c->udot); F(c->adot);
   F(c->node_count); F(c->gsize); F(c->gfirst); F(c->groups); F(c->level); F(c->lcx); F(c->lcy); F(c->lcz); F(c->reach); F(c->bvh); F(c->nodes); F(c->node_part); F(c->parent); F(c->nchild);
+  F(c->wnodes); F(c->wcount); F(c->wstart); F(c->widx); F(c->grav_spill);
   F(c->arrive); F(c->cnt); F(c->off); F(c->root); F(c->partial); F(c->cub_tmp); F(c->d_wt); F(c->d_dwt); F(c->d_gt);
   F(c->sink_buf); F(c->sink_partial); F(c->sc); F(c->ctr); F(c->work); F(c->keep); F(c->d_nsel); F(c->pos); F(c->stage_d); F(c->stage_d2);
   if (c->h_sc) cudaFreeHost(c->h_sc);

@@ -4,107 +4,263 @@
 // and sink_gravforces (F:559-591 | V:691-726).
 //
 // The reference's opening decision is per particle: `size/dist < theta .or. no children` with
-// dist = sqrt(|x - COM|^2 + 0.001*smoothing) (F:275-278).  To keep every accepted-node set identical, the
-// decision stays per lane; what changes is the traversal: one warp owns 32 Morton-adjacent particles and
-// walks the depth-first-preorder node array in lock step.  A lane that accepted node v sets its private
-// skip index to next[v] and sleeps until the walk leaves v's subtree; the warp descends (v+1) while any
-// lane still wants to open, else jumps to next[v].  Node records are warp-uniform 48-byte loads.
-// The visit order per lane is exactly the reference's recursion order (children 1..8), so the
-// accumulation order of the gravity terms matches the reference.
+// dist = sqrt(|x - COM|^2 + 0.001*smoothing) (F:275-278), and every accepted-node set stays identical to it.
+// What changes is who decides.  One warp owns a walk group (<= 32 Morton-adjacent particles in one octree
+// cell, lane = particle) and keeps a stack of (node, lane mask) entries in shared memory.  Each trip pops up
+// to 32 entries and classifies them lane-parallel against the group's bounding box (lane = node, one
+// coalesced 48-byte load each, child blocks are contiguous in the walk layout):
+//   * every particle of the group accepts (even the closest point of the box passes the test with a 1e-9
+//     margin, or the node is childless)            -> interaction list, mask unchanged;
+//   * every particle opens (even the farthest point fails it)  -> push the child block, mask unchanged;
+//   * otherwise the node is mixed: each particle in the mask runs the reference's own test (cheap form with
+//     a 1e-12 guard band, exact uncontracted arithmetic inside the band); the accepting lanes become the
+//     list entry's mask, the opening lanes the mask of the pushed children.
+// The interaction list (COM, G*M, mask) is evaluated in batches with lane = particle, so the force
+// arithmetic runs with every live lane busy and node data are read once per group instead of once per
+// particle.  The accumulation order differs from the reference's recursion order (rounding-level only).
 #pragma once
 #include "sph_common.cuh"
 #include "sph_walk.cuh"
 
 struct SinkArrays { double *x, *y, *z, *vx, *vy, *vz, *m, *radius, *ax, *ay, *az; };
 
-struct NodeRegs { double cx, cy, cz, m, size; int next, flags; };
-__device__ __forceinline__ NodeRegs load_node(const GNode* __restrict__ nodes, int v) {
-  const double2* p = reinterpret_cast<const double2*>(nodes + v);
-  const double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
-  NodeRegs r; r.cx = a.x; r.cy = a.y; r.cz = b.x; r.m = b.y; r.size = c.x;
-  r.next = __double2loint(c.y); r.flags = __double2hiint(c.y);
-  return r;
+#define GW_WARPS 24         // warps per block
+#define GW_STACK 384        // (node, mask) entries per warp in shared memory
+#define GW_LIST  64         // interaction-list entries per warp (evaluated when more than 32 are waiting)
+#define GW_SPILL 8192       // per-warp overflow entries in global memory (never reached in practice; loud if it is)
+
+#ifdef GW_DEBUG
+__device__ unsigned long long gw_dbg[16];
+__device__ unsigned long long gw_hist[33];
+#define GWD(i, v) do { if (lane == 0) atomicAdd(&gw_dbg[i], (unsigned long long)(v)); } while (0)
+__global__ void k_gw_dbg_print() {
+  printf("GWDBG trips %llu popped %llu A %llu O %llu M %llu evals %llu entries %llu lanework %llu spills %llu maxsn %llu mixacc %llu mixopen %llu\n",
+         gw_dbg[0], gw_dbg[1], gw_dbg[2], gw_dbg[3], gw_dbg[4], gw_dbg[5], gw_dbg[6], gw_dbg[7], gw_dbg[8], gw_dbg[9], gw_dbg[10], gw_dbg[11]);
+  for (int i = 0; i < 16; ++i) gw_dbg[i] = 0;
+}
+#else
+#define GWD(i, v)
+#endif
+
+struct GravWarpSmem {
+  int2     stack[GW_STACK];
+  double2  lxy[GW_LIST], lzg[GW_LIST];     // (cx, cy), (cz, G*M)
+  unsigned lmask[GW_LIST];
+  double   mcx[32], mcy[32], mcz[32], mgm[32], msize[32];   // mixed nodes of the current trip
+  int      mchild[32], mnch[32]; unsigned mmask[32];
+};
+
+// 1/sqrt(x): MUFU seed (~2^-20) + one Halley step (cubic: ~2^-58), x > 0
+__device__ __forceinline__ double fast_rsqrt(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double e = fma(-(x * y), y, 1.0);
+  const double t = fma(0.375, e, 0.5);
+  return fma(y * e, t, y);
 }
 
-// layout of dynamic smem: grav table (nq+1 doubles)
-__global__ void __launch_bounds__(256, 4)
-k_gravity(int p_begin, int p_end, DevParams P, const GNode* __restrict__ nodes, int n_nodes,
-          const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
+// one list entry against one particle: a -= G M g(dist/h) dir / dist^3                  F:279-281 | F:129-146
+__device__ __forceinline__ void grav_term(const double2 a, const double2 b, const bool on, const double xi, const double yi,
+                                          const double zi, const double inv_h, const double soft, const double* __restrict__ gt,
+                                          const int nq, const double dq, const double inv_dq, double& gx, double& gy, double& gz) {
+  const double dx = xi - a.x, dy = yi - a.y, dz = zi - b.x;                  // F:274
+  const double d2 = fma(dx, dx, fma(dy, dy, fma(dz, dz, soft)));
+  const bool v = on & (d2 > 0.0);                                           // F:279 (M > 0 is checked when the entry is listed)
+  const double rs = fast_rsqrt(v ? d2 : 1.0);
+  const double q = (d2 * rs) * inv_h;
+  double W = 1.0;
+  if (q <= 2.0) W = table_lerp1(gt, nq, dq, inv_dq, q);
+  double f = (b.y * W) * (rs * rs * rs);
+  f = v ? f : 0.0;
+  gx -= f * dx; gy -= f * dy; gz -= f * dz;
+}
+
+// dynamic smem: grav table (nq+1 doubles, padded to even) then one GravWarpSmem per warp
+__global__ void __launch_bounds__(GW_WARPS * 32, 1)
+k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox* __restrict__ gbox, DevParams P,
+          const WNode* __restrict__ wn, const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
           const double* __restrict__ h, const double* __restrict__ m, const double* __restrict__ g_gt,
           double* __restrict__ ax, double* __restrict__ ay, double* __restrict__ az,
-          int do_grav, int n_sink, SinkArrays S, double* __restrict__ sink_partial, WalkCounters* ctr) {
-  extern __shared__ double gt[];
+          int do_grav, int n_sink, SinkArrays S, double* __restrict__ sink_partial, WalkCounters* ctr, int* work,
+          int2* __restrict__ spill, int* err_flag) {
+  extern __shared__ __align__(16) double gsm[];
+  double* gt = gsm;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  GravWarpSmem& W = reinterpret_cast<GravWarpSmem*>(gsm + (P.nq + 1) + ((P.nq + 1) & 1))[warp];
   for (int i = threadIdx.x; i <= P.nq; i += blockDim.x) gt[i] = g_gt[i];
   __syncthreads();
-  const int i = p_begin + blockIdx.x * blockDim.x + threadIdx.x;
-  const int lane = threadIdx.x & 31;
-  const bool live = i < p_end;
-  const double xi = live ? x[i] : 0.0, yi = live ? y[i] : 0.0, zi = live ? z[i] : 0.0;
-  const double hi = live ? (P.variable_h ? h[i] : P.h_fixed) : 1.0;
-  const double inv_h = 1.0 / hi;
-  const double soft = P.soft_hi ? 0.001 * hi : 0.001 * P.h_fixed;          // F:275 | V:296 | T:298
+  int2* myspill = spill + (size_t)(blockIdx.x * (blockDim.x >> 5) + warp) * GW_SPILL;
+  const unsigned lt_mask = (1u << lane) - 1u;
   const double theta = P.theta, theta2 = theta * theta;
-  double gx = 0.0, gy = 0.0, gz = 0.0;
-  unsigned opened = 0, accepted = 0;
-  if (do_grav) {
-    int cur = 0;
-    int skip = live ? 0 : 0x7fffffff;
-    while (cur < n_nodes) {
-      const NodeRegs N = load_node(nodes, cur);
-      bool open = false;
-      if (cur >= skip) {
-        const double dx = xi - N.cx, dy = yi - N.cy, dz = zi - N.cz;          // F:274
-        const double d2 = dx * dx + dy * dy + dz * dz + soft;
-        bool accept;
-        if (N.flags & 1) accept = true;                                       // .not. allocated(children)
-        else {
-          const double s2 = N.size * N.size, t2 = theta2 * d2;
+  unsigned long long n_open = 0, n_acc = 0;
+
+  for (;;) {
+    int chunk = 0;
+    if (lane == 0) chunk = atomicAdd(work, 1);
+    chunk = __shfl_sync(FULL_MASK, chunk, 0);
+    if (chunk >= g_end) break;
+    const int2 tg = groups[chunk];
+    const int i = tg.x + lane;
+    const bool live = lane < tg.y;
+    const double xi = live ? x[i] : 0.0, yi = live ? y[i] : 0.0, zi = live ? z[i] : 0.0;
+    const double hi = live ? (P.variable_h ? h[i] : P.h_fixed) : 1.0;
+    const double inv_h = 1.0 / hi;
+    const double soft = P.soft_hi ? 0.001 * hi : 0.001 * P.h_fixed;          // F:275 | V:296 | T:298
+    double gx = 0.0, gy = 0.0, gz = 0.0, hx = 0.0, hy = 0.0, hz = 0.0;
+
+    auto evaluate_list = [&](int cnt) {
+      int k = 0;
+#ifdef GW_DEBUG
+      GWD(5, 1); GWD(6, cnt);
+      { unsigned long long w = 0; for (int q = 0; q < cnt; ++q) { int pc = __popc(W.lmask[q]); w += pc; if (lane == 0) { atomicAdd(&gw_hist[pc], 1ull); } } GWD(7, w); }
+#endif
+      for (; k + 1 < cnt; k += 2) {          // two independent chains per trip
+        const unsigned m0 = W.lmask[k], m1 = W.lmask[k + 1];
+        grav_term(W.lxy[k], W.lzg[k], (m0 >> lane) & 1u, xi, yi, zi, inv_h, soft, gt, P.nq, P.dq, P.inv_dq, gx, gy, gz);
+        grav_term(W.lxy[k + 1], W.lzg[k + 1], (m1 >> lane) & 1u, xi, yi, zi, inv_h, soft, gt, P.nq, P.dq, P.inv_dq, hx, hy, hz);
+      }
+      if (k < cnt) grav_term(W.lxy[k], W.lzg[k], (W.lmask[k] >> lane) & 1u, xi, yi, zi, inv_h, soft, gt, P.nq, P.dq, P.inv_dq, gx, gy, gz);
+    };
+
+    if (do_grav) {
+      const BvhBox gb = gbox[chunk];
+      const double lo0 = gb.plo[0], lo1 = gb.plo[1], lo2 = gb.plo[2], hi0 = gb.phi[0], hi1 = gb.phi[1], hi2 = gb.phi[2];
+      const double soft_min = warp_min(live ? soft : INFINITY), soft_max = warp_max(live ? soft : 0.0);
+      const unsigned livemask = __ballot_sync(FULL_MASK, live);
+      int sn = 1, gsp = 0, ln = 0;
+      if (lane == 0) W.stack[0] = make_int2(0, (int)livemask);
+      __syncwarp();
+
+      auto make_room = [&](int need) {       // keep the pushes inside the shared-memory stack
+        if (sn + need <= GW_STACK) return;
+        GWD(8, 1);
+        __syncwarp();
+        if (gsp + sn > GW_SPILL) { if (lane == 0) atomicExch(err_flag, 2); sn = 0; }     // loud: the host returns an error
+        for (int e = lane; e < sn; e += 32) myspill[gsp + e] = W.stack[e];
+        gsp += sn; sn = 0;
+        __syncwarp();
+      };
+
+      for (;;) {
+        if (sn == 0) {
+          if (gsp == 0) break;
+          const int take = gsp < GW_STACK / 2 ? gsp : GW_STACK / 2;
+          for (int e = lane; e < take; e += 32) W.stack[e] = myspill[gsp - take + e];
+          gsp -= take; sn = take;
+          __syncwarp();
+        }
+#ifdef GW_DEBUG
+        if (lane == 0) atomicMax(&gw_dbg[9], (unsigned long long)sn);
+#endif
+        const int npop = sn < 32 ? sn : 32;
+        const bool valid = lane < npop;
+        const int2 e = valid ? W.stack[sn - 1 - lane] : make_int2(0, 0);
+        __syncwarp();
+        sn -= npop;
+        // ---- lane = node: classify against the group box
+        int cls = 0;                           // 1 all accept, 2 all open, 3 mixed
+        double ncx = 0.0, ncy = 0.0, ncz = 0.0, nm = 0.0, nsize = 0.0; int nchild = 0, nnch = 0;
+        if (valid) {
+          const double2* p = reinterpret_cast<const double2*>(wn + e.x);
+          const double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+          ncx = a.x; ncy = a.y; ncz = b.x; nm = b.y; nsize = c.x;
+          nchild = __double2loint(c.y); nnch = __double2hiint(c.y);
+          const double nx = fmax(fmax(lo0 - ncx, ncx - hi0), 0.0), ny = fmax(fmax(lo1 - ncy, ncy - hi1), 0.0), nz = fmax(fmax(lo2 - ncz, ncz - hi2), 0.0);
+          const double fx = fmax(fabs(ncx - lo0), fabs(ncx - hi0)), fy = fmax(fabs(ncy - lo1), fabs(ncy - hi1)), fz = fmax(fabs(ncz - lo2), fabs(ncz - hi2));
+          const double dmin2 = nx * nx + ny * ny + nz * nz + soft_min, dmax2 = fx * fx + fy * fy + fz * fz + soft_max;
+          const double s2 = nsize * nsize;
+          if (nnch == 0 || s2 < theta2 * dmin2 * (1.0 - 1e-9)) cls = 1;
+          else if (s2 > theta2 * dmax2 * (1.0 + 1e-9)) cls = 2;
+          else cls = 3;
+        }
+        const unsigned emask = (unsigned)e.y;
+        if (cls == 1) n_acc += __popc(emask);
+        if (cls == 2) n_open += __popc(emask);
+        const unsigned balA = __ballot_sync(FULL_MASK, cls == 1), balM = __ballot_sync(FULL_MASK, cls == 3);
+        const unsigned balL = __ballot_sync(FULL_MASK, cls == 1 && nm > 0.0);      // F:279: massless nodes add nothing
+        if (cls == 1 && nm > 0.0) {
+          const int pos = ln + __popc(balL & lt_mask);
+          W.lxy[pos] = make_double2(ncx, ncy); W.lzg[pos] = make_double2(ncz, P.G * nm); W.lmask[pos] = emask;
+        }
+        ln += __popc(balL);
+        const int nmix = __popc(balM);
+        GWD(0, 1); GWD(1, npop); GWD(2, __popc(balA)); GWD(3, npop - __popc(balA) - nmix); GWD(4, nmix);
+        if (cls == 3) {
+          const int pos = __popc(balM & lt_mask);
+          W.mcx[pos] = ncx; W.mcy[pos] = ncy; W.mcz[pos] = ncz; W.mgm[pos] = P.G * nm; W.msize[pos] = nsize;
+          W.mchild[pos] = nchild; W.mnch[pos] = nnch; W.mmask[pos] = emask;
+        }
+        // children of the all-open nodes: exclusive scan of the block sizes over the lanes
+        const int nch = (cls == 2) ? nnch : 0;
+        int incl = nch;
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL_MASK, incl, o); if (lane >= o) incl += t; }
+        const int total = __shfl_sync(FULL_MASK, incl, 31);
+        make_room(total);
+        for (int k = 0; k < nch; ++k) W.stack[sn + incl - nch + k] = make_int2(nchild + k, (int)emask);
+        sn += total;
+        __syncwarp();
+        // ---- lane = particle: the reference's own test on the mixed nodes
+        for (int q = 0; q < nmix; ++q) {
+          const unsigned mm = W.mmask[q];
+          const bool in = (mm >> lane) & 1u;
+          const double dx = xi - W.mcx[q], dy = yi - W.mcy[q], dz = zi - W.mcz[q];          // F:274
+          const double d2 = dx * dx + dy * dy + dz * dz + soft;
+          const double size = W.msize[q];
+          const double s2 = size * size, t2 = theta2 * d2;
+          bool accept;
           if (s2 < t2 * (1.0 - 1e-12)) accept = true;
           else if (s2 > t2 * (1.0 + 1e-12)) accept = false;
           else {   // borderline: redo the reference's arithmetic exactly (no contraction)       F:275-278
-            double e2 = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)), soft);
-            accept = __ddiv_rn(N.size, __dsqrt_rn(e2)) < theta;
+            const double e2 = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)), soft);
+            accept = __ddiv_rn(size, __dsqrt_rn(e2)) < theta;
+          }
+          const unsigned balAcc = __ballot_sync(FULL_MASK, in && accept), balOpen = __ballot_sync(FULL_MASK, in && !accept);
+          GWD(10, balAcc != 0); GWD(11, balOpen != 0);
+          if (balAcc) {
+            if (lane == 0) n_acc += __popc(balAcc);
+            if (W.mgm[q] > 0.0) {
+              if (lane == 0) { W.lxy[ln] = make_double2(W.mcx[q], W.mcy[q]); W.lzg[ln] = make_double2(W.mcz[q], W.mgm[q]); W.lmask[ln] = balAcc; }
+              ++ln;
+            }
+          }
+          if (balOpen) {
+            const int nc = W.mnch[q];
+            make_room(nc);
+            if (lane < nc) W.stack[sn + lane] = make_int2(W.mchild[q] + lane, (int)balOpen);
+            if (lane == 0) n_open += __popc(balOpen);
+            sn += nc;
           }
         }
-        if (accept) {
-          ++accepted;
-          skip = N.next;
-          if (N.m > 0.0 && d2 > 0.0) {                                        // F:279
-            double dist, rs; fast_sqrt_rsqrt(d2, dist, rs);
-            const double q = dist * inv_h;
-            double W = 1.0;
-            if (q <= 2.0) W = table_lerp1(gt, P.nq, P.dq, P.inv_dq, q);       // F:129-146
-            const double f = (P.G * N.m * W) * (rs * rs * rs);                // F:281
-            gx -= f * dx; gy -= f * dy; gz -= f * dz;
-          }
-        } else { open = true; ++opened; }
+        __syncwarp();
+        if (ln > GW_LIST - 32) { evaluate_list(ln); ln = 0; __syncwarp(); }
       }
-      cur = __any_sync(FULL_MASK, open) ? cur + 1 : N.next;
+      if (ln > 0) evaluate_list(ln);
+      __syncwarp();
+      gx += hx; gy += hy; gz += hz;
     }
+    // direct sink <-> gas (unsoftened) F:567-576; per-group partial sums of the sink side (no block barrier)
+    for (int s = 0; s < n_sink; ++s) {
+      const double vx_ = xi - S.x[s], vy_ = yi - S.y[s], vz_ = zi - S.z[s];
+      const double dr = sqrt(vx_ * vx_ + vy_ * vy_ + vz_ * vz_);
+      const double d3 = dr * dr * dr;
+      double wx = P.G * vx_ / d3, wy = P.G * vy_ / d3, wz = P.G * vz_ / d3;    // F:572
+      const double ms = S.m[s];
+      double px = 0.0, py = 0.0, pz = 0.0;
+      if (live) {
+        gx -= ms * wx; gy -= ms * wy; gz -= ms * wz;                            // F:574
+        const double mi = m[i];
+        px = mi * wx; py = mi * wy; pz = mi * wz;                               // F:573
+      }
+      px = warp_sum(px); py = warp_sum(py); pz = warp_sum(pz);
+      if (lane == 0) {
+        double* o = sink_partial + ((size_t)(chunk - g_begin) * n_sink + s) * 3;
+        o[0] = px; o[1] = py; o[2] = pz;
+      }
+    }
+    if (live) { ax[i] = gx; ay[i] = gy; az[i] = gz; }
   }
-  // direct sink <-> gas (unsoftened) F:567-576; per-warp partial sums of the sink side (no block barrier)
-  const int gwarp = (i - p_begin) >> 5;
-  for (int s = 0; s < n_sink; ++s) {
-    const double vx_ = xi - S.x[s], vy_ = yi - S.y[s], vz_ = zi - S.z[s];
-    const double dr = sqrt(vx_ * vx_ + vy_ * vy_ + vz_ * vz_);
-    const double d3 = dr * dr * dr;
-    double wx = P.G * vx_ / d3, wy = P.G * vy_ / d3, wz = P.G * vz_ / d3;    // F:572
-    const double ms = S.m[s];
-    double px = 0.0, py = 0.0, pz = 0.0;
-    if (live) {
-      gx -= ms * wx; gy -= ms * wy; gz -= ms * wz;                            // F:574
-      const double mi = m[i];
-      px = mi * wx; py = mi * wy; pz = mi * wz;                               // F:573
-    }
-    px = warp_sum(px); py = warp_sum(py); pz = warp_sum(pz);
-    if (lane == 0) {
-      double* o = sink_partial + ((size_t)gwarp * n_sink + s) * 3;
-      o[0] = px; o[1] = py; o[2] = pz;
-    }
-  }
-  if (live) { ax[i] = gx; ay[i] = gy; az[i] = gz; }
-  opened = (unsigned)warp_sum_ll(opened); accepted = (unsigned)warp_sum_ll(accepted);
-  if (lane == 0 && do_grav) { atomicAdd(&ctr->grav_opened, (unsigned long long)opened); atomicAdd(&ctr->grav_accepted, (unsigned long long)accepted); }
+  n_open = (unsigned long long)warp_sum_ll((long long)n_open); n_acc = (unsigned long long)warp_sum_ll((long long)n_acc);
+  if (lane == 0 && do_grav) { atomicAdd(&ctr->grav_opened, n_open); atomicAdd(&ctr->grav_accepted, n_acc); }
 }
 
 // fold per-warp sink partials in a fixed order (deterministic). One block of 256.

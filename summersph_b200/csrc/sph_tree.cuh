@@ -294,16 +294,33 @@ __global__ void k_oct_nodes(int n, const uint64_t* __restrict__ key, const uint6
   node_count[slot] = 1;
 }
 
-// parent / child-count links: one thread per preorder slot; internal nodes walk their child chain
+// parent / child-count links: one thread per preorder slot; internal nodes walk their child chain.
+// wcount = number of children the gravity walk may descend into (0 for leaves and for the depth-limited
+// childless multi-particle nodes, F:182): sizes the child blocks of the walk layout below.
 __global__ void k_oct_link(int n_nodes, const GNode* __restrict__ nodes, const int* __restrict__ node_part,
-                           int* __restrict__ parent, int* __restrict__ nchild) {
+                           int* __restrict__ parent, int* __restrict__ nchild, int* __restrict__ wcount) {
   int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= n_nodes) return;
   if (v == 0) parent[0] = -1;
-  if (node_part[v] >= 0) { nchild[v] = 0; return; }
+  if (node_part[v] >= 0) { nchild[v] = 0; wcount[v] = 0; return; }
   int end = nodes[v].next, c = v + 1, k = 0;
   while (c < end) { parent[c] = v; ++k; c = nodes[c].next; }
   nchild[v] = k;
+  wcount[v] = (nodes[v].flags & 1) ? 0 : k;
+}
+
+// Walk layout of the octree: the children of a node are contiguous (block start = 1 + exclusive scan of
+// wcount in preorder), so one warp can classify up to 32 nodes per trip with lane-parallel loads and push
+// whole child blocks.  widx[v] = slot of preorder node v (-1: below a childless node, never visited).
+__global__ void k_oct_widx(int n_nodes, const GNode* __restrict__ nodes, const int* __restrict__ wcount,
+                           const int* __restrict__ wstart, int* __restrict__ widx) {
+  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n_nodes) return;
+  if (v == 0) widx[0] = 0;
+  if (wcount[v] == 0) return;
+  const int base = 1 + wstart[v];
+  int end = nodes[v].next, c = v + 1, k = 0;
+  while (c < end) { widx[c] = base + k; ++k; c = nodes[c].next; }
 }
 
 // bottom-up mass / first-moment sums: one thread per particle leaf, last arriver folds the parent
@@ -340,11 +357,19 @@ __global__ void k_oct_up(int n, const int* __restrict__ off, const int* __restri
   }
 }
 
-__global__ void k_oct_finalize(int n_nodes, GNode* nodes) {
+__global__ void k_oct_finalize(int n_nodes, GNode* nodes, const int* __restrict__ wcount, const int* __restrict__ wstart,
+                               const int* __restrict__ widx, WNode* __restrict__ wnodes) {
   int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= n_nodes) return;
-  double M = nodes[v].m;
-  if (M > 0.0) {                                                           // F:173-177
-    nodes[v].cx = __ddiv_rn(nodes[v].cx, M); nodes[v].cy = __ddiv_rn(nodes[v].cy, M); nodes[v].cz = __ddiv_rn(nodes[v].cz, M);
+  GNode g = nodes[v];
+  if (g.m > 0.0) {                                                         // F:173-177
+    g.cx = __ddiv_rn(g.cx, g.m); g.cy = __ddiv_rn(g.cy, g.m); g.cz = __ddiv_rn(g.cz, g.m);
+    nodes[v].cx = g.cx; nodes[v].cy = g.cy; nodes[v].cz = g.cz;
+  }
+  const int w = widx[v];
+  if (w >= 0) {
+    WNode o; o.cx = g.cx; o.cy = g.cy; o.cz = g.cz; o.m = g.m; o.size = g.size;
+    o.child = 1 + wstart[v]; o.nchild = wcount[v];
+    wnodes[w] = o;
   }
 }

@@ -128,6 +128,7 @@ struct DensityOp {
   float gplo[3], gphi[3];            // group position box (for the per-source prefilter)
   // lane state
   double xi, yi, zi, inv_h;
+  double r2max;                      // 4 h_i^2 (1 + 1e-9): beyond it q > 2 for certain and the term is an exact zero
   bool active;
   double accW, accB;                 // sum m_j w(q), sum m_j r dw(q)
   unsigned cand, contrib;
@@ -147,16 +148,19 @@ struct DensityOp {
     scx[s] = A.lcx[j]; scy[s] = A.lcy[j]; scz[s] = A.lcz[j]; sR[s] = A.reach[j];
   }
   __device__ __forceinline__ void consume(int count) {
-    unsigned mask = 0;
+    unsigned mask = 0, cmask = 0;
     if (active) {
 #pragma unroll 4
       for (int k = 0; k < count; ++k) {
         const double R = sR[k];
         const bool in = (fabs(xi - scx[k]) < R) & (fabs(yi - scy[k]) < R) & (fabs(zi - scz[k]) < R);   // F:443 | V:479
-        mask |= (in ? 1u : 0u) << k;
+        const double dx = xi - sx[k], dy = yi - sy[k], dz = zi - sz[k];
+        const bool nz = !(dx * dx + dy * dy + dz * dz > r2max);       // W(q > 2) = 0 exactly (F:112): only these need arithmetic
+        cmask |= (in ? 1u : 0u) << k;
+        mask |= ((in & nz) ? 1u : 0u) << k;
       }
     }
-    cand += __popc(mask);
+    cand += __popc(cmask);
     // two hits per trip, branch-free, so two independent dependency chains are in flight per lane
     double w2 = 0.0, b2 = 0.0;
     while (mask) {
@@ -224,7 +228,7 @@ k_density(int n_groups, const int2* __restrict__ groups, DevParams P, DensityArr
     const double mi = live ? A.m[i] : 0.0;
 
     if (!HITER) {
-      op.active = live; op.inv_h = 1.0 / hi; op.accW = 0.0; op.accB = 0.0;
+      op.active = live; op.inv_h = 1.0 / hi; op.r2max = 4.0 * hi * hi * (1.0 + 1e-9); op.accW = 0.0; op.accB = 0.0;
       neighbour_walk(op, groups, chunk, box, bi, stack, cq);
       if (live) {
         // W/(pi h^3), dW/(pi h^4): F:125-126 (global smoothing) | V:139-140
@@ -255,7 +259,7 @@ k_density(int n_groups, const int2* __restrict__ groups, DevParams P, DensityArr
         else hi = old_len;                                                                   // V:541
       }
       while (__any_sync(FULL_MASK, iter)) {
-        op.active = iter; op.inv_h = 1.0 / hi; op.accW = 0.0; op.accB = 0.0;
+        op.active = iter; op.inv_h = 1.0 / hi; op.r2max = 4.0 * hi * hi * (1.0 + 1e-9); op.accW = 0.0; op.accB = 0.0;
         if (iter) old_len = hi;
         neighbour_walk(op, groups, chunk, box, bi, stack, cq);
         if (iter) {
@@ -289,7 +293,7 @@ struct ForceArrays {
   const double *x, *y, *z, *vx, *vy, *vz, *m, *h, *rho, *c, *alpha, *por2, *lcx, *lcy, *lcz, *reach;
   const int* id;
 };
-#define FORCE_FIELDS 18
+#define FORCE_FIELDS 19
 
 struct ForceOp {
   static const bool SYMMETRIC = true;
@@ -302,6 +306,7 @@ struct ForceOp {
   // lane state
   bool live;
   double xi, yi, zi, vxi, vyi, vzi, hi, inv_hi, inv_n4i, rhoi, ci, alphai, por2i, cxi, cyi, czi, Ri;
+  double r2max;          // 4 h_i^2 (1 + 1e-9); a pair beyond max(r2max_i, r2max_j) has dW(h_i) = dW(h_j) = 0: every term is an exact zero
   int idi;
   double ax, ay, az, ud, ad;
   unsigned pairs;
@@ -327,6 +332,7 @@ struct ForceOp {
     t[6 * WALK_TILE + s] = A.m[j];  t[7 * WALK_TILE + s] = hj;
     t[8 * WALK_TILE + s] = 1.0 / (pi_norm * ((hj * hj) * (hj * hj)));
     t[17 * WALK_TILE + s] = 1.0 / hj;
+    t[18 * WALK_TILE + s] = 4.0 * hj * hj * (1.0 + 1e-9);
     t[9 * WALK_TILE + s] = A.rho[j]; t[10 * WALK_TILE + s] = A.c[j]; t[11 * WALK_TILE + s] = A.alpha[j];
     t[12 * WALK_TILE + s] = A.por2[j];
     t[13 * WALK_TILE + s] = A.lcx[j]; t[14 * WALK_TILE + s] = A.lcy[j]; t[15 * WALK_TILE + s] = A.lcz[j];
@@ -334,7 +340,7 @@ struct ForceOp {
     tid[s] = A.id[j];
   }
   __device__ __forceinline__ void consume(int count) {
-    unsigned mask = 0;
+    unsigned mask = 0, pmask = 0;
     if (live) {
 #pragma unroll 4
       for (int k = 0; k < count; ++k) {
@@ -342,14 +348,18 @@ struct ForceOp {
         // idj > idi: j is the `body` that visits i: is x_j inside Box(i)?   (Box(i) is empty when R_i = -1)
         const int idj = tid[k];
         const bool lt = idj < idi;
-        const double px = lt ? xi : t[0 * WALK_TILE + k], py = lt ? yi : t[1 * WALK_TILE + k], pz = lt ? zi : t[2 * WALK_TILE + k];
+        const double xj = t[0 * WALK_TILE + k], yj = t[1 * WALK_TILE + k], zj = t[2 * WALK_TILE + k];
+        const double px = lt ? xi : xj, py = lt ? yi : yj, pz = lt ? zi : zj;
         const double cx = lt ? t[13 * WALK_TILE + k] : cxi, cy = lt ? t[14 * WALK_TILE + k] : cyi, cz = lt ? t[15 * WALK_TILE + k] : czi;
         const double R = lt ? t[16 * WALK_TILE + k] : Ri;
         const bool in = (idj != idi) & (fabs(px - cx) < R) & (fabs(py - cy) < R) & (fabs(pz - cz) < R);
-        mask |= (in ? 1u : 0u) << k;
+        const double dx = xi - xj, dy = yi - yj, dz = zi - zj;
+        const bool nz = !(dx * dx + dy * dy + dz * dz > fmax(r2max, t[18 * WALK_TILE + k]));
+        pmask |= (in ? 1u : 0u) << k;
+        mask |= ((in & nz) ? 1u : 0u) << k;
       }
     }
-    pairs += __popc(mask);
+    pairs += __popc(pmask);
     while (mask) {
       const int k = __ffs(mask) - 1; mask &= mask - 1;
       double f, u, a;
@@ -436,6 +446,7 @@ k_force(int n_groups, const int2* __restrict__ groups, DevParams P, ForceArrays 
     op.xi = A.x[ii]; op.yi = A.y[ii]; op.zi = A.z[ii]; op.vxi = A.vx[ii]; op.vyi = A.vy[ii]; op.vzi = A.vz[ii];
     op.hi = P.variable_h ? A.h[ii] : P.h_fixed; op.inv_hi = 1.0 / op.hi;
     op.inv_n4i = 1.0 / (P.pi_norm * ((op.hi * op.hi) * (op.hi * op.hi)));
+    op.r2max = 4.0 * op.hi * op.hi * (1.0 + 1e-9);
     op.rhoi = A.rho[ii]; op.ci = A.c[ii]; op.alphai = A.alpha[ii]; op.por2i = A.por2[ii];
     op.cxi = A.lcx[ii]; op.cyi = A.lcy[ii]; op.czi = A.lcz[ii]; op.Ri = A.reach[ii]; op.idi = A.id[ii];
     op.ax = op.ay = op.az = op.ud = op.ad = 0.0; op.pairs = 0;
