@@ -195,7 +195,9 @@ def main():
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     launches = e.launch_count() - l0
-    counters = e.counters()
+    # interaction counts of the reference algorithm (every leaf-box candidate): one untimed evaluation with exact
+    # counters on the state the timed steps ended in; the timed steps cull exact-zero pairs before counting them
+    e.set_exact_counters(True); e.evaluate(); counters = e.counters(); e.set_exact_counters(False)
     n_now, ns_now = e.sizes()
     tm = torch.tensor([ms], dtype=torch.float64, device="cuda")
     per_rank = [ms]

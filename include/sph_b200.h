@@ -160,6 +160,13 @@ int sph_download_neighbours(sph_ctx* ctx, int32_t* count, uint64_t* hash,
 
 int sph_counters(sph_ctx* ctx, sph_counts* out);
 
+/* density_candidates / sph_pairs count every pair that passes the reference's leaf-box test (F:443 | V:479),
+ * most of which only add exact zeros (q > 2, F:112).  By default the walks drop sources that lie beyond
+ * 2 max(h) of a whole walk group before the per-pair tests - every field is bit-identical - and the two
+ * counters then cover the pairs that were tested.  on = 1 keeps every box candidate so that the counters
+ * equal the reference's (parity tests, flop accounting); it is slower. */
+int sph_set_exact_counters(sph_ctx* ctx, int32_t on);
+
 /* Per-stage device time of the most recent sph_step / sph_evaluate in milliseconds:
  * [0]=bbox+keys [1]=sort+reorder [2]=tree build [3]=density+EOS [4]=gravity(+sinks)
  * [5]=SPH pair [6]=integrate+dt [7]=h iteration [8]=accretion+cull [9]=NCCL exchanges (incl. waiting

@@ -69,7 +69,7 @@ struct sph_ctx {
   unsigned char* keep = nullptr; unsigned long long* acc_key[2] = {}; int* acc_val[2] = {}; int* d_nsel = nullptr;
   int* pos = nullptr;           // ascending-number position of each sorted particle (downloads)
   double* stage_d = nullptr; double* stage_d2 = nullptr; int stage_flip = 0;   // device staging for ordered downloads
-  bool tree_valid = false;
+  bool tree_valid = false; int exact_counters = 0;
   sph_counts counts; double stage_ms[ST_COUNT] = {};
   std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> ev_used; std::vector<cudaEvent_t> ev_pool;
   int64_t launches = 0;
@@ -377,7 +377,7 @@ int run_density(sph_ctx* c) {
   StateArrays s = state_of(c, c->cur);
   LAUNCH(k_set_int, 1, 1, 0, c->work, c->g0);
   LAUNCH(k_density<false>, walk_grid(c, W), W * 32, density_smem(c, W), c->g1, c->groups, c->dp, dens_arrays(c), c->bvh, c->bi, c->d_wt, c->d_dwt,
-         s.u, s.h, c->rho, c->omega, c->prs, c->cs, c->por2, c->ctr, c->work);
+         s.u, s.h, c->rho, c->omega, c->prs, c->cs, c->por2, c->ctr, c->work, c->exact_counters);
   stage_end(c);
   if (c->n_ranks > 1) { stage_begin(c, ST_COMM); double* bufs[5] = {c->rho, c->omega, c->prs, c->cs, c->por2}; int r_ = allgatherv(c, bufs, 5); if (r_) return r_; stage_end(c); }
   return SPH_OK;
@@ -388,7 +388,7 @@ int run_hiter(sph_ctx* c) {
   StateArrays s = state_of(c, c->cur);
   LAUNCH(k_set_int, 1, 1, 0, c->work, c->g0);
   LAUNCH(k_density<true>, walk_grid(c, W), W * 32, density_smem(c, W), c->g1, c->groups, c->dp, dens_arrays(c), c->bvh, c->bi, c->d_wt, c->d_dwt,
-         s.u, s.h, c->rho, c->omega, c->prs, c->cs, c->por2, c->ctr, c->work);
+         s.u, s.h, c->rho, c->omega, c->prs, c->cs, c->por2, c->ctr, c->work, c->exact_counters);
   stage_end(c);
   if (c->n_ranks > 1) { stage_begin(c, ST_COMM); double* bufs[1] = {s.h}; int r_ = allgatherv(c, bufs, 1); if (r_) return r_; stage_end(c); }
   return SPH_OK;
@@ -399,7 +399,7 @@ int run_force(sph_ctx* c) {
   StateArrays s = state_of(c, c->cur);
   ForceArrays A{s.x, s.y, s.z, s.vx, s.vy, s.vz, s.m, s.h, c->rho, c->cs, s.alpha, c->por2, c->lcx, c->lcy, c->lcz, c->reach, s.id};
   LAUNCH(k_set_int, 1, 1, 0, c->work, c->g0);
-  LAUNCH(k_force, walk_grid(c, W), W * 32, force_smem(c, W), c->g1, c->groups, c->dp, A, c->bvh, c->bi, c->d_dwt, c->ax, c->ay, c->az, c->udot, c->adot, c->ctr, c->work);
+  LAUNCH(k_force, walk_grid(c, W), W * 32, force_smem(c, W), c->g1, c->groups, c->dp, A, c->bvh, c->bi, c->d_dwt, c->ax, c->ay, c->az, c->udot, c->adot, c->ctr, c->work, c->exact_counters);
   stage_end(c);
   if (c->n_ranks > 1) { stage_begin(c, ST_COMM); double* bufs[5] = {c->ax, c->ay, c->az, c->udot, c->adot}; int r_ = allgatherv(c, bufs, 5); if (r_) return r_; stage_end(c); }
   return SPH_OK;
@@ -905,6 +905,12 @@ int sph_download_neighbours(sph_ctx* c, int32_t* count, uint64_t* hash, int64_t*
   CK(cudaStreamSynchronize(c->stream));
   cudaFree(d_count); cudaFree(d_hash); if (d_off) cudaFree(d_off); if (d_list) cudaFree(d_list);
   return rc;
+}
+
+int sph_set_exact_counters(sph_ctx* c, int32_t on) {
+  if (!c) return SPH_ERR_ARG;
+  c->exact_counters = on ? 1 : 0;
+  return SPH_OK;
 }
 
 int sph_counters(sph_ctx* c, sph_counts* out) {

@@ -129,6 +129,8 @@ struct DensityOp {
   // lane state
   double xi, yi, zi, inv_h;
   double r2max;                      // 4 h_i^2 (1 + 1e-9): beyond it q > 2 for certain and the term is an exact zero
+  double g_r2max;                    // the same for the largest h of the group's active targets
+  bool count_all;                    // keep every box candidate (exact candidate counter) instead of culling exact zeros early
   bool active;
   double accW, accB;                 // sum m_j w(q), sum m_j r dw(q)
   unsigned cand, contrib;
@@ -139,9 +141,14 @@ struct DensityOp {
     double R = A.reach[j];
     if (!(R > 0.0)) return false;
     double cx = A.lcx[j], cy = A.lcy[j], cz = A.lcz[j];
-    return (cx - R <= (double)gphi[0]) && (cx + R >= (double)gplo[0]) &&
-           (cy - R <= (double)gphi[1]) && (cy + R >= (double)gplo[1]) &&
-           (cz - R <= (double)gphi[2]) && (cz + R >= (double)gplo[2]);
+    if (!((cx - R <= (double)gphi[0]) && (cx + R >= (double)gplo[0]) &&
+          (cy - R <= (double)gphi[1]) && (cy + R >= (double)gplo[1]) &&
+          (cz - R <= (double)gphi[2]) && (cz + R >= (double)gplo[2]))) return false;
+    // farther than 2 h_i from every target of the group: W = 0 exactly for all of them
+    const double px = A.x[j], py = A.y[j], pz = A.z[j];
+    const double ex = fmax(fmax((double)gplo[0] - px, px - (double)gphi[0]), 0.0), ey = fmax(fmax((double)gplo[1] - py, py - (double)gphi[1]), 0.0),
+                 ez = fmax(fmax((double)gplo[2] - pz, pz - (double)gphi[2]), 0.0);
+    return !(ex * ex + ey * ey + ez * ez > g_r2max) || count_all;
   }
   __device__ __forceinline__ void stage(int s, int j) {
     sx[s] = A.x[j]; sy[s] = A.y[j]; sz[s] = A.z[j]; sm[s] = A.m[j];
@@ -194,7 +201,7 @@ k_density(int n_groups, const int2* __restrict__ groups, DevParams P, DensityArr
           const double* __restrict__ g_wt, const double* __restrict__ g_dwt,
           const double* __restrict__ u, double* __restrict__ h,
           double* __restrict__ rho, double* __restrict__ omega, double* __restrict__ prs, double* __restrict__ cs,
-          double* __restrict__ por2, WalkCounters* ctr, int* work) {
+          double* __restrict__ por2, WalkCounters* ctr, int* work, int count_all) {
   extern __shared__ double smem[];
   const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double* wt = smem; double* dwt = smem + (P.nq + 1);
@@ -223,12 +230,13 @@ k_density(int n_groups, const int2* __restrict__ groups, DevParams P, DensityArr
     const BvhBox g = box[bi.off[0] + chunk];
     for (int k = 0; k < 3; ++k) { op.gplo[k] = g.plo[k]; op.gphi[k] = g.phi[k]; }
     op.xi = live ? A.x[i] : 0.0; op.yi = live ? A.y[i] : 0.0; op.zi = live ? A.z[i] : 0.0;
-    op.cand = 0; op.contrib = 0;
+    op.cand = 0; op.contrib = 0; op.count_all = count_all != 0;
     double hi = live ? (P.variable_h ? h[i] : P.h_fixed) : 1.0;
     const double mi = live ? A.m[i] : 0.0;
 
     if (!HITER) {
       op.active = live; op.inv_h = 1.0 / hi; op.r2max = 4.0 * hi * hi * (1.0 + 1e-9); op.accW = 0.0; op.accB = 0.0;
+      op.g_r2max = warp_max(live ? op.r2max : 0.0);
       neighbour_walk(op, groups, chunk, box, bi, stack, cq);
       if (live) {
         // W/(pi h^3), dW/(pi h^4): F:125-126 (global smoothing) | V:139-140
@@ -260,6 +268,7 @@ k_density(int n_groups, const int2* __restrict__ groups, DevParams P, DensityArr
       }
       while (__any_sync(FULL_MASK, iter)) {
         op.active = iter; op.inv_h = 1.0 / hi; op.r2max = 4.0 * hi * hi * (1.0 + 1e-9); op.accW = 0.0; op.accB = 0.0;
+        op.g_r2max = warp_max(iter ? op.r2max : 0.0);
         if (iter) old_len = hi;
         neighbour_walk(op, groups, chunk, box, bi, stack, cq);
         if (iter) {
@@ -306,6 +315,7 @@ struct ForceOp {
   // lane state
   bool live;
   double xi, yi, zi, vxi, vyi, vzi, hi, inv_hi, inv_n4i, rhoi, ci, alphai, por2i, cxi, cyi, czi, Ri;
+  double g_r2max; bool count_all;   // group maximum of r2max; exact pair counter wanted (no early cull)
   double r2max;          // 4 h_i^2 (1 + 1e-9); a pair beyond max(r2max_i, r2max_j) has dW(h_i) = dW(h_j) = 0: every term is an exact zero
   int idi;
   double ax, ay, az, ud, ad;
@@ -320,10 +330,15 @@ struct ForceOp {
     bool a = (cx - R <= (double)gphi[0]) && (cx + R >= (double)gplo[0]) &&
              (cy - R <= (double)gphi[1]) && (cy + R >= (double)gplo[1]) &&
              (cz - R <= (double)gphi[2]) && (cz + R >= (double)gplo[2]);
-    if (a) return true;
-    double px = A.x[j], py = A.y[j], pz = A.z[j];
-    return px >= (double)grlo[0] && px <= (double)grhi[0] && py >= (double)grlo[1] && py <= (double)grhi[1] &&
-           pz >= (double)grlo[2] && pz <= (double)grhi[2];
+    const double px = A.x[j], py = A.y[j], pz = A.z[j];
+    if (!a) a = px >= (double)grlo[0] && px <= (double)grhi[0] && py >= (double)grlo[1] && py <= (double)grhi[1] &&
+                pz >= (double)grlo[2] && pz <= (double)grhi[2];
+    if (!a) return false;
+    // farther than 2 max(h_i, h_j) from every target of the group: both kernel gradients are exact zeros
+    const double ex = fmax(fmax((double)gplo[0] - px, px - (double)gphi[0]), 0.0), ey = fmax(fmax((double)gplo[1] - py, py - (double)gphi[1]), 0.0),
+                 ez = fmax(fmax((double)gplo[2] - pz, pz - (double)gphi[2]), 0.0);
+    const double hj = variable_h ? A.h[j] : h_fixed;
+    return !(ex * ex + ey * ey + ez * ez > fmax(g_r2max, 4.0 * hj * hj * (1.0 + 1e-9))) || count_all;
   }
   __device__ __forceinline__ void stage(int s, int j) {
     const double hj = variable_h ? A.h[j] : h_fixed;
@@ -413,7 +428,7 @@ struct ForceOp {
 __global__ void __launch_bounds__(512, 1)
 k_force(int n_groups, const int2* __restrict__ groups, DevParams P, ForceArrays A, const BvhBox* __restrict__ box, BvhInfo bi, const double* __restrict__ g_dwt,
         double* __restrict__ ax, double* __restrict__ ay, double* __restrict__ az, double* __restrict__ udot,
-        double* __restrict__ adot, WalkCounters* ctr, int* work) {
+        double* __restrict__ adot, WalkCounters* ctr, int* work, int count_all) {
   extern __shared__ double smem[];
   const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double* dwt = smem;
@@ -447,6 +462,7 @@ k_force(int n_groups, const int2* __restrict__ groups, DevParams P, ForceArrays 
     op.hi = P.variable_h ? A.h[ii] : P.h_fixed; op.inv_hi = 1.0 / op.hi;
     op.inv_n4i = 1.0 / (P.pi_norm * ((op.hi * op.hi) * (op.hi * op.hi)));
     op.r2max = 4.0 * op.hi * op.hi * (1.0 + 1e-9);
+    op.g_r2max = warp_max(live ? op.r2max : 0.0); op.count_all = count_all != 0;
     op.rhoi = A.rho[ii]; op.ci = A.c[ii]; op.alphai = A.alpha[ii]; op.por2i = A.por2[ii];
     op.cxi = A.lcx[ii]; op.cyi = A.lcy[ii]; op.czi = A.lcz[ii]; op.Ri = A.reach[ii]; op.idi = A.id[ii];
     op.ax = op.ay = op.az = op.ud = op.ad = 0.0; op.pairs = 0;

@@ -52,6 +52,7 @@ def load_library(path=None):
     lib.sph_download_tree.argtypes = [vp] + [vp] * 7
     lib.sph_download_neighbours.argtypes = [vp, vp, vp, vp, vp, i64]
     lib.sph_counters.argtypes = [vp, C.POINTER(SphCounts)]
+    lib.sph_set_exact_counters.argtypes = [vp, i32]
     lib.sph_stage_times.argtypes = [vp, vp, i32]
     lib.sph_launch_count.argtypes = [vp]
     lib.sph_launch_count.restype = i64
@@ -72,7 +73,7 @@ def _p(a):
 class Engine:
     """One engine context on one CUDA device (`sph_ctx`)."""
 
-    def __init__(self, params: SphParams, device=0):
+    def __init__(self, params: SphParams, device=0, exact_counters=False):
         self._l = load_library()
         self.params = params
         self._c = C.c_void_p()
@@ -81,6 +82,12 @@ class Engine:
             msg = self._l.sph_last_error(None)
             self._c = None
             raise SphError(rc, (msg or b"").decode())
+        if exact_counters:
+            self.set_exact_counters(True)
+
+    def set_exact_counters(self, on=True):
+        """Count every leaf-box candidate like the reference (slower); default: cull exact-zero pairs early."""
+        self._ck(self._l.sph_set_exact_counters(self._c, 1 if on else 0))
 
     def close(self):
         if getattr(self, "_c", None):
