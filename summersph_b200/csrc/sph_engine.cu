@@ -356,10 +356,10 @@ int build_tree_impl(sph_ctx* c, bool* retry_two_word) {
 }
 
 
-size_t density_smem(const sph_ctx* c, int nwarp) { return (size_t)2 * (c->p.nq + 1) * 8 + (size_t)nwarp * 8 * WALK_TILE * 8 + (size_t)nwarp * (WALK_STACK + WALK_CQ) * 4; }
+size_t density_smem(const sph_ctx* c, int nwarp) { return (size_t)2 * (c->p.nq + 1) * 8 + (size_t)nwarp * 8 * WALK_TILE * 8 + (size_t)nwarp * WALK_WS * 4; }
 size_t force_smem(const sph_ctx* c, int nwarp) {
   size_t t = (size_t)((c->p.nq + 1) + ((c->p.nq + 1) & 1)) * 8;
-  return t + (size_t)nwarp * FORCE_FIELDS * WALK_TILE * 8 + (size_t)nwarp * WALK_TILE * 4 + (size_t)nwarp * (WALK_STACK + WALK_CQ) * 4;
+  return t + (size_t)nwarp * FORCE_FIELDS * WALK_TILE * 8 + (size_t)nwarp * WALK_TILE * 4 + (size_t)nwarp * WALK_WS * 4;
 }
 int walk_grid(const sph_ctx* c, int nwarp) {
   const int nchunk = c->g1 - c->g0;
@@ -875,7 +875,7 @@ int sph_download_neighbours(sph_ctx* c, int32_t* count, uint64_t* hash, int64_t*
   int r; if ((r = compute_pos(c))) return r;
   int* d_count = nullptr; unsigned long long* d_hash = nullptr; long long* d_off = nullptr; int* d_list = nullptr;
   DA(d_count, n); DA(d_hash, n);
-  size_t smem = (size_t)W * 4 * WALK_TILE * 8 + (size_t)W * WALK_TILE * 4 + (size_t)W * (WALK_STACK + WALK_CQ) * 4;
+  size_t smem = (size_t)W * 4 * WALK_TILE * 8 + (size_t)W * WALK_TILE * 4 + (size_t)W * WALK_WS * 4;
   LAUNCH(k_neighbours, walk_grid(c, W), W * 32, smem, c->n_groups, c->groups, dens_arrays(c), c->pos, c->bvh, c->bi, d_count, d_hash, nullptr, nullptr);
   std::vector<int> cnt_sorted(n), pos(n), cnt_num(n);
   std::vector<unsigned long long> hash_sorted(n);

@@ -21,6 +21,7 @@ struct BvhInfo { int nlev; int off[12]; int cnt[12]; };
 #define WALK_STACK 224      // node stack entries per warp
 #define WALK_CQ    96       // chunk queue entries per warp
 #define WALK_TILE  32       // staged source particles per warp
+#define WALK_WS    (WALK_STACK + WALK_CQ + WALK_TILE)   // unsigned words of walk state per warp
 
 struct WalkCounters { unsigned long long dens_cand, dens_contrib, sph_pairs, grav_opened, grav_accepted, h_iters; };
 
@@ -36,6 +37,7 @@ __device__ __forceinline__ bool box_overlap(const float* alo, const float* ahi, 
 template <class OP>
 __device__ void neighbour_walk(OP& op, const int2* __restrict__ groups, int chunk, const BvhBox* __restrict__ box, const BvhInfo& bi,
                                unsigned* stack, unsigned* cq) {
+  unsigned* tix = cq + WALK_CQ;          // particle indices of the tile being collected
   const int lane = threadIdx.x & 31;
   const BvhBox g = box[bi.off[0] + chunk];
   int sn = 0, qn = 0, tn = 0;
@@ -45,17 +47,34 @@ __device__ void neighbour_walk(OP& op, const int2* __restrict__ groups, int chun
     if (OP::SYMMETRIC) r = r || box_overlap(g.rlo, g.rhi, b.plo, b.phi);
     return r;
   };
+  // Hit chunks -> passing sources.  The chunk descriptors of up to 32 queued chunks come in with one
+  // lane-parallel load; each chunk costs one round of filter loads (lane = source) that only appends the
+  // passing particle indices to a 32-entry list; a full list is staged by lane = list slot, every field load
+  // of a tile in flight at once, then consumed.
+  auto flush_tile = [&]() {
+    __syncwarp();
+    if (lane < tn) op.stage(lane, (int)tix[lane]);
+    __syncwarp();
+    op.consume(tn);
+    tn = 0;
+    __syncwarp();
+  };
   auto drain_chunks = [&]() {
-    for (int q = 0; q < qn; ++q) {
-      const int2 sg = groups[cq[q]];
-      const int j = sg.x + lane;
-      bool ok = (lane < sg.y) && op.source_filter(j);
-      unsigned bal = __ballot_sync(FULL_MASK, ok);
-      int cntc = __popc(bal);
-      if (cntc == 0) continue;
-      if (tn + cntc > WALK_TILE) { __syncwarp(); op.consume(tn); tn = 0; __syncwarp(); }
-      if (ok) op.stage(tn + __popc(bal & ((1u << lane) - 1u)), j);
-      tn += cntc;
+    for (int q0 = 0; q0 < qn; q0 += 32) {
+      const int nq = qn - q0 < 32 ? qn - q0 : 32;
+      int2 mysg = make_int2(0, 0);
+      if (lane < nq) mysg = groups[cq[q0 + lane]];
+      for (int q = 0; q < nq; ++q) {
+        const int sgx = __shfl_sync(FULL_MASK, mysg.x, q), sgy = __shfl_sync(FULL_MASK, mysg.y, q);
+        const int j = sgx + lane;
+        const bool ok = (lane < sgy) && op.source_filter(j);
+        const unsigned bal = __ballot_sync(FULL_MASK, ok);
+        const int cntc = __popc(bal);
+        if (cntc == 0) continue;
+        if (tn + cntc > WALK_TILE) flush_tile();
+        if (ok) tix[tn + __popc(bal & ((1u << lane) - 1u))] = (unsigned)j;
+        tn += cntc;
+      }
     }
     qn = 0;
   };
@@ -91,9 +110,7 @@ __device__ void neighbour_walk(OP& op, const int2* __restrict__ groups, int chun
     if (qn > WALK_CQ - 32) { drain_chunks(); }
   }
   drain_chunks();
-  __syncwarp();
-  if (tn > 0) op.consume(tn);
-  __syncwarp();
+  if (tn > 0) flush_tile();
 }
 
 // shared kernel-table lookup: returns table-space (w, dw) at q (<= 2 assumed), F:113-118
@@ -138,17 +155,15 @@ struct DensityOp {
   __device__ DensityOp(const DensityArrays& a) : A(a) {}
 
   __device__ __forceinline__ bool source_filter(int j) const {
-    double R = A.reach[j];
-    if (!(R > 0.0)) return false;
-    double cx = A.lcx[j], cy = A.lcy[j], cz = A.lcz[j];
-    if (!((cx - R <= (double)gphi[0]) && (cx + R >= (double)gplo[0]) &&
-          (cy - R <= (double)gphi[1]) && (cy + R >= (double)gplo[1]) &&
-          (cz - R <= (double)gphi[2]) && (cz + R >= (double)gplo[2]))) return false;
+    // all loads first (independent, one latency), then a branch-free decision
+    const double R = A.reach[j], cx = A.lcx[j], cy = A.lcy[j], cz = A.lcz[j], px = A.x[j], py = A.y[j], pz = A.z[j];
+    const bool box = (R > 0.0) & (cx - R <= (double)gphi[0]) & (cx + R >= (double)gplo[0]) &
+                     (cy - R <= (double)gphi[1]) & (cy + R >= (double)gplo[1]) &
+                     (cz - R <= (double)gphi[2]) & (cz + R >= (double)gplo[2]);
     // farther than 2 h_i from every target of the group: W = 0 exactly for all of them
-    const double px = A.x[j], py = A.y[j], pz = A.z[j];
     const double ex = fmax(fmax((double)gplo[0] - px, px - (double)gphi[0]), 0.0), ey = fmax(fmax((double)gplo[1] - py, py - (double)gphi[1]), 0.0),
                  ez = fmax(fmax((double)gplo[2] - pz, pz - (double)gphi[2]), 0.0);
-    return !(ex * ex + ey * ey + ez * ez > g_r2max) || count_all;
+    return box & (!(ex * ex + ey * ey + ez * ez > g_r2max) | count_all);
   }
   __device__ __forceinline__ void stage(int s, int j) {
     sx[s] = A.x[j]; sy[s] = A.y[j]; sz[s] = A.z[j]; sm[s] = A.m[j];
@@ -210,7 +225,7 @@ k_density(int n_groups, const int2* __restrict__ groups, DevParams P, DensityArr
   for (int i = threadIdx.x; i <= P.nq; i += blockDim.x) { wt[i] = g_wt[i]; dwt[i] = g_dwt[i]; }
   __syncthreads();
   double* tile = tiles + (size_t)warp * 8 * WALK_TILE;
-  unsigned* stack = ws + (size_t)warp * (WALK_STACK + WALK_CQ);
+  unsigned* stack = ws + (size_t)warp * WALK_WS;
   unsigned* cq = stack + WALK_STACK;
   const int nchunk = n_groups;
   unsigned long long tot_cand = 0, tot_contrib = 0, tot_iter = 0;
@@ -324,21 +339,21 @@ struct ForceOp {
   __device__ ForceOp(const ForceArrays& a) : A(a) {}
 
   __device__ __forceinline__ bool source_filter(int j) const {
-    double R = A.reach[j];
-    if (!(R > 0.0)) return false;
-    double cx = A.lcx[j], cy = A.lcy[j], cz = A.lcz[j];
-    bool a = (cx - R <= (double)gphi[0]) && (cx + R >= (double)gplo[0]) &&
-             (cy - R <= (double)gphi[1]) && (cy + R >= (double)gplo[1]) &&
-             (cz - R <= (double)gphi[2]) && (cz + R >= (double)gplo[2]);
-    const double px = A.x[j], py = A.y[j], pz = A.z[j];
-    if (!a) a = px >= (double)grlo[0] && px <= (double)grhi[0] && py >= (double)grlo[1] && py <= (double)grhi[1] &&
-                pz >= (double)grlo[2] && pz <= (double)grhi[2];
-    if (!a) return false;
+    // all loads first (independent, one latency), then a branch-free decision
+    const double R = A.reach[j], cx = A.lcx[j], cy = A.lcy[j], cz = A.lcz[j], px = A.x[j], py = A.y[j], pz = A.z[j];
+    const double hj = variable_h ? A.h[j] : h_fixed;
+    const double fj = A.por2[j] + A.c[j];          // NaN / inf here spreads through 0 * NaN in the reference: never cull it
+    const bool a = (cx - R <= (double)gphi[0]) & (cx + R >= (double)gplo[0]) &
+                   (cy - R <= (double)gphi[1]) & (cy + R >= (double)gplo[1]) &
+                   (cz - R <= (double)gphi[2]) & (cz + R >= (double)gplo[2]);
+    const bool b = (px >= (double)grlo[0]) & (px <= (double)grhi[0]) & (py >= (double)grlo[1]) & (py <= (double)grhi[1]) &
+                   (pz >= (double)grlo[2]) & (pz <= (double)grhi[2]);
     // farther than 2 max(h_i, h_j) from every target of the group: both kernel gradients are exact zeros
     const double ex = fmax(fmax((double)gplo[0] - px, px - (double)gphi[0]), 0.0), ey = fmax(fmax((double)gplo[1] - py, py - (double)gphi[1]), 0.0),
                  ez = fmax(fmax((double)gplo[2] - pz, pz - (double)gphi[2]), 0.0);
-    const double hj = variable_h ? A.h[j] : h_fixed;
-    return !(ex * ex + ey * ey + ez * ez > fmax(g_r2max, 4.0 * hj * hj * (1.0 + 1e-9))) || count_all;
+    const bool nz = !(ex * ex + ey * ey + ez * ez > fmax(g_r2max, 4.0 * hj * hj * (1.0 + 1e-9))) | !(fabs(fj) < INFINITY);
+    // R <= 0: j sits in a depth-limited multi-particle node - nobody finds it (a), but it still visits others (b)
+    return (((R > 0.0) & a) | b) & (nz | count_all);
   }
   __device__ __forceinline__ void stage(int s, int j) {
     const double hj = variable_h ? A.h[j] : h_fixed;
@@ -347,7 +362,7 @@ struct ForceOp {
     t[6 * WALK_TILE + s] = A.m[j];  t[7 * WALK_TILE + s] = hj;
     t[8 * WALK_TILE + s] = 1.0 / (pi_norm * ((hj * hj) * (hj * hj)));
     t[17 * WALK_TILE + s] = 1.0 / hj;
-    t[18 * WALK_TILE + s] = 4.0 * hj * hj * (1.0 + 1e-9);
+    t[18 * WALK_TILE + s] = (fabs(A.por2[j] + A.c[j]) < INFINITY) ? 4.0 * hj * hj * (1.0 + 1e-9) : INFINITY;
     t[9 * WALK_TILE + s] = A.rho[j]; t[10 * WALK_TILE + s] = A.c[j]; t[11 * WALK_TILE + s] = A.alpha[j];
     t[12 * WALK_TILE + s] = A.por2[j];
     t[13 * WALK_TILE + s] = A.lcx[j]; t[14 * WALK_TILE + s] = A.lcy[j]; t[15 * WALK_TILE + s] = A.lcz[j];
@@ -438,7 +453,7 @@ k_force(int n_groups, const int2* __restrict__ groups, DevParams P, ForceArrays 
   for (int i = threadIdx.x; i <= P.nq; i += blockDim.x) dwt[i] = g_dwt[i];
   __syncthreads();
   double* tile = tiles + (size_t)warp * FORCE_FIELDS * WALK_TILE;
-  unsigned* stack = ws + (size_t)warp * (WALK_STACK + WALK_CQ);
+  unsigned* stack = ws + (size_t)warp * WALK_WS;
   unsigned* cq = stack + WALK_STACK;
   const int nchunk = n_groups;
   unsigned long long tot_pairs = 0;
@@ -461,10 +476,10 @@ k_force(int n_groups, const int2* __restrict__ groups, DevParams P, ForceArrays 
     op.xi = A.x[ii]; op.yi = A.y[ii]; op.zi = A.z[ii]; op.vxi = A.vx[ii]; op.vyi = A.vy[ii]; op.vzi = A.vz[ii];
     op.hi = P.variable_h ? A.h[ii] : P.h_fixed; op.inv_hi = 1.0 / op.hi;
     op.inv_n4i = 1.0 / (P.pi_norm * ((op.hi * op.hi) * (op.hi * op.hi)));
-    op.r2max = 4.0 * op.hi * op.hi * (1.0 + 1e-9);
-    op.g_r2max = warp_max(live ? op.r2max : 0.0); op.count_all = count_all != 0;
     op.rhoi = A.rho[ii]; op.ci = A.c[ii]; op.alphai = A.alpha[ii]; op.por2i = A.por2[ii];
     op.cxi = A.lcx[ii]; op.cyi = A.lcy[ii]; op.czi = A.lcz[ii]; op.Ri = A.reach[ii]; op.idi = A.id[ii];
+    op.r2max = (fabs(op.por2i + op.ci) < INFINITY) ? 4.0 * op.hi * op.hi * (1.0 + 1e-9) : INFINITY;   // own NaN: keep every partner
+    op.g_r2max = warp_max(live ? op.r2max : 0.0); op.count_all = count_all != 0;
     op.ax = op.ay = op.az = op.ud = op.ad = 0.0; op.pairs = 0;
     neighbour_walk(op, groups, chunk, box, bi, stack, cq);
     if (live) {
@@ -520,7 +535,7 @@ k_neighbours(int n_groups, const int2* __restrict__ groups, DensityArrays A, con
   double* tile = smem + (size_t)warp * 4 * WALK_TILE;
   int* sid = reinterpret_cast<int*>(smem + (size_t)nwarp * 4 * WALK_TILE) + warp * WALK_TILE;
   unsigned* ws = reinterpret_cast<unsigned*>(reinterpret_cast<int*>(smem + (size_t)nwarp * 4 * WALK_TILE) + nwarp * WALK_TILE);
-  unsigned* stack = ws + (size_t)warp * (WALK_STACK + WALK_CQ);
+  unsigned* stack = ws + (size_t)warp * WALK_WS;
   unsigned* cq = stack + WALK_STACK;
   const int nchunk = n_groups;
   for (int chunk = blockIdx.x * nwarp + warp; chunk < nchunk; chunk += gridDim.x * nwarp) {

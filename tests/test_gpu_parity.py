@@ -207,6 +207,16 @@ def test_depth_limited_tree(max_depth, E, O):
         assert np.array_equal(de["rho"] == 0, do["rho"] == 0)
         for k in ("ax", "ay", "az"):
             assert relerr(de[k], do[k]) < TOL, k
+        # SPH pass: particles in a multi-particle node are found by nobody (rho = 0 -> P/rho^2 = NaN) but still
+        # visit their lower-numbered neighbours and hand them that NaN (F:354-391): same NaN pattern, same finite values
+        o.evaluate(); e.evaluate()
+        do, de = o.diag(), e.diag()
+        for k in ("ax", "udot", "alphadot"):
+            nan_o, nan_e = np.isnan(do[k]), np.isnan(de[k])
+            assert np.array_equal(nan_o, nan_e), k
+            assert not nan_o.all()
+            fin = ~nan_o
+            assert relerr(de[k][fin], do[k][fin]) < TOL, k
 
 
 def test_two_word_keys(E, O):
