@@ -379,7 +379,7 @@ int run_density(sph_ctx* c) {
   LAUNCH(k_density<false>, walk_grid(c, W), W * 32, density_smem(c, W), c->g1, c->groups, c->dp, dens_arrays(c), c->bvh, c->bi, c->d_wt, c->d_dwt,
          s.u, s.h, c->rho, c->omega, c->prs, c->cs, c->por2, c->ctr, c->work, c->exact_counters);
   stage_end(c);
-  if (c->n_ranks > 1) { stage_begin(c, ST_COMM); double* bufs[5] = {c->rho, c->omega, c->prs, c->cs, c->por2}; int r_ = allgatherv(c, bufs, 5); if (r_) return r_; stage_end(c); }
+  if (c->n_ranks > 1) { stage_begin(c, ST_COMM); double* bufs[3] = {c->rho, c->cs, c->por2}; int r_ = allgatherv(c, bufs, 3);   /* what the pair loop reads of its sources; Omega and P stay rank-local until a diagnostic download asks */ if (r_) return r_; stage_end(c); }
   return SPH_OK;
 }
 int run_hiter(sph_ctx* c) {
@@ -828,6 +828,7 @@ int sph_download_diag(sph_ctx* c, double* rho, double* omega, double* pressure, 
   if (c->n <= 0) { c->err = "no particles"; return SPH_ERR_STATE; }
   cudaSetDevice(c->device);
   int r; if ((r = compute_pos(c))) return r;
+  { double* bufs[2] = {c->omega, c->prs}; if ((r = allgatherv(c, bufs, 2))) return r; }
   const double* src[9] = {c->rho, c->omega, c->prs, c->cs, c->ax, c->ay, c->az, c->udot, c->adot};
   double* dst[9] = {rho, omega, pressure, sound, ax, ay, az, udot, alphadot};
   for (int f = 0; f < 9; ++f) if ((r = fetch_ordered(c, src[f], dst[f]))) return r;

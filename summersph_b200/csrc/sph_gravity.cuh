@@ -24,7 +24,12 @@
 
 struct SinkArrays { double *x, *y, *z, *vx, *vy, *vz, *m, *radius, *ax, *ay, *az; };
 
+#ifndef GW_WARPS
 #define GW_WARPS 24         // warps per block
+#endif
+#ifndef GW_ILP
+#define GW_ILP 2            // interaction-list entries in flight per lane
+#endif
 #define GW_STACK 384        // (node, mask) entries per warp in shared memory
 #define GW_LIST  64         // interaction-list entries per warp (evaluated when more than 32 are waiting)
 #define GW_SPILL 8192       // per-warp overflow entries in global memory (never reached in practice; loud if it is)
@@ -65,8 +70,8 @@ __device__ __forceinline__ void grav_term(const double2 a, const double2 b, cons
                                           const int nq, const double dq, const double inv_dq, double& gx, double& gy, double& gz) {
   const double dx = xi - a.x, dy = yi - a.y, dz = zi - b.x;                  // F:274
   const double d2 = fma(dx, dx, fma(dy, dy, fma(dz, dz, soft)));
-  const bool v = on & (d2 > 0.0);                                           // F:279 (M > 0 is checked when the entry is listed)
-  const double rs = fast_rsqrt(v ? d2 : 1.0);
+  const bool v = on;                          // F:279: M > 0 is checked when the entry is listed; d2 >= soft > 0
+  const double rs = fast_rsqrt(d2);
   const double q = (d2 * rs) * inv_h;
   double W = 1.0;
   if (q <= 2.0) W = table_lerp1(gt, nq, dq, inv_dq, q);
@@ -106,7 +111,9 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
     const double hi = live ? (P.variable_h ? h[i] : P.h_fixed) : 1.0;
     const double inv_h = 1.0 / hi;
     const double soft = P.soft_hi ? 0.001 * hi : 0.001 * P.h_fixed;          // F:275 | V:296 | T:298
-    double gx = 0.0, gy = 0.0, gz = 0.0, hx = 0.0, hy = 0.0, hz = 0.0;
+    double gx[GW_ILP], gy[GW_ILP], gz[GW_ILP];
+#pragma unroll
+    for (int u = 0; u < GW_ILP; ++u) gx[u] = gy[u] = gz[u] = 0.0;
 
     auto evaluate_list = [&](int cnt) {
       int k = 0;
@@ -114,12 +121,12 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
       GWD(5, 1); GWD(6, cnt);
       { unsigned long long w = 0; for (int q = 0; q < cnt; ++q) { int pc = __popc(W.lmask[q]); w += pc; if (lane == 0) { atomicAdd(&gw_hist[pc], 1ull); } } GWD(7, w); }
 #endif
-      for (; k + 1 < cnt; k += 2) {          // two independent chains per trip
-        const unsigned m0 = W.lmask[k], m1 = W.lmask[k + 1];
-        grav_term(W.lxy[k], W.lzg[k], (m0 >> lane) & 1u, xi, yi, zi, inv_h, soft, gt, P.nq, P.dq, P.inv_dq, gx, gy, gz);
-        grav_term(W.lxy[k + 1], W.lzg[k + 1], (m1 >> lane) & 1u, xi, yi, zi, inv_h, soft, gt, P.nq, P.dq, P.inv_dq, hx, hy, hz);
+      for (; k + GW_ILP <= cnt; k += GW_ILP) {          // GW_ILP independent chains per trip
+#pragma unroll
+        for (int u = 0; u < GW_ILP; ++u)
+          grav_term(W.lxy[k + u], W.lzg[k + u], (W.lmask[k + u] >> lane) & 1u, xi, yi, zi, inv_h, soft, gt, P.nq, P.dq, P.inv_dq, gx[u], gy[u], gz[u]);
       }
-      if (k < cnt) grav_term(W.lxy[k], W.lzg[k], (W.lmask[k] >> lane) & 1u, xi, yi, zi, inv_h, soft, gt, P.nq, P.dq, P.inv_dq, gx, gy, gz);
+      for (; k < cnt; ++k) grav_term(W.lxy[k], W.lzg[k], (W.lmask[k] >> lane) & 1u, xi, yi, zi, inv_h, soft, gt, P.nq, P.dq, P.inv_dq, gx[0], gy[0], gz[0]);
     };
 
     if (do_grav) {
@@ -236,8 +243,9 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
       }
       if (ln > 0) evaluate_list(ln);
       __syncwarp();
-      gx += hx; gy += hy; gz += hz;
     }
+#pragma unroll
+    for (int u = 1; u < GW_ILP; ++u) { gx[0] += gx[u]; gy[0] += gy[u]; gz[0] += gz[u]; }
     // direct sink <-> gas (unsoftened) F:567-576; per-group partial sums of the sink side (no block barrier)
     for (int s = 0; s < n_sink; ++s) {
       const double vx_ = xi - S.x[s], vy_ = yi - S.y[s], vz_ = zi - S.z[s];
@@ -247,7 +255,7 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
       const double ms = S.m[s];
       double px = 0.0, py = 0.0, pz = 0.0;
       if (live) {
-        gx -= ms * wx; gy -= ms * wy; gz -= ms * wz;                            // F:574
+        gx[0] -= ms * wx; gy[0] -= ms * wy; gz[0] -= ms * wz;                   // F:574
         const double mi = m[i];
         px = mi * wx; py = mi * wy; pz = mi * wz;                               // F:573
       }
@@ -257,7 +265,7 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
         o[0] = px; o[1] = py; o[2] = pz;
       }
     }
-    if (live) { ax[i] = gx; ay[i] = gy; az[i] = gz; }
+    if (live) { ax[i] = gx[0]; ay[i] = gy[0]; az[i] = gz[0]; }
   }
   n_open = (unsigned long long)warp_sum_ll((long long)n_open); n_acc = (unsigned long long)warp_sum_ll((long long)n_acc);
   if (lane == 0 && do_grav) { atomicAdd(&ctr->grav_opened, n_open); atomicAdd(&ctr->grav_accepted, n_acc); }
