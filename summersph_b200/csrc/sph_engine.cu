@@ -77,6 +77,12 @@ struct sph_ctx {
   // multi-GPU
   NcclApi nccl; void* comm = nullptr; int rank = 0, n_ranks = 1;
   std::vector<int> rank_g, rank_p;   // per-rank first group / first particle of its target slice (size n_ranks + 1)
+  // peer-memory exchange: every exchanged array of every rank mapped here (CUDA IPC, or the raw pointer when the peer
+  // lives in this process); slices are pushed with copy-engine transfers on their own stream
+  cudaStream_t xstream = nullptr; cudaEvent_t x_ready = nullptr, x_done = nullptr;
+  bool p2p_stale = true, p2p_ok = false, x_pending = false;
+  std::vector<std::vector<double*>> peer;      // [array slot][rank]
+  std::vector<void*> ipc_opened; int* d_flag = nullptr; void* d_blob = nullptr; size_t blob_cap = 0;
   int g0 = 0, g1 = 0, p0 = 0, p1 = 0;
 };
 
@@ -145,6 +151,7 @@ int ensure_capacity(sph_ctx* c, int64_t n) {
   if (cudaMalloc(&c->cub_tmp, c->cub_bytes) != cudaSuccess) { c->err = "cudaMalloc(cub temp)"; cudaGetLastError(); return SPH_ERR_OOM; }
   for (int b = 0; b < 2; ++b) if (c->key_lo[b]) { cudaFree(c->key_lo[b]); c->key_lo[b] = nullptr; }
   c->cap = cap;
+  c->p2p_stale = true;
   return SPH_OK;
 }
 
@@ -197,18 +204,124 @@ int upload_tables(sph_ctx* c) {
 // ---------------------------------------------------------------------------------------------------
 #define NC(call) do { int r_ = (call); if (r_ != 0) { c->err = std::string(#call) + ": " + (c->nccl.GetErrorString ? c->nccl.GetErrorString(r_) : "nccl error"); return SPH_ERR_COMM; } } while (0)
 
-int allgatherv(sph_ctx* c, double* const* bufs, int nbufs) {
-  if (c->n_ranks <= 1) return SPH_OK;
-  NC(c->nccl.GroupStart());
-  for (int b = 0; b < nbufs; ++b)
-    for (int r = 0; r < c->n_ranks; ++r) {
-      const int cnt = c->rank_p[r + 1] - c->rank_p[r];
-      if (cnt <= 0) continue;
-      double* p = bufs[b] + c->rank_p[r];
-      NC(c->nccl.Broadcast(p, p, (size_t)cnt, NC_FLOAT64, r, c->comm, c->stream));
+// ---- peer-memory all-gather-v -------------------------------------------------------------------------
+struct PeerRec { int pid; int device; unsigned long long hosthash; void* ptr; cudaIpcMemHandle_t h; };
+#include <unistd.h>
+
+std::vector<double*> exchanged_arrays(sph_ctx* c) {
+  return {c->rho, c->cs, c->por2, c->ax, c->ay, c->az, c->udot, c->adot, c->omega, c->prs, c->st[0][9], c->st[1][9]};
+}
+
+void p2p_close(sph_ctx* c) {
+  for (void* p : c->ipc_opened) cudaIpcCloseMemHandle(p);
+  c->ipc_opened.clear(); c->peer.clear(); c->p2p_ok = false;
+}
+
+// (Re)map the peers' arrays after an allocation changed. Collective. Falls back to NCCL broadcasts when any
+// rank cannot map a peer (no NVLink/PCIe peer access, IPC disabled): all ranks agree through an all-reduce.
+int p2p_setup(sph_ctx* c) {
+  c->p2p_stale = false;
+  p2p_close(c);
+  if (c->n_ranks <= 1 || !c->nccl.AllGather || getenv("SPH_B200_NO_P2P")) return SPH_OK;
+  if (!c->xstream) { CK(cudaStreamCreateWithFlags(&c->xstream, cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&c->x_ready, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c->x_done, cudaEventDisableTiming)); }
+  if (!c->d_flag) DA(c->d_flag, 4);
+  const std::vector<double*> arr = exchanged_arrays(c);
+  const int na = (int)arr.size(), R = c->n_ranks;
+  char host[256] = {0}; gethostname(host, 255);
+  unsigned long long hh = 1469598103934665603ull; for (char* q = host; *q; ++q) hh = (hh ^ (unsigned char)*q) * 1099511628211ull;
+  std::vector<PeerRec> mine(na), all((size_t)na * R);
+  int ok = 1;
+  for (int a = 0; a < na; ++a) {
+    mine[a].pid = (int)getpid(); mine[a].device = c->device; mine[a].hosthash = hh; mine[a].ptr = arr[a];
+    std::memset(&mine[a].h, 0, sizeof(mine[a].h));
+    if (cudaIpcGetMemHandle(&mine[a].h, arr[a]) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+  }
+  const size_t bytes = sizeof(PeerRec) * na;
+  if (c->blob_cap < bytes * R) { if (c->d_blob) cudaFree(c->d_blob); CK(cudaMalloc(&c->d_blob, bytes * R)); c->blob_cap = bytes * R; }
+  CK(cudaMemcpyAsync((char*)c->d_blob + bytes * c->rank, mine.data(), bytes, cudaMemcpyHostToDevice, c->stream));
+  NC(c->nccl.AllGather((char*)c->d_blob + bytes * c->rank, c->d_blob, bytes, 0 /*ncclInt8*/, c->comm, c->stream));
+  CK(cudaMemcpyAsync(all.data(), c->d_blob, bytes * R, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  c->peer.assign(na, std::vector<double*>(R, nullptr));
+  for (int r = 0; r < R && ok; ++r) {
+    for (int a = 0; a < na && ok; ++a) {
+      const PeerRec& pr = all[(size_t)r * na + a];
+      if (r == c->rank) { c->peer[a][r] = arr[a]; continue; }
+      if (pr.hosthash != hh) { ok = 0; break; }
+      if (pr.pid == (int)getpid()) {            // peer context lives in this process (threads): plain peer access
+        if (pr.device != c->device) {
+          int can = 0; cudaDeviceCanAccessPeer(&can, c->device, pr.device);
+          if (!can) { ok = 0; break; }
+          cudaError_t e = cudaDeviceEnablePeerAccess(pr.device, 0);
+          if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); ok = 0; break; }
+          cudaGetLastError();
+        }
+        c->peer[a][r] = (double*)pr.ptr;
+      } else {
+        void* q = nullptr;
+        if (cudaIpcOpenMemHandle(&q, pr.h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+        c->ipc_opened.push_back(q); c->peer[a][r] = (double*)q;
+      }
     }
-  NC(c->nccl.GroupEnd());
+  }
+  // every rank must have mapped every peer
+  CK(cudaMemcpyAsync(c->d_flag, &ok, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  NC(c->nccl.AllReduce(c->d_flag, c->d_flag, 1, 2 /*ncclInt32*/, NC_MIN, c->comm, c->stream));
+  int all_ok = 0;
+  CK(cudaMemcpyAsync(&all_ok, c->d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  if (!all_ok) { p2p_close(c); return SPH_OK; }
+  c->p2p_ok = true;
   return SPH_OK;
+}
+
+// Start the exchange of this rank's slice [p0, p1) of each array: push it into every peer's copy with
+// copy-engine transfers on the exchange stream (no SMs: it runs under whatever kernel follows on the main
+// stream), then a 4-byte all-reduce as the cross-rank "all pushes have landed" barrier.  allgatherv_end makes
+// the main stream wait for it.  Without peer mapping: one in-place ncclBroadcast per owner on the main stream.
+int allgatherv_begin(sph_ctx* c, double* const* bufs, int nbufs) {
+  if (c->n_ranks <= 1) return SPH_OK;
+  if (c->p2p_stale) { int r_ = p2p_setup(c); if (r_) return r_; }
+  if (!c->p2p_ok) {
+    NC(c->nccl.GroupStart());
+    for (int b = 0; b < nbufs; ++b)
+      for (int r = 0; r < c->n_ranks; ++r) {
+        const int cnt = c->rank_p[r + 1] - c->rank_p[r];
+        if (cnt <= 0) continue;
+        double* p = bufs[b] + c->rank_p[r];
+        NC(c->nccl.Broadcast(p, p, (size_t)cnt, NC_FLOAT64, r, c->comm, c->stream));
+      }
+    NC(c->nccl.GroupEnd());
+    return SPH_OK;
+  }
+  const std::vector<double*> arr = exchanged_arrays(c);
+  CK(cudaEventRecord(c->x_ready, c->stream));
+  CK(cudaStreamWaitEvent(c->xstream, c->x_ready, 0));
+  const size_t off = (size_t)c->p0, cnt = (size_t)(c->p1 - c->p0);
+  for (int b = 0; b < nbufs; ++b) {
+    int a = -1;
+    for (int k = 0; k < (int)arr.size(); ++k) if (arr[k] == bufs[b]) a = k;
+    if (a < 0) { c->err = "allgatherv: array is not registered for the peer exchange"; return SPH_ERR_STATE; }
+    if (cnt == 0) continue;
+    for (int k = 1; k < c->n_ranks; ++k) {      // staggered peer order spreads the traffic over the switch
+      const int r = (c->rank + k) % c->n_ranks;
+      CK(cudaMemcpyAsync(c->peer[a][r] + off, bufs[b] + off, cnt * 8, cudaMemcpyDefault, c->xstream));
+    }
+  }
+  NC(c->nccl.AllReduce(c->d_flag + 1, c->d_flag + 1, 1, 2 /*ncclInt32*/, NC_SUM, c->comm, c->xstream));
+  CK(cudaEventRecord(c->x_done, c->xstream));
+  c->x_pending = true;
+  return SPH_OK;
+}
+int allgatherv_end(sph_ctx* c) {
+  if (!c->x_pending) return SPH_OK;
+  CK(cudaStreamWaitEvent(c->stream, c->x_done, 0));
+  c->x_pending = false;
+  return SPH_OK;
+}
+int allgatherv(sph_ctx* c, double* const* bufs, int nbufs) {
+  int r = allgatherv_begin(c, bufs, nbufs);
+  return r ? r : allgatherv_end(c);
 }
 int allreduce(sph_ctx* c, void* buf, size_t count, int dtype, int op) {
   if (c->n_ranks <= 1) return SPH_OK;
@@ -379,7 +492,7 @@ int run_density(sph_ctx* c) {
   LAUNCH(k_density<false>, walk_grid(c, W), W * 32, density_smem(c, W), c->g1, c->groups, c->dp, dens_arrays(c), c->bvh, c->bi, c->d_wt, c->d_dwt,
          s.u, s.h, c->rho, c->omega, c->prs, c->cs, c->por2, c->ctr, c->work, c->exact_counters);
   stage_end(c);
-  if (c->n_ranks > 1) { stage_begin(c, ST_COMM); double* bufs[3] = {c->rho, c->cs, c->por2}; int r_ = allgatherv(c, bufs, 3);   /* what the pair loop reads of its sources; Omega and P stay rank-local until a diagnostic download asks */ if (r_) return r_; stage_end(c); }
+  if (c->n_ranks > 1) { stage_begin(c, ST_COMM); double* bufs[3] = {c->rho, c->cs, c->por2}; int r_ = allgatherv_begin(c, bufs, 3);   /* what the pair loop reads of its sources (Omega and P stay rank-local until a diagnostic download asks); completes under the gravity walk */ if (r_) return r_; stage_end(c); }
   return SPH_OK;
 }
 int run_hiter(sph_ctx* c) {
@@ -395,6 +508,7 @@ int run_hiter(sph_ctx* c) {
 }
 int run_force(sph_ctx* c) {
   const int n = (int)c->n, W = 16;
+  if (c->x_pending) { stage_begin(c, ST_COMM); int r_ = allgatherv_end(c); if (r_) return r_; stage_end(c); }
   stage_begin(c, ST_SPH);
   StateArrays s = state_of(c, c->cur);
   ForceArrays A{s.x, s.y, s.z, s.vx, s.vy, s.vz, s.m, s.h, c->rho, c->cs, s.alpha, c->por2, c->lcx, c->lcy, c->lcz, c->reach, s.id};
@@ -674,6 +788,10 @@ int sph_destroy(sph_ctx* c) {
   if (!c) return SPH_OK;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  p2p_close(c);
+  if (c->xstream) { cudaStreamSynchronize(c->xstream); cudaStreamDestroy(c->xstream); cudaEventDestroy(c->x_ready); cudaEventDestroy(c->x_done); }
+  if (c->d_flag) cudaFree(c->d_flag);
+  if (c->d_blob) cudaFree(c->d_blob);
   if (c->comm && c->nccl.CommDestroy) c->nccl.CommDestroy(c->comm);
   auto F = [](void* p) { if (p) cudaFree(p); };
   for (int b = 0; b < 2; ++b) { for (int f = 0; f < 10; ++f) F(c->st[b][f]); F(c->id[b]); F(c->key[b]); F(c->key_lo[b]); F(c->perm[b]); F(c->acc_key[b]); F(c->acc_val[b]); }
@@ -707,7 +825,7 @@ int sph_comm_init(sph_ctx* c, int32_t rank, int32_t n_ranks, const void* uid) {
   NcclUid id; std::memcpy(&id, uid, 128);
   int r = c->nccl.CommInitRank(&c->comm, n_ranks, id, rank);
   if (r != 0) { c->err = std::string("ncclCommInitRank: ") + (c->nccl.GetErrorString ? c->nccl.GetErrorString(r) : "?"); return SPH_ERR_COMM; }
-  c->rank = rank; c->n_ranks = n_ranks; c->tree_valid = false;
+  c->rank = rank; c->n_ranks = n_ranks; c->tree_valid = false; c->p2p_stale = true;
   return SPH_OK;
 }
 
