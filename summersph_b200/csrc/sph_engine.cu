@@ -16,6 +16,9 @@
 #include "sph_common.cuh"
 #include "sph_tree.cuh"
 #include "sph_walk.cuh"
+#ifndef GRAV_CHUNK_WIDTH
+#define GRAV_CHUNK_WIDTH 32        // gravity walk groups: fixed runs of this many Morton-consecutive particles (0: the SPH walk groups)
+#endif
 #include "sph_gravity.cuh"
 #include "sph_integrate.cuh"
 
@@ -59,6 +62,7 @@ struct sph_ctx {
   BvhBox* bvh = nullptr; size_t bvh_cap = 0; BvhInfo bi;
   int *node_count = nullptr, *gsize = nullptr, *gfirst = nullptr; int2* groups = nullptr; int n_groups = 0;
   GNode* nodes = nullptr; int *node_part = nullptr, *parent = nullptr, *nchild = nullptr, *arrive = nullptr, *cnt = nullptr, *off = nullptr;
+  int2* ggroups = nullptr; BvhBox* gbvh = nullptr; size_t ggroups_cap = 0;   // gravity walk groups (fixed runs of the rank's slice)
   WNode* wnodes = nullptr; int *wcount = nullptr, *wstart = nullptr, *widx = nullptr; int2* grav_spill = nullptr;   // gravity walk layout
   RootBox* root = nullptr; double* partial = nullptr; int n_partial = 0;
   void* cub_tmp = nullptr; size_t cub_bytes = 0;
@@ -469,10 +473,10 @@ int build_tree_impl(sph_ctx* c, bool* retry_two_word) {
 }
 
 
-size_t density_smem(const sph_ctx* c, int nwarp) { return (size_t)2 * (c->p.nq + 1) * 8 + (size_t)nwarp * 8 * WALK_TILE * 8 + (size_t)nwarp * WALK_WS * 4; }
+size_t density_smem(const sph_ctx* c, int nwarp) { return (size_t)2 * (c->p.nq + 1) * 8 + (size_t)nwarp * DENS_WARP_DOUBLES * 8 + (size_t)nwarp * WALK_WS * 4; }
 size_t force_smem(const sph_ctx* c, int nwarp) {
   size_t t = (size_t)((c->p.nq + 1) + ((c->p.nq + 1) & 1)) * 8;
-  return t + (size_t)nwarp * FORCE_FIELDS * WALK_TILE * 8 + (size_t)nwarp * WALK_TILE * 4 + (size_t)nwarp * WALK_WS * 4;
+  return t + (size_t)nwarp * FORCE_WARP_DOUBLES * 8 + (size_t)nwarp * WALK_TILE * 4 + (size_t)nwarp * WALK_WS * 4;
 }
 int walk_grid(const sph_ctx* c, int nwarp) {
   const int nchunk = c->g1 - c->g0;
@@ -515,6 +519,10 @@ int run_force(sph_ctx* c) {
   LAUNCH(k_set_int, 1, 1, 0, c->work, c->g0);
   LAUNCH(k_force, walk_grid(c, W), W * 32, force_smem(c, W), c->g1, c->groups, c->dp, A, c->bvh, c->bi, c->d_dwt, c->ax, c->ay, c->az, c->udot, c->adot, c->ctr, c->work, c->exact_counters);
   stage_end(c);
+#ifdef WALK_DEBUG
+  { unsigned long long d[16]; cudaStreamSynchronize(c->stream); cudaMemcpyFromSymbol(d, wk_dbg, sizeof(d)); unsigned long long z[16] = {}; cudaMemcpyToSymbol(wk_dbg, z, sizeof(z));
+    fprintf(stderr, "WKDBG groups %d force: tiles %llu staged %llu trips %llu hits %llu boxpairs %llu | density: tiles %llu staged %llu trips %llu hits %llu\n", c->n_groups, d[0], d[1], d[2], d[3], d[4], d[8], d[9], d[10], d[11]); }
+#endif
   if (c->n_ranks > 1) { stage_begin(c, ST_COMM); double* bufs[5] = {c->ax, c->ay, c->az, c->udot, c->adot}; int r_ = allgatherv(c, bufs, 5); if (r_) return r_; stage_end(c); }
   return SPH_OK;
 }
@@ -522,22 +530,34 @@ size_t gravity_smem(const sph_ctx* c, int nwarp) { return (size_t)((c->p.nq + 1)
 int run_gravity(sph_ctx* c, int do_grav, int do_sinks) {
   stage_begin(c, ST_GRAVITY);
   StateArrays s = state_of(c, c->cur);
+#if GRAV_CHUNK_WIDTH > 0
+  const int ng = cdiv(c->p1 - c->p0, GRAV_CHUNK_WIDTH);
+#else
   const int ng = c->g1 - c->g0;
+#endif
   const int ns = do_sinks ? c->n_sink : 0;
   if ((size_t)(ng + 8) * std::max(ns, 1) * 3 > c->sink_partial_cap) {
     c->sink_partial_cap = (size_t)(ng + 8) * std::max(ns, 1) * 3 * 2;
     DA(c->sink_partial, c->sink_partial_cap);
   }
   if (ng > 0) {
-    const int grid = walk_grid(c, GW_WARPS);
+    const int grid = std::max(1, std::min(cdiv(ng, GW_WARPS), c->n_sm));
     if (!c->grav_spill) DA(c->grav_spill, (size_t)c->n_sm * GW_WARPS * GW_SPILL);
+#if GRAV_CHUNK_WIDTH > 0
+    if ((size_t)ng > c->ggroups_cap) { c->ggroups_cap = (size_t)ng * 5 / 4 + 64; DA(c->ggroups, c->ggroups_cap); DA(c->gbvh, c->ggroups_cap); }
+    LAUNCH(k_grav_chunks, cdiv((int64_t)ng * 32, 256), 256, 0, c->p0, c->p1, GRAV_CHUNK_WIDTH, s.x, s.y, s.z, c->ggroups, c->gbvh);
+    LAUNCH(k_set_int, 1, 1, 0, c->work, 0);
+    LAUNCH(k_gravity, grid, GW_WARPS * 32, gravity_smem(c, GW_WARPS), 0, ng, c->ggroups, c->gbvh, c->dp, c->wnodes, s.x, s.y, s.z, s.h, s.m, c->d_gt,
+           c->ax, c->ay, c->az, do_grav, ns, c->S, c->sink_partial, c->ctr, c->work, c->grav_spill, &c->sc->err);
+#else
     LAUNCH(k_set_int, 1, 1, 0, c->work, c->g0);
     LAUNCH(k_gravity, grid, GW_WARPS * 32, gravity_smem(c, GW_WARPS), c->g0, c->g1, c->groups, c->bvh, c->dp, c->wnodes, s.x, s.y, s.z, s.h, s.m, c->d_gt,
            c->ax, c->ay, c->az, do_grav, ns, c->S, c->sink_partial, c->ctr, c->work, c->grav_spill, &c->sc->err);
+#endif
   }
 #ifdef GW_DEBUG
   { unsigned long long d[16]; cudaStreamSynchronize(c->stream); cudaMemcpyFromSymbol(d, gw_dbg, sizeof(d)); unsigned long long z[16] = {}; cudaMemcpyToSymbol(gw_dbg, z, sizeof(z));
-    fprintf(stderr, "GWDBG trips %llu popped %llu A %llu O %llu M %llu evals %llu entries %llu lanework %llu spills %llu maxsn %llu mixacc %llu mixopen %llu\n", d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7], d[8], d[9], d[10], d[11]);
+    fprintf(stderr, "GWDBG trips %llu popped %llu A %llu O %llu M %llu evals %llu entries %llu lanework %llu spills %llu maxsn %llu mixacc %llu mixopen %llu | T %d RC %d sparse rounds %llu lanework %llu dense entries %llu lanework %llu\n", d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7], d[8], d[9], d[10], d[11], GW_DBG_T, GW_DBG_RC, d[12], d[13], d[14], d[15]);
     unsigned long long hh[33]; cudaMemcpyFromSymbol(hh, gw_hist, sizeof(hh)); unsigned long long zz[33] = {}; cudaMemcpyToSymbol(gw_hist, zz, sizeof(zz));
     fprintf(stderr, "GWHIST"); for (int i = 0; i < 33; ++i) fprintf(stderr, " %llu", hh[i]); fprintf(stderr, "\n"); }
 #endif
@@ -797,7 +817,7 @@ int sph_destroy(sph_ctx* c) {
   for (int b = 0; b < 2; ++b) { for (int f = 0; f < 10; ++f) F(c->st[b][f]); F(c->id[b]); F(c->key[b]); F(c->key_lo[b]); F(c->perm[b]); F(c->acc_key[b]); F(c->acc_val[b]); }
   F(c->rho); F(c->omega); F(c->prs); F(c->cs); F(c->por2); F(c->ax); F(c->ay); F(c->az); F(c->udot); F(c->adot);
   F(c->node_count); F(c->gsize); F(c->gfirst); F(c->groups); F(c->level); F(c->lcx); F(c->lcy); F(c->lcz); F(c->reach); F(c->bvh); F(c->nodes); F(c->node_part); F(c->parent); F(c->nchild);
-  F(c->wnodes); F(c->wcount); F(c->wstart); F(c->widx); F(c->grav_spill);
+  F(c->ggroups); F(c->gbvh); F(c->wnodes); F(c->wcount); F(c->wstart); F(c->widx); F(c->grav_spill);
   F(c->arrive); F(c->cnt); F(c->off); F(c->root); F(c->partial); F(c->cub_tmp); F(c->d_wt); F(c->d_dwt); F(c->d_gt);
   F(c->sink_buf); F(c->sink_partial); F(c->sc); F(c->ctr); F(c->work); F(c->keep); F(c->d_nsel); F(c->pos); F(c->stage_d); F(c->stage_d2);
   if (c->h_sc) cudaFreeHost(c->h_sc);

@@ -35,6 +35,12 @@ struct SinkArrays { double *x, *y, *z, *vx, *vy, *vz, *m, *radius, *ax, *ay, *az
 #define GW_SPILL 8192       // per-warp overflow entries in global memory (never reached in practice; loud if it is)
 
 #ifdef GW_DEBUG
+#ifndef GW_DBG_T
+#define GW_DBG_T 16
+#endif
+#ifndef GW_DBG_RC
+#define GW_DBG_RC 64
+#endif
 __device__ unsigned long long gw_dbg[16];
 __device__ unsigned long long gw_hist[33];
 #define GWD(i, v) do { if (lane == 0) atomicAdd(&gw_dbg[i], (unsigned long long)(v)); } while (0)
@@ -135,6 +141,12 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
       const double soft_min = warp_min(live ? soft : INFINITY), soft_max = warp_max(live ? soft : 0.0);
       const unsigned livemask = __ballot_sync(FULL_MASK, live);
       int sn = 1, gsp = 0, ln = 0;
+#ifdef GW_DEBUG
+      int dq_len = 0, dq_ring = 0;
+      auto dq_flush = [&]() { int mx = dq_len, sm = dq_len; for (int o = 16; o > 0; o >>= 1) { mx = max(mx, __shfl_xor_sync(FULL_MASK, mx, o)); sm += __shfl_xor_sync(FULL_MASK, sm, o); }
+                              GWD(12, mx); GWD(13, sm); dq_len = 0; dq_ring = 0; };
+      auto dq_account = [&](unsigned m) { const int pc = __popc(m); if (pc < GW_DBG_T) { dq_len += (m >> lane) & 1u; if (++dq_ring == GW_DBG_RC) dq_flush(); } else { GWD(14, 1); GWD(15, pc); } };
+#endif
       if (lane == 0) W.stack[0] = make_int2(0, (int)livemask);
       __syncwarp();
 
@@ -189,6 +201,10 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
           const int pos = ln + __popc(balL & lt_mask);
           W.lxy[pos] = make_double2(ncx, ncy); W.lzg[pos] = make_double2(ncz, P.G * nm); W.lmask[pos] = emask;
         }
+#ifdef GW_DEBUG
+        __syncwarp();
+        for (int q = 0; q < __popc(balL); ++q) dq_account(W.lmask[ln + q]);
+#endif
         ln += __popc(balL);
         const int nmix = __popc(balM);
         GWD(0, 1); GWD(1, npop); GWD(2, __popc(balA)); GWD(3, npop - __popc(balA) - nmix); GWD(4, nmix);
@@ -228,6 +244,9 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
             if (W.mgm[q] > 0.0) {
               if (lane == 0) { W.lxy[ln] = make_double2(W.mcx[q], W.mcy[q]); W.lzg[ln] = make_double2(W.mcz[q], W.mgm[q]); W.lmask[ln] = balAcc; }
               ++ln;
+#ifdef GW_DEBUG
+              dq_account(balAcc);
+#endif
             }
           }
           if (balOpen) {
@@ -243,6 +262,9 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
       }
       if (ln > 0) evaluate_list(ln);
       __syncwarp();
+#ifdef GW_DEBUG
+      if (dq_ring) dq_flush();
+#endif
     }
 #pragma unroll
     for (int u = 1; u < GW_ILP; ++u) { gx[0] += gx[u]; gy[0] += gy[u]; gz[0] += gz[u]; }
@@ -269,6 +291,29 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
   }
   n_open = (unsigned long long)warp_sum_ll((long long)n_open); n_acc = (unsigned long long)warp_sum_ll((long long)n_acc);
   if (lane == 0 && do_grav) { atomicAdd(&ctr->grav_opened, n_open); atomicAdd(&ctr->grav_accepted, n_acc); }
+}
+
+// Gravity walk groups: fixed runs of 32 Morton-consecutive particles of this rank's slice [p0, p1) (one warp
+// per run computes its position box).  The gravity walk tolerates a run that straddles a coarse cell boundary
+// (more mixed nodes, decided per particle), and full warps matter more to it than tight boxes.
+__global__ void k_grav_chunks(int p0, int p1, int width, const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
+                              int2* __restrict__ groups, BvhBox* __restrict__ box) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int first = p0 + warp * width;
+  if (first >= p1) return;
+  const int cnt = min(width, p1 - first);
+  float plo[3] = {INFINITY, INFINITY, INFINITY}, phi[3] = {-INFINITY, -INFINITY, -INFINITY};
+  if (lane < cnt) {
+    const int i = first + lane;
+    const double p[3] = {x[i], y[i], z[i]};
+    for (int k = 0; k < 3; ++k) { plo[k] = __double2float_rd(p[k]); phi[k] = __double2float_ru(p[k]); }
+  }
+  for (int k = 0; k < 3; ++k) { plo[k] = warp_minf(plo[k]); phi[k] = warp_maxf(phi[k]); }
+  if (lane == 0) {
+    BvhBox b;
+    for (int k = 0; k < 3; ++k) { b.plo[k] = plo[k]; b.phi[k] = phi[k]; b.rlo[k] = 0.f; b.rhi[k] = 0.f; }
+    box[warp] = b; groups[warp] = make_int2(first, cnt);
+  }
 }
 
 // fold per-warp sink partials in a fixed order (deterministic). One block of 256.

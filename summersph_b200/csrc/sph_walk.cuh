@@ -22,6 +22,21 @@ struct BvhInfo { int nlev; int off[12]; int cnt[12]; };
 #define WALK_CQ    96       // chunk queue entries per warp
 #define WALK_TILE  32       // staged source particles per warp
 #define WALK_WS    (WALK_STACK + WALK_CQ + WALK_TILE)   // unsigned words of walk state per warp
+#ifndef DENS_COMPACT
+#define DENS_COMPACT 0
+#endif
+#ifndef FORCE_COMPACT
+#define FORCE_COMPACT 1
+#endif
+#define PAIR_WIN   64       // compacted (target, source) hits evaluated per window, lane = pair
+#define DENS_WARP_DOUBLES (8 * WALK_TILE + 4 * 32 + 2 * PAIR_WIN + PAIR_WIN / 4)   // tile + targets + results + hit list
+
+#ifdef WALK_DEBUG
+__device__ unsigned long long wk_dbg[16];
+#define WKD(i, v) do { if ((threadIdx.x & 31) == 0) atomicAdd(&wk_dbg[i], (unsigned long long)(v)); } while (0)
+#else
+#define WKD(i, v)
+#endif
 
 struct WalkCounters { unsigned long long dens_cand, dens_contrib, sph_pairs, grav_opened, grav_accepted, h_iters; };
 
@@ -39,78 +54,85 @@ __device__ void neighbour_walk(OP& op, const int2* __restrict__ groups, int chun
                                unsigned* stack, unsigned* cq) {
   unsigned* tix = cq + WALK_CQ;          // particle indices of the tile being collected
   const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
   const BvhBox g = box[bi.off[0] + chunk];
-  int sn = 0, qn = 0, tn = 0;
+  int sn = 0, qn = 0, qpos = 0, tn = 0;
 
   auto hit = [&](const BvhBox& b) -> bool {
     bool r = box_overlap(g.plo, g.phi, b.rlo, b.rhi);
     if (OP::SYMMETRIC) r = r || box_overlap(g.rlo, g.rhi, b.plo, b.phi);
     return r;
   };
-  // Hit chunks -> passing sources.  The chunk descriptors of up to 32 queued chunks come in with one
-  // lane-parallel load; each chunk costs one round of filter loads (lane = source) that only appends the
-  // passing particle indices to a 32-entry list; a full list is staged by lane = list slot, every field load
-  // of a tile in flight at once, then consumed.
-  auto flush_tile = [&]() {
-    __syncwarp();
-    if (lane < tn) op.stage(lane, (int)tix[lane]);
-    __syncwarp();
-    op.consume(tn);
-    tn = 0;
-    __syncwarp();
-  };
-  auto drain_chunks = [&]() {
-    for (int q0 = 0; q0 < qn; q0 += 32) {
-      const int nq = qn - q0 < 32 ? qn - q0 : 32;
-      int2 mysg = make_int2(0, 0);
-      if (lane < nq) mysg = groups[cq[q0 + lane]];
-      for (int q = 0; q < nq; ++q) {
-        const int sgx = __shfl_sync(FULL_MASK, mysg.x, q), sgy = __shfl_sync(FULL_MASK, mysg.y, q);
-        const int j = sgx + lane;
-        const bool ok = (lane < sgy) && op.source_filter(j);
-        const unsigned bal = __ballot_sync(FULL_MASK, ok);
-        const int cntc = __popc(bal);
-        if (cntc == 0) continue;
-        if (tn + cntc > WALK_TILE) flush_tile();
-        if (ok) tix[tn + __popc(bal & ((1u << lane) - 1u))] = (unsigned)j;
-        tn += cntc;
-      }
-    }
-    qn = 0;
-  };
-
   const int top = bi.nlev - 1;
   {
     bool ok = lane < bi.cnt[top];
     if (ok) ok = hit(box[bi.off[top] + lane]);
     unsigned bal = __ballot_sync(FULL_MASK, ok);
-    int pos = __popc(bal & ((1u << lane) - 1u));
+    int pos = __popc(bal & lt);
     if (ok) { if (top == 0) cq[pos] = (unsigned)lane; else stack[pos] = ((unsigned)top << 28) | (unsigned)lane; }
     if (top == 0) qn = __popc(bal); else sn = __popc(bal);
     __syncwarp();
   }
-  while (sn > 0) {
-    const int npop = sn < 4 ? sn : 4;
-    const int grp = lane >> 3;
-    bool valid = grp < npop;
-    unsigned e = valid ? stack[sn - 1 - grp] : 0u;
-    __syncwarp();
-    sn -= npop;
-    const int lev = (int)(e >> 28), idx = (int)(e & 0x0fffffffu);
-    const int clev = lev - 1;
-    const int child = idx * SPH_BVH_FAN + (lane & 7);
-    bool ok = valid && child < bi.cnt[clev > 0 ? clev : 0];
-    if (ok) ok = hit(box[bi.off[clev] + child]);
-    bool ok0 = ok && clev == 0, okn = ok && clev > 0;
-    unsigned b0 = __ballot_sync(FULL_MASK, ok0), bn = __ballot_sync(FULL_MASK, okn);
-    if (ok0) cq[qn + __popc(b0 & ((1u << lane) - 1u))] = (unsigned)child;
-    if (okn) stack[sn + __popc(bn & ((1u << lane) - 1u))] = ((unsigned)clev << 28) | (unsigned)child;
-    qn += __popc(b0); sn += __popc(bn);
-    __syncwarp();
-    if (qn > WALK_CQ - 32) { drain_chunks(); }
+  // One loop iteration = one tile.  The walk is written as a producer with its state in registers so that the
+  // source filter, the staging and the consumer are each instantiated ONCE in the kernel (three inlined copies of
+  // the consumer made the kernel instruction-fetch bound).  Hit chunks -> passing sources: the descriptors of up
+  // to 32 queued chunks come in with one lane-parallel load; each chunk costs one round of filter loads
+  // (lane = source) that appends the passing particle indices to the tile's index list; a chunk that does not
+  // fit stays pending (ballot + index in registers) and opens the next tile.
+  int2 mysg = make_int2(0, 0);
+  int pend_cnt = 0, pend_j = 0; unsigned pend_bal = 0; bool pend_ok = false;
+  for (;;) {
+    if (pend_cnt) { if (pend_ok) tix[__popc(pend_bal & lt)] = (unsigned)pend_j; tn = pend_cnt; pend_cnt = 0; }
+    bool exhausted = false;
+    for (;;) {
+      if (qpos < qn) {
+        if ((qpos & 31) == 0) mysg = (qpos + lane < qn) ? groups[cq[qpos + lane]] : make_int2(0, 0);
+        const int sgx = __shfl_sync(FULL_MASK, mysg.x, qpos & 31), sgy = __shfl_sync(FULL_MASK, mysg.y, qpos & 31);
+        ++qpos;
+        const int j = sgx + lane;
+        const bool ok = (lane < sgy) && op.source_filter(j);
+        const unsigned bal = __ballot_sync(FULL_MASK, ok);
+        const int cntc = __popc(bal);
+        if (cntc == 0) continue;
+        if (tn + cntc > WALK_TILE) { pend_cnt = cntc; pend_bal = bal; pend_j = j; pend_ok = ok; break; }
+        if (ok) tix[tn + __popc(bal & lt)] = (unsigned)j;
+        tn += cntc;
+        continue;
+      }
+      // chunk queue drained: refill it from the node stack (4 nodes x 8 child boxes per trip, coalesced)
+      qn = 0; qpos = 0;
+      if (sn == 0) { exhausted = true; break; }
+      __syncwarp();
+      while (sn > 0 && qn <= WALK_CQ - 32) {
+        const int npop = sn < 4 ? sn : 4;
+        const int grp = lane >> 3;
+        const bool valid = grp < npop;
+        const unsigned e = valid ? stack[sn - 1 - grp] : 0u;
+        __syncwarp();
+        sn -= npop;
+        const int lev = (int)(e >> 28), idx = (int)(e & 0x0fffffffu);
+        const int clev = lev - 1;
+        const int child = idx * SPH_BVH_FAN + (lane & 7);
+        bool ok = valid && child < bi.cnt[clev > 0 ? clev : 0];
+        if (ok) ok = hit(box[bi.off[clev] + child]);
+        const bool ok0 = ok && clev == 0, okn = ok && clev > 0;
+        const unsigned b0 = __ballot_sync(FULL_MASK, ok0), bn = __ballot_sync(FULL_MASK, okn);
+        if (ok0) cq[qn + __popc(b0 & lt)] = (unsigned)child;
+        if (okn) stack[sn + __popc(bn & lt)] = ((unsigned)clev << 28) | (unsigned)child;
+        qn += __popc(b0); sn += __popc(bn);
+        __syncwarp();
+      }
+    }
+    if (tn > 0) {
+      __syncwarp();
+      if (lane < tn) op.stage(lane, (int)tix[lane]);
+      __syncwarp();
+      op.consume(tn);
+      tn = 0;
+      __syncwarp();
+    }
+    if (exhausted && !pend_cnt) break;
   }
-  drain_chunks();
-  if (tn > 0) flush_tile();
 }
 
 // shared kernel-table lookup: returns table-space (w, dw) at q (<= 2 assumed), F:113-118
@@ -139,6 +161,9 @@ struct DensityOp {
   static const bool SYMMETRIC = false;
   // tile (per warp, shared memory): 8 arrays of WALK_TILE doubles
   double *sx, *sy, *sz, *sm, *scx, *scy, *scz, *sR;
+  double *tgx, *tgy, *tgz, *tgih;    // the group's targets (per warp, shared memory): x y z 1/h
+  double *resW, *resB;               // pair results of the current window
+  unsigned short* plist;             // compacted hit list of the current window: (target lane << 5) | tile slot
   const DensityArrays& A;
   const double *wt, *dwt;            // shared-memory tables
   int nq; double dq, inv_dq;
@@ -170,6 +195,7 @@ struct DensityOp {
     scx[s] = A.lcx[j]; scy[s] = A.lcy[j]; scz[s] = A.lcz[j]; sR[s] = A.reach[j];
   }
   __device__ __forceinline__ void consume(int count) {
+    const int lane = threadIdx.x & 31;
     unsigned mask = 0, cmask = 0;
     if (active) {
 #pragma unroll 4
@@ -183,6 +209,45 @@ struct DensityOp {
       }
     }
     cand += __popc(cmask);
+#ifdef WALK_DEBUG
+    { int hc = __popc(mask); int mx = hc, sm = hc; for (int o = 16; o > 0; o >>= 1) { mx = max(mx, __shfl_xor_sync(FULL_MASK, mx, o)); sm += __shfl_xor_sync(FULL_MASK, sm, o); }
+      WKD(8, 1); WKD(9, count); WKD(10, mx); WKD(11, sm); }
+#endif
+#if DENS_COMPACT
+    // The hits (target lane, tile slot) of the whole warp are compacted into one list and evaluated with
+    // lane = pair, so the kernel arithmetic runs with every lane busy whatever the spread of hits over the
+    // targets; each target then adds its own terms in tile order (deterministic).
+    const int c = __popc(mask);
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL_MASK, incl, o); if (lane >= o) incl += v; }
+    const int total = __shfl_sync(FULL_MASK, incl, 31);
+    unsigned mw = mask, ms = mask;
+    int gw = incl - c, gs = gw;
+    for (int base = 0; base < total; base += PAIR_WIN) {
+      const int lim = base + PAIR_WIN;
+      while (mw && gw < lim) { const int k = __ffs(mw) - 1; mw &= mw - 1; plist[gw - base] = (unsigned short)((lane << 5) | k); ++gw; }
+      __syncwarp();
+      const int nwin = total - base < PAIR_WIN ? total - base : PAIR_WIN;
+      for (int p = lane; p < nwin; p += 32) {
+        const int e = plist[p], t = e >> 5, k = e & 31;
+        const double dx = tgx[t] - sx[k], dy = tgy[t] - sy[k], dz = tgz[t] - sz[k];
+        const double r2 = dx * dx + dy * dy + dz * dz;
+        double r, rs; fast_sqrt_rsqrt(r2, r, rs);
+        r = (r2 == 0.0) ? 0.0 : r;                                           // self term, W(0)
+        const double q = r * tgih[t];
+        const bool in = q <= 2.0;
+        double w, dw; table_lerp(wt, dwt, nq, dq, inv_dq, in ? q : 0.0, w, dw);
+        const double mj = in ? sm[k] : 0.0;
+        resW[p] = mj * w;
+        resB[p] = mj * (r * dw);
+        contrib += in ? 1u : 0u;
+      }
+      __syncwarp();
+      while (ms && gs < lim) { ms &= ms - 1; accW += resW[gs - base]; accB += resB[gs - base]; ++gs; }
+      __syncwarp();
+    }
+#else
     // two hits per trip, branch-free, so two independent dependency chains are in flight per lane
     double w2 = 0.0, b2 = 0.0;
     while (mask) {
@@ -193,6 +258,7 @@ struct DensityOp {
       term(k1, v1, w2, b2);
     }
     accW += w2; accB += b2;
+#endif
   }
   __device__ __forceinline__ void term(int k, bool valid, double& aW, double& aB) {
     const double dx = xi - sx[k], dy = yi - sy[k], dz = zi - sz[k];
@@ -212,7 +278,7 @@ struct DensityOp {
 // dynamic shared memory layout: [tables: 2*(nq+1) doubles][per warp: tile 8*WALK_TILE doubles][per warp: stack+cq]
 template <bool HITER>
 __global__ void __launch_bounds__(512, 1)
-k_density(int n_groups, const int2* __restrict__ groups, DevParams P, DensityArrays A, const BvhBox* __restrict__ box, BvhInfo bi,
+k_density(int n_groups, const int2* __restrict__ groups, DevParams P, DensityArrays A, const BvhBox* __restrict__ box, const __grid_constant__ BvhInfo bi,
           const double* __restrict__ g_wt, const double* __restrict__ g_dwt,
           const double* __restrict__ u, double* __restrict__ h,
           double* __restrict__ rho, double* __restrict__ omega, double* __restrict__ prs, double* __restrict__ cs,
@@ -221,10 +287,10 @@ k_density(int n_groups, const int2* __restrict__ groups, DevParams P, DensityArr
   const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double* wt = smem; double* dwt = smem + (P.nq + 1);
   double* tiles = dwt + (P.nq + 1);
-  unsigned* ws = reinterpret_cast<unsigned*>(tiles + (size_t)nwarp * 8 * WALK_TILE);
+  unsigned* ws = reinterpret_cast<unsigned*>(tiles + (size_t)nwarp * DENS_WARP_DOUBLES);
   for (int i = threadIdx.x; i <= P.nq; i += blockDim.x) { wt[i] = g_wt[i]; dwt[i] = g_dwt[i]; }
   __syncthreads();
-  double* tile = tiles + (size_t)warp * 8 * WALK_TILE;
+  double* tile = tiles + (size_t)warp * DENS_WARP_DOUBLES;
   unsigned* stack = ws + (size_t)warp * WALK_WS;
   unsigned* cq = stack + WALK_STACK;
   const int nchunk = n_groups;
@@ -241,6 +307,8 @@ k_density(int n_groups, const int2* __restrict__ groups, DevParams P, DensityArr
     DensityOp op(A);
     op.sx = tile; op.sy = tile + WALK_TILE; op.sz = tile + 2 * WALK_TILE; op.sm = tile + 3 * WALK_TILE;
     op.scx = tile + 4 * WALK_TILE; op.scy = tile + 5 * WALK_TILE; op.scz = tile + 6 * WALK_TILE; op.sR = tile + 7 * WALK_TILE;
+    op.tgx = tile + 8 * WALK_TILE; op.tgy = op.tgx + 32; op.tgz = op.tgx + 64; op.tgih = op.tgx + 96;
+    op.resW = op.tgx + 128; op.resB = op.resW + PAIR_WIN; op.plist = reinterpret_cast<unsigned short*>(op.resB + PAIR_WIN);
     op.wt = wt; op.dwt = dwt; op.nq = P.nq; op.dq = P.dq; op.inv_dq = P.inv_dq;
     const BvhBox g = box[bi.off[0] + chunk];
     for (int k = 0; k < 3; ++k) { op.gplo[k] = g.plo[k]; op.gphi[k] = g.phi[k]; }
@@ -252,6 +320,8 @@ k_density(int n_groups, const int2* __restrict__ groups, DevParams P, DensityArr
     if (!HITER) {
       op.active = live; op.inv_h = 1.0 / hi; op.r2max = 4.0 * hi * hi * (1.0 + 1e-9); op.accW = 0.0; op.accB = 0.0;
       op.g_r2max = warp_max(live ? op.r2max : 0.0);
+      op.tgx[lane] = op.xi; op.tgy[lane] = op.yi; op.tgz[lane] = op.zi; op.tgih[lane] = op.inv_h;
+      __syncwarp();
       neighbour_walk(op, groups, chunk, box, bi, stack, cq);
       if (live) {
         // W/(pi h^3), dW/(pi h^4): F:125-126 (global smoothing) | V:139-140
@@ -285,6 +355,8 @@ k_density(int n_groups, const int2* __restrict__ groups, DevParams P, DensityArr
         op.active = iter; op.inv_h = 1.0 / hi; op.r2max = 4.0 * hi * hi * (1.0 + 1e-9); op.accW = 0.0; op.accB = 0.0;
         op.g_r2max = warp_max(iter ? op.r2max : 0.0);
         if (iter) old_len = hi;
+        op.tgx[lane] = op.xi; op.tgy[lane] = op.yi; op.tgz[lane] = op.zi; op.tgih[lane] = op.inv_h;
+        __syncwarp();
         neighbour_walk(op, groups, chunk, box, bi, stack, cq);
         if (iter) {
           const double n3 = P.pi_norm * ((hi * hi) * hi), n4 = P.pi_norm * ((hi * hi) * (hi * hi));
@@ -318,18 +390,23 @@ struct ForceArrays {
   const int* id;
 };
 #define FORCE_FIELDS 19
+#define FORCE_TG_FIELDS 13
+#define FORCE_WARP_DOUBLES (FORCE_FIELDS * WALK_TILE + FORCE_TG_FIELDS * 32 + 3 * PAIR_WIN + PAIR_WIN / 4)   // tile + targets + results + hit list
 
 struct ForceOp {
   static const bool SYMMETRIC = true;
   double* t;             // tile: FORCE_FIELDS arrays of WALK_TILE doubles
   int* tid;              // tile ids
+  double* tg;            // the group's targets: FORCE_TG_FIELDS arrays of 32 doubles (x y z vx vy vz h 1/h 1/(pi h^4) rho c alpha P/(Omega rho^2))
+  double* res;           // pair results of the current window: f, u, a
+  unsigned short* plist; // compacted hit list of the current window: (target lane << 5) | tile slot
   const ForceArrays& A;
   const double* dwt; int nq; double dq, inv_dq;
   float gplo[3], gphi[3], grlo[3], grhi[3];
   int variable_h; double h_fixed, pi_norm, lit_001;
   // lane state
   bool live;
-  double xi, yi, zi, vxi, vyi, vzi, hi, inv_hi, inv_n4i, rhoi, ci, alphai, por2i, cxi, cyi, czi, Ri;
+  double xi, yi, zi, cxi, cyi, czi, Ri;
   double g_r2max; bool count_all;   // group maximum of r2max; exact pair counter wanted (no early cull)
   double r2max;          // 4 h_i^2 (1 + 1e-9); a pair beyond max(r2max_i, r2max_j) has dW(h_i) = dW(h_j) = 0: every term is an exact zero
   int idi;
@@ -390,69 +467,113 @@ struct ForceOp {
       }
     }
     pairs += __popc(pmask);
+#ifdef WALK_DEBUG
+    { int hc = __popc(mask); int mx = hc, sm = hc; for (int o = 16; o > 0; o >>= 1) { mx = max(mx, __shfl_xor_sync(FULL_MASK, mx, o)); sm += __shfl_xor_sync(FULL_MASK, sm, o); }
+      WKD(0, 1); WKD(1, count); WKD(2, mx); WKD(3, sm); int pc = __popc(pmask); for (int o = 16; o > 0; o >>= 1) pc += __shfl_xor_sync(FULL_MASK, pc, o); WKD(4, pc); }
+#endif
+#if FORCE_COMPACT
+    // Compact the hits (target lane, tile slot) of the whole warp and evaluate them with lane = pair: the
+    // ~95 FP64 instructions of a pair run with every lane busy however unevenly a tile's sources fall among
+    // the targets.  Each target then adds its own terms in tile order (F:383-391, own side; deterministic).
+    const int lane = threadIdx.x & 31;
+    const int c = __popc(mask);
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL_MASK, incl, o); if (lane >= o) incl += v; }
+    const int total = __shfl_sync(FULL_MASK, incl, 31);
+    unsigned mw = mask, ms = mask;
+    int gw = incl - c, gs = gw;
+    for (int base = 0; base < total; base += PAIR_WIN) {
+      const int lim = base + PAIR_WIN;
+      while (mw && gw < lim) { const int k = __ffs(mw) - 1; mw &= mw - 1; plist[gw - base] = (unsigned short)((lane << 5) | k); ++gw; }
+      __syncwarp();
+      const int nwin = total - base < PAIR_WIN ? total - base : PAIR_WIN;
+      for (int p = lane; p < nwin; p += 32) {
+        const int e = plist[p];
+        double f, u, a;
+        pair(e >> 5, e & 31, f, u, a);
+        res[p] = f; res[PAIR_WIN + p] = u; res[2 * PAIR_WIN + p] = a;
+      }
+      __syncwarp();
+      while (ms && gs < lim) {
+        const int k = __ffs(ms) - 1; ms &= ms - 1;
+        const int q = gs - base;
+        const double f = res[q];
+        ax -= f * (xi - t[0 * WALK_TILE + k]);                            // F:383 (own side)
+        ay -= f * (yi - t[1 * WALK_TILE + k]);
+        az -= f * (zi - t[2 * WALK_TILE + k]);
+        ud += res[PAIR_WIN + q]; ad += res[2 * PAIR_WIN + q];
+        ++gs;
+      }
+      __syncwarp();
+    }
+#else
     while (mask) {
       const int k = __ffs(mask) - 1; mask &= mask - 1;
       double f, u, a;
-      pair(k, f, u, a);
-      ax -= f * (xi - t[0 * WALK_TILE + k]);                            // F:383 (own side)
+      pair(threadIdx.x & 31, k, f, u, a);
+      ax -= f * (xi - t[0 * WALK_TILE + k]);
       ay -= f * (yi - t[1 * WALK_TILE + k]);
       az -= f * (zi - t[2 * WALK_TILE + k]);
       ud += u; ad += a;
     }
+#endif
   }
-  // one pair (i, slot k): f = m_j * A / dr  (a_i -= f * (x_i - x_j)), u = du/dt term, a = alpha-rate term
-  __device__ __forceinline__ void pair(int k, double& f, double& u, double& a) const {
-    const double nx = xi - t[0 * WALK_TILE + k], ny = yi - t[1 * WALK_TILE + k], nz = zi - t[2 * WALK_TILE + k];   // F:356
-    const double wx = vxi - t[3 * WALK_TILE + k], wy = vyi - t[4 * WALK_TILE + k], wz = vzi - t[5 * WALK_TILE + k]; // F:358
+  // one pair (target lane tl, tile slot k): f = m_j * A / dr  (a_i -= f * (x_i - x_j)), u = du/dt term, a = alpha-rate term
+  __device__ __forceinline__ void pair(int tl, int k, double& f, double& u, double& a) const {
+    const double* g = tg + tl;
+    const double nx = g[0 * 32] - t[0 * WALK_TILE + k], ny = g[1 * 32] - t[1 * WALK_TILE + k], nz = g[2 * 32] - t[2 * WALK_TILE + k];   // F:356
+    const double wx = g[3 * 32] - t[3 * WALK_TILE + k], wy = g[4 * 32] - t[4 * WALK_TILE + k], wz = g[5 * 32] - t[5 * WALK_TILE + k];   // F:358
+    const double hi_ = g[6 * 32], inv_hi_ = g[7 * 32], inv_n4i_ = g[8 * 32], rhoi_ = g[9 * 32], ci_ = g[10 * 32], alphai_ = g[11 * 32], por2i_ = g[12 * 32];
     const double r2 = nx * nx + ny * ny + nz * nz;
     double dr, inv_dr; fast_sqrt_rsqrt(r2, dr, inv_dr);                 // dr == 0 -> NaN like F:363
     const double rv = wx * nx + wy * ny + wz * nz;
     const double vdotr = rv >= 0.0 ? 0.0 : rv;                          // F:361
     const double mj = t[6 * WALK_TILE + k], hj = t[7 * WALK_TILE + k];
     // kernel gradient magnitudes dW/dr at h_i and h_j                                   F:366 | V:395-396
-    const double qi = dr * inv_hi;
+    const double qi = dr * inv_hi_;
     const bool ini = qi <= 2.0;
-    const double dWi = ini ? table_lerp1(dwt, nq, dq, inv_dq, qi) * inv_n4i : ((qi != qi) ? qi : 0.0);
+    const double dWi = ini ? table_lerp1(dwt, nq, dq, inv_dq, qi) * inv_n4i_ : ((qi != qi) ? qi : 0.0);
     double dWj = dWi;
     if (variable_h) {
       const double qj = dr * t[17 * WALK_TILE + k];
       const bool inj = qj <= 2.0;
       dWj = inj ? table_lerp1(dwt, nq, dq, inv_dq, qj) * t[8 * WALK_TILE + k] : 0.0;
     }
-    const double hbar = variable_h ? (hi + hj) / 2.0 : hi;              // V:402
+    const double hbar = variable_h ? (hi_ + hj) / 2.0 : hi_;            // V:402
     const double nu = (hbar * vdotr) * fast_rcp(r2 + lit_001 * hbar * hbar);   // F:373 | V:405
-    const double cbar = 0.5 * (ci + t[10 * WALK_TILE + k]);
-    const double abar = 0.5 * (alphai + t[11 * WALK_TILE + k]);
-    const double visc = (-abar * cbar * nu + 2.0 * abar * nu * nu) * fast_rcp(0.5 * (rhoi + t[9 * WALK_TILE + k]));   // F:378 | V:410
+    const double cbar = 0.5 * (ci_ + t[10 * WALK_TILE + k]);
+    const double abar = 0.5 * (alphai_ + t[11 * WALK_TILE + k]);
+    const double visc = (-abar * cbar * nu + 2.0 * abar * nu * nu) * fast_rcp(0.5 * (rhoi_ + t[9 * WALK_TILE + k]));   // F:378 | V:410
     const double por2j = t[12 * WALK_TILE + k];
     const double rvn = rv * inv_dr;                                     // n_hat . v_ij
     double scal, vdg;
     if (variable_h) {
       vdg = (dWi * rvn + dWj * rvn) / 2.0;                              // V:401
-      scal = (por2i * dWi + por2j * dWj) + visc * (dWi + dWj) / 2.0;    // V:413-414
+      scal = (por2i_ * dWi + por2j * dWj) + visc * (dWi + dWj) / 2.0;   // V:413-414
     } else {
       vdg = dWi * rvn;                                                  // F:370
-      scal = ((por2i + por2j) + visc) * dWi;                            // F:381-382
+      scal = ((por2i_ + por2j) + visc) * dWi;                           // F:381-382
     }
     f = mj * scal * inv_dr;
-    u = mj * vdg * (por2i + 0.5 * visc);                                // F:387 | V:419-421
+    u = mj * vdg * (por2i_ + 0.5 * visc);                               // F:387 | V:419-421
     a = mj * vdg;                                                       // F:390
   }
 };
 
 __global__ void __launch_bounds__(512, 1)
-k_force(int n_groups, const int2* __restrict__ groups, DevParams P, ForceArrays A, const BvhBox* __restrict__ box, BvhInfo bi, const double* __restrict__ g_dwt,
+k_force(int n_groups, const int2* __restrict__ groups, DevParams P, ForceArrays A, const BvhBox* __restrict__ box, const __grid_constant__ BvhInfo bi, const double* __restrict__ g_dwt,
         double* __restrict__ ax, double* __restrict__ ay, double* __restrict__ az, double* __restrict__ udot,
         double* __restrict__ adot, WalkCounters* ctr, int* work, int count_all) {
   extern __shared__ double smem[];
   const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double* dwt = smem;
   double* tiles = dwt + (P.nq + 1) + ((P.nq + 1) & 1);
-  int* tids = reinterpret_cast<int*>(tiles + (size_t)nwarp * FORCE_FIELDS * WALK_TILE);
+  int* tids = reinterpret_cast<int*>(tiles + (size_t)nwarp * FORCE_WARP_DOUBLES);
   unsigned* ws = reinterpret_cast<unsigned*>(tids + (size_t)nwarp * WALK_TILE);
   for (int i = threadIdx.x; i <= P.nq; i += blockDim.x) dwt[i] = g_dwt[i];
   __syncthreads();
-  double* tile = tiles + (size_t)warp * FORCE_FIELDS * WALK_TILE;
+  double* tile = tiles + (size_t)warp * FORCE_WARP_DOUBLES;
   unsigned* stack = ws + (size_t)warp * WALK_WS;
   unsigned* cq = stack + WALK_STACK;
   const int nchunk = n_groups;
@@ -467,26 +588,33 @@ k_force(int n_groups, const int2* __restrict__ groups, DevParams P, ForceArrays 
     const bool live = lane < tg.y;
     ForceOp op(A);
     op.t = tile; op.tid = tids + warp * WALK_TILE;
+    op.tg = tile + FORCE_FIELDS * WALK_TILE; op.res = op.tg + FORCE_TG_FIELDS * 32;
+    op.plist = reinterpret_cast<unsigned short*>(op.res + 3 * PAIR_WIN);
     op.dwt = dwt; op.nq = P.nq; op.dq = P.dq; op.inv_dq = P.inv_dq;
     op.variable_h = P.variable_h; op.h_fixed = P.h_fixed; op.pi_norm = P.pi_norm; op.lit_001 = P.lit_001;
     const BvhBox g = box[bi.off[0] + chunk];
     for (int k = 0; k < 3; ++k) { op.gplo[k] = g.plo[k]; op.gphi[k] = g.phi[k]; op.grlo[k] = g.rlo[k]; op.grhi[k] = g.rhi[k]; }
     op.live = live;
     const int ii = live ? i : 0;
-    op.xi = A.x[ii]; op.yi = A.y[ii]; op.zi = A.z[ii]; op.vxi = A.vx[ii]; op.vyi = A.vy[ii]; op.vzi = A.vz[ii];
-    op.hi = P.variable_h ? A.h[ii] : P.h_fixed; op.inv_hi = 1.0 / op.hi;
-    op.inv_n4i = 1.0 / (P.pi_norm * ((op.hi * op.hi) * (op.hi * op.hi)));
-    op.rhoi = A.rho[ii]; op.ci = A.c[ii]; op.alphai = A.alpha[ii]; op.por2i = A.por2[ii];
+    op.xi = A.x[ii]; op.yi = A.y[ii]; op.zi = A.z[ii];
+    const double hi = P.variable_h ? A.h[ii] : P.h_fixed, rhoi = A.rho[ii], ci = A.c[ii], alphai = A.alpha[ii], por2i = A.por2[ii];
+    {
+      double* g = op.tg + lane;
+      g[0 * 32] = op.xi; g[1 * 32] = op.yi; g[2 * 32] = op.zi; g[3 * 32] = A.vx[ii]; g[4 * 32] = A.vy[ii]; g[5 * 32] = A.vz[ii];
+      g[6 * 32] = hi; g[7 * 32] = 1.0 / hi; g[8 * 32] = 1.0 / (P.pi_norm * ((hi * hi) * (hi * hi)));
+      g[9 * 32] = rhoi; g[10 * 32] = ci; g[11 * 32] = alphai; g[12 * 32] = por2i;
+    }
     op.cxi = A.lcx[ii]; op.cyi = A.lcy[ii]; op.czi = A.lcz[ii]; op.Ri = A.reach[ii]; op.idi = A.id[ii];
-    op.r2max = (fabs(op.por2i + op.ci) < INFINITY) ? 4.0 * op.hi * op.hi * (1.0 + 1e-9) : INFINITY;   // own NaN: keep every partner
+    op.r2max = (fabs(por2i + ci) < INFINITY) ? 4.0 * hi * hi * (1.0 + 1e-9) : INFINITY;   // own NaN: keep every partner
     op.g_r2max = warp_max(live ? op.r2max : 0.0); op.count_all = count_all != 0;
     op.ax = op.ay = op.az = op.ud = op.ad = 0.0; op.pairs = 0;
+    __syncwarp();
     neighbour_walk(op, groups, chunk, box, bi, stack, cq);
     if (live) {
       ax[i] += op.ax; ay[i] += op.ay; az[i] += op.az;
       udot[i] += op.ud;
       // alpha-rate clean-up F:316-318 | V:345-347
-      adot[i] = fmax(op.ad / op.rhoi, 0.0) + P.lit_015 * ((0.1 - op.alphai) * op.ci / op.hi);
+      adot[i] = fmax(op.ad / rhoi, 0.0) + P.lit_015 * ((0.1 - alphai) * ci / hi);
     }
     tot_pairs += op.pairs;
   }
@@ -527,7 +655,7 @@ struct NgbOp {
 };
 
 __global__ void __launch_bounds__(256)
-k_neighbours(int n_groups, const int2* __restrict__ groups, DensityArrays A, const int* __restrict__ id, const BvhBox* __restrict__ box, BvhInfo bi,
+k_neighbours(int n_groups, const int2* __restrict__ groups, DensityArrays A, const int* __restrict__ id, const BvhBox* __restrict__ box, const __grid_constant__ BvhInfo bi,
              int* __restrict__ count, unsigned long long* __restrict__ hash, const long long* __restrict__ offsets,
              int* __restrict__ list) {
   extern __shared__ double smem[];
