@@ -25,7 +25,7 @@
 struct SinkArrays { double *x, *y, *z, *vx, *vy, *vz, *m, *radius, *ax, *ay, *az; };
 
 #ifndef GW_WARPS
-#define GW_WARPS 24         // warps per block
+#define GW_WARPS 20         // warps per block
 #endif
 #ifndef GW_ILP
 #define GW_ILP 2            // interaction-list entries in flight per lane
@@ -57,8 +57,8 @@ struct GravWarpSmem {
   int2     stack[GW_STACK];
   double2  lxy[GW_LIST], lzg[GW_LIST];     // (cx, cy), (cz, G*M)
   unsigned lmask[GW_LIST];
-  double   mcx[32], mcy[32], mcz[32], mgm[32], msize[32];   // mixed nodes of the current trip
-  int      mchild[32], mnch[32]; unsigned mmask[32];
+  double   mcx[32], mcy[32], mcz[32], msize[32];            // mixed nodes of the current trip
+  unsigned mmask[32];
 };
 
 // 1/sqrt(x): MUFU seed (~2^-20) + one Halley step (cubic: ~2^-58), x > 0
@@ -71,19 +71,18 @@ __device__ __forceinline__ double fast_rsqrt(double x) {
 }
 
 // one list entry against one particle: a -= G M g(dist/h) dir / dist^3                  F:279-281 | F:129-146
+// h2x4 = 4 h^2: dist/h <= 2 is decided on the squares (g(2) = 1 and the table is continuous there, so which side
+// of the branch a borderline pair takes changes the term by rounding only); W = 1 beyond it needs no multiply.
 __device__ __forceinline__ void grav_term(const double2 a, const double2 b, const bool on, const double xi, const double yi,
-                                          const double zi, const double inv_h, const double soft, const double* __restrict__ gt,
+                                          const double zi, const double inv_h, const double h2x4, const double soft, const double* __restrict__ gt,
                                           const int nq, const double dq, const double inv_dq, double& gx, double& gy, double& gz) {
   const double dx = xi - a.x, dy = yi - a.y, dz = zi - b.x;                  // F:274
   const double d2 = fma(dx, dx, fma(dy, dy, fma(dz, dz, soft)));
-  const bool v = on;                          // F:279: M > 0 is checked when the entry is listed; d2 >= soft > 0
-  const double rs = fast_rsqrt(d2);
-  const double q = (d2 * rs) * inv_h;
-  double W = 1.0;
-  if (q <= 2.0) W = table_lerp1(gt, nq, dq, inv_dq, q);
-  double f = (b.y * W) * (rs * rs * rs);
-  f = v ? f : 0.0;
-  gx -= f * dx; gy -= f * dy; gz -= f * dz;
+  const double rs = fast_rsqrt(d2);                                          // F:279: M > 0 is checked when the entry is listed; d2 >= soft > 0
+  double gm = b.y;
+  if (d2 <= h2x4) gm *= table_lerp1(gt, nq, dq, inv_dq, (d2 * rs) * inv_h);
+  const double f = gm * (rs * rs * rs);
+  if (on) { gx = fma(-f, dx, gx); gy = fma(-f, dy, gy); gz = fma(-f, dz, gz); }
 }
 
 // dynamic smem: grav table (nq+1 doubles, padded to even) then one GravWarpSmem per warp
@@ -115,7 +114,7 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
     const bool live = lane < tg.y;
     const double xi = live ? x[i] : 0.0, yi = live ? y[i] : 0.0, zi = live ? z[i] : 0.0;
     const double hi = live ? (P.variable_h ? h[i] : P.h_fixed) : 1.0;
-    const double inv_h = 1.0 / hi;
+    const double inv_h = 1.0 / hi, h2x4 = 4.0 * hi * hi;
     const double soft = P.soft_hi ? 0.001 * hi : 0.001 * P.h_fixed;          // F:275 | V:296 | T:298
     double gx[GW_ILP], gy[GW_ILP], gz[GW_ILP];
 #pragma unroll
@@ -130,9 +129,9 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
       for (; k + GW_ILP <= cnt; k += GW_ILP) {          // GW_ILP independent chains per trip
 #pragma unroll
         for (int u = 0; u < GW_ILP; ++u)
-          grav_term(W.lxy[k + u], W.lzg[k + u], (W.lmask[k + u] >> lane) & 1u, xi, yi, zi, inv_h, soft, gt, P.nq, P.dq, P.inv_dq, gx[u], gy[u], gz[u]);
+          grav_term(W.lxy[k + u], W.lzg[k + u], (W.lmask[k + u] >> lane) & 1u, xi, yi, zi, inv_h, h2x4, soft, gt, P.nq, P.dq, P.inv_dq, gx[u], gy[u], gz[u]);
       }
-      for (; k < cnt; ++k) grav_term(W.lxy[k], W.lzg[k], (W.lmask[k] >> lane) & 1u, xi, yi, zi, inv_h, soft, gt, P.nq, P.dq, P.inv_dq, gx[0], gy[0], gz[0]);
+      for (; k < cnt; ++k) grav_term(W.lxy[k], W.lzg[k], (W.lmask[k] >> lane) & 1u, xi, yi, zi, inv_h, h2x4, soft, gt, P.nq, P.dq, P.inv_dq, gx[0], gy[0], gz[0]);
     };
 
     if (do_grav) {
@@ -193,37 +192,20 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
           else cls = 3;
         }
         const unsigned emask = (unsigned)e.y;
-        if (cls == 1) n_acc += __popc(emask);
-        if (cls == 2) n_open += __popc(emask);
-        const unsigned balA = __ballot_sync(FULL_MASK, cls == 1), balM = __ballot_sync(FULL_MASK, cls == 3);
-        const unsigned balL = __ballot_sync(FULL_MASK, cls == 1 && nm > 0.0);      // F:279: massless nodes add nothing
-        if (cls == 1 && nm > 0.0) {
-          const int pos = ln + __popc(balL & lt_mask);
-          W.lxy[pos] = make_double2(ncx, ncy); W.lzg[pos] = make_double2(ncz, P.G * nm); W.lmask[pos] = emask;
-        }
-#ifdef GW_DEBUG
-        __syncwarp();
-        for (int q = 0; q < __popc(balL); ++q) dq_account(W.lmask[ln + q]);
-#endif
-        ln += __popc(balL);
+        const unsigned balM = __ballot_sync(FULL_MASK, cls == 3);
         const int nmix = __popc(balM);
-        GWD(0, 1); GWD(1, npop); GWD(2, __popc(balA)); GWD(3, npop - __popc(balA) - nmix); GWD(4, nmix);
+        GWD(0, 1); GWD(1, npop); GWD(4, nmix);
         if (cls == 3) {
           const int pos = __popc(balM & lt_mask);
-          W.mcx[pos] = ncx; W.mcy[pos] = ncy; W.mcz[pos] = ncz; W.mgm[pos] = P.G * nm; W.msize[pos] = nsize;
-          W.mchild[pos] = nchild; W.mnch[pos] = nnch; W.mmask[pos] = emask;
+          W.mcx[pos] = ncx; W.mcy[pos] = ncy; W.mcz[pos] = ncz; W.msize[pos] = nsize; W.mmask[pos] = emask;
         }
-        // children of the all-open nodes: exclusive scan of the block sizes over the lanes
-        const int nch = (cls == 2) ? nnch : 0;
-        int incl = nch;
-        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL_MASK, incl, o); if (lane >= o) incl += t; }
-        const int total = __shfl_sync(FULL_MASK, incl, 31);
-        make_room(total);
-        for (int k = 0; k < nch; ++k) W.stack[sn + incl - nch + k] = make_int2(nchild + k, (int)emask);
-        sn += total;
         __syncwarp();
-        // ---- lane = particle: the reference's own test on the mixed nodes
+        // ---- lane = particle: the reference's own test on the mixed nodes; the node's lane keeps the two ballots
+        unsigned acc_mask = (cls == 1) ? emask : 0u, open_mask = (cls == 2) ? emask : 0u;
+        unsigned bm = balM;
+#pragma unroll 2
         for (int q = 0; q < nmix; ++q) {
+          const int L = __ffs(bm) - 1; bm &= bm - 1;
           const unsigned mm = W.mmask[q];
           const bool in = (mm >> lane) & 1u;
           const double dx = xi - W.mcx[q], dy = yi - W.mcy[q], dz = zi - W.mcz[q];          // F:274
@@ -238,25 +220,28 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
             accept = __ddiv_rn(size, __dsqrt_rn(e2)) < theta;
           }
           const unsigned balAcc = __ballot_sync(FULL_MASK, in && accept), balOpen = __ballot_sync(FULL_MASK, in && !accept);
-          GWD(10, balAcc != 0); GWD(11, balOpen != 0);
-          if (balAcc) {
-            if (lane == 0) n_acc += __popc(balAcc);
-            if (W.mgm[q] > 0.0) {
-              if (lane == 0) { W.lxy[ln] = make_double2(W.mcx[q], W.mcy[q]); W.lzg[ln] = make_double2(W.mcz[q], W.mgm[q]); W.lmask[ln] = balAcc; }
-              ++ln;
-#ifdef GW_DEBUG
-              dq_account(balAcc);
-#endif
-            }
-          }
-          if (balOpen) {
-            const int nc = W.mnch[q];
-            make_room(nc);
-            if (lane < nc) W.stack[sn + lane] = make_int2(W.mchild[q] + lane, (int)balOpen);
-            if (lane == 0) n_open += __popc(balOpen);
-            sn += nc;
-          }
+          if (lane == L) { acc_mask = balAcc; open_mask = balOpen; }
         }
+        // ---- lane = node again: accepted (node, lane set) pairs join the interaction list, opened ones push their child block
+        n_acc += __popc(acc_mask); n_open += __popc(open_mask);
+        const bool ins = acc_mask != 0u && nm > 0.0;                                // F:279: massless nodes add nothing
+        const unsigned balL = __ballot_sync(FULL_MASK, ins);
+        if (ins) {
+          const int pos = ln + __popc(balL & lt_mask);
+          W.lxy[pos] = make_double2(ncx, ncy); W.lzg[pos] = make_double2(ncz, P.G * nm); W.lmask[pos] = acc_mask;
+        }
+#ifdef GW_DEBUG
+        __syncwarp();
+        for (int q = 0; q < __popc(balL); ++q) dq_account(W.lmask[ln + q]);
+#endif
+        ln += __popc(balL);
+        const int nch = open_mask ? nnch : 0;
+        int incl = nch;
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL_MASK, incl, o); if (lane >= o) incl += t; }
+        const int total = __shfl_sync(FULL_MASK, incl, 31);
+        make_room(total);
+        for (int k = 0; k < nch; ++k) W.stack[sn + incl - nch + k] = make_int2(nchild + k, (int)open_mask);
+        sn += total;
         __syncwarp();
         if (ln > GW_LIST - 32) { evaluate_list(ln); ln = 0; __syncwarp(); }
       }
