@@ -73,7 +73,7 @@ struct sph_ctx {
   unsigned char* keep = nullptr; unsigned long long* acc_key[2] = {}; int* acc_val[2] = {}; int* d_nsel = nullptr;
   int* pos = nullptr;           // ascending-number position of each sorted particle (downloads)
   double* stage_d = nullptr; double* stage_d2 = nullptr; int stage_flip = 0;   // device staging for ordered downloads
-  bool tree_valid = false; int exact_counters = 0;
+  bool tree_valid = false; bool pos_moved = true; int tree_reuse = 1; int exact_counters = 0;   // pos_moved: positions / particle set changed since the last build
   sph_counts counts; double stage_ms[ST_COUNT] = {};
   std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> ev_used; std::vector<cudaEvent_t> ev_pool;
   int64_t launches = 0;
@@ -358,7 +358,23 @@ int build_tree_impl(sph_ctx* c, bool* retry_two_word);
 // Single-word (63-bit, 21-level) keys are the fast path.  If two particles share a full key while the
 // reference's max_depth is deeper, the build is repeated (and stays) on the two-word path: 42 levels,
 // sorted with two stable radix passes (low word, then high word).
+int refresh_tree(sph_ctx* c) {
+  const int n = (int)c->n, T = 256;
+  stage_begin(c, ST_TREE);
+  if (c->dp.variable_h) {
+    StateArrays s = state_of(c, c->cur);
+    LAUNCH(k_refresh_reach, cdiv(n, T), T, 0, n, s.h, c->level, c->root, c->dp, c->reach);
+    const BvhInfo& bi = c->bi;
+    LAUNCH(k_bvh_leaf, cdiv((int64_t)bi.cnt[0] * 32, T), T, 0, bi.cnt[0], c->groups, s.x, s.y, s.z, c->lcx, c->lcy, c->lcz, c->reach, c->bvh);
+    for (int l = 0; l + 1 < bi.nlev; ++l)
+      LAUNCH(k_bvh_up, cdiv(bi.cnt[l + 1], T), T, 0, bi.cnt[l], c->bvh + bi.off[l], c->bvh + bi.off[l + 1]);
+  }
+  stage_end(c);
+  return SPH_OK;
+}
+
 int build_tree(sph_ctx* c) {
+  if (c->tree_valid && !c->pos_moved && c->tree_reuse) return refresh_tree(c);
   bool retry = false;
   int r = build_tree_impl(c, &retry);
   if (r == SPH_OK && retry) {
@@ -468,7 +484,7 @@ int build_tree_impl(sph_ctx* c, bool* retry_two_word) {
     { int r_ = compute_slices(c); if (r_) return r_; }
   }
   stage_end(c);
-  c->tree_valid = true;
+  c->tree_valid = true; c->pos_moved = false;
   return SPH_OK;
 }
 
@@ -623,7 +639,7 @@ int compact(sph_ctx* c) {
   if (nsel > 0) LAUNCH(k_permute, cdiv(nsel, T), T, 0, nsel, c->perm[1], pa);
   c->cur ^= 1;
   c->n = nsel;
-  c->tree_valid = false;
+  c->tree_valid = false; c->pos_moved = true;
   return SPH_OK;
 }
 
@@ -634,6 +650,7 @@ int step(sph_ctx* c) {
   if ((r = evaluate(c, SPH_EVAL_ALL))) return r;                              // F:894-898
   stage_begin(c, ST_INTEGRATE);
   LAUNCH(k_kick<true>, cdiv(n, T), T, 0, n, state_of(c, c->cur), rates_of(c), c->sc);       // F:900,903
+  c->pos_moved = true;
   LAUNCH(k_kick_sinks<true>, 1, SPH_MAX_SINKS, 0, c->S, c->sc);
   stage_end(c);
   if ((r = evaluate(c, SPH_EVAL_ALL))) return r;                              // F:905-910
@@ -772,6 +789,7 @@ int sph_create(const sph_params* p, int32_t device, sph_ctx** out) {
   if (cudaSetDevice(device) != cudaSuccess) { c->err = "cudaSetDevice failed"; return fail(SPH_ERR_CUDA); }
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { c->err = "stream create failed"; return fail(SPH_ERR_CUDA); }
   make_dev_params(c);
+  c->tree_reuse = getenv("SPH_B200_NO_TREE_REUSE") ? 0 : 1;     // developer switch: rebuild the tree in every evaluation
   int r;
   if ((r = upload_tables(c))) return fail(r);
   c->n_partial = 4096;
@@ -845,7 +863,7 @@ int sph_comm_init(sph_ctx* c, int32_t rank, int32_t n_ranks, const void* uid) {
   NcclUid id; std::memcpy(&id, uid, 128);
   int r = c->nccl.CommInitRank(&c->comm, n_ranks, id, rank);
   if (r != 0) { c->err = std::string("ncclCommInitRank: ") + (c->nccl.GetErrorString ? c->nccl.GetErrorString(r) : "?"); return SPH_ERR_COMM; }
-  c->rank = rank; c->n_ranks = n_ranks; c->tree_valid = false; c->p2p_stale = true;
+  c->rank = rank; c->n_ranks = n_ranks; c->tree_valid = false; c->pos_moved = true; c->p2p_stale = true;
   return SPH_OK;
 }
 
@@ -860,7 +878,7 @@ int sph_upload(sph_ctx* c, int64_t n, const double* x, const double* y, const do
   if (c->dp.variable_h && !h) { c->err = "variable-h mode needs the smoothing-length column"; return SPH_ERR_ARG; }
   cudaSetDevice(c->device);
   int r = ensure_capacity(c, n); if (r) return r;
-  c->n = n; c->n_upload = n; c->cur = 0; c->tree_valid = false;
+  c->n = n; c->n_upload = n; c->cur = 0; c->tree_valid = false; c->pos_moved = true;
   const double* src[10] = {x, y, z, vx, vy, vz, u, m, alpha, c->dp.variable_h ? h : nullptr};   // F ignores column 10
   for (int f = 0; f < 10; ++f) {
     if (src[f]) CK(cudaMemcpyAsync(c->st[0][f], src[f], (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));

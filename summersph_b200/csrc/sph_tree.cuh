@@ -132,6 +132,21 @@ __global__ void k_leaf(int n, const uint64_t* __restrict__ key, const uint64_t* 
   reach[i] = multi ? -1.0 : __dadd_rn(2.0 * hh, s / 2.0);                // V:479 `2*max_len + size/2`
 }
 
+// The positions did not move since the last build (evaluation A of a step follows evaluation B of the previous
+// one, F:894 after F:905, unless particles were removed): keys, order, leaf cells, octree, masses and walk
+// groups are what a rebuild would produce again; only h changed (calc_smoothing, V:1152), so only the reach
+// R = 2h + size/2 of every leaf (and the BVH boxes built from it) is refreshed.
+__global__ void k_refresh_reach(int n, const double* __restrict__ h, const int* __restrict__ level, const RootBox* __restrict__ rb,
+                                DevParams P, double* __restrict__ reach) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (!(reach[i] > 0.0)) return;                                         // depth-limited multi-particle node: stays -1
+  double s = rb->size; const int lev = level[i];
+  for (int l = 0; l < lev; ++l) s = s * 0.5;
+  const double hh = P.variable_h ? h[i] : P.h_fixed;
+  reach[i] = __dadd_rn(2.0 * hh, s / 2.0);                               // V:479 `2*max_len + size/2`
+}
+
 // ------------------------------------------------------------------------------------------------------
 // implicit 8-ary BVH over walk groups (neighbour walks only need a conservative superset; the exact
 // per-particle leaf-box test decides membership).

@@ -346,3 +346,32 @@ def test_disc_200k_vs_threaded_oracle(E, O):
     with E(p) as e:
         e.upload(b, s); e.evaluate(mask)
         compare_eval(o, e, check_ngb=False, mask=mask)
+
+
+@pytest.mark.parametrize("mode", [MODE_FIXED_H, MODE_VARIABLE_H])
+def test_tree_reuse_is_bit_identical(mode, E, monkeypatch):
+    """Evaluation A of a step sees the positions of the previous step's evaluation B (F:894 after F:905): the
+    engine keeps that tree and only refreshes the reach R = 2h + size/2 with the new h (V:1152).  The state after
+    several steps must equal, bit for bit, the state of a context that rebuilds the tree in every evaluation
+    (which is what the oracle-checked tests above establish as the reference's result)."""
+    p = default_params(mode)
+    b, s = ics.keplerian_disc(20_000, seed=5)
+    out = []
+    for no_reuse in (False, True):
+        if no_reuse:
+            monkeypatch.setenv("SPH_B200_NO_TREE_REUSE", "1")
+        else:
+            monkeypatch.delenv("SPH_B200_NO_TREE_REUSE", raising=False)
+        with E(p) as e:
+            e.upload(b, s)
+            dt, t = 0.01, 0.0
+            for _ in range(4):
+                dt, t = e.step(dt, t)
+            be, se = e.download()
+            out.append((dt, t, be, se, e.stage_times()))
+    (dt0, t0, b0, s0, st0), (dt1, t1, b1, s1, st1) = out
+    assert (dt0, t0) == (dt1, t1)
+    for k in GAS_FIELDS:
+        assert np.array_equal(getattr(b0, k), getattr(b1, k)), k
+    for k in ("x", "y", "z", "vx", "vy", "vz", "m"):
+        assert np.array_equal(getattr(s0, k), getattr(s1, k)), k
