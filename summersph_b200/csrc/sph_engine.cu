@@ -62,6 +62,7 @@ struct sph_ctx {
   BvhBox* bvh = nullptr; size_t bvh_cap = 0; BvhInfo bi;
   int *node_count = nullptr, *gsize = nullptr, *gfirst = nullptr; int2* groups = nullptr; int n_groups = 0;
   GNode* nodes = nullptr; int *node_part = nullptr, *parent = nullptr, *nchild = nullptr, *arrive = nullptr, *cnt = nullptr, *off = nullptr;
+  int* nl_pool = nullptr; size_t nl_pool_blocks = 0; int* nl_head = nullptr; size_t nl_head_cap = 0; int* nl_ctl = nullptr; bool nl_valid = false;   // saved candidate lists (density pass -> pair loop)
   int2* ggroups = nullptr; BvhBox* gbvh = nullptr; size_t ggroups_cap = 0;   // gravity walk groups (fixed runs of the rank's slice)
   WNode* wnodes = nullptr; int *wcount = nullptr, *wstart = nullptr, *widx = nullptr; int2* grav_spill = nullptr;   // gravity walk layout
   RootBox* root = nullptr; double* partial = nullptr; int n_partial = 0;
@@ -73,7 +74,7 @@ struct sph_ctx {
   unsigned char* keep = nullptr; unsigned long long* acc_key[2] = {}; int* acc_val[2] = {}; int* d_nsel = nullptr;
   int* pos = nullptr;           // ascending-number position of each sorted particle (downloads)
   double* stage_d = nullptr; double* stage_d2 = nullptr; int stage_flip = 0;   // device staging for ordered downloads
-  bool tree_valid = false; bool pos_moved = true; int tree_reuse = 1; int exact_counters = 0;   // pos_moved: positions / particle set changed since the last build
+  bool tree_valid = false; bool pos_moved = true; int tree_reuse = 1; int use_lists = 1; int nl_exact = 0; int exact_counters = 0;   // pos_moved: positions / particle set changed since the last build
   sph_counts counts; double stage_ms[ST_COUNT] = {};
   std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> ev_used; std::vector<cudaEvent_t> ev_pool;
   int64_t launches = 0;
@@ -360,6 +361,7 @@ int build_tree_impl(sph_ctx* c, bool* retry_two_word);
 // sorted with two stable radix passes (low word, then high word).
 int refresh_tree(sph_ctx* c) {
   const int n = (int)c->n, T = 256;
+  c->nl_valid = false;
   stage_begin(c, ST_TREE);
   if (c->dp.variable_h) {
     StateArrays s = state_of(c, c->cur);
@@ -388,6 +390,7 @@ int build_tree(sph_ctx* c) {
 
 int build_tree_impl(sph_ctx* c, bool* retry_two_word) {
   const int n = (int)c->n;
+  c->nl_valid = false;
   const int T = 256;
   *retry_two_word = false;
   if (c->two_word && !c->key_lo[0]) { for (int b = 0; b < 2; ++b) DA(c->key_lo[b], c->cap); }
@@ -508,20 +511,32 @@ int run_density(sph_ctx* c) {
   const int n = (int)c->n, W = 16;
   stage_begin(c, ST_DENSITY);
   StateArrays s = state_of(c, c->cur);
+  // pool of 32-int blocks for the saved candidate lists: about one block (30 sources) per local particle, grown
+  // when an evaluation overflowed it (that evaluation's pair loop walks by itself instead)
+  {
+    const size_t want = (size_t)(c->p1 - c->p0) + 4 * (size_t)(c->g1 - c->g0) + 1024;
+    if (want > c->nl_pool_blocks) { c->nl_pool_blocks = want + want / 4; DA(c->nl_pool, c->nl_pool_blocks * 32); }
+    if ((size_t)c->n_groups + 1 > c->nl_head_cap) { c->nl_head_cap = (size_t)c->n_groups * 5 / 4 + 64; DA(c->nl_head, c->nl_head_cap); }
+    CK(cudaMemsetAsync(c->nl_ctl, 0, 2 * sizeof(int), c->stream));      // ctl[2] (overflow) is sticky until the host has seen it
+  }
+  const NeighbourListSink nl{c->nl_pool, c->nl_head, c->nl_ctl, (int)std::min<size_t>(c->nl_pool_blocks, 0x7fffffff)};
   LAUNCH(k_set_int, 1, 1, 0, c->work, c->g0);
   LAUNCH(k_density<false>, walk_grid(c, W), W * 32, density_smem(c, W), c->g1, c->groups, c->dp, dens_arrays(c), c->bvh, c->bi, c->d_wt, c->d_dwt,
-         s.u, s.h, c->rho, c->omega, c->prs, c->cs, c->por2, c->ctr, c->work, c->exact_counters);
+         s.u, s.h, c->rho, c->omega, c->prs, c->cs, c->por2, c->ctr, c->work, c->exact_counters, nl);
+  c->nl_valid = true; c->nl_exact = c->exact_counters;
+  if (c->n_ranks > 1) { int r_ = allreduce(c, c->nl_ctl + 1, 1, 2 /*ncclInt32*/, 2 /*ncclMax*/); if (r_) return r_; }   // a non-finite particle anywhere voids every rank's lists
   stage_end(c);
   if (c->n_ranks > 1) { stage_begin(c, ST_COMM); double* bufs[3] = {c->rho, c->cs, c->por2}; int r_ = allgatherv_begin(c, bufs, 3);   /* what the pair loop reads of its sources (Omega and P stay rank-local until a diagnostic download asks); completes under the gravity walk */ if (r_) return r_; stage_end(c); }
   return SPH_OK;
 }
 int run_hiter(sph_ctx* c) {
   const int n = (int)c->n, W = 16;
+  c->nl_valid = false;                       // h changes: the saved lists' distance culls no longer hold
   stage_begin(c, ST_HITER);
   StateArrays s = state_of(c, c->cur);
   LAUNCH(k_set_int, 1, 1, 0, c->work, c->g0);
   LAUNCH(k_density<true>, walk_grid(c, W), W * 32, density_smem(c, W), c->g1, c->groups, c->dp, dens_arrays(c), c->bvh, c->bi, c->d_wt, c->d_dwt,
-         s.u, s.h, c->rho, c->omega, c->prs, c->cs, c->por2, c->ctr, c->work, c->exact_counters);
+         s.u, s.h, c->rho, c->omega, c->prs, c->cs, c->por2, c->ctr, c->work, c->exact_counters, NeighbourListSink{nullptr, nullptr, c->nl_ctl, 0});
   stage_end(c);
   if (c->n_ranks > 1) { stage_begin(c, ST_COMM); double* bufs[1] = {s.h}; int r_ = allgatherv(c, bufs, 1); if (r_) return r_; stage_end(c); }
   return SPH_OK;
@@ -532,8 +547,14 @@ int run_force(sph_ctx* c) {
   stage_begin(c, ST_SPH);
   StateArrays s = state_of(c, c->cur);
   ForceArrays A{s.x, s.y, s.z, s.vx, s.vy, s.vz, s.m, s.h, c->rho, c->cs, s.alpha, c->por2, c->lcx, c->lcy, c->lcz, c->reach, s.id};
+  const NeighbourListSink nl{c->nl_pool, c->nl_head, c->nl_ctl, (int)std::min<size_t>(c->nl_pool_blocks, 0x7fffffff)};
+  const bool listed = c->nl_valid && c->nl_exact == c->exact_counters && c->use_lists;
+  if (listed) {
+    LAUNCH(k_set_int, 1, 1, 0, c->work, c->g0);
+    LAUNCH(k_force<true>, walk_grid(c, W), W * 32, force_smem(c, W), c->g1, c->groups, c->dp, A, c->bvh, c->bi, c->d_dwt, c->ax, c->ay, c->az, c->udot, c->adot, c->ctr, c->work, c->exact_counters, nl, 0);
+  }
   LAUNCH(k_set_int, 1, 1, 0, c->work, c->g0);
-  LAUNCH(k_force, walk_grid(c, W), W * 32, force_smem(c, W), c->g1, c->groups, c->dp, A, c->bvh, c->bi, c->d_dwt, c->ax, c->ay, c->az, c->udot, c->adot, c->ctr, c->work, c->exact_counters);
+  LAUNCH(k_force<false>, walk_grid(c, W), W * 32, force_smem(c, W), c->g1, c->groups, c->dp, A, c->bvh, c->bi, c->d_dwt, c->ax, c->ay, c->az, c->udot, c->adot, c->ctr, c->work, c->exact_counters, nl, listed ? 1 : 0);
   stage_end(c);
 #ifdef WALK_DEBUG
   { unsigned long long d[16]; cudaStreamSynchronize(c->stream); cudaMemcpyFromSymbol(d, wk_dbg, sizeof(d)); unsigned long long z[16] = {}; cudaMemcpyToSymbol(wk_dbg, z, sizeof(z));
@@ -694,7 +715,15 @@ int step(sph_ctx* c) {
   CK(cudaMemsetAsync(&c->sc->n_removed, 0, sizeof(int) * 2, c->stream));
   if (n_removed > 0) { if ((r = compact(c))) return r; }
   CK(cudaMemcpyAsync(c->h_sc, c->sc, sizeof(SimScalars), cudaMemcpyDeviceToHost, c->stream));
+  int nl_host[4] = {0, 0, 0, 0};
+  CK(cudaMemcpyAsync(nl_host, c->nl_ctl, sizeof(nl_host), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
+  if (nl_host[2]) {                          // the candidate-list pool overflowed in this step: double it for the next one
+    const size_t want = c->nl_pool_blocks * 2;
+    DA(c->nl_pool, want * 32); c->nl_pool_blocks = want;
+    CK(cudaMemsetAsync(c->nl_ctl, 0, 4 * sizeof(int), c->stream));
+  }
+  c->nl_valid = false;
   c->n_sink = c->h_sc->n_sink;
   stage_end(c);
   return SPH_OK;
@@ -789,7 +818,8 @@ int sph_create(const sph_params* p, int32_t device, sph_ctx** out) {
   if (cudaSetDevice(device) != cudaSuccess) { c->err = "cudaSetDevice failed"; return fail(SPH_ERR_CUDA); }
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { c->err = "stream create failed"; return fail(SPH_ERR_CUDA); }
   make_dev_params(c);
-  c->tree_reuse = getenv("SPH_B200_NO_TREE_REUSE") ? 0 : 1;     // developer switch: rebuild the tree in every evaluation
+  c->tree_reuse = getenv("SPH_B200_NO_TREE_REUSE") ? 0 : 1;
+  c->use_lists = getenv("SPH_B200_NO_LISTS") ? 0 : 1;            // developer switch: the pair loop always walks by itself     // developer switch: rebuild the tree in every evaluation
   int r;
   if ((r = upload_tables(c))) return fail(r);
   c->n_partial = 4096;
@@ -798,6 +828,8 @@ int sph_create(const sph_params* p, int32_t device, sph_ctx** out) {
   if ((r = dalloc(c, &c->sc, 1))) return fail(r);
   if ((r = dalloc(c, &c->ctr, 1))) return fail(r);
   if ((r = dalloc(c, &c->work, 4))) return fail(r);
+  if ((r = dalloc(c, &c->nl_ctl, 4))) return fail(r);
+  cudaMemset(c->nl_ctl, 0, 4 * sizeof(int));
   if ((r = dalloc(c, &c->d_nsel, 1))) return fail(r);
   if ((r = dalloc(c, &c->sink_buf, (size_t)SPH_MAX_SINKS * 11))) return fail(r);
   { double* b = c->sink_buf; const int M = SPH_MAX_SINKS;
@@ -814,7 +846,8 @@ int sph_create(const sph_params* p, int32_t device, sph_ctx** out) {
   if ((size_t)maxsm < need) { c->err = "device shared memory too small for the walk kernels"; return fail(SPH_ERR_CUDA); }
   cudaFuncSetAttribute(k_density<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)density_smem(c, 16));
   cudaFuncSetAttribute(k_density<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)density_smem(c, 16));
-  cudaFuncSetAttribute(k_force, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)force_smem(c, 16));
+  cudaFuncSetAttribute(k_force<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)force_smem(c, 16));
+  cudaFuncSetAttribute(k_force<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)force_smem(c, 16));
   cudaFuncSetAttribute(k_gravity, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gravity_smem(c, GW_WARPS));
   cudaFuncSetAttribute(k_neighbours, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   if (cudaGetLastError() != cudaSuccess) { c->err = "cudaFuncSetAttribute failed (was the library built for this GPU's architecture?)"; return fail(SPH_ERR_CUDA); }
@@ -835,7 +868,7 @@ int sph_destroy(sph_ctx* c) {
   for (int b = 0; b < 2; ++b) { for (int f = 0; f < 10; ++f) F(c->st[b][f]); F(c->id[b]); F(c->key[b]); F(c->key_lo[b]); F(c->perm[b]); F(c->acc_key[b]); F(c->acc_val[b]); }
   F(c->rho); F(c->omega); F(c->prs); F(c->cs); F(c->por2); F(c->ax); F(c->ay); F(c->az); F(c->udot); F(c->adot);
   F(c->node_count); F(c->gsize); F(c->gfirst); F(c->groups); F(c->level); F(c->lcx); F(c->lcy); F(c->lcz); F(c->reach); F(c->bvh); F(c->nodes); F(c->node_part); F(c->parent); F(c->nchild);
-  F(c->ggroups); F(c->gbvh); F(c->wnodes); F(c->wcount); F(c->wstart); F(c->widx); F(c->grav_spill);
+  F(c->nl_pool); F(c->nl_head); F(c->nl_ctl); F(c->ggroups); F(c->gbvh); F(c->wnodes); F(c->wcount); F(c->wstart); F(c->widx); F(c->grav_spill);
   F(c->arrive); F(c->cnt); F(c->off); F(c->root); F(c->partial); F(c->cub_tmp); F(c->d_wt); F(c->d_dwt); F(c->d_gt);
   F(c->sink_buf); F(c->sink_partial); F(c->sc); F(c->ctr); F(c->work); F(c->keep); F(c->d_nsel); F(c->pos); F(c->stage_d); F(c->stage_d2);
   if (c->h_sc) cudaFreeHost(c->h_sc);

@@ -29,7 +29,7 @@ struct BvhInfo { int nlev; int off[12]; int cnt[12]; };
 #define FORCE_COMPACT 1
 #endif
 #define PAIR_WIN   64       // compacted (target, source) hits evaluated per window, lane = pair
-#define DENS_WARP_DOUBLES (8 * WALK_TILE + 4 * 32 + 2 * PAIR_WIN + PAIR_WIN / 4)   // tile + targets + results + hit list
+#define DENS_WARP_DOUBLES (8 * WALK_TILE + 4 * 32 + 2 * PAIR_WIN + PAIR_WIN / 4 + 32)   // tile + targets + results + hit list + saved-list buffer (64 ints)
 
 #ifdef WALK_DEBUG
 __device__ unsigned long long wk_dbg[16];
@@ -46,7 +46,9 @@ __device__ __forceinline__ bool box_overlap(const float* alo, const float* ahi, 
 
 // Generic warp walk. OP interface:
 //   static const bool SYMMETRIC;                     // also accept sources lying inside the group's reach box
-//   bool   source_filter(int j)                      // per-source prefilter against the group (lane = source)
+//   static const bool LISTS;                         // the op also saves a candidate list for a later pass (list_append)
+//   int    source_filter(int j)                      // per-source prefilter against the group (lane = source):
+//                                                    // bit 0 = stage into the tile, bit 1 = append to the saved list
 //   void   stage(int slot, int j)                    // copy source j into tile slot
 //   void   consume(int count)                        // all lanes process tile[0..count)
 template <class OP>
@@ -90,7 +92,9 @@ __device__ void neighbour_walk(OP& op, const int2* __restrict__ groups, int chun
         const int sgx = __shfl_sync(FULL_MASK, mysg.x, qpos & 31), sgy = __shfl_sync(FULL_MASK, mysg.y, qpos & 31);
         ++qpos;
         const int j = sgx + lane;
-        const bool ok = (lane < sgy) && op.source_filter(j);
+        const int fl = (lane < sgy) ? op.source_filter(j) : 0;
+        if constexpr (OP::LISTS) op.list_append((fl & 2) != 0, j);
+        const bool ok = (fl & 1) != 0;
         const unsigned bal = __ballot_sync(FULL_MASK, ok);
         const int cntc = __popc(bal);
         if (cntc == 0) continue;
@@ -135,6 +139,16 @@ __device__ void neighbour_walk(OP& op, const int2* __restrict__ groups, int chun
   }
 }
 
+// Saved candidate lists.  The density pass walks the BVH with the symmetric (pair-loop) criterion and writes,
+// per walk group, the indices of every source the pair loop will need into a chain of 32-int blocks taken from
+// a global pool: ints [0, NL_PER_BLOCK) = sorted particle indices, [30] = how many, [31] = next block (-1: end).
+// The pair loop of the same evaluation then streams its group's chain instead of walking and filtering again.
+// ctl[0] = block cursor, ctl[2] = pool overflowed (the host grows it), ctl[1] = "lists unusable" (pool overflow, or a non-finite P/(Omega rho^2) + c somewhere:
+// the reference lets such a particle poison every box partner through 0 * NaN, which the distance cull applied
+// to the list would hide) -> the walking pair kernel runs instead.
+#define NL_PER_BLOCK 30
+struct NeighbourListSink { int* pool; int* head; int* ctl; int pool_blocks; };
+
 // shared kernel-table lookup: returns table-space (w, dw) at q (<= 2 assumed), F:113-118
 __device__ __forceinline__ void table_lerp(const double* __restrict__ wt, const double* __restrict__ dwt,
                                            int nq, double dq, double inv_dq, double q, double& w, double& dw) {
@@ -157,8 +171,12 @@ struct DensityArrays {
   const double *x, *y, *z, *m, *lcx, *lcy, *lcz, *reach;
 };
 
+template <bool PRODUCE>
 struct DensityOp {
-  static const bool SYMMETRIC = false;
+  static const bool SYMMETRIC = PRODUCE;
+  static const bool LISTS = PRODUCE;
+  // saved-list state (PRODUCE): lbuf = 64 ints of shared memory per warp
+  NeighbourListSink nl; int* lbuf; int ln, cur_blk; float grlo[3], grhi[3]; const double* hsrc; int variable_h; double h_fixed;
   // tile (per warp, shared memory): 8 arrays of WALK_TILE doubles
   double *sx, *sy, *sz, *sm, *scx, *scy, *scz, *sR;
   double *tgx, *tgy, *tgz, *tgih;    // the group's targets (per warp, shared memory): x y z 1/h
@@ -179,17 +197,76 @@ struct DensityOp {
 
   __device__ DensityOp(const DensityArrays& a) : A(a) {}
 
-  __device__ __forceinline__ bool source_filter(int j) const {
+  __device__ __forceinline__ int source_filter(int j) const {
     // all loads first (independent, one latency), then a branch-free decision
     const double R = A.reach[j], cx = A.lcx[j], cy = A.lcy[j], cz = A.lcz[j], px = A.x[j], py = A.y[j], pz = A.z[j];
+    double hj = h_fixed;
+    if (PRODUCE && variable_h) hj = hsrc[j];
     const bool box = (R > 0.0) & (cx - R <= (double)gphi[0]) & (cx + R >= (double)gplo[0]) &
                      (cy - R <= (double)gphi[1]) & (cy + R >= (double)gplo[1]) &
                      (cz - R <= (double)gphi[2]) & (cz + R >= (double)gplo[2]);
     // farther than 2 h_i from every target of the group: W = 0 exactly for all of them
     const double ex = fmax(fmax((double)gplo[0] - px, px - (double)gphi[0]), 0.0), ey = fmax(fmax((double)gplo[1] - py, py - (double)gphi[1]), 0.0),
                  ez = fmax(fmax((double)gplo[2] - pz, pz - (double)gphi[2]), 0.0);
-    return box & (!(ex * ex + ey * ey + ez * ez > g_r2max) | count_all);
+    const double e2 = ex * ex + ey * ey + ez * ez;
+    int fl = (box & (!(e2 > g_r2max) | count_all)) ? 1 : 0;
+    if (PRODUCE) {
+      // the pair loop's criterion (ForceOp::source_filter): j's box reaches a target, or j sits inside a target's box,
+      // and j is not farther than 2 max(h_i, h_j) from every target
+      const bool b = (px >= (double)grlo[0]) & (px <= (double)grhi[0]) & (py >= (double)grlo[1]) & (py <= (double)grhi[1]) &
+                     (pz >= (double)grlo[2]) & (pz <= (double)grhi[2]);
+      const bool nz = !(e2 > fmax(g_r2max, 4.0 * hj * hj * (1.0 + 1e-9)));
+      fl |= ((box | b) & (nz | count_all)) ? 2 : 0;
+    }
+    return fl;
   }
+  // ---- saved list: append the flagged sources of one chunk (lane = source), flushing full blocks to the pool
+  __device__ __forceinline__ void list_flush(int cnt, bool last) {
+    const int lane = threadIdx.x & 31;
+    int nxt = -1;
+    if (!last) {
+      if (lane == 0) {
+        nxt = atomicAdd(&nl.ctl[0], 1);
+        if (nxt >= nl.pool_blocks) { nl.ctl[1] = 1; nl.ctl[2] = 1; nxt = -2; }  // pool exhausted: the lists of this evaluation are void
+      }
+      nxt = __shfl_sync(FULL_MASK, nxt, 0);
+    }
+    if (cur_blk >= 0) {
+      const int v = lane < cnt ? lbuf[lane] : (lane == 30 ? cnt : (lane == 31 ? (nxt < 0 ? -1 : nxt) : 0));
+      nl.pool[(size_t)cur_blk * 32 + lane] = v;
+    }
+    cur_blk = nxt;
+  }
+  __device__ __forceinline__ void list_begin(int chunk) {
+    const int lane = threadIdx.x & 31;
+    int b = 0;
+    if (lane == 0) {
+      b = atomicAdd(&nl.ctl[0], 1);
+      if (b >= nl.pool_blocks) { nl.ctl[1] = 1; nl.ctl[2] = 1; b = -2; }
+      nl.head[chunk] = b;
+    }
+    cur_blk = __shfl_sync(FULL_MASK, b, 0); ln = 0;
+  }
+  __device__ __forceinline__ void list_append(bool want, int j) {
+    const int lane = threadIdx.x & 31;
+    const unsigned bal = __ballot_sync(FULL_MASK, want);
+    const int cnt = __popc(bal);
+    if (cnt == 0) return;
+    const int pos = ln + __popc(bal & ((1u << lane) - 1u));
+    if (want) lbuf[pos] = j;                                                     // ln <= 29, cnt <= 32: fits the 64-int buffer
+    ln += cnt;
+    while (ln >= NL_PER_BLOCK) {
+      __syncwarp();
+      list_flush(NL_PER_BLOCK, false);
+      __syncwarp();
+      const int rest = ln - NL_PER_BLOCK;
+      const int v = lane < rest ? lbuf[NL_PER_BLOCK + lane] : 0;
+      __syncwarp();
+      if (lane < rest) lbuf[lane] = v;
+      ln = rest;
+    }
+  }
+  __device__ __forceinline__ void list_end() { __syncwarp(); list_flush(ln, true); __syncwarp(); }
   __device__ __forceinline__ void stage(int s, int j) {
     sx[s] = A.x[j]; sy[s] = A.y[j]; sz[s] = A.z[j]; sm[s] = A.m[j];
     scx[s] = A.lcx[j]; scy[s] = A.lcy[j]; scz[s] = A.lcz[j]; sR[s] = A.reach[j];
@@ -282,7 +359,7 @@ k_density(int n_groups, const int2* __restrict__ groups, DevParams P, DensityArr
           const double* __restrict__ g_wt, const double* __restrict__ g_dwt,
           const double* __restrict__ u, double* __restrict__ h,
           double* __restrict__ rho, double* __restrict__ omega, double* __restrict__ prs, double* __restrict__ cs,
-          double* __restrict__ por2, WalkCounters* ctr, int* work, int count_all) {
+          double* __restrict__ por2, WalkCounters* ctr, int* work, int count_all, NeighbourListSink nl) {
   extern __shared__ double smem[];
   const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double* wt = smem; double* dwt = smem + (P.nq + 1);
@@ -304,14 +381,16 @@ k_density(int n_groups, const int2* __restrict__ groups, DevParams P, DensityArr
     const int2 tg = groups[chunk];
     const int i = tg.x + lane;
     const bool live = lane < tg.y;
-    DensityOp op(A);
+    DensityOp<!HITER> op(A);
     op.sx = tile; op.sy = tile + WALK_TILE; op.sz = tile + 2 * WALK_TILE; op.sm = tile + 3 * WALK_TILE;
     op.scx = tile + 4 * WALK_TILE; op.scy = tile + 5 * WALK_TILE; op.scz = tile + 6 * WALK_TILE; op.sR = tile + 7 * WALK_TILE;
     op.tgx = tile + 8 * WALK_TILE; op.tgy = op.tgx + 32; op.tgz = op.tgx + 64; op.tgih = op.tgx + 96;
     op.resW = op.tgx + 128; op.resB = op.resW + PAIR_WIN; op.plist = reinterpret_cast<unsigned short*>(op.resB + PAIR_WIN);
+    op.lbuf = reinterpret_cast<int*>(op.resB + PAIR_WIN + PAIR_WIN / 4);
+    op.nl = nl; op.hsrc = h; op.variable_h = P.variable_h; op.h_fixed = P.h_fixed;
     op.wt = wt; op.dwt = dwt; op.nq = P.nq; op.dq = P.dq; op.inv_dq = P.inv_dq;
     const BvhBox g = box[bi.off[0] + chunk];
-    for (int k = 0; k < 3; ++k) { op.gplo[k] = g.plo[k]; op.gphi[k] = g.phi[k]; }
+    for (int k = 0; k < 3; ++k) { op.gplo[k] = g.plo[k]; op.gphi[k] = g.phi[k]; op.grlo[k] = g.rlo[k]; op.grhi[k] = g.rhi[k]; }
     op.xi = live ? A.x[i] : 0.0; op.yi = live ? A.y[i] : 0.0; op.zi = live ? A.z[i] : 0.0;
     op.cand = 0; op.contrib = 0; op.count_all = count_all != 0;
     double hi = live ? (P.variable_h ? h[i] : P.h_fixed) : 1.0;
@@ -322,7 +401,9 @@ k_density(int n_groups, const int2* __restrict__ groups, DevParams P, DensityArr
       op.g_r2max = warp_max(live ? op.r2max : 0.0);
       op.tgx[lane] = op.xi; op.tgy[lane] = op.yi; op.tgz[lane] = op.zi; op.tgih[lane] = op.inv_h;
       __syncwarp();
+      op.list_begin(chunk);
       neighbour_walk(op, groups, chunk, box, bi, stack, cq);
+      op.list_end();
       if (live) {
         // W/(pi h^3), dW/(pi h^4): F:125-126 (global smoothing) | V:139-140
         const double hn = P.variable_h ? hi : P.h_fixed;
@@ -337,7 +418,9 @@ k_density(int n_groups, const int2* __restrict__ groups, DevParams P, DensityArr
         const double p = P.gm1 * u[i] * r;                               // F:465 | V:509
         const double c = sqrt(P.gamma * p / r);                          // F:466 | V:510
         rho[i] = r; omega[i] = om; prs[i] = p; cs[i] = c;
-        por2[i] = P.variable_h ? p / ((om * r) * r) : p / (r * r);       // V:413 | F:381
+        const double po = P.variable_h ? p / ((om * r) * r) : p / (r * r);     // V:413 | F:381
+        por2[i] = po;
+        if (!(fabs(po + c) < INFINITY)) nl.ctl[1] = 1;                        // the pair loop must see every box partner of this particle
       }
       tot_cand += op.cand; tot_contrib += op.contrib;
     } else {
@@ -395,6 +478,7 @@ struct ForceArrays {
 
 struct ForceOp {
   static const bool SYMMETRIC = true;
+  static const bool LISTS = false;
   double* t;             // tile: FORCE_FIELDS arrays of WALK_TILE doubles
   int* tid;              // tile ids
   double* tg;            // the group's targets: FORCE_TG_FIELDS arrays of 32 doubles (x y z vx vy vz h 1/h 1/(pi h^4) rho c alpha P/(Omega rho^2))
@@ -561,10 +645,16 @@ struct ForceOp {
   }
 };
 
+// LISTED: stream the group's saved candidate chain (written by the density pass of this evaluation) instead of
+// walking the BVH and filtering the sources again; runs only while the lists are usable (nl.ctl[1] == 0).
+// !LISTED: the walking form; with only_if_void it runs only when the lists were declared void on the device.
+template <bool LISTED>
 __global__ void __launch_bounds__(512, 1)
 k_force(int n_groups, const int2* __restrict__ groups, DevParams P, ForceArrays A, const BvhBox* __restrict__ box, const __grid_constant__ BvhInfo bi, const double* __restrict__ g_dwt,
         double* __restrict__ ax, double* __restrict__ ay, double* __restrict__ az, double* __restrict__ udot,
-        double* __restrict__ adot, WalkCounters* ctr, int* work, int count_all) {
+        double* __restrict__ adot, WalkCounters* ctr, int* work, int count_all, NeighbourListSink nl, int only_if_void) {
+  if (LISTED) { if (nl.ctl[1] != 0) return; }
+  else if (only_if_void && nl.ctl[1] == 0) return;
   extern __shared__ double smem[];
   const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double* dwt = smem;
@@ -609,7 +699,26 @@ k_force(int n_groups, const int2* __restrict__ groups, DevParams P, ForceArrays 
     op.g_r2max = warp_max(live ? op.r2max : 0.0); op.count_all = count_all != 0;
     op.ax = op.ay = op.az = op.ud = op.ad = 0.0; op.pairs = 0;
     __syncwarp();
-    neighbour_walk(op, groups, chunk, box, bi, stack, cq);
+    if (LISTED) {
+      // one block = one tile; the next block's words are requested before the current tile is consumed
+      int blk = nl.head[chunk];
+      int v = nl.pool[(size_t)blk * 32 + lane];
+      for (;;) {
+        const int cnt = __shfl_sync(FULL_MASK, v, 30), nxt = __shfl_sync(FULL_MASK, v, 31);
+        int vn = 0;
+        if (nxt >= 0) vn = nl.pool[(size_t)nxt * 32 + lane];
+        if (cnt > 0) {
+          if (lane < cnt) op.stage(lane, v);
+          __syncwarp();
+          op.consume(cnt);
+          __syncwarp();
+        }
+        if (nxt < 0) break;
+        v = vn;
+      }
+    } else {
+      neighbour_walk(op, groups, chunk, box, bi, stack, cq);
+    }
     if (live) {
       ax[i] += op.ax; ay[i] += op.ay; az[i] += op.az;
       udot[i] += op.ud;
@@ -627,6 +736,7 @@ k_force(int n_groups, const int2* __restrict__ groups, DevParams P, ForceArrays 
 // ------------------------------------------------------------------------------------------------------
 struct NgbOp {
   static const bool SYMMETRIC = false;
+  static const bool LISTS = false;
   double *scx, *scy, *scz, *sR; int* sid;
   const DensityArrays& A; const int* id;
   float gplo[3], gphi[3];
