@@ -49,7 +49,7 @@ enum { NC_UINT64 = 5, NC_FLOAT64 = 8, NC_SUM = 0, NC_MIN = 3 };
 }  // namespace
 
 struct sph_ctx {
-  sph_params p; DevParams dp; int device = 0; int n_sm = 148; cudaStream_t stream = nullptr;
+  sph_params p; DevParams dp; int device = 0; int n_sm = 148; int max_smem = 0; cudaStream_t stream = nullptr;
   std::string err;
   int64_t n = 0, cap = 0, n_upload = 0; int n_sink = 0;
   // particle state, double buffered for the Morton re-order / compaction
@@ -493,9 +493,15 @@ int build_tree_impl(sph_ctx* c, bool* retry_two_word) {
 
 
 size_t density_smem(const sph_ctx* c, int nwarp) { return (size_t)2 * (c->p.nq + 1) * 8 + (size_t)nwarp * DENS_WARP_DOUBLES * 8 + (size_t)nwarp * WALK_WS * 4; }
-size_t force_smem(const sph_ctx* c, int nwarp) {
+size_t force_smem(const sph_ctx* c, int nwarp, bool listed) {
   size_t t = (size_t)((c->p.nq + 1) + ((c->p.nq + 1) & 1)) * 8;
-  return t + (size_t)nwarp * FORCE_WARP_DOUBLES * 8 + (size_t)nwarp * WALK_TILE * 4 + (size_t)nwarp * WALK_WS * 4;
+  return t + (size_t)nwarp * FORCE_WARP_DOUBLES * 8 + (size_t)nwarp * WALK_TILE * 4 + (listed ? 0 : (size_t)nwarp * WALK_WS * 4);
+}
+// warps per block of the pair kernels: as many (<= 16) as the shared memory left beside the kernel table allows
+int force_warps(const sph_ctx* c, bool listed) {
+  int w = 16;
+  while (w > 1 && force_smem(c, w, listed) > (size_t)c->max_smem) --w;
+  return w;
 }
 int walk_grid(const sph_ctx* c, int nwarp) {
   const int nchunk = c->g1 - c->g0;
@@ -549,12 +555,13 @@ int run_force(sph_ctx* c) {
   ForceArrays A{s.x, s.y, s.z, s.vx, s.vy, s.vz, s.m, s.h, c->rho, c->cs, s.alpha, c->por2, c->lcx, c->lcy, c->lcz, c->reach, s.id};
   const NeighbourListSink nl{c->nl_pool, c->nl_head, c->nl_ctl, (int)std::min<size_t>(c->nl_pool_blocks, 0x7fffffff)};
   const bool listed = c->nl_valid && c->nl_exact == c->exact_counters && c->use_lists;
+  const int WL = force_warps(c, true), WW = force_warps(c, false);
   if (listed) {
     LAUNCH(k_set_int, 1, 1, 0, c->work, c->g0);
-    LAUNCH(k_force<true>, walk_grid(c, W), W * 32, force_smem(c, W), c->g1, c->groups, c->dp, A, c->bvh, c->bi, c->d_dwt, c->ax, c->ay, c->az, c->udot, c->adot, c->ctr, c->work, c->exact_counters, nl, 0);
+    LAUNCH(k_force<true>, walk_grid(c, WL), WL * 32, force_smem(c, WL, true), c->g1, c->groups, c->dp, A, c->bvh, c->bi, c->d_dwt, c->ax, c->ay, c->az, c->udot, c->adot, c->ctr, c->work, c->exact_counters, nl, 0);
   }
   LAUNCH(k_set_int, 1, 1, 0, c->work, c->g0);
-  LAUNCH(k_force<false>, walk_grid(c, W), W * 32, force_smem(c, W), c->g1, c->groups, c->dp, A, c->bvh, c->bi, c->d_dwt, c->ax, c->ay, c->az, c->udot, c->adot, c->ctr, c->work, c->exact_counters, nl, listed ? 1 : 0);
+  LAUNCH(k_force<false>, walk_grid(c, WW), WW * 32, force_smem(c, WW, false), c->g1, c->groups, c->dp, A, c->bvh, c->bi, c->d_dwt, c->ax, c->ay, c->az, c->udot, c->adot, c->ctr, c->work, c->exact_counters, nl, listed ? 1 : 0);
   stage_end(c);
 #ifdef WALK_DEBUG
   { unsigned long long d[16]; cudaStreamSynchronize(c->stream); cudaMemcpyFromSymbol(d, wk_dbg, sizeof(d)); unsigned long long z[16] = {}; cudaMemcpyToSymbol(wk_dbg, z, sizeof(z));
@@ -841,13 +848,14 @@ int sph_create(const sph_params* p, int32_t device, sph_ctx** out) {
   cudaMemset(c->ctr, 0, sizeof(WalkCounters));
   // opt in to large dynamic shared memory
   int maxsm = 0; cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  c->max_smem = maxsm;
   cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, device);
-  size_t need = std::max(std::max(density_smem(c, 16), force_smem(c, 16)), gravity_smem(c, GW_WARPS));
+  size_t need = std::max(std::max(density_smem(c, 16), std::max(force_smem(c, force_warps(c, true), true), force_smem(c, force_warps(c, false), false))), gravity_smem(c, GW_WARPS));
   if ((size_t)maxsm < need) { c->err = "device shared memory too small for the walk kernels"; return fail(SPH_ERR_CUDA); }
   cudaFuncSetAttribute(k_density<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)density_smem(c, 16));
   cudaFuncSetAttribute(k_density<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)density_smem(c, 16));
-  cudaFuncSetAttribute(k_force<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)force_smem(c, 16));
-  cudaFuncSetAttribute(k_force<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)force_smem(c, 16));
+  cudaFuncSetAttribute(k_force<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)force_smem(c, force_warps(c, true), true));
+  cudaFuncSetAttribute(k_force<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)force_smem(c, force_warps(c, false), false));
   cudaFuncSetAttribute(k_gravity, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gravity_smem(c, GW_WARPS));
   cudaFuncSetAttribute(k_neighbours, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   if (cudaGetLastError() != cudaSuccess) { c->err = "cudaFuncSetAttribute failed (was the library built for this GPU's architecture?)"; return fail(SPH_ERR_CUDA); }

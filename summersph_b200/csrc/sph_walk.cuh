@@ -25,9 +25,6 @@ struct BvhInfo { int nlev; int off[12]; int cnt[12]; };
 #ifndef DENS_COMPACT
 #define DENS_COMPACT 0
 #endif
-#ifndef FORCE_COMPACT
-#define FORCE_COMPACT 1
-#endif
 #define PAIR_WIN   64       // compacted (target, source) hits evaluated per window, lane = pair
 #define DENS_WARP_DOUBLES (8 * WALK_TILE + 4 * 32 + 2 * PAIR_WIN + PAIR_WIN / 4 + 32)   // tile + targets + results + hit list + saved-list buffer (64 ints)
 
@@ -473,15 +470,19 @@ struct ForceArrays {
   const int* id;
 };
 #define FORCE_FIELDS 19
-#define FORCE_TG_FIELDS 13
-#define FORCE_WARP_DOUBLES (FORCE_FIELDS * WALK_TILE + FORCE_TG_FIELDS * 32 + 3 * PAIR_WIN + PAIR_WIN / 4)   // tile + targets + results + hit list
+#define FORCE_TG_FIELDS 19
+#define FORCE_WARP_DOUBLES (FORCE_FIELDS * WALK_TILE + FORCE_TG_FIELDS * 32 + 3 * PAIR_WIN + PAIR_WIN / 4 + 2 * WALK_TILE)   // tile + targets + results + hit list + float4 tile
 
 struct ForceOp {
   static const bool SYMMETRIC = true;
   static const bool LISTS = false;
   double* t;             // tile: FORCE_FIELDS arrays of WALK_TILE doubles
   int* tid;              // tile ids
-  double* tg;            // the group's targets: FORCE_TG_FIELDS arrays of 32 doubles (x y z vx vy vz h 1/h 1/(pi h^4) rho c alpha P/(Omega rho^2))
+  double* tg;            // the group's targets: FORCE_TG_FIELDS arrays of 32 doubles (x y z vx vy vz h 1/h 1/(pi h^4) rho c alpha P/(Omega rho^2)
+                         //   leaf centre (3) reach r2max id)
+  float4* ft;            // float copy of the tile for the prefilter: position relative to the group's origin, r2max rounded up
+  double g0x, g0y, g0z;  // the group's origin (centre of its position box)
+  float xif, yif, zif, r2maxif;
   double* res;           // pair results of the current window: f, u, a
   unsigned short* plist; // compacted hit list of the current window: (target lane << 5) | tile slot
   const ForceArrays& A;
@@ -490,10 +491,8 @@ struct ForceOp {
   int variable_h; double h_fixed, pi_norm, lit_001;
   // lane state
   bool live;
-  double xi, yi, zi, cxi, cyi, czi, Ri;
+  double xi, yi, zi;
   double g_r2max; bool count_all;   // group maximum of r2max; exact pair counter wanted (no early cull)
-  double r2max;          // 4 h_i^2 (1 + 1e-9); a pair beyond max(r2max_i, r2max_j) has dW(h_i) = dW(h_j) = 0: every term is an exact zero
-  int idi;
   double ax, ay, az, ud, ad;
   unsigned pairs;
 
@@ -529,33 +528,29 @@ struct ForceOp {
     t[13 * WALK_TILE + s] = A.lcx[j]; t[14 * WALK_TILE + s] = A.lcy[j]; t[15 * WALK_TILE + s] = A.lcz[j];
     t[16 * WALK_TILE + s] = A.reach[j];
     tid[s] = A.id[j];
+    ft[s] = make_float4((float)(t[0 * WALK_TILE + s] - g0x), (float)(t[1 * WALK_TILE + s] - g0y), (float)(t[2 * WALK_TILE + s] - g0z),
+                        __double2float_ru(t[18 * WALK_TILE + s]));
   }
   __device__ __forceinline__ void consume(int count) {
-    unsigned mask = 0, pmask = 0;
+    // Prefilter, lane = target, FP32: |x_i - x_j|^2 against max(r2max_i, r2max_j) with a 1e-4 margin that covers the
+    // float rounding of the group-relative coordinates (|coordinate| is a few h: error ~1e-6 of the limit).  It only
+    // ever drops pairs whose every term is an exact zero; the reference's own membership test (FP64, F:351-354 |
+    // V:380-383) and the exact distance cull run in the lane = pair phase on the survivors.  With the exact pair
+    // counter on, every staged source is a candidate.
+    unsigned mask = 0;
     if (live) {
+      if (count_all) mask = count >= 32 ? 0xffffffffu : ((1u << count) - 1u);
+      else {
 #pragma unroll 4
-      for (int k = 0; k < count; ++k) {
-        // idj < idi: i is the higher-numbered `body`: is x_i inside Box(j)?   F:351-354 | V:380-383
-        // idj > idi: j is the `body` that visits i: is x_j inside Box(i)?   (Box(i) is empty when R_i = -1)
-        const int idj = tid[k];
-        const bool lt = idj < idi;
-        const double xj = t[0 * WALK_TILE + k], yj = t[1 * WALK_TILE + k], zj = t[2 * WALK_TILE + k];
-        const double px = lt ? xi : xj, py = lt ? yi : yj, pz = lt ? zi : zj;
-        const double cx = lt ? t[13 * WALK_TILE + k] : cxi, cy = lt ? t[14 * WALK_TILE + k] : cyi, cz = lt ? t[15 * WALK_TILE + k] : czi;
-        const double R = lt ? t[16 * WALK_TILE + k] : Ri;
-        const bool in = (idj != idi) & (fabs(px - cx) < R) & (fabs(py - cy) < R) & (fabs(pz - cz) < R);
-        const double dx = xi - xj, dy = yi - yj, dz = zi - zj;
-        const bool nz = !(dx * dx + dy * dy + dz * dz > fmax(r2max, t[18 * WALK_TILE + k]));
-        pmask |= (in ? 1u : 0u) << k;
-        mask |= ((in & nz) ? 1u : 0u) << k;
+        for (int k = 0; k < count; ++k) {
+          const float4 sj = ft[k];
+          const float dx = xif - sj.x, dy = yif - sj.y, dz = zif - sj.z;
+          const float r2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+          const bool far = r2 > fmaxf(r2maxif, sj.w) * 1.0001f;
+          mask |= (far ? 0u : 1u) << k;
+        }
       }
     }
-    pairs += __popc(pmask);
-#ifdef WALK_DEBUG
-    { int hc = __popc(mask); int mx = hc, sm = hc; for (int o = 16; o > 0; o >>= 1) { mx = max(mx, __shfl_xor_sync(FULL_MASK, mx, o)); sm += __shfl_xor_sync(FULL_MASK, sm, o); }
-      WKD(0, 1); WKD(1, count); WKD(2, mx); WKD(3, sm); int pc = __popc(pmask); for (int o = 16; o > 0; o >>= 1) pc += __shfl_xor_sync(FULL_MASK, pc, o); WKD(4, pc); }
-#endif
-#if FORCE_COMPACT
     // Compact the hits (target lane, tile slot) of the whole warp and evaluate them with lane = pair: the
     // ~95 FP64 instructions of a pair run with every lane busy however unevenly a tile's sources fall among
     // the targets.  Each target then adds its own terms in tile order (F:383-391, own side; deterministic).
@@ -573,9 +568,23 @@ struct ForceOp {
       __syncwarp();
       const int nwin = total - base < PAIR_WIN ? total - base : PAIR_WIN;
       for (int p = lane; p < nwin; p += 32) {
-        const int e = plist[p];
-        double f, u, a;
-        pair(e >> 5, e & 31, f, u, a);
+        const int e = plist[p], tl = e >> 5, k = e & 31;
+        // idj < idi: i is the higher-numbered `body`: is x_i inside Box(j)?   F:351-354 | V:380-383
+        // idj > idi: j is the `body` that visits i: is x_j inside Box(i)?   (Box(i) is empty when R_i = -1)
+        const double* g = tg + tl;
+        const int idj = tid[k], idi_ = (int)g[18 * 32];
+        const bool lt = idj < idi_;
+        const double xi_ = g[0 * 32], yi_ = g[1 * 32], zi_ = g[2 * 32];
+        const double xj = t[0 * WALK_TILE + k], yj = t[1 * WALK_TILE + k], zj = t[2 * WALK_TILE + k];
+        const double px = lt ? xi_ : xj, py = lt ? yi_ : yj, pz = lt ? zi_ : zj;
+        const double cx = lt ? t[13 * WALK_TILE + k] : g[13 * 32], cy = lt ? t[14 * WALK_TILE + k] : g[14 * 32], cz = lt ? t[15 * WALK_TILE + k] : g[15 * 32];
+        const double R = lt ? t[16 * WALK_TILE + k] : g[16 * 32];
+        const bool in = (idj != idi_) & (fabs(px - cx) < R) & (fabs(py - cy) < R) & (fabs(pz - cz) < R);
+        const double dx = xi_ - xj, dy = yi_ - yj, dz = zi_ - zj;
+        const bool nz = !(dx * dx + dy * dy + dz * dz > fmax(g[17 * 32], t[18 * WALK_TILE + k]));
+        pairs += in ? 1u : 0u;
+        double f = 0.0, u = 0.0, a = 0.0;
+        if (in & nz) pair(tl, k, f, u, a);
         res[p] = f; res[PAIR_WIN + p] = u; res[2 * PAIR_WIN + p] = a;
       }
       __syncwarp();
@@ -591,17 +600,6 @@ struct ForceOp {
       }
       __syncwarp();
     }
-#else
-    while (mask) {
-      const int k = __ffs(mask) - 1; mask &= mask - 1;
-      double f, u, a;
-      pair(threadIdx.x & 31, k, f, u, a);
-      ax -= f * (xi - t[0 * WALK_TILE + k]);
-      ay -= f * (yi - t[1 * WALK_TILE + k]);
-      az -= f * (zi - t[2 * WALK_TILE + k]);
-      ud += u; ad += a;
-    }
-#endif
   }
   // one pair (target lane tl, tile slot k): f = m_j * A / dr  (a_i -= f * (x_i - x_j)), u = du/dt term, a = alpha-rate term
   __device__ __forceinline__ void pair(int tl, int k, double& f, double& u, double& a) const {
@@ -660,7 +658,7 @@ k_force(int n_groups, const int2* __restrict__ groups, DevParams P, ForceArrays 
   double* dwt = smem;
   double* tiles = dwt + (P.nq + 1) + ((P.nq + 1) & 1);
   int* tids = reinterpret_cast<int*>(tiles + (size_t)nwarp * FORCE_WARP_DOUBLES);
-  unsigned* ws = reinterpret_cast<unsigned*>(tids + (size_t)nwarp * WALK_TILE);
+  unsigned* ws = reinterpret_cast<unsigned*>(tids + (size_t)nwarp * WALK_TILE);     // only the walking form uses (and sizes) it
   for (int i = threadIdx.x; i <= P.nq; i += blockDim.x) dwt[i] = g_dwt[i];
   __syncthreads();
   double* tile = tiles + (size_t)warp * FORCE_WARP_DOUBLES;
@@ -680,6 +678,7 @@ k_force(int n_groups, const int2* __restrict__ groups, DevParams P, ForceArrays 
     op.t = tile; op.tid = tids + warp * WALK_TILE;
     op.tg = tile + FORCE_FIELDS * WALK_TILE; op.res = op.tg + FORCE_TG_FIELDS * 32;
     op.plist = reinterpret_cast<unsigned short*>(op.res + 3 * PAIR_WIN);
+    op.ft = reinterpret_cast<float4*>(op.res + 3 * PAIR_WIN + PAIR_WIN / 4);
     op.dwt = dwt; op.nq = P.nq; op.dq = P.dq; op.inv_dq = P.inv_dq;
     op.variable_h = P.variable_h; op.h_fixed = P.h_fixed; op.pi_norm = P.pi_norm; op.lit_001 = P.lit_001;
     const BvhBox g = box[bi.off[0] + chunk];
@@ -694,9 +693,14 @@ k_force(int n_groups, const int2* __restrict__ groups, DevParams P, ForceArrays 
       g[6 * 32] = hi; g[7 * 32] = 1.0 / hi; g[8 * 32] = 1.0 / (P.pi_norm * ((hi * hi) * (hi * hi)));
       g[9 * 32] = rhoi; g[10 * 32] = ci; g[11 * 32] = alphai; g[12 * 32] = por2i;
     }
-    op.cxi = A.lcx[ii]; op.cyi = A.lcy[ii]; op.czi = A.lcz[ii]; op.Ri = A.reach[ii]; op.idi = A.id[ii];
-    op.r2max = (fabs(por2i + ci) < INFINITY) ? 4.0 * hi * hi * (1.0 + 1e-9) : INFINITY;   // own NaN: keep every partner
-    op.g_r2max = warp_max(live ? op.r2max : 0.0); op.count_all = count_all != 0;
+    const double r2max = (fabs(por2i + ci) < INFINITY) ? 4.0 * hi * hi * (1.0 + 1e-9) : INFINITY;   // own NaN: keep every partner
+    {
+      double* g = op.tg + lane;
+      g[13 * 32] = A.lcx[ii]; g[14 * 32] = A.lcy[ii]; g[15 * 32] = A.lcz[ii]; g[16 * 32] = A.reach[ii]; g[17 * 32] = r2max; g[18 * 32] = (double)A.id[ii];
+    }
+    op.g0x = 0.5 * ((double)g.plo[0] + (double)g.phi[0]); op.g0y = 0.5 * ((double)g.plo[1] + (double)g.phi[1]); op.g0z = 0.5 * ((double)g.plo[2] + (double)g.phi[2]);
+    op.xif = (float)(op.xi - op.g0x); op.yif = (float)(op.yi - op.g0y); op.zif = (float)(op.zi - op.g0z); op.r2maxif = __double2float_ru(r2max);
+    op.g_r2max = warp_max(live ? r2max : 0.0); op.count_all = count_all != 0;
     op.ax = op.ay = op.az = op.ud = op.ad = 0.0; op.pairs = 0;
     __syncwarp();
     if (LISTED) {
