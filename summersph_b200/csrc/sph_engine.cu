@@ -63,7 +63,7 @@ struct sph_ctx {
   int *node_count = nullptr, *gsize = nullptr, *gfirst = nullptr; int2* groups = nullptr; int n_groups = 0;
   GNode* nodes = nullptr; int *node_part = nullptr, *parent = nullptr, *nchild = nullptr, *arrive = nullptr, *cnt = nullptr, *off = nullptr;
   int* nl_pool = nullptr; size_t nl_pool_blocks = 0; int* nl_head = nullptr; size_t nl_head_cap = 0; int* nl_ctl = nullptr; bool nl_valid = false;   // saved candidate lists (density pass -> pair loop)
-  int2* ggroups = nullptr; BvhBox* gbvh = nullptr; size_t ggroups_cap = 0;   // gravity walk groups (fixed runs of the rank's slice)
+  int2* ggroups = nullptr; BvhBox* gbvh = nullptr; size_t ggroups_cap = 0; int *seg_cnt = nullptr, *seg_off = nullptr; size_t seg_cap = 0; bool grav_groups_valid = false;   // gravity walk groups (fixed runs of the rank's slice)
   WNode* wnodes = nullptr; int *wcount = nullptr, *wstart = nullptr, *widx = nullptr; int2* grav_spill = nullptr;   // gravity walk layout
   RootBox* root = nullptr; double* partial = nullptr; int n_partial = 0;
   void* cub_tmp = nullptr; size_t cub_bytes = 0;
@@ -339,7 +339,8 @@ __global__ void k_set_int(int* p, int v) { *p = v; }
 int compute_slices(sph_ctx* c) {
   const int R = c->n_ranks, ng = c->n_groups, n = (int)c->n;
   c->rank_g.assign(R + 1, 0); c->rank_p.assign(R + 1, 0);
-  for (int r = 0; r <= R; ++r) c->rank_g[r] = (int)((int64_t)ng * r / R);
+  // slices are cut at multiples of GRAV_SEG groups (the gravity runs restart there: sph_gravity.cuh)
+  for (int r = 0; r <= R; ++r) c->rank_g[r] = r == R ? ng : (int)(((int64_t)ng * r / R) / GRAV_SEG * GRAV_SEG);
   c->rank_p[R] = n;
   if (R > 1) {
     for (int r = 1; r < R; ++r)
@@ -390,7 +391,7 @@ int build_tree(sph_ctx* c) {
 
 int build_tree_impl(sph_ctx* c, bool* retry_two_word) {
   const int n = (int)c->n;
-  c->nl_valid = false;
+  c->nl_valid = false; c->grav_groups_valid = false;
   const int T = 256;
   *retry_two_word = false;
   if (c->two_word && !c->key_lo[0]) { for (int b = 0; b < 2; ++b) DA(c->key_lo[b], c->cap); }
@@ -575,7 +576,9 @@ int run_gravity(sph_ctx* c, int do_grav, int do_sinks) {
   stage_begin(c, ST_GRAVITY);
   StateArrays s = state_of(c, c->cur);
 #if GRAV_CHUNK_WIDTH > 0
-  const int ng = cdiv(c->p1 - c->p0, GRAV_CHUNK_WIDTH);
+  // upper bound of the number of runs in this rank's slice; unused tail entries stay empty (first = 0, count = 0)
+  const int seg0 = c->g0 / GRAV_SEG, nseg = cdiv(c->g1 - c->g0, GRAV_SEG);
+  const int ng = cdiv(c->p1 - c->p0, GRAV_CHUNK_WIDTH) + nseg;
 #else
   const int ng = c->g1 - c->g0;
 #endif
@@ -584,12 +587,21 @@ int run_gravity(sph_ctx* c, int do_grav, int do_sinks) {
     c->sink_partial_cap = (size_t)(ng + 8) * std::max(ns, 1) * 3 * 2;
     DA(c->sink_partial, c->sink_partial_cap);
   }
-  if (ng > 0) {
+  if (ng > 0 && c->g1 > c->g0) {
     const int grid = std::max(1, std::min(cdiv(ng, GW_WARPS), c->n_sm));
     if (!c->grav_spill) DA(c->grav_spill, (size_t)c->n_sm * GW_WARPS * GW_SPILL);
 #if GRAV_CHUNK_WIDTH > 0
-    if ((size_t)ng > c->ggroups_cap) { c->ggroups_cap = (size_t)ng * 5 / 4 + 64; DA(c->ggroups, c->ggroups_cap); DA(c->gbvh, c->ggroups_cap); }
-    LAUNCH(k_grav_chunks, cdiv((int64_t)ng * 32, 256), 256, 0, c->p0, c->p1, GRAV_CHUNK_WIDTH, s.x, s.y, s.z, c->ggroups, c->gbvh);
+    if (!c->grav_groups_valid) {
+      if ((size_t)ng > c->ggroups_cap) { c->ggroups_cap = (size_t)ng * 5 / 4 + 64; DA(c->ggroups, c->ggroups_cap); DA(c->gbvh, c->ggroups_cap); }
+      if ((size_t)nseg + 1 > c->seg_cap) { c->seg_cap = (size_t)nseg * 5 / 4 + 64; DA(c->seg_cnt, c->seg_cap); DA(c->seg_off, c->seg_cap); }
+      CK(cudaMemsetAsync(c->ggroups, 0, sizeof(int2) * (size_t)ng, c->stream));
+      LAUNCH(k_seg_count, cdiv(nseg + 1, 256), 256, 0, seg0, nseg, c->n_groups, (int)c->n, GRAV_CHUNK_WIDTH, c->gfirst, c->seg_cnt);
+      size_t bytes = c->cub_bytes;
+      CK(cub::DeviceScan::ExclusiveSum(c->cub_tmp, bytes, c->seg_cnt, c->seg_off, nseg + 1, c->stream));
+      LAUNCH(k_seg_chunks, cdiv((int64_t)nseg * 32, 256), 256, 0, seg0, nseg, c->n_groups, (int)c->n, GRAV_CHUNK_WIDTH, c->gfirst, c->seg_off, c->ggroups);
+      LAUNCH(k_grav_boxes, cdiv((int64_t)ng * 32, 256), 256, 0, ng, c->ggroups, s.x, s.y, s.z, c->gbvh);
+      c->grav_groups_valid = true;
+    }
     LAUNCH(k_set_int, 1, 1, 0, c->work, 0);
     LAUNCH(k_gravity, grid, GW_WARPS * 32, gravity_smem(c, GW_WARPS), 0, ng, c->ggroups, c->gbvh, c->dp, c->wnodes, s.x, s.y, s.z, s.h, s.m, c->d_gt,
            c->ax, c->ay, c->az, do_grav, ns, c->S, c->sink_partial, c->ctr, c->work, c->grav_spill, &c->sc->err);
@@ -876,7 +888,7 @@ int sph_destroy(sph_ctx* c) {
   for (int b = 0; b < 2; ++b) { for (int f = 0; f < 10; ++f) F(c->st[b][f]); F(c->id[b]); F(c->key[b]); F(c->key_lo[b]); F(c->perm[b]); F(c->acc_key[b]); F(c->acc_val[b]); }
   F(c->rho); F(c->omega); F(c->prs); F(c->cs); F(c->por2); F(c->ax); F(c->ay); F(c->az); F(c->udot); F(c->adot);
   F(c->node_count); F(c->gsize); F(c->gfirst); F(c->groups); F(c->level); F(c->lcx); F(c->lcy); F(c->lcz); F(c->reach); F(c->bvh); F(c->nodes); F(c->node_part); F(c->parent); F(c->nchild);
-  F(c->nl_pool); F(c->nl_head); F(c->nl_ctl); F(c->ggroups); F(c->gbvh); F(c->wnodes); F(c->wcount); F(c->wstart); F(c->widx); F(c->grav_spill);
+  F(c->nl_pool); F(c->nl_head); F(c->nl_ctl); F(c->ggroups); F(c->gbvh); F(c->seg_cnt); F(c->seg_off); F(c->wnodes); F(c->wcount); F(c->wstart); F(c->widx); F(c->grav_spill);
   F(c->arrive); F(c->cnt); F(c->off); F(c->root); F(c->partial); F(c->cub_tmp); F(c->d_wt); F(c->d_dwt); F(c->d_gt);
   F(c->sink_buf); F(c->sink_partial); F(c->sc); F(c->ctr); F(c->work); F(c->keep); F(c->d_nsel); F(c->pos); F(c->stage_d); F(c->stage_d2);
   if (c->h_sc) cudaFreeHost(c->h_sc);

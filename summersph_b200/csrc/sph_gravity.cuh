@@ -134,7 +134,7 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
       for (; k < cnt; ++k) grav_term(W.lxy[k], W.lzg[k], (W.lmask[k] >> lane) & 1u, xi, yi, zi, inv_h, h2x4, soft, gt, P.nq, P.dq, P.inv_dq, gx[0], gy[0], gz[0]);
     };
 
-    if (do_grav) {
+    if (do_grav && tg.y > 0) {               // tg.y == 0: an unused tail entry of the run table
       const BvhBox gb = gbox[chunk];
       const double lo0 = gb.plo[0], lo1 = gb.plo[1], lo2 = gb.plo[2], hi0 = gb.phi[0], hi1 = gb.phi[1], hi2 = gb.phi[2];
       const double soft_min = warp_min(live ? soft : INFINITY), soft_max = warp_max(live ? soft : 0.0);
@@ -278,18 +278,39 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
   if (lane == 0 && do_grav) { atomicAdd(&ctr->grav_opened, n_open); atomicAdd(&ctr->grav_accepted, n_acc); }
 }
 
-// Gravity walk groups: fixed runs of 32 Morton-consecutive particles of this rank's slice [p0, p1) (one warp
-// per run computes its position box).  The gravity walk tolerates a run that straddles a coarse cell boundary
-// (more mixed nodes, decided per particle), and full warps matter more to it than tight boxes.
-__global__ void k_grav_chunks(int p0, int p1, int width, const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
-                              int2* __restrict__ groups, BvhBox* __restrict__ box) {
+// Gravity walk groups: runs of GRAV_CHUNK_WIDTH Morton-consecutive particles.  The gravity walk tolerates a run that
+// straddles a coarse cell boundary (more mixed nodes, decided per particle), and full warps matter more to it than
+// tight boxes.  Runs restart at every GRAV_SEG-th SPH walk group, and rank slices are cut only at those boundaries,
+// so the set of runs - hence every particle's accumulation order - does not depend on the number of ranks.
+#define GRAV_SEG 64
+// chunks per segment (segment s = SPH groups [s * GRAV_SEG, (s + 1) * GRAV_SEG))
+__global__ void k_seg_count(int seg0, int nseg, int n_groups, int n, int width, const int* __restrict__ gfirst, int* __restrict__ cnt) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s > nseg) return;
+  if (s == nseg) { cnt[s] = 0; return; }
+  const int ga = (seg0 + s) * GRAV_SEG, gb = min(ga + GRAV_SEG, n_groups);
+  const int pa = gfirst[ga], pb = gb < n_groups ? gfirst[gb] : n;
+  cnt[s] = (pb - pa + width - 1) / width;
+}
+// one warp per segment writes its runs
+__global__ void k_seg_chunks(int seg0, int nseg, int n_groups, int n, int width, const int* __restrict__ gfirst, const int* __restrict__ off,
+                             int2* __restrict__ groups) {
+  const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (s >= nseg) return;
+  const int ga = (seg0 + s) * GRAV_SEG, gb = min(ga + GRAV_SEG, n_groups);
+  const int pa = gfirst[ga], pb = gb < n_groups ? gfirst[gb] : n;
+  const int nch = (pb - pa + width - 1) / width, o = off[s];
+  for (int k = lane; k < nch; k += 32) groups[o + k] = make_int2(pa + k * width, min(width, pb - (pa + k * width)));
+}
+// one warp per run: its position box
+__global__ void k_grav_boxes(int n_chunks, const int2* __restrict__ groups, const double* __restrict__ x, const double* __restrict__ y,
+                             const double* __restrict__ z, BvhBox* __restrict__ box) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  const int first = p0 + warp * width;
-  if (first >= p1) return;
-  const int cnt = min(width, p1 - first);
+  if (warp >= n_chunks) return;
+  const int2 g = groups[warp];
   float plo[3] = {INFINITY, INFINITY, INFINITY}, phi[3] = {-INFINITY, -INFINITY, -INFINITY};
-  if (lane < cnt) {
-    const int i = first + lane;
+  if (lane < g.y) {
+    const int i = g.x + lane;
     const double p[3] = {x[i], y[i], z[i]};
     for (int k = 0; k < 3; ++k) { plo[k] = __double2float_rd(p[k]); phi[k] = __double2float_ru(p[k]); }
   }
@@ -297,7 +318,7 @@ __global__ void k_grav_chunks(int p0, int p1, int width, const double* __restric
   if (lane == 0) {
     BvhBox b;
     for (int k = 0; k < 3; ++k) { b.plo[k] = plo[k]; b.phi[k] = phi[k]; b.rlo[k] = 0.f; b.rhi[k] = 0.f; }
-    box[warp] = b; groups[warp] = make_int2(first, cnt);
+    box[warp] = b;
   }
 }
 
