@@ -57,7 +57,7 @@ struct GravWarpSmem {
   int2     stack[GW_STACK];
   double2  lxy[GW_LIST], lzg[GW_LIST];     // (cx, cy), (cz, G*M)
   unsigned lmask[GW_LIST];
-  double   mcx[32], mcy[32], mcz[32], msize[32];            // mixed nodes of the current trip
+  double   mcx[32], mcy[32], mcz[32], msize[32], mlo[32], mhi[32];   // mixed nodes of the current trip: COM, size, d2 band of the cheap test
   unsigned mmask[32];
 };
 
@@ -101,7 +101,7 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
   __syncthreads();
   int2* myspill = spill + (size_t)(blockIdx.x * (blockDim.x >> 5) + warp) * GW_SPILL;
   const unsigned lt_mask = (1u << lane) - 1u;
-  const double theta = P.theta, theta2 = theta * theta;
+  const double theta = P.theta, theta2 = theta * theta, inv_theta2 = 1.0 / theta2;
   unsigned long long n_open = 0, n_acc = 0;
 
   for (;;) {
@@ -198,6 +198,9 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
         if (cls == 3) {
           const int pos = __popc(balM & lt_mask);
           W.mcx[pos] = ncx; W.mcy[pos] = ncy; W.mcz[pos] = ncz; W.msize[pos] = nsize; W.mmask[pos] = emask;
+          // size^2 < theta^2 d2 (1 - 1e-12)  <=>  d2 > size^2 / (theta^2 (1 - 1e-12)); the band in between gets the exact test
+          const double s2t = nsize * nsize * inv_theta2;
+          W.mhi[pos] = s2t * (1.0 + 2e-12); W.mlo[pos] = s2t * (1.0 - 2e-12);
         }
         __syncwarp();
         // ---- lane = particle: the reference's own test on the mixed nodes; the node's lane keeps the two ballots
@@ -209,13 +212,10 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
           const unsigned mm = W.mmask[q];
           const bool in = (mm >> lane) & 1u;
           const double dx = xi - W.mcx[q], dy = yi - W.mcy[q], dz = zi - W.mcz[q];          // F:274
-          const double d2 = dx * dx + dy * dy + dz * dz + soft;
-          const double size = W.msize[q];
-          const double s2 = size * size, t2 = theta2 * d2;
-          bool accept;
-          if (s2 < t2 * (1.0 - 1e-12)) accept = true;
-          else if (s2 > t2 * (1.0 + 1e-12)) accept = false;
-          else {   // borderline: redo the reference's arithmetic exactly (no contraction)       F:275-278
+          const double d2 = fma(dx, dx, fma(dy, dy, fma(dz, dz, soft)));
+          bool accept = d2 > W.mhi[q];
+          if (!accept && !(d2 < W.mlo[q])) {   // borderline: redo the reference's arithmetic exactly (no contraction)       F:275-278
+            const double size = W.msize[q];
             const double e2 = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)), soft);
             accept = __ddiv_rn(size, __dsqrt_rn(e2)) < theta;
           }

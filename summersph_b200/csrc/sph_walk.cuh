@@ -22,11 +22,8 @@ struct BvhInfo { int nlev; int off[12]; int cnt[12]; };
 #define WALK_CQ    96       // chunk queue entries per warp
 #define WALK_TILE  32       // staged source particles per warp
 #define WALK_WS    (WALK_STACK + WALK_CQ + WALK_TILE)   // unsigned words of walk state per warp
-#ifndef DENS_COMPACT
-#define DENS_COMPACT 0
-#endif
 #define PAIR_WIN   64       // compacted (target, source) hits evaluated per window, lane = pair
-#define DENS_WARP_DOUBLES (8 * WALK_TILE + 4 * 32 + 2 * PAIR_WIN + PAIR_WIN / 4 + 32)   // tile + targets + results + hit list + saved-list buffer (64 ints)
+#define DENS_WARP_DOUBLES (8 * WALK_TILE + 2 * WALK_TILE + 32)   // tile + float4 tile + saved-list buffer (64 ints)
 
 #ifdef WALK_DEBUG
 __device__ unsigned long long wk_dbg[16];
@@ -176,9 +173,8 @@ struct DensityOp {
   NeighbourListSink nl; int* lbuf; int ln, cur_blk; float grlo[3], grhi[3]; const double* hsrc; int variable_h; double h_fixed;
   // tile (per warp, shared memory): 8 arrays of WALK_TILE doubles
   double *sx, *sy, *sz, *sm, *scx, *scy, *scz, *sR;
-  double *tgx, *tgy, *tgz, *tgih;    // the group's targets (per warp, shared memory): x y z 1/h
-  double *resW, *resB;               // pair results of the current window
-  unsigned short* plist;             // compacted hit list of the current window: (target lane << 5) | tile slot
+  float4* ft;                        // float copy of the tile positions, relative to the group's origin (prefilter)
+  double g0x, g0y, g0z; float xif, yif, zif, r2maxif;
   const DensityArrays& A;
   const double *wt, *dwt;            // shared-memory tables
   int nq; double dq, inv_dq;
@@ -265,64 +261,34 @@ struct DensityOp {
   }
   __device__ __forceinline__ void list_end() { __syncwarp(); list_flush(ln, true); __syncwarp(); }
   __device__ __forceinline__ void stage(int s, int j) {
-    sx[s] = A.x[j]; sy[s] = A.y[j]; sz[s] = A.z[j]; sm[s] = A.m[j];
+    const double px = A.x[j], py = A.y[j], pz = A.z[j];
+    sx[s] = px; sy[s] = py; sz[s] = pz; sm[s] = A.m[j];
     scx[s] = A.lcx[j]; scy[s] = A.lcy[j]; scz[s] = A.lcz[j]; sR[s] = A.reach[j];
+    ft[s] = make_float4((float)(px - g0x), (float)(py - g0y), (float)(pz - g0z), 0.f);
   }
   __device__ __forceinline__ void consume(int count) {
-    const int lane = threadIdx.x & 31;
-    unsigned mask = 0, cmask = 0;
+    // Prefilter, lane = target, FP32 on group-relative coordinates: |x_i - x_j|^2 against 4 h_i^2 with a 1e-4 margin
+    // (float rounding is ~1e-6 of the limit).  Beyond it W(q > 2) = 0 exactly (F:112), so it only drops exact zeros;
+    // the reference's leaf-box test (F:443 | V:479) and q <= 2 are evaluated in FP64 on the survivors.  With the
+    // exact candidate counter on, every staged source goes through the FP64 tests.
+    unsigned mask = 0;
     if (active) {
+      if (count_all) mask = count >= 32 ? 0xffffffffu : ((1u << count) - 1u);
+      else {
 #pragma unroll 4
-      for (int k = 0; k < count; ++k) {
-        const double R = sR[k];
-        const bool in = (fabs(xi - scx[k]) < R) & (fabs(yi - scy[k]) < R) & (fabs(zi - scz[k]) < R);   // F:443 | V:479
-        const double dx = xi - sx[k], dy = yi - sy[k], dz = zi - sz[k];
-        const bool nz = !(dx * dx + dy * dy + dz * dz > r2max);       // W(q > 2) = 0 exactly (F:112): only these need arithmetic
-        cmask |= (in ? 1u : 0u) << k;
-        mask |= ((in & nz) ? 1u : 0u) << k;
+        for (int k = 0; k < count; ++k) {
+          const float4 sj = ft[k];
+          const float dx = xif - sj.x, dy = yif - sj.y, dz = zif - sj.z;
+          const bool far = fmaf(dx, dx, fmaf(dy, dy, dz * dz)) > r2maxif;
+          mask |= (far ? 0u : 1u) << k;
+        }
       }
     }
-    cand += __popc(cmask);
 #ifdef WALK_DEBUG
     { int hc = __popc(mask); int mx = hc, sm = hc; for (int o = 16; o > 0; o >>= 1) { mx = max(mx, __shfl_xor_sync(FULL_MASK, mx, o)); sm += __shfl_xor_sync(FULL_MASK, sm, o); }
       WKD(8, 1); WKD(9, count); WKD(10, mx); WKD(11, sm); }
 #endif
-#if DENS_COMPACT
-    // The hits (target lane, tile slot) of the whole warp are compacted into one list and evaluated with
-    // lane = pair, so the kernel arithmetic runs with every lane busy whatever the spread of hits over the
-    // targets; each target then adds its own terms in tile order (deterministic).
-    const int c = __popc(mask);
-    int incl = c;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL_MASK, incl, o); if (lane >= o) incl += v; }
-    const int total = __shfl_sync(FULL_MASK, incl, 31);
-    unsigned mw = mask, ms = mask;
-    int gw = incl - c, gs = gw;
-    for (int base = 0; base < total; base += PAIR_WIN) {
-      const int lim = base + PAIR_WIN;
-      while (mw && gw < lim) { const int k = __ffs(mw) - 1; mw &= mw - 1; plist[gw - base] = (unsigned short)((lane << 5) | k); ++gw; }
-      __syncwarp();
-      const int nwin = total - base < PAIR_WIN ? total - base : PAIR_WIN;
-      for (int p = lane; p < nwin; p += 32) {
-        const int e = plist[p], t = e >> 5, k = e & 31;
-        const double dx = tgx[t] - sx[k], dy = tgy[t] - sy[k], dz = tgz[t] - sz[k];
-        const double r2 = dx * dx + dy * dy + dz * dz;
-        double r, rs; fast_sqrt_rsqrt(r2, r, rs);
-        r = (r2 == 0.0) ? 0.0 : r;                                           // self term, W(0)
-        const double q = r * tgih[t];
-        const bool in = q <= 2.0;
-        double w, dw; table_lerp(wt, dwt, nq, dq, inv_dq, in ? q : 0.0, w, dw);
-        const double mj = in ? sm[k] : 0.0;
-        resW[p] = mj * w;
-        resB[p] = mj * (r * dw);
-        contrib += in ? 1u : 0u;
-      }
-      __syncwarp();
-      while (ms && gs < lim) { ms &= ms - 1; accW += resW[gs - base]; accB += resB[gs - base]; ++gs; }
-      __syncwarp();
-    }
-#else
-    // two hits per trip, branch-free, so two independent dependency chains are in flight per lane
+    // two survivors per trip, branch-free, so two independent dependency chains are in flight per lane
     double w2 = 0.0, b2 = 0.0;
     while (mask) {
       const int k0 = __ffs(mask) - 1; mask &= mask - 1;
@@ -332,19 +298,21 @@ struct DensityOp {
       term(k1, v1, w2, b2);
     }
     accW += w2; accB += b2;
-#endif
   }
   __device__ __forceinline__ void term(int k, bool valid, double& aW, double& aB) {
+    const double R = sR[k];
     const double dx = xi - sx[k], dy = yi - sy[k], dz = zi - sz[k];
+    const bool box = valid & (fabs(xi - scx[k]) < R) & (fabs(yi - scy[k]) < R) & (fabs(zi - scz[k]) < R);   // F:443 | V:479
     const double r2 = dx * dx + dy * dy + dz * dz;
     double r, rs; fast_sqrt_rsqrt(r2, r, rs);
     r = (r2 == 0.0) ? 0.0 : r;                                           // self term, W(0)
     const double q = r * inv_h;
-    const bool in = valid & (q <= 2.0);
+    const bool in = box & (q <= 2.0);
     double w, dw; table_lerp(wt, dwt, nq, dq, inv_dq, in ? q : 0.0, w, dw);
     const double mj = in ? sm[k] : 0.0;
     aW += mj * w;
     aB += mj * (r * dw);
+    cand += box ? 1u : 0u;
     contrib += in ? 1u : 0u;
   }
 };
@@ -381,23 +349,23 @@ k_density(int n_groups, const int2* __restrict__ groups, DevParams P, DensityArr
     DensityOp<!HITER> op(A);
     op.sx = tile; op.sy = tile + WALK_TILE; op.sz = tile + 2 * WALK_TILE; op.sm = tile + 3 * WALK_TILE;
     op.scx = tile + 4 * WALK_TILE; op.scy = tile + 5 * WALK_TILE; op.scz = tile + 6 * WALK_TILE; op.sR = tile + 7 * WALK_TILE;
-    op.tgx = tile + 8 * WALK_TILE; op.tgy = op.tgx + 32; op.tgz = op.tgx + 64; op.tgih = op.tgx + 96;
-    op.resW = op.tgx + 128; op.resB = op.resW + PAIR_WIN; op.plist = reinterpret_cast<unsigned short*>(op.resB + PAIR_WIN);
-    op.lbuf = reinterpret_cast<int*>(op.resB + PAIR_WIN + PAIR_WIN / 4);
+    op.ft = reinterpret_cast<float4*>(tile + 8 * WALK_TILE);
+    op.lbuf = reinterpret_cast<int*>(tile + 10 * WALK_TILE);
     op.nl = nl; op.hsrc = h; op.variable_h = P.variable_h; op.h_fixed = P.h_fixed;
     op.wt = wt; op.dwt = dwt; op.nq = P.nq; op.dq = P.dq; op.inv_dq = P.inv_dq;
     const BvhBox g = box[bi.off[0] + chunk];
     for (int k = 0; k < 3; ++k) { op.gplo[k] = g.plo[k]; op.gphi[k] = g.phi[k]; op.grlo[k] = g.rlo[k]; op.grhi[k] = g.rhi[k]; }
     op.xi = live ? A.x[i] : 0.0; op.yi = live ? A.y[i] : 0.0; op.zi = live ? A.z[i] : 0.0;
     op.cand = 0; op.contrib = 0; op.count_all = count_all != 0;
+    op.g0x = 0.5 * ((double)g.plo[0] + (double)g.phi[0]); op.g0y = 0.5 * ((double)g.plo[1] + (double)g.phi[1]); op.g0z = 0.5 * ((double)g.plo[2] + (double)g.phi[2]);
+    op.xif = (float)(op.xi - op.g0x); op.yif = (float)(op.yi - op.g0y); op.zif = (float)(op.zi - op.g0z);
     double hi = live ? (P.variable_h ? h[i] : P.h_fixed) : 1.0;
     const double mi = live ? A.m[i] : 0.0;
 
     if (!HITER) {
       op.active = live; op.inv_h = 1.0 / hi; op.r2max = 4.0 * hi * hi * (1.0 + 1e-9); op.accW = 0.0; op.accB = 0.0;
       op.g_r2max = warp_max(live ? op.r2max : 0.0);
-      op.tgx[lane] = op.xi; op.tgy[lane] = op.yi; op.tgz[lane] = op.zi; op.tgih[lane] = op.inv_h;
-      __syncwarp();
+      op.r2maxif = __double2float_ru(op.r2max) * 1.0001f;
       op.list_begin(chunk);
       neighbour_walk(op, groups, chunk, box, bi, stack, cq);
       op.list_end();
@@ -435,8 +403,7 @@ k_density(int n_groups, const int2* __restrict__ groups, DevParams P, DensityArr
         op.active = iter; op.inv_h = 1.0 / hi; op.r2max = 4.0 * hi * hi * (1.0 + 1e-9); op.accW = 0.0; op.accB = 0.0;
         op.g_r2max = warp_max(iter ? op.r2max : 0.0);
         if (iter) old_len = hi;
-        op.tgx[lane] = op.xi; op.tgy[lane] = op.yi; op.tgz[lane] = op.zi; op.tgih[lane] = op.inv_h;
-        __syncwarp();
+        op.r2maxif = __double2float_ru(op.r2max) * 1.0001f;
         neighbour_walk(op, groups, chunk, box, bi, stack, cq);
         if (iter) {
           const double n3 = P.pi_norm * ((hi * hi) * hi), n4 = P.pi_norm * ((hi * hi) * (hi * hi));
