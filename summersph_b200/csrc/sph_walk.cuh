@@ -436,9 +436,9 @@ struct ForceArrays {
   const double *x, *y, *z, *vx, *vy, *vz, *m, *h, *rho, *c, *alpha, *por2, *lcx, *lcy, *lcz, *reach;
   const int* id;
 };
-#define FORCE_FIELDS 19
+#define FORCE_FIELDS 18
 #define FORCE_TG_FIELDS 19
-#define FORCE_WARP_DOUBLES (FORCE_FIELDS * WALK_TILE + FORCE_TG_FIELDS * 32 + 3 * PAIR_WIN + PAIR_WIN / 4 + 2 * WALK_TILE)   // tile + targets + results + hit list + float4 tile
+#define FORCE_WARP_DOUBLES (FORCE_FIELDS * WALK_TILE + FORCE_TG_FIELDS * 32 + 5 * PAIR_WIN + PAIR_WIN / 4 + 2 * WALK_TILE)   // tile + targets + results + hit list + float4 tile
 
 struct ForceOp {
   static const bool SYMMETRIC = true;
@@ -450,7 +450,7 @@ struct ForceOp {
   float4* ft;            // float copy of the tile for the prefilter: position relative to the group's origin, r2max rounded up
   double g0x, g0y, g0z;  // the group's origin (centre of its position box)
   float xif, yif, zif, r2maxif;
-  double* res;           // pair results of the current window: f, u, a
+  double* res;           // pair results of the current window: f dx, f dy, f dz, u, a
   unsigned short* plist; // compacted hit list of the current window: (target lane << 5) | tile slot
   const ForceArrays& A;
   const double* dwt; int nq; double dq, inv_dq;
@@ -489,14 +489,14 @@ struct ForceOp {
     t[6 * WALK_TILE + s] = A.m[j];  t[7 * WALK_TILE + s] = hj;
     t[8 * WALK_TILE + s] = 1.0 / (pi_norm * ((hj * hj) * (hj * hj)));
     t[17 * WALK_TILE + s] = 1.0 / hj;
-    t[18 * WALK_TILE + s] = (fabs(A.por2[j] + A.c[j]) < INFINITY) ? 4.0 * hj * hj * (1.0 + 1e-9) : INFINITY;
     t[9 * WALK_TILE + s] = A.rho[j]; t[10 * WALK_TILE + s] = A.c[j]; t[11 * WALK_TILE + s] = A.alpha[j];
     t[12 * WALK_TILE + s] = A.por2[j];
     t[13 * WALK_TILE + s] = A.lcx[j]; t[14 * WALK_TILE + s] = A.lcy[j]; t[15 * WALK_TILE + s] = A.lcz[j];
     t[16 * WALK_TILE + s] = A.reach[j];
     tid[s] = A.id[j];
+    const double r2max_j = (fabs(A.por2[j] + A.c[j]) < INFINITY) ? 4.0 * hj * hj * (1.0 + 1e-9) : INFINITY;
     ft[s] = make_float4((float)(t[0 * WALK_TILE + s] - g0x), (float)(t[1 * WALK_TILE + s] - g0y), (float)(t[2 * WALK_TILE + s] - g0z),
-                        __double2float_ru(t[18 * WALK_TILE + s]));
+                        __double2float_ru(r2max_j));
   }
   __device__ __forceinline__ void consume(int count) {
     // Prefilter, lane = target, FP32: |x_i - x_j|^2 against max(r2max_i, r2max_j) with a 1e-4 margin that covers the
@@ -548,22 +548,22 @@ struct ForceOp {
         const double R = lt ? t[16 * WALK_TILE + k] : g[16 * 32];
         const bool in = (idj != idi_) & (fabs(px - cx) < R) & (fabs(py - cy) < R) & (fabs(pz - cz) < R);
         const double dx = xi_ - xj, dy = yi_ - yj, dz = zi_ - zj;
-        const bool nz = !(dx * dx + dy * dy + dz * dz > fmax(g[17 * 32], t[18 * WALK_TILE + k]));
+        const double hj_ = t[7 * WALK_TILE + k];
+        const double r2max_j = (fabs(t[12 * WALK_TILE + k] + t[10 * WALK_TILE + k]) < INFINITY) ? 4.0 * hj_ * hj_ * (1.0 + 1e-9) : INFINITY;
+        const bool nz = !(dx * dx + dy * dy + dz * dz > fmax(g[17 * 32], r2max_j));
         pairs += in ? 1u : 0u;
         double f = 0.0, u = 0.0, a = 0.0;
         if (in & nz) pair(tl, k, f, u, a);
-        res[p] = f; res[PAIR_WIN + p] = u; res[2 * PAIR_WIN + p] = a;
+        res[p] = f * dx; res[PAIR_WIN + p] = f * dy; res[2 * PAIR_WIN + p] = f * dz;      // F:383 (own side)
+        res[3 * PAIR_WIN + p] = u; res[4 * PAIR_WIN + p] = a;
       }
       __syncwarp();
-      while (ms && gs < lim) {
-        const int k = __ffs(ms) - 1; ms &= ms - 1;
+      const int ge = gs + __popc(ms) < lim ? gs + __popc(ms) : lim;       // this lane's hits are contiguous in the list
+      for (; gs < ge; ++gs) {
         const int q = gs - base;
-        const double f = res[q];
-        ax -= f * (xi - t[0 * WALK_TILE + k]);                            // F:383 (own side)
-        ay -= f * (yi - t[1 * WALK_TILE + k]);
-        az -= f * (zi - t[2 * WALK_TILE + k]);
-        ud += res[PAIR_WIN + q]; ad += res[2 * PAIR_WIN + q];
-        ++gs;
+        ax -= res[q]; ay -= res[PAIR_WIN + q]; az -= res[2 * PAIR_WIN + q];
+        ud += res[3 * PAIR_WIN + q]; ad += res[4 * PAIR_WIN + q];
+        ms &= ms - 1;
       }
       __syncwarp();
     }
@@ -644,8 +644,8 @@ k_force(int n_groups, const int2* __restrict__ groups, DevParams P, ForceArrays 
     ForceOp op(A);
     op.t = tile; op.tid = tids + warp * WALK_TILE;
     op.tg = tile + FORCE_FIELDS * WALK_TILE; op.res = op.tg + FORCE_TG_FIELDS * 32;
-    op.plist = reinterpret_cast<unsigned short*>(op.res + 3 * PAIR_WIN);
-    op.ft = reinterpret_cast<float4*>(op.res + 3 * PAIR_WIN + PAIR_WIN / 4);
+    op.plist = reinterpret_cast<unsigned short*>(op.res + 5 * PAIR_WIN);
+    op.ft = reinterpret_cast<float4*>(op.res + 5 * PAIR_WIN + PAIR_WIN / 4);
     op.dwt = dwt; op.nq = P.nq; op.dq = P.dq; op.inv_dq = P.inv_dq;
     op.variable_h = P.variable_h; op.h_fixed = P.h_fixed; op.pi_norm = P.pi_norm; op.lit_001 = P.lit_001;
     const BvhBox g = box[bi.off[0] + chunk];
