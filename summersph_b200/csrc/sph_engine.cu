@@ -85,6 +85,7 @@ struct sph_ctx {
   // peer-memory exchange: every exchanged array of every rank mapped here (CUDA IPC, or the raw pointer when the peer
   // lives in this process); slices are pushed with copy-engine transfers on their own stream
   cudaStream_t xstream = nullptr; cudaEvent_t x_ready = nullptr, x_done = nullptr;
+  std::vector<cudaStream_t> pstream; std::vector<cudaEvent_t> pevent;   // one copy stream per peer: the pushes to different peers run on different copy engines
   bool p2p_stale = true, p2p_ok = false, x_pending = false;
   std::vector<std::vector<double*>> peer;      // [array slot][rank]
   std::vector<void*> ipc_opened; int* d_flag = nullptr; void* d_blob = nullptr; size_t blob_cap = 0;
@@ -302,16 +303,26 @@ int allgatherv_begin(sph_ctx* c, double* const* bufs, int nbufs) {
   const std::vector<double*> arr = exchanged_arrays(c);
   CK(cudaEventRecord(c->x_ready, c->stream));
   CK(cudaStreamWaitEvent(c->xstream, c->x_ready, 0));
+  while ((int)c->pstream.size() < c->n_ranks - 1) {
+    cudaStream_t st; cudaEvent_t ev;
+    CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    c->pstream.push_back(st); c->pevent.push_back(ev);
+  }
   const size_t off = (size_t)c->p0, cnt = (size_t)(c->p1 - c->p0);
+  std::vector<int> slot(nbufs, -1);
   for (int b = 0; b < nbufs; ++b) {
-    int a = -1;
-    for (int k = 0; k < (int)arr.size(); ++k) if (arr[k] == bufs[b]) a = k;
-    if (a < 0) { c->err = "allgatherv: array is not registered for the peer exchange"; return SPH_ERR_STATE; }
-    if (cnt == 0) continue;
-    for (int k = 1; k < c->n_ranks; ++k) {      // staggered peer order spreads the traffic over the switch
-      const int r = (c->rank + k) % c->n_ranks;
-      CK(cudaMemcpyAsync(c->peer[a][r] + off, bufs[b] + off, cnt * 8, cudaMemcpyDefault, c->xstream));
-    }
+    for (int k = 0; k < (int)arr.size(); ++k) if (arr[k] == bufs[b]) slot[b] = k;
+    if (slot[b] < 0) { c->err = "allgatherv: array is not registered for the peer exchange"; return SPH_ERR_STATE; }
+  }
+  for (int k = 1; k < c->n_ranks; ++k) {        // staggered peer order spreads the traffic over the switch
+    const int r = (c->rank + k) % c->n_ranks;
+    cudaStream_t st = c->pstream[k - 1];
+    CK(cudaStreamWaitEvent(st, c->x_ready, 0));
+    if (cnt > 0)
+      for (int b = 0; b < nbufs; ++b)
+        CK(cudaMemcpyAsync(c->peer[slot[b]][r] + off, bufs[b] + off, cnt * 8, cudaMemcpyDefault, st));
+    CK(cudaEventRecord(c->pevent[k - 1], st));
+    CK(cudaStreamWaitEvent(c->xstream, c->pevent[k - 1], 0));
   }
   NC(c->nccl.AllReduce(c->d_flag + 1, c->d_flag + 1, 1, 2 /*ncclInt32*/, NC_SUM, c->comm, c->xstream));
   CK(cudaEventRecord(c->x_done, c->xstream));
@@ -423,7 +434,7 @@ int build_tree_impl(sph_ctx* c, bool* retry_two_word) {
     PermuteArgs pa;
     for (int f = 0; f < 10; ++f) { pa.src[f] = c->st[c->cur][f]; pa.dst[f] = c->st[c->cur ^ 1][f]; }
     pa.id_src = c->id[c->cur]; pa.id_dst = c->id[c->cur ^ 1];
-    LAUNCH(k_permute, cdiv(n, T), T, 0, n, c->perm[0], pa);
+    LAUNCH(k_permute, cdiv(n, 4 * T), T, 0, n, c->perm[0], pa);
     c->cur ^= 1;
     if (c->two_word) {     // regenerate both key words in the final order from the re-ordered positions
       StateArrays s = state_of(c, c->cur);
@@ -583,8 +594,8 @@ int run_gravity(sph_ctx* c, int do_grav, int do_sinks) {
   const int ng = c->g1 - c->g0;
 #endif
   const int ns = do_sinks ? c->n_sink : 0;
-  if ((size_t)(ng + 8) * std::max(ns, 1) * 3 > c->sink_partial_cap) {
-    c->sink_partial_cap = (size_t)(ng + 8) * std::max(ns, 1) * 3 * 2;
+  if ((size_t)(ng + 8 + SINK_RED_BLOCKS) * std::max(ns, 1) * 3 > c->sink_partial_cap) {
+    c->sink_partial_cap = (size_t)(ng + 8 + SINK_RED_BLOCKS) * std::max(ns, 1) * 3 * 2;
     DA(c->sink_partial, c->sink_partial_cap);
   }
   if (ng > 0 && c->g1 > c->g0) {
@@ -617,7 +628,12 @@ int run_gravity(sph_ctx* c, int do_grav, int do_sinks) {
     unsigned long long hh[33]; cudaMemcpyFromSymbol(hh, gw_hist, sizeof(hh)); unsigned long long zz[33] = {}; cudaMemcpyToSymbol(gw_hist, zz, sizeof(zz));
     fprintf(stderr, "GWHIST"); for (int i = 0; i < 33; ++i) fprintf(stderr, " %llu", hh[i]); fprintf(stderr, "\n"); }
 #endif
-  LAUNCH(k_sink_reduce, 1, 256, 0, ng, c->n_sink, c->sink_partial, c->S, do_sinks);
+  if (do_sinks && ng > 4 * SINK_RED_BLOCKS) {
+    double* rows = c->sink_partial + (size_t)ng * std::max(ns, 1) * 3;      // spare rows behind the per-run partials
+    LAUNCH(k_sink_reduce_slices, SINK_RED_BLOCKS, 256, 0, ng, c->n_sink, c->sink_partial, rows);
+    LAUNCH(k_sink_reduce, 1, 256, 0, SINK_RED_BLOCKS, c->n_sink, rows, c->S, do_sinks);
+  } else
+    LAUNCH(k_sink_reduce, 1, 256, 0, ng, c->n_sink, c->sink_partial, c->S, do_sinks);
   stage_end(c);
   if (c->n_ranks > 1) { stage_begin(c, ST_COMM); int r_ = allreduce(c, c->S.ax, (size_t)3 * SPH_MAX_SINKS, NC_FLOAT64, NC_SUM); if (r_) return r_; stage_end(c); }
   stage_begin(c, ST_GRAVITY);
@@ -676,7 +692,7 @@ int compact(sph_ctx* c) {
   PermuteArgs pa;
   for (int f = 0; f < 10; ++f) { pa.src[f] = c->st[c->cur][f]; pa.dst[f] = c->st[c->cur ^ 1][f]; }
   pa.id_src = c->id[c->cur]; pa.id_dst = c->id[c->cur ^ 1];
-  if (nsel > 0) LAUNCH(k_permute, cdiv(nsel, T), T, 0, nsel, c->perm[1], pa);
+  if (nsel > 0) LAUNCH(k_permute, cdiv(nsel, 4 * T), T, 0, nsel, c->perm[1], pa);
   c->cur ^= 1;
   c->n = nsel;
   c->tree_valid = false; c->pos_moved = true;
@@ -880,6 +896,8 @@ int sph_destroy(sph_ctx* c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   p2p_close(c);
+  for (auto st : c->pstream) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+  for (auto ev : c->pevent) cudaEventDestroy(ev);
   if (c->xstream) { cudaStreamSynchronize(c->xstream); cudaStreamDestroy(c->xstream); cudaEventDestroy(c->x_ready); cudaEventDestroy(c->x_done); }
   if (c->d_flag) cudaFree(c->d_flag);
   if (c->d_blob) cudaFree(c->d_blob);

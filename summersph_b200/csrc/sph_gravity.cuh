@@ -322,7 +322,25 @@ __global__ void k_grav_boxes(int n_chunks, const int2* __restrict__ groups, cons
   }
 }
 
-// fold per-warp sink partials in a fixed order (deterministic). One block of 256.
+// fold the per-run sink partials in a fixed order (deterministic): SINK_RED_BLOCKS blocks each fold a contiguous
+// slice of the runs into out[block][sink][3]; k_sink_reduce then folds those few rows.
+#define SINK_RED_BLOCKS 128
+__global__ void k_sink_reduce_slices(int n_parts, int n_sink, const double* __restrict__ partial, double* __restrict__ out) {
+  __shared__ double red[256];
+  const int t = threadIdx.x;
+  const int per = (n_parts + gridDim.x - 1) / gridDim.x;
+  const int b0 = blockIdx.x * per, b1 = min(b0 + per, n_parts);
+  for (int s = 0; s < n_sink; ++s)
+    for (int k = 0; k < 3; ++k) {
+      double v = 0.0;
+      for (int b = b0 + t; b < b1; b += 256) v += partial[((size_t)b * n_sink + s) * 3 + k];
+      red[t] = v;
+      __syncthreads();
+      for (int o = 128; o > 0; o >>= 1) { if (t < o) red[t] += red[t + o]; __syncthreads(); }
+      if (t == 0) out[((size_t)blockIdx.x * n_sink + s) * 3 + k] = red[0];
+      __syncthreads();
+    }
+}
 __global__ void k_sink_reduce(int n_parts, int n_sink, const double* __restrict__ partial, SinkArrays S, int do_sinks) {
   __shared__ double red[256];
   const int t = threadIdx.x;

@@ -90,13 +90,26 @@ __global__ void k_gather_u64(int n, const int* __restrict__ perm, const uint64_t
 
 // physical re-order of the state into sorted order
 struct PermuteArgs { const double* src[10]; double* dst[10]; const int* id_src; int* id_dst; };
+// Four particles per thread, field-major: the four gathers of one field are in flight together and a block touches
+// two streams (one source, one destination array) at a time instead of twenty-two.
 __global__ void k_permute(int n, const int* __restrict__ perm, PermuteArgs a) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  int p = perm[i];
+  const int base = blockIdx.x * (blockDim.x * 4) + threadIdx.x;
+  int p[4]; bool ok[4];
 #pragma unroll
-  for (int f = 0; f < 10; ++f) a.dst[f][i] = a.src[f][p];
-  a.id_dst[i] = a.id_src[p];
+  for (int k = 0; k < 4; ++k) { const int i = base + k * blockDim.x; ok[k] = i < n; p[k] = ok[k] ? perm[i] : 0; }
+#pragma unroll
+  for (int f = 0; f < 10; ++f) {
+    double v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = a.src[f][p[k]];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) if (ok[k]) a.dst[f][base + k * blockDim.x] = v[k];
+  }
+  int w[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) w[k] = a.id_src[p[k]];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) if (ok[k]) a.id_dst[base + k * blockDim.x] = w[k];
 }
 
 // ------------------------------------------------------------------------------------------------------
