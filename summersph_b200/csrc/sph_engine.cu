@@ -532,7 +532,7 @@ int run_density(sph_ctx* c) {
   // pool of 32-int blocks for the saved candidate lists: about one block (30 sources) per local particle, grown
   // when an evaluation overflowed it (that evaluation's pair loop walks by itself instead)
   {
-    const size_t want = (size_t)(c->p1 - c->p0) + 4 * (size_t)(c->g1 - c->g0) + 1024;
+    const size_t want = (size_t)(c->p1 - c->p0) + 4 * (size_t)(c->g1 - c->g0) + 1024 + (size_t)NL_BATCH * 16 * c->n_sm;
     if (want > c->nl_pool_blocks) { c->nl_pool_blocks = want + want / 4; DA(c->nl_pool, c->nl_pool_blocks * 32); }
     if ((size_t)c->n_groups + 1 > c->nl_head_cap) { c->nl_head_cap = (size_t)c->n_groups * 5 / 4 + 64; DA(c->nl_head, c->nl_head_cap); }
     CK(cudaMemsetAsync(c->nl_ctl, 0, 2 * sizeof(int), c->stream));      // ctl[2] (overflow) is sticky until the host has seen it
@@ -589,7 +589,7 @@ int run_gravity(sph_ctx* c, int do_grav, int do_sinks) {
 #if GRAV_CHUNK_WIDTH > 0
   // upper bound of the number of runs in this rank's slice; unused tail entries stay empty (first = 0, count = 0)
   const int seg0 = c->g0 / GRAV_SEG, nseg = cdiv(c->g1 - c->g0, GRAV_SEG);
-  const int ng = cdiv(c->p1 - c->p0, GRAV_CHUNK_WIDTH) + nseg;
+  const int ng = cdiv(c->p1 - c->p0, std::min(GRAV_CHUNK_WIDTH, GRAV_MINFILL)) + 2 * nseg;
 #else
   const int ng = c->g1 - c->g0;
 #endif
@@ -606,10 +606,10 @@ int run_gravity(sph_ctx* c, int do_grav, int do_sinks) {
       if ((size_t)ng > c->ggroups_cap) { c->ggroups_cap = (size_t)ng * 5 / 4 + 64; DA(c->ggroups, c->ggroups_cap); DA(c->gbvh, c->ggroups_cap); }
       if ((size_t)nseg + 1 > c->seg_cap) { c->seg_cap = (size_t)nseg * 5 / 4 + 64; DA(c->seg_cnt, c->seg_cap); DA(c->seg_off, c->seg_cap); }
       CK(cudaMemsetAsync(c->ggroups, 0, sizeof(int2) * (size_t)ng, c->stream));
-      LAUNCH(k_seg_count, cdiv(nseg + 1, 256), 256, 0, seg0, nseg, c->n_groups, (int)c->n, GRAV_CHUNK_WIDTH, c->gfirst, c->seg_cnt);
+      LAUNCH(k_seg_count, cdiv(nseg + 1, 64), 64, 0, seg0, nseg, c->n_groups, GRAV_CHUNK_WIDTH, c->groups, c->seg_cnt);
       size_t bytes = c->cub_bytes;
       CK(cub::DeviceScan::ExclusiveSum(c->cub_tmp, bytes, c->seg_cnt, c->seg_off, nseg + 1, c->stream));
-      LAUNCH(k_seg_chunks, cdiv((int64_t)nseg * 32, 256), 256, 0, seg0, nseg, c->n_groups, (int)c->n, GRAV_CHUNK_WIDTH, c->gfirst, c->seg_off, c->ggroups);
+      LAUNCH(k_seg_chunks, cdiv(nseg, 64), 64, 0, seg0, nseg, c->n_groups, GRAV_CHUNK_WIDTH, c->groups, c->seg_off, c->ggroups);
       LAUNCH(k_grav_boxes, cdiv((int64_t)ng * 32, 256), 256, 0, ng, c->ggroups, s.x, s.y, s.z, c->gbvh);
       c->grav_groups_valid = true;
     }

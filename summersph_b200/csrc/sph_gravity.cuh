@@ -224,7 +224,11 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
         }
         // ---- lane = node again: accepted (node, lane set) pairs join the interaction list, opened ones push their child block
         n_acc += __popc(acc_mask); n_open += __popc(open_mask);
+#ifdef GW_SKIP_T
+        const bool ins = acc_mask != 0u && nm > 0.0 && __popc(acc_mask) >= GW_SKIP_T;   // timing experiment only: drops the sparse entries (wrong forces)
+#else
         const bool ins = acc_mask != 0u && nm > 0.0;                                // F:279: massless nodes add nothing
+#endif
         const unsigned balL = __ballot_sync(FULL_MASK, ins);
         if (ins) {
           const int pos = ln + __popc(balL & lt_mask);
@@ -283,24 +287,41 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
 // tight boxes.  Runs restart at every GRAV_SEG-th SPH walk group, and rank slices are cut only at those boundaries,
 // so the set of runs - hence every particle's accumulation order - does not depend on the number of ranks.
 #define GRAV_SEG 64
-// chunks per segment (segment s = SPH groups [s * GRAV_SEG, (s + 1) * GRAV_SEG))
-__global__ void k_seg_count(int seg0, int nseg, int n_groups, int n, int width, const int* __restrict__ gfirst, int* __restrict__ cnt) {
+// Run formation inside one segment (SPH groups [s * GRAV_SEG, (s + 1) * GRAV_SEG), particles [pa, pb)): walk groups
+// are appended to the current run; when the next group does not fit, the run is closed at that (cell) boundary if it
+// already holds GRAV_MINFILL particles, else it is filled up with the head of the group.  One thread per segment.
+#ifndef GRAV_MINFILL
+#define GRAV_MINFILL 33          // > width: never close early (fixed runs)
+#endif
+template <bool WRITE>
+__device__ __forceinline__ int seg_runs(int ga, int gb, int width, const int2* __restrict__ sg, int2* __restrict__ out) {
+  int n_runs = 0, first = sg[ga].x, cur = 0;
+  for (int g = ga; g < gb; ++g) {
+    int sz = sg[g].y;
+    while (sz > 0) {
+      const int space = width - cur;
+      if (sz <= space) { cur += sz; sz = 0; }
+      else if (cur >= GRAV_MINFILL) { if (WRITE) out[n_runs] = make_int2(first, cur); ++n_runs; first += cur; cur = 0; continue; }
+      else { cur += space; sz -= space; }
+      if (cur == width) { if (WRITE) out[n_runs] = make_int2(first, cur); ++n_runs; first += cur; cur = 0; }
+    }
+  }
+  if (cur > 0) { if (WRITE) out[n_runs] = make_int2(first, cur); ++n_runs; }
+  return n_runs;
+}
+__global__ void k_seg_count(int seg0, int nseg, int n_groups, int width, const int2* __restrict__ sg, int* __restrict__ cnt) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s > nseg) return;
   if (s == nseg) { cnt[s] = 0; return; }
   const int ga = (seg0 + s) * GRAV_SEG, gb = min(ga + GRAV_SEG, n_groups);
-  const int pa = gfirst[ga], pb = gb < n_groups ? gfirst[gb] : n;
-  cnt[s] = (pb - pa + width - 1) / width;
+  cnt[s] = seg_runs<false>(ga, gb, width, sg, nullptr);
 }
-// one warp per segment writes its runs
-__global__ void k_seg_chunks(int seg0, int nseg, int n_groups, int n, int width, const int* __restrict__ gfirst, const int* __restrict__ off,
+__global__ void k_seg_chunks(int seg0, int nseg, int n_groups, int width, const int2* __restrict__ sg, const int* __restrict__ off,
                              int2* __restrict__ groups) {
-  const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= nseg) return;
   const int ga = (seg0 + s) * GRAV_SEG, gb = min(ga + GRAV_SEG, n_groups);
-  const int pa = gfirst[ga], pb = gb < n_groups ? gfirst[gb] : n;
-  const int nch = (pb - pa + width - 1) / width, o = off[s];
-  for (int k = lane; k < nch; k += 32) groups[o + k] = make_int2(pa + k * width, min(width, pb - (pa + k * width)));
+  seg_runs<true>(ga, gb, width, sg, groups + off[s]);
 }
 // one warp per run: its position box
 __global__ void k_grav_boxes(int n_chunks, const int2* __restrict__ groups, const double* __restrict__ x, const double* __restrict__ y,

@@ -141,6 +141,7 @@ __device__ void neighbour_walk(OP& op, const int2* __restrict__ groups, int chun
 // the reference lets such a particle poison every box partner through 0 * NaN, which the distance cull applied
 // to the list would hide) -> the walking pair kernel runs instead.
 #define NL_PER_BLOCK 30
+#define NL_BATCH 16
 struct NeighbourListSink { int* pool; int* head; int* ctl; int pool_blocks; };
 
 // shared kernel-table lookup: returns table-space (w, dw) at q (<= 2 assumed), F:113-118
@@ -170,7 +171,7 @@ struct DensityOp {
   static const bool SYMMETRIC = PRODUCE;
   static const bool LISTS = PRODUCE;
   // saved-list state (PRODUCE): lbuf = 64 ints of shared memory per warp
-  NeighbourListSink nl; int* lbuf; int ln, cur_blk; float grlo[3], grhi[3]; const double* hsrc; int variable_h; double h_fixed;
+  NeighbourListSink nl; int* lbuf; int ln, cur_blk, res_next, res_end; float grlo[3], grhi[3]; const double* hsrc; int variable_h; double h_fixed;
   // tile (per warp, shared memory): 8 arrays of WALK_TILE doubles
   double *sx, *sy, *sz, *sm, *scx, *scy, *scz, *sR;
   float4* ft;                        // float copy of the tile positions, relative to the group's origin (prefilter)
@@ -214,16 +215,21 @@ struct DensityOp {
     return fl;
   }
   // ---- saved list: append the flagged sources of one chunk (lane = source), flushing full blocks to the pool
+  // blocks are taken from the pool NL_BATCH at a time per warp (one returning atomic per batch, not per block)
+  __device__ __forceinline__ int take_block() {
+    const int lane = threadIdx.x & 31;
+    if (res_next == res_end) {
+      int b = 0;
+      if (lane == 0) b = atomicAdd(&nl.ctl[0], NL_BATCH);
+      res_next = __shfl_sync(FULL_MASK, b, 0); res_end = res_next + NL_BATCH;
+    }
+    int r = res_next++;
+    if (r >= nl.pool_blocks) { if (lane == 0) { nl.ctl[1] = 1; nl.ctl[2] = 1; } r = -2; }   // pool exhausted: this evaluation's lists are void
+    return r;
+  }
   __device__ __forceinline__ void list_flush(int cnt, bool last) {
     const int lane = threadIdx.x & 31;
-    int nxt = -1;
-    if (!last) {
-      if (lane == 0) {
-        nxt = atomicAdd(&nl.ctl[0], 1);
-        if (nxt >= nl.pool_blocks) { nl.ctl[1] = 1; nl.ctl[2] = 1; nxt = -2; }  // pool exhausted: the lists of this evaluation are void
-      }
-      nxt = __shfl_sync(FULL_MASK, nxt, 0);
-    }
+    const int nxt = last ? -1 : take_block();
     if (cur_blk >= 0) {
       const int v = lane < cnt ? lbuf[lane] : (lane == 30 ? cnt : (lane == 31 ? (nxt < 0 ? -1 : nxt) : 0));
       nl.pool[(size_t)cur_blk * 32 + lane] = v;
@@ -231,14 +237,8 @@ struct DensityOp {
     cur_blk = nxt;
   }
   __device__ __forceinline__ void list_begin(int chunk) {
-    const int lane = threadIdx.x & 31;
-    int b = 0;
-    if (lane == 0) {
-      b = atomicAdd(&nl.ctl[0], 1);
-      if (b >= nl.pool_blocks) { nl.ctl[1] = 1; nl.ctl[2] = 1; b = -2; }
-      nl.head[chunk] = b;
-    }
-    cur_blk = __shfl_sync(FULL_MASK, b, 0); ln = 0;
+    cur_blk = take_block(); ln = 0;
+    if ((threadIdx.x & 31) == 0) nl.head[chunk] = cur_blk;
   }
   __device__ __forceinline__ void list_append(bool want, int j) {
     const int lane = threadIdx.x & 31;
@@ -337,6 +337,7 @@ k_density(int n_groups, const int2* __restrict__ groups, DevParams P, DensityArr
   unsigned* cq = stack + WALK_STACK;
   const int nchunk = n_groups;
   unsigned long long tot_cand = 0, tot_contrib = 0, tot_iter = 0;
+  int res_next = 0, res_end = 0;         // this warp's reserve of list-pool blocks
 
   for (;;) {
     int chunk = 0;
@@ -351,7 +352,7 @@ k_density(int n_groups, const int2* __restrict__ groups, DevParams P, DensityArr
     op.scx = tile + 4 * WALK_TILE; op.scy = tile + 5 * WALK_TILE; op.scz = tile + 6 * WALK_TILE; op.sR = tile + 7 * WALK_TILE;
     op.ft = reinterpret_cast<float4*>(tile + 8 * WALK_TILE);
     op.lbuf = reinterpret_cast<int*>(tile + 10 * WALK_TILE);
-    op.nl = nl; op.hsrc = h; op.variable_h = P.variable_h; op.h_fixed = P.h_fixed;
+    op.nl = nl; op.hsrc = h; op.variable_h = P.variable_h; op.h_fixed = P.h_fixed; op.res_next = res_next; op.res_end = res_end;
     op.wt = wt; op.dwt = dwt; op.nq = P.nq; op.dq = P.dq; op.inv_dq = P.inv_dq;
     const BvhBox g = box[bi.off[0] + chunk];
     for (int k = 0; k < 3; ++k) { op.gplo[k] = g.plo[k]; op.gphi[k] = g.phi[k]; op.grlo[k] = g.rlo[k]; op.grhi[k] = g.rhi[k]; }
@@ -369,6 +370,7 @@ k_density(int n_groups, const int2* __restrict__ groups, DevParams P, DensityArr
       op.list_begin(chunk);
       neighbour_walk(op, groups, chunk, box, bi, stack, cq);
       op.list_end();
+      res_next = op.res_next; res_end = op.res_end;
       if (live) {
         // W/(pi h^3), dW/(pi h^4): F:125-126 (global smoothing) | V:139-140
         const double hn = P.variable_h ? hi : P.h_fixed;
