@@ -526,7 +526,7 @@ DensityArrays dens_arrays(sph_ctx* c) {
 }
 
 int run_density(sph_ctx* c) {
-  const int n = (int)c->n, W = 16;
+  const int n = (int)c->n, W = DENS_WARPS;
   stage_begin(c, ST_DENSITY);
   StateArrays s = state_of(c, c->cur);
   // pool of 32-int blocks for the saved candidate lists: about one block (30 sources) per local particle, grown
@@ -548,7 +548,7 @@ int run_density(sph_ctx* c) {
   return SPH_OK;
 }
 int run_hiter(sph_ctx* c) {
-  const int n = (int)c->n, W = 16;
+  const int n = (int)c->n, W = DENS_WARPS;
   c->nl_valid = false;                       // h changes: the saved lists' distance culls no longer hold
   stage_begin(c, ST_HITER);
   StateArrays s = state_of(c, c->cur);
@@ -878,10 +878,10 @@ int sph_create(const sph_params* p, int32_t device, sph_ctx** out) {
   int maxsm = 0; cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
   c->max_smem = maxsm;
   cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, device);
-  size_t need = std::max(std::max(density_smem(c, 16), std::max(force_smem(c, force_warps(c, true), true), force_smem(c, force_warps(c, false), false))), gravity_smem(c, GW_WARPS));
+  size_t need = std::max(std::max(density_smem(c, DENS_WARPS), std::max(force_smem(c, force_warps(c, true), true), force_smem(c, force_warps(c, false), false))), gravity_smem(c, GW_WARPS));
   if ((size_t)maxsm < need) { c->err = "device shared memory too small for the walk kernels"; return fail(SPH_ERR_CUDA); }
-  cudaFuncSetAttribute(k_density<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)density_smem(c, 16));
-  cudaFuncSetAttribute(k_density<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)density_smem(c, 16));
+  cudaFuncSetAttribute(k_density<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)density_smem(c, DENS_WARPS));
+  cudaFuncSetAttribute(k_density<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)density_smem(c, DENS_WARPS));
   cudaFuncSetAttribute(k_force<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)force_smem(c, force_warps(c, true), true));
   cudaFuncSetAttribute(k_force<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)force_smem(c, force_warps(c, false), false));
   cudaFuncSetAttribute(k_gravity, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gravity_smem(c, GW_WARPS));

@@ -18,6 +18,9 @@
 
 struct BvhInfo { int nlev; int off[12]; int cnt[12]; };
 
+#ifndef DENS_WARPS
+#define DENS_WARPS 16        // warps per block of the density kernels
+#endif
 #define WALK_STACK 224      // node stack entries per warp
 #define WALK_CQ    96       // chunk queue entries per warp
 #define WALK_TILE  32       // staged source particles per warp
@@ -319,7 +322,7 @@ struct DensityOp {
 
 // dynamic shared memory layout: [tables: 2*(nq+1) doubles][per warp: tile 8*WALK_TILE doubles][per warp: stack+cq]
 template <bool HITER>
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(DENS_WARPS * 32, 1)
 k_density(int n_groups, const int2* __restrict__ groups, DevParams P, DensityArrays A, const BvhBox* __restrict__ box, const __grid_constant__ BvhInfo bi,
           const double* __restrict__ g_wt, const double* __restrict__ g_dwt,
           const double* __restrict__ u, double* __restrict__ h,
