@@ -533,7 +533,9 @@ int run_density(sph_ctx* c) {
   // when an evaluation overflowed it (that evaluation's pair loop walks by itself instead)
   {
     const size_t want = (size_t)(c->p1 - c->p0) + 4 * (size_t)(c->g1 - c->g0) + 1024 + (size_t)NL_BATCH * 16 * c->n_sm;
-    if (want > c->nl_pool_blocks) { c->nl_pool_blocks = want + want / 4; DA(c->nl_pool, c->nl_pool_blocks * 32); }
+    if (c->nl_pool_blocks == 0 && getenv("SPH_B200_LIST_POOL_BLOCKS")) {      // test hook: start with a pool that is too small
+      c->nl_pool_blocks = (size_t)std::max(64, atoi(getenv("SPH_B200_LIST_POOL_BLOCKS"))); DA(c->nl_pool, c->nl_pool_blocks * 32);
+    } else if (want > c->nl_pool_blocks && !getenv("SPH_B200_LIST_POOL_BLOCKS")) { c->nl_pool_blocks = want + want / 4; DA(c->nl_pool, c->nl_pool_blocks * 32); }
     if ((size_t)c->n_groups + 1 > c->nl_head_cap) { c->nl_head_cap = (size_t)c->n_groups * 5 / 4 + 64; DA(c->nl_head, c->nl_head_cap); }
     CK(cudaMemsetAsync(c->nl_ctl, 0, 2 * sizeof(int), c->stream));      // ctl[2] (overflow) is sticky until the host has seen it
   }

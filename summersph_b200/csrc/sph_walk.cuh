@@ -26,7 +26,8 @@ struct BvhInfo { int nlev; int off[12]; int cnt[12]; };
 #define WALK_TILE  32       // staged source particles per warp
 #define WALK_WS    (WALK_STACK + WALK_CQ + WALK_TILE)   // unsigned words of walk state per warp
 #define PAIR_WIN   64       // compacted (target, source) hits evaluated per window, lane = pair
-#define DENS_WARP_DOUBLES (8 * WALK_TILE + 2 * WALK_TILE + 32)   // tile + float4 tile + saved-list buffer (64 ints)
+#define DENS_SLOTS (2 * WALK_TILE)                                 // tile slots: WALK_TILE consumed at a time + one chunk of overflow
+#define DENS_WARP_DOUBLES (8 * DENS_SLOTS + 2 * DENS_SLOTS + 32)    // tile + float4 tile + saved-list buffer (64 ints)
 
 #ifdef WALK_DEBUG
 __device__ unsigned long long wk_dbg[16];
@@ -89,6 +90,11 @@ __device__ void neighbour_walk(OP& op, const int2* __restrict__ groups, int chun
         const int sgx = __shfl_sync(FULL_MASK, mysg.x, qpos & 31), sgy = __shfl_sync(FULL_MASK, mysg.y, qpos & 31);
         ++qpos;
         const int j = sgx + lane;
+        if constexpr (OP::FUSED) {
+          tn += op.filter_stage(j, lane < sgy, tn);
+          if (tn >= WALK_TILE) break;
+          continue;
+        }
         const int fl = (lane < sgy) ? op.source_filter(j) : 0;
         if constexpr (OP::LISTS) op.list_append((fl & 2) != 0, j);
         const bool ok = (fl & 1) != 0;
@@ -123,6 +129,19 @@ __device__ void neighbour_walk(OP& op, const int2* __restrict__ groups, int chun
         qn += __popc(b0); sn += __popc(bn);
         __syncwarp();
       }
+    }
+    if constexpr (OP::FUSED) {
+      if (tn > 0) {
+        const int cnt = tn < WALK_TILE ? tn : WALK_TILE;
+        __syncwarp();
+        op.consume(cnt);
+        __syncwarp();
+        op.shift(tn - cnt);
+        tn -= cnt;
+        __syncwarp();
+      }
+      if (exhausted && tn == 0) break;
+      continue;
     }
     if (tn > 0) {
       __syncwarp();
@@ -173,6 +192,7 @@ template <bool PRODUCE>
 struct DensityOp {
   static const bool SYMMETRIC = PRODUCE;
   static const bool LISTS = PRODUCE;
+  static const bool FUSED = true;          // filter_stage() instead of source_filter() + stage()
   // saved-list state (PRODUCE): lbuf = 64 ints of shared memory per warp
   NeighbourListSink nl; int* lbuf; int ln, cur_blk, res_next, res_end; float grlo[3], grhi[3]; const double* hsrc; int variable_h; double h_fixed;
   // tile (per warp, shared memory): 8 arrays of WALK_TILE doubles
@@ -194,6 +214,48 @@ struct DensityOp {
 
   __device__ DensityOp(const DensityArrays& a) : A(a) {}
 
+  // Fused filter + stage (lane = source of one chunk): the values that decide the filter are the values the tile
+  // needs, so the passing lanes write them straight from registers into the tile slots [tn, tn + count) - no index
+  // list, no second (gathered) read.  The tile has 2 * WALK_TILE slots: the walk consumes the first WALK_TILE when
+  // they are full and shifts the rest down.  Returns how many sources were staged.
+  __device__ __forceinline__ int filter_stage(int j, bool in_range, int tn) {
+    const int lane = threadIdx.x & 31;
+    double R = -1.0, cx = 0.0, cy = 0.0, cz = 0.0, px = 0.0, py = 0.0, pz = 0.0, mj = 0.0, hj = h_fixed;
+    if (in_range) {
+      R = A.reach[j]; cx = A.lcx[j]; cy = A.lcy[j]; cz = A.lcz[j]; px = A.x[j]; py = A.y[j]; pz = A.z[j]; mj = A.m[j];
+      if (PRODUCE && variable_h) hj = hsrc[j];
+    }
+    const bool box = (R > 0.0) & (cx - R <= (double)gphi[0]) & (cx + R >= (double)gplo[0]) &
+                     (cy - R <= (double)gphi[1]) & (cy + R >= (double)gplo[1]) &
+                     (cz - R <= (double)gphi[2]) & (cz + R >= (double)gplo[2]);
+    const double ex = fmax(fmax((double)gplo[0] - px, px - (double)gphi[0]), 0.0), ey = fmax(fmax((double)gplo[1] - py, py - (double)gphi[1]), 0.0),
+                 ez = fmax(fmax((double)gplo[2] - pz, pz - (double)gphi[2]), 0.0);
+    const double e2 = ex * ex + ey * ey + ez * ez;
+    const bool ok = in_range & box & (!(e2 > g_r2max) | count_all);      // farther than 2 h_i from every target: W = 0 exactly
+    if (PRODUCE) {
+      const bool b = (px >= (double)grlo[0]) & (px <= (double)grhi[0]) & (py >= (double)grlo[1]) & (py <= (double)grhi[1]) &
+                     (pz >= (double)grlo[2]) & (pz <= (double)grhi[2]);
+      const bool nz = !(e2 > fmax(g_r2max, 4.0 * hj * hj * (1.0 + 1e-9)));
+      list_append(in_range & (box | b) & (nz | count_all), j);            // the pair loop's criterion (ForceOp::source_filter)
+    }
+    const unsigned bal = __ballot_sync(FULL_MASK, ok);
+    if (ok) {
+      const int s = tn + __popc(bal & ((1u << lane) - 1u));
+      sx[s] = px; sy[s] = py; sz[s] = pz; sm[s] = mj; scx[s] = cx; scy[s] = cy; scz[s] = cz; sR[s] = R;
+      ft[s] = make_float4((float)(px - g0x), (float)(py - g0y), (float)(pz - g0z), 0.f);
+    }
+    return __popc(bal);
+  }
+  // move the slots [WALK_TILE, WALK_TILE + rest) down to [0, rest)
+  __device__ __forceinline__ void shift(int rest) {
+    const int lane = threadIdx.x & 31;
+    const bool mv = lane < rest;
+    const int s = WALK_TILE + lane;
+    double v0 = 0, v1 = 0, v2 = 0, v3 = 0, v4 = 0, v5 = 0, v6 = 0, v7 = 0; float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (mv) { v0 = sx[s]; v1 = sy[s]; v2 = sz[s]; v3 = sm[s]; v4 = scx[s]; v5 = scy[s]; v6 = scz[s]; v7 = sR[s]; f = ft[s]; }
+    __syncwarp();
+    if (mv) { sx[lane] = v0; sy[lane] = v1; sz[lane] = v2; sm[lane] = v3; scx[lane] = v4; scy[lane] = v5; scz[lane] = v6; sR[lane] = v7; ft[lane] = f; }
+  }
   __device__ __forceinline__ int source_filter(int j) const {
     // all loads first (independent, one latency), then a branch-free decision
     const double R = A.reach[j], cx = A.lcx[j], cy = A.lcy[j], cz = A.lcz[j], px = A.x[j], py = A.y[j], pz = A.z[j];
@@ -351,10 +413,10 @@ k_density(int n_groups, const int2* __restrict__ groups, DevParams P, DensityArr
     const int i = tg.x + lane;
     const bool live = lane < tg.y;
     DensityOp<!HITER> op(A);
-    op.sx = tile; op.sy = tile + WALK_TILE; op.sz = tile + 2 * WALK_TILE; op.sm = tile + 3 * WALK_TILE;
-    op.scx = tile + 4 * WALK_TILE; op.scy = tile + 5 * WALK_TILE; op.scz = tile + 6 * WALK_TILE; op.sR = tile + 7 * WALK_TILE;
-    op.ft = reinterpret_cast<float4*>(tile + 8 * WALK_TILE);
-    op.lbuf = reinterpret_cast<int*>(tile + 10 * WALK_TILE);
+    op.sx = tile; op.sy = tile + DENS_SLOTS; op.sz = tile + 2 * DENS_SLOTS; op.sm = tile + 3 * DENS_SLOTS;
+    op.scx = tile + 4 * DENS_SLOTS; op.scy = tile + 5 * DENS_SLOTS; op.scz = tile + 6 * DENS_SLOTS; op.sR = tile + 7 * DENS_SLOTS;
+    op.ft = reinterpret_cast<float4*>(tile + 8 * DENS_SLOTS);
+    op.lbuf = reinterpret_cast<int*>(tile + 10 * DENS_SLOTS);
     op.nl = nl; op.hsrc = h; op.variable_h = P.variable_h; op.h_fixed = P.h_fixed; op.res_next = res_next; op.res_end = res_end;
     op.wt = wt; op.dwt = dwt; op.nq = P.nq; op.dq = P.dq; op.inv_dq = P.inv_dq;
     const BvhBox g = box[bi.off[0] + chunk];
@@ -448,6 +510,7 @@ struct ForceArrays {
 struct ForceOp {
   static const bool SYMMETRIC = true;
   static const bool LISTS = false;
+  static const bool FUSED = false;
   double* t;             // tile: FORCE_FIELDS arrays of WALK_TILE doubles
   int* tid;              // tile ids
   double* tg;            // the group's targets: FORCE_TG_FIELDS arrays of 32 doubles (x y z vx vy vz h 1/h 1/(pi h^4) rho c alpha P/(Omega rho^2)
@@ -713,6 +776,7 @@ k_force(int n_groups, const int2* __restrict__ groups, DevParams P, ForceArrays 
 struct NgbOp {
   static const bool SYMMETRIC = false;
   static const bool LISTS = false;
+  static const bool FUSED = false;
   double *scx, *scy, *scz, *sR; int* sid;
   const DensityArrays& A; const int* id;
   float gplo[3], gphi[3];

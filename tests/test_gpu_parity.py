@@ -375,3 +375,30 @@ def test_tree_reuse_is_bit_identical(mode, E, monkeypatch):
         assert np.array_equal(getattr(b0, k), getattr(b1, k)), k
     for k in ("x", "y", "z", "vx", "vy", "vz", "m"):
         assert np.array_equal(getattr(s0, k), getattr(s1, k)), k
+
+
+def test_candidate_list_pool_overflow_falls_back(E, monkeypatch):
+    """The density pass saves the pair loop's candidate lists in a pool of blocks.  A pool that is too small voids
+    the lists on the device: the walking pair kernel runs instead and the host doubles the pool for the next
+    step.  Either way each target adds the same terms in the same order, so the states are bit-identical."""
+    p = default_params(MODE_VARIABLE_H)
+    b, s = ics.keplerian_disc(30_000, seed=21)
+    out = []
+    for tiny in (False, True):
+        if tiny:
+            monkeypatch.setenv("SPH_B200_LIST_POOL_BLOCKS", "64")
+        else:
+            monkeypatch.delenv("SPH_B200_LIST_POOL_BLOCKS", raising=False)
+        with E(p) as e:
+            e.upload(b, s)
+            dt, t = 0.01, 0.0
+            for _ in range(3):
+                dt, t = e.step(dt, t)
+            e.evaluate()
+            out.append((dt, t, e.download()[0], e.diag()))
+    (dt0, t0, b0, d0), (dt1, t1, b1, d1) = out
+    assert (dt0, t0) == (dt1, t1)
+    for k in GAS_FIELDS:
+        assert np.array_equal(getattr(b0, k), getattr(b1, k)), k
+    for k in d0:
+        assert np.array_equal(d0[k], d1[k]), k
