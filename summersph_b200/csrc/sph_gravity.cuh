@@ -57,7 +57,8 @@ struct GravWarpSmem {
   int2     stack[GW_STACK];
   double2  lxy[GW_LIST], lzg[GW_LIST];     // (cx, cy), (cz, G*M)
   unsigned lmask[GW_LIST];
-  double   mcx[32], mcy[32], mcz[32], msize[32], mlo[32], mhi[32];   // mixed nodes of the current trip: COM, size, d2 band of the cheap test
+  double   mcx[32], mcy[32], mcz[32], msize[32], mlo[32], mhi[32];   // mixed nodes of the current trip: COM, size, d2 band of the cheap FP64 test
+  float4   mf[32];                                                   // the same nodes for the FP32 screen: COM relative to the run's origin, size^2 / theta^2
   unsigned mmask[32];
 };
 
@@ -139,6 +140,14 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
       const double lo0 = gb.plo[0], lo1 = gb.plo[1], lo2 = gb.plo[2], hi0 = gb.phi[0], hi1 = gb.phi[1], hi2 = gb.phi[2];
       const double soft_min = warp_min(live ? soft : INFINITY), soft_max = warp_max(live ? soft : 0.0);
       const unsigned livemask = __ballot_sync(FULL_MASK, live);
+      // FP32 screens (classification against the run's box, and the per-particle test on mixed nodes): coordinates
+      // relative to the box centre, 3e-5 margins (float rounding of d^2 stays below ~1e-6 relative because
+      // d^2 >= soft); whatever falls inside a margin is decided by the FP64 tests below, so no decision changes.
+      const double g0x = 0.5 * (lo0 + hi0), g0y = 0.5 * (lo1 + hi1), g0z = 0.5 * (lo2 + hi2);
+      const float hxf = __double2float_ru(0.5 * (hi0 - lo0)) * 1.00001f, hyf = __double2float_ru(0.5 * (hi1 - lo1)) * 1.00001f, hzf = __double2float_ru(0.5 * (hi2 - lo2)) * 1.00001f;
+      const float xif = (float)(xi - g0x), yif = (float)(yi - g0y), zif = (float)(zi - g0z);
+      const float softf = (float)soft, softf_min = __double2float_rd(soft_min), softf_max = __double2float_ru(soft_max);
+      const float th2f = (float)theta2, inv_th2f = (float)inv_theta2;
       int sn = 1, gsp = 0, ln = 0;
 #ifdef GW_DEBUG
       int dq_len = 0, dq_ring = 0;
@@ -178,17 +187,21 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
         // ---- lane = node: classify against the group box
         int cls = 0;                           // 1 all accept, 2 all open, 3 mixed
         double ncx = 0.0, ncy = 0.0, ncz = 0.0, nm = 0.0, nsize = 0.0; int nchild = 0, nnch = 0;
+        float rxf = 0.f, ryf = 0.f, rzf = 0.f, s2f = 0.f;
         if (valid) {
           const double2* p = reinterpret_cast<const double2*>(wn + e.x);
           const double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
           ncx = a.x; ncy = a.y; ncz = b.x; nm = b.y; nsize = c.x;
           nchild = __double2loint(c.y); nnch = __double2hiint(c.y);
-          const double nx = fmax(fmax(lo0 - ncx, ncx - hi0), 0.0), ny = fmax(fmax(lo1 - ncy, ncy - hi1), 0.0), nz = fmax(fmax(lo2 - ncz, ncz - hi2), 0.0);
-          const double fx = fmax(fabs(ncx - lo0), fabs(ncx - hi0)), fy = fmax(fabs(ncy - lo1), fabs(ncy - hi1)), fz = fmax(fabs(ncz - lo2), fabs(ncz - hi2));
-          const double dmin2 = nx * nx + ny * ny + nz * nz + soft_min, dmax2 = fx * fx + fy * fy + fz * fz + soft_max;
-          const double s2 = nsize * nsize;
-          if (nnch == 0 || s2 < theta2 * dmin2 * (1.0 - 1e-9)) cls = 1;
-          else if (s2 > theta2 * dmax2 * (1.0 + 1e-9)) cls = 2;
+          rxf = (float)(ncx - g0x); ryf = (float)(ncy - g0y); rzf = (float)(ncz - g0z);
+          const float axf = fabsf(rxf), ayf = fabsf(ryf), azf = fabsf(rzf);
+          const float nx = fmaxf(axf - hxf, 0.f), ny = fmaxf(ayf - hyf, 0.f), nz = fmaxf(azf - hzf, 0.f);
+          const float fx = axf + hxf, fy = ayf + hyf, fz = azf + hzf;
+          const float dmin2 = fmaf(nx, nx, fmaf(ny, ny, fmaf(nz, nz, softf_min))), dmax2 = fmaf(fx, fx, fmaf(fy, fy, fmaf(fz, fz, softf_max)));
+          const float szf = (float)nsize;
+          s2f = szf * szf;
+          if (nnch == 0 || s2f < th2f * dmin2 * (1.f - 3e-5f)) cls = 1;
+          else if (s2f > th2f * dmax2 * (1.f + 3e-5f)) cls = 2;
           else cls = 3;
         }
         const unsigned emask = (unsigned)e.y;
@@ -201,6 +214,7 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
           // size^2 < theta^2 d2 (1 - 1e-12)  <=>  d2 > size^2 / (theta^2 (1 - 1e-12)); the band in between gets the exact test
           const double s2t = nsize * nsize * inv_theta2;
           W.mhi[pos] = s2t * (1.0 + 2e-12); W.mlo[pos] = s2t * (1.0 - 2e-12);
+          W.mf[pos] = make_float4(rxf, ryf, rzf, s2f * inv_th2f);
         }
         __syncwarp();
         // ---- lane = particle: the reference's own test on the mixed nodes; the node's lane keeps the two ballots
@@ -211,13 +225,19 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
           const int L = __ffs(bm) - 1; bm &= bm - 1;
           const unsigned mm = W.mmask[q];
           const bool in = (mm >> lane) & 1u;
-          const double dx = xi - W.mcx[q], dy = yi - W.mcy[q], dz = zi - W.mcz[q];          // F:274
-          const double d2 = fma(dx, dx, fma(dy, dy, fma(dz, dz, soft)));
-          bool accept = d2 > W.mhi[q];
-          if (!accept && !(d2 < W.mlo[q])) {   // borderline: redo the reference's arithmetic exactly (no contraction)       F:275-278
-            const double size = W.msize[q];
-            const double e2 = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)), soft);
-            accept = __ddiv_rn(size, __dsqrt_rn(e2)) < theta;
+          const float4 mq = W.mf[q];
+          const float dxf = xif - mq.x, dyf = yif - mq.y, dzf = zif - mq.z;
+          const float d2f = fmaf(dxf, dxf, fmaf(dyf, dyf, fmaf(dzf, dzf, softf)));
+          bool accept = d2f > mq.w * (1.f + 3e-5f);
+          if (!accept && !(d2f < mq.w * (1.f - 3e-5f))) {       // inside the float margin: the FP64 test
+            const double dx = xi - W.mcx[q], dy = yi - W.mcy[q], dz = zi - W.mcz[q];          // F:274
+            const double d2 = fma(dx, dx, fma(dy, dy, fma(dz, dz, soft)));
+            accept = d2 > W.mhi[q];
+            if (!accept && !(d2 < W.mlo[q])) {   // borderline: redo the reference's arithmetic exactly (no contraction)       F:275-278
+              const double size = W.msize[q];
+              const double e2 = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)), soft);
+              accept = __ddiv_rn(size, __dsqrt_rn(e2)) < theta;
+            }
           }
           const unsigned balAcc = __ballot_sync(FULL_MASK, in && accept), balOpen = __ballot_sync(FULL_MASK, in && !accept);
           if (lane == L) { acc_mask = balAcc; open_mask = balOpen; }
