@@ -5,19 +5,21 @@
 //
 // The reference's opening decision is per particle: `size/dist < theta .or. no children` with
 // dist = sqrt(|x - COM|^2 + 0.001*smoothing) (F:275-278), and every accepted-node set stays identical to it.
-// What changes is who decides.  One warp owns a walk group (<= 32 Morton-adjacent particles in one octree
-// cell, lane = particle) and keeps a stack of (node, lane mask) entries in shared memory.  Each trip pops up
-// to 32 entries and classifies them lane-parallel against the group's bounding box (lane = node, one
-// coalesced 48-byte load each, child blocks are contiguous in the walk layout):
-//   * every particle of the group accepts (even the closest point of the box passes the test with a 1e-9
-//     margin, or the node is childless)            -> interaction list, mask unchanged;
+// What changes is who decides.  One warp owns a run of 32 Morton-consecutive particles (lane = particle; the runs
+// restart at every 64th walk group, see k_seg_chunks) and keeps a stack of (node, lane mask) entries in shared
+// memory.  Each trip pops up to 32 entries and classifies them lane-parallel against the run's bounding box
+// (lane = node, one coalesced 48-byte load each, child blocks are contiguous in the walk layout) - in FP32 on
+// box-relative coordinates with 3e-5 margins, since anything uncertain is simply "mixed":
+//   * every particle of the run accepts (even the closest point of the box passes the test, or the node is
+//     childless)                                   -> interaction list, mask unchanged;
 //   * every particle opens (even the farthest point fails it)  -> push the child block, mask unchanged;
-//   * otherwise the node is mixed: each particle in the mask runs the reference's own test (cheap form with
-//     a 1e-12 guard band, exact uncontracted arithmetic inside the band); the accepting lanes become the
-//     list entry's mask, the opening lanes the mask of the pushed children.
-// The interaction list (COM, G*M, mask) is evaluated in batches with lane = particle, so the force
-// arithmetic runs with every live lane busy and node data are read once per group instead of once per
-// particle.  The accumulation order differs from the reference's recursion order (rounding-level only).
+//   * otherwise the node is mixed: each particle in the mask runs the reference's own test (FP32 screen, then
+//     the FP64 form with a 2e-12 guard band, then the exact uncontracted arithmetic inside the band); the node's
+//     lane collects the two ballots: the accepting lanes become the list entry's mask, the opening lanes the
+//     mask of the pushed children.  One list insert and one child push per trip serve all three classes.
+// The interaction list (COM, G*M, mask) is evaluated in batches with lane = particle (18 FP64 instructions per
+// entry, two entries in flight per lane), node data read once per run instead of once per particle.  The
+// accumulation order differs from the reference's recursion order (rounding-level only).
 #pragma once
 #include "sph_common.cuh"
 #include "sph_walk.cuh"
@@ -244,11 +246,7 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
         }
         // ---- lane = node again: accepted (node, lane set) pairs join the interaction list, opened ones push their child block
         n_acc += __popc(acc_mask); n_open += __popc(open_mask);
-#ifdef GW_SKIP_T
-        const bool ins = acc_mask != 0u && nm > 0.0 && __popc(acc_mask) >= GW_SKIP_T;   // timing experiment only: drops the sparse entries (wrong forces)
-#else
         const bool ins = acc_mask != 0u && nm > 0.0;                                // F:279: massless nodes add nothing
-#endif
         const unsigned balL = __ballot_sync(FULL_MASK, ins);
         if (ins) {
           const int pos = ln + __popc(balL & lt_mask);

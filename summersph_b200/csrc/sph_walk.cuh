@@ -7,12 +7,15 @@
 // Membership is the reference's, bit for bit: j is a candidate of i iff the leaf box test
 //     all_k |x_i,k - c_leaf(j),k| < 2 h_j + size_leaf(j)/2          (F:443 | V:479)
 // passes (h_j = the value in the tree = at build time; F: the global smoothing), evaluated in FP64 with
-// the same operations.  HOW candidates are found is free: one warp owns a chunk of 32 Morton-adjacent
-// targets (lane = target), walks the implicit 8-ary BVH of chunk boxes with a shared-memory stack (8 child
-// boxes per popped node tested by 8 lanes, coalesced), stages the surviving source particles of each hit
-// chunk into a shared-memory tile, and every lane then runs the exact box test against the tile and the
-// kernel arithmetic for its own hits.  The pair force is evaluated in gather form:
-// each particle sums its own side, no atomics, every term equal to the reference's term.
+// the same operations.  HOW candidates are found is free: one warp owns a walk group of <= 32 Morton-adjacent
+// targets (lane = target), walks the implicit 8-ary BVH of group boxes with a shared-memory stack (8 child
+// boxes per popped node tested by 8 lanes, coalesced), filters the source particles of each hit group
+// (lane = source) into a shared-memory tile, and consumes the tile: an FP32 prefilter (could any term be
+// non-zero?) followed by the exact FP64 leaf-box test and the kernel arithmetic on the survivors.  The density
+// pass also saves, per group, the candidate list the pair loop needs (NeighbourListSink), so the pair loop of
+// the same evaluation streams that list instead of walking again; it evaluates its hits with lane = pair
+// (compacted hit list) and in gather form: each particle sums its own side, no
+// atomics, every term equal to the reference's term, per-target sums in a fixed order.
 #pragma once
 #include "sph_common.cuh"
 
