@@ -584,8 +584,15 @@ int run_force(sph_ctx* c) {
   if (c->n_ranks > 1) { stage_begin(c, ST_COMM); double* bufs[5] = {c->ax, c->ay, c->az, c->udot, c->adot}; int r_ = allgatherv(c, bufs, 5); if (r_) return r_; stage_end(c); }
   return SPH_OK;
 }
+int grav_warps(const sph_ctx* c);
 size_t gravity_smem(const sph_ctx* c, int nwarp) { return (size_t)((c->p.nq + 1) + ((c->p.nq + 1) & 1)) * 8 + (size_t)nwarp * sizeof(GravWarpSmem); }
+int grav_warps(const sph_ctx* c) {     // as many warps (<= GW_WARPS) as the shared memory beside the kernel table holds
+  int w = GW_WARPS;
+  while (w > 1 && gravity_smem(c, w) > (size_t)c->max_smem) --w;
+  return w;
+}
 int run_gravity(sph_ctx* c, int do_grav, int do_sinks) {
+  const int GWW = grav_warps(c);
   stage_begin(c, ST_GRAVITY);
   StateArrays s = state_of(c, c->cur);
 #if GRAV_CHUNK_WIDTH > 0
@@ -601,7 +608,7 @@ int run_gravity(sph_ctx* c, int do_grav, int do_sinks) {
     DA(c->sink_partial, c->sink_partial_cap);
   }
   if (ng > 0 && c->g1 > c->g0) {
-    const int grid = std::max(1, std::min(cdiv(ng, GW_WARPS), c->n_sm));
+    const int grid = std::max(1, std::min(cdiv(ng, GWW), c->n_sm));
     if (!c->grav_spill) DA(c->grav_spill, (size_t)c->n_sm * GW_WARPS * GW_SPILL);
 #if GRAV_CHUNK_WIDTH > 0
     if (!c->grav_groups_valid) {
@@ -616,11 +623,11 @@ int run_gravity(sph_ctx* c, int do_grav, int do_sinks) {
       c->grav_groups_valid = true;
     }
     LAUNCH(k_set_int, 1, 1, 0, c->work, 0);
-    LAUNCH(k_gravity, grid, GW_WARPS * 32, gravity_smem(c, GW_WARPS), 0, ng, c->ggroups, c->gbvh, c->dp, c->wnodes, s.x, s.y, s.z, s.h, s.m, c->d_gt,
+    LAUNCH(k_gravity, grid, GWW * 32, gravity_smem(c, GWW), 0, ng, c->ggroups, c->gbvh, c->dp, c->wnodes, s.x, s.y, s.z, s.h, s.m, c->d_gt,
            c->ax, c->ay, c->az, do_grav, ns, c->S, c->sink_partial, c->ctr, c->work, c->grav_spill, &c->sc->err);
 #else
     LAUNCH(k_set_int, 1, 1, 0, c->work, c->g0);
-    LAUNCH(k_gravity, grid, GW_WARPS * 32, gravity_smem(c, GW_WARPS), c->g0, c->g1, c->groups, c->bvh, c->dp, c->wnodes, s.x, s.y, s.z, s.h, s.m, c->d_gt,
+    LAUNCH(k_gravity, grid, GWW * 32, gravity_smem(c, GWW), c->g0, c->g1, c->groups, c->bvh, c->dp, c->wnodes, s.x, s.y, s.z, s.h, s.m, c->d_gt,
            c->ax, c->ay, c->az, do_grav, ns, c->S, c->sink_partial, c->ctr, c->work, c->grav_spill, &c->sc->err);
 #endif
   }
@@ -880,13 +887,13 @@ int sph_create(const sph_params* p, int32_t device, sph_ctx** out) {
   int maxsm = 0; cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
   c->max_smem = maxsm;
   cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, device);
-  size_t need = std::max(std::max(density_smem(c, DENS_WARPS), std::max(force_smem(c, force_warps(c, true), true), force_smem(c, force_warps(c, false), false))), gravity_smem(c, GW_WARPS));
+  size_t need = std::max(std::max(density_smem(c, DENS_WARPS), std::max(force_smem(c, force_warps(c, true), true), force_smem(c, force_warps(c, false), false))), gravity_smem(c, grav_warps(c)));
   if ((size_t)maxsm < need) { c->err = "device shared memory too small for the walk kernels"; return fail(SPH_ERR_CUDA); }
   cudaFuncSetAttribute(k_density<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)density_smem(c, DENS_WARPS));
   cudaFuncSetAttribute(k_density<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)density_smem(c, DENS_WARPS));
   cudaFuncSetAttribute(k_force<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)force_smem(c, force_warps(c, true), true));
   cudaFuncSetAttribute(k_force<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)force_smem(c, force_warps(c, false), false));
-  cudaFuncSetAttribute(k_gravity, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gravity_smem(c, GW_WARPS));
+  cudaFuncSetAttribute(k_gravity, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gravity_smem(c, grav_warps(c)));
   cudaFuncSetAttribute(k_neighbours, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   if (cudaGetLastError() != cudaSuccess) { c->err = "cudaFuncSetAttribute failed (was the library built for this GPU's architecture?)"; return fail(SPH_ERR_CUDA); }
   *out = c;
