@@ -74,7 +74,7 @@ struct sph_ctx {
   unsigned char* keep = nullptr; unsigned long long* acc_key[2] = {}; int* acc_val[2] = {}; int* d_nsel = nullptr;
   int* pos = nullptr;           // ascending-number position of each sorted particle (downloads)
   double* stage_d = nullptr; double* stage_d2 = nullptr; int stage_flip = 0;   // device staging for ordered downloads
-  bool tree_valid = false; bool pos_moved = true; int tree_reuse = 1; int use_lists = 1; int nl_exact = 0; int exact_counters = 0;   // pos_moved: positions / particle set changed since the last build
+  bool tree_valid = false; bool pos_moved = true; int tree_reuse = 1; int use_lists = 1; int fused_push = 1; int nl_exact = 0; int exact_counters = 0;   // pos_moved: positions / particle set changed since the last build
   sph_counts counts; double stage_ms[ST_COUNT] = {};
   std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> ev_used; std::vector<cudaEvent_t> ev_pool;
   int64_t launches = 0;
@@ -570,18 +570,36 @@ int run_force(sph_ctx* c) {
   const NeighbourListSink nl{c->nl_pool, c->nl_head, c->nl_ctl, (int)std::min<size_t>(c->nl_pool_blocks, 0x7fffffff)};
   const bool listed = c->nl_valid && c->nl_exact == c->exact_counters && c->use_lists;
   const int WL = force_warps(c, true), WW = force_warps(c, false);
+  // peers' copies of the five output arrays: the kernel pushes its results itself (exchanged_arrays slots 3..7)
+  PeerOut po; po.n = 0;
+  if (c->n_ranks > 1) {
+    if (c->p2p_stale) { int r_ = p2p_setup(c); if (r_) return r_; }
+    if (c->p2p_ok && c->n_ranks - 1 <= SPH_MAX_PEERS && c->fused_push) {
+      for (int k = 1; k < c->n_ranks; ++k) {
+        const int r = (c->rank + k) % c->n_ranks;
+        for (int f = 0; f < 5; ++f) po.p[po.n][f] = c->peer[3 + f][r];
+        ++po.n;
+      }
+    }
+  }
   if (listed) {
     LAUNCH(k_set_int, 1, 1, 0, c->work, c->g0);
-    LAUNCH(k_force<true>, walk_grid(c, WL), WL * 32, force_smem(c, WL, true), c->g1, c->groups, c->dp, A, c->bvh, c->bi, c->d_dwt, c->ax, c->ay, c->az, c->udot, c->adot, c->ctr, c->work, c->exact_counters, nl, 0);
+    LAUNCH(k_force<true>, walk_grid(c, WL), WL * 32, force_smem(c, WL, true), c->g1, c->groups, c->dp, A, c->bvh, c->bi, c->d_dwt, c->ax, c->ay, c->az, c->udot, c->adot, c->ctr, c->work, c->exact_counters, nl, 0, po);
   }
   LAUNCH(k_set_int, 1, 1, 0, c->work, c->g0);
-  LAUNCH(k_force<false>, walk_grid(c, WW), WW * 32, force_smem(c, WW, false), c->g1, c->groups, c->dp, A, c->bvh, c->bi, c->d_dwt, c->ax, c->ay, c->az, c->udot, c->adot, c->ctr, c->work, c->exact_counters, nl, listed ? 1 : 0);
+  LAUNCH(k_force<false>, walk_grid(c, WW), WW * 32, force_smem(c, WW, false), c->g1, c->groups, c->dp, A, c->bvh, c->bi, c->d_dwt, c->ax, c->ay, c->az, c->udot, c->adot, c->ctr, c->work, c->exact_counters, nl, listed ? 1 : 0, po);
   stage_end(c);
 #ifdef WALK_DEBUG
   { unsigned long long d[16]; cudaStreamSynchronize(c->stream); cudaMemcpyFromSymbol(d, wk_dbg, sizeof(d)); unsigned long long z[16] = {}; cudaMemcpyToSymbol(wk_dbg, z, sizeof(z));
     fprintf(stderr, "WKDBG groups %d force: tiles %llu staged %llu trips %llu hits %llu boxpairs %llu | density: tiles %llu staged %llu trips %llu hits %llu\n", c->n_groups, d[0], d[1], d[2], d[3], d[4], d[8], d[9], d[10], d[11]); }
 #endif
-  if (c->n_ranks > 1) { stage_begin(c, ST_COMM); double* bufs[5] = {c->ax, c->ay, c->az, c->udot, c->adot}; int r_ = allgatherv(c, bufs, 5); if (r_) return r_; stage_end(c); }
+  if (c->n_ranks > 1) {
+    stage_begin(c, ST_COMM);
+    if (po.n > 0) {     // the kernels pushed their slices themselves: only the "every rank's kernel has finished" barrier is left
+      NC(c->nccl.AllReduce(c->d_flag + 2, c->d_flag + 2, 1, 2 /*ncclInt32*/, NC_SUM, c->comm, c->stream));
+    } else { double* bufs[5] = {c->ax, c->ay, c->az, c->udot, c->adot}; int r_ = allgatherv(c, bufs, 5); if (r_) return r_; }
+    stage_end(c);
+  }
   return SPH_OK;
 }
 int grav_warps(const sph_ctx* c);
@@ -863,6 +881,7 @@ int sph_create(const sph_params* p, int32_t device, sph_ctx** out) {
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { c->err = "stream create failed"; return fail(SPH_ERR_CUDA); }
   make_dev_params(c);
   c->tree_reuse = getenv("SPH_B200_NO_TREE_REUSE") ? 0 : 1;
+  c->fused_push = getenv("SPH_B200_NO_FUSED_PUSH") ? 0 : 1;     // developer switch: copy-engine exchange after the pair kernel
   c->use_lists = getenv("SPH_B200_NO_LISTS") ? 0 : 1;            // developer switch: the pair loop always walks by itself     // developer switch: rebuild the tree in every evaluation
   int r;
   if ((r = upload_tables(c))) return fail(r);

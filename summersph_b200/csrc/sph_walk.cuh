@@ -681,6 +681,13 @@ struct ForceOp {
   }
 };
 
+// Multi-GPU: the pair kernel is the last writer of a, du/dt and d(alpha)/dt, and every rank needs them for all
+// particles (replicated integration).  Instead of copying the finished slice afterwards, the kernel stores each value
+// into every peer's copy of the arrays as it is produced (peer-mapped pointers, NVLink stores), so the exchange
+// overlaps the walk and only a barrier remains after the kernel.
+#define SPH_MAX_PEERS 7
+struct PeerOut { int n; double* p[SPH_MAX_PEERS][5]; };
+
 // LISTED: stream the group's saved candidate chain (written by the density pass of this evaluation) instead of
 // walking the BVH and filtering the sources again; runs only while the lists are usable (nl.ctl[1] == 0).
 // !LISTED: the walking form; with only_if_void it runs only when the lists were declared void on the device.
@@ -688,7 +695,7 @@ template <bool LISTED>
 __global__ void __launch_bounds__(512, 1)
 k_force(int n_groups, const int2* __restrict__ groups, DevParams P, ForceArrays A, const BvhBox* __restrict__ box, const __grid_constant__ BvhInfo bi, const double* __restrict__ g_dwt,
         double* __restrict__ ax, double* __restrict__ ay, double* __restrict__ az, double* __restrict__ udot,
-        double* __restrict__ adot, WalkCounters* ctr, int* work, int count_all, NeighbourListSink nl, int only_if_void) {
+        double* __restrict__ adot, WalkCounters* ctr, int* work, int count_all, NeighbourListSink nl, int only_if_void, const __grid_constant__ PeerOut po) {
   if (LISTED) { if (nl.ctl[1] != 0) return; }
   else if (only_if_void && nl.ctl[1] == 0) return;
   extern __shared__ double smem[];
@@ -762,10 +769,13 @@ k_force(int n_groups, const int2* __restrict__ groups, DevParams P, ForceArrays 
       neighbour_walk(op, groups, chunk, box, bi, stack, cq);
     }
     if (live) {
-      ax[i] += op.ax; ay[i] += op.ay; az[i] += op.az;
-      udot[i] += op.ud;
+      const double vax = ax[i] + op.ax, vay = ay[i] + op.ay, vaz = az[i] + op.az, vud = udot[i] + op.ud;
       // alpha-rate clean-up F:316-318 | V:345-347
-      adot[i] = fmax(op.ad / rhoi, 0.0) + P.lit_015 * ((0.1 - alphai) * ci / hi);
+      const double vad = fmax(op.ad / rhoi, 0.0) + P.lit_015 * ((0.1 - alphai) * ci / hi);
+      ax[i] = vax; ay[i] = vay; az[i] = vaz; udot[i] = vud; adot[i] = vad;
+      for (int r = 0; r < po.n; ++r) {
+        po.p[r][0][i] = vax; po.p[r][1][i] = vay; po.p[r][2][i] = vaz; po.p[r][3][i] = vud; po.p[r][4][i] = vad;
+      }
     }
     tot_pairs += op.pairs;
   }
