@@ -48,9 +48,11 @@ __device__ __forceinline__ bool box_overlap(const float* alo, const float* ahi, 
 // Generic warp walk. OP interface:
 //   static const bool SYMMETRIC;                     // also accept sources lying inside the group's reach box
 //   static const bool LISTS;                         // the op also saves a candidate list for a later pass (list_append)
+//   static const bool FUSED;                         // filter_stage() instead of source_filter() + stage()
 //   int    source_filter(int j)                      // per-source prefilter against the group (lane = source):
 //                                                    // bit 0 = stage into the tile, bit 1 = append to the saved list
 //   void   stage(int slot, int j)                    // copy source j into tile slot
+//   int    filter_stage(int j, bool in_range, int tn), void shift(int rest)    // FUSED: both at once, 2-tile slots
 //   void   consume(int count)                        // all lanes process tile[0..count)
 template <class OP>
 __device__ void neighbour_walk(OP& op, const int2* __restrict__ groups, int chunk, const BvhBox* __restrict__ box, const BvhInfo& bi,
@@ -97,17 +99,18 @@ __device__ void neighbour_walk(OP& op, const int2* __restrict__ groups, int chun
           tn += op.filter_stage(j, lane < sgy, tn);
           if (tn >= WALK_TILE) break;
           continue;
+        } else {
+          const int fl = (lane < sgy) ? op.source_filter(j) : 0;
+          if constexpr (OP::LISTS) op.list_append((fl & 2) != 0, j);
+          const bool ok = (fl & 1) != 0;
+          const unsigned bal = __ballot_sync(FULL_MASK, ok);
+          const int cntc = __popc(bal);
+          if (cntc == 0) continue;
+          if (tn + cntc > WALK_TILE) { pend_cnt = cntc; pend_bal = bal; pend_j = j; pend_ok = ok; break; }
+          if (ok) tix[tn + __popc(bal & lt)] = (unsigned)j;
+          tn += cntc;
+          continue;
         }
-        const int fl = (lane < sgy) ? op.source_filter(j) : 0;
-        if constexpr (OP::LISTS) op.list_append((fl & 2) != 0, j);
-        const bool ok = (fl & 1) != 0;
-        const unsigned bal = __ballot_sync(FULL_MASK, ok);
-        const int cntc = __popc(bal);
-        if (cntc == 0) continue;
-        if (tn + cntc > WALK_TILE) { pend_cnt = cntc; pend_bal = bal; pend_j = j; pend_ok = ok; break; }
-        if (ok) tix[tn + __popc(bal & lt)] = (unsigned)j;
-        tn += cntc;
-        continue;
       }
       // chunk queue drained: refill it from the node stack (4 nodes x 8 child boxes per trip, coalesced)
       qn = 0; qpos = 0;
@@ -144,17 +147,17 @@ __device__ void neighbour_walk(OP& op, const int2* __restrict__ groups, int chun
         __syncwarp();
       }
       if (exhausted && tn == 0) break;
-      continue;
+    } else {
+      if (tn > 0) {
+        __syncwarp();
+        if (lane < tn) op.stage(lane, (int)tix[lane]);
+        __syncwarp();
+        op.consume(tn);
+        tn = 0;
+        __syncwarp();
+      }
+      if (exhausted && !pend_cnt) break;
     }
-    if (tn > 0) {
-      __syncwarp();
-      if (lane < tn) op.stage(lane, (int)tix[lane]);
-      __syncwarp();
-      op.consume(tn);
-      tn = 0;
-      __syncwarp();
-    }
-    if (exhausted && !pend_cnt) break;
   }
 }
 
@@ -259,29 +262,6 @@ struct DensityOp {
     __syncwarp();
     if (mv) { sx[lane] = v0; sy[lane] = v1; sz[lane] = v2; sm[lane] = v3; scx[lane] = v4; scy[lane] = v5; scz[lane] = v6; sR[lane] = v7; ft[lane] = f; }
   }
-  __device__ __forceinline__ int source_filter(int j) const {
-    // all loads first (independent, one latency), then a branch-free decision
-    const double R = A.reach[j], cx = A.lcx[j], cy = A.lcy[j], cz = A.lcz[j], px = A.x[j], py = A.y[j], pz = A.z[j];
-    double hj = h_fixed;
-    if (PRODUCE && variable_h) hj = hsrc[j];
-    const bool box = (R > 0.0) & (cx - R <= (double)gphi[0]) & (cx + R >= (double)gplo[0]) &
-                     (cy - R <= (double)gphi[1]) & (cy + R >= (double)gplo[1]) &
-                     (cz - R <= (double)gphi[2]) & (cz + R >= (double)gplo[2]);
-    // farther than 2 h_i from every target of the group: W = 0 exactly for all of them
-    const double ex = fmax(fmax((double)gplo[0] - px, px - (double)gphi[0]), 0.0), ey = fmax(fmax((double)gplo[1] - py, py - (double)gphi[1]), 0.0),
-                 ez = fmax(fmax((double)gplo[2] - pz, pz - (double)gphi[2]), 0.0);
-    const double e2 = ex * ex + ey * ey + ez * ez;
-    int fl = (box & (!(e2 > g_r2max) | count_all)) ? 1 : 0;
-    if (PRODUCE) {
-      // the pair loop's criterion (ForceOp::source_filter): j's box reaches a target, or j sits inside a target's box,
-      // and j is not farther than 2 max(h_i, h_j) from every target
-      const bool b = (px >= (double)grlo[0]) & (px <= (double)grhi[0]) & (py >= (double)grlo[1]) & (py <= (double)grhi[1]) &
-                     (pz >= (double)grlo[2]) & (pz <= (double)grhi[2]);
-      const bool nz = !(e2 > fmax(g_r2max, 4.0 * hj * hj * (1.0 + 1e-9)));
-      fl |= ((box | b) & (nz | count_all)) ? 2 : 0;
-    }
-    return fl;
-  }
   // ---- saved list: append the flagged sources of one chunk (lane = source), flushing full blocks to the pool
   // blocks are taken from the pool NL_BATCH at a time per warp (one returning atomic per batch, not per block)
   __device__ __forceinline__ int take_block() {
@@ -328,12 +308,6 @@ struct DensityOp {
     }
   }
   __device__ __forceinline__ void list_end() { __syncwarp(); list_flush(ln, true); __syncwarp(); }
-  __device__ __forceinline__ void stage(int s, int j) {
-    const double px = A.x[j], py = A.y[j], pz = A.z[j];
-    sx[s] = px; sy[s] = py; sz[s] = pz; sm[s] = A.m[j];
-    scx[s] = A.lcx[j]; scy[s] = A.lcy[j]; scz[s] = A.lcz[j]; sR[s] = A.reach[j];
-    ft[s] = make_float4((float)(px - g0x), (float)(py - g0y), (float)(pz - g0z), 0.f);
-  }
   __device__ __forceinline__ void consume(int count) {
     // Prefilter, lane = target, FP32 on group-relative coordinates: |x_i - x_j|^2 against 4 h_i^2 with a 1e-4 margin
     // (float rounding is ~1e-6 of the limit).  Beyond it W(q > 2) = 0 exactly (F:112), so it only drops exact zeros;
