@@ -15,38 +15,28 @@
 #include <vector>
 #include <fstream>
 #include <sstream>
-#include <sys/stat.h>
 
 #include "../include/sph_b200.h"
+#include "../include/sph_textio.h"
 
 struct Table { std::vector<double> c[10]; std::vector<double> s[8]; };
 
 static bool read_data_from_file(const std::string& fn, const sph_params& p, Table& t) {    // F:594-716
-  std::ifstream f(fn);
-  if (!f) { std::fprintf(stderr, " Error opening file: %s\n", fn.c_str()); return false; }
-  std::string line;
-  std::getline(f, line);                                                                   // header, F:617
-  const bool variable = p.mode & SPH_MODE_VARIABLE_H;
-  size_t row = 0;
-  while (std::getline(f, line)) {
-    std::istringstream is(line);
-    double v[10]; int k = 0;
-    while (k < 10 && (is >> v[k])) ++k;
-    if (k == 0) break;
-    ++row;
-    if (k < 8) { std::fprintf(stderr, " Error reading line %zu\n", row); return false; }
-    if (v[6] == 0.0) {                                                                     // sink, F:659
-      const double sv[8] = {v[0], v[1], v[2], v[3], v[4], v[5], v[7], p.sink_radius};
-      for (int q = 0; q < 8; ++q) t.s[q].push_back(sv[q]);
-    } else {
-      if (variable && k < 10) { std::fprintf(stderr, " Error reading line %zu\n", row); return false; }
-      for (int q = 0; q < 8; ++q) t.c[q].push_back(v[q]);
-      t.c[8].push_back(variable ? v[8] : 0.0);                                             // F:681
-      t.c[9].push_back(variable ? v[9] : p.h_fixed);
-    }
+  // host-parallel parser (include/sph_textio.h): header skipped, 8 | 10 columns, u == 0 rows are sinks, dummy sink if none
+  sph_ics* ics = nullptr;
+  if (sph_ics_open(fn.c_str(), (p.mode & SPH_MODE_VARIABLE_H) ? 1 : 0, p.h_fixed, p.sink_radius, 0, &ics)) {
+    std::fprintf(stderr, " %s\n", sph_textio_last_error());
+    return false;
   }
-  if (row == 0) { std::fprintf(stderr, " No data found in file: %s\n", fn.c_str()); return false; }
-  std::printf(" Successfully read %zu bodies and %zu sinks from %s.\n", t.c[0].size(), t.s[0].empty() ? (size_t)1 : t.s[0].size(), fn.c_str());
+  int64_t n = 0; int32_t ns = 0;
+  sph_ics_sizes(ics, &n, &ns);
+  for (auto& v : t.c) v.resize((size_t)n);
+  for (auto& v : t.s) v.resize((size_t)ns);
+  sph_ics_fetch(ics, t.c[0].data(), t.c[1].data(), t.c[2].data(), t.c[3].data(), t.c[4].data(), t.c[5].data(), t.c[6].data(), t.c[7].data(),
+                t.c[8].data(), t.c[9].data(), t.s[0].data(), t.s[1].data(), t.s[2].data(), t.s[3].data(), t.s[4].data(), t.s[5].data(),
+                t.s[6].data(), t.s[7].data());
+  sph_ics_close(ics);
+  std::printf(" Successfully read %lld bodies and %d sinks from %s.\n", (long long)n, (int)ns, fn.c_str());   // F:714
   return true;
 }
 
@@ -76,17 +66,13 @@ static bool make_save(sph_ctx* ctx, const sph_params& p, int number, const std::
                    c[8].data(), c[9].data(), s[0].data(), s[1].data(), s[2].data(), s[3].data(), s[4].data(), s[5].data(),
                    s[6].data(), s[7].data())) return false;
   const std::string fn = dir + "/save" + std::to_string(number) + ".txt";
-  struct stat st;
-  if (stat(fn.c_str(), &st) == 0) { std::fprintf(stderr, "%s exists (status=\"new\")\n", fn.c_str()); return false; }   // F:728
-  FILE* f = std::fopen(fn.c_str(), "w");
-  if (!f) return false;
-  const bool variable = p.mode & SPH_MODE_VARIABLE_H;
-  std::fprintf(f, " x  y  z  vx  vy vz energy mass  alpha  %s\n", variable ? "smoothing" : "");
-  const int nc = variable ? 10 : 9;
-  for (int64_t i = 0; i < n; ++i) { for (int q = 0; q < nc; ++q) std::fprintf(f, "%25.17E", c[q][i]); std::fputc('\n', f); }
-  for (int i = 0; i < ns; ++i)
-    std::fprintf(f, "%25.17E%25.17E%25.17E%25.17E%25.17E%25.17E%25.17E%25.17E\n", s[0][i], s[1][i], s[2][i], s[3][i], s[4][i], s[5][i], 0.0, s[6][i]);
-  std::fclose(f);
+  // an existing file is an error like status="new" (F:728); rows formatted and written by all host cores
+  if (sph_save_write(fn.c_str(), (p.mode & SPH_MODE_VARIABLE_H) ? 1 : 0, n, c[0].data(), c[1].data(), c[2].data(), c[3].data(), c[4].data(),
+                     c[5].data(), c[6].data(), c[7].data(), c[8].data(), c[9].data(), ns, s[0].data(), s[1].data(), s[2].data(), s[3].data(),
+                     s[4].data(), s[5].data(), s[6].data(), 0)) {
+    std::fprintf(stderr, "%s\n", sph_textio_last_error());
+    return false;
+  }
   return true;
 }
 
