@@ -6,7 +6,9 @@
 One "step" = one body of the reference loop (SUMMER_SPH - Variable.f90:1120-1162): two full evaluations
 (tree + density + EOS + gravity + sinks + SPH pairs), two half kicks, drift, dt ladder, h Newton-Raphson,
 sink creation, accretion, bounds cull.  N = 1 workload: BASELINE.json configs[3] (Keplerian disc, 16M gas
-particles + central sink, variable h, FP64).  Prints ONE JSON line (see README / DESIGN.md §Measurement).
+particles + central sink, variable h, FP64).  Prints ONE JSON line (see README / DESIGN.md §Measurement); it is
+the LAST line of stdout: with NCCL_DEBUG=VERSION in the environment (the GPU boxes set it) NCCL itself prints its
+version banner on stdout once when the first communicator of a multi-rank run is created.
 
 --impl reference times the CPU implementation of the same path (the oracle port of the Fortran loops —
 no Fortran compiler exists in this image, so the reference itself cannot be built) on the host cores.
