@@ -3,7 +3,10 @@
 // C-ABI of include/sph_b200.h.  It exists because this image has no Fortran compiler; the Fortran host
 // host/run_sph_b200.f90 binds the same entry points with ISO_C_BINDING.
 //
-//   run_sph [--variable] [--params parameters.txt] [--end-time T] [--max-steps N] [--save-dir DIR] ics.txt
+//   run_sph [--variable] [--params parameters.txt] [--end-time T] [--max-steps N] [--save-dir DIR] [--drift] ics.txt
+//
+// --drift adds what the reference never prints: the engine's conserved sums (sph_conserved) before the first and
+// after the last step and their relative drift (energy, momentum, angular momentum, mass).
 //
 // Surface kept from the reference: header + whitespace rows, 8 columns read in fixed-h mode (alpha := 0),
 // 10 in variable-h mode, u == 0 marks a sink, dummy sink if none, save<k>.txt cadence t > k*end_time/1000,
@@ -11,6 +14,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <cmath>
 #include <string>
 #include <vector>
 #include <fstream>
@@ -76,7 +80,20 @@ static bool make_save(sph_ctx* ctx, const sph_params& p, int number, const std::
   return true;
 }
 
+// relative drifts between two sph_conserved() results (same scales as summersph_b200/_abi.py:drift_report)
+static void print_drift(const double* a, const double* b, long steps) {
+  const double e0 = a[0] + a[1] + a[2], e1 = b[0] + b[1] + b[2];
+  auto nz = [](double v) { return v != 0.0 ? v : 1.0; };
+  const double dp = std::sqrt((b[3] - a[3]) * (b[3] - a[3]) + (b[4] - a[4]) * (b[4] - a[4]) + (b[5] - a[5]) * (b[5] - a[5]));
+  const double dl = std::sqrt((b[6] - a[6]) * (b[6] - a[6]) + (b[7] - a[7]) * (b[7] - a[7]) + (b[8] - a[8]) * (b[8] - a[8]));
+  const double l0 = std::sqrt(a[6] * a[6] + a[7] * a[7] + a[8] * a[8]);
+  std::printf(" Conserved sums: E = %.17g -> %.17g  (kin %.17g int %.17g pot %.17g)\n", e0, e1, b[0], b[1], b[2]);
+  std::printf(" Drift over %ld steps: dE/|E0| = %.3e  |dP|/sqrt(2 E_kin M) = %.3e  |dL|/|L0| = %.3e  dM/M0 = %.3e\n", steps,
+              (e1 - e0) / nz(std::fabs(e0)), dp / nz(std::sqrt(2.0 * std::fabs(a[0]) * a[9])), dl / nz(l0), (b[9] - a[9]) / nz(a[9]));
+}
+
 int main(int argc, char** argv) {
+  bool drift = false;
   int mode = SPH_MODE_FIXED_H; std::string params_file, save_dir, ics; double end_override = -1; long max_steps = -1;
   for (int i = 1; i < argc; ++i) {
     std::string a = argv[i];
@@ -85,9 +102,10 @@ int main(int argc, char** argv) {
     else if (a == "--end-time" && i + 1 < argc) end_override = std::atof(argv[++i]);
     else if (a == "--max-steps" && i + 1 < argc) max_steps = std::atol(argv[++i]);
     else if (a == "--save-dir" && i + 1 < argc) save_dir = argv[++i];
+    else if (a == "--drift") drift = true;
     else ics = a;
   }
-  if (ics.empty()) { std::fprintf(stderr, "usage: run_sph [--variable] [--params parameters.txt] [--end-time T] [--max-steps N] [--save-dir DIR] ics.txt\n"); return 2; }
+  if (ics.empty()) { std::fprintf(stderr, "usage: run_sph [--variable] [--params parameters.txt] [--end-time T] [--max-steps N] [--save-dir DIR] [--drift] ics.txt\n"); return 2; }
   sph_params p; sph_default_params(mode, &p);
   if (!params_file.empty() && !read_params_from_file(params_file, p)) return 1;
   if (end_override >= 0) p.end_time = end_override;
@@ -100,6 +118,8 @@ int main(int argc, char** argv) {
                  t.s[2].data(), t.s[3].data(), t.s[4].data(), t.s[5].data(), t.s[6].data(), t.s[7].data())) {
     std::fprintf(stderr, "sph_upload: %s\n", sph_last_error(ctx)); return 1;
   }
+  double cons0[SPH_CONSERVED_COUNT] = {}, cons1[SPH_CONSERVED_COUNT] = {};
+  if (drift && sph_conserved(ctx, cons0, SPH_CONSERVED_COUNT)) { std::fprintf(stderr, "sph_conserved: %s\n", sph_last_error(ctx)); return 1; }
   double tt = 0.0, dt = 1.0e-2;                                                            // F:872,875
   int t_test = 0; long steps = 0; int64_t n = (int64_t)t.c[0].size(); int32_t ns = 0;
   while (tt < p.end_time) {                                                                // F:879
@@ -110,7 +130,12 @@ int main(int argc, char** argv) {
     std::printf(" SPH Particles: %lld dt :   %.17g time :    %.17g\n", (long long)n, dt, tt);   // F:891
     std::fflush(stdout);
     if (sph_step(ctx, &dt, &tt, &n, &ns)) { std::fprintf(stderr, "sph_step: %s\n", sph_last_error(ctx)); return 1; }
-    if (max_steps >= 0 && ++steps >= max_steps) break;
+    ++steps;
+    if (max_steps >= 0 && steps >= max_steps) break;
+  }
+  if (drift) {
+    if (sph_conserved(ctx, cons1, SPH_CONSERVED_COUNT)) { std::fprintf(stderr, "sph_conserved: %s\n", sph_last_error(ctx)); return 1; }
+    print_drift(cons0, cons1, steps);
   }
   sph_destroy(ctx);
   return 0;

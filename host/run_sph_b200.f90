@@ -71,6 +71,12 @@ module sph_b200_c
       real(c_double), intent(out) :: x(*), y(*), z(*), vx(*), vy(*), vz(*), u(*), m(*), alpha(*), h(*)
       real(c_double), intent(out) :: sx(*), sy(*), sz(*), svx(*), svy(*), svz(*), sm(*), srad(*)
     end function
+    integer(c_int) function sph_conserved(ctx, out, n_out) bind(C, name="sph_conserved")
+      import :: c_int, c_int32_t, c_double, c_ptr
+      type(c_ptr), value :: ctx
+      real(c_double), intent(out) :: out(*)          ! E_kin E_int E_pot P(3) L(3) M E_pot_gas E_pot_sink
+      integer(c_int32_t), value :: n_out
+    end function
   end interface
 end module sph_b200_c
 
@@ -85,7 +91,7 @@ program run_sph
   real(dp), allocatable :: x(:), y(:), z(:), vx(:), vy(:), vz(:), u(:), m(:), alpha(:), h(:)
   real(dp), allocatable :: sx(:), sy(:), sz(:), svx(:), svy(:), svz(:), sm(:), srad(:)
   real(dp), allocatable :: row(:,:)
-  real(dp) :: t, dt, v(10)
+  real(dp) :: t, dt, v(10), cons0(12), cons1(12), e0, e1
   integer :: status, num_lines, i, nb, ns, t_test, rc, ncol
   integer(c_int64_t) :: n_gas
   integer(c_int32_t) :: n_sink
@@ -146,6 +152,7 @@ program run_sph
   rc = sph_upload(ctx, int(nb, c_int64_t), x, y, z, vx, vy, vz, u, m, alpha, h, int(ns, c_int32_t), &
                   sx, sy, sz, svx, svy, svz, sm, srad)
   if (rc /= 0) stop 'sph_upload failed'
+  rc = sph_conserved(ctx, cons0, 12_c_int32_t)           ! not in the reference: conserved sums for the drift report
   t = 0.0_dp; dt = 1.0e-2_dp; t_test = 0                 ! F:871-875
   n_gas = nb
   do while (t < p%end_time)                              ! F:879
@@ -157,6 +164,10 @@ program run_sph
     rc = sph_step(ctx, dt, t, n_gas, n_sink)
     if (rc /= 0) stop 'sph_step failed'
   end do
+  rc = sph_conserved(ctx, cons1, 12_c_int32_t)
+  e0 = sum(cons0(1:3)); e1 = sum(cons1(1:3))
+  print *, "Energy:", e0, "->", e1, " dE/|E0| =", (e1 - e0) / abs(e0)
+  print *, "|dP| =", norm2(cons1(4:6) - cons0(4:6)), " |dL|/|L0| =", norm2(cons1(7:9) - cons0(7:9)) / norm2(cons0(7:9))
   rc = sph_destroy(ctx)
 
 contains

@@ -186,6 +186,24 @@ int sph_timer_stop(sph_ctx* ctx, double* elapsed_ms);
 /* FP64 FMA throughput of the device in TFLOP/s, measured with a register-resident FMA kernel. */
 int sph_fp64_peak(sph_ctx* ctx, double* tflops);
 
+/* Conserved-quantity sums of the resident state, for the drift report of a run (north_star: "energy/momentum
+ * drift reported over the full run").  The reference keeps no such bookkeeping (nothing in SUMMER_SPH.f90
+ * 863-930 sums energies or momenta); the definitions are this build's own, chosen to match the forces the
+ * reference applies:
+ *   out[0]  E_kin  = sum 1/2 m v.v over gas and sinks
+ *   out[1]  E_int  = sum m u over gas
+ *   out[2]  E_pot  = out[10] + out[11]
+ *   out[3..5]  linear momentum, out[6..8] angular momentum about the origin (gas + sinks)
+ *   out[9]  total mass
+ *   out[10] gas-gas potential: 1/2 sum_i m_i G sum_{nodes accepted by the reference's Barnes-Hut walk for i,
+ *           F:273-279 | V:294-300} M_node phi(dist/h)/h, phi = the cubic-spline softened potential whose
+ *           derivative is the reference's g(q)/q^2 (F:91,94); i's own single-particle leaf is left out
+ *   out[11] sink terms: -G m_s m_j / r over sink-gas and sink-sink pairs (unsoftened like F:559-591)
+ * n_out <= SPH_CONSERVED_COUNT slots are written.  Builds the octree of the current positions if the context
+ * holds none (it is then reused by the next evaluation); in a multi-GPU run every rank returns the same sums. */
+#define SPH_CONSERVED_COUNT 12
+int sph_conserved(sph_ctx* ctx, double* out, int32_t n_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,7 +7,7 @@ import os
 import subprocess
 import numpy as np
 
-from summersph_b200._abi import SphParams, SphCounts, EVAL_ALL
+from summersph_b200._abi import SphParams, SphCounts, EVAL_ALL, CONSERVED, conserved_dict
 from summersph_b200.state import Bodies, Sinks
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -169,6 +169,11 @@ class Oracle:
             self._l.orc_download_neighbours(self._c, _p(count), _p(hsh), _p(off), _p(lst), C.c_int64(tot))
             lst = lst[:tot]
         return count, hsh, off, lst
+
+    def conserved(self):
+        out = np.zeros(len(CONSERVED))
+        self._l.orc_conserved(self._c, _p(out))
+        return conserved_dict(out)
 
     def counters(self):
         c = SphCounts()

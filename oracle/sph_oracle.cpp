@@ -646,6 +646,73 @@ void step(Oracle& o, double& dt, double& t) {
   check_bounds(o);
 }
 
+// ---- conserved sums: NOT in the reference (it keeps no energy / momentum bookkeeping) ----------------
+// The checker's statement of include/sph_b200.h's sph_conserved(): serial sums in ascending `number`;
+// the gas-gas potential runs over the node set particle_gravforce_one accepts (F:273-279 | V:294-300).
+inline double soft_potential(double q) {   // d phi/dq = g(q)/q^2, g = the polynomials of F:91,94; -1/q beyond 2
+  if (q < 1.0) { const double q2 = q * q; return -1.4 + q2 * (2.0 / 3.0 + q2 * (-0.3 + 0.1 * q)); }
+  if (q < 2.0) { const double q2 = q * q; return -1.6 + 1.0 / (15.0 * q) + q2 * (4.0 / 3.0 - q + 0.3 * q2 - (1.0 / 30.0) * q2 * q); }
+  return -1.0 / q;
+}
+void potential_one(const Oracle& o, int ni, int self, const Particle& p, double theta, double& phi) {
+  const Node& nd = o.nodes[ni];
+  double dir[3]; for (int d = 0; d < 3; ++d) dir[d] = p.position[d] - nd.mass_center[d];
+  const double soft = o.soft_hi ? 0.001 * p.s_length : 0.001 * o.p.h_fixed;
+  const double d2 = (((dir[0] * dir[0]) + dir[1] * dir[1]) + dir[2] * dir[2]) + soft;
+  const double dist = std::sqrt(d2);
+  if ((nd.size / dist) < theta || !nd.has_children) {
+    const bool own_leaf = nd.n_particles == 1 && o.order[nd.first] == self;
+    if (nd.mass_total > 0.0 && dist > 0.0 && !own_leaf) {
+      const double h = o.variable_h ? p.s_length : o.p.h_fixed;
+      phi += nd.mass_total * (soft_potential(dist * (1.0 / h)) * (1.0 / h));
+    }
+  } else {
+    for (int c = 0; c < 8; ++c) if (nd.child[c] >= 0) potential_one(o, nd.child[c], self, p, theta, phi);
+  }
+}
+void conserved(Oracle& o, double* out) {
+  const int n = (int)o.bodies.size();
+  create_tree(o);
+  const double theta = o.p.theta_override ? o.p.theta : 0.5;
+  std::vector<double> phi(n, 0.0);
+  #pragma omp parallel for schedule(guided) if (o.threads > 1)
+  for (int i = 0; i < n; ++i) potential_one(o, 0, i, o.bodies[i], theta, phi[i]);
+  double ekin = 0, eint = 0, P[3] = {0, 0, 0}, L[3] = {0, 0, 0}, mass = 0, egg = 0, es = 0;
+  auto add = [&](double m, const double* x, const double* v) {
+    ekin += 0.5 * m * (v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    for (int d = 0; d < 3; ++d) P[d] += m * v[d];
+    L[0] += m * (x[1] * v[2] - x[2] * v[1]); L[1] += m * (x[2] * v[0] - x[0] * v[2]); L[2] += m * (x[0] * v[1] - x[1] * v[0]);
+    mass += m;
+  };
+  for (int i = 0; i < n; ++i) {
+    const Particle& b = o.bodies[i];
+    add(b.mass, b.position, b.velocity);
+    eint += b.mass * b.internal_energy;
+    egg += 0.5 * b.mass * (G_REF * phi[i]);
+    double e = 0.0;
+    for (const auto& s : o.sinks) {
+      if (!(s.mass > 0.0)) continue;
+      const double a = b.position[0] - s.position[0], c = b.position[1] - s.position[1], d = b.position[2] - s.position[2];
+      e -= s.mass / std::sqrt(a * a + c * c + d * d);
+    }
+    es += G_REF * b.mass * e;
+  }
+  for (size_t a = 0; a < o.sinks.size(); ++a) {
+    const Sink& s = o.sinks[a];
+    if (!(s.mass > 0.0)) continue;
+    add(s.mass, s.position, s.velocity);
+    for (size_t b = 0; b < a; ++b) {
+      const Sink& t = o.sinks[b];
+      if (!(t.mass > 0.0)) continue;
+      const double dx = s.position[0] - t.position[0], dy = s.position[1] - t.position[1], dz = s.position[2] - t.position[2];
+      es -= G_REF * s.mass * t.mass / std::sqrt(dx * dx + dy * dy + dz * dz);
+    }
+  }
+  out[0] = ekin; out[1] = eint; out[2] = egg + es;
+  for (int d = 0; d < 3; ++d) { out[3 + d] = P[d]; out[6 + d] = L[d]; }
+  out[9] = mass; out[10] = egg; out[11] = es;
+}
+
 }  // namespace
 
 // =====================================================================================================
@@ -789,5 +856,6 @@ int64_t orc_download_neighbours(orc_ctx* c, int32_t* count, uint64_t* hash, int6
   return tot;
 }
 void orc_counters(orc_ctx* c, sph_counts* out) { *out = c->o.cnt; }
+void orc_conserved(orc_ctx* c, double* out12) { conserved(c->o, out12); }
 
 }  // extern "C"

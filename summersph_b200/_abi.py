@@ -15,6 +15,35 @@ ERRORS = {0: "ok", -1: "bad argument", -2: "no CUDA device", -3: "CUDA error", -
           -5: "bad state", -6: "key depth exceeded", -7: "communicator error"}
 
 
+# slots of sph_conserved() (include/sph_b200.h)
+CONSERVED = ("e_kin", "e_int", "e_pot", "px", "py", "pz", "lx", "ly", "lz", "mass", "e_pot_gas", "e_pot_sink")
+
+
+def conserved_dict(out):
+    d = {k: float(v) for k, v in zip(CONSERVED, out)}
+    d["e_total"] = d["e_kin"] + d["e_int"] + d["e_pot"]
+    return d
+
+
+def drift_report(first, last):
+    """Drift of the conserved sums between two `conserved()` dicts: energy relative to |E_total| of the first,
+    momentum relative to sqrt(2 E_kin M) (the momentum the system would carry if it all moved one way),
+    angular momentum relative to |L| of the first.  Tree gravity (Barnes-Hut monopoles) is not symmetric, so
+    momentum is not conserved by the reference's scheme: this is a report, not a test."""
+    import math
+    p_scale = math.sqrt(2.0 * abs(first["e_kin"]) * first["mass"]) or 1.0
+    l0 = math.sqrt(first["lx"] ** 2 + first["ly"] ** 2 + first["lz"] ** 2) or 1.0
+    dp = math.sqrt(sum((last[k] - first[k]) ** 2 for k in ("px", "py", "pz")))
+    dl = math.sqrt(sum((last[k] - first[k]) ** 2 for k in ("lx", "ly", "lz")))
+    return {
+        "energy_rel": (last["e_total"] - first["e_total"]) / (abs(first["e_total"]) or 1.0),
+        "momentum_rel": dp / p_scale,
+        "angular_momentum_rel": dl / l0,
+        "mass_rel": (last["mass"] - first["mass"]) / (first["mass"] or 1.0),
+        "e_total_first": first["e_total"], "e_total_last": last["e_total"],
+    }
+
+
 class SphParams(C.Structure):
     """`sph_params` — V's type(param) (Variable.f90:54-64) + F's compile-time constants (SUMMER_SPH.f90:7-11)."""
     _fields_ = [

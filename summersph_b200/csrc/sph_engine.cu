@@ -21,6 +21,7 @@
 #endif
 #include "sph_gravity.cuh"
 #include "sph_integrate.cuh"
+#include "sph_conserved.cuh"
 
 namespace {
 
@@ -90,6 +91,7 @@ struct sph_ctx {
   std::vector<std::vector<double*>> peer;      // [array slot][rank]
   std::vector<void*> ipc_opened; int* d_flag = nullptr; void* d_blob = nullptr; size_t blob_cap = 0;
   int g0 = 0, g1 = 0, p0 = 0, p1 = 0;
+  double* cons_partial = nullptr; double* cons_out = nullptr;   // sph_conserved: block partials, result slots
 };
 
 namespace {
@@ -935,6 +937,7 @@ int sph_destroy(sph_ctx* c) {
   F(c->rho); F(c->omega); F(c->prs); F(c->cs); F(c->por2); F(c->ax); F(c->ay); F(c->az); F(c->udot); F(c->adot);
   F(c->node_count); F(c->gsize); F(c->gfirst); F(c->groups); F(c->level); F(c->lcx); F(c->lcy); F(c->lcz); F(c->reach); F(c->bvh); F(c->nodes); F(c->node_part); F(c->parent); F(c->nchild);
   F(c->nl_pool); F(c->nl_head); F(c->nl_ctl); F(c->ggroups); F(c->gbvh); F(c->seg_cnt); F(c->seg_off); F(c->wnodes); F(c->wcount); F(c->wstart); F(c->widx); F(c->grav_spill);
+  F(c->cons_partial); F(c->cons_out);
   F(c->arrive); F(c->cnt); F(c->off); F(c->root); F(c->partial); F(c->cub_tmp); F(c->d_wt); F(c->d_dwt); F(c->d_gt);
   F(c->sink_buf); F(c->sink_partial); F(c->sc); F(c->ctr); F(c->work); F(c->keep); F(c->d_nsel); F(c->pos); F(c->stage_d); F(c->stage_d2);
   if (c->h_sc) cudaFreeHost(c->h_sc);
@@ -1222,6 +1225,32 @@ int sph_fp64_peak(sph_ctx* c, double* tflops) {
   }
   cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(out);
   *tflops = best;
+  return SPH_OK;
+}
+
+int sph_conserved(sph_ctx* c, double* out, int32_t n_out) {
+  if (!c || !out || n_out < 1) return SPH_ERR_ARG;
+  if (c->n < 2) { c->err = "need at least 2 gas particles"; return SPH_ERR_STATE; }
+  cudaSetDevice(c->device);
+  double keep_ms[ST_COUNT]; std::memcpy(keep_ms, c->stage_ms, sizeof(keep_ms));
+  if (!(c->tree_valid && !c->pos_moved)) {        // the octree of the current positions (kept for the next evaluation)
+    int r = build_tree(c); if (r) return r;
+  }
+  if (!c->cons_partial) { DA(c->cons_partial, (size_t)CONS_MAX_BLOCKS * CONS_SUMS); DA(c->cons_out, CONS_FIELDS); }
+  const int n = (int)c->n;
+  const int nb = std::max(1, std::min(cdiv(n, CONS_THREADS), std::min(CONS_MAX_BLOCKS, c->n_sm * 16)));
+  LAUNCH(k_conserved_partial, nb, CONS_THREADS, 0, n, (int)c->counts.n_nodes, c->dp, state_of(c, c->cur), c->nodes, c->node_part,
+         c->n_sink, c->S, c->cons_partial);
+  LAUNCH(k_conserved_final, 1, 32, 0, nb, c->cons_partial, c->dp, c->n_sink, c->S, c->cons_out);
+  double host[CONS_FIELDS];
+  CK(cudaMemcpyAsync(host, c->cons_out, sizeof(host), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(c->h_sc, c->sc, sizeof(SimScalars), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  stage_collect(c, false);                        // a tree build here is not part of any step's stage times
+  std::memcpy(c->stage_ms, keep_ms, sizeof(keep_ms));
+  CK(cudaGetLastError());
+  { int r = check_device_error(c); if (r) return r; }                  // key-depth error of a tree built here
+  for (int k = 0; k < n_out && k < CONS_FIELDS; ++k) out[k] = host[k];
   return SPH_OK;
 }
 

@@ -8,7 +8,7 @@ import ctypes as C
 import os
 import numpy as np
 
-from ._abi import SphParams, SphCounts, EVAL_ALL, ERRORS
+from ._abi import SphParams, SphCounts, EVAL_ALL, ERRORS, CONSERVED, conserved_dict
 from .state import Bodies, Sinks
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -61,6 +61,7 @@ def load_library(path=None):
     lib.sph_timer_start.argtypes = [vp]
     lib.sph_timer_stop.argtypes = [vp, C.POINTER(dbl)]
     lib.sph_fp64_peak.argtypes = [vp, C.POINTER(dbl)]
+    lib.sph_conserved.argtypes = [vp, vp, i32]
     if path is None:
         _LIB = lib
     return lib
@@ -208,6 +209,12 @@ class Engine:
         v = C.c_double()
         self._ck(self._l.sph_fp64_peak(self._c, C.byref(v)))
         return v.value
+
+    def conserved(self):
+        """Energy / momentum / angular-momentum sums of the resident state (`sph_conserved`)."""
+        out = np.zeros(len(CONSERVED))
+        self._ck(self._l.sph_conserved(self._c, _p(out), len(out)))
+        return conserved_dict(out)
 
     def group_count(self):
         return int(self._l.sph_group_count(self._c))
