@@ -204,6 +204,16 @@ int sph_fp64_peak(sph_ctx* ctx, double* tflops);
 #define SPH_CONSERVED_COUNT 12
 int sph_conserved(sph_ctx* ctx, double* out, int32_t n_out);
 
+/* Column-density image of the resident gas: what the reference's post-processing script Density_Image.py
+ * draws from a save file (a 120^3 density grid with fixed h = 1.25 summed along z, Density_Image.py:105-145),
+ * computed on the device from the live state with every particle's own h (`smoothing` in fixed-h mode):
+ *   image[iv * nu + iu] = sum_j m_j F(|d| / h_j) / (pi h_j^2),  d = pixel centre - particle in the image plane,
+ * F = line-of-sight integral of the M4 kernel shape (F:66,70).  axis = 0|1|2 projects along x|y|z with image
+ * axes (y,z)|(z,x)|(x,y); pixel (iu, iv) is centred at (u0 + (iu+1/2)(u1-u0)/nu, v0 + (iv+1/2)(v1-v0)/nv).
+ * Particles narrower than a pixel are widened to h = pixel/2.  `image` holds nu*nv doubles (host memory). */
+int sph_column_density(sph_ctx* ctx, int32_t axis, double u0, double u1, double v0, double v1,
+                       int32_t nu, int32_t nv, double* image);
+
 #ifdef __cplusplus
 }
 #endif

@@ -22,6 +22,7 @@
 #include "sph_gravity.cuh"
 #include "sph_integrate.cuh"
 #include "sph_conserved.cuh"
+#include "sph_image.cuh"
 
 namespace {
 
@@ -92,6 +93,7 @@ struct sph_ctx {
   std::vector<void*> ipc_opened; int* d_flag = nullptr; void* d_blob = nullptr; size_t blob_cap = 0;
   int g0 = 0, g1 = 0, p0 = 0, p1 = 0;
   double* cons_partial = nullptr; double* cons_out = nullptr;   // sph_conserved: block partials, result slots
+  double* img_table = nullptr;                                    // sph_column_density: line-of-sight integral of the M4 shape
 };
 
 namespace {
@@ -937,7 +939,7 @@ int sph_destroy(sph_ctx* c) {
   F(c->rho); F(c->omega); F(c->prs); F(c->cs); F(c->por2); F(c->ax); F(c->ay); F(c->az); F(c->udot); F(c->adot);
   F(c->node_count); F(c->gsize); F(c->gfirst); F(c->groups); F(c->level); F(c->lcx); F(c->lcy); F(c->lcz); F(c->reach); F(c->bvh); F(c->nodes); F(c->node_part); F(c->parent); F(c->nchild);
   F(c->nl_pool); F(c->nl_head); F(c->nl_ctl); F(c->ggroups); F(c->gbvh); F(c->seg_cnt); F(c->seg_off); F(c->wnodes); F(c->wcount); F(c->wstart); F(c->widx); F(c->grav_spill);
-  F(c->cons_partial); F(c->cons_out);
+  F(c->cons_partial); F(c->cons_out); F(c->img_table);
   F(c->arrive); F(c->cnt); F(c->off); F(c->root); F(c->partial); F(c->cub_tmp); F(c->d_wt); F(c->d_dwt); F(c->d_gt);
   F(c->sink_buf); F(c->sink_partial); F(c->sc); F(c->ctr); F(c->work); F(c->keep); F(c->d_nsel); F(c->pos); F(c->stage_d); F(c->stage_d2);
   if (c->h_sc) cudaFreeHost(c->h_sc);
@@ -1251,6 +1253,43 @@ int sph_conserved(sph_ctx* c, double* out, int32_t n_out) {
   CK(cudaGetLastError());
   { int r = check_device_error(c); if (r) return r; }                  // key-depth error of a tree built here
   for (int k = 0; k < n_out && k < CONS_FIELDS; ++k) out[k] = host[k];
+  return SPH_OK;
+}
+
+int sph_column_density(sph_ctx* c, int32_t axis, double u0, double u1, double v0, double v1, int32_t nu, int32_t nv, double* image) {
+  if (!c || !image) return SPH_ERR_ARG;
+  if (axis < 0 || axis > 2 || nu < 1 || nv < 1 || nu > 16384 || nv > 16384 || !(u1 > u0) || !(v1 > v0)) { c->err = "bad image frame"; return SPH_ERR_ARG; }
+  if (c->n <= 0) { c->err = "no particles uploaded"; return SPH_ERR_STATE; }
+  cudaSetDevice(c->device);
+  if (!c->img_table) {
+    // F(q_b) = 2 int_0^sqrt(4 - q_b^2) w(sqrt(q_b^2 + s^2)) ds, w = the M4 shape of F:66,70; composite Simpson, 4096 intervals
+    std::vector<double> F(IMG_TABLE + 2, 0.0);
+    auto w = [](double q) { return q <= 1.0 ? 1.0 - 1.5 * q * q + 0.75 * q * q * q : (q <= 2.0 ? 0.25 * (2.0 - q) * (2.0 - q) * (2.0 - q) : 0.0); };
+    for (int i = 0; i < IMG_TABLE; ++i) {
+      const double qb = 2.0 * i / IMG_TABLE, smax = std::sqrt(4.0 - qb * qb);
+      const int m = 4096; const double hs = smax / m;
+      double acc = w(qb) + w(std::sqrt(qb * qb + smax * smax));
+      for (int k = 1; k < m; ++k) { const double sv = k * hs; acc += ((k & 1) ? 4.0 : 2.0) * w(std::sqrt(qb * qb + sv * sv)); }
+      F[i] = 2.0 * acc * hs / 3.0;
+    }
+    DA(c->img_table, IMG_TABLE + 2);
+    CK(cudaMemcpy(c->img_table, F.data(), F.size() * 8, cudaMemcpyHostToDevice));
+  }
+  double* d_img = nullptr;
+  const size_t npx = (size_t)nu * nv;
+  if (cudaMalloc((void**)&d_img, npx * 8) != cudaSuccess) { cudaGetLastError(); c->err = "cudaMalloc(image)"; return SPH_ERR_OOM; }
+  cudaError_t e = cudaMemsetAsync(d_img, 0, npx * 8, c->stream);
+  if (e == cudaSuccess) {
+    const int n = (int)c->n;
+    const int grid = std::max(1, std::min(cdiv((int64_t)n * 32, IMG_THREADS), c->n_sm * 8));
+    LAUNCH(k_column_density, grid, IMG_THREADS, 0, n, state_of(c, c->cur), c->dp.variable_h, c->dp.h_fixed, (int)axis, u0, v0,
+           (u1 - u0) / nu, (v1 - v0) / nv, (int)nu, (int)nv, c->img_table, d_img);
+    e = cudaMemcpyAsync(image, d_img, npx * 8, cudaMemcpyDeviceToHost, c->stream);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  cudaFree(d_img);
+  if (e != cudaSuccess) { c->err = std::string("sph_column_density: ") + cudaGetErrorString(e); return SPH_ERR_CUDA; }
   return SPH_OK;
 }
 

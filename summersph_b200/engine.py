@@ -62,6 +62,7 @@ def load_library(path=None):
     lib.sph_timer_stop.argtypes = [vp, C.POINTER(dbl)]
     lib.sph_fp64_peak.argtypes = [vp, C.POINTER(dbl)]
     lib.sph_conserved.argtypes = [vp, vp, i32]
+    lib.sph_column_density.argtypes = [vp, i32, dbl, dbl, dbl, dbl, i32, i32, vp]
     if path is None:
         _LIB = lib
     return lib
@@ -215,6 +216,17 @@ class Engine:
         out = np.zeros(len(CONSERVED))
         self._ck(self._l.sph_conserved(self._c, _p(out), len(out)))
         return conserved_dict(out)
+
+    def column_density(self, axis="z", extent=(-100.0, 100.0, -100.0, 100.0), shape=(512, 512)):
+        """Column density of the resident gas projected along `axis` (`sph_column_density`): array of shape
+        (nv, nu) = `shape`, rows along the image ordinate; extent = (u0, u1, v0, v1) like matplotlib's imshow
+        with origin='lower'.  Image axes: x -> (y, z), y -> (z, x), z -> (x, y)."""
+        ax = {"x": 0, "y": 1, "z": 2}.get(axis, axis)
+        nv, nu = int(shape[0]), int(shape[1])
+        img = np.zeros((nv, nu))
+        u0, u1, v0, v1 = (float(e) for e in extent)
+        self._ck(self._l.sph_column_density(self._c, int(ax), u0, u1, v0, v1, nu, nv, _p(img)))
+        return img
 
     def group_count(self):
         return int(self._l.sph_group_count(self._c))

@@ -88,6 +88,59 @@ def sod_tube(n_target=100_000, rho_scale=1e-9, gamma=1.4, eta=1.2, alpha=1.0, wi
     return bodies, Sinks.empty(0)
 
 
+def sod_box(n_target=100_000, t_end=0.2, rho_scale=1e-9, gamma=1.4, eta=1.2, alpha=1.0, core_cells=4):
+    """Sod shock tube sized for a comparison with the exact solution at time `t_end` (config 2).
+
+    The reference has no periodic or wall boundaries, so a lattice tube expands into vacuum from every face.
+    The box is therefore made just large enough that, at `t_end`, a core of `core_cells` right-hand lattice
+    cells around the axis and the whole wave pattern (rarefaction head at -c_L t, shock at 1.752 t) have not
+    been reached by the rarefactions coming in from the side walls (speed <= c_L) and the two ends, with one
+    kernel radius (2 h_right) to spare.  Same states as `sod_tube`: rho 1 | 0.125, P 1 | 0.1 (times `rho_scale`,
+    which makes the always-on self gravity negligible), equal-mass particles on cubic lattices of spacing
+    dl | 2 dl, h = eta * spacing, no particle at the origin, no sinks.
+    Returns (Bodies, Sinks, geom) with geom = {len_l, len_r, width, dl, dr, h_left, h_right, t_end}."""
+    c_l = np.sqrt(gamma * 1.0 / 1.0); c_r = np.sqrt(gamma * 0.1 / 0.125)
+    s_shock = 1.7522                                  # shock speed of Sod's problem for gamma = 1.4 (exact: analytic.py)
+    if abs(gamma - 1.4) > 1e-12:
+        from .analytic import riemann_star, SOD
+        ps, _ = riemann_star(gamma=gamma, **SOD)
+        s_shock = c_r * np.sqrt((gamma + 1) / (2 * gamma) * ps / 0.1 + (gamma - 1) / (2 * gamma))
+
+    def geometry(dl):
+        dr = 2.0 * dl; pad = 2.0 * eta * dr
+        nw = int(np.ceil((2.0 * (c_l * t_end + pad) + core_cells * dr) / dr))          # width in right-hand cells
+        nl = int(np.ceil((2.0 * c_l * t_end + pad + dr) / dl))                          # left length in dl
+        nr = int(np.ceil(((s_shock + c_r) * t_end + pad + dr) / dr))                    # right length in dr
+        return nl, nr, nw, nl * (2 * nw) ** 2 + nr * nw ** 2
+
+    lo, hi = 1e-4, 1.0                                # particle count falls monotonically with dl
+    for _ in range(60):
+        mid = np.sqrt(lo * hi)
+        if geometry(mid)[3] > n_target:
+            lo = mid
+        else:
+            hi = mid
+    dl = hi; dr = 2.0 * dl
+    nl, nr, nw, _ = geometry(dl)
+
+    def lattice(nx, ny, d, x0):
+        i, j, k = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(ny), indexing="ij")
+        return (x0 + (i.ravel() + 0.5) * d, (j.ravel() + 0.5) * d, (k.ravel() + 0.5) * d)
+
+    xl, yl, zl = lattice(nl, 2 * nw, dl, -nl * dl)
+    xr, yr, zr = lattice(nr, nw, dr, 0.0)
+    x = np.concatenate([xl, xr]); y = np.concatenate([yl, yr]); z = np.concatenate([zl, zr])
+    n = x.size
+    rho_l, p_l, p_r, rho_r = rho_scale, rho_scale, 0.1 * rho_scale, 0.125 * rho_scale
+    m = np.full(n, rho_l * dl ** 3)
+    u = np.concatenate([np.full(xl.size, p_l / ((gamma - 1.0) * rho_l)), np.full(xr.size, p_r / ((gamma - 1.0) * rho_r))])
+    h = np.concatenate([np.full(xl.size, eta * dl), np.full(xr.size, eta * dr)])
+    geom = {"len_l": nl * dl, "len_r": nr * dr, "width": nw * dr, "dl": dl, "dr": dr, "h_left": eta * dl,
+            "h_right": eta * dr, "t_end": t_end}
+    bodies = Bodies(x, y, z, np.zeros(n), np.zeros(n), np.zeros(n), u, m, np.full(n, alpha), h)
+    return bodies, Sinks.empty(0), geom
+
+
 def uniform_sphere(n, seed=7, radius=100.0, m_total=5.0, u=0.25, alpha=0.1, eta=1.2):
     """The 'Collapse' geometry Disc_ICs.py sketches (uniform sphere R<=100 AU, v=0 here)."""
     rng = np.random.default_rng(seed)
