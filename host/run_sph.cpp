@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <cmath>
+#include <algorithm>
 #include <string>
 #include <vector>
 #include <fstream>
@@ -86,10 +87,10 @@ static void print_drift(const double* a, const double* b, long steps) {
   auto nz = [](double v) { return v != 0.0 ? v : 1.0; };
   const double dp = std::sqrt((b[3] - a[3]) * (b[3] - a[3]) + (b[4] - a[4]) * (b[4] - a[4]) + (b[5] - a[5]) * (b[5] - a[5]));
   const double dl = std::sqrt((b[6] - a[6]) * (b[6] - a[6]) + (b[7] - a[7]) * (b[7] - a[7]) + (b[8] - a[8]) * (b[8] - a[8]));
-  const double l0 = std::sqrt(a[6] * a[6] + a[7] * a[7] + a[8] * a[8]);
+  const double l0 = std::max(std::sqrt(a[6] * a[6] + a[7] * a[7] + a[8] * a[8]), std::sqrt(b[6] * b[6] + b[7] * b[7] + b[8] * b[8]));
   std::printf(" Conserved sums: E = %.17g -> %.17g  (kin %.17g int %.17g pot %.17g)\n", e0, e1, b[0], b[1], b[2]);
-  std::printf(" Drift over %ld steps: dE/|E0| = %.3e  |dP|/sqrt(2 E_kin M) = %.3e  |dL|/|L0| = %.3e  dM/M0 = %.3e\n", steps,
-              (e1 - e0) / nz(std::fabs(e0)), dp / nz(std::sqrt(2.0 * std::fabs(a[0]) * a[9])), dl / nz(l0), (b[9] - a[9]) / nz(a[9]));
+  std::printf(" Drift over %ld steps: dE/|E0| = %.3e  |dP|/sqrt(2 E_kin M) = %.3e  |dL|/|L| = %.3e  dM/M0 = %.3e\n", steps,
+              (e1 - e0) / nz(std::fabs(e0)), dp / nz(std::sqrt(2.0 * std::max(std::fabs(a[0]), std::fabs(b[0])) * std::max(a[9], b[9]))), dl / nz(l0), (b[9] - a[9]) / nz(a[9]));
 }
 
 int main(int argc, char** argv) {

@@ -27,19 +27,24 @@ def conserved_dict(out):
 
 def drift_report(first, last):
     """Drift of the conserved sums between two `conserved()` dicts: energy relative to |E_total| of the first,
-    momentum relative to sqrt(2 E_kin M) (the momentum the system would carry if it all moved one way),
-    angular momentum relative to |L| of the first.  Tree gravity (Barnes-Hut monopoles) is not symmetric, so
-    momentum is not conserved by the reference's scheme: this is a report, not a test."""
+    momentum relative to sqrt(2 E_kin M) (the momentum the system would carry if it all moved one way; the larger
+    E_kin of the two states, so that a start from rest still has a scale), angular momentum relative to the larger
+    |L| of the two.  Absolute changes are given as well; a relative value is None when its scale is zero.
+    Tree gravity (Barnes-Hut monopoles) is not symmetric, so momentum is not conserved by the reference's scheme
+    (SURVEY.md Appendix D): this is a report, not a test."""
     import math
-    p_scale = math.sqrt(2.0 * abs(first["e_kin"]) * first["mass"]) or 1.0
-    l0 = math.sqrt(first["lx"] ** 2 + first["ly"] ** 2 + first["lz"] ** 2) or 1.0
+    norm = lambda d, ks: math.sqrt(sum(d[k] ** 2 for k in ks))   # noqa: E731
+    p_scale = math.sqrt(2.0 * max(abs(first["e_kin"]), abs(last["e_kin"])) * max(first["mass"], last["mass"]))
+    l_scale = max(norm(first, ("lx", "ly", "lz")), norm(last, ("lx", "ly", "lz")))
     dp = math.sqrt(sum((last[k] - first[k]) ** 2 for k in ("px", "py", "pz")))
     dl = math.sqrt(sum((last[k] - first[k]) ** 2 for k in ("lx", "ly", "lz")))
+    de = last["e_total"] - first["e_total"]
     return {
-        "energy_rel": (last["e_total"] - first["e_total"]) / (abs(first["e_total"]) or 1.0),
-        "momentum_rel": dp / p_scale,
-        "angular_momentum_rel": dl / l0,
-        "mass_rel": (last["mass"] - first["mass"]) / (first["mass"] or 1.0),
+        "energy_rel": de / abs(first["e_total"]) if first["e_total"] else None,
+        "momentum_rel": dp / p_scale if p_scale else None,
+        "angular_momentum_rel": dl / l_scale if l_scale else None,
+        "mass_rel": (last["mass"] - first["mass"]) / first["mass"] if first["mass"] else None,
+        "energy_abs": de, "momentum_abs": dp, "angular_momentum_abs": dl,
         "e_total_first": first["e_total"], "e_total_last": last["e_total"],
     }
 

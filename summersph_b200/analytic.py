@@ -90,29 +90,33 @@ def sod_exact(x, t, gamma=1.4, rho_scale=1.0):
     return rho * rho_scale, v, p * rho_scale
 
 
-def sod_core_mask(x, y, z, t, geom, gamma=1.4, margin_h=1.0):
+# Omega of the variable-h program on a uniform cubic lattice with h = 1.2 spacings ("SUMMER_SPH - Variable.f90":455,487
+# as coded: 1 + h/(3 rho) sum m (3 W - r dW/dr)/h; tests/test_widen_sod.py measures it with the oracle).
+OMEGA_LATTICE = 2.98
+
+
+def effective_gas(gamma=1.4, omega=1.0):
+    """The gas the variable-h program actually evolves.  Its momentum and energy equations both carry P/Omega
+    (V:413-425) and its Omega is ~3 where the textbook grad-h factor is ~1 (V:487 has -(r dW - 3W)/h where
+    dW/dh = -(3W + r dW/dr)/h; SURVEY.md §8(a) #9 keeps it as coded).  With a uniform Omega the particles follow
+    an ideal gas of pressure P/Omega and adiabatic index 1 + (gamma-1)/Omega at unchanged rho and u.
+    Returns (gamma_eff, Sod states with the effective pressures); omega = 1 is the fixed-h program / the textbook."""
+    st = dict(SOD)
+    st["p_l"] = SOD["p_l"] / omega; st["p_r"] = SOD["p_r"] / omega
+    return 1.0 + (gamma - 1.0) / omega, st
+
+
+def sod_core_mask(x, y, z, t, geom, gamma=1.4):
     """Particles whose history is still one-dimensional at time t in a tube with free (vacuum) boundaries:
-    the lateral rarefactions move in from the side walls at the local sound speed (at most c_L), the end
-    rarefactions from x = -len_l and x = +len_r; `margin_h` kernel radii (2 h_right each) are kept clear on top
-    (`ics.sod_box` sizes the tube for margin_h = 1)."""
-    c_l = np.sqrt(gamma * SOD["p_l"] / SOD["rho_l"]); c_r = np.sqrt(gamma * SOD["p_r"] / SOD["rho_r"])
-    pad = margin_h * 2.0 * geom["h_right"]
+    the lateral rarefactions move in from the side walls at the sound speed of the left state, the end
+    rarefactions from x = -len_l and x = +len_r; one kernel radius (2 h_right) is kept clear on top, which is
+    what `ics.sod_box` sizes the tube for (wave speeds of the effective gas for geom['omega'])."""
+    g_eff, st = effective_gas(gamma, geom.get("omega", 1.0))
+    c_l = np.sqrt(g_eff * st["p_l"] / st["rho_l"]); c_r = np.sqrt(g_eff * st["p_r"] / st["rho_r"])
+    pad = 2.0 * geom["h_right"]
     half = 0.5 * geom["width"] - c_l * t - pad
     if half <= 0:
         raise ValueError("the lateral rarefactions have reached the axis: tube too narrow for this time")
     yc = zc = 0.5 * geom["width"]
     return ((np.abs(y - yc) < half) & (np.abs(z - zc) < half) &
             (x > -geom["len_l"] + c_l * t + pad) & (x < geom["len_r"] - c_r * t - pad))
-
-
-def sod_l1_errors(x, rho, vx, prs, t, mask, gamma=1.4, rho_scale=1.0):
-    """Mean absolute deviation from the exact solution over the masked particles, normalised by the mean
-    absolute exact value (velocity: by the star-region velocity)."""
-    re, ve, pe = sod_exact(x[mask], t, gamma, rho_scale)
-    _, vstar = riemann_star(gamma=gamma, **SOD)
-    return {
-        "n_core": int(np.count_nonzero(mask)),
-        "rho_l1": float(np.mean(np.abs(rho[mask] - re)) / np.mean(re)),
-        "v_l1": float(np.mean(np.abs(vx[mask] - ve)) / vstar),
-        "p_l1": float(np.mean(np.abs(prs[mask] - pe)) / np.mean(pe)),
-    }

@@ -88,23 +88,25 @@ def sod_tube(n_target=100_000, rho_scale=1e-9, gamma=1.4, eta=1.2, alpha=1.0, wi
     return bodies, Sinks.empty(0)
 
 
-def sod_box(n_target=100_000, t_end=0.2, rho_scale=1e-9, gamma=1.4, eta=1.2, alpha=1.0, core_cells=4):
+def sod_box(n_target=100_000, t_end=0.2, rho_scale=1e-9, gamma=1.4, eta=1.2, alpha=1.0, core_cells=4, omega=1.0):
     """Sod shock tube sized for a comparison with the exact solution at time `t_end` (config 2).
 
     The reference has no periodic or wall boundaries, so a lattice tube expands into vacuum from every face.
     The box is therefore made just large enough that, at `t_end`, a core of `core_cells` right-hand lattice
-    cells around the axis and the whole wave pattern (rarefaction head at -c_L t, shock at 1.752 t) have not
+    cells around the axis and the whole wave pattern (rarefaction head at -c_L t, shock at s t) have not
     been reached by the rarefactions coming in from the side walls (speed <= c_L) and the two ends, with one
     kernel radius (2 h_right) to spare.  Same states as `sod_tube`: rho 1 | 0.125, P 1 | 0.1 (times `rho_scale`,
     which makes the always-on self gravity negligible), equal-mass particles on cubic lattices of spacing
     dl | 2 dl, h = eta * spacing, no particle at the origin, no sinks.
-    Returns (Bodies, Sinks, geom) with geom = {len_l, len_r, width, dl, dr, h_left, h_right, t_end}."""
-    c_l = np.sqrt(gamma * 1.0 / 1.0); c_r = np.sqrt(gamma * 0.1 / 0.125)
-    s_shock = 1.7522                                  # shock speed of Sod's problem for gamma = 1.4 (exact: analytic.py)
-    if abs(gamma - 1.4) > 1e-12:
-        from .analytic import riemann_star, SOD
-        ps, _ = riemann_star(gamma=gamma, **SOD)
-        s_shock = c_r * np.sqrt((gamma + 1) / (2 * gamma) * ps / 0.1 + (gamma - 1) / (2 * gamma))
+
+    `omega`: the variable-h program divides its pressure terms by Omega ~ 3 (see analytic.effective_gas), which
+    slows every wave; pass the lattice value (analytic.OMEGA_LATTICE) to size the box for those waves instead.
+    Returns (Bodies, Sinks, geom) with geom = {len_l, len_r, width, dl, dr, h_left, h_right, t_end, omega}."""
+    from .analytic import riemann_star, effective_gas, SOD
+    g_eff, st = effective_gas(gamma, omega)
+    c_l = np.sqrt(g_eff * st["p_l"] / st["rho_l"]); c_r = np.sqrt(g_eff * st["p_r"] / st["rho_r"])
+    ps, _ = riemann_star(gamma=g_eff, **st)
+    s_shock = c_r * np.sqrt((g_eff + 1) / (2 * g_eff) * ps / st["p_r"] + (g_eff - 1) / (2 * g_eff))
 
     def geometry(dl):
         dr = 2.0 * dl; pad = 2.0 * eta * dr
@@ -136,7 +138,7 @@ def sod_box(n_target=100_000, t_end=0.2, rho_scale=1e-9, gamma=1.4, eta=1.2, alp
     u = np.concatenate([np.full(xl.size, p_l / ((gamma - 1.0) * rho_l)), np.full(xr.size, p_r / ((gamma - 1.0) * rho_r))])
     h = np.concatenate([np.full(xl.size, eta * dl), np.full(xr.size, eta * dr)])
     geom = {"len_l": nl * dl, "len_r": nr * dr, "width": nw * dr, "dl": dl, "dr": dr, "h_left": eta * dl,
-            "h_right": eta * dr, "t_end": t_end}
+            "h_right": eta * dr, "t_end": t_end, "omega": omega}
     bodies = Bodies(x, y, z, np.zeros(n), np.zeros(n), np.zeros(n), u, m, np.full(n, alpha), h)
     return bodies, Sinks.empty(0), geom
 

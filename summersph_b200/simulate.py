@@ -45,8 +45,9 @@ def simulate(bodies: Bodies, sinks: Sinks, params: SphParams, engine=None, save_
             last = engine.conserved()
             drift.update(first=first, last=last, steps=steps, t=t, **drift_report(first, last))
             log(f" Conserved sums: E = {first['e_total']!r} -> {last['e_total']!r}  (kin {last['e_kin']!r} int {last['e_int']!r} pot {last['e_pot']!r})")
-            log(f" Drift over {steps} steps: dE/|E0| = {drift['energy_rel']:.3e}  |dP|/sqrt(2 E_kin M) = {drift['momentum_rel']:.3e}"
-                f"  |dL|/|L0| = {drift['angular_momentum_rel']:.3e}  dM/M0 = {drift['mass_rel']:.3e}")
+            fmt = lambda v: "n/a" if v is None else f"{v:.3e}"   # noqa: E731
+            log(f" Drift over {steps} steps: dE/|E0| = {fmt(drift['energy_rel'])}  |dP|/sqrt(2 E_kin M) = {fmt(drift['momentum_rel'])}"
+                f"  |dL|/|L| = {fmt(drift['angular_momentum_rel'])}  dM/M0 = {fmt(drift['mass_rel'])}")
         b, s = engine.download()
         return b, s, t, dt, steps
     finally:

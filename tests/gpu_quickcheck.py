@@ -1,0 +1,89 @@
+"""One short GPU pass over the on-demand entry points added after the step path (sph_conserved,
+sph_column_density, the 100k Sod tube): each check prints one JSON line and appends it to gpurun_out/quickcheck.jsonl
+as soon as it is done.  No torch import (the engine is ctypes + CUDA only), so it fits in a minute of box time:
+
+    python tests/gpu_quickcheck.py [conserved] [image] [sod_variable] [sod_fixed]
+"""
+import json
+import os
+import sys
+import time
+import traceback
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+OUT = os.path.join(ROOT, "gpurun_out", "quickcheck.jsonl")
+
+
+def emit(name, t0, **kw):
+    rec = dict(check=name, seconds=round(time.perf_counter() - t0, 3), **kw)
+    line = json.dumps(rec, default=float)
+    print(line, flush=True)
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    with open(OUT, "a") as f:
+        f.write(line + "\n")
+
+
+def check_conserved():
+    from summersph_b200 import default_params, MODE_VARIABLE_H, ics
+    from summersph_b200.engine import Engine
+    from oracle.oracle import Oracle
+    from test_widen_conserved import assert_same_sums
+    t0 = time.perf_counter()
+    p = default_params(MODE_VARIABLE_H)
+    b, s = ics.keplerian_disc(4000, seed=42)
+    o = Oracle(p); o.upload(b, s)
+    with Engine(p) as e:
+        e.upload(b, s)
+        g0, o0 = e.conserved(), o.conserved()
+        assert_same_sums(g0, o0)
+        dto, to = o.step(0.01, 0.0); dte, te = e.step(0.01, 0.0)
+        assert (dto, to) == (dte, te)
+        g1, o1 = e.conserved(), o.conserved()
+        assert_same_sums(g1, o1)
+    emit("conserved", t0, ok=True, engine_first=g0, oracle_first=o0, engine_after_step=g1, oracle_after_step=o1)
+
+
+def check_image():
+    from summersph_b200 import default_params, MODE_VARIABLE_H, ics
+    from summersph_b200.engine import Engine
+    from test_widen_density_image import image_ref
+    t0 = time.perf_counter()
+    p = default_params(MODE_VARIABLE_H)
+    b, s = ics.keplerian_disc(800, seed=12)
+    extent, shape = (-110.0, 90.0, -60.0, 120.0), (48, 40)
+    with Engine(p) as e:
+        e.upload(b, s)
+        img = e.column_density("z", extent, shape)
+        imx = e.column_density("x", extent, shape)
+    ref = image_ref(b.x, b.y, b.m, b.h, extent, shape)
+    rex = image_ref(b.y, b.z, b.m, b.h, extent, shape)
+    err = float(np.max(np.abs(img - ref)) / ref.max()); erx = float(np.max(np.abs(imx - rex)) / rex.max())
+    emit("image", t0, ok=bool(err < 1e-9 and erx < 1e-9), rel_err_z=err, rel_err_x=erx, mass=float(img.sum() * (200 / 40) * (180 / 48)), mass_true=float(b.m.sum()))
+
+
+def check_sod(kind):
+    from summersph_b200.engine import Engine
+    from sod_report import run_sod, sod_case
+    t0 = time.perf_counter()
+    p, b, s, geom = sod_case(kind, 100_000)
+    with Engine(p) as e:
+        rep = run_sod(e, b, s, geom)
+    emit("sod_100k_" + kind, t0, ok=True, **rep)
+
+
+CHECKS = {"conserved": check_conserved, "image": check_image,
+          "sod_variable": lambda: check_sod("variable"), "sod_fixed": lambda: check_sod("fixed")}
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or list(CHECKS)
+    rc = 0
+    for name in which:
+        try:
+            CHECKS[name]()
+        except Exception:
+            rc = 1
+            emit(name, time.perf_counter(), ok=False, error=traceback.format_exc()[-1500:])
+    sys.exit(rc)

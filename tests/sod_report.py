@@ -1,9 +1,9 @@
 """Sod shock tube against the exact Riemann solution (BASELINE.json configs[1]) — shared by the GPU test
-(tests/test_sod_analytic.py: the CUDA engine at the full 100k particles) and by the command line below, which can
+(tests/test_widen_sod.py: the CUDA engine at the full 100k particles) and by the command line below, which can
 also run the CPU oracle so that the two L1 errors sit side by side ("compared against the analytic solution and
 the reference").  Lives under tests/ because it may load the oracle; the product never imports it.
 
-    python tests/sod_report.py [--n 100000] [--t-end 0.2] [--engine | --oracle [--threads 8]] [--out report.json]
+    python tests/sod_report.py [--n 100000] [--fixed] [--oracle [--threads 8]] [--out report.json]
 """
 import argparse
 import json
@@ -17,9 +17,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-from summersph_b200 import default_params, MODE_VARIABLE_H, EVAL_TREE, EVAL_DENSITY, ics   # noqa: E402
+from summersph_b200 import default_params, MODE_FIXED_H, MODE_VARIABLE_H, EVAL_TREE, EVAL_DENSITY, ics   # noqa: E402
 from summersph_b200._abi import drift_report                                               # noqa: E402
-from summersph_b200.analytic import sod_core_mask, sod_l1_errors                           # noqa: E402
+from summersph_b200.analytic import sod_core_mask, riemann_exact, riemann_star, effective_gas, OMEGA_LATTICE                         # noqa: E402
 
 RHO_SCALE = 1e-9
 
@@ -27,8 +27,22 @@ RHO_SCALE = 1e-9
 def run_sod(sim, bodies, sinks, geom, gamma=1.4):
     """Advance `sim` (Engine or Oracle: same interface) with the reference's loop (dt0 = 1e-2, no final-step
     clipping, SUMMER_SPH.f90:872-879) to the first t >= geom['t_end'], then compare the core particles with the
-    exact solution at that t.  Returns the report dict."""
+    exact solution at that t.  Returns the report dict.
+
+    Two exact solutions are reported.  `nominal`: Sod's problem for the ideal gas the ICs describe (gamma = 1.4).
+    `effective`: the variable-h program divides every pressure term by its grad-h factor Omega (V:413-425), and its
+    Omega (V:455,487: 1 + h/(3 rho) sum m (3W - r dW/dr)/h) is ~3 on a uniform lattice, not ~1 — SURVEY.md §8(a) #9
+    keeps the sign as coded.  Momentum and energy equations both carry P/Omega, so the particles evolve an ideal
+    gas with P_eff = P/Omega0 and gamma_eff = 1 + (gamma-1)/Omega0; Omega0 is measured on the initial lattice.
+    In fixed-h mode there is no Omega (Omega0 = 1) and the two solutions coincide."""
+    variable = bool(sim.params.mode & MODE_VARIABLE_H)
     sim.upload(bodies, sinks)
+    omega0 = 1.0
+    if variable:
+        sim.evaluate(EVAL_TREE | EVAL_DENSITY)
+        m0 = sod_core_mask(bodies.x, bodies.y, bodies.z, 0.0, geom, gamma)
+        omega0 = float(np.median(sim.diag()["omega"][m0]))
+        sim.upload(bodies, sinks)
     first = sim.conserved()
     dt, t, steps = 1.0e-2, 0.0, 0
     t0 = time.perf_counter()
@@ -37,37 +51,54 @@ def run_sod(sim, bodies, sinks, geom, gamma=1.4):
         steps += 1
     wall = time.perf_counter() - t0
     last = sim.conserved()
-    sim.evaluate(EVAL_TREE | EVAL_DENSITY)             # rho and P of the final state (F:894-896)
+    sim.evaluate(EVAL_TREE | EVAL_DENSITY)             # rho of the final state (F:894-896)
     b, _ = sim.download()
     d = sim.diag()
     mask = sod_core_mask(b.x, b.y, b.z, t, geom, gamma)
-    rep = sod_l1_errors(b.x, d["rho"], b.vx, d["P"], t, mask, gamma, RHO_SCALE)
-    # plateau values between contact and shock / contact and rarefaction tail (exact: 0.26557 | 0.42632, v 0.92745, P 0.30313)
-    xs = b.x[mask] / t
-    post = mask.copy(); post[mask] = (xs > 1.15) & (xs < 1.5)
-    star_l = mask.copy(); star_l[mask] = (xs > 0.15) & (xs < 0.7)
-    rep.update(
-        n=len(b), steps=steps, t=t, dt_last=dt, wall_s=wall,
-        rho_post_shock=float(np.mean(d["rho"][post]) / RHO_SCALE) if post.any() else None,
-        rho_star_left=float(np.mean(d["rho"][star_l]) / RHO_SCALE) if star_l.any() else None,
-        v_star=float(np.mean(b.vx[post | star_l])) if (post | star_l).any() else None,
-        p_star=float(np.mean(d["P"][post | star_l]) / RHO_SCALE) if (post | star_l).any() else None,
-        drift={k: v for k, v in drift_report(first, last).items()},
-        geom={k: float(v) for k, v in geom.items()},
-    )
+    rho = d["rho"][mask] / RHO_SCALE; vx = b.vx[mask]; u = b.u[mask]; xi = b.x[mask] / t
+
+    def errors(om):
+        g_eff, st = effective_gas(gamma, om)
+        re, ve, pe = riemann_exact(xi, gamma=g_eff, **st)
+        ue = pe / ((g_eff - 1.0) * re)
+        ps, vs = riemann_star(gamma=g_eff, **st)
+        return {"gamma": g_eff, "p_star": ps * om, "v_star": vs,
+                "rho_l1": float(np.mean(np.abs(rho - re)) / np.mean(re)),
+                "v_l1": float(np.mean(np.abs(vx - ve)) / vs),
+                "u_l1": float(np.mean(np.abs(u - ue)) / np.mean(ue))}
+
+    rep = {
+        "mode": "variable_h" if variable else "fixed_h", "n": len(b), "n_core": int(np.count_nonzero(mask)),
+        "steps": steps, "t": t, "dt_last": dt, "wall_s": wall, "omega0": omega0,
+        "nominal": errors(1.0),
+        "effective": errors(omega0),
+        "drift": drift_report(first, last),
+        "geom": {k: float(v) for k, v in geom.items()},
+    }
     return rep
+
+
+def sod_case(kind, n=100_000):
+    """The two canonical runs of config 2.  'variable': "SUMMER_SPH - Variable.f90", tube sized for the waves of its
+    effective gas (Omega ~ 3) and run to t = 0.4 so that every h stays above the 0.01 below which that program
+    never updates h (V:528).  'fixed': SUMMER_SPH.f90 with smoothing = eta * right-hand spacing, t = 0.2.
+    Returns (params, bodies, sinks, geom)."""
+    if kind == "variable":
+        b, s, geom = ics.sod_box(n, 0.4, rho_scale=RHO_SCALE, omega=OMEGA_LATTICE)
+        return default_params(MODE_VARIABLE_H), b, s, geom
+    b, s, geom = ics.sod_box(n, 0.2, rho_scale=RHO_SCALE)
+    return default_params(MODE_FIXED_H, h_fixed=geom["h_right"]), b, s, geom
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=100_000)
-    ap.add_argument("--t-end", type=float, default=0.2)
     ap.add_argument("--oracle", action="store_true", help="run the CPU oracle instead of the CUDA engine")
     ap.add_argument("--threads", type=int, default=os.cpu_count() or 1)
+    ap.add_argument("--fixed", action="store_true", help="the fixed-h program instead of the variable-h one")
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
-    p = default_params(MODE_VARIABLE_H)
-    b, s, geom = ics.sod_box(a.n, a.t_end, rho_scale=RHO_SCALE)
+    p, b, s, geom = sod_case("fixed" if a.fixed else "variable", a.n)
     if a.oracle:
         from oracle.oracle import Oracle
         sim = Oracle(p, threads=a.threads)
