@@ -34,6 +34,10 @@ extern "C" {
 #define SPH_MODE_FIXED_H     0   /* SUMMER_SPH.f90                     */
 #define SPH_MODE_VARIABLE_H  1   /* "SUMMER_SPH - Variable.f90"        */
 #define SPH_FLAG_SOFT_USES_HI 2  /* "(test new)" softening 0.001*h_i (T:298), OR-ed into mode */
+#define SPH_FLAG_SINK_MERGE_SPIN 4 /* NOT the reference's behaviour (opt-in, OR-ed into mode): fill the sinks' `spin`
+                                      (declared F:33, never updated: "also need something to track the angular momentum",
+                                      F:509) at accretion, and run the sink merger the reference leaves as an empty stub
+                                      (check_sink_merger, V:1067-1073; call commented out at V:1159) after check_bounds */
 
 #define SPH_OK               0
 #define SPH_ERR_ARG         -1
@@ -193,7 +197,7 @@ int sph_fp64_peak(sph_ctx* ctx, double* tflops);
  *   out[0]  E_kin  = sum 1/2 m v.v over gas and sinks
  *   out[1]  E_int  = sum m u over gas
  *   out[2]  E_pot  = out[10] + out[11]
- *   out[3..5]  linear momentum, out[6..8] angular momentum about the origin (gas + sinks)
+ *   out[3..5]  linear momentum, out[6..8] angular momentum about the origin (gas + sinks, + sink spin when kept)
  *   out[9]  total mass
  *   out[10] gas-gas potential: 1/2 sum_i m_i G sum_{nodes accepted by the reference's Barnes-Hut walk for i,
  *           F:273-279 | V:294-300} M_node phi(dist/h)/h, phi = the cubic-spline softened potential whose
@@ -203,6 +207,13 @@ int sph_fp64_peak(sph_ctx* ctx, double* tflops);
  * holds none (it is then reused by the next evaluation); in a multi-GPU run every rank returns the same sums. */
 #define SPH_CONSERVED_COUNT 12
 int sph_conserved(sph_ctx* ctx, double* out, int32_t n_out);
+
+/* Spin of every sink (3 x n_sink doubles; any pointer may be NULL).  All zero unless the context was created with
+ * SPH_FLAG_SINK_MERGE_SPIN: the reference declares `sink%spin`, sets it to zero (F:695, V:580) and never updates it.
+ * With the flag, accretion and sink mergers move into the spin exactly the orbital angular momentum (about the origin)
+ * that the mass-weighted merge removes, so sum(m x cross v) + sum(spin) over sinks and gas only changes through forces;
+ * out[6..8] of sph_conserved then include the spin. */
+int sph_download_sink_spin(sph_ctx* ctx, double* spin_x, double* spin_y, double* spin_z);
 
 /* Column-density image of the resident gas: what the reference's post-processing script Density_Image.py
  * draws from a save file (a 120^3 density grid with fixed h = 1.25 summed along z, Density_Image.py:105-145),

@@ -170,6 +170,15 @@ class Oracle:
             lst = lst[:tot]
         return count, hsh, off, lst
 
+    def check_sink_merger(self):
+        self._l.orc_check_sink_merger(self._c)
+
+    def sink_spin(self):
+        _, ns = self.sizes()
+        sp = [np.zeros(ns) for _ in range(3)]
+        self._l.orc_download_sink_spin(self._c, *[_p(v) for v in sp])
+        return np.stack(sp, 1)
+
     def conserved(self):
         out = np.zeros(len(CONSERVED))
         self._l.orc_conserved(self._c, _p(out))

@@ -60,6 +60,7 @@ struct Particle {               // F:14-27 | V:14-29
 };
 struct Sink {                   // F:30-37
   double mass, radius, position[3], velocity[3], acceleration[3];
+  double spin[3];                     // F:33 `spin`: declared and zeroed by the reference, never updated (SPH_FLAG_SINK_MERGE_SPIN fills it)
 };
 struct Node {                   // F:40-49 | V:42-52 ; particle "copies" are index ranges + snapshots
   double center[3], size;
@@ -73,6 +74,7 @@ struct Node {                   // F:40-49 | V:42-52 ; particle "copies" are ind
 struct Oracle {
   sph_params p;
   bool variable_h, soft_hi;
+  bool sink_extras;               // SPH_FLAG_SINK_MERGE_SPIN: spin bookkeeping + the merger the reference leaves as a stub (V:1067-1073)
   int nq; double dq;
   std::vector<double> w_table, dw_table, grav_table;
   std::vector<Particle> bodies;
@@ -553,7 +555,7 @@ void check_sink_creation(Oracle& o) {
         if (dr < s.radius + 2 * b.s_length) return;                        // V:563-565
       }
       Sink ns;
-      for (int k = 0; k < 3; ++k) { ns.position[k] = b.position[k]; ns.velocity[k] = b.velocity[k]; ns.acceleration[k] = 0.0; }
+      for (int k = 0; k < 3; ++k) { ns.position[k] = b.position[k]; ns.velocity[k] = b.velocity[k]; ns.acceleration[k] = 0.0; ns.spin[k] = 0.0; }   // V:576-580
       ns.mass = 0.00000000001; ns.radius = 2 * b.s_length;                 // V:581-582
       o.sinks.push_back(ns);
       return;
@@ -586,6 +588,13 @@ void sink2gasdists(const Oracle& o, const Sink& s, int ni, std::vector<char>& ke
   }
 }
 
+// acc += m * (x cross v)
+inline void cross_add(double* acc, double m, const double* x, const double* v) {
+  acc[0] = acc[0] + m * (x[1] * v[2] - x[2] * v[1]);
+  acc[1] = acc[1] + m * (x[2] * v[0] - x[0] * v[2]);
+  acc[2] = acc[2] + m * (x[0] * v[1] - x[1] * v[0]);
+}
+
 template <class T, class M> void pack_vec(std::vector<T>& v, const M& keep) {
   size_t w = 0;
   for (size_t i = 0; i < v.size(); ++i) if (keep[i]) { if (w != i) v[w] = v[i]; ++w; }
@@ -598,17 +607,25 @@ void initiate_sink_accretion(Oracle& o) {
   for (auto& s : o.sinks) {
     std::fill(keep.begin(), keep.end(), 1);
     sink2gasdists(o, s, 0, keep);
-    double sm = 0.0, sp[3] = {0, 0, 0}, sv[3] = {0, 0, 0};
+    double sm = 0.0, sp[3] = {0, 0, 0}, sv[3] = {0, 0, 0}, la[3] = {0, 0, 0}; size_t n_acc = 0;
     for (size_t j = 0; j < n; ++j) if (!keep[j]) {
       const Particle& b = o.bodies[j];
       sm = sm + b.mass;
       for (int d = 0; d < 3; ++d) { sp[d] = sp[d] + b.mass * b.position[d]; sv[d] = sv[d] + b.mass * b.velocity[d]; }
-      any_keep[j] = 0;
+      cross_add(la, b.mass, b.position, b.velocity);
+      any_keep[j] = 0; ++n_acc;
     }
+    double l_before[3] = {la[0], la[1], la[2]};
+    cross_add(l_before, s.mass, s.position, s.velocity);
     double new_mass = s.mass + sm;                                         // F:497
     for (int d = 0; d < 3; ++d) s.position[d] = (s.mass * s.position[d] + sp[d]) / new_mass;   // F:498-501
     for (int d = 0; d < 3; ++d) s.velocity[d] = (s.mass * s.velocity[d] + sv[d]) / new_mass;   // F:503-506
     s.mass = s.mass + sm;                                                  // F:508
+    if (o.sink_extras && n_acc > 0) {     // what the orbit lost goes into the spin: sum of L over sink + accreted is unchanged
+      double l_after[3] = {0, 0, 0};
+      cross_add(l_after, s.mass, s.position, s.velocity);
+      for (int d = 0; d < 3; ++d) s.spin[d] = s.spin[d] + (l_before[d] - l_after[d]);
+    }
   }
   pack_vec(o.bodies, any_keep);                                            // F:546-556
 }
@@ -631,6 +648,41 @@ void check_bounds(Oracle& o) {                                             // F:
   }
 }
 
+// ---- sink merger: NOT in the reference (check_sink_merger is an empty stub, V:1067-1073, its call commented
+// out at V:1159).  Opt-in (SPH_FLAG_SINK_MERGE_SPIN), run where that call sits: after check_bounds.
+// Two sinks with mass merge when one centre lies inside the other's accretion radius: |x_a - x_b| < max(R_a, R_b).
+// The lower index survives with the summed mass, the mass-weighted position, velocity and acceleration, the larger
+// radius and spin = S_a + S_b + (orbital L of the two about the origin - orbital L of the merged sink); the higher
+// index is removed (order preserving).  Pairs are scanned (a, b > a) ascending and the scan restarts after a merge.
+void check_sink_merger(Oracle& o) {
+  bool merged = true;
+  while (merged) {
+    merged = false;
+    for (size_t a = 0; a < o.sinks.size() && !merged; ++a)
+      for (size_t b = a + 1; b < o.sinks.size() && !merged; ++b) {
+        Sink& A = o.sinks[a]; Sink& B = o.sinks[b];
+        if (!(A.mass > 0.0 && B.mass > 0.0)) continue;
+        double d[3]; for (int k = 0; k < 3; ++k) d[k] = A.position[k] - B.position[k];
+        const double dr = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+        if (!(dr < std::max(A.radius, B.radius))) continue;
+        double l_before[3] = {0, 0, 0}, l_after[3] = {0, 0, 0};
+        cross_add(l_before, A.mass, A.position, A.velocity);
+        cross_add(l_before, B.mass, B.position, B.velocity);
+        const double M = A.mass + B.mass;
+        for (int k = 0; k < 3; ++k) {
+          A.position[k] = (A.mass * A.position[k] + B.mass * B.position[k]) / M;
+          A.velocity[k] = (A.mass * A.velocity[k] + B.mass * B.velocity[k]) / M;
+          A.acceleration[k] = (A.mass * A.acceleration[k] + B.mass * B.acceleration[k]) / M;
+        }
+        A.mass = M; A.radius = std::max(A.radius, B.radius);
+        cross_add(l_after, A.mass, A.position, A.velocity);
+        for (int k = 0; k < 3; ++k) A.spin[k] = A.spin[k] + B.spin[k] + (l_before[k] - l_after[k]);
+        o.sinks.erase(o.sinks.begin() + (long)b);
+        merged = true;
+      }
+  }
+}
+
 // one body of simulate's loop: F:886-928 | V:1120-1162
 void step(Oracle& o, double& dt, double& t) {
   evaluate(o, SPH_EVAL_ALL);
@@ -644,6 +696,7 @@ void step(Oracle& o, double& dt, double& t) {
   bool any_mass = false; for (auto& s : o.sinks) if (s.mass > 0.0) any_mass = true;
   if (any_mass) initiate_sink_accretion(o);                                // F:919
   check_bounds(o);
+  if (o.sink_extras) check_sink_merger(o);                                 // V:1159 (commented out in the reference)
 }
 
 // ---- conserved sums: NOT in the reference (it keeps no energy / momentum bookkeeping) ----------------
@@ -701,6 +754,7 @@ void conserved(Oracle& o, double* out) {
     const Sink& s = o.sinks[a];
     if (!(s.mass > 0.0)) continue;
     add(s.mass, s.position, s.velocity);
+    if (o.sink_extras) for (int d = 0; d < 3; ++d) L[d] += s.spin[d];
     for (size_t b = 0; b < a; ++b) {
       const Sink& t = o.sinks[b];
       if (!(t.mass > 0.0)) continue;
@@ -726,6 +780,7 @@ orc_ctx* orc_create(const sph_params* p, int threads) {
   o.p = *p;
   o.variable_h = (p->mode & SPH_MODE_VARIABLE_H) != 0;
   o.soft_hi = (p->mode & SPH_FLAG_SOFT_USES_HI) != 0;
+  o.sink_extras = (p->mode & SPH_FLAG_SINK_MERGE_SPIN) != 0;
   o.nq = p->nq; o.dq = 2.0 / p->nq;                                        // F:10
   o.record_ngb = false; o.threads = threads < 1 ? 1 : threads;
 #ifdef _OPENMP
@@ -857,5 +912,9 @@ int64_t orc_download_neighbours(orc_ctx* c, int32_t* count, uint64_t* hash, int6
 }
 void orc_counters(orc_ctx* c, sph_counts* out) { *out = c->o.cnt; }
 void orc_conserved(orc_ctx* c, double* out12) { conserved(c->o, out12); }
+void orc_check_sink_merger(orc_ctx* c) { check_sink_merger(c->o); }
+void orc_download_sink_spin(orc_ctx* c, double* sx, double* sy, double* sz) {
+  for (size_t i = 0; i < c->o.sinks.size(); ++i) { sx[i] = c->o.sinks[i].spin[0]; sy[i] = c->o.sinks[i].spin[1]; sz[i] = c->o.sinks[i].spin[2]; }
+}
 
 }  // extern "C"

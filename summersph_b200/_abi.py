@@ -7,6 +7,7 @@ import ctypes as C
 MODE_FIXED_H = 0        # SUMMER_SPH.f90
 MODE_VARIABLE_H = 1     # "SUMMER_SPH - Variable.f90"
 FLAG_SOFT_USES_HI = 2   # "(test new)" softening 0.001*h_i (T:298)
+FLAG_SINK_MERGE_SPIN = 4   # opt-in, not the reference: sink spin bookkeeping (F:33,509) + the merger stub V:1067-1073
 
 EVAL_TREE, EVAL_DENSITY, EVAL_GRAVITY, EVAL_SINKS, EVAL_SPH = 1, 2, 4, 8, 16
 EVAL_ALL = 31

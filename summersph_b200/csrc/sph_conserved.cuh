@@ -11,7 +11,7 @@
 //             phi is the cubic-spline softened point-mass potential whose radial derivative is the reference's
 //             g(q) / q^2 (the polynomials of init_grav_kernel_table, F:91,94), -1/q beyond q = 2.
 //   E_sink  = -G sum_sinks sum_gas m_s m_j / r  -  G sum_{sink pairs} m_a m_b / r     (unsoftened, F:559-591)
-//   P, L    = sum m v, sum m x cross v over gas and sinks; M = total mass.
+//   P, L    = sum m v, sum m x cross v over gas and sinks (+ the sinks' spin when SPH_FLAG_SINK_MERGE_SPIN keeps it); M = total mass.
 // The walk here is one thread per particle over the preorder octree with skip pointers (GNode.next): a diagnostic
 // called a few times per run, not a hot kernel.
 #pragma once
@@ -96,7 +96,7 @@ k_conserved_partial(int n, int n_nodes, DevParams P, StateArrays s, const GNode*
 
 // one warp: fold the block partials in block order, add the sinks' own terms, write the CONS_FIELDS outputs
 __global__ void k_conserved_final(int nblocks, const double* __restrict__ partial, DevParams P, int n_sink, SinkArrays S,
-                                  double* __restrict__ out) {
+                                  const double* __restrict__ spin, double* __restrict__ out) {
   __shared__ double tot[CONS_SUMS];
   const int l = threadIdx.x;
   for (int k = 0; k < CONS_SUMS; ++k) {
@@ -116,6 +116,7 @@ __global__ void k_conserved_final(int nblocks, const double* __restrict__ partia
     ekin += 0.5 * ma * (vx * vx + vy * vy + vz * vz);
     px += ma * vx; py += ma * vy; pz += ma * vz;
     lx += ma * (y * vz - z * vy); ly += ma * (z * vx - x * vz); lz += ma * (x * vy - y * vx);
+    if (spin) { lx += spin[a]; ly += spin[SPH_MAX_SINKS + a]; lz += spin[2 * SPH_MAX_SINKS + a]; }   // SPH_FLAG_SINK_MERGE_SPIN
     mass += ma;
     for (int b = 0; b < a; ++b) {
       const double mb = S.m[b];

@@ -93,6 +93,7 @@ struct sph_ctx {
   std::vector<void*> ipc_opened; int* d_flag = nullptr; void* d_blob = nullptr; size_t blob_cap = 0;
   int g0 = 0, g1 = 0, p0 = 0, p1 = 0;
   double* cons_partial = nullptr; double* cons_out = nullptr;   // sph_conserved: block partials, result slots
+  double* sink_spin = nullptr; int sink_extras = 0;               // SPH_FLAG_SINK_MERGE_SPIN: spin[3][SPH_MAX_SINKS]; null pointer into the kernels when off
   double* img_table = nullptr;                                    // sph_column_density: line-of-sight integral of the M4 shape
 };
 
@@ -756,7 +757,7 @@ int step(sph_ctx* c) {
     if ((r = run_hiter(c))) return r;                                         // V:1152
     stage_begin(c, ST_CULL);
     LAUNCH(k_create_scan, cdiv(n, T), T, 0, n, c->dp, state_of(c, c->cur), c->sc);          // V:1155
-    LAUNCH(k_create_apply, 1, 32, 0, state_of(c, c->cur), c->S, c->sc);
+    LAUNCH(k_create_apply, 1, 32, 0, state_of(c, c->cur), c->S, c->sc, c->sink_spin);
     stage_end(c);
   }
   stage_begin(c, ST_CULL);
@@ -774,8 +775,9 @@ int step(sph_ctx* c) {
     if (dk.Current() != c->acc_key[0]) std::swap(c->acc_key[0], c->acc_key[1]);
     if (dv.Current() != c->acc_val[0]) std::swap(c->acc_val[0], c->acc_val[1]);
   }
-  LAUNCH(k_accrete_apply, 1, SPH_MAX_SINKS, 0, n_acc, c->acc_key[0], c->acc_val[0], state_of(c, c->cur), c->S, c->sc);
-  if (c->dp.variable_h) LAUNCH(k_cull_sinks, 1, 32, 0, c->dp, c->S, c->sc);   // V:613
+  LAUNCH(k_accrete_apply, 1, SPH_MAX_SINKS, 0, n_acc, c->acc_key[0], c->acc_val[0], state_of(c, c->cur), c->S, c->sc, c->sink_spin);
+  if (c->dp.variable_h) LAUNCH(k_cull_sinks, 1, 32, 0, c->dp, c->S, c->sc, c->sink_spin);   // V:613
+  if (c->sink_extras) LAUNCH(k_sink_merge, 1, 32, 0, c->S, c->sc, c->sink_spin);            // V:1159 (commented out in the reference)
   const int n_removed = c->h_sc->n_removed;
   // reset per-step device counters
   CK(cudaMemsetAsync(&c->sc->n_removed, 0, sizeof(int) * 2, c->stream));
@@ -902,6 +904,8 @@ int sph_create(const sph_params* p, int32_t device, sph_ctx** out) {
   { double* b = c->sink_buf; const int M = SPH_MAX_SINKS;
     c->S = SinkArrays{b, b + M, b + 2 * M, b + 3 * M, b + 4 * M, b + 5 * M, b + 6 * M, b + 7 * M, b + 8 * M, b + 9 * M, b + 10 * M}; }
   cudaMemset(c->sink_buf, 0, (size_t)SPH_MAX_SINKS * 11 * 8);
+  c->sink_extras = (p->mode & SPH_FLAG_SINK_MERGE_SPIN) ? 1 : 0;
+  if (c->sink_extras) { if ((r = dalloc(c, &c->sink_spin, (size_t)SPH_MAX_SINKS * 3))) return fail(r); cudaMemset(c->sink_spin, 0, (size_t)SPH_MAX_SINKS * 3 * 8); }
   if (cudaMallocHost((void**)&c->h_sc, sizeof(SimScalars)) != cudaSuccess || cudaMallocHost((void**)&c->h_ctr, sizeof(WalkCounters)) != cudaSuccess) { c->err = "cudaMallocHost failed"; return fail(SPH_ERR_OOM); }
   std::memset(c->h_sc, 0, sizeof(SimScalars)); c->h_sc->create_cand = ~0ull; c->h_sc->dt = 1.0e-2;
   cudaMemcpy(c->sc, c->h_sc, sizeof(SimScalars), cudaMemcpyHostToDevice);
@@ -939,7 +943,7 @@ int sph_destroy(sph_ctx* c) {
   F(c->rho); F(c->omega); F(c->prs); F(c->cs); F(c->por2); F(c->ax); F(c->ay); F(c->az); F(c->udot); F(c->adot);
   F(c->node_count); F(c->gsize); F(c->gfirst); F(c->groups); F(c->level); F(c->lcx); F(c->lcy); F(c->lcz); F(c->reach); F(c->bvh); F(c->nodes); F(c->node_part); F(c->parent); F(c->nchild);
   F(c->nl_pool); F(c->nl_head); F(c->nl_ctl); F(c->ggroups); F(c->gbvh); F(c->seg_cnt); F(c->seg_off); F(c->wnodes); F(c->wcount); F(c->wstart); F(c->widx); F(c->grav_spill);
-  F(c->cons_partial); F(c->cons_out); F(c->img_table);
+  F(c->cons_partial); F(c->cons_out); F(c->img_table); F(c->sink_spin);
   F(c->arrive); F(c->cnt); F(c->off); F(c->root); F(c->partial); F(c->cub_tmp); F(c->d_wt); F(c->d_dwt); F(c->d_gt);
   F(c->sink_buf); F(c->sink_partial); F(c->sc); F(c->ctr); F(c->work); F(c->keep); F(c->d_nsel); F(c->pos); F(c->stage_d); F(c->stage_d2);
   if (c->h_sc) cudaFreeHost(c->h_sc);
@@ -998,6 +1002,7 @@ int sph_upload(sph_ctx* c, int64_t n, const double* x, const double* y, const do
   for (int s = 0; s < ns; ++s) hb[(size_t)7 * M + s] = (srad && srad[s] == srad[s]) ? srad[s] : c->p.sink_radius;
   c->n_sink = ns > 0 ? ns : 1;
   CK(cudaMemcpyAsync(c->sink_buf, hb.data(), hb.size() * 8, cudaMemcpyHostToDevice, c->stream));
+  if (c->sink_spin) CK(cudaMemsetAsync(c->sink_spin, 0, (size_t)SPH_MAX_SINKS * 3 * 8, c->stream));   // F:695 spin = 0
   CK(cudaStreamSynchronize(c->stream));
   c->h_sc->n_sink = c->n_sink; c->h_sc->n_removed = 0; c->h_sc->n_accreted = 0; c->h_sc->err = 0; c->h_sc->create_cand = ~0ull;
   CK(cudaMemcpyAsync(c->sc, c->h_sc, sizeof(SimScalars), cudaMemcpyHostToDevice, c->stream));
@@ -1243,7 +1248,7 @@ int sph_conserved(sph_ctx* c, double* out, int32_t n_out) {
   const int nb = std::max(1, std::min(cdiv(n, CONS_THREADS), std::min(CONS_MAX_BLOCKS, c->n_sm * 16)));
   LAUNCH(k_conserved_partial, nb, CONS_THREADS, 0, n, (int)c->counts.n_nodes, c->dp, state_of(c, c->cur), c->nodes, c->node_part,
          c->n_sink, c->S, c->cons_partial);
-  LAUNCH(k_conserved_final, 1, 32, 0, nb, c->cons_partial, c->dp, c->n_sink, c->S, c->cons_out);
+  LAUNCH(k_conserved_final, 1, 32, 0, nb, c->cons_partial, c->dp, c->n_sink, c->S, c->sink_spin, c->cons_out);
   double host[CONS_FIELDS];
   CK(cudaMemcpyAsync(host, c->cons_out, sizeof(host), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaMemcpyAsync(c->h_sc, c->sc, sizeof(SimScalars), cudaMemcpyDeviceToHost, c->stream));
@@ -1290,6 +1295,19 @@ int sph_column_density(sph_ctx* c, int32_t axis, double u0, double u1, double v0
   if (e == cudaSuccess) e = cudaGetLastError();
   cudaFree(d_img);
   if (e != cudaSuccess) { c->err = std::string("sph_column_density: ") + cudaGetErrorString(e); return SPH_ERR_CUDA; }
+  return SPH_OK;
+}
+
+int sph_download_sink_spin(sph_ctx* c, double* sx, double* sy, double* sz) {
+  if (!c) return SPH_ERR_ARG;
+  cudaSetDevice(c->device);
+  double* dst[3] = {sx, sy, sz};
+  for (int k = 0; k < 3; ++k) {
+    if (!dst[k] || c->n_sink == 0) continue;
+    if (c->sink_spin) CK(cudaMemcpyAsync(dst[k], c->sink_spin + (size_t)k * SPH_MAX_SINKS, (size_t)c->n_sink * 8, cudaMemcpyDeviceToHost, c->stream));
+    else std::memset(dst[k], 0, (size_t)c->n_sink * 8);        // the reference's sinks keep spin = 0 (F:695)
+  }
+  CK(cudaStreamSynchronize(c->stream));
   return SPH_OK;
 }
 

@@ -101,7 +101,7 @@ __global__ void k_create_scan(int n, DevParams P, StateArrays s, SimScalars* sc)
   if (s.m[i] * ((e * e) * e) > 0.5)
     atomicMin(&sc->create_cand, ((unsigned long long)(unsigned)s.id[i] << 32) | (unsigned)i);
 }
-__global__ void k_create_apply(StateArrays s, SinkArrays S, SimScalars* sc) {
+__global__ void k_create_apply(StateArrays s, SinkArrays S, SimScalars* sc, double* __restrict__ spin) {
   if (threadIdx.x != 0) return;
   const unsigned long long c = sc->create_cand;
   sc->create_cand = ~0ull;
@@ -118,6 +118,7 @@ __global__ void k_create_apply(StateArrays s, SinkArrays S, SimScalars* sc) {
   S.vx[ns] = s.vx[i]; S.vy[ns] = s.vy[i]; S.vz[ns] = s.vz[i];
   S.ax[ns] = S.ay[ns] = S.az[ns] = 0.0;
   S.m[ns] = 0.00000000001; S.radius[ns] = 2.0 * s.h[i];                            // V:581-582
+  if (spin) spin[ns] = spin[SPH_MAX_SINKS + ns] = spin[2 * SPH_MAX_SINKS + ns] = 0.0;  // V:580
   sc->n_sink = ns + 1;
 }
 
@@ -179,20 +180,32 @@ __global__ void k_flags(int n, DevParams P, StateArrays s, const uint64_t* __res
 }
 
 // sink update from the (sink, number)-sorted accretion list: sums in ascending number like sum(pack(...)) F:497-508
+// `spin` (null unless SPH_FLAG_SINK_MERGE_SPIN): what the orbit loses goes into the sink's spin, so that the summed
+// angular momentum of sink + accreted gas about the origin is unchanged (not in the reference, F:509 asks for it).
 __global__ void k_accrete_apply(int n_acc, const unsigned long long* __restrict__ acc_key, const int* __restrict__ acc_val,
-                                StateArrays s, SinkArrays S, SimScalars* sc) {
+                                StateArrays s, SinkArrays S, SimScalars* sc, double* __restrict__ spin) {
   const int j = threadIdx.x;
   if (j >= sc->n_sink || !sc->any_sink_mass) return;
-  double sm = 0.0, sp[3] = {0.0, 0.0, 0.0}, sv[3] = {0.0, 0.0, 0.0};
+  double sm = 0.0, sp[3] = {0.0, 0.0, 0.0}, sv[3] = {0.0, 0.0, 0.0}, lb[3] = {0.0, 0.0, 0.0};
+  int n_mine = 0;
   for (int e = 0; e < n_acc; ++e) {
     if ((int)(acc_key[e] >> 32) != j) continue;
     const int i = acc_val[e];
     const double mi = s.m[i];
+    if (spin) {
+      const double x = s.x[i], y = s.y[i], z = s.z[i], vx = s.vx[i], vy = s.vy[i], vz = s.vz[i];
+      lb[0] = lb[0] + mi * (y * vz - z * vy); lb[1] = lb[1] + mi * (z * vx - x * vz); lb[2] = lb[2] + mi * (x * vy - y * vx);
+      ++n_mine;
+    }
     sm = __dadd_rn(sm, mi);
     sp[0] = __dadd_rn(sp[0], __dmul_rn(mi, s.x[i])); sp[1] = __dadd_rn(sp[1], __dmul_rn(mi, s.y[i])); sp[2] = __dadd_rn(sp[2], __dmul_rn(mi, s.z[i]));
     sv[0] = __dadd_rn(sv[0], __dmul_rn(mi, s.vx[i])); sv[1] = __dadd_rn(sv[1], __dmul_rn(mi, s.vy[i])); sv[2] = __dadd_rn(sv[2], __dmul_rn(mi, s.vz[i]));
   }
   const double ms = S.m[j];
+  if (spin && n_mine > 0) {
+    const double x = S.x[j], y = S.y[j], z = S.z[j], vx = S.vx[j], vy = S.vy[j], vz = S.vz[j];
+    lb[0] = lb[0] + ms * (y * vz - z * vy); lb[1] = lb[1] + ms * (z * vx - x * vz); lb[2] = lb[2] + ms * (x * vy - y * vx);
+  }
   const double nm = __dadd_rn(ms, sm);                                                          // F:497
   S.x[j] = __ddiv_rn(__dadd_rn(__dmul_rn(ms, S.x[j]), sp[0]), nm);                              // F:498-501
   S.y[j] = __ddiv_rn(__dadd_rn(__dmul_rn(ms, S.y[j]), sp[1]), nm);
@@ -201,6 +214,12 @@ __global__ void k_accrete_apply(int n_acc, const unsigned long long* __restrict_
   S.vy[j] = __ddiv_rn(__dadd_rn(__dmul_rn(ms, S.vy[j]), sv[1]), nm);
   S.vz[j] = __ddiv_rn(__dadd_rn(__dmul_rn(ms, S.vz[j]), sv[2]), nm);
   S.m[j] = __dadd_rn(ms, sm);                                                                   // F:508
+  if (spin && n_mine > 0) {
+    const double x = S.x[j], y = S.y[j], z = S.z[j], vx = S.vx[j], vy = S.vy[j], vz = S.vz[j], m2 = S.m[j];
+    spin[j] = spin[j] + (lb[0] - (0.0 + m2 * (y * vz - z * vy)));
+    spin[SPH_MAX_SINKS + j] = spin[SPH_MAX_SINKS + j] + (lb[1] - (0.0 + m2 * (z * vx - x * vz)));
+    spin[2 * SPH_MAX_SINKS + j] = spin[2 * SPH_MAX_SINKS + j] + (lb[2] - (0.0 + m2 * (x * vy - y * vx)));
+  }
 }
 
 __global__ void k_any_sink_mass(SinkArrays S, SimScalars* sc) {
@@ -211,7 +230,7 @@ __global__ void k_any_sink_mass(SinkArrays S, SimScalars* sc) {
 }
 
 // V:610,613 cull sinks outside the bounding cube (order preserving)
-__global__ void k_cull_sinks(DevParams P, SinkArrays S, SimScalars* sc) {
+__global__ void k_cull_sinks(DevParams P, SinkArrays S, SimScalars* sc, double* __restrict__ spin) {
   if (threadIdx.x != 0) return;
   const int ns = sc->n_sink; int w = 0;
   for (int j = 0; j < ns; ++j) {
@@ -219,11 +238,56 @@ __global__ void k_cull_sinks(DevParams P, SinkArrays S, SimScalars* sc) {
       if (w != j) {
         S.x[w] = S.x[j]; S.y[w] = S.y[j]; S.z[w] = S.z[j]; S.vx[w] = S.vx[j]; S.vy[w] = S.vy[j]; S.vz[w] = S.vz[j];
         S.m[w] = S.m[j]; S.radius[w] = S.radius[j]; S.ax[w] = S.ax[j]; S.ay[w] = S.ay[j]; S.az[w] = S.az[j];
+        if (spin) for (int k = 0; k < 3; ++k) spin[k * SPH_MAX_SINKS + w] = spin[k * SPH_MAX_SINKS + j];
       }
       ++w;
     }
   }
   sc->n_sink = w;
+}
+
+// Sink merger: NOT in the reference (check_sink_merger is an empty stub, V:1067-1073; its call is commented out at
+// V:1159).  Opt-in (SPH_FLAG_SINK_MERGE_SPIN), run where that call sits.  Two sinks with mass merge when one centre lies
+// inside the other's accretion radius, |x_a - x_b| < max(R_a, R_b): the lower index survives with the summed mass, the
+// mass-weighted position / velocity / acceleration, the larger radius and spin = S_a + S_b + (orbital L of the two -
+// orbital L of the merged sink); the higher index is removed, order preserved.  Pairs (a, b > a) are scanned ascending
+// and the scan restarts after every merge.  One thread: at most SPH_MAX_SINKS sinks.
+__global__ void k_sink_merge(SinkArrays S, SimScalars* sc, double* __restrict__ spin) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int M = SPH_MAX_SINKS;
+  int ns = sc->n_sink;
+  bool merged = true;
+  while (merged) {
+    merged = false;
+    for (int a = 0; a < ns && !merged; ++a)
+      for (int b = a + 1; b < ns && !merged; ++b) {
+        const double ma = S.m[a], mb = S.m[b];
+        if (!(ma > 0.0 && mb > 0.0)) continue;
+        const double dx = S.x[a] - S.x[b], dy = S.y[a] - S.y[b], dz = S.z[a] - S.z[b];
+        const double dr = sqrt(dx * dx + dy * dy + dz * dz);
+        const double R = fmax(S.radius[a], S.radius[b]);
+        if (!(dr < R)) continue;
+        double lb[3];
+        lb[0] = 0.0 + ma * (S.y[a] * S.vz[a] - S.z[a] * S.vy[a]); lb[1] = 0.0 + ma * (S.z[a] * S.vx[a] - S.x[a] * S.vz[a]); lb[2] = 0.0 + ma * (S.x[a] * S.vy[a] - S.y[a] * S.vx[a]);
+        lb[0] = lb[0] + mb * (S.y[b] * S.vz[b] - S.z[b] * S.vy[b]); lb[1] = lb[1] + mb * (S.z[b] * S.vx[b] - S.x[b] * S.vz[b]); lb[2] = lb[2] + mb * (S.x[b] * S.vy[b] - S.y[b] * S.vx[b]);
+        const double Mt = ma + mb;
+        double* f[9] = {S.x, S.y, S.z, S.vx, S.vy, S.vz, S.ax, S.ay, S.az};
+        for (int k = 0; k < 9; ++k) f[k][a] = (ma * f[k][a] + mb * f[k][b]) / Mt;
+        S.m[a] = Mt; S.radius[a] = R;
+        const double l0 = 0.0 + Mt * (S.y[a] * S.vz[a] - S.z[a] * S.vy[a]), l1 = 0.0 + Mt * (S.z[a] * S.vx[a] - S.x[a] * S.vz[a]), l2 = 0.0 + Mt * (S.x[a] * S.vy[a] - S.y[a] * S.vx[a]);
+        spin[a] = spin[a] + spin[b] + (lb[0] - l0);
+        spin[M + a] = spin[M + a] + spin[M + b] + (lb[1] - l1);
+        spin[2 * M + a] = spin[2 * M + a] + spin[2 * M + b] + (lb[2] - l2);
+        for (int j = b; j + 1 < ns; ++j) {
+          for (int k = 0; k < 9; ++k) f[k][j] = f[k][j + 1];
+          S.m[j] = S.m[j + 1]; S.radius[j] = S.radius[j + 1];
+          for (int k = 0; k < 3; ++k) spin[k * M + j] = spin[k * M + j + 1];
+        }
+        --ns;
+        merged = true;
+      }
+  }
+  sc->n_sink = ns;
 }
 
 __global__ void k_iota(int n, int* a) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) a[i] = i; }

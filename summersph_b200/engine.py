@@ -62,6 +62,7 @@ def load_library(path=None):
     lib.sph_timer_stop.argtypes = [vp, C.POINTER(dbl)]
     lib.sph_fp64_peak.argtypes = [vp, C.POINTER(dbl)]
     lib.sph_conserved.argtypes = [vp, vp, i32]
+    lib.sph_download_sink_spin.argtypes = [vp, vp, vp, vp]
     lib.sph_column_density.argtypes = [vp, i32, dbl, dbl, dbl, dbl, i32, i32, vp]
     if path is None:
         _LIB = lib
@@ -216,6 +217,13 @@ class Engine:
         out = np.zeros(len(CONSERVED))
         self._ck(self._l.sph_conserved(self._c, _p(out), len(out)))
         return conserved_dict(out)
+
+    def sink_spin(self):
+        """(n_sink, 3) array of sink spins (`sph_download_sink_spin`): zero unless FLAG_SINK_MERGE_SPIN is set."""
+        _, ns = self.sizes()
+        sp = [np.zeros(ns) for _ in range(3)]
+        self._ck(self._l.sph_download_sink_spin(self._c, *[_p(v) for v in sp]))
+        return np.stack(sp, 1)
 
     def column_density(self, axis="z", extent=(-100.0, 100.0, -100.0, 100.0), shape=(512, 512)):
         """Column density of the resident gas projected along `axis` (`sph_column_density`): array of shape
