@@ -74,7 +74,31 @@ def check_sod(kind):
     emit("sod_100k_" + kind, t0, ok=True, **rep)
 
 
-CHECKS = {"conserved": check_conserved, "image": check_image,
+def check_merger():
+    from summersph_b200 import default_params, MODE_VARIABLE_H, FLAG_SINK_MERGE_SPIN, ics, Sinks
+    from summersph_b200.engine import Engine
+    from oracle.oracle import Oracle
+    from test_widen_sink_merger import compare_sinks, orbital_L, sinks_L
+    t0 = time.perf_counter()
+    p = default_params(MODE_VARIABLE_H | FLAG_SINK_MERGE_SPIN, bounding_size=85.0)
+    b, _ = ics.keplerian_disc(8_000, seed=9)
+    s = Sinks([0.0, 40.0, 43.0], [0.0, 0.0, 1.0], [0.0, 0.0, 0.0], [0.0, 0.0, 0.2], [0.0, 6.0, 5.5], [0.0, 0.0, 0.0],
+              [1.0, 0.01, 0.02], [13.0, 6.0, 2.0])
+    L_scale = np.linalg.norm(orbital_L(b.m, b.x, b.y, b.z, b.vx, b.vy, b.vz)) + np.linalg.norm(sinks_L(s))
+    o = Oracle(p); o.upload(b, s)
+    with Engine(p) as e:
+        e.upload(b, s)
+        dto = dte = 0.01; to = te = 0.0
+        for _ in range(2):
+            dto, to = o.step(dto, to); dte, te = e.step(dte, te)
+            assert o.sizes() == e.sizes() and (dto, to) == (dte, te)
+            compare_sinks(e, o, L_scale)
+        ce, co = e.conserved(), o.conserved()
+        emit("merger", t0, ok=True, sizes=list(e.sizes()), spin_engine=e.sink_spin().tolist(), spin_oracle=o.sink_spin().tolist(),
+             lz_engine=ce["lz"], lz_oracle=co["lz"])
+
+
+CHECKS = {"conserved": check_conserved, "image": check_image, "merger": check_merger,
           "sod_variable": lambda: check_sod("variable"), "sod_fixed": lambda: check_sod("fixed")}
 
 if __name__ == "__main__":
