@@ -32,6 +32,12 @@ struct SinkArrays { double *x, *y, *z, *vx, *vy, *vz, *m, *radius, *ax, *ay, *az
 #ifndef GW_ILP
 #define GW_ILP 2            // interaction-list entries in flight per lane
 #endif
+#ifndef GW_SUBLISTS
+#define GW_SUBLISTS 1       // experiment (scripts/build_variant.sh sub4 "-DGW_SUBLISTS=4"): the interaction list is read through
+                            // GW_SUBLISTS index lists, one per group of 32 / GW_SUBLISTS consecutive lanes, each holding only the
+                            // entries whose mask touches that group, so a sparse entry costs evaluation slots only in the lane
+                            // groups it belongs to.  Every lane still adds its own terms in list order.  1 = one list for the warp.
+#endif
 #define GW_STACK 384        // (node, mask) entries per warp in shared memory
 #define GW_LIST  64         // interaction-list entries per warp (evaluated when more than 32 are waiting)
 #define GW_SPILL 8192       // per-warp overflow entries in global memory (never reached in practice; loud if it is)
@@ -62,6 +68,9 @@ struct GravWarpSmem {
   double   mcx[32], mcy[32], mcz[32], msize[32], mlo[32], mhi[32];   // mixed nodes of the current trip: COM, size, d2 band of the cheap FP64 test
   float4   mf[32];                                                   // the same nodes for the FP32 screen: COM relative to the run's origin, size^2 / theta^2
   unsigned mmask[32];
+#if GW_SUBLISTS > 1
+  unsigned char sub[GW_SUBLISTS][GW_LIST];   // per lane group: positions (in lxy / lzg / lmask) of the entries that touch the group
+#endif
 };
 
 // 1/sqrt(x): MUFU seed (~2^-20) + one Halley step (cubic: ~2^-58), x > 0
@@ -123,6 +132,32 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
 #pragma unroll
     for (int u = 0; u < GW_ILP; ++u) gx[u] = gy[u] = gz[u] = 0.0;
 
+#if GW_SUBLISTS > 1
+    int sl[GW_SUBLISTS];                       // entries in each lane group's index list (warp-uniform)
+#pragma unroll
+    for (int q = 0; q < GW_SUBLISTS; ++q) sl[q] = 0;
+    const int myq = lane / (32 / GW_SUBLISTS);
+    auto evaluate_list = [&](int) {
+      int mylen = 0, maxlen = 0;
+#pragma unroll
+      for (int q = 0; q < GW_SUBLISTS; ++q) { if (q == myq) mylen = sl[q]; maxlen = sl[q] > maxlen ? sl[q] : maxlen; sl[q] = 0; }
+      const unsigned char* mysub = W.sub[myq];
+      int k = 0;
+      for (; k + GW_ILP <= maxlen; k += GW_ILP) {
+#pragma unroll
+        for (int u = 0; u < GW_ILP; ++u) {
+          const bool have = k + u < mylen;
+          const int idx = have ? (int)mysub[k + u] : 0;
+          grav_term(W.lxy[idx], W.lzg[idx], have && ((W.lmask[idx] >> lane) & 1u), xi, yi, zi, inv_h, h2x4, soft, gt, P.nq, P.dq, P.inv_dq, gx[u], gy[u], gz[u]);
+        }
+      }
+      for (; k < maxlen; ++k) {
+        const bool have = k < mylen;
+        const int idx = have ? (int)mysub[k] : 0;
+        grav_term(W.lxy[idx], W.lzg[idx], have && ((W.lmask[idx] >> lane) & 1u), xi, yi, zi, inv_h, h2x4, soft, gt, P.nq, P.dq, P.inv_dq, gx[0], gy[0], gz[0]);
+      }
+    };
+#else
     auto evaluate_list = [&](int cnt) {
       int k = 0;
 #ifdef GW_DEBUG
@@ -136,6 +171,7 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
       }
       for (; k < cnt; ++k) grav_term(W.lxy[k], W.lzg[k], (W.lmask[k] >> lane) & 1u, xi, yi, zi, inv_h, h2x4, soft, gt, P.nq, P.dq, P.inv_dq, gx[0], gy[0], gz[0]);
     };
+#endif
 
     if (do_grav && tg.y > 0) {               // tg.y == 0: an unused tail entry of the run table
       const BvhBox gb = gbox[chunk];
@@ -248,10 +284,25 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
         n_acc += __popc(acc_mask); n_open += __popc(open_mask);
         const bool ins = acc_mask != 0u && nm > 0.0;                                // F:279: massless nodes add nothing
         const unsigned balL = __ballot_sync(FULL_MASK, ins);
+#if GW_SUBLISTS > 1
+        const int lpos = ln + __popc(balL & lt_mask);
+        if (ins) {
+          W.lxy[lpos] = make_double2(ncx, ncy); W.lzg[lpos] = make_double2(ncz, P.G * nm); W.lmask[lpos] = acc_mask;
+        }
+#pragma unroll
+        for (int q = 0; q < GW_SUBLISTS; ++q) {
+          const unsigned qm = ((1u << (32 / GW_SUBLISTS)) - 1u) << (q * (32 / GW_SUBLISTS));
+          const bool hit = ins && (acc_mask & qm) != 0u;
+          const unsigned bq = __ballot_sync(FULL_MASK, hit);
+          if (hit) W.sub[q][sl[q] + __popc(bq & lt_mask)] = (unsigned char)lpos;
+          sl[q] += __popc(bq);
+        }
+#else
         if (ins) {
           const int pos = ln + __popc(balL & lt_mask);
           W.lxy[pos] = make_double2(ncx, ncy); W.lzg[pos] = make_double2(ncz, P.G * nm); W.lmask[pos] = acc_mask;
         }
+#endif
 #ifdef GW_DEBUG
         __syncwarp();
         for (int q = 0; q < __popc(balL); ++q) dq_account(W.lmask[ln + q]);
