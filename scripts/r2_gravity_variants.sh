@@ -1,0 +1,22 @@
+#!/bin/bash
+# Round-2 helper for the GW_SUBLISTS experiment in k_gravity.
+#   here (no GPU):   scripts/r2_gravity_variants.sh build              # nvcc -> summersph_b200/variants/libsph_sub{2,4,8}.so
+#   on the GPU box:  gpurun --timeout 900 -- 'scripts/r2_gravity_variants.sh run 16e6 > gpurun_out/r2_variants.log 2>&1'
+# `run` first holds every variant to the oracle (the parity tests through the C-ABI, SPH_B200_LIB selects the
+# library), then times the default library and the variants at N particles (per-stage device times of 3 steps).
+set -u
+cd "$(dirname "$0")/.."
+case "${1:-}" in
+  build)
+    for q in 2 4 8; do scripts/build_variant.sh sub$q "-DGW_SUBLISTS=$q" || exit 1; done ;;
+  run)
+    N=${2:-16e6}
+    for q in 2 4 8; do
+      lib=summersph_b200/variants/libsph_sub$q.so
+      [ -f "$lib" ] || { echo "missing $lib (run 'build' before gpurun)"; continue; }
+      echo "== parity sub$q"
+      SPH_B200_LIB=$lib python -m pytest tests/test_gpu_parity.py -q -m gpu -x 2>&1 | tail -3
+    done
+    scripts/gpu_variants.sh "$N" 3 sub2 sub4 sub8 ;;
+  *) echo "usage: $0 build | run [N]"; exit 2 ;;
+esac
