@@ -9,8 +9,11 @@
  * compiler exists in the build container, so this restatement could not be
  * checked against the reference's own executable.  What pins it instead: the formula-derived
  * known-answer values of SURVEY.md §4 (tests/test_oracle_kat.py), an independent O(N^2) numpy
- * brute force for the geometry-independent fixed-h definitions (tests/test_oracle_bruteforce.py)
- * and an independent derivation of leaf cells from sorted descent keys.
+ * brute force for the geometry-independent fixed-h definitions (tests/test_oracle_bruteforce.py),
+ * an independent derivation of leaf cells from sorted descent keys, and a second, literal Python
+ * reading of both Fortran programs (oracle/pyref.py: AoS records, pointer octree of particle copies,
+ * recursive walks) that this file must match bit for bit over whole loop bodies
+ * (tests/test_oracle_pyref.py).
  *
  * Citations: F = /root/reference/SUMMER_SPH.f90, V = "/root/reference/SUMMER_SPH - Variable.f90",
  * T = "/root/reference/SUMMER_SPH - Variable (test new)).f90".
