@@ -90,8 +90,9 @@ class Program:
     """Module-level state of one of the two programs: constants, kernel tables, bodies(:), sinks(:)."""
 
     def __init__(self, variable, max_depth=1000, bounding_size=1500.0, gamma=1.4, eta=1.2, convergence_criteria=1e-3,
-                 max_length=50.0, timestep_scale=0.25, sink_radius=None):
+                 max_length=50.0, timestep_scale=0.25, sink_radius=None, soft_uses_hi=False):
         self.variable = variable
+        self.soft_uses_hi = soft_uses_hi                          # "SUMMER_SPH - Variable (test new)).f90":298
         self.smoothing = 2.5                                      # F:11 | V:11
         self.nq = 2500 if variable else 5000                      # V:8 | F:8
         self.dq = 2.0 / self.nq                                   # F:10
@@ -203,7 +204,7 @@ class Program:
     # ---- gravity F:264-290 | V:285-311 ------------------------------------------------------------------
     def particle_gravforce_one(self, node, p, theta):
         direction = [p.position[k] - node.mass_center[k] for k in range(3)]
-        d2 = vsum([d * d for d in direction]) + 0.001 * self.smoothing
+        d2 = vsum([d * d for d in direction]) + (0.001 * p.s_length if self.soft_uses_hi else 0.001 * self.smoothing)   # T:298 | F:275, V:296
         dist = math.sqrt(d2)
         if (node.size / dist) < theta or node.children is None:
             if node.mass_total > 0.0 and dist > 0.0:

@@ -11,7 +11,7 @@ bit-identical: the tolerance is zero; dt, t, particle counts and iteration count
 import numpy as np
 import pytest
 
-from summersph_b200 import default_params, MODE_FIXED_H, MODE_VARIABLE_H, ics, Sinks
+from summersph_b200 import default_params, MODE_FIXED_H, MODE_VARIABLE_H, FLAG_SOFT_USES_HI, ics, Sinks
 from oracle.oracle import Oracle
 from oracle.pyref import Program
 from conftest import relerr
@@ -22,7 +22,7 @@ def program_for(p):
     variable = bool(p.mode & MODE_VARIABLE_H)
     return Program(variable, max_depth=p.max_depth, bounding_size=p.bounding_size, gamma=p.gamma, eta=p.eta,
                    convergence_criteria=p.convergence_criteria, max_length=p.max_length,
-                   timestep_scale=p.timestep_scale, sink_radius=p.sink_radius)
+                   timestep_scale=p.timestep_scale, sink_radius=p.sink_radius, soft_uses_hi=bool(p.mode & FLAG_SOFT_USES_HI))
 
 
 def col(items, attr, k=None):
@@ -65,7 +65,7 @@ def test_tables_and_literals_agree():
             assert o.lookup_grav_kernel(r, h) == py.lookup_grav_kernel(r, h)
 
 
-@pytest.mark.parametrize("mode", [MODE_FIXED_H, MODE_VARIABLE_H])
+@pytest.mark.parametrize("mode", [MODE_FIXED_H, MODE_VARIABLE_H, MODE_VARIABLE_H | FLAG_SOFT_USES_HI])
 def test_one_evaluation(mode):
     """create_tree + get_density + EOS + find_forces (F:894-898) with two sinks and viscosity on."""
     p = default_params(mode)
