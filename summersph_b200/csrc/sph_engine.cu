@@ -531,7 +531,7 @@ DensityArrays dens_arrays(sph_ctx* c) {
 }
 
 int run_density(sph_ctx* c) {
-  const int n = (int)c->n, W = DENS_WARPS;
+  const int W = DENS_WARPS;
   stage_begin(c, ST_DENSITY);
   StateArrays s = state_of(c, c->cur);
   // pool of 32-int blocks for the saved candidate lists: about one block (30 sources) per local particle, grown
@@ -555,7 +555,7 @@ int run_density(sph_ctx* c) {
   return SPH_OK;
 }
 int run_hiter(sph_ctx* c) {
-  const int n = (int)c->n, W = DENS_WARPS;
+  const int W = DENS_WARPS;
   c->nl_valid = false;                       // h changes: the saved lists' distance culls no longer hold
   stage_begin(c, ST_HITER);
   StateArrays s = state_of(c, c->cur);
@@ -567,7 +567,6 @@ int run_hiter(sph_ctx* c) {
   return SPH_OK;
 }
 int run_force(sph_ctx* c) {
-  const int n = (int)c->n, W = 16;
   if (c->x_pending) { stage_begin(c, ST_COMM); int r_ = allgatherv_end(c); if (r_) return r_; stage_end(c); }
   stage_begin(c, ST_SPH);
   StateArrays s = state_of(c, c->cur);
@@ -1137,7 +1136,7 @@ int sph_download_neighbours(sph_ctx* c, int32_t* count, uint64_t* hash, int64_t*
   if (!c) return SPH_ERR_ARG;
   if (!c->tree_valid) { c->err = "no tree"; return SPH_ERR_STATE; }
   cudaSetDevice(c->device);
-  const int n = (int)c->n, T = 256, W = 8;
+  const int n = (int)c->n, W = 8;
   int r; if ((r = compute_pos(c))) return r;
   int* d_count = nullptr; unsigned long long* d_hash = nullptr; long long* d_off = nullptr; int* d_list = nullptr;
   DA(d_count, n); DA(d_hash, n);
