@@ -135,6 +135,8 @@ def main():
     ap.add_argument("--cpu-baseline-particles", type=int, default=100_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (large multi-GPU sizing runs)")
+    ap.add_argument("--drift", action="store_true", help="add the energy / momentum / angular-momentum drift over the timed steps "
+                    "(sph_conserved before and after them, outside the timed region) as a \"drift\" key")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -183,6 +185,7 @@ def main():
     for _ in range(args.warmup):
         dt, t = e.step(dt, t)
     stage_acc = {}
+    cons_first = e.conserved() if args.drift else None      # builds / reuses the tree; never changes a later step
     sampler = ClockSampler(local)
     barrier()
     if rank == 0:
@@ -197,6 +200,10 @@ def main():
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     launches = e.launch_count() - l0
+    drift = None
+    if args.drift:
+        from summersph_b200._abi import drift_report
+        drift = drift_report(cons_first, e.conserved())
     # interaction counts of the reference algorithm (every leaf-box candidate): one untimed evaluation with exact
     # counters on the state the timed steps ended in; the timed steps cull exact-zero pairs before counting them
     e.set_exact_counters(True); e.evaluate(); counters = e.counters(); e.set_exact_counters(False)
@@ -289,6 +296,8 @@ def main():
             "per_rank_ms_per_step": [v / args.steps for v in per_rank],
             "counters": counters,
         }
+        if drift is not None:
+            line["drift"] = dict(drift, over_steps=args.steps)
         if world > 1:
             line["per_rank_walk_ms_per_step"] = per_rank_walk
             line["per_rank_comm_ms_per_step"] = per_rank_comm
