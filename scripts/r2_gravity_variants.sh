@@ -1,6 +1,7 @@
 #!/bin/bash
-# Round-2 helper for the GW_SUBLISTS experiment in k_gravity.
-#   here (no GPU):   scripts/r2_gravity_variants.sh build              # nvcc -> summersph_b200/variants/libsph_sub{2,4,8}.so
+# Round-2 helper for the two unmeasured experiments of DESIGN.md §9: GW_SUBLISTS (k_gravity's interaction list read through
+# per-lane-group index lists) and GROUP_SPLIT_BUCKETS (walk groups cut into full 32-particle runs inside a run of sibling buckets).
+#   here (no GPU):   scripts/r2_gravity_variants.sh build              # nvcc -> summersph_b200/variants/libsph_{sub2,sub4,sub8,split,split_sub4}.so
 #   on the GPU box:  gpurun --timeout 900 -- 'scripts/r2_gravity_variants.sh run 16e6 > gpurun_out/r2_variants.log 2>&1'
 # `run` first holds every variant to the oracle (the parity tests through the C-ABI, SPH_B200_LIB selects the
 # library), then times the default library and the variants at N particles (per-stage device times of 3 steps).
@@ -8,15 +9,17 @@ set -u
 cd "$(dirname "$0")/.."
 case "${1:-}" in
   build)
-    for q in 2 4 8; do scripts/build_variant.sh sub$q "-DGW_SUBLISTS=$q" || exit 1; done ;;
+    for q in 2 4 8; do scripts/build_variant.sh sub$q "-DGW_SUBLISTS=$q" || exit 1; done
+    scripts/build_variant.sh split "-DGROUP_SPLIT_BUCKETS" || exit 1
+    scripts/build_variant.sh split_sub4 "-DGROUP_SPLIT_BUCKETS -DGW_SUBLISTS=4" || exit 1 ;;
   run)
     N=${2:-16e6}
-    for q in 2 4 8; do
-      lib=summersph_b200/variants/libsph_sub$q.so
+    for v in sub2 sub4 sub8 split split_sub4; do
+      lib=summersph_b200/variants/libsph_$v.so
       [ -f "$lib" ] || { echo "missing $lib (run 'build' before gpurun)"; continue; }
-      echo "== parity sub$q"
+      echo "== parity $v"
       SPH_B200_LIB=$lib python -m pytest tests/test_gpu_parity.py -q -m gpu -x 2>&1 | tail -3
     done
-    scripts/gpu_variants.sh "$N" 3 sub2 sub4 sub8 ;;
+    scripts/gpu_variants.sh "$N" 3 sub2 sub4 sub8 split split_sub4 ;;
   *) echo "usage: $0 build | run [N]"; exit 2 ;;
 esac
