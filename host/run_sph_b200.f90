@@ -13,6 +13,7 @@ module sph_b200_c
   implicit none
 
   integer(c_int32_t), parameter :: SPH_MODE_FIXED_H = 0, SPH_MODE_VARIABLE_H = 1
+  integer(c_int32_t), parameter :: SPH_FLAG_SOFT_USES_HI = 2, SPH_FLAG_SINK_MERGE_SPIN = 4     ! OR-ed into sph_params%mode
 
   type, bind(C) :: sph_params          ! mirrors `struct sph_params` (and V's type(param), V:54-64)
     integer(c_int32_t) :: mode, max_depth, nq, n_ranks
@@ -76,6 +77,20 @@ module sph_b200_c
       type(c_ptr), value :: ctx
       real(c_double), intent(out) :: out(*)          ! E_kin E_int E_pot P(3) L(3) M E_pot_gas E_pot_sink
       integer(c_int32_t), value :: n_out
+    end function
+    ! column-density image of the resident gas (the Density_Image.py counterpart); image holds nu*nv doubles, row iv, column iu
+    integer(c_int) function sph_column_density(ctx, axis, u0, u1, v0, v1, nu, nv, image) bind(C, name="sph_column_density")
+      import :: c_int, c_int32_t, c_double, c_ptr
+      type(c_ptr), value :: ctx
+      integer(c_int32_t), value :: axis, nu, nv
+      real(c_double), value :: u0, u1, v0, v1
+      real(c_double), intent(out) :: image(*)
+    end function
+    ! sink spins (all zero unless the context was created with mode + SPH_FLAG_SINK_MERGE_SPIN)
+    integer(c_int) function sph_download_sink_spin(ctx, spin_x, spin_y, spin_z) bind(C, name="sph_download_sink_spin")
+      import :: c_int, c_double, c_ptr
+      type(c_ptr), value :: ctx
+      real(c_double), intent(out) :: spin_x(*), spin_y(*), spin_z(*)
     end function
   end interface
 end module sph_b200_c
