@@ -53,6 +53,32 @@ def compare_state(py, o):
         assert np.array_equal(getattr(s, name), col(py.sinks, attr, k)), "sink " + name
 
 
+def leaves_in_dfs_order(node, level=0, out=None):
+    """(number, level, centre, size, n_particles) of every childless node in the reference's recursion order (F:240-244)."""
+    out = [] if out is None else out
+    if node.children is None:
+        for q in node.particles:
+            out.append((q.number, level, tuple(node.center), node.size, node.n_particles))
+        return out
+    for ch in node.children:
+        if ch.n_particles > 0:
+            leaves_in_dfs_order(ch, level + 1, out)
+    return out
+
+
+def compare_tree(py, o):
+    """Depth-first leaf order (= the Morton order the engine sorts into), leaf level, cell centre and size."""
+    t = o.tree()
+    lv = leaves_in_dfs_order(py.root)
+    order = np.array([q[0] - 1 for q in lv], np.int32)
+    assert np.array_equal(order, t["order"])
+    assert np.array_equal(py.root.center, t["root_center"]) and py.root.size == t["root_size"]
+    for (num, level, ctr, size, npart) in lv:
+        i = num - 1
+        assert level == t["level"][i] and size == t["size"][i] and npart == t["n_in_leaf"][i], num
+        assert ctr == (t["cx"][i], t["cy"][i], t["cz"][i]), num
+
+
 def test_tables_and_literals_agree():
     for mode in (MODE_FIXED_H, MODE_VARIABLE_H):
         p = default_params(mode)
@@ -79,6 +105,7 @@ def test_one_evaluation(mode):
         q.number = i + 1
     py.evaluate()
     compare_rates(py, o)
+    compare_tree(py, o)
     assert max(abs(q.alpha_rate) for q in py.bodies) > 0 and max(abs(q.internal_energy_rate) for q in py.bodies) > 0
 
 
@@ -159,3 +186,5 @@ def test_depth_limited_tree_and_coincident_particles(mode):
     for k, v in (("ax", col(py.bodies, "acceleration", 0)), ("udot", col(py.bodies, "internal_energy_rate")), ("c", col(py.bodies, "sound_speed"))):
         assert np.array_equal(d[k], v, equal_nan=True), k
     assert np.array_equal(d["rho"], rho)
+    compare_tree(py, o)
+    assert max(q[4] for q in leaves_in_dfs_order(py.root)) > 1            # there are multi-particle childless nodes
