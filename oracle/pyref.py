@@ -103,6 +103,8 @@ class Program:
         self.max_length, self.timestep_scale = max_length, timestep_scale
         self.sink_radius = sink_radius if sink_radius is not None else (5.0 if variable else 3.5)   # V:830 | F:694
         self.bodies, self.sinks, self.root = [], [], None
+        # interaction counts of the most recent evaluation (not in the reference: what include/sph_b200.h's sph_counts reports)
+        self.cnt = {"density_candidates": 0, "density_contributing": 0, "sph_pairs": 0, "grav_opened": 0, "grav_accepted": 0}
         self.init_kernel_table(); self.init_grav_kernel_table()
 
     # ---- F:55-101 | V:69-115 ----------------------------------------------------------------------------
@@ -207,11 +209,13 @@ class Program:
         d2 = vsum([d * d for d in direction]) + (0.001 * p.s_length if self.soft_uses_hi else 0.001 * self.smoothing)   # T:298 | F:275, V:296
         dist = math.sqrt(d2)
         if (node.size / dist) < theta or node.children is None:
+            self.cnt["grav_accepted"] += 1
             if node.mass_total > 0.0 and dist > 0.0:
                 W = self.lookup_grav_kernel(dist, p.s_length if self.variable else self.smoothing)   # V:301 | F:280
                 d3 = ipow(dist, 3)
                 p.acceleration = [p.acceleration[k] - (self.G * node.mass_total * W * direction[k] / d3) for k in range(3)]
         else:
+            self.cnt["grav_opened"] += 1
             for ch in node.children:
                 if ch.n_particles > 0:
                     self.particle_gravforce_one(ch, p, theta)
@@ -251,7 +255,11 @@ class Program:
             other = node.particles[0]
             nr = [body.position[k] - other.position[k] for k in range(3)]
             dr = math.sqrt(vsum([a * a for a in nr]))
-            Wj, dWj_mag = self.lookup_kernel(dr, body.s_length if self.variable else self.smoothing)
+            hb = body.s_length if self.variable else self.smoothing
+            Wj, dWj_mag = self.lookup_kernel(dr, hb)
+            self.cnt["density_candidates"] += 1
+            if dr / hb <= 2.0:
+                self.cnt["density_contributing"] += 1
             body.density = body.density + other.mass * Wj
             if self.variable:
                 W_h = -(dr * dWj_mag - 3 * Wj) / body.s_length   # V:487
@@ -287,6 +295,7 @@ class Program:
             if leafp.number >= body.number:
                 return
             other = bodies[leafp.number - 1]
+            self.cnt["sph_pairs"] += 1
             nr = [body.position[k] - other.position[k] for k in range(3)]
             dr = math.sqrt(vsum([a * a for a in nr]))
             vij = [body.velocity[k] - other.velocity[k] for k in range(3)]
@@ -463,6 +472,8 @@ class Program:
 
     # ---- one body of simulate's loop F:886-928 | V:1120-1162 --------------------------------------------
     def evaluate(self):
+        for k in self.cnt:
+            self.cnt[k] = 0
         self.create_tree()
         self.get_density()
         self.get_pressure_and_sound_speed()

@@ -106,6 +106,8 @@ def test_one_evaluation(mode):
     py.evaluate()
     compare_rates(py, o)
     compare_tree(py, o)
+    co = o.counters()
+    assert {k: co[k] for k in py.cnt} == py.cnt          # the interaction counts the engine's parity tests compare with
     assert max(abs(q.alpha_rate) for q in py.bodies) > 0 and max(abs(q.internal_energy_rate) for q in py.bodies) > 0
 
 
