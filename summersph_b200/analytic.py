@@ -91,7 +91,7 @@ def sod_exact(x, t, gamma=1.4, rho_scale=1.0):
 
 
 # Omega of the variable-h program on a uniform cubic lattice with h = 1.2 spacings ("SUMMER_SPH - Variable.f90":455,487
-# as coded: 1 + h/(3 rho) sum m (3 W - r dW/dr)/h; tests/test_widen_sod.py measures it with the oracle).
+# as coded: 1 + h/(3 rho) sum m (3 W - r dW/dr)/h; tests/test_widen_shock_tube.py measures it with the oracle).
 OMEGA_LATTICE = 2.98
 
 

@@ -1,5 +1,5 @@
 """Sod shock tube against the exact Riemann solution (BASELINE.json configs[1]) — shared by the GPU test
-(tests/test_widen_sod.py: the CUDA engine at the full 100k particles) and by the command line below, which can
+(tests/test_widen_shock_tube.py: the CUDA engine at the full 100k particles) and by the command line below, which can
 also run the CPU oracle so that the two L1 errors sit side by side ("compared against the analytic solution and
 the reference").  Lives under tests/ because it may load the oracle; the product never imports it.
 
