@@ -39,7 +39,9 @@ struct SinkArrays { double *x, *y, *z, *vx, *vy, *vz, *m, *radius, *ax, *ay, *az
                             // groups it belongs to.  Every lane still adds its own terms in list order.  1 = one list for the warp.
 #endif
 #define GW_STACK 384        // (node, mask) entries per warp in shared memory
-#define GW_LIST  64         // interaction-list entries per warp (evaluated when more than 32 are waiting)
+#ifndef GW_LIST
+#define GW_LIST  64         // interaction-list entries per warp (evaluated when fewer than 32 slots are left); <= 256 with GW_SUBLISTS
+#endif
 #define GW_SPILL 8192       // per-warp overflow entries in global memory (never reached in practice; loud if it is)
 
 #ifdef GW_DEBUG
