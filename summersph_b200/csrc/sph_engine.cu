@@ -94,6 +94,10 @@ struct sph_ctx {
   int g0 = 0, g1 = 0, p0 = 0, p1 = 0;
   double* cons_partial = nullptr; double* cons_out = nullptr;   // sph_conserved: block partials, result slots
   double* sink_spin = nullptr; int sink_extras = 0;               // SPH_FLAG_SINK_MERGE_SPIN: spin[3][SPH_MAX_SINKS]; null pointer into the kernels when off
+#ifdef GW_FAR_REUSE
+  double *far_x = nullptr, *far_y = nullptr, *far_z = nullptr, *far_hcut = nullptr, *far_dec = nullptr; int* far_flag = nullptr;   // sph_gravity.cuh: GW_FAR_REUSE
+  bool far_valid = false; int far_nsink = 0; double far_sinks[4 * SPH_MAX_SINKS] = {}; int64_t far_reused = 0, far_full = 0;
+#endif
   double* img_table = nullptr;                                    // sph_column_density: line-of-sight integral of the M4 shape
 };
 
@@ -149,6 +153,10 @@ int ensure_capacity(sph_ctx* c, int64_t n) {
   DA(c->cnt, cap + 1); DA(c->off, cap + 1);
   DA(c->wnodes, 2 * cap); DA(c->wcount, 2 * cap); DA(c->wstart, 2 * cap); DA(c->widx, 2 * cap);
   DA(c->keep, cap); DA(c->pos, cap); DA(c->stage_d, cap); DA(c->stage_d2, cap);
+#ifdef GW_FAR_REUSE
+  DA(c->far_x, cap); DA(c->far_y, cap); DA(c->far_z, cap); DA(c->far_hcut, cap); c->far_valid = false;
+  if (!c->far_flag) { DA(c->far_flag, 1); DA(c->far_dec, 1); CK(cudaMemset(c->far_flag, 0, sizeof(int))); }
+#endif
   // CUB temp: radix sort pairs (u64,int), exclusive scan, select
   size_t b1 = 0, b2 = 0, b3 = 0, b4 = 0, b5 = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, b5, c->wcount, c->wstart, (int)(2 * cap), c->stream);
@@ -408,6 +416,9 @@ int build_tree(sph_ctx* c) {
 int build_tree_impl(sph_ctx* c, bool* retry_two_word) {
   const int n = (int)c->n;
   c->nl_valid = false; c->grav_groups_valid = false;
+#ifdef GW_FAR_REUSE
+  c->far_valid = false;                      // new positions / particle set: the stored far sums are void
+#endif
   const int T = 256;
   *retry_two_word = false;
   if (c->two_word && !c->key_lo[0]) { for (int b = 0; b < 2; ++b) DA(c->key_lo[b], c->cap); }
@@ -625,6 +636,38 @@ int run_gravity(sph_ctx* c, int do_grav, int do_sinks) {
   const int ng = c->g1 - c->g0;
 #endif
   const int ns = do_sinks ? c->n_sink : 0;
+#ifdef GW_FAR_REUSE
+  // Pass 1 (near terms + the far sums stored by the last full walk) when nothing the far sums depend on has changed:
+  // same tree (the stored sums are voided by every rebuild), same sinks, every h still below its cutoff.
+  GravFar FR{0, c->far_x, c->far_y, c->far_z, c->far_hcut};
+  {
+    double dec = 0.0;
+    const int M = SPH_MAX_SINKS;
+    if (c->far_valid && do_grav && do_sinks && !c->exact_counters && !c->dp.soft_hi && c->grav_groups_valid && c->n_sink == c->far_nsink) {
+      double now[4 * SPH_MAX_SINKS]; int flag = 1;
+      CK(cudaMemcpyAsync(now, c->sink_buf, sizeof(double) * 3 * M, cudaMemcpyDeviceToHost, c->stream));              // x y z
+      CK(cudaMemcpyAsync(now + 3 * M, c->sink_buf + 6 * M, sizeof(double) * M, cudaMemcpyDeviceToHost, c->stream));   // m
+      CK(cudaMemcpyAsync(&flag, c->far_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      if (flag == 0 && std::memcmp(now, c->far_sinks, sizeof(now)) == 0) dec = 1.0;
+    }
+    if (c->n_ranks > 1) {      // every rank takes the same path: the sink all-reduce below is collective
+      CK(cudaMemcpyAsync(c->far_dec, &dec, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+      { int r_ = allreduce(c, c->far_dec, 1, NC_FLOAT64, NC_MIN); if (r_) return r_; }
+      CK(cudaMemcpyAsync(&dec, c->far_dec, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+    }
+    FR.pass = dec > 0.5 ? 1 : 0;
+    if (FR.pass) ++c->far_reused; else ++c->far_full;
+  }
+  const bool far_pass = FR.pass != 0;
+  const int ns_k = far_pass ? 0 : ns;
+#define GW_FAR_ARG , FR
+#else
+  const bool far_pass = false;
+  const int ns_k = ns;
+#define GW_FAR_ARG
+#endif
   if ((size_t)(ng + 8 + SINK_RED_BLOCKS) * std::max(ns, 1) * 3 > c->sink_partial_cap) {
     c->sink_partial_cap = (size_t)(ng + 8 + SINK_RED_BLOCKS) * std::max(ns, 1) * 3 * 2;
     DA(c->sink_partial, c->sink_partial_cap);
@@ -646,11 +689,21 @@ int run_gravity(sph_ctx* c, int do_grav, int do_sinks) {
     }
     LAUNCH(k_set_int, 1, 1, 0, c->work, 0);
     LAUNCH(k_gravity, grid, GWW * 32, gravity_smem(c, GWW), 0, ng, c->ggroups, c->gbvh, c->dp, c->wnodes, s.x, s.y, s.z, s.h, s.m, c->d_gt,
-           c->ax, c->ay, c->az, do_grav, ns, c->S, c->sink_partial, c->ctr, c->work, c->grav_spill, &c->sc->err);
+           c->ax, c->ay, c->az, do_grav, ns_k, c->S, c->sink_partial, c->ctr, c->work, c->grav_spill, &c->sc->err GW_FAR_ARG);
 #else
     LAUNCH(k_set_int, 1, 1, 0, c->work, c->g0);
     LAUNCH(k_gravity, grid, GWW * 32, gravity_smem(c, GWW), c->g0, c->g1, c->groups, c->bvh, c->dp, c->wnodes, s.x, s.y, s.z, s.h, s.m, c->d_gt,
-           c->ax, c->ay, c->az, do_grav, ns, c->S, c->sink_partial, c->ctr, c->work, c->grav_spill, &c->sc->err);
+           c->ax, c->ay, c->az, do_grav, ns_k, c->S, c->sink_partial, c->ctr, c->work, c->grav_spill, &c->sc->err GW_FAR_ARG);
+#endif
+#ifdef GW_FAR_REUSE
+    if (!far_pass && do_grav && do_sinks && !c->dp.soft_hi) {      // a full walk just stored its far sums: remember the sinks they hold
+      const int M = SPH_MAX_SINKS;
+      CK(cudaMemcpyAsync(c->far_sinks, c->sink_buf, sizeof(double) * 3 * M, cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaMemcpyAsync(c->far_sinks + 3 * M, c->sink_buf + 6 * M, sizeof(double) * M, cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaMemsetAsync(c->far_flag, 0, sizeof(int), c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      c->far_nsink = c->n_sink; c->far_valid = true;
+    } else if (!far_pass) c->far_valid = false;
 #endif
   }
 #ifdef GW_DEBUG
@@ -659,6 +712,7 @@ int run_gravity(sph_ctx* c, int do_grav, int do_sinks) {
     unsigned long long hh[33]; cudaMemcpyFromSymbol(hh, gw_hist, sizeof(hh)); unsigned long long zz[33] = {}; cudaMemcpyToSymbol(gw_hist, zz, sizeof(zz));
     fprintf(stderr, "GWHIST"); for (int i = 0; i < 33; ++i) fprintf(stderr, " %llu", hh[i]); fprintf(stderr, "\n"); }
 #endif
+  if (far_pass) { stage_end(c); return SPH_OK; }      // the sinks keep the accelerations of the walk that stored the far sums
   if (do_sinks && ng > 4 * SINK_RED_BLOCKS) {
     double* rows = c->sink_partial + (size_t)ng * std::max(ns, 1) * 3;      // spare rows behind the per-run partials
     LAUNCH(k_sink_reduce_slices, SINK_RED_BLOCKS, 256, 0, ng, c->n_sink, c->sink_partial, rows);
@@ -754,6 +808,9 @@ int step(sph_ctx* c) {
   stage_end(c);
   if (c->dp.variable_h) {
     if ((r = run_hiter(c))) return r;                                         // V:1152
+#ifdef GW_FAR_REUSE
+    if (c->far_valid && c->p1 > c->p0) LAUNCH(k_check_hcut, cdiv(c->p1 - c->p0, T), T, 0, c->p0, c->p1, state_of(c, c->cur).h, c->far_hcut, c->far_flag);
+#endif
     stage_begin(c, ST_CULL);
     LAUNCH(k_create_scan, cdiv(n, T), T, 0, n, c->dp, state_of(c, c->cur), c->sc);          // V:1155
     LAUNCH(k_create_apply, 1, 32, 0, state_of(c, c->cur), c->S, c->sc, c->sink_spin);
@@ -928,6 +985,9 @@ int sph_create(const sph_params* p, int32_t device, sph_ctx** out) {
 
 int sph_destroy(sph_ctx* c) {
   if (!c) return SPH_OK;
+#ifdef GW_FAR_REUSE
+  if (getenv("SPH_B200_FAR_STATS")) fprintf(stderr, "GW_FAR_REUSE: %lld near-only gravity passes, %lld full walks\n", (long long)c->far_reused, (long long)c->far_full);
+#endif
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   p2p_close(c);
@@ -943,6 +1003,9 @@ int sph_destroy(sph_ctx* c) {
   F(c->node_count); F(c->gsize); F(c->gfirst); F(c->groups); F(c->level); F(c->lcx); F(c->lcy); F(c->lcz); F(c->reach); F(c->bvh); F(c->nodes); F(c->node_part); F(c->parent); F(c->nchild);
   F(c->nl_pool); F(c->nl_head); F(c->nl_ctl); F(c->ggroups); F(c->gbvh); F(c->seg_cnt); F(c->seg_off); F(c->wnodes); F(c->wcount); F(c->wstart); F(c->widx); F(c->grav_spill);
   F(c->cons_partial); F(c->cons_out); F(c->img_table); F(c->sink_spin);
+#ifdef GW_FAR_REUSE
+  F(c->far_x); F(c->far_y); F(c->far_z); F(c->far_hcut); F(c->far_dec); F(c->far_flag);
+#endif
   F(c->arrive); F(c->cnt); F(c->off); F(c->root); F(c->partial); F(c->cub_tmp); F(c->d_wt); F(c->d_dwt); F(c->d_gt);
   F(c->sink_buf); F(c->sink_partial); F(c->sc); F(c->ctr); F(c->work); F(c->keep); F(c->d_nsel); F(c->pos); F(c->stage_d); F(c->stage_d2);
   if (c->h_sc) cudaFreeHost(c->h_sc);

@@ -99,6 +99,47 @@ __device__ __forceinline__ void grav_term(const double2 a, const double2 b, cons
   if (on) { gx = fma(-f, dx, gx); gy = fma(-f, dy, gy); gz = fma(-f, dz, gz); }
 }
 
+#ifdef GW_FAR_REUSE
+// Experiment (scripts/r2_gravity_variants.sh): evaluation A of a loop body sees the positions of the previous
+// body's evaluation B (F:894 after F:905-912: the second kick moves no particle), so every accepted (node, particle) pair
+// and its distance are the same; only h changed (calc_smoothing, V:1152), and h enters a gravity term only through
+// g(dist / h) for dist < 2h (F:138-141: W = 1 beyond).  Pass 0 (a full walk) therefore adds the terms with
+// dist^2 <= 4 hcut^2 (hcut = GW_HCUT * h, kept per particle) and all the others apart and stores the far sum together with
+// the sink terms; pass 1 (the next evaluation on the same tree, same sinks, every h <= hcut) walks only what can hold a
+// near term - subtrees whose cell is farther than 2 max(hcut) from the run's box are dropped - re-evaluates the near terms
+// with the new h and adds the stored far sum.  Same terms as the full walk, summed in another order (rounding level).
+#ifndef GW_HCUT
+#define GW_HCUT 1.25
+#endif
+struct GravFar { int pass; double *fx, *fy, *fz, *hcut; };
+#define GW_FAR_PARAM , GravFar FR
+__device__ __forceinline__ void grav_term_split(const double2 a, const double2 b, const bool on, const double xi, const double yi,
+                                                const double zi, const double inv_h, const double h2x4, const double hc2x4, const int pass,
+                                                const double soft, const double* __restrict__ gt, const int nq, const double dq,
+                                                const double inv_dq, double& gx, double& gy, double& gz, double& qx, double& qy, double& qz) {
+  const double dx = xi - a.x, dy = yi - a.y, dz = zi - b.x;
+  const double d2 = fma(dx, dx, fma(dy, dy, fma(dz, dz, soft)));
+  if (d2 <= hc2x4) {                           // near class: the only terms that can depend on h
+    const double rs = fast_rsqrt(d2);
+    double gm = b.y;
+    if (d2 <= h2x4) gm *= table_lerp1(gt, nq, dq, inv_dq, (d2 * rs) * inv_h);
+    const double f = gm * (rs * rs * rs);
+    if (on) { qx = fma(-f, dx, qx); qy = fma(-f, dy, qy); qz = fma(-f, dz, qz); }
+  } else if (pass == 0) {
+    const double rs = fast_rsqrt(d2);
+    const double f = b.y * (rs * rs * rs);
+    if (on) { gx = fma(-f, dx, gx); gy = fma(-f, dy, gy); gz = fma(-f, dz, gz); }
+  }
+}
+// any h of this rank's slice above its cutoff voids the stored far sums (the near class would miss terms)
+__global__ void k_check_hcut(int p0, int p1, const double* __restrict__ h, const double* __restrict__ hcut, int* flag) {
+  const int i = p0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < p1 && !(h[i] <= hcut[i])) *flag = 1;
+}
+#else
+#define GW_FAR_PARAM
+#endif
+
 // dynamic smem: grav table (nq+1 doubles, padded to even) then one GravWarpSmem per warp
 __global__ void __launch_bounds__(GW_WARPS * 32, 1)
 k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox* __restrict__ gbox, DevParams P,
@@ -106,7 +147,7 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
           const double* __restrict__ h, const double* __restrict__ m, const double* __restrict__ g_gt,
           double* __restrict__ ax, double* __restrict__ ay, double* __restrict__ az,
           int do_grav, int n_sink, SinkArrays S, double* __restrict__ sink_partial, WalkCounters* ctr, int* work,
-          int2* __restrict__ spill, int* err_flag) {
+          int2* __restrict__ spill, int* err_flag GW_FAR_PARAM) {
   extern __shared__ __align__(16) double gsm[];
   double* gt = gsm;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -134,6 +175,16 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
 #pragma unroll
     for (int u = 0; u < GW_ILP; ++u) gx[u] = gy[u] = gz[u] = 0.0;
 
+#ifdef GW_FAR_REUSE
+#if GW_SUBLISTS > 1
+#error "GW_FAR_REUSE and GW_SUBLISTS are separate experiments"
+#endif
+    const double hc = live ? (FR.pass == 0 ? GW_HCUT * hi : FR.hcut[i]) : 1.0;
+    const double hc2x4 = 4.0 * hc * hc;
+    double qx[GW_ILP], qy[GW_ILP], qz[GW_ILP];      // near terms
+#pragma unroll
+    for (int u = 0; u < GW_ILP; ++u) qx[u] = qy[u] = qz[u] = 0.0;
+#endif
 #if GW_SUBLISTS > 1
     int sl[GW_SUBLISTS];                       // entries in each lane group's index list (warp-uniform)
 #pragma unroll
@@ -158,6 +209,19 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
         const int idx = have ? (int)mysub[k] : 0;
         grav_term(W.lxy[idx], W.lzg[idx], have && ((W.lmask[idx] >> lane) & 1u), xi, yi, zi, inv_h, h2x4, soft, gt, P.nq, P.dq, P.inv_dq, gx[0], gy[0], gz[0]);
       }
+    };
+#elif defined(GW_FAR_REUSE)
+    auto evaluate_list = [&](int cnt) {
+      int k = 0;
+      for (; k + GW_ILP <= cnt; k += GW_ILP) {
+#pragma unroll
+        for (int u = 0; u < GW_ILP; ++u)
+          grav_term_split(W.lxy[k + u], W.lzg[k + u], (W.lmask[k + u] >> lane) & 1u, xi, yi, zi, inv_h, h2x4, hc2x4, FR.pass, soft, gt,
+                          P.nq, P.dq, P.inv_dq, gx[u], gy[u], gz[u], qx[u], qy[u], qz[u]);
+      }
+      for (; k < cnt; ++k)
+        grav_term_split(W.lxy[k], W.lzg[k], (W.lmask[k] >> lane) & 1u, xi, yi, zi, inv_h, h2x4, hc2x4, FR.pass, soft, gt,
+                        P.nq, P.dq, P.inv_dq, gx[0], gy[0], gz[0], qx[0], qy[0], qz[0]);
     };
 #else
     auto evaluate_list = [&](int cnt) {
@@ -188,6 +252,10 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
       const float xif = (float)(xi - g0x), yif = (float)(yi - g0y), zif = (float)(zi - g0z);
       const float softf = (float)soft, softf_min = __double2float_rd(soft_min), softf_max = __double2float_ru(soft_max);
       const float th2f = (float)theta2, inv_th2f = (float)inv_theta2;
+#ifdef GW_FAR_REUSE
+      // pass 1: distance (float, rounded up) beyond which no particle of the run can have a near term
+      const float rcf = FR.pass ? __double2float_ru(2.0 * warp_max(live ? hc : 0.0)) * 1.0001f : 0.f;
+#endif
       int sn = 1, gsp = 0, ln = 0;
 #ifdef GW_DEBUG
       int dq_len = 0, dq_ring = 0;
@@ -228,6 +296,9 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
         int cls = 0;                           // 1 all accept, 2 all open, 3 mixed
         double ncx = 0.0, ncy = 0.0, ncz = 0.0, nm = 0.0, nsize = 0.0; int nchild = 0, nnch = 0;
         float rxf = 0.f, ryf = 0.f, rzf = 0.f, s2f = 0.f;
+#ifdef GW_FAR_REUSE
+        bool far_entry = false;
+#endif
         if (valid) {
           const double2* p = reinterpret_cast<const double2*>(wn + e.x);
           const double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
@@ -243,6 +314,13 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
           if (nnch == 0 || s2f < th2f * dmin2 * (1.f - 3e-5f)) cls = 1;
           else if (s2f > th2f * dmax2 * (1.f + 3e-5f)) cls = 2;
           else cls = 3;
+#ifdef GW_FAR_REUSE
+          if (FR.pass) {     // the node's particles lie inside its cell, i.e. within sqrt(3) size of its centre of mass
+            const float dminf = sqrtf(fmaf(nx, nx, fmaf(ny, ny, nz * nz))) * 0.9999f;
+            if (dminf - 1.7321f * szf > rcf) cls = 0;            // nothing at or below this node is near any particle of the run
+            else if (dminf > rcf) far_entry = true;              // its own term is far for every particle; its children may not be
+          }
+#endif
         }
         const unsigned emask = (unsigned)e.y;
         const unsigned balM = __ballot_sync(FULL_MASK, cls == 3);
@@ -284,7 +362,11 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
         }
         // ---- lane = node again: accepted (node, lane set) pairs join the interaction list, opened ones push their child block
         n_acc += __popc(acc_mask); n_open += __popc(open_mask);
+#ifdef GW_FAR_REUSE
+        const bool ins = acc_mask != 0u && nm > 0.0 && !far_entry;
+#else
         const bool ins = acc_mask != 0u && nm > 0.0;                                // F:279: massless nodes add nothing
+#endif
         const unsigned balL = __ballot_sync(FULL_MASK, ins);
 #if GW_SUBLISTS > 1
         const int lpos = ln + __popc(balL & lt_mask);
@@ -347,6 +429,15 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
         o[0] = px; o[1] = py; o[2] = pz;
       }
     }
+#ifdef GW_FAR_REUSE
+#pragma unroll
+    for (int u = 1; u < GW_ILP; ++u) { qx[0] += qx[u]; qy[0] += qy[u]; qz[0] += qz[u]; }
+    if (live) {
+      if (FR.pass == 0) { FR.fx[i] = gx[0]; FR.fy[i] = gy[0]; FR.fz[i] = gz[0]; FR.hcut[i] = hc; }   // far terms + sinks (the loop above)
+      else { gx[0] = FR.fx[i]; gy[0] = FR.fy[i]; gz[0] = FR.fz[i]; }                                 // pass 1 is launched with n_sink = 0
+      gx[0] += qx[0]; gy[0] += qy[0]; gz[0] += qz[0];
+    }
+#endif
     if (live) { ax[i] = gx[0]; ay[i] = gy[0]; az[i] = gz[0]; }
   }
   n_open = (unsigned long long)warp_sum_ll((long long)n_open); n_acc = (unsigned long long)warp_sum_ll((long long)n_acc);
