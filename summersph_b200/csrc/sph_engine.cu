@@ -96,6 +96,7 @@ struct sph_ctx {
   double* sink_spin = nullptr; int sink_extras = 0;               // SPH_FLAG_SINK_MERGE_SPIN: spin[3][SPH_MAX_SINKS]; null pointer into the kernels when off
 #ifdef GW_FAR_REUSE
   double *far_x = nullptr, *far_y = nullptr, *far_z = nullptr, *far_hcut = nullptr, *far_dec = nullptr; int* far_flag = nullptr;   // sph_gravity.cuh: GW_FAR_REUSE
+  int2* far_near = nullptr; int* far_near_cnt = nullptr; size_t far_near_runs = 0;
   bool far_valid = false; int far_nsink = 0; double far_sinks[4 * SPH_MAX_SINKS] = {}; int64_t far_reused = 0, far_full = 0;
 #endif
   double* img_table = nullptr;                                    // sph_column_density: line-of-sight integral of the M4 shape
@@ -639,7 +640,12 @@ int run_gravity(sph_ctx* c, int do_grav, int do_sinks) {
 #ifdef GW_FAR_REUSE
   // Pass 1 (near terms + the far sums stored by the last full walk) when nothing the far sums depend on has changed:
   // same tree (the stored sums are voided by every rebuild), same sinks, every h still below its cutoff.
-  GravFar FR{0, c->far_x, c->far_y, c->far_z, c->far_hcut};
+  if (GW_NEAR_CAP > 0 && (size_t)ng > c->far_near_runs) {      // per-run near lists of pass 0 (8 B x GW_NEAR_CAP per run)
+    c->far_near_runs = (size_t)ng * 5 / 4 + 64;
+    DA(c->far_near, c->far_near_runs * (size_t)GW_NEAR_CAP); DA(c->far_near_cnt, c->far_near_runs);
+    c->far_valid = false;
+  }
+  GravFar FR{0, c->far_x, c->far_y, c->far_z, c->far_hcut, c->far_near, c->far_near_cnt, GW_NEAR_CAP};
   {
     double dec = 0.0;
     const int M = SPH_MAX_SINKS;
@@ -1004,7 +1010,7 @@ int sph_destroy(sph_ctx* c) {
   F(c->nl_pool); F(c->nl_head); F(c->nl_ctl); F(c->ggroups); F(c->gbvh); F(c->seg_cnt); F(c->seg_off); F(c->wnodes); F(c->wcount); F(c->wstart); F(c->widx); F(c->grav_spill);
   F(c->cons_partial); F(c->cons_out); F(c->img_table); F(c->sink_spin);
 #ifdef GW_FAR_REUSE
-  F(c->far_x); F(c->far_y); F(c->far_z); F(c->far_hcut); F(c->far_dec); F(c->far_flag);
+  F(c->far_x); F(c->far_y); F(c->far_z); F(c->far_hcut); F(c->far_dec); F(c->far_flag); F(c->far_near); F(c->far_near_cnt);
 #endif
   F(c->arrive); F(c->cnt); F(c->off); F(c->root); F(c->partial); F(c->cub_tmp); F(c->d_wt); F(c->d_dwt); F(c->d_gt);
   F(c->sink_buf); F(c->sink_partial); F(c->sc); F(c->ctr); F(c->work); F(c->keep); F(c->d_nsel); F(c->pos); F(c->stage_d); F(c->stage_d2);

@@ -111,7 +111,12 @@ __device__ __forceinline__ void grav_term(const double2 a, const double2 b, cons
 #ifndef GW_HCUT
 #define GW_HCUT 1.25
 #endif
-struct GravFar { int pass; double *fx, *fy, *fz, *hcut; };
+#ifndef GW_NEAR_CAP
+#define GW_NEAR_CAP 512     // (node, lane mask) pairs kept per run for pass 1; a run that needs more falls back to the near walk; 0: always walk
+#endif
+// near / near_cnt: pass 0 also records, per run, every listed entry that can be near for some particle of the run; pass 1 then
+// evaluates that list instead of walking (the walk has to visit nearly every node of the full walk just to drop it)
+struct GravFar { int pass; double *fx, *fy, *fz, *hcut; int2* near; int* near_cnt; int near_cap; };
 #define GW_FAR_PARAM , GravFar FR
 __device__ __forceinline__ void grav_term_split(const double2 a, const double2 b, const bool on, const double xi, const double yi,
                                                 const double zi, const double inv_h, const double h2x4, const double hc2x4, const int pass,
@@ -253,10 +258,31 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
       const float softf = (float)soft, softf_min = __double2float_rd(soft_min), softf_max = __double2float_ru(soft_max);
       const float th2f = (float)theta2, inv_th2f = (float)inv_theta2;
 #ifdef GW_FAR_REUSE
-      // pass 1: distance (float, rounded up) beyond which no particle of the run can have a near term
-      const float rcf = FR.pass ? __double2float_ru(2.0 * warp_max(live ? hc : 0.0)) * 1.0001f : 0.f;
+      // distance (float, rounded up) beyond which no particle of the run can have a near term
+      const float rcf = __double2float_ru(2.0 * warp_max(live ? hc : 0.0)) * 1.0001f;
+      int ncnt = 0;                          // pass 0: entries recorded in this run's near list (may exceed the capacity: overflow)
 #endif
       int sn = 1, gsp = 0, ln = 0;
+#ifdef GW_FAR_REUSE
+      if (FR.pass && FR.near_cap > 0) {      // pass 1 from the recorded list: same entries, same masks, same order as the walk would list
+        const int cnt_near = FR.near_cnt[chunk];
+        if (cnt_near <= FR.near_cap) {
+          for (int base = 0; base < cnt_near; base += 32) {
+            const int k = base + lane;
+            if (k < cnt_near) {
+              const int2 en = FR.near[(size_t)chunk * FR.near_cap + k];
+              const double2* p = reinterpret_cast<const double2*>(wn + en.x);
+              const double2 a = __ldg(p), b = __ldg(p + 1);
+              W.lxy[lane] = a; W.lzg[lane] = make_double2(b.x, P.G * b.y); W.lmask[lane] = (unsigned)en.y;
+            }
+            __syncwarp();
+            evaluate_list(cnt_near - base < 32 ? cnt_near - base : 32);
+            __syncwarp();
+          }
+          sn = 0;                            // nothing to walk
+        }
+      }
+#endif
 #ifdef GW_DEBUG
       int dq_len = 0, dq_ring = 0;
       auto dq_flush = [&]() { int mx = dq_len, sm = dq_len; for (int o = 16; o > 0; o >>= 1) { mx = max(mx, __shfl_xor_sync(FULL_MASK, mx, o)); sm += __shfl_xor_sync(FULL_MASK, sm, o); }
@@ -297,7 +323,7 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
         double ncx = 0.0, ncy = 0.0, ncz = 0.0, nm = 0.0, nsize = 0.0; int nchild = 0, nnch = 0;
         float rxf = 0.f, ryf = 0.f, rzf = 0.f, s2f = 0.f;
 #ifdef GW_FAR_REUSE
-        bool far_entry = false;
+        bool far_entry = false, near_poss = false;
 #endif
         if (valid) {
           const double2* p = reinterpret_cast<const double2*>(wn + e.x);
@@ -315,10 +341,12 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
           else if (s2f > th2f * dmax2 * (1.f + 3e-5f)) cls = 2;
           else cls = 3;
 #ifdef GW_FAR_REUSE
-          if (FR.pass) {     // the node's particles lie inside its cell, i.e. within sqrt(3) size of its centre of mass
+          {                  // the node's particles lie inside its cell, i.e. within sqrt(3) size of its centre of mass
             const float dminf = sqrtf(fmaf(nx, nx, fmaf(ny, ny, nz * nz))) * 0.9999f;
-            if (dminf - 1.7321f * szf > rcf) cls = 0;            // nothing at or below this node is near any particle of the run
-            else if (dminf > rcf) far_entry = true;              // its own term is far for every particle; its children may not be
+            if (FR.pass) {
+              if (dminf - 1.7321f * szf > rcf) cls = 0;          // nothing at or below this node is near any particle of the run
+              else if (dminf > rcf) far_entry = true;            // its own term is far for every particle; its children may not be
+            } else near_poss = !(dminf > rcf);                   // pass 0: worth recording for pass 1
           }
 #endif
         }
@@ -387,6 +415,17 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
           W.lxy[pos] = make_double2(ncx, ncy); W.lzg[pos] = make_double2(ncz, P.G * nm); W.lmask[pos] = acc_mask;
         }
 #endif
+#ifdef GW_FAR_REUSE
+        if (FR.pass == 0 && FR.near_cap > 0) {
+          const bool rec = ins && near_poss;
+          const unsigned balN = __ballot_sync(FULL_MASK, rec);
+          if (rec) {
+            const int q = ncnt + __popc(balN & lt_mask);
+            if (q < FR.near_cap) FR.near[(size_t)chunk * FR.near_cap + q] = make_int2(e.x, (int)acc_mask);
+          }
+          ncnt += __popc(balN);
+        }
+#endif
 #ifdef GW_DEBUG
         __syncwarp();
         for (int q = 0; q < __popc(balL); ++q) dq_account(W.lmask[ln + q]);
@@ -404,6 +443,9 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
       }
       if (ln > 0) evaluate_list(ln);
       __syncwarp();
+#ifdef GW_FAR_REUSE
+      if (FR.pass == 0 && FR.near_cap > 0 && lane == 0) FR.near_cnt[chunk] = ncnt;
+#endif
 #ifdef GW_DEBUG
       if (dq_ring) dq_flush();
 #endif
