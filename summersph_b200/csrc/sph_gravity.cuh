@@ -104,15 +104,15 @@ __device__ __forceinline__ void grav_term(const double2 a, const double2 b, cons
 // body's evaluation B (F:894 after F:905-912: the second kick moves no particle), so every accepted (node, particle) pair
 // and its distance are the same; only h changed (calc_smoothing, V:1152), and h enters a gravity term only through
 // g(dist / h) for dist < 2h (F:138-141: W = 1 beyond).  Pass 0 (a full walk) therefore adds the terms with
-// dist^2 <= 4 hcut^2 (hcut = GW_HCUT * h, kept per particle) and all the others apart and stores the far sum together with
+// dist^2 <= 4 hcut^2 (hcut = GW_HCUT * h = 1.1 h, kept per particle) and all the others apart and stores the far sum together with
 // the sink terms; pass 1 (the next evaluation on the same tree, same sinks, every h <= hcut) walks only what can hold a
 // near term - subtrees whose cell is farther than 2 max(hcut) from the run's box are dropped - re-evaluates the near terms
 // with the new h and adds the stored far sum.  Same terms as the full walk, summed in another order (rounding level).
 #ifndef GW_HCUT
-#define GW_HCUT 1.25
+#define GW_HCUT 1.1
 #endif
 #ifndef GW_NEAR_CAP
-#define GW_NEAR_CAP 512     // (node, lane mask) pairs kept per run for pass 1; a run that needs more falls back to the near walk; 0: always walk
+#define GW_NEAR_CAP 1024    // (node, lane mask) pairs kept per run for pass 1; a run that needs more falls back to the near walk; 0: always walk
 #endif
 // near / near_cnt: pass 0 also records, per run, every listed entry that can be near for some particle of the run; pass 1 then
 // evaluates that list instead of walking (the walk has to visit nearly every node of the full walk just to drop it)
