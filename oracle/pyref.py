@@ -103,7 +103,9 @@ class Program:
         self.max_length, self.timestep_scale = max_length, timestep_scale
         self.sink_radius = sink_radius if sink_radius is not None else (5.0 if variable else 3.5)   # V:830 | F:694
         self.bodies, self.sinks, self.root = [], [], None
+        self._ngb_open = False
         # interaction counts of the most recent evaluation (not in the reference: what include/sph_b200.h's sph_counts reports)
+        self.record_ngb, self.ngb = False, None               # per particle: numbers (0-based) of the leaves whose box test passes (F:443 | V:479)
         self.cnt = {"density_candidates": 0, "density_contributing": 0, "sph_pairs": 0, "grav_opened": 0, "grav_accepted": 0}
         self.init_kernel_table(); self.init_grav_kernel_table()
 
@@ -258,6 +260,8 @@ class Program:
             hb = body.s_length if self.variable else self.smoothing
             Wj, dWj_mag = self.lookup_kernel(dr, hb)
             self.cnt["density_candidates"] += 1
+            if self.record_ngb and self._ngb_open:
+                self.ngb[body.number - 1].append(other.number - 1)
             if dr / hb <= 2.0:
                 self.cnt["density_contributing"] += 1
             body.density = body.density + other.mass * Wj
@@ -266,6 +270,9 @@ class Program:
                 body.omega = body.omega + other.mass * W_h
 
     def get_density(self):
+        self._ngb_open = True
+        if self.record_ngb:
+            self.ngb = [[] for _ in self.bodies]
         for b in self.bodies:
             b.density = 0.0
             b.omega = 0.0
@@ -392,6 +399,7 @@ class Program:
 
     # ---- V:515-546 --------------------------------------------------------------------------------------
     def calc_smoothing(self):
+        self._ngb_open = False                    # its re-walks are not part of the evaluation's neighbour sets
         eta = self.eta
         iterations = 0
         for b in self.bodies:

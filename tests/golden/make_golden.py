@@ -2,7 +2,8 @@
 
 The reference ships no golden vectors and cannot be built here (no Fortran compiler), so these fixtures
 pin the ORACLE's output (regression pin for the restatement, and the small-case target for the CUDA
-engine), not the Fortran program's.  Re-run:  python tests/golden/make_golden.py
+engine), not the Fortran program's.  The second, literal restatement (oracle/pyref.py) reproduces every file bit for bit
+(tests/test_oracle_pyref.py::test_pyref_reproduces_golden).  Re-run:  python tests/golden/make_golden.py
 """
 import os
 import sys
