@@ -203,7 +203,7 @@ def _mix64(z):
     return z ^ (z >> 31)
 
 
-@pytest.mark.parametrize("name", ["disc600_fixed_accrete", "disc600_variable_accrete", "disc600_variable", "sod_variable"])
+@pytest.mark.parametrize("name", ["disc600_fixed", "disc600_fixed_accrete", "disc600_variable", "disc600_variable_accrete", "sod_variable"])
 def test_pyref_reproduces_golden(name):
     from _cases import load_golden
     z, p, b, s = load_golden(name)
