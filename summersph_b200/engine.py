@@ -76,8 +76,9 @@ def _p(a):
 class Engine:
     """One engine context on one CUDA device (`sph_ctx`)."""
 
-    def __init__(self, params: SphParams, device=0, exact_counters=False):
-        self._l = load_library()
+    def __init__(self, params: SphParams, device=0, exact_counters=False, lib_path=None):
+        """`lib_path`: developer experiments only (a variant build under summersph_b200/variants/)."""
+        self._l = load_library(lib_path)
         self.params = params
         self._c = C.c_void_p()
         rc = self._l.sph_create(C.byref(params), int(device), C.byref(self._c))
