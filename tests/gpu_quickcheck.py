@@ -2,7 +2,7 @@
 sph_column_density, the 100k Sod tube): each check prints one JSON line and appends it to gpurun_out/quickcheck.jsonl
 as soon as it is done.  No torch import (the engine is ctypes + CUDA only), so it fits in a minute of box time:
 
-    python tests/gpu_quickcheck.py [conserved] [image] [sod_variable] [sod_fixed]
+    python tests/gpu_quickcheck.py [conserved] [image] [merger] [sod_variable] [sod_fixed] [ring]
 """
 import json
 import os
@@ -98,7 +98,30 @@ def check_merger():
              lz_engine=ce["lz"], lz_oracle=co["lz"])
 
 
-CHECKS = {"conserved": check_conserved, "image": check_image, "merger": check_merger,
+def check_ring():
+    """The 1M thin ring for 20 steps (tests/test_widen_thin_ring.py::test_ring_1M_20_steps) with its numbers printed."""
+    import test_widen_thin_ring as TR
+    from summersph_b200 import default_params, MODE_VARIABLE_H, ics
+    from summersph_b200._abi import drift_report
+    from summersph_b200.engine import Engine
+    t0 = time.perf_counter()
+    p = default_params(MODE_VARIABLE_H)
+    b, s = ics.thin_ring(TR.N_FULL)
+    m0 = TR.ring_moments(b)
+    with Engine(p) as e:
+        e.upload(b, s)
+        first = e.conserved()
+        dt, t = 0.01, 0.0
+        ts = time.perf_counter()
+        for _ in range(TR.STEPS):
+            dt, t = e.step(dt, t)
+        wall = time.perf_counter() - ts
+        last = e.conserved()
+        b1, _ = e.download()
+    emit("ring_1M", t0, ok=True, t=t, dt=dt, wall_s=wall, moments_first=m0, moments_last=TR.ring_moments(b1), drift=drift_report(first, last))
+
+
+CHECKS = {"conserved": check_conserved, "ring": check_ring, "image": check_image, "merger": check_merger,
           "sod_variable": lambda: check_sod("variable"), "sod_fixed": lambda: check_sod("fixed")}
 
 if __name__ == "__main__":
