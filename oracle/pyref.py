@@ -54,6 +54,23 @@ def fmax(a, b):
     return a if a > b else b
 
 
+def maxval(v):
+    """gfortran MAXVAL / MINVAL on reals skip NaNs (NaN only when every element is one)."""
+    r = None
+    for a in v:
+        if a == a and (r is None or a > r):
+            r = a
+    return math.nan if r is None else r
+
+
+def minval(v):
+    r = None
+    for a in v:
+        if a == a and (r is None or a < r):
+            r = a
+    return math.nan if r is None else r
+
+
 def vsum(v):
     s = 0.0
     for a in v:
@@ -162,7 +179,7 @@ class Program:
             node.mass_total = node.mass_total + p.mass
             node.mass_center = [node.mass_center[k] + p.mass * p.position[k] for k in range(3)]
             lens.append(p.s_length)
-        node.max_len = max(lens)                                  # V:192
+        node.max_len = maxval(lens)                               # V:192
         if node.mass_total > 0.0:
             node.mass_center = [c / node.mass_total for c in node.mass_center]
         else:
@@ -196,10 +213,10 @@ class Program:
 
     def create_tree(self):                                        # F:795-816 | V:999-1020
         root = Branch()
-        mx = [max(b.position[k] for b in self.bodies) for k in range(3)]
-        mn = [min(b.position[k] for b in self.bodies) for k in range(3)]
+        mx = [maxval(b.position[k] for b in self.bodies) for k in range(3)]
+        mn = [minval(b.position[k] for b in self.bodies) for k in range(3)]
         root.center = [(mx[k] + mn[k]) / 2.0 for k in range(3)]
-        root.size = max(mx[k] - mn[k] for k in range(3))
+        root.size = maxval(mx[k] - mn[k] for k in range(3))
         root.n_particles = len(self.bodies)
         root.particles = [b.copy() for b in self.bodies]
         self.build_tree(root, self.max_depth, 1)
@@ -243,6 +260,8 @@ class Program:
 
     # ---- density F:398-457 | V:440-496 ------------------------------------------------------------------
     def reach(self, node):
+        if node.n_particles == 0:
+            return 0.0        # an empty child reached from get_SPH's loop over all eight (F:307): max_len is undefined, neither branch can fire
         return 2.0 * node.max_len if self.variable else 2.0 * self.smoothing      # V:471 | F:431
 
     def density_tree_search(self, node, body):
@@ -390,7 +409,7 @@ class Program:
             cands.append(b.internal_energy / abs(b.internal_energy_rate) if b.internal_energy_rate != 0.0 else math.inf)
             cands.append(hh / math.sqrt(vv) if vv != 0.0 else math.inf)
             cands.append(hh / (b.sound_speed + 1.2 * b.sound_speed))
-        dt_candidate = min(c for c in cands if c == c) * (self.timestep_scale if self.variable else 0.25)   # V:1056 | F:851
+        dt_candidate = minval(cands) * (self.timestep_scale if self.variable else 0.25)   # V:1056 | F:851
         if dt_candidate > 2 * dt and 1.5 * dt < r4(0.1):
             dt = 1.5 * dt
         elif dt_candidate < 0.5 * dt and dt * 0.5 > r4(0.0001):
@@ -404,15 +423,15 @@ class Program:
         iterations = 0
         for b in self.bodies:
             old_len = b.s_length
-            b.s_length = b.s_length * (1 + ((b.mass * ipow(eta / b.s_length, 3) / b.density) - 1) / (3 * b.omega))
+            b.s_length = b.s_length * (1 + div(div(b.mass * ipow(eta / b.s_length, 3), b.density) - 1, 3 * b.omega))
             if b.s_length < self.max_length and b.s_length > r4(0.01):
                 while ((b.s_length - old_len) / old_len) > self.convergence_criteria and b.s_length < 10.0:
                     old_len = b.s_length
                     b.density = 0.0
                     b.omega = 0.0
                     self.density_tree_search(self.root, b)
-                    b.omega = 1.0 + (b.s_length / (3 * b.density)) * b.omega
-                    b.s_length = b.s_length * (1 + ((b.mass * ipow(eta / b.s_length, 3)) / b.density - 1) / (3 * b.omega))
+                    b.omega = 1.0 + div(b.s_length, 3 * b.density) * b.omega
+                    b.s_length = b.s_length * (1 + div(div(b.mass * ipow(eta / b.s_length, 3), b.density) - 1, 3 * b.omega))
                     iterations += 1
             else:
                 b.s_length = old_len
@@ -465,8 +484,8 @@ class Program:
             self.sink2gasdists(s, self.root, mask)
             acc = [b for b, keep in zip(self.bodies, mask) if not keep]
             new_mass = s.mass + vsum([b.mass for b in acc])
-            s.position = [(s.mass * s.position[k] + vsum([b.mass * b.position[k] for b in acc])) / new_mass for k in range(3)]
-            s.velocity = [(s.mass * s.velocity[k] + vsum([b.mass * b.velocity[k] for b in acc])) / new_mass for k in range(3)]
+            s.position = [div(s.mass * s.position[k] + vsum([b.mass * b.position[k] for b in acc]), new_mass) for k in range(3)]   # 0/0 for a massless sink that accretes nothing
+            s.velocity = [div(s.mass * s.velocity[k] + vsum([b.mass * b.velocity[k] for b in acc]), new_mass) for k in range(3)]
             s.mass = s.mass + vsum([b.mass for b in acc])
             masks.append(mask)
         keep_all = [all(m[j] for m in masks) for j in range(n)]   # pack_sinks F:546-556
