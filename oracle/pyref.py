@@ -16,6 +16,9 @@ the serial order is the parity order).
 """
 import math
 import struct
+import sys
+
+sys.setrecursionlimit(max(sys.getrecursionlimit(), 20000))   # build_tree recurses to max_depth (1000) when particles coincide or are NaN
 
 
 def r4(x):
