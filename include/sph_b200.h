@@ -107,6 +107,18 @@ const char* sph_last_error(const sph_ctx* ctx);   /* ctx may be NULL for create 
 int sph_comm_unique_id(void* unique_id_128);
 int sph_comm_init(sph_ctx* ctx, int32_t rank, int32_t n_ranks, const void* unique_id_128);
 
+/* The same multi-rank engine with its few small collectives (scalar all-reduces, a few KB of all-gather, barriers)
+ * carried through a POSIX shared-memory segment `name` (e.g. "/sph_b200_1234") instead of NCCL.  For ranks that are
+ * threads of one process or processes on one node, on any number of devices - several ranks may share one GPU, which
+ * NCCL refuses - so the multi-rank logic can be exercised on a single-GPU box.  Bulk data still moves over peer-mapped
+ * device memory (CUDA IPC); every collective synchronises the stream: a bring-up / test path, not the fast one.
+ * Call on every rank with the same name; rank 0 creates the segment. */
+int sph_comm_init_host(sph_ctx* ctx, int32_t rank, int32_t n_ranks, const char* name);
+
+/* Target slices of the replicated-state multi-rank mode (host arithmetic only, no device needed): rank r walks the
+ * groups [first_group[r], first_group[r + 1]) of the Morton-ordered group list; first_group has n_ranks + 1 entries. */
+int sph_slice_bounds(int32_t n_groups, int32_t n_ranks, int32_t* first_group);
+
 /* Replace the particle state (what read_data_from_file produces, F:594-716 | V:729-852).
  * alpha may be NULL (=0, F:681); h may be NULL in fixed-h mode. n_sink may be 0: the
  * reference's dummy zero-mass sink (F:698-707) is then created internally. */

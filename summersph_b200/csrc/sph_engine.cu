@@ -14,6 +14,7 @@
 
 #include "../../include/sph_b200.h"
 #include "sph_common.cuh"
+#include "sph_hostcomm.h"
 #include "sph_tree.cuh"
 #include "sph_walk.cuh"
 #ifndef GRAV_CHUNK_WIDTH
@@ -46,7 +47,7 @@ struct NcclApi {   // resolved at run time from the already-loaded (torch-bundle
   int (*GroupStart)() = nullptr;
   int (*GroupEnd)() = nullptr;
 };
-enum { NC_UINT64 = 5, NC_FLOAT64 = 8, NC_SUM = 0, NC_MIN = 3 };
+enum { NC_INT8 = 0, NC_INT32 = 2, NC_UINT64 = 5, NC_FLOAT64 = 8, NC_SUM = 0, NC_MAX = 2, NC_MIN = 3 };
 
 }  // namespace
 
@@ -71,6 +72,7 @@ struct sph_ctx {
   void* cub_tmp = nullptr; size_t cub_bytes = 0;
   double *d_wt = nullptr, *d_dwt = nullptr, *d_gt = nullptr;
   SinkArrays S = {}; double* sink_buf = nullptr; double* sink_partial = nullptr; size_t sink_partial_cap = 0;
+  double* sink_seg = nullptr; size_t sink_seg_cap = 0;     // [global GRAV_SEG segment][sink][3]: gas terms of the sink accelerations (exchanged between ranks)
   SimScalars* sc = nullptr; SimScalars* h_sc = nullptr;     // device + pinned host mirror
   WalkCounters* ctr = nullptr; WalkCounters* h_ctr = nullptr; int* work = nullptr;
   unsigned char* keep = nullptr; unsigned long long* acc_key[2] = {}; int* acc_val[2] = {}; int* d_nsel = nullptr;
@@ -83,6 +85,7 @@ struct sph_ctx {
   cudaEvent_t tm0 = nullptr, tm1 = nullptr;
   // multi-GPU
   NcclApi nccl; void* comm = nullptr; int rank = 0, n_ranks = 1;
+  HostComm* hc = nullptr;            // sph_comm_init_host: small collectives through host shared memory instead of NCCL (sph_hostcomm.h)
   std::vector<int> rank_g, rank_p;   // per-rank first group / first particle of its target slice (size n_ranks + 1)
   // peer-memory exchange: every exchanged array of every rank mapped here (CUDA IPC, or the raw pointer when the peer
   // lives in this process); slices are pushed with copy-engine transfers on their own stream
@@ -145,6 +148,8 @@ template <class T> int dalloc(sph_ctx* c, T** p, size_t count) {
 int ensure_capacity(sph_ctx* c, int64_t n) {
   if (n <= c->cap) return SPH_OK;
   const int64_t cap = n + n / 64 + 1024;
+  c->cap = 0; c->tree_valid = false; c->pos_moved = true; c->p2p_stale = true;      // a failed grow must not leave the old capacity standing over freed arrays
+  for (int b = 0; b < 2; ++b) if (c->key_lo[b]) { cudaFree(c->key_lo[b]); c->key_lo[b] = nullptr; }
   for (int b = 0; b < 2; ++b) { for (int f = 0; f < 10; ++f) DA(c->st[b][f], cap); DA(c->id[b], cap); DA(c->key[b], cap); DA(c->perm[b], cap); DA(c->acc_key[b], cap); DA(c->acc_val[b], cap); }
   DA(c->rho, cap); DA(c->omega, cap); DA(c->prs, cap); DA(c->cs, cap); DA(c->por2, cap);
   DA(c->ax, cap); DA(c->ay, cap); DA(c->az, cap); DA(c->udot, cap); DA(c->adot, cap);
@@ -169,7 +174,6 @@ int ensure_capacity(sph_ctx* c, int64_t n) {
   c->cub_bytes = std::max(std::max(std::max(b1, b4), std::max(b2, b3)), b5) + 256;
   if (c->cub_tmp) { cudaFree(c->cub_tmp); c->cub_tmp = nullptr; }
   if (cudaMalloc(&c->cub_tmp, c->cub_bytes) != cudaSuccess) { c->err = "cudaMalloc(cub temp)"; cudaGetLastError(); return SPH_ERR_OOM; }
-  for (int b = 0; b < 2; ++b) if (c->key_lo[b]) { cudaFree(c->key_lo[b]); c->key_lo[b] = nullptr; }
   c->cap = cap;
   c->p2p_stale = true;
   return SPH_OK;
@@ -224,12 +228,47 @@ int upload_tables(sph_ctx* c) {
 // ---------------------------------------------------------------------------------------------------
 #define NC(call) do { int r_ = (call); if (r_ != 0) { c->err = std::string(#call) + ": " + (c->nccl.GetErrorString ? c->nccl.GetErrorString(r_) : "nccl error"); return SPH_ERR_COMM; } } while (0)
 
+// ---- small collectives: NCCL on the given stream, or (sph_comm_init_host) through the host segment ----------------
+size_t nc_size(int dtype) { return dtype == NC_INT8 ? 1 : dtype == NC_INT32 ? 4 : 8; }
+template <class T> void host_fold(T* acc, const T* v, size_t count, int op) {
+  for (size_t i = 0; i < count; ++i) acc[i] = op == NC_SUM ? (T)(acc[i] + v[i]) : op == NC_MAX ? (v[i] > acc[i] ? v[i] : acc[i]) : (v[i] < acc[i] ? v[i] : acc[i]);
+}
+int coll_allreduce(sph_ctx* c, cudaStream_t st, void* buf, size_t count, int dtype, int op) {
+  if (c->n_ranks <= 1) return SPH_OK;
+  if (!c->hc) { NC(c->nccl.AllReduce(buf, buf, count, dtype, op, c->comm, st)); return SPH_OK; }
+  const size_t bytes = count * nc_size(dtype);
+  std::vector<char> mine(bytes), all(bytes * c->n_ranks);
+  CK(cudaMemcpyAsync(mine.data(), buf, bytes, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+  if (!c->hc->allgather(mine.data(), bytes, all.data())) { c->err = "host communicator: all-gather failed (payload too large or a peer timed out)"; return SPH_ERR_COMM; }
+  std::memcpy(mine.data(), all.data(), bytes);                       // rank order 0..R-1: the same fold on every rank
+  for (int r = 1; r < c->n_ranks; ++r) {
+    const char* v = all.data() + bytes * r;
+    if (dtype == NC_FLOAT64) host_fold((double*)mine.data(), (const double*)v, count, op);
+    else if (dtype == NC_UINT64) host_fold((unsigned long long*)mine.data(), (const unsigned long long*)v, count, op);
+    else if (dtype == NC_INT32) host_fold((int*)mine.data(), (const int*)v, count, op);
+    else host_fold((signed char*)mine.data(), (const signed char*)v, count, op);
+  }
+  CK(cudaMemcpyAsync(buf, mine.data(), bytes, cudaMemcpyHostToDevice, st)); CK(cudaStreamSynchronize(st));
+  return SPH_OK;
+}
+// recv[r * bytes ...] = rank r's send block (device buffers; send may alias its own block of recv)
+int coll_allgather(sph_ctx* c, cudaStream_t st, const void* send, void* recv, size_t bytes) {
+  if (c->n_ranks <= 1) { if (send != recv) CK(cudaMemcpyAsync(recv, send, bytes, cudaMemcpyDeviceToDevice, st)); return SPH_OK; }
+  if (!c->hc) { NC(c->nccl.AllGather(send, recv, bytes, NC_INT8, c->comm, st)); return SPH_OK; }
+  std::vector<char> mine(bytes), all(bytes * c->n_ranks);
+  CK(cudaMemcpyAsync(mine.data(), send, bytes, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+  if (!c->hc->allgather(mine.data(), bytes, all.data())) { c->err = "host communicator: all-gather failed (payload too large or a peer timed out)"; return SPH_ERR_COMM; }
+  CK(cudaMemcpyAsync(recv, all.data(), all.size(), cudaMemcpyHostToDevice, st)); CK(cudaStreamSynchronize(st));
+  return SPH_OK;
+}
+bool have_comm(const sph_ctx* c) { return c->hc != nullptr || c->comm != nullptr; }
+
 // ---- peer-memory all-gather-v -------------------------------------------------------------------------
 struct PeerRec { int pid; int device; unsigned long long hosthash; void* ptr; cudaIpcMemHandle_t h; };
 #include <unistd.h>
 
 std::vector<double*> exchanged_arrays(sph_ctx* c) {
-  return {c->rho, c->cs, c->por2, c->ax, c->ay, c->az, c->udot, c->adot, c->omega, c->prs, c->st[0][9], c->st[1][9]};
+  return {c->rho, c->cs, c->por2, c->ax, c->ay, c->az, c->udot, c->adot, c->omega, c->prs, c->st[0][9], c->st[1][9], c->sink_seg};
 }
 
 void p2p_close(sph_ctx* c) {
@@ -242,7 +281,7 @@ void p2p_close(sph_ctx* c) {
 int p2p_setup(sph_ctx* c) {
   c->p2p_stale = false;
   p2p_close(c);
-  if (c->n_ranks <= 1 || !c->nccl.AllGather || getenv("SPH_B200_NO_P2P")) return SPH_OK;
+  if (c->n_ranks <= 1 || !have_comm(c) || (!c->hc && !c->nccl.AllGather) || getenv("SPH_B200_NO_P2P")) return SPH_OK;
   if (!c->xstream) { CK(cudaStreamCreateWithFlags(&c->xstream, cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&c->x_ready, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c->x_done, cudaEventDisableTiming)); }
   if (!c->d_flag) DA(c->d_flag, 4);
   const std::vector<double*> arr = exchanged_arrays(c);
@@ -259,7 +298,7 @@ int p2p_setup(sph_ctx* c) {
   const size_t bytes = sizeof(PeerRec) * na;
   if (c->blob_cap < bytes * R) { if (c->d_blob) cudaFree(c->d_blob); CK(cudaMalloc(&c->d_blob, bytes * R)); c->blob_cap = bytes * R; }
   CK(cudaMemcpyAsync((char*)c->d_blob + bytes * c->rank, mine.data(), bytes, cudaMemcpyHostToDevice, c->stream));
-  NC(c->nccl.AllGather((char*)c->d_blob + bytes * c->rank, c->d_blob, bytes, 0 /*ncclInt8*/, c->comm, c->stream));
+  { int r_ = coll_allgather(c, c->stream, (char*)c->d_blob + bytes * c->rank, c->d_blob, bytes); if (r_) return r_; }
   CK(cudaMemcpyAsync(all.data(), c->d_blob, bytes * R, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   c->peer.assign(na, std::vector<double*>(R, nullptr));
@@ -286,7 +325,7 @@ int p2p_setup(sph_ctx* c) {
   }
   // every rank must have mapped every peer
   CK(cudaMemcpyAsync(c->d_flag, &ok, sizeof(int), cudaMemcpyHostToDevice, c->stream));
-  NC(c->nccl.AllReduce(c->d_flag, c->d_flag, 1, 2 /*ncclInt32*/, NC_MIN, c->comm, c->stream));
+  { int r_ = coll_allreduce(c, c->stream, c->d_flag, 1, NC_INT32, NC_MIN); if (r_) return r_; }
   int all_ok = 0;
   CK(cudaMemcpyAsync(&all_ok, c->d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
@@ -299,16 +338,18 @@ int p2p_setup(sph_ctx* c) {
 // copy-engine transfers on the exchange stream (no SMs: it runs under whatever kernel follows on the main
 // stream), then a 4-byte all-reduce as the cross-rank "all pushes have landed" barrier.  allgatherv_end makes
 // the main stream wait for it.  Without peer mapping: one in-place ncclBroadcast per owner on the main stream.
-int allgatherv_begin(sph_ctx* c, double* const* bufs, int nbufs) {
+// `roff` (n_ranks + 1 element offsets) replaces the particle slices [rank_p[r], rank_p[r + 1]) when given.
+int allgatherv_begin(sph_ctx* c, double* const* bufs, int nbufs, const size_t* roff = nullptr) {
   if (c->n_ranks <= 1) return SPH_OK;
   if (c->p2p_stale) { int r_ = p2p_setup(c); if (r_) return r_; }
   if (!c->p2p_ok) {
+    if (c->hc) { c->err = "the host communicator moves bulk data over peer-mapped device memory only (peer mapping failed or SPH_B200_NO_P2P is set)"; return SPH_ERR_COMM; }
     NC(c->nccl.GroupStart());
     for (int b = 0; b < nbufs; ++b)
       for (int r = 0; r < c->n_ranks; ++r) {
-        const int cnt = c->rank_p[r + 1] - c->rank_p[r];
+        const long long cnt = roff ? (long long)(roff[r + 1] - roff[r]) : (long long)(c->rank_p[r + 1] - c->rank_p[r]);
         if (cnt <= 0) continue;
-        double* p = bufs[b] + c->rank_p[r];
+        double* p = bufs[b] + (roff ? roff[r] : (size_t)c->rank_p[r]);
         NC(c->nccl.Broadcast(p, p, (size_t)cnt, NC_FLOAT64, r, c->comm, c->stream));
       }
     NC(c->nccl.GroupEnd());
@@ -322,7 +363,7 @@ int allgatherv_begin(sph_ctx* c, double* const* bufs, int nbufs) {
     CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     c->pstream.push_back(st); c->pevent.push_back(ev);
   }
-  const size_t off = (size_t)c->p0, cnt = (size_t)(c->p1 - c->p0);
+  const size_t off = roff ? roff[c->rank] : (size_t)c->p0, cnt = roff ? roff[c->rank + 1] - roff[c->rank] : (size_t)(c->p1 - c->p0);
   std::vector<int> slot(nbufs, -1);
   for (int b = 0; b < nbufs; ++b) {
     for (int k = 0; k < (int)arr.size(); ++k) if (arr[k] == bufs[b]) slot[b] = k;
@@ -338,7 +379,7 @@ int allgatherv_begin(sph_ctx* c, double* const* bufs, int nbufs) {
     CK(cudaEventRecord(c->pevent[k - 1], st));
     CK(cudaStreamWaitEvent(c->xstream, c->pevent[k - 1], 0));
   }
-  NC(c->nccl.AllReduce(c->d_flag + 1, c->d_flag + 1, 1, 2 /*ncclInt32*/, NC_SUM, c->comm, c->xstream));
+  { int r_ = coll_allreduce(c, c->xstream, c->d_flag + 1, 1, NC_INT32, NC_SUM); if (r_) return r_; }
   CK(cudaEventRecord(c->x_done, c->xstream));
   c->x_pending = true;
   return SPH_OK;
@@ -349,23 +390,26 @@ int allgatherv_end(sph_ctx* c) {
   c->x_pending = false;
   return SPH_OK;
 }
-int allgatherv(sph_ctx* c, double* const* bufs, int nbufs) {
-  int r = allgatherv_begin(c, bufs, nbufs);
+int allgatherv(sph_ctx* c, double* const* bufs, int nbufs, const size_t* roff = nullptr) {
+  int r = allgatherv_begin(c, bufs, nbufs, roff);
   return r ? r : allgatherv_end(c);
 }
 int allreduce(sph_ctx* c, void* buf, size_t count, int dtype, int op) {
   if (c->n_ranks <= 1) return SPH_OK;
-  NC(c->nccl.AllReduce(buf, buf, count, dtype, op, c->comm, c->stream));
-  return SPH_OK;
+  return coll_allreduce(c, c->stream, buf, count, dtype, op);
 }
 
 __global__ void k_set_int(int* p, int v) { *p = v; }
 
+// first walk group of every rank's target slice (n_ranks + 1 entries): contiguous, cut only at multiples of GRAV_SEG
+// groups (the gravity runs restart there, sph_gravity.cuh), so runs and segments are the same for any rank count
+void slice_first_groups(int ng, int R, int* first) {
+  for (int r = 0; r <= R; ++r) first[r] = r == R ? ng : (int)(((int64_t)ng * r / R) / GRAV_SEG * GRAV_SEG);
+}
 int compute_slices(sph_ctx* c) {
   const int R = c->n_ranks, ng = c->n_groups, n = (int)c->n;
   c->rank_g.assign(R + 1, 0); c->rank_p.assign(R + 1, 0);
-  // slices are cut at multiples of GRAV_SEG groups (the gravity runs restart there: sph_gravity.cuh)
-  for (int r = 0; r <= R; ++r) c->rank_g[r] = r == R ? ng : (int)(((int64_t)ng * r / R) / GRAV_SEG * GRAV_SEG);
+  slice_first_groups(ng, R, c->rank_g.data());
   c->rank_p[R] = n;
   if (R > 1) {
     for (int r = 1; r < R; ++r)
@@ -514,6 +558,10 @@ int build_tree_impl(sph_ctx* c, bool* retry_two_word) {
     }
     bi.nlev = l + 1;
     { int r_ = compute_slices(c); if (r_) return r_; }
+    {   // global segment table of the sink sums: sized here so that the peer mapping (first exchange = density) sees it
+      const int nst = cdiv(c->n_groups, GRAV_SEG), nsk = std::max(c->n_sink, 1);
+      if ((size_t)nst * nsk * 3 > c->sink_seg_cap) { c->sink_seg_cap = (size_t)(nst + nst / 8 + 64) * (nsk + 1) * 3; DA(c->sink_seg, c->sink_seg_cap); c->p2p_stale = true; }
+    }
   }
   stage_end(c);
   c->tree_valid = true; c->pos_moved = false;
@@ -612,7 +660,7 @@ int run_force(sph_ctx* c) {
   if (c->n_ranks > 1) {
     stage_begin(c, ST_COMM);
     if (po.n > 0) {     // the kernels pushed their slices themselves: only the "every rank's kernel has finished" barrier is left
-      NC(c->nccl.AllReduce(c->d_flag + 2, c->d_flag + 2, 1, 2 /*ncclInt32*/, NC_SUM, c->comm, c->stream));
+      { int r_ = coll_allreduce(c, c->stream, c->d_flag + 2, 1, NC_INT32, NC_SUM); if (r_) return r_; }
     } else { double* bufs[5] = {c->ax, c->ay, c->az, c->udot, c->adot}; int r_ = allgatherv(c, bufs, 5); if (r_) return r_; }
     stage_end(c);
   }
@@ -674,8 +722,8 @@ int run_gravity(sph_ctx* c, int do_grav, int do_sinks) {
   const int ns_k = ns;
 #define GW_FAR_ARG
 #endif
-  if ((size_t)(ng + 8 + SINK_RED_BLOCKS) * std::max(ns, 1) * 3 > c->sink_partial_cap) {
-    c->sink_partial_cap = (size_t)(ng + 8 + SINK_RED_BLOCKS) * std::max(ns, 1) * 3 * 2;
+  if ((size_t)(ng + 8) * std::max(ns, 1) * 3 > c->sink_partial_cap) {
+    c->sink_partial_cap = (size_t)(ng + 8) * std::max(ns, 1) * 3 * 2;
     DA(c->sink_partial, c->sink_partial_cap);
   }
   if (ng > 0 && c->g1 > c->g0) {
@@ -719,14 +767,28 @@ int run_gravity(sph_ctx* c, int do_grav, int do_sinks) {
     fprintf(stderr, "GWHIST"); for (int i = 0; i < 33; ++i) fprintf(stderr, " %llu", hh[i]); fprintf(stderr, "\n"); }
 #endif
   if (far_pass) { stage_end(c); return SPH_OK; }      // the sinks keep the accelerations of the walk that stored the far sums
-  if (do_sinks && ng > 4 * SINK_RED_BLOCKS) {
-    double* rows = c->sink_partial + (size_t)ng * std::max(ns, 1) * 3;      // spare rows behind the per-run partials
-    LAUNCH(k_sink_reduce_slices, SINK_RED_BLOCKS, 256, 0, ng, c->n_sink, c->sink_partial, rows);
-    LAUNCH(k_sink_reduce, 1, 256, 0, SINK_RED_BLOCKS, c->n_sink, rows, c->S, do_sinks);
-  } else
-    LAUNCH(k_sink_reduce, 1, 256, 0, ng, c->n_sink, c->sink_partial, c->S, do_sinks);
-  stage_end(c);
-  if (c->n_ranks > 1) { stage_begin(c, ST_COMM); int r_ = allreduce(c, c->S.ax, (size_t)3 * SPH_MAX_SINKS, NC_FLOAT64, NC_SUM); if (r_) return r_; stage_end(c); }
+  // sink side of the gas terms: per-segment folds -> exchange of the rows -> one fixed fold over all segments (rank-count independent)
+  {
+    const int nst = cdiv(c->n_groups, GRAV_SEG), nsk = std::max(c->n_sink, 1);
+    if ((size_t)nst * nsk * 3 > c->sink_seg_cap) {
+      c->sink_seg_cap = (size_t)(nst + nst / 8 + 64) * (nsk + 1) * 3;
+      DA(c->sink_seg, c->sink_seg_cap); c->p2p_stale = true;
+    }
+    if (do_sinks && nseg > 0 && c->g1 > c->g0)
+      LAUNCH(k_sink_seg_fold, cdiv((int64_t)nseg * c->n_sink * 3, 128), 128, 0, nseg, seg0, c->n_sink, c->seg_off, c->sink_partial, c->sink_seg);
+    stage_end(c);
+    if (c->n_ranks > 1 && do_sinks) {
+      stage_begin(c, ST_COMM);
+      std::vector<size_t> roff(c->n_ranks + 1);
+      for (int r = 0; r <= c->n_ranks; ++r) roff[r] = (size_t)(r == c->n_ranks ? nst : c->rank_g[r] / GRAV_SEG) * c->n_sink * 3;
+      double* bufs[1] = {c->sink_seg};
+      int r_ = allgatherv(c, bufs, 1, roff.data()); if (r_) return r_;
+      stage_end(c);
+    }
+    stage_begin(c, ST_GRAVITY);
+    LAUNCH(k_sink_reduce, 1, 256, 0, nst, c->n_sink, c->sink_seg, c->S, do_sinks);
+    stage_end(c);
+  }
   stage_begin(c, ST_GRAVITY);
   LAUNCH(k_sink_pairs, 1, 32, 0, c->n_sink, c->S, c->dp.G, do_sinks);
   stage_end(c);
@@ -764,6 +826,7 @@ int fetch_counters(sph_ctx* c) {
 
 int check_device_error(sph_ctx* c) {
   if (c->h_sc->err == 2) { c->err = "gravity walk: node stack overflow (GW_SPILL)"; return SPH_ERR_STATE; }
+  if (c->h_sc->err == 3) { c->err = "sink table full (SPH_MAX_SINKS): check_sink_creation (V:549-597) could not append a sink"; return SPH_ERR_STATE; }
   if (c->h_sc->err) {
     c->err = "particles share a full 126-bit descent key (closer than root_size/2^42) while max_depth > 42";
     return SPH_ERR_DEPTH;
@@ -829,7 +892,11 @@ int step(sph_ctx* c) {
   CK(cudaMemcpyAsync(c->h_sc, c->sc, sizeof(SimScalars), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   if ((r = check_device_error(c))) return r;
-  int n_acc = std::min(c->h_sc->n_accreted, (int)c->cap);
+  if (c->h_sc->n_accreted > (int)c->cap) {      // k_flags already dropped the particles: never truncate silently
+    c->err = "accretion list overflow: " + std::to_string(c->h_sc->n_accreted) + " (sink, particle) entries, capacity " + std::to_string((long long)c->cap);
+    return SPH_ERR_STATE;
+  }
+  int n_acc = c->h_sc->n_accreted;
   if (n_acc > 1) {
     cub::DoubleBuffer<unsigned long long> dk(c->acc_key[0], c->acc_key[1]); cub::DoubleBuffer<int> dv(c->acc_val[0], c->acc_val[1]);
     size_t bytes = c->cub_bytes;
@@ -1003,6 +1070,7 @@ int sph_destroy(sph_ctx* c) {
   if (c->d_flag) cudaFree(c->d_flag);
   if (c->d_blob) cudaFree(c->d_blob);
   if (c->comm && c->nccl.CommDestroy) c->nccl.CommDestroy(c->comm);
+  if (c->hc) { c->hc->close(); delete c->hc; c->hc = nullptr; }
   auto F = [](void* p) { if (p) cudaFree(p); };
   for (int b = 0; b < 2; ++b) { for (int f = 0; f < 10; ++f) F(c->st[b][f]); F(c->id[b]); F(c->key[b]); F(c->key_lo[b]); F(c->perm[b]); F(c->acc_key[b]); F(c->acc_val[b]); }
   F(c->rho); F(c->omega); F(c->prs); F(c->cs); F(c->por2); F(c->ax); F(c->ay); F(c->az); F(c->udot); F(c->adot);
@@ -1013,7 +1081,7 @@ int sph_destroy(sph_ctx* c) {
   F(c->far_x); F(c->far_y); F(c->far_z); F(c->far_hcut); F(c->far_dec); F(c->far_flag); F(c->far_near); F(c->far_near_cnt);
 #endif
   F(c->arrive); F(c->cnt); F(c->off); F(c->root); F(c->partial); F(c->cub_tmp); F(c->d_wt); F(c->d_dwt); F(c->d_gt);
-  F(c->sink_buf); F(c->sink_partial); F(c->sc); F(c->ctr); F(c->work); F(c->keep); F(c->d_nsel); F(c->pos); F(c->stage_d); F(c->stage_d2);
+  F(c->sink_buf); F(c->sink_partial); F(c->sink_seg); F(c->sc); F(c->ctr); F(c->work); F(c->keep); F(c->d_nsel); F(c->pos); F(c->stage_d); F(c->stage_d2);
   if (c->h_sc) cudaFreeHost(c->h_sc);
   if (c->h_ctr) cudaFreeHost(c->h_ctr);
   for (auto& e : c->ev_used) { cudaEventDestroy(e.second.first); cudaEventDestroy(e.second.second); }
@@ -1039,6 +1107,26 @@ int sph_comm_init(sph_ctx* c, int32_t rank, int32_t n_ranks, const void* uid) {
   NcclUid id; std::memcpy(&id, uid, 128);
   int r = c->nccl.CommInitRank(&c->comm, n_ranks, id, rank);
   if (r != 0) { c->err = std::string("ncclCommInitRank: ") + (c->nccl.GetErrorString ? c->nccl.GetErrorString(r) : "?"); return SPH_ERR_COMM; }
+  c->rank = rank; c->n_ranks = n_ranks; c->tree_valid = false; c->pos_moved = true; c->p2p_stale = true;
+  return SPH_OK;
+}
+
+int sph_slice_bounds(int32_t n_groups, int32_t n_ranks, int32_t* first_group) {
+  if (n_groups < 0 || n_ranks < 1 || !first_group) return SPH_ERR_ARG;
+  slice_first_groups(n_groups, n_ranks, first_group);
+  return SPH_OK;
+}
+
+int sph_comm_init_host(sph_ctx* c, int32_t rank, int32_t n_ranks, const char* name) {
+  if (!c || !name || n_ranks < 1 || rank < 0 || rank >= n_ranks) return SPH_ERR_ARG;
+  if (c->comm || c->hc) { c->err = "communicator already initialised"; return SPH_ERR_STATE; }
+  cudaSetDevice(c->device);
+  if (n_ranks > 1) {
+    HostComm* hc = new HostComm();
+    const std::string e = hc->open(name, rank, n_ranks);
+    if (!e.empty()) { c->err = "sph_comm_init_host: " + e; hc->close(); delete hc; return SPH_ERR_COMM; }
+    c->hc = hc;
+  }
   c->rank = rank; c->n_ranks = n_ranks; c->tree_valid = false; c->pos_moved = true; c->p2p_stale = true;
   return SPH_OK;
 }

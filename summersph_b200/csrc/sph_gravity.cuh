@@ -547,24 +547,20 @@ __global__ void k_grav_boxes(int n_chunks, const int2* __restrict__ groups, cons
   }
 }
 
-// fold the per-run sink partials in a fixed order (deterministic): SINK_RED_BLOCKS blocks each fold a contiguous
-// slice of the runs into out[block][sink][3]; k_sink_reduce then folds those few rows.
-#define SINK_RED_BLOCKS 128
-__global__ void k_sink_reduce_slices(int n_parts, int n_sink, const double* __restrict__ partial, double* __restrict__ out) {
-  __shared__ double red[256];
-  const int t = threadIdx.x;
-  const int per = (n_parts + gridDim.x - 1) / gridDim.x;
-  const int b0 = blockIdx.x * per, b1 = min(b0 + per, n_parts);
-  for (int s = 0; s < n_sink; ++s)
-    for (int k = 0; k < 3; ++k) {
-      double v = 0.0;
-      for (int b = b0 + t; b < b1; b += 256) v += partial[((size_t)b * n_sink + s) * 3 + k];
-      red[t] = v;
-      __syncthreads();
-      for (int o = 128; o > 0; o >>= 1) { if (t < o) red[t] += red[t + o]; __syncthreads(); }
-      if (t == 0) out[((size_t)blockIdx.x * n_sink + s) * 3 + k] = red[0];
-      __syncthreads();
-    }
+// Sink-side sums of the gas terms, in an order that does not depend on the number of ranks: the per-run partials
+// (one warp sum per 32-particle run, written by k_gravity) are folded serially per GRAV_SEG segment - segments and
+// their runs are the same for any rank count, rank slices are cut at segment boundaries - into the global segment
+// table seg[global segment][sink][3]; the ranks exchange their rows; k_sink_reduce then folds ALL segments of the
+// tree with one fixed pattern on every rank.  (Per-rank totals added by an all-reduce would group the FP64 sum by
+// rank: the sinks start at v = 0, so an ulp there reaches every gas acceleration within a step.)
+__global__ void k_sink_seg_fold(int nseg, int seg0, int n_sink, const int* __restrict__ seg_off, const double* __restrict__ partial,
+                                double* __restrict__ seg) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nseg * n_sink * 3) return;
+  const int s = t / (n_sink * 3), r = t % (n_sink * 3);
+  double v = 0.0;
+  for (int b = seg_off[s]; b < seg_off[s + 1]; ++b) v += partial[(size_t)b * n_sink * 3 + r];
+  seg[(size_t)(seg0 + s) * n_sink * 3 + r] = v;
 }
 __global__ void k_sink_reduce(int n_parts, int n_sink, const double* __restrict__ partial, SinkArrays S, int do_sinks) {
   __shared__ double red[256];

@@ -113,7 +113,7 @@ __global__ void k_create_apply(StateArrays s, SinkArrays S, SimScalars* sc, doub
     const double dr = sqrt(dx * dx + dy * dy + dz * dz);
     if (dr < S.radius[j] + 2.0 * s.h[i]) return;                                   // V:563-565
   }
-  if (ns >= SPH_MAX_SINKS) return;
+  if (ns >= SPH_MAX_SINKS) { sc->err = 3; return; }      // loud: the reference grows sinks(:) without bound (V:568-586)
   S.x[ns] = s.x[i]; S.y[ns] = s.y[i]; S.z[ns] = s.z[i];
   S.vx[ns] = s.vx[i]; S.vy[ns] = s.vy[i]; S.vz[ns] = s.vz[i];
   S.ax[ns] = S.ay[ns] = S.az[ns] = 0.0;
@@ -188,8 +188,12 @@ __global__ void k_accrete_apply(int n_acc, const unsigned long long* __restrict_
   if (j >= sc->n_sink || !sc->any_sink_mass) return;
   double sm = 0.0, sp[3] = {0.0, 0.0, 0.0}, sv[3] = {0.0, 0.0, 0.0}, lb[3] = {0.0, 0.0, 0.0};
   int n_mine = 0;
-  for (int e = 0; e < n_acc; ++e) {
-    if ((int)(acc_key[e] >> 32) != j) continue;
+  // the list is sorted by (sink, number): this sink's entries are one contiguous range, summed in ascending number
+  int lo = 0, hi = n_acc;
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if ((int)(acc_key[mid] >> 32) < j) lo = mid + 1; else hi = mid; }
+  int e1 = lo; hi = n_acc;
+  while (e1 < hi) { const int mid = (e1 + hi) >> 1; if ((int)(acc_key[mid] >> 32) <= j) e1 = mid + 1; else hi = mid; }
+  for (int e = lo; e < e1; ++e) {
     const int i = acc_val[e];
     const double mi = s.m[i];
     if (spin) {

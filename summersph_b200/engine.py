@@ -42,6 +42,8 @@ def load_library(path=None):
     lib.sph_destroy.argtypes = [vp]
     lib.sph_comm_unique_id.argtypes = [vp]
     lib.sph_comm_init.argtypes = [vp, i32, i32, vp]
+    lib.sph_slice_bounds.argtypes = [i32, i32, vp]
+    lib.sph_comm_init_host.argtypes = [vp, i32, i32, C.c_char_p]
     lib.sph_upload.argtypes = [vp, i64] + [vp] * 10 + [i32] + [vp] * 8
     lib.sph_evaluate.argtypes = [vp, i32]
     lib.sph_step.argtypes = [vp, C.POINTER(dbl), C.POINTER(dbl), C.POINTER(i64), C.POINTER(i32)]
@@ -125,6 +127,10 @@ class Engine:
     def comm_init(self, rank, n_ranks, unique_id: bytes):
         buf = (C.c_char * 128).from_buffer_copy(unique_id)
         self._ck(self._l.sph_comm_init(self._c, int(rank), int(n_ranks), buf))
+
+    def comm_init_host(self, rank, n_ranks, name: str):
+        """Small collectives through a host shared-memory segment instead of NCCL (several ranks may share a GPU)."""
+        self._ck(self._l.sph_comm_init_host(self._c, int(rank), int(n_ranks), name.encode()))
 
     # -- state -------------------------------------------------------------------------------------
     def upload(self, b: Bodies, s: Sinks):

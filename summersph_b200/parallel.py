@@ -9,8 +9,15 @@ bit-identical state after each step, and an N-rank run is bit-identical to the 1
 
 
 def slice_bounds(n_groups, rank, world):
-    """Group slice [g0, g1) of `rank` — the same integer arithmetic as compute_slices() in sph_engine.cu."""
-    return (n_groups * rank) // world, (n_groups * (rank + 1)) // world
+    """Group slice [g0, g1) of `rank`: the engine's own `sph_slice_bounds` (the function compute_slices() in
+    sph_engine.cu uses; cuts fall on multiples of 64 groups so the gravity runs do not depend on the rank count)."""
+    import ctypes as C
+    from .engine import load_library
+    first = (C.c_int32 * (world + 1))()
+    rc = load_library().sph_slice_bounds(int(n_groups), int(world), first)
+    if rc != 0:
+        raise ValueError("sph_slice_bounds: bad arguments")
+    return int(first[rank]), int(first[rank + 1])
 
 
 def init_comm(engine, rank, world, broadcast_bytes):

@@ -1,0 +1,54 @@
+"""Worker of tests/test_multi_gpu.py: ONE rank of an N-rank engine run, in its own process (the way bench.py and a
+production host run it: one process per rank, CUDA-IPC peers).  Not a test module.
+
+  python tests/_mp_rank.py RANK WORLD COMM DEVICE MODE STEPS OUT.npz [UID_HEX | SHM_NAME] [N] [DOMAINS]
+
+COMM = nccl (needs one GPU per rank) | host (shared-memory collectives: ranks may share a device).
+"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+def case(mode, n=60_000):
+    from summersph_b200 import default_params, ics
+    p = default_params(mode, bounding_size=95.0)
+    b, s = ics.keplerian_disc(n, seed=12)
+    s.radius[:] = 12.0                      # accretion + bounds removals exercised too
+    return p, b, s
+
+
+def main():
+    rank, world, comm, device, mode, steps, out = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3], int(sys.argv[4]), int(sys.argv[5]), int(sys.argv[6]), sys.argv[7]
+    token = sys.argv[8] if len(sys.argv) > 8 else ""
+    n = int(sys.argv[9]) if len(sys.argv) > 9 else 60_000
+    from summersph_b200.engine import Engine
+    from summersph_b200.state import GAS_FIELDS
+    p, b, s = case(mode, n)
+    with Engine(p, device=device) as e:
+        if world > 1:
+            if comm == "nccl":
+                e.comm_init(rank, world, bytes.fromhex(token))
+            else:
+                e.comm_init_host(rank, world, token)
+        e.upload(b, s)
+        dt, t = 0.01, 0.0
+        for _ in range(steps):
+            dt, t = e.step(dt, t)
+        bb, ss = e.download()
+        d = e.diag()
+        c = e.counters()
+        res = {k: getattr(bb, k) for k in GAS_FIELDS}
+        res.update({"s_" + k: getattr(ss, k) for k in ("x", "y", "z", "vx", "vy", "vz", "m")})
+        res.update({"d_" + k: v for k, v in d.items()})
+        res["meta"] = np.array([dt, t, float(e.sizes()[0]), float(e.sizes()[1])])
+        res["counters"] = np.array([c[k] for k in sorted(c)], dtype=np.int64)
+        np.savez(out, **res)
+
+
+if __name__ == "__main__":
+    main()

@@ -62,3 +62,4 @@ def test_slice_bounds_cover():
             assert b[0][0] == 0 and b[-1][1] == ng
             assert all(b[i][1] == b[i + 1][0] for i in range(world - 1))
             assert all(g1 >= g0 for g0, g1 in b)
+            assert all(g0 % 64 == 0 for g0, _ in b)          # cuts only where the gravity runs restart (GRAV_SEG)
