@@ -106,15 +106,18 @@ def cpu_reference_rate(n_sample, steps, warmup, threads):
     return n * steps / el, el / steps
 
 
+REF_THREADS = 16      # fixed, so that records taken on boxes with different core counts are comparable
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = min(REF_THREADS, os.cpu_count() or 1)
     n_sample = args.ref_particles
-    rate, sec = cpu_reference_rate(n_sample, args.steps, min(args.warmup, 1), threads)
+    rate, sec = cpu_reference_rate(n_sample, args.steps, args.warmup, threads)
     line = {
         "impl": "reference", "metric": "particle-steps/s", "value": rate, "unit": "particle-steps/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"Keplerian disc {args.particles} gas + 1 sink, variable h (BASELINE configs[3]); each step timed on a {n_sample}-particle sample of it"},
         "cpu_baseline": {"value": rate, "unit": "particle-steps/s", "cores": threads, "kind": "port",
@@ -131,7 +134,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--particles", type=int, default=16_000_000)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--ref-particles", type=int, default=200_000)
+    ap.add_argument("--ref-particles", type=int, default=1_000_000)
     ap.add_argument("--cpu-baseline-particles", type=int, default=100_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (large multi-GPU sizing runs)")

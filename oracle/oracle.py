@@ -170,6 +170,17 @@ class Oracle:
             lst = lst[:tot]
         return count, hsh, off, lst
 
+    def sample_eval(self, targets):
+        """One evaluation's results for a few target particles only (0-based numbers); the tree is built over the
+        whole set.  For checking the engine at sizes the full serial pair loop cannot reach (sph_oracle.cpp: sample_eval)."""
+        tg = np.ascontiguousarray(targets, dtype=np.int32)
+        nt = len(tg)
+        d = {k: np.zeros(nt) for k in ("rho", "omega", "P", "c", "ax", "ay", "az", "udot", "alphadot")}
+        d["count"] = np.zeros(nt, np.int32); d["hash"] = np.zeros(nt, np.uint64); d["pairs"] = np.zeros(nt, np.int64)
+        self._l.orc_sample_eval(self._c, C.c_int32(nt), _p(tg), *[_p(d[k]) for k in ("rho", "omega", "P", "c", "ax", "ay", "az", "udot",
+                                                                                   "alphadot", "count", "hash", "pairs")])
+        return d
+
     def check_sink_merger(self):
         self._l.orc_check_sink_merger(self._c)
 

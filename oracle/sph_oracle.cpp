@@ -343,20 +343,11 @@ void sink_gravforces(Oracle& o) {
     }
 }
 
-// ---- SPH pair walk: F:323-395 | V:352-432 ----------------------------------------------------------
-// `atomic_updates`: timing-only OpenMP variant makes the neighbour-side update atomic (the
-// reference's OMP loop is racy, F:302-313); the serial parity path is the literal order.
-template <bool ATOMIC>
-void SPH_tree_search(Oracle& o, int ni, Particle& body, int64_t& pairs) {
-  const Node& nd = o.nodes[ni];
-  const double reach = search_reach(o, nd);
-  if (nd.n_particles > 1 && box_test(body.position, nd, reach) && nd.has_children) {
-    for (int c = 0; c < 8; ++c) if (nd.child[c] >= 0) SPH_tree_search<ATOMIC>(o, nd.child[c], body, pairs);
-  } else if (nd.n_particles == 1 && box_test(body.position, nd, reach)) {
-    const int num = o.order[nd.first];
-    if (o.bodies[num].number >= body.number) return;                       // F:354
-    Particle& nb = o.bodies[num];
-    pairs++;
+// One pair as the reference evaluates it with `body` = the higher-numbered particle that found `nb` in its walk
+// (F:356-387 | V:385-421): acc_contrib (F:381-382 | V:413-414), vdotgradW (F:370 | V:401) and the two du/dt terms.
+// hn = the leaf copy's s_length (V:396).  Shared by the full pair loop and by the sampled evaluation below.
+inline void pair_terms(const Oracle& o, const Particle& body, const Particle& nb, double hn_tree,
+                       double acc_contrib[3], double& vdotgradW, double& ub, double& un) {
     double nr[3], vij[3];
     for (int d = 0; d < 3; ++d) nr[d] = body.position[d] - nb.position[d];
     double dr = std::sqrt(((nr[0] * nr[0]) + nr[1] * nr[1]) + nr[2] * nr[2]);
@@ -364,7 +355,7 @@ void SPH_tree_search(Oracle& o, int ni, Particle& body, int64_t& pairs) {
     double vdotr = ((vij[0] * nr[0]) + vij[1] * nr[1]) + vij[2] * nr[2];
     if (vdotr >= 0) vdotr = 0.0;                                           // F:361
     for (int d = 0; d < 3; ++d) nr[d] = nr[d] / dr;                        // F:363
-    double acc_contrib[3], vdotgradW, viscous_cont, Pi_term, Pj_term;
+    double viscous_cont, Pi_term, Pj_term;
     if (!o.variable_h) {
       const double h = o.p.h_fixed;
       double Wj, dWm; lookup_kernel(o, dr, h, Wj, dWm);                    // F:366
@@ -378,7 +369,7 @@ void SPH_tree_search(Oracle& o, int ni, Particle& body, int64_t& pairs) {
       Pj_term = nb.pressure / (nb.density * nb.density);
       for (int d = 0; d < 3; ++d) acc_contrib[d] = ((Pi_term + Pj_term) + viscous_cont) * dWj[d];   // F:381-382
     } else {
-      const double hb = body.s_length, hn = o.h_tree[num];                 // V:395-396 (leaf copy's s_length)
+      const double hb = body.s_length, hn = hn_tree;                 // V:395-396 (leaf copy's s_length)
       double Wj, dWjm, Wi, dWim;
       lookup_kernel(o, dr, hb, Wj, dWjm);
       lookup_kernel(o, dr, hn, Wi, dWim);
@@ -397,8 +388,26 @@ void SPH_tree_search(Oracle& o, int ni, Particle& body, int64_t& pairs) {
       for (int d = 0; d < 3; ++d)
         acc_contrib[d] = ((Pi_term * dWj[d]) + (Pj_term * dWi[d])) + viscous_cont * (dWi[d] + dWj[d]) / 2;   // V:413-414
     }
-    const double ub = nb.mass * vdotgradW * (Pi_term + 0.5 * viscous_cont);  // F:387 | V:419-421
-    const double un = body.mass * vdotgradW * (Pj_term + 0.5 * viscous_cont);
+    ub = nb.mass * vdotgradW * (Pi_term + 0.5 * viscous_cont);  // F:387 | V:419-421
+    un = body.mass * vdotgradW * (Pj_term + 0.5 * viscous_cont);
+}
+
+// ---- SPH pair walk: F:323-395 | V:352-432 ----------------------------------------------------------
+// `atomic_updates`: timing-only OpenMP variant makes the neighbour-side update atomic (the
+// reference's OMP loop is racy, F:302-313); the serial parity path is the literal order.
+template <bool ATOMIC>
+void SPH_tree_search(Oracle& o, int ni, Particle& body, int64_t& pairs) {
+  const Node& nd = o.nodes[ni];
+  const double reach = search_reach(o, nd);
+  if (nd.n_particles > 1 && box_test(body.position, nd, reach) && nd.has_children) {
+    for (int c = 0; c < 8; ++c) if (nd.child[c] >= 0) SPH_tree_search<ATOMIC>(o, nd.child[c], body, pairs);
+  } else if (nd.n_particles == 1 && box_test(body.position, nd, reach)) {
+    const int num = o.order[nd.first];
+    if (o.bodies[num].number >= body.number) return;                       // F:354
+    Particle& nb = o.bodies[num];
+    pairs++;
+    double acc_contrib[3], vdotgradW, ub, un;
+    pair_terms(o, body, nb, o.variable_h ? o.h_tree[num] : o.p.h_fixed, acc_contrib, vdotgradW, ub, un);
     for (int d = 0; d < 3; ++d) body.acceleration[d] = body.acceleration[d] - nb.mass * acc_contrib[d];
     body.internal_energy_rate = body.internal_energy_rate + ub;
     body.alpha_rate = body.alpha_rate + nb.mass * vdotgradW;
@@ -484,6 +493,108 @@ void evaluate(Oracle& o, int mask) {
   o.cnt.n_gas = n; o.cnt.n_nodes = (int64_t)o.nodes.size();
   if (mask & SPH_EVAL_DENSITY) { get_density(o); get_pressure_and_sound_speed(o); }
   find_forces(o, mask);
+}
+
+// ---- sampled evaluation: what ONE full evaluation (F:894-898 | V:1128-1132) gives to a few target particles ------------
+// For checking the engine at sizes where the full serial pair loop would take hours (16M particles): the tree is
+// built over the whole set, then each target's density, gravity, sink and SPH sums are evaluated on their own.  The
+// pair loop is taken in gather form: target i meets every j < i its own walk finds
+// (F:351-354 | V:380-383: x_i inside Box(j)) and every j > i whose walk finds it (x_j inside Box(i), all ancestor
+// tests of V:368 replayed along the root-to-leaf path of i); each term is pair_terms() with the reference's roles
+// (`body` = higher number), so only the order of accumulation differs from the full loop (rounding level).
+struct SampleCache { std::vector<int> idx; std::vector<double> rho, omega; };
+static void sample_density(const Oracle& o, int i, double& rho, double& omega, std::vector<int>* list) {
+  const Particle& b = o.bodies[i];
+  DensAcc acc{0.0, 0.0, 0, 0, list};
+  density_tree_search(o, 0, b.position, b.s_length, acc);
+  rho = acc.rho;
+  omega = o.variable_h ? 1.0 + (b.s_length / (3.0 * rho)) * acc.omega : 1.0;          // V:455
+}
+// all j whose position lies inside Box(i) = every node of i's root-to-leaf path passes the walk's test for x_j
+static void sample_box_query(const Oracle& o, const std::vector<int>& path, int ni, const double* lo, const double* hi, std::vector<int>& out) {
+  const Node& nd = o.nodes[ni];
+  for (int d = 0; d < 3; ++d) if (nd.center[d] + nd.size / 2.0 < lo[d] || nd.center[d] - nd.size / 2.0 > hi[d]) return;
+  if (nd.has_children) { for (int c = 0; c < 8; ++c) if (nd.child[c] >= 0) sample_box_query(o, path, nd.child[c], lo, hi, out); return; }
+  for (int k = 0; k < nd.n_particles; ++k) {
+    const int j = o.order[nd.first + k];
+    const double* pos = &o.x_tree[3 * (size_t)j];
+    bool ok = true;
+    for (size_t q = 0; q < path.size() && ok; ++q) {
+      const Node& pn = o.nodes[path[q]];
+      ok = box_test(pos, pn, search_reach(o, pn)) && (q + 1 == path.size() ? pn.n_particles == 1 : (pn.n_particles > 1 && pn.has_children));
+    }
+    if (ok) out.push_back(j);
+  }
+}
+void sample_eval(Oracle& o, int nt, const int* targets, double* rho, double* omega, double* P, double* cs,
+                 double* ax, double* ay, double* az, double* udot, double* adot, int32_t* ncount, uint64_t* nhash, int64_t* npairs) {
+  const double gm1 = o.variable_h ? (o.p.gamma - 1.0) : 0.4, gam = o.variable_h ? o.p.gamma : 1.4;
+  const double theta = o.p.theta_override ? o.p.theta : 0.5;
+  auto mix = [](uint64_t z) { z += 0x9E3779B97F4A7C15ull; z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; return z ^ (z >> 31); };
+  #pragma omp parallel for schedule(dynamic, 4) if (o.threads > 1)
+  for (int t = 0; t < nt; ++t) {
+    const int i = targets[t];
+    auto fill = [&](Particle& p, int idx, std::vector<int>* list) {       // density + EOS of one particle (F:398-468)
+      p = o.bodies[idx];
+      double r, om; sample_density(o, idx, r, om, list);
+      p.density = r; p.omega = om;
+      p.pressure = gm1 * p.internal_energy * p.density;
+      p.sound_speed = std::sqrt(gam * p.pressure / p.density);
+    };
+    Particle bi; std::vector<int> found;
+    fill(bi, i, &found);
+    { std::vector<int> v = found; std::sort(v.begin(), v.end()); uint64_t hs = 0; for (int j : v) hs += mix((uint64_t)j); ncount[t] = (int32_t)v.size(); nhash[t] = hs; }
+    for (int d = 0; d < 3; ++d) bi.acceleration[d] = 0.0;
+    bi.internal_energy_rate = 0.0; bi.alpha_rate = 0.0;
+    // gravity (F:264-290), then sinks (F:567-576), then the pair terms: the reference's order of the three blocks
+    int64_t op = 0, ac = 0;
+    particle_gravforce_one(o, 0, bi, theta, op, ac);
+    for (const Sink& s : o.sinks) {
+      double v[3]; for (int d = 0; d < 3; ++d) v[d] = bi.position[d] - s.position[d];
+      const double dr = std::sqrt(((v[0] * v[0]) + v[1] * v[1]) + v[2] * v[2]), dd = dr * dr * dr;
+      for (int d = 0; d < 3; ++d) { const double w = G_REF * v[d] / dd; bi.acceleration[d] = bi.acceleration[d] - (s.mass * w); }
+    }
+    int64_t pairs = 0;
+    for (int j : found) {                                                  // j < i: i is the `body`
+      if (o.bodies[j].number >= bi.number) continue;                       // F:354
+      Particle nb; fill(nb, j, nullptr);
+      double acc[3], vdg, ub, un;
+      pair_terms(o, bi, nb, o.variable_h ? o.h_tree[j] : o.p.h_fixed, acc, vdg, ub, un);
+      for (int d = 0; d < 3; ++d) bi.acceleration[d] = bi.acceleration[d] - nb.mass * acc[d];
+      bi.internal_energy_rate = bi.internal_energy_rate + ub;
+      bi.alpha_rate = bi.alpha_rate + nb.mass * vdg;
+      ++pairs;
+    }
+    const Node& leaf = o.nodes[o.leaf_of[i]];
+    if (leaf.n_particles == 1) {                                           // j > i: j is the `body` whose walk reaches leaf i
+      std::vector<int> path; int ni = 0;
+      for (;;) {
+        path.push_back(ni);
+        if (ni == o.leaf_of[i]) break;
+        const Node& nd = o.nodes[ni]; int ci = 0;
+        for (int d = 0; d < 3; ++d) { if (o.x_tree[3 * (size_t)i + d] > nd.center[d]) ci |= (1 << d); }   // F:208-214
+        ni = nd.child[ci];
+      }
+      const double lim = search_reach(o, leaf) + leaf.size / 2.0;
+      double lo[3], hi[3]; for (int d = 0; d < 3; ++d) { lo[d] = leaf.center[d] - lim; hi[d] = leaf.center[d] + lim; }
+      std::vector<int> in; sample_box_query(o, path, 0, lo, hi, in);
+      for (int j : in) {
+        if (o.bodies[j].number <= bi.number) continue;
+        Particle bj; fill(bj, j, nullptr);
+        double acc[3], vdg, ub, un;
+        pair_terms(o, bj, bi, o.variable_h ? o.h_tree[i] : o.p.h_fixed, acc, vdg, ub, un);
+        for (int d = 0; d < 3; ++d) bi.acceleration[d] = bi.acceleration[d] + bj.mass * acc[d];      // F:384
+        bi.internal_energy_rate = bi.internal_energy_rate + un;                                   // F:388
+        bi.alpha_rate = bi.alpha_rate + bj.mass * vdg;                                            // F:391
+        ++pairs;
+      }
+    }
+    const double h = o.variable_h ? bi.s_length : o.p.h_fixed;
+    bi.alpha_rate = std::max(bi.alpha_rate / bi.density, 0.0) + LIT_015 * ((0.1 - bi.alpha) * bi.sound_speed / h);   // F:316-318
+    rho[t] = bi.density; omega[t] = bi.omega; P[t] = bi.pressure; cs[t] = bi.sound_speed;
+    ax[t] = bi.acceleration[0]; ay[t] = bi.acceleration[1]; az[t] = bi.acceleration[2];
+    udot[t] = bi.internal_energy_rate; adot[t] = bi.alpha_rate; npairs[t] = pairs;
+  }
 }
 
 // ---- integrator: F:742-776 -------------------------------------------------------------------------
@@ -912,6 +1023,15 @@ int64_t orc_download_neighbours(orc_ctx* c, int32_t* count, uint64_t* hash, int6
   }
   if (offsets) offsets[n] = tot;
   return tot;
+}
+/* sampled evaluation (see sample_eval): builds the tree over the whole set, then evaluates the `nt` targets
+ * (0-based numbers) on their own; outputs have nt entries */
+void orc_sample_eval(orc_ctx* c, int32_t nt, const int32_t* targets, double* rho, double* omega, double* P, double* cs,
+                     double* ax, double* ay, double* az, double* udot, double* adot, int32_t* ncount, uint64_t* nhash, int64_t* npairs) {
+  Oracle& o = c->o;
+  for (size_t i = 0; i < o.bodies.size(); ++i) o.bodies[i].number = (int)i + 1;   // F:886-888
+  create_tree(o);
+  sample_eval(o, nt, targets, rho, omega, P, cs, ax, ay, az, udot, adot, ncount, nhash, npairs);
 }
 void orc_counters(orc_ctx* c, sph_counts* out) { *out = c->o.cnt; }
 void orc_conserved(orc_ctx* c, double* out12) { conserved(c->o, out12); }

@@ -17,9 +17,7 @@
 #include "sph_hostcomm.h"
 #include "sph_tree.cuh"
 #include "sph_walk.cuh"
-#ifndef GRAV_CHUNK_WIDTH
-#define GRAV_CHUNK_WIDTH 32        // gravity walk groups: fixed runs of this many Morton-consecutive particles (0: the SPH walk groups)
-#endif
+#define GRAV_CHUNK_WIDTH 32        // gravity walk groups: fixed runs of this many Morton-consecutive particles
 #include "sph_gravity.cuh"
 #include "sph_integrate.cuh"
 #include "sph_conserved.cuh"
@@ -97,11 +95,6 @@ struct sph_ctx {
   int g0 = 0, g1 = 0, p0 = 0, p1 = 0;
   double* cons_partial = nullptr; double* cons_out = nullptr;   // sph_conserved: block partials, result slots
   double* sink_spin = nullptr; int sink_extras = 0;               // SPH_FLAG_SINK_MERGE_SPIN: spin[3][SPH_MAX_SINKS]; null pointer into the kernels when off
-#ifdef GW_FAR_REUSE
-  double *far_x = nullptr, *far_y = nullptr, *far_z = nullptr, *far_hcut = nullptr, *far_dec = nullptr; int* far_flag = nullptr;   // sph_gravity.cuh: GW_FAR_REUSE
-  int2* far_near = nullptr; int* far_near_cnt = nullptr; size_t far_near_runs = 0;
-  bool far_valid = false; int far_nsink = 0; double far_sinks[4 * SPH_MAX_SINKS] = {}; int64_t far_reused = 0, far_full = 0;
-#endif
   double* img_table = nullptr;                                    // sph_column_density: line-of-sight integral of the M4 shape
 };
 
@@ -159,10 +152,6 @@ int ensure_capacity(sph_ctx* c, int64_t n) {
   DA(c->cnt, cap + 1); DA(c->off, cap + 1);
   DA(c->wnodes, 2 * cap); DA(c->wcount, 2 * cap); DA(c->wstart, 2 * cap); DA(c->widx, 2 * cap);
   DA(c->keep, cap); DA(c->pos, cap); DA(c->stage_d, cap); DA(c->stage_d2, cap);
-#ifdef GW_FAR_REUSE
-  DA(c->far_x, cap); DA(c->far_y, cap); DA(c->far_z, cap); DA(c->far_hcut, cap); c->far_valid = false;
-  if (!c->far_flag) { DA(c->far_flag, 1); DA(c->far_dec, 1); CK(cudaMemset(c->far_flag, 0, sizeof(int))); }
-#endif
   // CUB temp: radix sort pairs (u64,int), exclusive scan, select
   size_t b1 = 0, b2 = 0, b3 = 0, b4 = 0, b5 = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, b5, c->wcount, c->wstart, (int)(2 * cap), c->stream);
@@ -461,9 +450,6 @@ int build_tree(sph_ctx* c) {
 int build_tree_impl(sph_ctx* c, bool* retry_two_word) {
   const int n = (int)c->n;
   c->nl_valid = false; c->grav_groups_valid = false;
-#ifdef GW_FAR_REUSE
-  c->far_valid = false;                      // new positions / particle set: the stored far sums are void
-#endif
   const int T = 256;
   *retry_two_word = false;
   if (c->two_word && !c->key_lo[0]) { for (int b = 0; b < 2; ++b) DA(c->key_lo[b], c->cap); }
@@ -677,51 +663,10 @@ int run_gravity(sph_ctx* c, int do_grav, int do_sinks) {
   const int GWW = grav_warps(c);
   stage_begin(c, ST_GRAVITY);
   StateArrays s = state_of(c, c->cur);
-#if GRAV_CHUNK_WIDTH > 0
   // upper bound of the number of runs in this rank's slice; unused tail entries stay empty (first = 0, count = 0)
   const int seg0 = c->g0 / GRAV_SEG, nseg = cdiv(c->g1 - c->g0, GRAV_SEG);
   const int ng = cdiv(c->p1 - c->p0, std::min(GRAV_CHUNK_WIDTH, GRAV_MINFILL)) + 2 * nseg;
-#else
-  const int ng = c->g1 - c->g0;
-#endif
   const int ns = do_sinks ? c->n_sink : 0;
-#ifdef GW_FAR_REUSE
-  // Pass 1 (near terms + the far sums stored by the last full walk) when nothing the far sums depend on has changed:
-  // same tree (the stored sums are voided by every rebuild), same sinks, every h still below its cutoff.
-  if (GW_NEAR_CAP > 0 && (size_t)ng > c->far_near_runs) {      // per-run near lists of pass 0 (8 B x GW_NEAR_CAP per run)
-    c->far_near_runs = (size_t)ng * 5 / 4 + 64;
-    DA(c->far_near, c->far_near_runs * (size_t)GW_NEAR_CAP); DA(c->far_near_cnt, c->far_near_runs);
-    c->far_valid = false;
-  }
-  GravFar FR{0, c->far_x, c->far_y, c->far_z, c->far_hcut, c->far_near, c->far_near_cnt, GW_NEAR_CAP};
-  {
-    double dec = 0.0;
-    const int M = SPH_MAX_SINKS;
-    if (c->far_valid && do_grav && do_sinks && !c->exact_counters && !c->dp.soft_hi && c->grav_groups_valid && c->n_sink == c->far_nsink) {
-      double now[4 * SPH_MAX_SINKS]; int flag = 1;
-      CK(cudaMemcpyAsync(now, c->sink_buf, sizeof(double) * 3 * M, cudaMemcpyDeviceToHost, c->stream));              // x y z
-      CK(cudaMemcpyAsync(now + 3 * M, c->sink_buf + 6 * M, sizeof(double) * M, cudaMemcpyDeviceToHost, c->stream));   // m
-      CK(cudaMemcpyAsync(&flag, c->far_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-      CK(cudaStreamSynchronize(c->stream));
-      if (flag == 0 && std::memcmp(now, c->far_sinks, sizeof(now)) == 0) dec = 1.0;
-    }
-    if (c->n_ranks > 1) {      // every rank takes the same path: the sink all-reduce below is collective
-      CK(cudaMemcpyAsync(c->far_dec, &dec, sizeof(double), cudaMemcpyHostToDevice, c->stream));
-      { int r_ = allreduce(c, c->far_dec, 1, NC_FLOAT64, NC_MIN); if (r_) return r_; }
-      CK(cudaMemcpyAsync(&dec, c->far_dec, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-      CK(cudaStreamSynchronize(c->stream));
-    }
-    FR.pass = dec > 0.5 ? 1 : 0;
-    if (FR.pass) ++c->far_reused; else ++c->far_full;
-  }
-  const bool far_pass = FR.pass != 0;
-  const int ns_k = far_pass ? 0 : ns;
-#define GW_FAR_ARG , FR
-#else
-  const bool far_pass = false;
-  const int ns_k = ns;
-#define GW_FAR_ARG
-#endif
   if ((size_t)(ng + 8) * std::max(ns, 1) * 3 > c->sink_partial_cap) {
     c->sink_partial_cap = (size_t)(ng + 8) * std::max(ns, 1) * 3 * 2;
     DA(c->sink_partial, c->sink_partial_cap);
@@ -729,7 +674,6 @@ int run_gravity(sph_ctx* c, int do_grav, int do_sinks) {
   if (ng > 0 && c->g1 > c->g0) {
     const int grid = std::max(1, std::min(cdiv(ng, GWW), c->n_sm));
     if (!c->grav_spill) DA(c->grav_spill, (size_t)c->n_sm * GW_WARPS * GW_SPILL);
-#if GRAV_CHUNK_WIDTH > 0
     if (!c->grav_groups_valid) {
       if ((size_t)ng > c->ggroups_cap) { c->ggroups_cap = (size_t)ng * 5 / 4 + 64; DA(c->ggroups, c->ggroups_cap); DA(c->gbvh, c->ggroups_cap); }
       if ((size_t)nseg + 1 > c->seg_cap) { c->seg_cap = (size_t)nseg * 5 / 4 + 64; DA(c->seg_cnt, c->seg_cap); DA(c->seg_off, c->seg_cap); }
@@ -743,22 +687,7 @@ int run_gravity(sph_ctx* c, int do_grav, int do_sinks) {
     }
     LAUNCH(k_set_int, 1, 1, 0, c->work, 0);
     LAUNCH(k_gravity, grid, GWW * 32, gravity_smem(c, GWW), 0, ng, c->ggroups, c->gbvh, c->dp, c->wnodes, s.x, s.y, s.z, s.h, s.m, c->d_gt,
-           c->ax, c->ay, c->az, do_grav, ns_k, c->S, c->sink_partial, c->ctr, c->work, c->grav_spill, &c->sc->err GW_FAR_ARG);
-#else
-    LAUNCH(k_set_int, 1, 1, 0, c->work, c->g0);
-    LAUNCH(k_gravity, grid, GWW * 32, gravity_smem(c, GWW), c->g0, c->g1, c->groups, c->bvh, c->dp, c->wnodes, s.x, s.y, s.z, s.h, s.m, c->d_gt,
-           c->ax, c->ay, c->az, do_grav, ns_k, c->S, c->sink_partial, c->ctr, c->work, c->grav_spill, &c->sc->err GW_FAR_ARG);
-#endif
-#ifdef GW_FAR_REUSE
-    if (!far_pass && do_grav && do_sinks && !c->dp.soft_hi) {      // a full walk just stored its far sums: remember the sinks they hold
-      const int M = SPH_MAX_SINKS;
-      CK(cudaMemcpyAsync(c->far_sinks, c->sink_buf, sizeof(double) * 3 * M, cudaMemcpyDeviceToHost, c->stream));
-      CK(cudaMemcpyAsync(c->far_sinks + 3 * M, c->sink_buf + 6 * M, sizeof(double) * M, cudaMemcpyDeviceToHost, c->stream));
-      CK(cudaMemsetAsync(c->far_flag, 0, sizeof(int), c->stream));
-      CK(cudaStreamSynchronize(c->stream));
-      c->far_nsink = c->n_sink; c->far_valid = true;
-    } else if (!far_pass) c->far_valid = false;
-#endif
+           c->ax, c->ay, c->az, do_grav, ns, c->S, c->sink_partial, c->ctr, c->work, c->grav_spill, &c->sc->err);
   }
 #ifdef GW_DEBUG
   { unsigned long long d[16]; cudaStreamSynchronize(c->stream); cudaMemcpyFromSymbol(d, gw_dbg, sizeof(d)); unsigned long long z[16] = {}; cudaMemcpyToSymbol(gw_dbg, z, sizeof(z));
@@ -766,7 +695,6 @@ int run_gravity(sph_ctx* c, int do_grav, int do_sinks) {
     unsigned long long hh[33]; cudaMemcpyFromSymbol(hh, gw_hist, sizeof(hh)); unsigned long long zz[33] = {}; cudaMemcpyToSymbol(gw_hist, zz, sizeof(zz));
     fprintf(stderr, "GWHIST"); for (int i = 0; i < 33; ++i) fprintf(stderr, " %llu", hh[i]); fprintf(stderr, "\n"); }
 #endif
-  if (far_pass) { stage_end(c); return SPH_OK; }      // the sinks keep the accelerations of the walk that stored the far sums
   // sink side of the gas terms: per-segment folds -> exchange of the rows -> one fixed fold over all segments (rank-count independent)
   {
     const int nst = cdiv(c->n_groups, GRAV_SEG), nsk = std::max(c->n_sink, 1);
@@ -877,9 +805,6 @@ int step(sph_ctx* c) {
   stage_end(c);
   if (c->dp.variable_h) {
     if ((r = run_hiter(c))) return r;                                         // V:1152
-#ifdef GW_FAR_REUSE
-    if (c->far_valid && c->p1 > c->p0) LAUNCH(k_check_hcut, cdiv(c->p1 - c->p0, T), T, 0, c->p0, c->p1, state_of(c, c->cur).h, c->far_hcut, c->far_flag);
-#endif
     stage_begin(c, ST_CULL);
     LAUNCH(k_create_scan, cdiv(n, T), T, 0, n, c->dp, state_of(c, c->cur), c->sc);          // V:1155
     LAUNCH(k_create_apply, 1, 32, 0, state_of(c, c->cur), c->S, c->sc, c->sink_spin);
@@ -1058,9 +983,6 @@ int sph_create(const sph_params* p, int32_t device, sph_ctx** out) {
 
 int sph_destroy(sph_ctx* c) {
   if (!c) return SPH_OK;
-#ifdef GW_FAR_REUSE
-  if (getenv("SPH_B200_FAR_STATS")) fprintf(stderr, "GW_FAR_REUSE: %lld near-only gravity passes, %lld full walks\n", (long long)c->far_reused, (long long)c->far_full);
-#endif
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   p2p_close(c);
@@ -1077,9 +999,6 @@ int sph_destroy(sph_ctx* c) {
   F(c->node_count); F(c->gsize); F(c->gfirst); F(c->groups); F(c->level); F(c->lcx); F(c->lcy); F(c->lcz); F(c->reach); F(c->bvh); F(c->nodes); F(c->node_part); F(c->parent); F(c->nchild);
   F(c->nl_pool); F(c->nl_head); F(c->nl_ctl); F(c->ggroups); F(c->gbvh); F(c->seg_cnt); F(c->seg_off); F(c->wnodes); F(c->wcount); F(c->wstart); F(c->widx); F(c->grav_spill);
   F(c->cons_partial); F(c->cons_out); F(c->img_table); F(c->sink_spin);
-#ifdef GW_FAR_REUSE
-  F(c->far_x); F(c->far_y); F(c->far_z); F(c->far_hcut); F(c->far_dec); F(c->far_flag); F(c->far_near); F(c->far_near_cnt);
-#endif
   F(c->arrive); F(c->cnt); F(c->off); F(c->root); F(c->partial); F(c->cub_tmp); F(c->d_wt); F(c->d_dwt); F(c->d_gt);
   F(c->sink_buf); F(c->sink_partial); F(c->sink_seg); F(c->sc); F(c->ctr); F(c->work); F(c->keep); F(c->d_nsel); F(c->pos); F(c->stage_d); F(c->stage_d2);
   if (c->h_sc) cudaFreeHost(c->h_sc);

@@ -32,15 +32,9 @@ struct SinkArrays { double *x, *y, *z, *vx, *vy, *vz, *m, *radius, *ax, *ay, *az
 #ifndef GW_ILP
 #define GW_ILP 2            // interaction-list entries in flight per lane
 #endif
-#ifndef GW_SUBLISTS
-#define GW_SUBLISTS 1       // experiment (scripts/build_variant.sh sub4 "-DGW_SUBLISTS=4"): the interaction list is read through
-                            // GW_SUBLISTS index lists, one per group of 32 / GW_SUBLISTS consecutive lanes, each holding only the
-                            // entries whose mask touches that group, so a sparse entry costs evaluation slots only in the lane
-                            // groups it belongs to.  Every lane still adds its own terms in list order.  1 = one list for the warp.
-#endif
 #define GW_STACK 384        // (node, mask) entries per warp in shared memory
 #ifndef GW_LIST
-#define GW_LIST  64         // interaction-list entries per warp (evaluated when fewer than 32 slots are left); <= 256 with GW_SUBLISTS
+#define GW_LIST  64         // interaction-list entries per warp (evaluated when fewer than 32 slots are left)
 #endif
 #define GW_SPILL 8192       // per-warp overflow entries in global memory (never reached in practice; loud if it is)
 
@@ -70,9 +64,6 @@ struct GravWarpSmem {
   double   mcx[32], mcy[32], mcz[32], msize[32], mlo[32], mhi[32];   // mixed nodes of the current trip: COM, size, d2 band of the cheap FP64 test
   float4   mf[32];                                                   // the same nodes for the FP32 screen: COM relative to the run's origin, size^2 / theta^2
   unsigned mmask[32];
-#if GW_SUBLISTS > 1
-  unsigned char sub[GW_SUBLISTS][GW_LIST];   // per lane group: positions (in lxy / lzg / lmask) of the entries that touch the group
-#endif
 };
 
 // 1/sqrt(x): MUFU seed (~2^-20) + one Halley step (cubic: ~2^-58), x > 0
@@ -99,51 +90,6 @@ __device__ __forceinline__ void grav_term(const double2 a, const double2 b, cons
   if (on) { gx = fma(-f, dx, gx); gy = fma(-f, dy, gy); gz = fma(-f, dz, gz); }
 }
 
-#ifdef GW_FAR_REUSE
-// Experiment (scripts/r2_gravity_variants.sh): evaluation A of a loop body sees the positions of the previous
-// body's evaluation B (F:894 after F:905-912: the second kick moves no particle), so every accepted (node, particle) pair
-// and its distance are the same; only h changed (calc_smoothing, V:1152), and h enters a gravity term only through
-// g(dist / h) for dist < 2h (F:138-141: W = 1 beyond).  Pass 0 (a full walk) therefore adds the terms with
-// dist^2 <= 4 hcut^2 (hcut = GW_HCUT * h = 1.1 h, kept per particle) and all the others apart and stores the far sum together with
-// the sink terms; pass 1 (the next evaluation on the same tree, same sinks, every h <= hcut) walks only what can hold a
-// near term - subtrees whose cell is farther than 2 max(hcut) from the run's box are dropped - re-evaluates the near terms
-// with the new h and adds the stored far sum.  Same terms as the full walk, summed in another order (rounding level).
-#ifndef GW_HCUT
-#define GW_HCUT 1.1
-#endif
-#ifndef GW_NEAR_CAP
-#define GW_NEAR_CAP 1024    // (node, lane mask) pairs kept per run for pass 1; a run that needs more falls back to the near walk; 0: always walk
-#endif
-// near / near_cnt: pass 0 also records, per run, every listed entry that can be near for some particle of the run; pass 1 then
-// evaluates that list instead of walking (the walk has to visit nearly every node of the full walk just to drop it)
-struct GravFar { int pass; double *fx, *fy, *fz, *hcut; int2* near; int* near_cnt; int near_cap; };
-#define GW_FAR_PARAM , GravFar FR
-__device__ __forceinline__ void grav_term_split(const double2 a, const double2 b, const bool on, const double xi, const double yi,
-                                                const double zi, const double inv_h, const double h2x4, const double hc2x4, const int pass,
-                                                const double soft, const double* __restrict__ gt, const int nq, const double dq,
-                                                const double inv_dq, double& gx, double& gy, double& gz, double& qx, double& qy, double& qz) {
-  const double dx = xi - a.x, dy = yi - a.y, dz = zi - b.x;
-  const double d2 = fma(dx, dx, fma(dy, dy, fma(dz, dz, soft)));
-  if (d2 <= hc2x4) {                           // near class: the only terms that can depend on h
-    const double rs = fast_rsqrt(d2);
-    double gm = b.y;
-    if (d2 <= h2x4) gm *= table_lerp1(gt, nq, dq, inv_dq, (d2 * rs) * inv_h);
-    const double f = gm * (rs * rs * rs);
-    if (on) { qx = fma(-f, dx, qx); qy = fma(-f, dy, qy); qz = fma(-f, dz, qz); }
-  } else if (pass == 0) {
-    const double rs = fast_rsqrt(d2);
-    const double f = b.y * (rs * rs * rs);
-    if (on) { gx = fma(-f, dx, gx); gy = fma(-f, dy, gy); gz = fma(-f, dz, gz); }
-  }
-}
-// any h of this rank's slice above its cutoff voids the stored far sums (the near class would miss terms)
-__global__ void k_check_hcut(int p0, int p1, const double* __restrict__ h, const double* __restrict__ hcut, int* flag) {
-  const int i = p0 + blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < p1 && !(h[i] <= hcut[i])) *flag = 1;
-}
-#else
-#define GW_FAR_PARAM
-#endif
 
 // dynamic smem: grav table (nq+1 doubles, padded to even) then one GravWarpSmem per warp
 __global__ void __launch_bounds__(GW_WARPS * 32, 1)
@@ -152,7 +98,7 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
           const double* __restrict__ h, const double* __restrict__ m, const double* __restrict__ g_gt,
           double* __restrict__ ax, double* __restrict__ ay, double* __restrict__ az,
           int do_grav, int n_sink, SinkArrays S, double* __restrict__ sink_partial, WalkCounters* ctr, int* work,
-          int2* __restrict__ spill, int* err_flag GW_FAR_PARAM) {
+          int2* __restrict__ spill, int* err_flag) {
   extern __shared__ __align__(16) double gsm[];
   double* gt = gsm;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -180,55 +126,6 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
 #pragma unroll
     for (int u = 0; u < GW_ILP; ++u) gx[u] = gy[u] = gz[u] = 0.0;
 
-#ifdef GW_FAR_REUSE
-#if GW_SUBLISTS > 1
-#error "GW_FAR_REUSE and GW_SUBLISTS are separate experiments"
-#endif
-    const double hc = live ? (FR.pass == 0 ? GW_HCUT * hi : FR.hcut[i]) : 1.0;
-    const double hc2x4 = 4.0 * hc * hc;
-    double qx[GW_ILP], qy[GW_ILP], qz[GW_ILP];      // near terms
-#pragma unroll
-    for (int u = 0; u < GW_ILP; ++u) qx[u] = qy[u] = qz[u] = 0.0;
-#endif
-#if GW_SUBLISTS > 1
-    int sl[GW_SUBLISTS];                       // entries in each lane group's index list (warp-uniform)
-#pragma unroll
-    for (int q = 0; q < GW_SUBLISTS; ++q) sl[q] = 0;
-    const int myq = lane / (32 / GW_SUBLISTS);
-    auto evaluate_list = [&](int) {
-      int mylen = 0, maxlen = 0;
-#pragma unroll
-      for (int q = 0; q < GW_SUBLISTS; ++q) { if (q == myq) mylen = sl[q]; maxlen = sl[q] > maxlen ? sl[q] : maxlen; sl[q] = 0; }
-      const unsigned char* mysub = W.sub[myq];
-      int k = 0;
-      for (; k + GW_ILP <= maxlen; k += GW_ILP) {
-#pragma unroll
-        for (int u = 0; u < GW_ILP; ++u) {
-          const bool have = k + u < mylen;
-          const int idx = have ? (int)mysub[k + u] : 0;
-          grav_term(W.lxy[idx], W.lzg[idx], have && ((W.lmask[idx] >> lane) & 1u), xi, yi, zi, inv_h, h2x4, soft, gt, P.nq, P.dq, P.inv_dq, gx[u], gy[u], gz[u]);
-        }
-      }
-      for (; k < maxlen; ++k) {
-        const bool have = k < mylen;
-        const int idx = have ? (int)mysub[k] : 0;
-        grav_term(W.lxy[idx], W.lzg[idx], have && ((W.lmask[idx] >> lane) & 1u), xi, yi, zi, inv_h, h2x4, soft, gt, P.nq, P.dq, P.inv_dq, gx[0], gy[0], gz[0]);
-      }
-    };
-#elif defined(GW_FAR_REUSE)
-    auto evaluate_list = [&](int cnt) {
-      int k = 0;
-      for (; k + GW_ILP <= cnt; k += GW_ILP) {
-#pragma unroll
-        for (int u = 0; u < GW_ILP; ++u)
-          grav_term_split(W.lxy[k + u], W.lzg[k + u], (W.lmask[k + u] >> lane) & 1u, xi, yi, zi, inv_h, h2x4, hc2x4, FR.pass, soft, gt,
-                          P.nq, P.dq, P.inv_dq, gx[u], gy[u], gz[u], qx[u], qy[u], qz[u]);
-      }
-      for (; k < cnt; ++k)
-        grav_term_split(W.lxy[k], W.lzg[k], (W.lmask[k] >> lane) & 1u, xi, yi, zi, inv_h, h2x4, hc2x4, FR.pass, soft, gt,
-                        P.nq, P.dq, P.inv_dq, gx[0], gy[0], gz[0], qx[0], qy[0], qz[0]);
-    };
-#else
     auto evaluate_list = [&](int cnt) {
       int k = 0;
 #ifdef GW_DEBUG
@@ -242,7 +139,6 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
       }
       for (; k < cnt; ++k) grav_term(W.lxy[k], W.lzg[k], (W.lmask[k] >> lane) & 1u, xi, yi, zi, inv_h, h2x4, soft, gt, P.nq, P.dq, P.inv_dq, gx[0], gy[0], gz[0]);
     };
-#endif
 
     if (do_grav && tg.y > 0) {               // tg.y == 0: an unused tail entry of the run table
       const BvhBox gb = gbox[chunk];
@@ -257,32 +153,7 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
       const float xif = (float)(xi - g0x), yif = (float)(yi - g0y), zif = (float)(zi - g0z);
       const float softf = (float)soft, softf_min = __double2float_rd(soft_min), softf_max = __double2float_ru(soft_max);
       const float th2f = (float)theta2, inv_th2f = (float)inv_theta2;
-#ifdef GW_FAR_REUSE
-      // distance (float, rounded up) beyond which no particle of the run can have a near term
-      const float rcf = __double2float_ru(2.0 * warp_max(live ? hc : 0.0)) * 1.0001f;
-      int ncnt = 0;                          // pass 0: entries recorded in this run's near list (may exceed the capacity: overflow)
-#endif
       int sn = 1, gsp = 0, ln = 0;
-#ifdef GW_FAR_REUSE
-      if (FR.pass && FR.near_cap > 0) {      // pass 1 from the recorded list: same entries, same masks, same order as the walk would list
-        const int cnt_near = FR.near_cnt[chunk];
-        if (cnt_near <= FR.near_cap) {
-          for (int base = 0; base < cnt_near; base += 32) {
-            const int k = base + lane;
-            if (k < cnt_near) {
-              const int2 en = FR.near[(size_t)chunk * FR.near_cap + k];
-              const double2* p = reinterpret_cast<const double2*>(wn + en.x);
-              const double2 a = __ldg(p), b = __ldg(p + 1);
-              W.lxy[lane] = a; W.lzg[lane] = make_double2(b.x, P.G * b.y); W.lmask[lane] = (unsigned)en.y;
-            }
-            __syncwarp();
-            evaluate_list(cnt_near - base < 32 ? cnt_near - base : 32);
-            __syncwarp();
-          }
-          sn = 0;                            // nothing to walk
-        }
-      }
-#endif
 #ifdef GW_DEBUG
       int dq_len = 0, dq_ring = 0;
       auto dq_flush = [&]() { int mx = dq_len, sm = dq_len; for (int o = 16; o > 0; o >>= 1) { mx = max(mx, __shfl_xor_sync(FULL_MASK, mx, o)); sm += __shfl_xor_sync(FULL_MASK, sm, o); }
@@ -322,9 +193,6 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
         int cls = 0;                           // 1 all accept, 2 all open, 3 mixed
         double ncx = 0.0, ncy = 0.0, ncz = 0.0, nm = 0.0, nsize = 0.0; int nchild = 0, nnch = 0;
         float rxf = 0.f, ryf = 0.f, rzf = 0.f, s2f = 0.f;
-#ifdef GW_FAR_REUSE
-        bool far_entry = false, near_poss = false;
-#endif
         if (valid) {
           const double2* p = reinterpret_cast<const double2*>(wn + e.x);
           const double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
@@ -340,15 +208,6 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
           if (nnch == 0 || s2f < th2f * dmin2 * (1.f - 3e-5f)) cls = 1;
           else if (s2f > th2f * dmax2 * (1.f + 3e-5f)) cls = 2;
           else cls = 3;
-#ifdef GW_FAR_REUSE
-          {                  // the node's particles lie inside its cell, i.e. within sqrt(3) size of its centre of mass
-            const float dminf = sqrtf(fmaf(nx, nx, fmaf(ny, ny, nz * nz))) * 0.9999f;
-            if (FR.pass) {
-              if (dminf - 1.7321f * szf > rcf) cls = 0;          // nothing at or below this node is near any particle of the run
-              else if (dminf > rcf) far_entry = true;            // its own term is far for every particle; its children may not be
-            } else near_poss = !(dminf > rcf);                   // pass 0: worth recording for pass 1
-          }
-#endif
         }
         const unsigned emask = (unsigned)e.y;
         const unsigned balM = __ballot_sync(FULL_MASK, cls == 3);
@@ -390,42 +249,12 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
         }
         // ---- lane = node again: accepted (node, lane set) pairs join the interaction list, opened ones push their child block
         n_acc += __popc(acc_mask); n_open += __popc(open_mask);
-#ifdef GW_FAR_REUSE
-        const bool ins = acc_mask != 0u && nm > 0.0 && !far_entry;
-#else
         const bool ins = acc_mask != 0u && nm > 0.0;                                // F:279: massless nodes add nothing
-#endif
         const unsigned balL = __ballot_sync(FULL_MASK, ins);
-#if GW_SUBLISTS > 1
-        const int lpos = ln + __popc(balL & lt_mask);
-        if (ins) {
-          W.lxy[lpos] = make_double2(ncx, ncy); W.lzg[lpos] = make_double2(ncz, P.G * nm); W.lmask[lpos] = acc_mask;
-        }
-#pragma unroll
-        for (int q = 0; q < GW_SUBLISTS; ++q) {
-          const unsigned qm = ((1u << (32 / GW_SUBLISTS)) - 1u) << (q * (32 / GW_SUBLISTS));
-          const bool hit = ins && (acc_mask & qm) != 0u;
-          const unsigned bq = __ballot_sync(FULL_MASK, hit);
-          if (hit) W.sub[q][sl[q] + __popc(bq & lt_mask)] = (unsigned char)lpos;
-          sl[q] += __popc(bq);
-        }
-#else
         if (ins) {
           const int pos = ln + __popc(balL & lt_mask);
           W.lxy[pos] = make_double2(ncx, ncy); W.lzg[pos] = make_double2(ncz, P.G * nm); W.lmask[pos] = acc_mask;
         }
-#endif
-#ifdef GW_FAR_REUSE
-        if (FR.pass == 0 && FR.near_cap > 0) {
-          const bool rec = ins && near_poss;
-          const unsigned balN = __ballot_sync(FULL_MASK, rec);
-          if (rec) {
-            const int q = ncnt + __popc(balN & lt_mask);
-            if (q < FR.near_cap) FR.near[(size_t)chunk * FR.near_cap + q] = make_int2(e.x, (int)acc_mask);
-          }
-          ncnt += __popc(balN);
-        }
-#endif
 #ifdef GW_DEBUG
         __syncwarp();
         for (int q = 0; q < __popc(balL); ++q) dq_account(W.lmask[ln + q]);
@@ -443,9 +272,6 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
       }
       if (ln > 0) evaluate_list(ln);
       __syncwarp();
-#ifdef GW_FAR_REUSE
-      if (FR.pass == 0 && FR.near_cap > 0 && lane == 0) FR.near_cnt[chunk] = ncnt;
-#endif
 #ifdef GW_DEBUG
       if (dq_ring) dq_flush();
 #endif
@@ -471,15 +297,6 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
         o[0] = px; o[1] = py; o[2] = pz;
       }
     }
-#ifdef GW_FAR_REUSE
-#pragma unroll
-    for (int u = 1; u < GW_ILP; ++u) { qx[0] += qx[u]; qy[0] += qy[u]; qz[0] += qz[u]; }
-    if (live) {
-      if (FR.pass == 0) { FR.fx[i] = gx[0]; FR.fy[i] = gy[0]; FR.fz[i] = gz[0]; FR.hcut[i] = hc; }   // far terms + sinks (the loop above)
-      else { gx[0] = FR.fx[i]; gy[0] = FR.fy[i]; gz[0] = FR.fz[i]; }                                 // pass 1 is launched with n_sink = 0
-      gx[0] += qx[0]; gy[0] += qy[0]; gz[0] += qz[0];
-    }
-#endif
     if (live) { ax[i] = gx[0]; ay[i] = gy[0]; az[i] = gz[0]; }
   }
   n_open = (unsigned long long)warp_sum_ll((long long)n_open); n_acc = (unsigned long long)warp_sum_ll((long long)n_acc);

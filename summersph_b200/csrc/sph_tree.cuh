@@ -179,21 +179,6 @@ __global__ void k_group_mark(int n_nodes, const GNode* __restrict__ nodes, const
   if (node_part[v] >= 0 || cnt <= SPH_CHUNK) return;
   const int end = nodes[v].next;
   int c = v + 1, run_first = -1, run_n = 0;
-#ifdef GROUP_SPLIT_BUCKETS
-  // experiment (scripts/r2_gravity_variants.sh): a maximal run of consecutive sibling buckets is cut into full
-  // SPH_CHUNK-particle groups (+ one remainder) instead of closing a group whenever the next bucket does not fit;
-  // every group still lies inside this node's cell, and the walks accept any contiguous partition.
-  auto emit = [&](int f, int n) { for (int o = 0; o < n; o += SPH_CHUNK) gsize[f + o] = (n - o < SPH_CHUNK) ? n - o : SPH_CHUNK; };
-  while (c < end) {
-    const int cc = node_count[c];
-    const int pc = node_part[c];
-    const int first = pc >= 0 ? pc : -1 - pc;
-    if (cc <= SPH_CHUNK) { if (run_n == 0) run_first = first; run_n += cc; }
-    else if (run_n > 0) { emit(run_first, run_n); run_n = 0; }
-    c = nodes[c].next;
-  }
-  if (run_n > 0) emit(run_first, run_n);
-#else
   while (c < end) {
     const int cc = node_count[c];
     const int pc = node_part[c];
@@ -206,7 +191,6 @@ __global__ void k_group_mark(int n_nodes, const GNode* __restrict__ nodes, const
     c = nodes[c].next;
   }
   if (run_n > 0) gsize[run_first] = run_n;
-#endif
 }
 
 // compacted (first, size) per group -> packed int2
