@@ -19,7 +19,7 @@ module sph_b200_c
     integer(c_int32_t) :: mode, max_depth, nq, n_ranks
     real(c_double)     :: h_fixed, bounding_size, theta, gamma, eta, convergence_criteria
     real(c_double)     :: max_length, timestep_scale, end_time, sink_radius
-    integer(c_int32_t) :: theta_override, reserved
+    integer(c_int32_t) :: theta_override, decomposition
   end type sph_params
 
   interface

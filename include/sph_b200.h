@@ -76,7 +76,8 @@ typedef struct sph_params {
   double  end_time;             /* F:873 (1000) | params%end_time (host loop only)      */
   double  sink_radius;          /* F:694 (3.5) | V:830 (5.0): radius given to IC sinks  */
   int32_t theta_override;       /* 0: use literal 0.5 like the reference; 1: use .theta */
-  int32_t reserved;
+  int32_t decomposition;        /* multi-rank form: 0 = replicated state, Morton-sliced walks (bit-identical to one rank);
+                                   1 = Morton-ordered domains with halo exchange and a top-tree all-gather */
 } sph_params;
 
 /* Interaction counters of the most recent evaluation (for flop rooflines). */
@@ -130,6 +131,25 @@ int sph_upload(sph_ctx* ctx, int64_t n_gas,
                const double* sx, const double* sy, const double* sz,
                const double* svx, const double* svy, const double* svz,
                const double* sm, const double* srad);
+
+/* Domain decomposition only (params.decomposition = 1 after sph_comm_init*): this rank hands over rows
+ * [id_first, id_first + n_local) of the n_global gas rows (any partition of the file between the ranks; the first tree
+ * build sends every particle to the rank that owns its Morton range).  Sinks are replicated: pass the same on every rank. */
+int sph_upload_local(sph_ctx* ctx, int64_t n_global, int64_t id_first, int64_t n_local,
+                     const double* x, const double* y, const double* z,
+                     const double* vx, const double* vy, const double* vz,
+                     const double* u, const double* m, const double* alpha, const double* h,
+                     int32_t n_sink,
+                     const double* sx, const double* sy, const double* sz,
+                     const double* svx, const double* svy, const double* svz,
+                     const double* sm, const double* srad);
+/* The rows this rank owns now (domain decomposition; elsewhere: all rows): *n_local of them, `number` = their 0-based
+ * row numbers of the upload (persistent across removals), fields as in sph_download; any pointer may be NULL.  Capacity of
+ * each array >= the value sph_local_size returns. */
+int sph_local_size(sph_ctx* ctx, int64_t* n_local);
+int sph_download_local(sph_ctx* ctx, int32_t* number,
+                       double* x, double* y, double* z, double* vx, double* vy, double* vz,
+                       double* u, double* m, double* alpha, double* h);
 
 /* One evaluation (tree + density + EOS + find_forces) on the current state, no integration:
  * the parity hook. `mask` selects phases (SPH_EVAL_*); rates are zeroed first (F:824). */

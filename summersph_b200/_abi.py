@@ -57,7 +57,7 @@ class SphParams(C.Structure):
         ("h_fixed", C.c_double), ("bounding_size", C.c_double), ("theta", C.c_double), ("gamma", C.c_double),
         ("eta", C.c_double), ("convergence_criteria", C.c_double), ("max_length", C.c_double),
         ("timestep_scale", C.c_double), ("end_time", C.c_double), ("sink_radius", C.c_double),
-        ("theta_override", C.c_int32), ("reserved", C.c_int32),
+        ("theta_override", C.c_int32), ("decomposition", C.c_int32),
     ]
 
     @property

@@ -9,6 +9,7 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <functional>
 #include <dlfcn.h>
 #include <cub/cub.cuh>
 
@@ -22,6 +23,7 @@
 #include "sph_integrate.cuh"
 #include "sph_conserved.cuh"
 #include "sph_image.cuh"
+#include "sph_domain.cuh"
 
 namespace {
 
@@ -95,7 +97,18 @@ struct sph_ctx {
   int g0 = 0, g1 = 0, p0 = 0, p1 = 0;
   double* cons_partial = nullptr; double* cons_out = nullptr;   // sph_conserved: block partials, result slots
   double* sink_spin = nullptr; int sink_extras = 0;               // SPH_FLAG_SINK_MERGE_SPIN: spin[3][SPH_MAX_SINKS]; null pointer into the kernels when off
-  double* img_table = nullptr;                                    // sph_column_density: line-of-sight integral of the M4 shape
+  double* img_table = nullptr;
+  // ---- Morton-domain decomposition (sph_domain.cuh / sph_domain_host.inl); in this mode n = own particles, cap = own + halo capacity
+  bool dd = false; int64_t n_global = 0; int n_halo = 0, ng_own = 0, ng_halo = 0;
+  uint64_t* key_alloc[2] = {}; int* perm_alloc[2] = {};          // the allocations behind key[] / perm[] (which swap)
+  uint64_t *dd_samples = nullptr, *dd_split = nullptr; long long* dd_counts = nullptr; int* dd_sendoff = nullptr;
+  DDCell* dd_cells = nullptr; DDContrib* dd_contrib = nullptr; BvhBox* dd_dom = nullptr; int* dd_let_ctl = nullptr; double* dd_create8 = nullptr; unsigned long long* dd_cand = nullptr;
+  DDLetEntry* dd_let_f[2] = {}; int dd_let_fcap = 0, dd_let_begin = 0, dd_let_end = 0, dd_let_used = 0, dd_top_n = 0;
+  unsigned char* dd_halo_flag = nullptr; int *dd_halo_list = nullptr, *dd_halo_size = nullptr, *dd_halo_poff = nullptr; size_t dd_halo_cap = 0;
+  unsigned long long* dd_acc_key = nullptr; DDAccRec* dd_acc_rec = nullptr;                      // exported: this rank's accretion records
+  unsigned long long* dd_accg_key[2] = {}; int* dd_accg_idx[2] = {}; DDAccRec* dd_accg_rec = nullptr; size_t dd_accg_cap = 0;   // all ranks' records
+  std::vector<DDInfo> dd_info; DDPeerGroups dd_pg; std::vector<DDContrib> dd_top_recs;
+  int *dd_gid = nullptr, *dd_gpos = nullptr, *dd_gcnt = nullptr, *dd_goff = nullptr; double* dd_gstage = nullptr; size_t dd_g_cap = 0;   // gathers for the host-facing downloads                                    // sph_column_density: line-of-sight integral of the M4 shape
 };
 
 namespace {
@@ -144,13 +157,21 @@ int ensure_capacity(sph_ctx* c, int64_t n) {
   c->cap = 0; c->tree_valid = false; c->pos_moved = true; c->p2p_stale = true;      // a failed grow must not leave the old capacity standing over freed arrays
   for (int b = 0; b < 2; ++b) if (c->key_lo[b]) { cudaFree(c->key_lo[b]); c->key_lo[b] = nullptr; }
   for (int b = 0; b < 2; ++b) { for (int f = 0; f < 10; ++f) DA(c->st[b][f], cap); DA(c->id[b], cap); DA(c->key[b], cap); DA(c->perm[b], cap); DA(c->acc_key[b], cap); DA(c->acc_val[b], cap); }
+  for (int b = 0; b < 2; ++b) { c->key_alloc[b] = c->key[b]; c->perm_alloc[b] = c->perm[b]; }
   DA(c->rho, cap); DA(c->omega, cap); DA(c->prs, cap); DA(c->cs, cap); DA(c->por2, cap);
   DA(c->ax, cap); DA(c->ay, cap); DA(c->az, cap); DA(c->udot, cap); DA(c->adot, cap);
   DA(c->level, cap); DA(c->lcx, cap); DA(c->lcy, cap); DA(c->lcz, cap); DA(c->reach, cap);
   DA(c->node_count, 2 * cap); DA(c->gsize, cap); DA(c->gfirst, cap); DA(c->groups, cap);
   DA(c->nodes, 2 * cap); DA(c->node_part, 2 * cap); DA(c->parent, 2 * cap); DA(c->nchild, 2 * cap); DA(c->arrive, 2 * cap);
   DA(c->cnt, cap + 1); DA(c->off, cap + 1);
-  DA(c->wnodes, 2 * cap); DA(c->wcount, 2 * cap); DA(c->wstart, 2 * cap); DA(c->widx, 2 * cap);
+  if (c->dd) {      // walk layout: [top tree | local tree | locally essential nodes of the peers]; accretion records; LET frontier; fixed BVH capacity (exported)
+    c->dd_let_begin = DD_TOP_CAP + (int)(2 * cap); c->dd_let_end = c->dd_let_begin + (int)cap; c->dd_let_fcap = (int)std::max<int64_t>(cap / 4, 65536);
+    DA(c->wnodes, (size_t)c->dd_let_end);
+    DA(c->dd_let_f[0], c->dd_let_fcap); DA(c->dd_let_f[1], c->dd_let_fcap);
+    DA(c->dd_acc_key, cap); DA(c->dd_acc_rec, cap);
+    c->bvh_cap = (size_t)(cap + cap / 7 + 64) * 5 / 4; DA(c->bvh, c->bvh_cap);
+  } else DA(c->wnodes, 2 * cap);
+  DA(c->wcount, 2 * cap); DA(c->wstart, 2 * cap); DA(c->widx, 2 * cap);
   DA(c->keep, cap); DA(c->pos, cap); DA(c->stage_d, cap); DA(c->stage_d2, cap);
   // CUB temp: radix sort pairs (u64,int), exclusive scan, select
   size_t b1 = 0, b2 = 0, b3 = 0, b4 = 0, b5 = 0;
@@ -260,6 +281,8 @@ std::vector<double*> exchanged_arrays(sph_ctx* c) {
   return {c->rho, c->cs, c->por2, c->ax, c->ay, c->az, c->udot, c->adot, c->omega, c->prs, c->st[0][9], c->st[1][9], c->sink_seg};
 }
 
+std::vector<void*> dd_exported(sph_ctx* c);      // sph_domain_host.inl
+
 void p2p_close(sph_ctx* c) {
   for (void* p : c->ipc_opened) cudaIpcCloseMemHandle(p);
   c->ipc_opened.clear(); c->peer.clear(); c->p2p_ok = false;
@@ -273,7 +296,8 @@ int p2p_setup(sph_ctx* c) {
   if (c->n_ranks <= 1 || !have_comm(c) || (!c->hc && !c->nccl.AllGather) || getenv("SPH_B200_NO_P2P")) return SPH_OK;
   if (!c->xstream) { CK(cudaStreamCreateWithFlags(&c->xstream, cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&c->x_ready, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c->x_done, cudaEventDisableTiming)); }
   if (!c->d_flag) DA(c->d_flag, 4);
-  const std::vector<double*> arr = exchanged_arrays(c);
+  std::vector<void*> arr;
+  if (c->dd) arr = dd_exported(c); else for (double* q : exchanged_arrays(c)) arr.push_back(q);
   const int na = (int)arr.size(), R = c->n_ranks;
   char host[256] = {0}; gethostname(host, 255);
   unsigned long long hh = 1469598103934665603ull; for (char* q = host; *q; ++q) hh = (hh ^ (unsigned char)*q) * 1099511628211ull;
@@ -294,7 +318,7 @@ int p2p_setup(sph_ctx* c) {
   for (int r = 0; r < R && ok; ++r) {
     for (int a = 0; a < na && ok; ++a) {
       const PeerRec& pr = all[(size_t)r * na + a];
-      if (r == c->rank) { c->peer[a][r] = arr[a]; continue; }
+      if (r == c->rank) { c->peer[a][r] = (double*)arr[a]; continue; }
       if (pr.hosthash != hh) { ok = 0; break; }
       if (pr.pid == (int)getpid()) {            // peer context lives in this process (threads): plain peer access
         if (pr.device != c->device) {
@@ -389,6 +413,7 @@ int allreduce(sph_ctx* c, void* buf, size_t count, int dtype, int op) {
 }
 
 __global__ void k_set_int(int* p, int v) { *p = v; }
+__global__ void k_iota_from(int n, int first, int* a) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) a[i] = first + i; }
 
 // first walk group of every rank's target slice (n_ranks + 1 entries): contiguous, cut only at multiples of GRAV_SEG
 // groups (the gravity runs restart there, sph_gravity.cuh), so runs and segments are the same for any rank count
@@ -415,6 +440,8 @@ int compute_slices(sph_ctx* c) {
 // ---------------------------------------------------------------------------------------------------
 int build_tree_impl(sph_ctx* c, bool* retry_two_word);
 
+#include "sph_domain_host.inl"
+
 // Single-word (63-bit, 21-level) keys are the fast path.  If two particles share a full key while the
 // reference's max_depth is deeper, the build is repeated (and stays) on the two-word path: 42 levels,
 // sorted with two stable radix passes (low word, then high word).
@@ -435,6 +462,7 @@ int refresh_tree(sph_ctx* c) {
 }
 
 int build_tree(sph_ctx* c) {
+  if (c->dd) return (c->tree_valid && !c->pos_moved && c->tree_reuse) ? dd_refresh_tree(c) : dd_build_tree(c);
   if (c->tree_valid && !c->pos_moved && c->tree_reuse) return refresh_tree(c);
   bool retry = false;
   int r = build_tree_impl(c, &retry);
@@ -597,7 +625,8 @@ int run_density(sph_ctx* c) {
   c->nl_valid = true; c->nl_exact = c->exact_counters;
   if (c->n_ranks > 1) { int r_ = allreduce(c, c->nl_ctl + 1, 1, 2 /*ncclInt32*/, 2 /*ncclMax*/); if (r_) return r_; }   // a non-finite particle anywhere voids every rank's lists
   stage_end(c);
-  if (c->n_ranks > 1) { stage_begin(c, ST_COMM); double* bufs[3] = {c->rho, c->cs, c->por2}; int r_ = allgatherv_begin(c, bufs, 3);   /* what the pair loop reads of its sources (Omega and P stay rank-local until a diagnostic download asks); completes under the gravity walk */ if (r_) return r_; stage_end(c); }
+  if (c->dd) { stage_begin(c, ST_COMM); int r_ = dd_pull_density_fields(c); if (r_) return r_; stage_end(c); }
+  else if (c->n_ranks > 1) { stage_begin(c, ST_COMM); double* bufs[3] = {c->rho, c->cs, c->por2}; int r_ = allgatherv_begin(c, bufs, 3);   /* what the pair loop reads of its sources (Omega and P stay rank-local until a diagnostic download asks); completes under the gravity walk */ if (r_) return r_; stage_end(c); }
   return SPH_OK;
 }
 int run_hiter(sph_ctx* c) {
@@ -609,7 +638,7 @@ int run_hiter(sph_ctx* c) {
   LAUNCH(k_density<true>, walk_grid(c, W), W * 32, density_smem(c, W), c->g1, c->groups, c->dp, dens_arrays(c), c->bvh, c->bi, c->d_wt, c->d_dwt,
          s.u, s.h, c->rho, c->omega, c->prs, c->cs, c->por2, c->ctr, c->work, c->exact_counters, NeighbourListSink{nullptr, nullptr, c->nl_ctl, 0});
   stage_end(c);
-  if (c->n_ranks > 1) { stage_begin(c, ST_COMM); double* bufs[1] = {s.h}; int r_ = allgatherv(c, bufs, 1); if (r_) return r_; stage_end(c); }
+  if (c->n_ranks > 1 && !c->dd) { stage_begin(c, ST_COMM); double* bufs[1] = {s.h}; int r_ = allgatherv(c, bufs, 1); if (r_) return r_; stage_end(c); }
   return SPH_OK;
 }
 int run_force(sph_ctx* c) {
@@ -622,7 +651,7 @@ int run_force(sph_ctx* c) {
   const int WL = force_warps(c, true), WW = force_warps(c, false);
   // peers' copies of the five output arrays: the kernel pushes its results itself (exchanged_arrays slots 3..7)
   PeerOut po; po.n = 0;
-  if (c->n_ranks > 1) {
+  if (c->n_ranks > 1 && !c->dd) {
     if (c->p2p_stale) { int r_ = p2p_setup(c); if (r_) return r_; }
     if (c->p2p_ok && c->n_ranks - 1 <= SPH_MAX_PEERS && c->fused_push) {
       for (int k = 1; k < c->n_ranks; ++k) {
@@ -643,7 +672,7 @@ int run_force(sph_ctx* c) {
   { unsigned long long d[16]; cudaStreamSynchronize(c->stream); cudaMemcpyFromSymbol(d, wk_dbg, sizeof(d)); unsigned long long z[16] = {}; cudaMemcpyToSymbol(wk_dbg, z, sizeof(z));
     fprintf(stderr, "WKDBG groups %d force: tiles %llu staged %llu trips %llu hits %llu boxpairs %llu | density: tiles %llu staged %llu trips %llu hits %llu\n", c->n_groups, d[0], d[1], d[2], d[3], d[4], d[8], d[9], d[10], d[11]); }
 #endif
-  if (c->n_ranks > 1) {
+  if (c->n_ranks > 1 && !c->dd) {
     stage_begin(c, ST_COMM);
     if (po.n > 0) {     // the kernels pushed their slices themselves: only the "every rank's kernel has finished" barrier is left
       { int r_ = coll_allreduce(c, c->stream, c->d_flag + 2, 1, NC_INT32, NC_SUM); if (r_) return r_; }
@@ -678,10 +707,10 @@ int run_gravity(sph_ctx* c, int do_grav, int do_sinks) {
       if ((size_t)ng > c->ggroups_cap) { c->ggroups_cap = (size_t)ng * 5 / 4 + 64; DA(c->ggroups, c->ggroups_cap); DA(c->gbvh, c->ggroups_cap); }
       if ((size_t)nseg + 1 > c->seg_cap) { c->seg_cap = (size_t)nseg * 5 / 4 + 64; DA(c->seg_cnt, c->seg_cap); DA(c->seg_off, c->seg_cap); }
       CK(cudaMemsetAsync(c->ggroups, 0, sizeof(int2) * (size_t)ng, c->stream));
-      LAUNCH(k_seg_count, cdiv(nseg + 1, 64), 64, 0, seg0, nseg, c->n_groups, GRAV_CHUNK_WIDTH, c->groups, c->seg_cnt);
+      LAUNCH(k_seg_count, cdiv(nseg + 1, 64), 64, 0, seg0, nseg, c->g1, GRAV_CHUNK_WIDTH, c->groups, c->seg_cnt);
       size_t bytes = c->cub_bytes;
       CK(cub::DeviceScan::ExclusiveSum(c->cub_tmp, bytes, c->seg_cnt, c->seg_off, nseg + 1, c->stream));
-      LAUNCH(k_seg_chunks, cdiv(nseg, 64), 64, 0, seg0, nseg, c->n_groups, GRAV_CHUNK_WIDTH, c->groups, c->seg_off, c->ggroups);
+      LAUNCH(k_seg_chunks, cdiv(nseg, 64), 64, 0, seg0, nseg, c->g1, GRAV_CHUNK_WIDTH, c->groups, c->seg_off, c->ggroups);
       LAUNCH(k_grav_boxes, cdiv((int64_t)ng * 32, 256), 256, 0, ng, c->ggroups, s.x, s.y, s.z, c->gbvh);
       c->grav_groups_valid = true;
     }
@@ -697,15 +726,15 @@ int run_gravity(sph_ctx* c, int do_grav, int do_sinks) {
 #endif
   // sink side of the gas terms: per-segment folds -> exchange of the rows -> one fixed fold over all segments (rank-count independent)
   {
-    const int nst = cdiv(c->n_groups, GRAV_SEG), nsk = std::max(c->n_sink, 1);
+    const int nst = cdiv(c->dd ? c->g1 : c->n_groups, GRAV_SEG), nsk = std::max(c->n_sink, 1);
     if ((size_t)nst * nsk * 3 > c->sink_seg_cap) {
       c->sink_seg_cap = (size_t)(nst + nst / 8 + 64) * (nsk + 1) * 3;
-      DA(c->sink_seg, c->sink_seg_cap); c->p2p_stale = true;
+      DA(c->sink_seg, c->sink_seg_cap); if (!c->dd) c->p2p_stale = true;
     }
     if (do_sinks && nseg > 0 && c->g1 > c->g0)
       LAUNCH(k_sink_seg_fold, cdiv((int64_t)nseg * c->n_sink * 3, 128), 128, 0, nseg, seg0, c->n_sink, c->seg_off, c->sink_partial, c->sink_seg);
     stage_end(c);
-    if (c->n_ranks > 1 && do_sinks) {
+    if (c->n_ranks > 1 && do_sinks && !c->dd) {
       stage_begin(c, ST_COMM);
       std::vector<size_t> roff(c->n_ranks + 1);
       for (int r = 0; r <= c->n_ranks; ++r) roff[r] = (size_t)(r == c->n_ranks ? nst : c->rank_g[r] / GRAV_SEG) * c->n_sink * 3;
@@ -716,6 +745,8 @@ int run_gravity(sph_ctx* c, int do_grav, int do_sinks) {
     stage_begin(c, ST_GRAVITY);
     LAUNCH(k_sink_reduce, 1, 256, 0, nst, c->n_sink, c->sink_seg, c->S, do_sinks);
     stage_end(c);
+    // domains: the segments are per rank (walk groups differ at domain boundaries), so the ranks' totals are added
+    if (c->dd) { stage_begin(c, ST_COMM); int r_ = allreduce(c, c->S.ax, (size_t)3 * SPH_MAX_SINKS, NC_FLOAT64, NC_SUM); if (r_) return r_; stage_end(c); }
   }
   stage_begin(c, ST_GRAVITY);
   LAUNCH(k_sink_pairs, 1, 32, 0, c->n_sink, c->S, c->dp.G, do_sinks);
@@ -735,7 +766,7 @@ int evaluate(sph_ctx* c, int mask) {
   if (mask & SPH_EVAL_DENSITY) { if ((r = run_density(c))) return r; }
   if ((r = run_gravity(c, (mask & SPH_EVAL_GRAVITY) ? 1 : 0, (mask & SPH_EVAL_SINKS) ? 1 : 0))) return r;
   if (mask & SPH_EVAL_SPH) { if ((r = run_force(c))) return r; }
-  else { double* bufs[3] = {c->ax, c->ay, c->az}; if ((r = allgatherv(c, bufs, 3))) return r; }
+  else if (!c->dd) { double* bufs[3] = {c->ax, c->ay, c->az}; if ((r = allgatherv(c, bufs, 3))) return r; }
   return SPH_OK;
 }
 
@@ -743,7 +774,7 @@ int fetch_counters(sph_ctx* c) {
   { int r_ = allreduce(c, c->ctr, sizeof(WalkCounters) / 8, NC_UINT64, NC_SUM); if (r_) return r_; }
   CK(cudaMemcpyAsync(c->h_ctr, c->ctr, sizeof(WalkCounters), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
-  c->counts.n_gas = c->n;
+  c->counts.n_gas = c->dd ? c->n_global : c->n;
   c->counts.density_candidates = (int64_t)c->h_ctr->dens_cand;
   c->counts.density_contributing = (int64_t)c->h_ctr->dens_contrib;
   c->counts.sph_pairs = (int64_t)(c->h_ctr->sph_pairs / 2);
@@ -807,6 +838,15 @@ int step(sph_ctx* c) {
     if ((r = run_hiter(c))) return r;                                         // V:1152
     stage_begin(c, ST_CULL);
     LAUNCH(k_create_scan, cdiv(n, T), T, 0, n, c->dp, state_of(c, c->cur), c->sc);          // V:1155
+    if (c->dd) {      // the lowest-numbered over-dense particle of ALL domains; its owner publishes x v h
+      CK(cudaMemcpyAsync(c->dd_cand, &c->sc->create_cand, 8, cudaMemcpyDeviceToDevice, c->stream));
+      CK(cudaMemcpyAsync(c->dd_cand + 1, &c->sc->create_cand, 8, cudaMemcpyDeviceToDevice, c->stream));
+      LAUNCH(k_dd_cand_id, 1, 1, 0, c->dd_cand + 1);
+      { int r_ = allreduce(c, c->dd_cand + 1, 1, NC_UINT64, NC_MIN); if (r_) return r_; }
+      LAUNCH(k_dd_create_publish, 1, 32, 0, c->dd_cand, c->dd_cand + 1, state_of(c, c->cur), c->dd_create8);
+      { int r_ = allreduce(c, c->dd_create8, 8, NC_FLOAT64, NC_SUM); if (r_) return r_; }
+      LAUNCH(k_dd_create_apply, 1, 32, 0, c->dd_create8, c->S, c->sc, c->sink_spin);
+    } else
     LAUNCH(k_create_apply, 1, 32, 0, state_of(c, c->cur), c->S, c->sc, c->sink_spin);
     stage_end(c);
   }
@@ -822,20 +862,25 @@ int step(sph_ctx* c) {
     return SPH_ERR_STATE;
   }
   int n_acc = c->h_sc->n_accreted;
-  if (n_acc > 1) {
-    cub::DoubleBuffer<unsigned long long> dk(c->acc_key[0], c->acc_key[1]); cub::DoubleBuffer<int> dv(c->acc_val[0], c->acc_val[1]);
-    size_t bytes = c->cub_bytes;
-    CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp, bytes, dk, dv, n_acc, 0, 64, c->stream));
-    if (dk.Current() != c->acc_key[0]) std::swap(c->acc_key[0], c->acc_key[1]);
-    if (dv.Current() != c->acc_val[0]) std::swap(c->acc_val[0], c->acc_val[1]);
+  int n_removed_global = c->h_sc->n_removed;
+  if (c->dd) { int r_ = dd_accrete(c, n_acc, &n_removed_global); if (r_) return r_; }
+  else {
+    if (n_acc > 1) {
+      cub::DoubleBuffer<unsigned long long> dk(c->acc_key[0], c->acc_key[1]); cub::DoubleBuffer<int> dv(c->acc_val[0], c->acc_val[1]);
+      size_t bytes = c->cub_bytes;
+      CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp, bytes, dk, dv, n_acc, 0, 64, c->stream));
+      if (dk.Current() != c->acc_key[0]) std::swap(c->acc_key[0], c->acc_key[1]);
+      if (dv.Current() != c->acc_val[0]) std::swap(c->acc_val[0], c->acc_val[1]);
+    }
+    LAUNCH(k_accrete_apply, 1, SPH_MAX_SINKS, 0, n_acc, c->acc_key[0], c->acc_val[0], state_of(c, c->cur), c->S, c->sc, c->sink_spin);
   }
-  LAUNCH(k_accrete_apply, 1, SPH_MAX_SINKS, 0, n_acc, c->acc_key[0], c->acc_val[0], state_of(c, c->cur), c->S, c->sc, c->sink_spin);
   if (c->dp.variable_h) LAUNCH(k_cull_sinks, 1, 32, 0, c->dp, c->S, c->sc, c->sink_spin);   // V:613
   if (c->sink_extras) LAUNCH(k_sink_merge, 1, 32, 0, c->S, c->sc, c->sink_spin);            // V:1159 (commented out in the reference)
   const int n_removed = c->h_sc->n_removed;
   // reset per-step device counters
   CK(cudaMemsetAsync(&c->sc->n_removed, 0, sizeof(int) * 2, c->stream));
   if (n_removed > 0) { if ((r = compact(c))) return r; }
+  if (c->dd && n_removed_global > 0) { c->tree_valid = false; c->pos_moved = true; c->n_global -= n_removed_global; }      // every domain rebuilds when any lost a particle
   CK(cudaMemcpyAsync(c->h_sc, c->sc, sizeof(SimScalars), cudaMemcpyDeviceToHost, c->stream));
   int nl_host[4] = {0, 0, 0, 0};
   CK(cudaMemcpyAsync(nl_host, c->nl_ctl, sizeof(nl_host), cudaMemcpyDeviceToHost, c->stream));
@@ -998,6 +1043,9 @@ int sph_destroy(sph_ctx* c) {
   F(c->rho); F(c->omega); F(c->prs); F(c->cs); F(c->por2); F(c->ax); F(c->ay); F(c->az); F(c->udot); F(c->adot);
   F(c->node_count); F(c->gsize); F(c->gfirst); F(c->groups); F(c->level); F(c->lcx); F(c->lcy); F(c->lcz); F(c->reach); F(c->bvh); F(c->nodes); F(c->node_part); F(c->parent); F(c->nchild);
   F(c->nl_pool); F(c->nl_head); F(c->nl_ctl); F(c->ggroups); F(c->gbvh); F(c->seg_cnt); F(c->seg_off); F(c->wnodes); F(c->wcount); F(c->wstart); F(c->widx); F(c->grav_spill);
+  F(c->dd_samples); F(c->dd_split); F(c->dd_counts); F(c->dd_sendoff); F(c->dd_cells); F(c->dd_contrib); F(c->dd_dom); F(c->dd_let_ctl); F(c->dd_create8); F(c->dd_cand);
+  F(c->dd_let_f[0]); F(c->dd_let_f[1]); F(c->dd_halo_flag); F(c->dd_halo_list); F(c->dd_halo_size); F(c->dd_halo_poff); F(c->dd_acc_key); F(c->dd_acc_rec);
+  F(c->dd_accg_key[0]); F(c->dd_accg_key[1]); F(c->dd_accg_idx[0]); F(c->dd_accg_idx[1]); F(c->dd_accg_rec); F(c->dd_gid); F(c->dd_gpos); F(c->dd_gcnt); F(c->dd_goff); F(c->dd_gstage);
   F(c->cons_partial); F(c->cons_out); F(c->img_table); F(c->sink_spin);
   F(c->arrive); F(c->cnt); F(c->off); F(c->root); F(c->partial); F(c->cub_tmp); F(c->d_wt); F(c->d_dwt); F(c->d_gt);
   F(c->sink_buf); F(c->sink_partial); F(c->sink_seg); F(c->sc); F(c->ctr); F(c->work); F(c->keep); F(c->d_nsel); F(c->pos); F(c->stage_d); F(c->stage_d2);
@@ -1050,6 +1098,41 @@ int sph_comm_init_host(sph_ctx* c, int32_t rank, int32_t n_ranks, const char* na
   return SPH_OK;
 }
 
+// n_local rows starting at global number id_first out of n_global (single rank / replicated: all of them)
+static int upload_impl(sph_ctx* c, int64_t n_global, int64_t id_first, int64_t n, const double* const* src,
+                       int32_t ns, const double* const* ssrc, const double* srad) {
+  cudaSetDevice(c->device);
+  c->dd = c->n_ranks > 1 && c->p.decomposition == 1;
+  int64_t want = n;
+  if (c->dd) {      // own share + halo + migration slack; every exported array is sized once here (the peers map them once)
+    double slack = 0.6; if (const char* e = getenv("SPH_B200_DOMAIN_SLACK")) slack = atof(e);
+    want = std::max<int64_t>(n, (int64_t)((double)(n_global / c->n_ranks) * (1.0 + slack)) + 65536);
+  }
+  if (c->dd && !c->dd_acc_key) c->cap = 0;        // the exported arrays of the decomposition are sized in ensure_capacity
+  int r = ensure_capacity(c, want); if (r) return r;
+  c->n_halo = 0; c->ng_halo = 0; c->dd_info.clear();
+  c->n = n; c->n_upload = n_global; c->n_global = n_global; c->cur = 0; c->tree_valid = false; c->pos_moved = true;
+  for (int f = 0; f < 10; ++f) {
+    if (src[f]) { if (n > 0) CK(cudaMemcpyAsync(c->st[0][f], src[f], (size_t)n * 8, cudaMemcpyHostToDevice, c->stream)); }
+    else if (f == 8) CK(cudaMemsetAsync(c->st[0][f], 0, (size_t)std::max<int64_t>(n, 1) * 8, c->stream));            // alpha := 0, F:681
+    else { std::vector<double> hv((size_t)std::max<int64_t>(n, 1), c->p.h_fixed); CK(cudaMemcpyAsync(c->st[0][f], hv.data(), hv.size() * 8, cudaMemcpyHostToDevice, c->stream)); CK(cudaStreamSynchronize(c->stream)); }
+  }
+  if (n > 0) LAUNCH(k_iota_from, cdiv(n, 256), 256, 0, (int)n, (int)id_first, c->id[0]);
+  // sinks (dummy zero sink if none: F:698-707)
+  std::vector<double> hb((size_t)SPH_MAX_SINKS * 11, 0.0);
+  const int M = SPH_MAX_SINKS;
+  for (int k = 0; k < 7; ++k) for (int q = 0; q < ns; ++q) hb[(size_t)k * M + q] = ssrc[k] ? ssrc[k][q] : 0.0;
+  for (int q = 0; q < ns; ++q) hb[(size_t)7 * M + q] = (srad && srad[q] == srad[q]) ? srad[q] : c->p.sink_radius;
+  c->n_sink = ns > 0 ? ns : 1;
+  CK(cudaMemcpyAsync(c->sink_buf, hb.data(), hb.size() * 8, cudaMemcpyHostToDevice, c->stream));
+  if (c->sink_spin) CK(cudaMemsetAsync(c->sink_spin, 0, (size_t)SPH_MAX_SINKS * 3 * 8, c->stream));   // F:695 spin = 0
+  CK(cudaStreamSynchronize(c->stream));
+  c->h_sc->n_sink = c->n_sink; c->h_sc->n_removed = 0; c->h_sc->n_accreted = 0; c->h_sc->err = 0; c->h_sc->create_cand = ~0ull;
+  CK(cudaMemcpyAsync(c->sc, c->h_sc, sizeof(SimScalars), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return SPH_OK;
+}
+
 int sph_upload(sph_ctx* c, int64_t n, const double* x, const double* y, const double* z,
                const double* vx, const double* vy, const double* vz, const double* u, const double* m,
                const double* alpha, const double* h, int32_t ns,
@@ -1059,30 +1142,30 @@ int sph_upload(sph_ctx* c, int64_t n, const double* x, const double* y, const do
   if (n < 2 || n > 0x0fffffff * (int64_t)SPH_CHUNK || !x || !y || !z || !vx || !vy || !vz || !u || !m) { c->err = "bad particle arrays"; return SPH_ERR_ARG; }
   if (ns < 0 || ns > SPH_MAX_SINKS - 8) { c->err = "too many sinks"; return SPH_ERR_ARG; }
   if (c->dp.variable_h && !h) { c->err = "variable-h mode needs the smoothing-length column"; return SPH_ERR_ARG; }
-  cudaSetDevice(c->device);
-  int r = ensure_capacity(c, n); if (r) return r;
-  c->n = n; c->n_upload = n; c->cur = 0; c->tree_valid = false; c->pos_moved = true;
   const double* src[10] = {x, y, z, vx, vy, vz, u, m, alpha, c->dp.variable_h ? h : nullptr};   // F ignores column 10
-  for (int f = 0; f < 10; ++f) {
-    if (src[f]) CK(cudaMemcpyAsync(c->st[0][f], src[f], (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
-    else if (f == 8) CK(cudaMemsetAsync(c->st[0][f], 0, (size_t)n * 8, c->stream));            // alpha := 0, F:681
-    else { std::vector<double> hv((size_t)n, c->p.h_fixed); CK(cudaMemcpyAsync(c->st[0][f], hv.data(), (size_t)n * 8, cudaMemcpyHostToDevice, c->stream)); CK(cudaStreamSynchronize(c->stream)); }
-  }
-  LAUNCH(k_iota, cdiv(n, 256), 256, 0, (int)n, c->id[0]);
-  // sinks (dummy zero sink if none: F:698-707)
-  std::vector<double> hb((size_t)SPH_MAX_SINKS * 11, 0.0);
-  const int M = SPH_MAX_SINKS;
   const double* ssrc[7] = {sx, sy, sz, svx, svy, svz, sm};
-  for (int k = 0; k < 7; ++k) for (int s = 0; s < ns; ++s) hb[(size_t)k * M + s] = ssrc[k] ? ssrc[k][s] : 0.0;
-  for (int s = 0; s < ns; ++s) hb[(size_t)7 * M + s] = (srad && srad[s] == srad[s]) ? srad[s] : c->p.sink_radius;
-  c->n_sink = ns > 0 ? ns : 1;
-  CK(cudaMemcpyAsync(c->sink_buf, hb.data(), hb.size() * 8, cudaMemcpyHostToDevice, c->stream));
-  if (c->sink_spin) CK(cudaMemsetAsync(c->sink_spin, 0, (size_t)SPH_MAX_SINKS * 3 * 8, c->stream));   // F:695 spin = 0
-  CK(cudaStreamSynchronize(c->stream));
-  c->h_sc->n_sink = c->n_sink; c->h_sc->n_removed = 0; c->h_sc->n_accreted = 0; c->h_sc->err = 0; c->h_sc->create_cand = ~0ull;
-  CK(cudaMemcpyAsync(c->sc, c->h_sc, sizeof(SimScalars), cudaMemcpyHostToDevice, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
-  return SPH_OK;
+  int64_t first = 0, cnt = n;
+  if (c->n_ranks > 1 && c->p.decomposition == 1) {      // Morton domains: this rank starts from rows [n r / R, n (r + 1) / R); the first tree build sends every particle to its owner
+    first = n * c->rank / c->n_ranks; cnt = n * (c->rank + 1) / c->n_ranks - first;
+    for (int f = 0; f < 10; ++f) if (src[f]) src[f] += first;
+  }
+  return upload_impl(c, n, first, cnt, src, ns, ssrc, srad);
+}
+
+int sph_upload_local(sph_ctx* c, int64_t n_global, int64_t id_first, int64_t n_local, const double* x, const double* y, const double* z,
+                     const double* vx, const double* vy, const double* vz, const double* u, const double* m,
+                     const double* alpha, const double* h, int32_t ns,
+                     const double* sx, const double* sy, const double* sz, const double* svx, const double* svy, const double* svz,
+                     const double* sm, const double* srad) {
+  if (!c) return SPH_ERR_ARG;
+  if (!(c->n_ranks > 1 && c->p.decomposition == 1)) { c->err = "sph_upload_local needs the domain decomposition (params.decomposition = 1 and a communicator)"; return SPH_ERR_STATE; }
+  if (n_global < 2 || n_local < 0 || id_first < 0 || id_first + n_local > n_global || n_global > 0x7fffffff) { c->err = "bad row range"; return SPH_ERR_ARG; }
+  if (n_local > 0 && (!x || !y || !z || !vx || !vy || !vz || !u || !m)) { c->err = "bad particle arrays"; return SPH_ERR_ARG; }
+  if (ns < 0 || ns > SPH_MAX_SINKS - 8) { c->err = "too many sinks"; return SPH_ERR_ARG; }
+  if (c->dp.variable_h && !h && n_local > 0) { c->err = "variable-h mode needs the smoothing-length column"; return SPH_ERR_ARG; }
+  const double* src[10] = {x, y, z, vx, vy, vz, u, m, alpha, c->dp.variable_h ? h : nullptr};
+  const double* ssrc[7] = {sx, sy, sz, svx, svy, svz, sm};
+  return upload_impl(c, n_global, id_first, n_local, src, ns, ssrc, srad);
 }
 
 int sph_evaluate(sph_ctx* c, int32_t mask) {
@@ -1109,7 +1192,7 @@ int sph_step(sph_ctx* c, double* dt, double* t, int64_t* n_out, int32_t* ns_out)
   stage_collect(c, true);
   CK(cudaGetLastError());
   *dt = c->h_sc->dt; *t = c->h_sc->t;
-  if (n_out) *n_out = c->n;
+  if (n_out) *n_out = c->dd ? c->n_global : c->n;
   if (ns_out) *ns_out = c->n_sink;
   return SPH_OK;
 }
@@ -1131,14 +1214,14 @@ int sph_run_until(sph_ctx* c, double t_stop, int64_t max_steps, double* dt, doub
   if (!r) { r = fetch_counters(c); c->counts.h_iterations = (int64_t)c->h_ctr->h_iters; }
   *dt = c->h_sc->dt; *t = c->h_sc->t;
   if (steps_out) *steps_out = steps;
-  if (n_out) *n_out = c->n;
+  if (n_out) *n_out = c->dd ? c->n_global : c->n;
   if (ns_out) *ns_out = c->n_sink;
   return r;
 }
 
 int sph_sizes(sph_ctx* c, int64_t* n, int32_t* ns) {
   if (!c) return SPH_ERR_ARG;
-  if (n) *n = c->n;
+  if (n) *n = c->dd ? c->n_global : c->n;
   if (ns) *ns = c->n_sink;
   return SPH_OK;
 }
@@ -1149,7 +1232,11 @@ int sph_download(sph_ctx* c, double* x, double* y, double* z, double* vx, double
   if (!c) return SPH_ERR_ARG;
   cudaSetDevice(c->device);
   int r;
-  if (c->n > 0) {
+  if (c->dd) {      // every rank receives all rows (tests, saves of small runs); production hosts use sph_download_local
+    if ((r = dd_prepare_download(c))) return r;
+    double* dst[10] = {x, y, z, vx, vy, vz, u, m, alpha, h};
+    for (int f = 0; f < 10; ++f) if ((r = dd_fetch_ordered(c, DS_ST + f, 1, dst[f]))) return r;
+  } else if (c->n > 0) {
     if ((r = compute_pos(c))) return r;
     double* dst[10] = {x, y, z, vx, vy, vz, u, m, alpha, h};
     for (int f = 0; f < 10; ++f) if ((r = fetch_ordered(c, c->st[c->cur][f], dst[f]))) return r;
@@ -1161,14 +1248,47 @@ int sph_download(sph_ctx* c, double* x, double* y, double* z, double* vx, double
   return SPH_OK;
 }
 
+int sph_local_size(sph_ctx* c, int64_t* n_local) {
+  if (!c || !n_local) return SPH_ERR_ARG;
+  *n_local = c->n;
+  return SPH_OK;
+}
+
+int sph_download_local(sph_ctx* c, int32_t* number, double* x, double* y, double* z, double* vx, double* vy, double* vz,
+                       double* u, double* m, double* alpha, double* h) {
+  if (!c) return SPH_ERR_ARG;
+  cudaSetDevice(c->device);
+  const size_t n = (size_t)c->n;
+  double* dst[10] = {x, y, z, vx, vy, vz, u, m, alpha, h};
+  if (n > 0) {
+    if (number) CK(cudaMemcpyAsync(number, c->id[c->cur], n * 4, cudaMemcpyDeviceToHost, c->stream));
+    for (int f = 0; f < 10; ++f) if (dst[f]) CK(cudaMemcpyAsync(dst[f], c->st[c->cur][f], n * 8, cudaMemcpyDeviceToHost, c->stream));
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  return SPH_OK;
+}
+
 int sph_download_diag(sph_ctx* c, double* rho, double* omega, double* pressure, double* sound,
                       double* ax, double* ay, double* az, double* udot, double* alphadot,
                       double* sax, double* say, double* saz) {
   if (!c) return SPH_ERR_ARG;
   if (c->n <= 0) { c->err = "no particles"; return SPH_ERR_STATE; }
   cudaSetDevice(c->device);
-  int r; if ((r = compute_pos(c))) return r;
-  { double* bufs[2] = {c->omega, c->prs}; if ((r = allgatherv(c, bufs, 2))) return r; }
+  int r;
+  if (c->dd) {
+    if ((r = dd_prepare_download(c))) return r;
+    const int slots[9] = {DS_RHO, DS_OMEGA, DS_PRS, DS_CS, DS_AX, DS_AY, DS_AZ, DS_UDOT, DS_ADOT};
+    double* dst[9] = {rho, omega, pressure, sound, ax, ay, az, udot, alphadot};
+    for (int f = 0; f < 9; ++f) if ((r = dd_fetch_ordered(c, slots[f], 0, dst[f]))) return r;
+    if ((r = fetch_sink(c, c->S.ax, sax))) return r;
+    if ((r = fetch_sink(c, c->S.ay, say))) return r;
+    if ((r = fetch_sink(c, c->S.az, saz))) return r;
+    CK(cudaStreamSynchronize(c->stream));
+    return SPH_OK;
+  }
+  if ((r = compute_pos(c))) return r;
+  // Omega and P stay rank-local during a step, and calc_smoothing rewrites rho / Omega of the particles it iterated (V:535): bring every slice up to date
+  { double* bufs[3] = {c->omega, c->prs, c->rho}; if ((r = allgatherv(c, bufs, 3))) return r; }
   const double* src[9] = {c->rho, c->omega, c->prs, c->cs, c->ax, c->ay, c->az, c->udot, c->adot};
   double* dst[9] = {rho, omega, pressure, sound, ax, ay, az, udot, alphadot};
   for (int f = 0; f < 9; ++f) if ((r = fetch_ordered(c, src[f], dst[f]))) return r;
@@ -1184,8 +1304,34 @@ int sph_download_tree(sph_ctx* c, int32_t* order, uint64_t* key, int32_t* level,
   if (!c) return SPH_ERR_ARG;
   if (!c->tree_valid) { c->err = "no tree"; return SPH_ERR_STATE; }
   cudaSetDevice(c->device);
+  int r;
+  if (c->dd) {      // the global depth-first order = the domains' orders in rank order
+    if ((r = dd_prepare_download(c))) return r;
+    const int n = (int)c->n_global, T = 256;
+    if (order) { CK(cudaMemcpyAsync(order, c->dd_gpos, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream)); }
+    if (key) {
+      if ((r = dd_gather(c, DS_KEY, 2, 8, c->dd_gstage))) return r;
+      LAUNCH(k_scatter_u64, cdiv(n, T), T, 0, n, c->dd_gpos, (const unsigned long long*)c->dd_gstage, (unsigned long long*)(c->dd_gstage + c->dd_g_cap));
+      CK(cudaMemcpyAsync(key, c->dd_gstage + c->dd_g_cap, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream));
+    }
+    std::vector<int> lev(n);
+    if (level || size) {
+      if ((r = dd_gather(c, DS_LEVEL, 0, 4, c->dd_gstage))) return r;
+      LAUNCH(k_scatter_i, cdiv(n, T), T, 0, n, c->dd_gpos, (const int*)c->dd_gstage, (int*)(c->dd_gstage + c->dd_g_cap));
+      CK(cudaMemcpyAsync(lev.data(), c->dd_gstage + c->dd_g_cap, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream));
+      if (level) std::memcpy(level, lev.data(), (size_t)n * 4);
+    }
+    if ((r = dd_fetch_ordered(c, DS_LCX, 0, cx))) return r;
+    if ((r = dd_fetch_ordered(c, DS_LCY, 0, cy))) return r;
+    if ((r = dd_fetch_ordered(c, DS_LCZ, 0, cz))) return r;
+    if (size) {
+      RootBox rb; CK(cudaMemcpy(&rb, c->root, sizeof(rb), cudaMemcpyDeviceToHost));
+      for (int i = 0; i < n; ++i) { double s = rb.size; for (int q = 0; q < lev[i]; ++q) s *= 0.5; size[i] = s; }
+    }
+    return SPH_OK;
+  }
   const int n = (int)c->n, T = 256;
-  int r; if ((r = compute_pos(c))) return r;
+  if ((r = compute_pos(c))) return r;
   if (order) { CK(cudaMemcpyAsync(order, c->pos, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream)); }
   if (key) {
     LAUNCH(k_scatter_u64, cdiv(n, T), T, 0, n, c->pos, (const unsigned long long*)c->key[0], (unsigned long long*)c->stage_d);
@@ -1213,7 +1359,26 @@ int sph_download_neighbours(sph_ctx* c, int32_t* count, uint64_t* hash, int64_t*
   if (!c->tree_valid) { c->err = "no tree"; return SPH_ERR_STATE; }
   cudaSetDevice(c->device);
   const int n = (int)c->n, W = 8;
-  int r; if ((r = compute_pos(c))) return r;
+  int r;
+  if (c->dd) {      // counts and hashes of all ranks' own particles (the CSR list form is single-rank / replicated only)
+    if (list) { c->err = "sph_download_neighbours: the list form is not available under the domain decomposition"; return SPH_ERR_STATE; }
+    if ((r = dd_prepare_download(c))) return r;
+    const int ng = (int)c->n_global, T = 256;
+    size_t smem = (size_t)W * 4 * WALK_TILE * 8 + (size_t)W * WALK_TILE * 4 + (size_t)W * WALK_WS * 4;
+    LAUNCH(k_neighbours, walk_grid(c, W), W * 32, smem, c->g1, c->groups, dens_arrays(c), c->pos, c->bvh, c->bi, (int*)c->stage_d, (unsigned long long*)c->stage_d2, nullptr, nullptr);
+    std::vector<int> cnt(ng); std::vector<unsigned long long> hs(ng);
+    if ((r = dd_gather(c, DS_STAGE1, 0, 4, c->dd_gstage))) return r;
+    LAUNCH(k_scatter_i, cdiv(ng, T), T, 0, ng, c->dd_gpos, (const int*)c->dd_gstage, (int*)(c->dd_gstage + c->dd_g_cap));
+    CK(cudaMemcpyAsync(cnt.data(), c->dd_gstage + c->dd_g_cap, (size_t)ng * 4, cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream));
+    if ((r = dd_gather(c, DS_STAGE2, 0, 8, c->dd_gstage))) return r;
+    LAUNCH(k_scatter_u64, cdiv(ng, T), T, 0, ng, c->dd_gpos, (const unsigned long long*)c->dd_gstage, (unsigned long long*)(c->dd_gstage + c->dd_g_cap));
+    CK(cudaMemcpyAsync(hs.data(), c->dd_gstage + c->dd_g_cap, (size_t)ng * 8, cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream));
+    if (count) std::memcpy(count, cnt.data(), (size_t)ng * 4);
+    if (hash) std::memcpy(hash, hs.data(), (size_t)ng * 8);
+    if (offsets) { offsets[0] = 0; for (int i = 0; i < ng; ++i) offsets[i + 1] = offsets[i] + cnt[i]; }
+    return SPH_OK;
+  }
+  if ((r = compute_pos(c))) return r;
   int* d_count = nullptr; unsigned long long* d_hash = nullptr; long long* d_off = nullptr; int* d_list = nullptr;
   DA(d_count, n); DA(d_hash, n);
   size_t smem = (size_t)W * 4 * WALK_TILE * 8 + (size_t)W * WALK_TILE * 4 + (size_t)W * WALK_WS * 4;
@@ -1313,6 +1478,7 @@ int sph_fp64_peak(sph_ctx* c, double* tflops) {
 int sph_conserved(sph_ctx* c, double* out, int32_t n_out) {
   if (!c || !out || n_out < 1) return SPH_ERR_ARG;
   if (c->n < 2) { c->err = "need at least 2 gas particles"; return SPH_ERR_STATE; }
+  if (c->dd) { c->err = "sph_conserved is not available under the domain decomposition (use decomposition = 0 for the drift report)"; return SPH_ERR_STATE; }
   cudaSetDevice(c->device);
   double keep_ms[ST_COUNT]; std::memcpy(keep_ms, c->stage_ms, sizeof(keep_ms));
   if (!(c->tree_valid && !c->pos_moved)) {        // the octree of the current positions (kept for the next evaluation)

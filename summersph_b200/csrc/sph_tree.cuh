@@ -56,6 +56,12 @@ __global__ void k_bbox_final(int nblocks, const double* __restrict__ partial, Ro
   }
 }
 
+// domain decomposition: the ranks' boxes merge with ONE min all-reduce over [mn, -mx]
+__global__ void k_dd_box_pack(const RootBox* __restrict__ rb, double* __restrict__ v) {
+  if (threadIdx.x < 3) { v[threadIdx.x] = rb->mn[threadIdx.x]; v[3 + threadIdx.x] = -rb->mx[threadIdx.x]; }
+}
+__global__ void k_dd_box_unpack(double* __restrict__ v) { if (threadIdx.x < 3) v[3 + threadIdx.x] = -v[3 + threadIdx.x]; }
+
 // ------------------------------------------------------------------------------------------------------
 // descent keys: replay of F:190-214 for lmax levels. Digit = [x>cx] + 2[y>cy] + 4[z>cz] (strict >).
 // ------------------------------------------------------------------------------------------------------
@@ -120,12 +126,15 @@ __global__ void k_permute(int n, const int* __restrict__ perm, PermuteArgs a) {
 // ------------------------------------------------------------------------------------------------------
 __global__ void k_leaf(int n, const uint64_t* __restrict__ key, const uint64_t* __restrict__ key_lo, const double* __restrict__ h,
                        const RootBox* __restrict__ rb, DevParams P, int* __restrict__ level, double* __restrict__ lcx,
-                       double* __restrict__ lcy, double* __restrict__ lcz, double* __restrict__ reach, int* __restrict__ err_flag) {
+                       double* __restrict__ lcy, double* __restrict__ lcz, double* __restrict__ reach, int* __restrict__ err_flag,
+                       int has_prev = 0, uint64_t key_prev = 0, int has_next = 0, uint64_t key_next = 0) {
+  // has_prev / has_next (domain decomposition, single-word keys): the last key of the preceding domain / the first key
+  // of the following one stand in for the neighbours a rank does not hold, so the leaf cells equal the global tree's
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint64_t k = key[i], k2 = key_lo ? key_lo[i] : 0;
-  int d = (i > 0) ? lcp_levels2(key[i - 1], key_lo ? key_lo[i - 1] : 0, k, k2, P.lmax) : -1;
-  int e = (i < n - 1) ? lcp_levels2(k, k2, key[i + 1], key_lo ? key_lo[i + 1] : 0, P.lmax) : -1;
+  int d = (i > 0) ? lcp_levels2(key[i - 1], key_lo ? key_lo[i - 1] : 0, k, k2, P.lmax) : (has_prev ? lcp_levels2(key_prev, 0, k, k2, P.lmax) : -1);
+  int e = (i < n - 1) ? lcp_levels2(k, k2, key[i + 1], key_lo ? key_lo[i + 1] : 0, P.lmax) : (has_next ? lcp_levels2(k, k2, key_next, 0, P.lmax) : -1);
   int m = d > e ? d : e;
   bool multi = (m >= P.lmax);
   int lev = multi ? P.lmax : m + 1;
@@ -385,8 +394,9 @@ __global__ void k_oct_up(int n, const int* __restrict__ off, const int* __restri
   }
 }
 
+// wbase: first walk-layout slot of this tree (0; DD_TOP_CAP under the domain decomposition, where the top tree comes first)
 __global__ void k_oct_finalize(int n_nodes, GNode* nodes, const int* __restrict__ wcount, const int* __restrict__ wstart,
-                               const int* __restrict__ widx, WNode* __restrict__ wnodes) {
+                               const int* __restrict__ widx, WNode* __restrict__ wnodes, int wbase = 0) {
   int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= n_nodes) return;
   GNode g = nodes[v];
@@ -397,7 +407,7 @@ __global__ void k_oct_finalize(int n_nodes, GNode* nodes, const int* __restrict_
   const int w = widx[v];
   if (w >= 0) {
     WNode o; o.cx = g.cx; o.cy = g.cy; o.cz = g.cz; o.m = g.m; o.size = g.size;
-    o.child = 1 + wstart[v]; o.nchild = wcount[v];
-    wnodes[w] = o;
+    o.child = wbase + 1 + wstart[v]; o.nchild = wcount[v];
+    wnodes[wbase + w] = o;
   }
 }

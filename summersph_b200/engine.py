@@ -45,6 +45,9 @@ def load_library(path=None):
     lib.sph_slice_bounds.argtypes = [i32, i32, vp]
     lib.sph_comm_init_host.argtypes = [vp, i32, i32, C.c_char_p]
     lib.sph_upload.argtypes = [vp, i64] + [vp] * 10 + [i32] + [vp] * 8
+    lib.sph_upload_local.argtypes = [vp, i64, i64, i64] + [vp] * 10 + [i32] + [vp] * 8
+    lib.sph_local_size.argtypes = [vp, C.POINTER(i64)]
+    lib.sph_download_local.argtypes = [vp] + [vp] * 11
     lib.sph_evaluate.argtypes = [vp, i32]
     lib.sph_step.argtypes = [vp, C.POINTER(dbl), C.POINTER(dbl), C.POINTER(i64), C.POINTER(i32)]
     lib.sph_run_until.argtypes = [vp, dbl, i64, C.POINTER(dbl), C.POINTER(dbl), C.POINTER(i64), C.POINTER(i64), C.POINTER(i32)]
@@ -138,6 +141,26 @@ class Engine:
         self._ck(self._l.sph_upload(self._c, len(b), _p(b.x), _p(b.y), _p(b.z), _p(b.vx), _p(b.vy), _p(b.vz),
                                     _p(b.u), _p(b.m), _p(b.alpha), _p(b.h), len(s),
                                     _p(s.x), _p(s.y), _p(s.z), _p(s.vx), _p(s.vy), _p(s.vz), _p(s.m), _p(rad)))
+
+    def upload_local(self, n_global, id_first, b: Bodies, s: Sinks):
+        """Domain decomposition: hand over rows [id_first, id_first + len(b)) of the n_global gas rows (`sph_upload_local`)."""
+        self._ck(self._l.sph_upload_local(self._c, int(n_global), int(id_first), len(b), _p(b.x), _p(b.y), _p(b.z), _p(b.vx), _p(b.vy), _p(b.vz),
+                                          _p(b.u), _p(b.m), _p(b.alpha), _p(b.h), len(s),
+                                          _p(s.x), _p(s.y), _p(s.z), _p(s.vx), _p(s.vy), _p(s.vz), _p(s.m), _p(s.radius)))
+
+    def local_size(self):
+        n = C.c_int64()
+        self._ck(self._l.sph_local_size(self._c, C.byref(n)))
+        return n.value
+
+    def download_local(self, into=None):
+        """The rows this rank owns: (numbers, Bodies) in the rank's Morton order (`sph_download_local`)."""
+        n = self.local_size()
+        b = into if into is not None else Bodies.empty(n)
+        num = np.zeros(n, np.int32)
+        self._ck(self._l.sph_download_local(self._c, _p(num), _p(b.x), _p(b.y), _p(b.z), _p(b.vx), _p(b.vy), _p(b.vz), _p(b.u), _p(b.m),
+                                            _p(b.alpha), _p(b.h)))
+        return num, b
 
     def sizes(self):
         n, ns = C.c_int64(), C.c_int32()

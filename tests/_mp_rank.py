@@ -14,9 +14,9 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 
-def case(mode, n=60_000):
+def case(mode, n=60_000, decomposition=0):
     from summersph_b200 import default_params, ics
-    p = default_params(mode, bounding_size=95.0)
+    p = default_params(mode, bounding_size=95.0, decomposition=decomposition)
     b, s = ics.keplerian_disc(n, seed=12)
     s.radius[:] = 12.0                      # accretion + bounds removals exercised too
     return p, b, s
@@ -26,9 +26,10 @@ def main():
     rank, world, comm, device, mode, steps, out = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3], int(sys.argv[4]), int(sys.argv[5]), int(sys.argv[6]), sys.argv[7]
     token = sys.argv[8] if len(sys.argv) > 8 else ""
     n = int(sys.argv[9]) if len(sys.argv) > 9 else 60_000
+    domains = int(sys.argv[10]) if len(sys.argv) > 10 else 0
     from summersph_b200.engine import Engine
     from summersph_b200.state import GAS_FIELDS
-    p, b, s = case(mode, n)
+    p, b, s = case(mode, n, domains)
     with Engine(p, device=device) as e:
         if world > 1:
             if comm == "nccl":
@@ -42,11 +43,21 @@ def main():
         bb, ss = e.download()
         d = e.diag()
         c = e.counters()
+        extra = {}
+        if len(sys.argv) > 11 and sys.argv[11] == "tree":      # one more evaluation on the end state with exact counters: tree + neighbour sets
+            e.set_exact_counters(True); e.evaluate(); e.set_exact_counters(False)
+            t = e.tree(); cnt, hsh, _, _ = e.neighbours(with_list=False)
+            extra = {"t_" + k: v for k, v in t.items()}
+            extra.update({"n_count": cnt, "n_hash": hsh})
+            d2 = e.diag(); extra.update({"e_" + k: v for k, v in d2.items()})
+            c2 = e.counters(); extra["e_counters"] = np.array([c2[k] for k in sorted(c2)], dtype=np.int64)
+            extra["local_n"] = np.array([e.local_size()])
         res = {k: getattr(bb, k) for k in GAS_FIELDS}
         res.update({"s_" + k: getattr(ss, k) for k in ("x", "y", "z", "vx", "vy", "vz", "m")})
         res.update({"d_" + k: v for k, v in d.items()})
         res["meta"] = np.array([dt, t, float(e.sizes()[0]), float(e.sizes()[1])])
         res["counters"] = np.array([c[k] for k in sorted(c)], dtype=np.int64)
+        res.update(extra)
         np.savez(out, **res)
 
 
