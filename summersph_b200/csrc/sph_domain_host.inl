@@ -481,12 +481,12 @@ int dd_refresh_tree(sph_ctx* c) {
 }
 
 // ---- gathers for the host-facing downloads (tests, saves): every rank ends up with all ranks' own values, in rank order --
-int dd_gather(sph_ctx* c, int slot_base, int per_cur /* 0: fixed slot, 1: + the owner's current state buffer, 2: + the owner's sorted-key buffer */, size_t elem, void* dst_dev) {
+int dd_gather(sph_ctx* c, int slot_base, int per_cur /* 0: fixed slot, 1: + the owner's current buffer index (ids), 2: + the owner's sorted-key buffer, 3: + 10 x the owner's current buffer (state fields) */, size_t elem, void* dst_dev) {
   { int r_ = dd_barrier(c); if (r_) return r_; }
   size_t off = 0;
   for (int q = 0; q < c->n_ranks; ++q) {
     const size_t cnt = (size_t)c->dd_info[q].n_own;
-    const int slot = slot_base + (per_cur == 1 ? c->dd_info[q].cur : per_cur == 2 ? c->dd_info[q].key_slot : 0);
+    const int slot = slot_base + (per_cur == 1 ? c->dd_info[q].cur : per_cur == 2 ? c->dd_info[q].key_slot : per_cur == 3 ? 10 * c->dd_info[q].cur : 0);
     const void* src = q == c->rank ? dd_exported(c)[slot] : c->peer[slot][q];
     if (cnt) CK(cudaMemcpyAsync((char*)dst_dev + off * elem, src, cnt * elem, cudaMemcpyDefault, c->stream));
     off += cnt;
@@ -572,6 +572,7 @@ int dd_prepare_download(sph_ctx* c) {
   CK(cub::DeviceScan::ExclusiveSum(c->cub_tmp, bytes, c->dd_gcnt, c->dd_goff, nu + 1, c->stream));
   LAUNCH(k_rank_of_ids, cdiv(n, T), T, 0, n, c->dd_gid, c->dd_goff, c->dd_gpos);
   // the same for the particles this rank holds (own + halo): their ascending-number positions (neighbour diagnostics)
+  if (!c->tree_valid) { c->n_halo = 0; c->ng_halo = 0; }      // a compaction voided the halo region
   const int nl = (int)c->n + c->n_halo;
   LAUNCH(k_rank_of_ids, cdiv(nl, T), T, 0, nl, c->id[c->cur], c->dd_goff, c->pos);
   return SPH_OK;

@@ -756,13 +756,13 @@ int run_gravity(sph_ctx* c, int do_grav, int do_sinks) {
 
 int evaluate(sph_ctx* c, int mask) {
   if (c->n < 2) { c->err = "need at least 2 gas particles"; return SPH_ERR_STATE; }
-  const size_t nb = (size_t)c->n * 8;
-  CK(cudaMemsetAsync(c->ax, 0, nb, c->stream)); CK(cudaMemsetAsync(c->ay, 0, nb, c->stream)); CK(cudaMemsetAsync(c->az, 0, nb, c->stream));
-  CK(cudaMemsetAsync(c->udot, 0, nb, c->stream)); CK(cudaMemsetAsync(c->adot, 0, nb, c->stream));     // F:824
-  CK(cudaMemsetAsync(c->ctr, 0, sizeof(WalkCounters), c->stream));
   int r;
   if (mask & SPH_EVAL_TREE) { if ((r = build_tree(c))) return r; }
   else if (!c->tree_valid) { c->err = "no tree: evaluate with SPH_EVAL_TREE first"; return SPH_ERR_STATE; }
+  const size_t nb = (size_t)c->n * 8;        // after the build: under the domain decomposition the build changes which particles live here
+  CK(cudaMemsetAsync(c->ax, 0, nb, c->stream)); CK(cudaMemsetAsync(c->ay, 0, nb, c->stream)); CK(cudaMemsetAsync(c->az, 0, nb, c->stream));
+  CK(cudaMemsetAsync(c->udot, 0, nb, c->stream)); CK(cudaMemsetAsync(c->adot, 0, nb, c->stream));     // F:824
+  CK(cudaMemsetAsync(c->ctr, 0, sizeof(WalkCounters), c->stream));
   if (mask & SPH_EVAL_DENSITY) { if ((r = run_density(c))) return r; }
   if ((r = run_gravity(c, (mask & SPH_EVAL_GRAVITY) ? 1 : 0, (mask & SPH_EVAL_SINKS) ? 1 : 0))) return r;
   if (mask & SPH_EVAL_SPH) { if ((r = run_force(c))) return r; }
@@ -817,12 +817,14 @@ int step(sph_ctx* c) {
   int r;
   int n = (int)c->n;
   if ((r = evaluate(c, SPH_EVAL_ALL))) return r;                              // F:894-898
+  n = (int)c->n;                                                               // domains: the build may have moved particles between ranks
   stage_begin(c, ST_INTEGRATE);
   LAUNCH(k_kick<true>, cdiv(n, T), T, 0, n, state_of(c, c->cur), rates_of(c), c->sc);       // F:900,903
   c->pos_moved = true;
   LAUNCH(k_kick_sinks<true>, 1, SPH_MAX_SINKS, 0, c->S, c->sc);
   stage_end(c);
   if ((r = evaluate(c, SPH_EVAL_ALL))) return r;                              // F:905-910
+  n = (int)c->n;
   stage_begin(c, ST_INTEGRATE);
   LAUNCH(k_kick<false>, cdiv(n, T), T, 0, n, state_of(c, c->cur), rates_of(c), c->sc);      // F:912
   LAUNCH(k_kick_sinks<false>, 1, SPH_MAX_SINKS, 0, c->S, c->sc);
@@ -1235,7 +1237,7 @@ int sph_download(sph_ctx* c, double* x, double* y, double* z, double* vx, double
   if (c->dd) {      // every rank receives all rows (tests, saves of small runs); production hosts use sph_download_local
     if ((r = dd_prepare_download(c))) return r;
     double* dst[10] = {x, y, z, vx, vy, vz, u, m, alpha, h};
-    for (int f = 0; f < 10; ++f) if ((r = dd_fetch_ordered(c, DS_ST + f, 1, dst[f]))) return r;
+    for (int f = 0; f < 10; ++f) if ((r = dd_fetch_ordered(c, DS_ST + f, 3, dst[f]))) return r;
   } else if (c->n > 0) {
     if ((r = compute_pos(c))) return r;
     double* dst[10] = {x, y, z, vx, vy, vz, u, m, alpha, h};

@@ -46,8 +46,8 @@ def main():
         extra = {}
         if len(sys.argv) > 11 and sys.argv[11] == "tree":      # one more evaluation on the end state with exact counters: tree + neighbour sets
             e.set_exact_counters(True); e.evaluate(); e.set_exact_counters(False)
-            t = e.tree(); cnt, hsh, _, _ = e.neighbours(with_list=False)
-            extra = {"t_" + k: v for k, v in t.items()}
+            tr = e.tree(); cnt, hsh, _, _ = e.neighbours(with_list=False)
+            extra = {"t_" + k: v for k, v in tr.items()}
             extra.update({"n_count": cnt, "n_hash": hsh})
             d2 = e.diag(); extra.update({"e_" + k: v for k, v in d2.items()})
             c2 = e.counters(); extra["e_counters"] = np.array([c2[k] for k in sorted(c2)], dtype=np.int64)

@@ -53,7 +53,7 @@ def run_ranks(tmp_path, tag, world, comm, mode, steps=3, env_extra=None, n=60_00
     logs = []
     for p in procs:
         try:
-            o, _ = p.communicate(timeout=900)
+            o, _ = p.communicate(timeout=float(os.environ.get('SPH_TEST_RANK_TIMEOUT', '900')))
         except subprocess.TimeoutExpired:
             for q in procs:
                 q.kill()
