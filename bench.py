@@ -26,6 +26,7 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
+N_CONFIG5 = 64_000_000                  # BASELINE configs[4]
 BYTES_PER_PARTICLE_STEP = 1960.0        # compulsory HBM bytes per particle-step
 BYTES_SPH_PER_LAUNCH = 144.0            # SPH force pass, per particle per launch
 BYTES_DENSITY_PER_LAUNCH = 80.0
@@ -127,6 +128,73 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def engine_for(p, local, rank, world):
+    """Engine context + (world > 1) its own NCCL communicator, bootstrapped over torch.distributed."""
+    from summersph_b200.engine import Engine
+    e = Engine(p, device=local)
+    if world > 1:
+        from summersph_b200.parallel import init_comm, torch_broadcast_bytes
+        init_comm(e, rank, world, torch_broadcast_bytes)
+    return e
+
+
+def multi_gpu_check(p, local, rank, world, dist, torch):
+    """Untimed: a 60k disc with accretion and bounds removals, 3 loop bodies on all ranks (this run's multi-rank form:
+    one process per GPU, NCCL, peer memory) and on a private single-rank context of rank 0; every rank compares."""
+    from summersph_b200.state import GAS_FIELDS
+    from summersph_b200.engine import Engine
+    q = p.copy(bounding_size=95.0, sink_radius=12.0)
+    res = {}
+    for tag in ("multi", "single"):
+        if tag == "single" and rank != 0:
+            continue
+        e = engine_for(q, local, rank, world) if tag == "multi" else Engine(q.copy(decomposition=0), device=local)
+        e.ics_disc(60_000, seed=12)
+        dt, t = 0.01, 0.0
+        for _ in range(3):
+            dt, t = e.step(dt, t)
+        b, s = e.download()
+        res[tag] = (dt, t, e.sizes(), b, s, e.state_hash()[0])
+        e.close()
+    out = None
+    if rank == 0:
+        (dt1, t1, sz1, b1, s1, h1), (dt0, t0, sz0, b0, s0, h0) = res["multi"], res["single"]
+        dev = 0.0
+        same = (dt1, t1, sz1) == (dt0, t0, sz0)
+        if sz1 == sz0:
+            for k in GAS_FIELDS:
+                a, r = getattr(b1, k), getattr(b0, k)
+                sc = np.maximum(np.abs(r), np.sqrt(np.mean(r * r)) + 1e-300)
+                dev = max(dev, float(np.max(np.abs(a - r) / sc)))
+        out = {"case": "60k disc, sink radius 12, bounding 95, 3 steps, ranks vs a private 1-rank context on rank 0",
+               "bit_identical": bool(h1 == h0), "dt_t_sizes_equal": bool(same), "max_rel_dev": dev,
+               "state_hash": f"{h1:016x}", "state_hash_1rank": f"{h0:016x}"}
+    return out
+
+
+def timed_run(e, n, steps, warmup, barrier, sampler=None, before=None):
+    """warmup untimed steps, then `steps` timed steps on the engine's stream (CUDA events inside the engine)."""
+    dt, t = 0.01, 0.0
+    for _ in range(warmup):
+        dt, t = e.step(dt, t)
+    if before:
+        before()                                 # untimed hook between warm-up and the timed region (--drift)
+    stage_acc = {}
+    barrier()
+    if sampler:
+        sampler.start()
+    l0 = e.launch_count()
+    e.timer_start()
+    for _ in range(steps):
+        dt, t = e.step(dt, t)
+        for k, v in e.stage_times().items():
+            stage_acc[k] = stage_acc.get(k, 0.0) + v
+    ms = e.timer_stop()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    return ms, stage_acc, e.launch_count() - l0, clocks, (dt, t)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -134,12 +202,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--particles", type=int, default=16_000_000)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--decomposition", type=int, default=None, help="multi-rank form: 1 = Morton domains + halo exchange (default for --gpus > 1), "
+                    "0 = replicated state with Morton-sliced walks (bit-identical to one rank)")
     ap.add_argument("--ref-particles", type=int, default=1_000_000)
     ap.add_argument("--cpu-baseline-particles", type=int, default=100_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (large multi-GPU sizing runs)")
+    ap.add_argument("--no-config5", action="store_true", help="skip the short 64M-particle sub-run (BASELINE configs[4])")
+    ap.add_argument("--no-check", action="store_true", help="skip the untimed multi-rank vs single-rank comparison")
     ap.add_argument("--drift", action="store_true", help="add the energy / momentum / angular-momentum drift over the timed steps "
-                    "(sph_conserved before and after them, outside the timed region) as a \"drift\" key")
+                    "(sph_conserved before and after them, outside the timed region) as a \"drift\" key (single rank / replicated form)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -150,168 +222,217 @@ def main():
     import torch
     import torch.distributed as dist
     from summersph_b200 import default_params, MODE_VARIABLE_H, Bodies, Sinks
-    from summersph_b200.state import GAS_FIELDS, SINK_FIELDS
-    from summersph_b200.engine import Engine
+    from summersph_b200.state import GAS_FIELDS
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the SPH step)")
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    decomp = (1 if world > 1 else 0) if args.decomposition is None else (args.decomposition if world > 1 else 0)
 
     p = default_params(MODE_VARIABLE_H)
     p.n_ranks = world
+    p.decomposition = decomp
     n = args.particles
-    b, s = make_ics(n)
-    s.radius[:] = p.sink_radius
-    # pinned host buffers (torch is only the allocator here)
-    pin = {k: torch.empty(n, dtype=torch.float64).pin_memory() for k in GAS_FIELDS}
-    for k in GAS_FIELDS:
-        pin[k].numpy()[:] = getattr(b, k)
-    hb = Bodies(*[pin[k].numpy() for k in GAS_FIELDS])
-    out_pin = {k: torch.empty(n, dtype=torch.float64).pin_memory() for k in GAS_FIELDS}
-    ob = Bodies(*[out_pin[k].numpy() for k in GAS_FIELDS])
-
-    e = Engine(p, device=local)
-    if world > 1:
-        from summersph_b200.parallel import init_comm, torch_broadcast_bytes
-        init_comm(e, rank, world, torch_broadcast_bytes)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def allmax(v):
+        tv = torch.tensor([v], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tv, op=dist.ReduceOp.MAX)
+        return float(tv.item())
+
+    def allgather(v):
+        tv = torch.tensor([v], dtype=torch.float64, device="cuda")
+        if world == 1:
+            return [float(v)]
+        out = [torch.zeros_like(tv) for _ in range(world)]
+        dist.all_gather(out, tv)
+        return [float(x.item()) for x in out]
+
+    check = None
+    if world > 1 and not args.no_check:
+        check = multi_gpu_check(p, local, rank, world, dist, torch)
+
     # ---- device-resident throughput ("value") ---------------------------------------------------------
-    e.upload(hb, s)
-    dt, t = 0.01, 0.0
-    for _ in range(args.warmup):
-        dt, t = e.step(dt, t)
-    stage_acc = {}
-    cons_first = e.conserved() if args.drift else None      # builds / reuses the tree; never changes a later step
-    sampler = ClockSampler(local)
-    barrier()
-    if rank == 0:
-        sampler.start()
-    l0 = e.launch_count()
-    e.timer_start()
-    for _ in range(args.steps):
-        dt, t = e.step(dt, t)
-        for k, v in e.stage_times().items():
-            stage_acc[k] = stage_acc.get(k, 0.0) + v
-    ms = e.timer_stop()
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    launches = e.launch_count() - l0
+    e = engine_for(p, local, rank, world)
+    e.ics_disc(n, seed=20251018)                 # generated on the device: every rank its own rows under the decomposition
+    cons = {}
+    sampler = ClockSampler(local) if rank == 0 else None
+    want_drift = args.drift and decomp == 0      # sph_conserved walks the single-rank / replicated tree
+    ms, stage_acc, launches, clocks, (dt, t) = timed_run(e, n, args.steps, args.warmup, barrier, sampler,
+                                                         before=(lambda: cons.update(first=e.conserved())) if want_drift else None)
+    per_rank = allgather(ms)
+    per_rank_walk = [v / args.steps for v in allgather(stage_acc.get("density", 0) + stage_acc.get("gravity", 0) + stage_acc.get("sph", 0))]
+    per_rank_comm = [v / args.steps for v in allgather(stage_acc.get("comm", 0))]
+    per_rank_build = [v / args.steps for v in allgather(stage_acc.get("keys", 0) + stage_acc.get("sort", 0) + stage_acc.get("tree", 0))]
+    ms = allmax(ms)
+    value = n * args.steps / (ms * 1e-3)
+    counters_exec = e.counters()                 # what the last timed step actually tested (exact-zero pairs culled before counting)
+    dstats = e.domain_stats()
+    dstats_all = {k: [int(x) for x in allgather(float(dstats[k]))] for k in ("own", "halo", "let_nodes")} if decomp else None
+    state_hash, state_sums = e.state_hash()
     drift = None
-    if args.drift:
+    if want_drift:
         from summersph_b200._abi import drift_report
-        drift = drift_report(cons_first, e.conserved())
+        drift = drift_report(cons["first"], e.conserved())
     # interaction counts of the reference algorithm (every leaf-box candidate): one untimed evaluation with exact
-    # counters on the state the timed steps ended in; the timed steps cull exact-zero pairs before counting them
+    # counters on the state the timed steps ended in
     e.set_exact_counters(True); e.evaluate(); counters = e.counters(); e.set_exact_counters(False)
     n_now, ns_now = e.sizes()
-    tm = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    per_rank = [ms]
-    if world > 1:
-        allms = [torch.zeros_like(tm) for _ in range(world)]
-        dist.all_gather(allms, tm)
-        per_rank = [float(x.item()) for x in allms]
-        walk = torch.tensor([stage_acc.get("density", 0) + stage_acc.get("gravity", 0) + stage_acc.get("sph", 0)], dtype=torch.float64, device="cuda")
-        allw = [torch.zeros_like(walk) for _ in range(world)]
-        dist.all_gather(allw, walk)
-        per_rank_walk = [float(x.item()) / args.steps for x in allw]
-        comm = torch.tensor([stage_acc.get("comm", 0)], dtype=torch.float64, device="cuda")
-        allc = [torch.zeros_like(comm) for _ in range(world)]
-        dist.all_gather(allc, comm)
-        per_rank_comm = [float(x.item()) / args.steps for x in allc]
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    ms = float(tm.item())
-    value = n * args.steps / (ms * 1e-3)
 
     # ---- end to end through the C-ABI with host buffers ("e2e") -----------------------------------------
-    # The host owns the state between steps (what the Fortran loop does): every step uploads the state it
-    # got back from the previous step, advances it, and downloads the result.
-    e2e_steps = 0 if args.no_e2e else max(1, min(args.steps, 3))
-    hs = Sinks.empty(e.sizes()[1])
+    # The host owns the state between steps (what the Fortran loop does): every step uploads the state it got back from
+    # the previous step, advances it and downloads the result.  Under the decomposition each rank moves only the rows it
+    # owns (sph_upload_local / sph_download_local); in the replicated form every rank moves all rows.
+    e2e_steps = 0 if args.no_e2e else args.steps
+    e2e_value = None; h2d = d2h = 0
     if e2e_steps:
-        e.download(into=(ob, hs))             # current state -> pinned host (untimed)
-    dt2, t2 = dt, t
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        nb_now = e.sizes()[0]
-        view = Bodies(*[getattr(ob, k)[:nb_now] for k in GAS_FIELDS])
-        e.upload(view, hs)                    # H2D of the step's inputs from pinned host memory
-        dt2, t2 = e.step(dt2, t2)
-        hs = Sinks.empty(e.sizes()[1])
-        e.download(into=(ob, hs))             # D2H of the step's result (the new state)
-    barrier()
-    e2e_sec = time.perf_counter() - t0
-    te = torch.tensor([e2e_sec], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = n * e2e_steps / float(te.item()) if e2e_steps else None
-    h2d = 10 * 8 * n + 8 * 8 * len(s)
-    d2h = 10 * 8 * n + 8 * 8 * len(s)
+        n_loc = e.local_size() if decomp else n_now
+        capn = int(n_loc * 1.25) + 4096
+        pin = {k: torch.empty(capn, dtype=torch.float64).pin_memory() for k in GAS_FIELDS}
+        num = torch.empty(capn, dtype=torch.int32).pin_memory()
+        hs = Sinks.empty(ns_now)
+        def views(m):
+            return Bodies(*[pin[k].numpy()[:m] for k in GAS_FIELDS])
+        if decomp:
+            numbers, _ = e.download_local(into=views(n_loc)); num.numpy()[:n_loc] = numbers
+            hs = e.sinks_only()
+        else:
+            e.download(into=(views(n_loc), hs))
+        dt2, t2 = dt, t
+        moved = 0
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            if decomp:
+                e.upload_local(n, views(n_loc), hs, numbers=num.numpy()[:n_loc])
+            else:
+                e.upload(views(n_loc), hs)
+            dt2, t2 = e.step(dt2, t2)
+            if decomp:
+                n_loc = e.local_size()
+                if n_loc > capn:
+                    raise SystemExit("e2e: pinned buffers too small for this rank's rows")
+                numbers, _ = e.download_local(into=views(n_loc)); num.numpy()[:n_loc] = numbers
+                hs = e.sinks_only()
+            else:
+                n_loc = e.sizes()[0]
+                hs = Sinks.empty(e.sizes()[1])
+                e.download(into=(views(n_loc), hs))
+            moved += n_loc
+        barrier()
+        e2e_sec = allmax(time.perf_counter() - t0)
+        e2e_value = n * e2e_steps / e2e_sec
+        rows = sum(allgather(float(moved))) / e2e_steps            # rows moved per step, all ranks
+        h2d = int(rows * (10 * 8 + (4 if decomp else 0)) + world * 8 * 8 * len(hs))
+        d2h = h2d
+
+    # ---- BASELINE configs[4]: the 64M-particle disc, a short run of the same engine (sub-record) ----------------
+    config5 = None
+    if not args.no_config5 and n != N_CONFIG5:
+        e.close(); e = None
+        torch.cuda.empty_cache()
+        try:
+            e5 = engine_for(p, local, rank, world)
+            e5.ics_disc(N_CONFIG5, seed=20251018)
+            ms5, st5, _, _, _ = timed_run(e5, N_CONFIG5, 2, 2, barrier)
+            ms5 = allmax(ms5)
+            h5, sums5 = e5.state_hash()
+            config5 = {"workload": f"Keplerian disc {N_CONFIG5} gas + 1 sink (BASELINE configs[4])", "particles": N_CONFIG5, "n_gpus": world, "steps": 2, "warmup": 2,
+                       "ms_per_step": ms5 / 2, "value": N_CONFIG5 * 2 / (ms5 * 1e-3), "unit": "particle-steps/s",
+                       "stage_ms_per_step": {k: v / 2 for k, v in st5.items()}, "state_sums": sums5,
+                       "domain_stats": e5.domain_stats() if decomp else None}
+            e5.close()
+        except Exception as ex:                  # never lose the main line to the sub-run
+            config5 = {"error": str(ex)[:300]}
 
     if rank == 0:
         peaks, peak_src = measured_peaks()
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        # dominant kernel = the stage with the largest share of the step
         per_launch = {"sph": (BYTES_SPH_PER_LAUNCH, "k_force"), "density": (BYTES_DENSITY_PER_LAUNCH, "k_density"), "gravity": (BYTES_GRAVITY_PER_LAUNCH, "k_gravity")}
         dom = max(per_launch, key=lambda k: stage_acc.get(k, 0.0))
         dom_ms = stage_acc[dom] / (2 * args.steps)           # two launches per step
-        achieved = per_launch[dom][0] * (n / world) / (dom_ms * 1e-3) / 1e9       # per-rank launch processes n/world targets
-        traffic = None
+        achieved = per_launch[dom][0] * (n / world) / (dom_ms * 1e-3) / 1e9       # one rank's launch processes n / world targets
+        traffic = None; traffic_note = "no ncu capture at this particle count in profiles/"
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-            # ncu capture was taken at tr["particles"]; DRAM traffic of the walk kernels scales with N
-            traffic = tr["dram_bytes_per_launch"][per_launch[dom][1]] / tr["particles"] * n / max(world, 1)
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+            if int(tr["particles"]) == n and world == 1:
+                traffic = tr["dram_bytes_per_launch"][per_launch[dom][1]]; traffic_note = tr.get("note", "")
         except Exception:
             pass
-        fp64_peak = e.fp64_peak() * world
-        flops_eval = (counters["density_candidates"] * FLOPS["density_candidate"] + counters["sph_pairs"] * FLOPS["sph_pair"]
-                      + counters["grav_opened"] * FLOPS["grav_opened"] + counters["grav_accepted"] * FLOPS["grav_accepted"]
-                      + n * ns_now * FLOPS["sink_gas"])
-        step_flops = 2.0 * flops_eval
+        if e is None:
+            from summersph_b200.engine import Engine
+            e = Engine(p.copy(decomposition=0), device=local)
+        fp64_one = e.fp64_peak()
+        fp64_peak = fp64_one * world
+        def flops(c):
+            return (c["density_candidates"] * FLOPS["density_candidate"] + c["sph_pairs"] * FLOPS["sph_pair"]
+                    + c["grav_opened"] * FLOPS["grav_opened"] + c["grav_accepted"] * FLOPS["grav_accepted"] + n * ns_now * FLOPS["sink_gas"])
+        step_flops = 2.0 * flops(counters)
+        step_flops_exec = 2.0 * flops(counters_exec)
+        dom_flops = {"gravity": counters["grav_opened"] * FLOPS["grav_opened"] + counters["grav_accepted"] * FLOPS["grav_accepted"] + n * ns_now * FLOPS["sink_gas"],
+                     "sph": counters["sph_pairs"] * FLOPS["sph_pair"], "density": counters["density_candidates"] * FLOPS["density_candidate"]}[dom]
+        dom_tflops = dom_flops / world / (dom_ms * 1e-3) / 1e12
+        sec = ms / args.steps * 1e-3
         line = {
             "metric": "particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"Keplerian disc {n} gas + 1 central sink, variable h, eta 1.2, theta 0.5 (BASELINE configs[3])",
-                       "particles": n, "mode": "variable_h", "parallelism": f"{world} rank(s)",
+                       "particles": n, "mode": "variable_h",
+                       "parallelism": f"{world} rank(s)" + ("" if world == 1 else (", Morton-ordered domains + halo exchange + top-tree all-gather" if decomp else ", replicated state + Morton-sliced walks")),
+                       "ics": "generated on the device (sph_ics_disc, counter-based, seed 20251018)",
                        "l2": "inputs (>=1.3 GB state + tree) exceed the 126 MB L2; no flush needed"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "what": "sph_upload (pinned host SoA) + sph_step + sph_download (ascending number order) per step"},
+                    "steps": e2e_steps, "what": ("sph_upload_local + sph_step + sph_download_local per step: every rank moves the rows it owns (pinned host SoA + their numbers)" if decomp else
+                                                 "sph_upload (pinned host SoA) + sph_step + sph_download (ascending number order) per step")},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": per_launch[dom][1], "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": traffic, "traffic_note": "bytes/launch; dram__bytes_read+write from the 2M-particle ncu capture scaled linearly to this N", "peak_source": peak_src,
-                         "algorithmic_bytes_per_particle_per_launch": per_launch[dom][0], "launch_ms": dom_ms,
-                         "note": "walk kernels are FP64-pipe / latency bound (SURVEY.md §8(d)); see fp64"},
-            "fp64": {"achieved_tflops": step_flops / (ms / args.steps * 1e-3) / 1e12, "peak_tflops": fp64_peak,
-                     "frac": step_flops / (ms / args.steps * 1e-3) / 1e12 / fp64_peak, "algorithmic_flops_per_step": step_flops,
-                     "how": "reference-expression flop counts x interaction counters (SURVEY.md §8(d)); peak = in-library FMA probe"},
-            "hbm_step": {"achieved": BYTES_PER_PARTICLE_STEP * n / (ms / args.steps * 1e-3) / 1e9, "peak": hbm_peak,
-                         "frac": BYTES_PER_PARTICLE_STEP * n / (ms / args.steps * 1e-3) / 1e9 / hbm_peak, "unit": "GB/s"},
+            "roofline": {"bound": "fp64", "kernel": per_launch[dom][1], "achieved": dom_tflops, "peak": fp64_one, "unit": "TFLOP/s", "frac": dom_tflops / fp64_one,
+                         "peak_source": "in-library FP64 FMA probe (sph_fp64_peak) run at the end of this process; MEASURED_PEAKS.json holds no FP64 figure",
+                         "launch_ms": dom_ms, "algorithmic_flops_per_launch": dom_flops / world,
+                         "hbm": {"achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "peak_source": peak_src,
+                                 "algorithmic_bytes_per_particle_per_launch": per_launch[dom][0]},
+                         "traffic": traffic, "traffic_note": traffic_note,
+                         "note": "the walk kernels re-read their sources from L1 / L2 / shared memory: the FP64 pipe binds, the HBM fraction is given beside it (SURVEY.md 8(d))"},
+            "fp64": {"achieved_tflops": step_flops / sec / 1e12, "peak_tflops": fp64_peak, "frac": step_flops / sec / 1e12 / fp64_peak,
+                     "algorithmic_flops_per_step": step_flops,
+                     "executed": {"flops_per_step": step_flops_exec, "achieved_tflops": step_flops_exec / sec / 1e12, "frac": step_flops_exec / sec / 1e12 / fp64_peak,
+                                  "what": "the same per-interaction flop counts on the pairs the timed kernels actually tested (exact-zero pairs are culled before any FP64 work)"},
+                     "how": "reference-expression flop counts x interaction counters (SURVEY.md 8(d)): 44 per density candidate, 173 per unordered pair, 13 / 35 per opened / accepted node, 20 per sink-gas pair"},
+            "hbm_step": {"achieved": BYTES_PER_PARTICLE_STEP * n / sec / 1e9, "peak": hbm_peak * world,
+                         "frac": BYTES_PER_PARTICLE_STEP * n / sec / 1e9 / (hbm_peak * world), "unit": "GB/s"},
             "stage_ms_per_step": {k: v / args.steps for k, v in stage_acc.items()},
             "per_rank_ms_per_step": [v / args.steps for v in per_rank],
-            "counters": counters,
+            "counters": counters, "counters_executed": counters_exec,
+            "state_hash": f"{state_hash:016x}", "state_sums": state_sums,
         }
-        if drift is not None:
-            line["drift"] = dict(drift, over_steps=args.steps)
         if world > 1:
             line["per_rank_walk_ms_per_step"] = per_rank_walk
             line["per_rank_comm_ms_per_step"] = per_rank_comm
+            line["per_rank_build_ms_per_step"] = per_rank_build
+            line["multi_gpu_check"] = check
+            if dstats_all:
+                line["domain_stats"] = dstats_all
+        if drift is not None:
+            line["drift"] = dict(drift, over_steps=args.steps)
+        if config5 is not None:
+            line["config5"] = config5
         if not args.no_cpu_baseline and world == 1:
-            threads = os.cpu_count() or 1
+            threads = min(REF_THREADS, os.cpu_count() or 1)
             nb = args.cpu_baseline_particles
-            rate, sec = cpu_reference_rate(nb, 1, 0, threads)
+            rate, sec_c = cpu_reference_rate(nb, 1, 0, threads)
             line["cpu_baseline"] = {"value": rate, "unit": "particle-steps/s", "cores": threads, "kind": "port",
-                                    "sample": f"{nb}-particle Keplerian disc (same generator/seed), 1 full step, oracle port with OpenMP; restatement, not gfortran"}
+                                    "sample": f"{nb}-particle Keplerian disc (same parameters), 1 full step, oracle port with OpenMP; restatement, not gfortran (no Fortran compiler on the box: profiles/r2_fortran_probe_gpubox.log)"}
         print(json.dumps(line), flush=True)
-    e.close()
+    if e is not None:
+        e.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -132,10 +132,12 @@ int sph_upload(sph_ctx* ctx, int64_t n_gas,
                const double* svx, const double* svy, const double* svz,
                const double* sm, const double* srad);
 
-/* Domain decomposition only (params.decomposition = 1 after sph_comm_init*): this rank hands over rows
- * [id_first, id_first + n_local) of the n_global gas rows (any partition of the file between the ranks; the first tree
- * build sends every particle to the rank that owns its Morton range).  Sinks are replicated: pass the same on every rank. */
-int sph_upload_local(sph_ctx* ctx, int64_t n_global, int64_t id_first, int64_t n_local,
+/* Domain decomposition only (params.decomposition = 1 after sph_comm_init*): this rank hands over n_local of the gas
+ * rows: rows [id_first, id_first + n_local) when `number` is NULL, else the rows with the given 0-based numbers (what
+ * sph_download_local returned: a host that owns the state between steps).  n_global = size of the number space (rows
+ * of the original file).  Any partition between the ranks: the first tree build sends every particle to the rank that
+ * owns its Morton range.  Sinks are replicated: pass the same on every rank. */
+int sph_upload_local(sph_ctx* ctx, int64_t n_global, int64_t id_first, const int32_t* number, int64_t n_local,
                      const double* x, const double* y, const double* z,
                      const double* vx, const double* vy, const double* vz,
                      const double* u, const double* m, const double* alpha, const double* h,
@@ -150,6 +152,14 @@ int sph_local_size(sph_ctx* ctx, int64_t* n_local);
 int sph_download_local(sph_ctx* ctx, int32_t* number,
                        double* x, double* y, double* z, double* vx, double* vy, double* vz,
                        double* u, double* m, double* alpha, double* h);
+
+/* Seeded synthetic start generated on the device (replaces what Disc_ICs.py:1-41 sketches): n gas particles of a
+ * uniform-surface-density Keplerian disc between r_in and r_out (z ~ N(0, (aspect r)^2) clipped at 3 sigma, v_phi =
+ * sqrt(G m_star / r), m = m_disc / n, the given u and alpha, h = eta (m / rho)^(1/3)) around one sink of mass m_star at
+ * the origin (radius = params.sink_radius).  Row i depends only on (seed, i): under the domain decomposition every rank
+ * generates its own rows.  Equivalent to sph_upload of those rows. */
+int sph_ics_disc(sph_ctx* ctx, int64_t n_gas, uint64_t seed, double r_in, double r_out, double aspect, double m_star,
+                 double m_disc, double u, double alpha, double eta);
 
 /* One evaluation (tree + density + EOS + find_forces) on the current state, no integration:
  * the parity hook. `mask` selects phases (SPH_EVAL_*); rates are zeroed first (F:824). */
@@ -195,6 +205,16 @@ int sph_download_neighbours(sph_ctx* ctx, int32_t* count, uint64_t* hash,
                             int64_t* offsets, int32_t* list, int64_t list_cap);
 
 int sph_counters(sph_ctx* ctx, sph_counts* out);
+
+/* Order-independent 64-bit fingerprint of the resident state (gas: number + the bit patterns of the ten fields; sinks):
+ * equal fingerprints <=> bit-identical states, whatever the storage order or the number of ranks.  sums5 (may be NULL):
+ * sum m, sum m|x|^2, sum m|v|^2, sum m u, particle count - for comparisons with a tolerance.  Collective under the
+ * domain decomposition. */
+int sph_state_hash(sph_ctx* ctx, uint64_t* hash, double* sums5);
+
+/* Decomposition figures of the most recent tree build: out8 = { 1 if Morton domains are on, own particles, halo particles,
+ * own walk groups, halo walk groups, locally-essential-tree nodes pulled from the peers, top-tree slots, global particles }. */
+int sph_domain_stats(sph_ctx* ctx, int64_t* out8);
 
 /* density_candidates / sph_pairs count every pair that passes the reference's leaf-box test (F:443 | V:479),
  * most of which only add exact zeros (q > 2, F:112).  By default the walks drop sources that lie beyond

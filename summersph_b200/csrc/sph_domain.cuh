@@ -330,3 +330,25 @@ __global__ void k_dd_create_apply(const double* __restrict__ in8, SinkArrays S, 
   if (spin) spin[ns] = spin[SPH_MAX_SINKS + ns] = spin[2 * SPH_MAX_SINKS + ns] = 0.0;
   sc->n_sink = ns + 1;
 }
+
+// ---- state fingerprint -----------------------------------------------------------------------------------------------------
+// Order-independent 64-bit fingerprint of the gas state: sum over particles of a hash chain over (number, the bit
+// patterns of x y z vx vy vz u m alpha h), so that two runs hold bit-identical states iff (up to hash collisions) their
+// fingerprints agree - whatever the storage order and however the particles are spread over ranks.  sums[0..4] =
+// sum m, sum m |x|^2, sum m |v|^2, sum m u, count (plain FP64 atomics: compare with a tolerance, not bit for bit).
+__global__ void k_state_hash(int n, StateArrays s, unsigned long long* hash, double* sums) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long hv = 0ull; double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, a4 = 0.0;
+  if (i < n) {
+    const double f[10] = {s.x[i], s.y[i], s.z[i], s.vx[i], s.vy[i], s.vz[i], s.u[i], s.m[i], s.alpha[i], s.h[i]};
+    hv = mix64((unsigned long long)(unsigned)s.id[i]);
+    for (int k = 0; k < 10; ++k) hv = mix64(hv ^ (unsigned long long)__double_as_longlong(f[k]));
+    a0 = f[7]; a1 = f[7] * (f[0] * f[0] + f[1] * f[1] + f[2] * f[2]); a2 = f[7] * (f[3] * f[3] + f[4] * f[4] + f[5] * f[5]); a3 = f[7] * f[6]; a4 = 1.0;
+  }
+  for (int o = 16; o > 0; o >>= 1) { hv += __shfl_xor_sync(FULL_MASK, hv, o); }
+  a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3); a4 = warp_sum(a4);
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(hash, hv);
+    atomicAdd(sums, a0); atomicAdd(sums + 1, a1); atomicAdd(sums + 2, a2); atomicAdd(sums + 3, a3); atomicAdd(sums + 4, a4);
+  }
+}

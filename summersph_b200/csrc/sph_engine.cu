@@ -24,6 +24,7 @@
 #include "sph_conserved.cuh"
 #include "sph_image.cuh"
 #include "sph_domain.cuh"
+#include "sph_ics.cuh"
 
 namespace {
 
@@ -1102,7 +1103,7 @@ int sph_comm_init_host(sph_ctx* c, int32_t rank, int32_t n_ranks, const char* na
 
 // n_local rows starting at global number id_first out of n_global (single rank / replicated: all of them)
 static int upload_impl(sph_ctx* c, int64_t n_global, int64_t id_first, int64_t n, const double* const* src,
-                       int32_t ns, const double* const* ssrc, const double* srad) {
+                       int32_t ns, const double* const* ssrc, const double* srad, bool gas_on_device = false) {
   cudaSetDevice(c->device);
   c->dd = c->n_ranks > 1 && c->p.decomposition == 1;
   int64_t want = n;
@@ -1114,7 +1115,7 @@ static int upload_impl(sph_ctx* c, int64_t n_global, int64_t id_first, int64_t n
   int r = ensure_capacity(c, want); if (r) return r;
   c->n_halo = 0; c->ng_halo = 0; c->dd_info.clear();
   c->n = n; c->n_upload = n_global; c->n_global = n_global; c->cur = 0; c->tree_valid = false; c->pos_moved = true;
-  for (int f = 0; f < 10; ++f) {
+  for (int f = 0; f < 10 && !gas_on_device; ++f) {
     if (src[f]) { if (n > 0) CK(cudaMemcpyAsync(c->st[0][f], src[f], (size_t)n * 8, cudaMemcpyHostToDevice, c->stream)); }
     else if (f == 8) CK(cudaMemsetAsync(c->st[0][f], 0, (size_t)std::max<int64_t>(n, 1) * 8, c->stream));            // alpha := 0, F:681
     else { std::vector<double> hv((size_t)std::max<int64_t>(n, 1), c->p.h_fixed); CK(cudaMemcpyAsync(c->st[0][f], hv.data(), hv.size() * 8, cudaMemcpyHostToDevice, c->stream)); CK(cudaStreamSynchronize(c->stream)); }
@@ -1154,20 +1155,41 @@ int sph_upload(sph_ctx* c, int64_t n, const double* x, const double* y, const do
   return upload_impl(c, n, first, cnt, src, ns, ssrc, srad);
 }
 
-int sph_upload_local(sph_ctx* c, int64_t n_global, int64_t id_first, int64_t n_local, const double* x, const double* y, const double* z,
+int sph_ics_disc(sph_ctx* c, int64_t n, uint64_t seed, double r_in, double r_out, double aspect, double m_star, double m_disc,
+                 double u, double alpha, double eta) {
+  if (!c) return SPH_ERR_ARG;
+  if (n < 2 || n > 0x7fffffff || !(r_out > r_in) || !(r_in > 0.0) || !(m_star > 0.0)) { c->err = "bad disc parameters"; return SPH_ERR_ARG; }
+  int64_t first = 0, cnt = n;
+  if (c->n_ranks > 1 && c->p.decomposition == 1) { first = n * c->rank / c->n_ranks; cnt = n * (c->rank + 1) / c->n_ranks - first; }
+  const double* none[10] = {};
+  const double zero = 0.0;
+  const double* ssrc[7] = {&zero, &zero, &zero, &zero, &zero, &zero, &m_star};
+  int r = upload_impl(c, n, first, cnt, none, 1, ssrc, nullptr, true); if (r) return r;
+  IcsDisc P{r_in, r_out, aspect, m_star, m_disc, u, alpha, eta, c->dp.G};
+  double** st = c->st[0];
+  if (cnt > 0) LAUNCH(k_ics_disc, cdiv(cnt, 256), 256, 0, (long long)n, (long long)first, (int)cnt, seed, P, st[0], st[1], st[2], st[3], st[4], st[5], st[6], st[7], st[8], st[9]);
+  if (!c->dp.variable_h && cnt > 0) { std::vector<double> hv((size_t)cnt, c->p.h_fixed); CK(cudaMemcpyAsync(st[9], hv.data(), hv.size() * 8, cudaMemcpyHostToDevice, c->stream)); }
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaGetLastError());
+  return SPH_OK;
+}
+
+int sph_upload_local(sph_ctx* c, int64_t n_global, int64_t id_first, const int32_t* number, int64_t n_local, const double* x, const double* y, const double* z,
                      const double* vx, const double* vy, const double* vz, const double* u, const double* m,
                      const double* alpha, const double* h, int32_t ns,
                      const double* sx, const double* sy, const double* sz, const double* svx, const double* svy, const double* svz,
                      const double* sm, const double* srad) {
   if (!c) return SPH_ERR_ARG;
   if (!(c->n_ranks > 1 && c->p.decomposition == 1)) { c->err = "sph_upload_local needs the domain decomposition (params.decomposition = 1 and a communicator)"; return SPH_ERR_STATE; }
-  if (n_global < 2 || n_local < 0 || id_first < 0 || id_first + n_local > n_global || n_global > 0x7fffffff) { c->err = "bad row range"; return SPH_ERR_ARG; }
+  if (n_global < 2 || n_local < 0 || id_first < 0 || (!number && id_first + n_local > n_global) || n_local > n_global || n_global > 0x7fffffff) { c->err = "bad row range"; return SPH_ERR_ARG; }
   if (n_local > 0 && (!x || !y || !z || !vx || !vy || !vz || !u || !m)) { c->err = "bad particle arrays"; return SPH_ERR_ARG; }
   if (ns < 0 || ns > SPH_MAX_SINKS - 8) { c->err = "too many sinks"; return SPH_ERR_ARG; }
   if (c->dp.variable_h && !h && n_local > 0) { c->err = "variable-h mode needs the smoothing-length column"; return SPH_ERR_ARG; }
   const double* src[10] = {x, y, z, vx, vy, vz, u, m, alpha, c->dp.variable_h ? h : nullptr};
   const double* ssrc[7] = {sx, sy, sz, svx, svy, svz, sm};
-  return upload_impl(c, n_global, id_first, n_local, src, ns, ssrc, srad);
+  int r = upload_impl(c, n_global, id_first, n_local, src, ns, ssrc, srad); if (r) return r;
+  if (number && n_local > 0) { CK(cudaMemcpyAsync(c->id[0], number, (size_t)n_local * 4, cudaMemcpyHostToDevice, c->stream)); CK(cudaStreamSynchronize(c->stream)); }
+  return SPH_OK;
 }
 
 int sph_evaluate(sph_ctx* c, int32_t mask) {
@@ -1234,7 +1256,9 @@ int sph_download(sph_ctx* c, double* x, double* y, double* z, double* vx, double
   if (!c) return SPH_ERR_ARG;
   cudaSetDevice(c->device);
   int r;
-  if (c->dd) {      // every rank receives all rows (tests, saves of small runs); production hosts use sph_download_local
+  const bool any_gas = x || y || z || vx || vy || vz || u || m || alpha || h;
+  if (!any_gas) {}
+  else if (c->dd) {      // every rank receives all rows (tests, saves of small runs); production hosts use sph_download_local
     if ((r = dd_prepare_download(c))) return r;
     double* dst[10] = {x, y, z, vx, vy, vz, u, m, alpha, h};
     for (int f = 0; f < 10; ++f) if ((r = dd_fetch_ordered(c, DS_ST + f, 3, dst[f]))) return r;
@@ -1247,6 +1271,37 @@ int sph_download(sph_ctx* c, double* x, double* y, double* z, double* vx, double
   const double* ss[8] = {c->S.x, c->S.y, c->S.z, c->S.vx, c->S.vy, c->S.vz, c->S.m, c->S.radius};
   for (int k = 0; k < 8; ++k) if ((r = fetch_sink(c, ss[k], sd[k]))) return r;
   CK(cudaStreamSynchronize(c->stream));
+  return SPH_OK;
+}
+
+int sph_state_hash(sph_ctx* c, uint64_t* hash, double* sums5) {
+  if (!c || !hash) return SPH_ERR_ARG;
+  cudaSetDevice(c->device);
+  unsigned long long* d = nullptr; DA(d, 8);
+  CK(cudaMemsetAsync(d, 0, 64, c->stream));
+  const int n = (int)c->n;
+  if (n > 0) LAUNCH(k_state_hash, cdiv(n, 256), 256, 0, n, state_of(c, c->cur), d, (double*)(d + 1));
+  if (c->dd) {      // the domains' partial fingerprints add up (the hash is a sum; the sums are compared with a tolerance)
+    { int r_ = allreduce(c, d, 1, NC_UINT64, NC_SUM); if (r_) { cudaFree(d); return r_; } }
+    { int r_ = allreduce(c, d + 1, 5, NC_FLOAT64, NC_SUM); if (r_) { cudaFree(d); return r_; } }
+  }
+  unsigned long long h[8];
+  CK(cudaMemcpyAsync(h, d, 64, cudaMemcpyDeviceToHost, c->stream));
+  std::vector<double> sk((size_t)SPH_MAX_SINKS * 8);
+  CK(cudaMemcpyAsync(sk.data(), c->sink_buf, sk.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  cudaFree(d);
+  unsigned long long hv = h[0];
+  for (int q = 0; q < c->n_sink; ++q) { unsigned long long t = mix64(0x5151ull + q); for (int k = 0; k < 8; ++k) { unsigned long long b; std::memcpy(&b, &sk[(size_t)k * SPH_MAX_SINKS + q], 8); t = mix64(t ^ b); } hv += t; }
+  *hash = hv;
+  if (sums5) std::memcpy(sums5, h + 1, 40);
+  return SPH_OK;
+}
+
+int sph_domain_stats(sph_ctx* c, int64_t* out8) {
+  if (!c || !out8) return SPH_ERR_ARG;
+  out8[0] = c->dd ? 1 : 0; out8[1] = c->n; out8[2] = c->n_halo; out8[3] = c->dd ? c->ng_own : c->n_groups; out8[4] = c->ng_halo;
+  out8[5] = c->dd_let_used; out8[6] = c->dd_top_n; out8[7] = c->dd ? c->n_global : c->n;
   return SPH_OK;
 }
 

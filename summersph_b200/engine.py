@@ -45,9 +45,12 @@ def load_library(path=None):
     lib.sph_slice_bounds.argtypes = [i32, i32, vp]
     lib.sph_comm_init_host.argtypes = [vp, i32, i32, C.c_char_p]
     lib.sph_upload.argtypes = [vp, i64] + [vp] * 10 + [i32] + [vp] * 8
-    lib.sph_upload_local.argtypes = [vp, i64, i64, i64] + [vp] * 10 + [i32] + [vp] * 8
+    lib.sph_upload_local.argtypes = [vp, i64, i64, vp, i64] + [vp] * 10 + [i32] + [vp] * 8
+    lib.sph_state_hash.argtypes = [vp, C.POINTER(C.c_uint64), vp]
+    lib.sph_domain_stats.argtypes = [vp, vp]
     lib.sph_local_size.argtypes = [vp, C.POINTER(i64)]
     lib.sph_download_local.argtypes = [vp] + [vp] * 11
+    lib.sph_ics_disc.argtypes = [vp, i64, C.c_uint64] + [dbl] * 8
     lib.sph_evaluate.argtypes = [vp, i32]
     lib.sph_step.argtypes = [vp, C.POINTER(dbl), C.POINTER(dbl), C.POINTER(i64), C.POINTER(i32)]
     lib.sph_run_until.argtypes = [vp, dbl, i64, C.POINTER(dbl), C.POINTER(dbl), C.POINTER(i64), C.POINTER(i64), C.POINTER(i32)]
@@ -142,11 +145,28 @@ class Engine:
                                     _p(b.u), _p(b.m), _p(b.alpha), _p(b.h), len(s),
                                     _p(s.x), _p(s.y), _p(s.z), _p(s.vx), _p(s.vy), _p(s.vz), _p(s.m), _p(rad)))
 
-    def upload_local(self, n_global, id_first, b: Bodies, s: Sinks):
-        """Domain decomposition: hand over rows [id_first, id_first + len(b)) of the n_global gas rows (`sph_upload_local`)."""
-        self._ck(self._l.sph_upload_local(self._c, int(n_global), int(id_first), len(b), _p(b.x), _p(b.y), _p(b.z), _p(b.vx), _p(b.vy), _p(b.vz),
+    def state_hash(self):
+        """(fingerprint, sums): `sph_state_hash` - equal fingerprints <=> bit-identical states."""
+        h = C.c_uint64(); sums = np.zeros(5)
+        self._ck(self._l.sph_state_hash(self._c, C.byref(h), _p(sums)))
+        return int(h.value), dict(zip(("mass", "m_x2", "m_v2", "m_u", "count"), sums.tolist()))
+
+    def domain_stats(self):
+        out = np.zeros(8, np.int64)
+        self._ck(self._l.sph_domain_stats(self._c, _p(out)))
+        return dict(zip(("domains", "own", "halo", "own_groups", "halo_groups", "let_nodes", "top_slots", "global"), out.tolist()))
+
+    def upload_local(self, n_global, b: Bodies, s: Sinks, id_first=0, numbers=None):
+        """Domain decomposition: hand over rows [id_first, id_first + len(b)) - or the rows `numbers` - of the
+        n_global gas rows (`sph_upload_local`)."""
+        num = None if numbers is None else np.ascontiguousarray(numbers, dtype=np.int32)
+        self._ck(self._l.sph_upload_local(self._c, int(n_global), int(id_first), _p(num), len(b), _p(b.x), _p(b.y), _p(b.z), _p(b.vx), _p(b.vy), _p(b.vz),
                                           _p(b.u), _p(b.m), _p(b.alpha), _p(b.h), len(s),
                                           _p(s.x), _p(s.y), _p(s.z), _p(s.vx), _p(s.vy), _p(s.vz), _p(s.m), _p(s.radius)))
+
+    def ics_disc(self, n, seed=20251018, r_in=10.0, r_out=100.0, aspect=0.05, m_star=1.0, m_disc=0.01, u=0.25, alpha=0.1, eta=1.2):
+        """Keplerian disc + central sink generated on the device (`sph_ics_disc`); same parameters as ics.keplerian_disc."""
+        self._ck(self._l.sph_ics_disc(self._c, int(n), int(seed), r_in, r_out, aspect, m_star, m_disc, u, alpha, eta))
 
     def local_size(self):
         n = C.c_int64()
@@ -188,6 +208,13 @@ class Engine:
                                       _p(b.alpha), _p(b.h), _p(s.x), _p(s.y), _p(s.z), _p(s.vx), _p(s.vy), _p(s.vz),
                                       _p(s.m), _p(s.radius)))
         return b, s
+
+    def sinks_only(self):
+        """The (replicated) sinks without touching the gas rows."""
+        _, ns = self.sizes()
+        s = Sinks.empty(ns)
+        self._ck(self._l.sph_download(self._c, *([None] * 10), _p(s.x), _p(s.y), _p(s.z), _p(s.vx), _p(s.vy), _p(s.vz), _p(s.m), _p(s.radius)))
+        return s
 
     def diag(self):
         n, ns = self.sizes()

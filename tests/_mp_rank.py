@@ -36,7 +36,10 @@ def main():
                 e.comm_init(rank, world, bytes.fromhex(token))
             else:
                 e.comm_init_host(rank, world, token)
-        e.upload(b, s)
+        if len(sys.argv) > 12 and sys.argv[12] == "devics":
+            e.ics_disc(n, seed=12)           # every rank generates its own rows on the device
+        else:
+            e.upload(b, s)
         dt, t = 0.01, 0.0
         for _ in range(steps):
             dt, t = e.step(dt, t)
