@@ -269,7 +269,7 @@ def main():
                                                          before=(lambda: cons.update(first=e.conserved())) if want_drift else None)
     per_rank = allgather(ms)
     per_rank_walk = [v / args.steps for v in allgather(stage_acc.get("density", 0) + stage_acc.get("gravity", 0) + stage_acc.get("sph", 0))]
-    per_rank_comm = [v / args.steps for v in allgather(stage_acc.get("comm", 0))]
+    per_rank_comm = [v / args.steps for v in allgather(sum(stage_acc.get(k, 0) for k in ("comm", "halo", "let", "migrate")))]
     per_rank_build = [v / args.steps for v in allgather(stage_acc.get("keys", 0) + stage_acc.get("sort", 0) + stage_acc.get("tree", 0))]
     ms = allmax(ms)
     value = n * args.steps / (ms * 1e-3)

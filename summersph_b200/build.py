@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libsph_b200.so")
 SOURCES = ["sph_engine.cu"]
-HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h")))      # every header sph_engine.cu may include
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h", ".inl")))      # every header sph_engine.cu may include
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

@@ -17,7 +17,6 @@
 
 #define DD_MAX_RANKS 8
 #define DD_SAMPLES 2048            // key samples per rank for the splitter search
-#define DD_BOXES 64                // boxes that describe one rank's domain to the others (LET criterion, halo selection)
 #define DD_TOP_CAP 4096            // walk-layout slots reserved for the top tree (straddling cells x children)
 #define DD_MAX_CELLS 512           // straddling cells (<= (ranks - 1) x 22 levels)
 #define DD_PULL_FIELDS 16
@@ -126,73 +125,81 @@ __global__ void k_dd_top_contrib(int ncell, const DDCell* __restrict__ cells, in
   out[t] = rec;
 }
 
-// ---- what the other ranks need to know about this domain: DD_BOXES boxes over contiguous chunks of the own walk groups
-__global__ void k_dd_domain_boxes(int ng_own, const BvhBox* __restrict__ gbox, BvhBox* __restrict__ out) {
-  const int b = blockIdx.x, lane = threadIdx.x;
-  const int g0 = (int)((long long)ng_own * b / DD_BOXES), g1 = (int)((long long)ng_own * (b + 1) / DD_BOXES);
-  float plo[3] = {INFINITY, INFINITY, INFINITY}, phi[3] = {-INFINITY, -INFINITY, -INFINITY};
-  float rlo[3] = {INFINITY, INFINITY, INFINITY}, rhi[3] = {-INFINITY, -INFINITY, -INFINITY};
-  for (int g = g0 + lane; g < g1; g += 32) {
-    const BvhBox q = gbox[g];
-    for (int k = 0; k < 3; ++k) { plo[k] = fminf(plo[k], q.plo[k]); phi[k] = fmaxf(phi[k], q.phi[k]); rlo[k] = fminf(rlo[k], q.rlo[k]); rhi[k] = fmaxf(rhi[k], q.rhi[k]); }
+// ---- what decides "near this domain": the 8-ary BVH over the OWN walk groups (level 0 = the exported group boxes in
+// c->bvh, upper levels in a private array), walked per query with early exit.  A chunk of a Morton range can span a whole
+// parent cell, so a fixed handful of chunk boxes selected most of the other domain; the group boxes themselves are tight.
+struct DDBvh { int nlev; int off[12]; int cnt[12]; };
+template <class PRED>
+__device__ __forceinline__ bool dd_bvh_any(const BvhBox* __restrict__ lvl0, const BvhBox* __restrict__ upper, const DDBvh& bi, PRED pred) {
+  int stack[112]; int sn = 0;                                    // <= 32 top boxes + 7 net pushes per level
+  const int top = bi.nlev - 1;
+  const BvhBox* tb = top == 0 ? lvl0 : upper + bi.off[top];
+  for (int i = 0; i < bi.cnt[top]; ++i) if (pred(tb[i])) { if (top == 0) return true; stack[sn++] = (top << 27) | i; }
+  while (sn > 0) {
+    const int e = stack[--sn]; const int cl = (e >> 27) - 1, idx = e & 0x7ffffff;
+    const BvhBox* cb = cl == 0 ? lvl0 : upper + bi.off[cl];
+    const int c0 = idx * SPH_BVH_FAN, c1 = min(c0 + SPH_BVH_FAN, bi.cnt[cl]);
+    for (int ch = c0; ch < c1; ++ch) if (pred(cb[ch])) { if (cl == 0) return true; if (sn < 112) stack[sn++] = (cl << 27) | ch; else return true; }
   }
-  for (int k = 0; k < 3; ++k) { plo[k] = warp_minf(plo[k]); phi[k] = warp_maxf(phi[k]); rlo[k] = warp_minf(rlo[k]); rhi[k] = warp_maxf(rhi[k]); }
-  if (lane == 0) {
-    BvhBox o;
-    for (int k = 0; k < 3; ++k) { o.plo[k] = plo[k]; o.phi[k] = phi[k]; o.rlo[k] = rlo[k]; o.rhi[k] = rhi[k]; }
-    out[b] = o;
-  }
+  return false;
 }
 
 // ---- locally essential tree -------------------------------------------------------------------------------------------
 // A remote node must have its children here iff some particle of this domain may open it (the reference's test,
-// F:275-278: size / sqrt(d^2 + soft) >= theta).  Conservative form against the DD_BOXES boxes of this domain, with
-// soft = 0 and a 1e-4 margin (the walk's own float screens use 3e-5): a node that fails it is accepted by every run of
-// this rank whatever path the classification takes, so its children are never read.
+// F:275-278: size / sqrt(d^2 + soft) >= theta).  Conservative form against the position boxes of this domain's walk
+// groups, with soft = 0 and a 1e-4 margin (the walk's own float screens use 3e-5): a node that fails it is accepted by
+// every run of this rank whatever path the classification takes, so its children are never read.
 struct DDLetEntry { int slot, owner, rchild, nchild; };    // patch wnodes[slot].child; children live at peer `owner`, index rchild
 struct DDPeerNodes { const WNode* wn[DD_MAX_RANKS]; };
-__device__ __forceinline__ bool dd_may_open(const WNode& w, const BvhBox* __restrict__ dom, double theta2) {
+__device__ __forceinline__ bool dd_may_open(const WNode& w, const BvhBox* __restrict__ lvl0, const BvhBox* __restrict__ upper, const DDBvh& bi, double theta2) {
   const double s2 = w.size * w.size * (1.0 + 1e-4);
-  for (int b = 0; b < DD_BOXES; ++b) {
-    const BvhBox q = dom[b];
-    if (!(q.plo[0] <= q.phi[0])) continue;                       // empty chunk
-    const double ex = fmax(fmax((double)q.plo[0] - w.cx, w.cx - (double)q.phi[0]), 0.0);
-    const double ey = fmax(fmax((double)q.plo[1] - w.cy, w.cy - (double)q.phi[1]), 0.0);
-    const double ez = fmax(fmax((double)q.plo[2] - w.cz, w.cz - (double)q.phi[2]), 0.0);
-    if (s2 >= theta2 * (ex * ex + ey * ey + ez * ez)) return true;
-  }
-  return false;
+  const double cx = w.cx, cy = w.cy, cz = w.cz;
+  return dd_bvh_any(lvl0, upper, bi, [&](const BvhBox& q) {
+    const double ex = fmax(fmax((double)q.plo[0] - cx, cx - (double)q.phi[0]), 0.0);
+    const double ey = fmax(fmax((double)q.plo[1] - cy, cy - (double)q.phi[1]), 0.0);
+    const double ez = fmax(fmax((double)q.plo[2] - cz, cz - (double)q.phi[2]), 0.0);
+    return s2 >= theta2 * (ex * ex + ey * ey + ez * ez);          // empty boxes (plo = +inf) never pass
+  });
 }
 // one BFS level: every frontier entry copies its children block from the owner's node array into a fresh block of the
 // LET area (atomic cursor: the block positions are arbitrary, the child ORDER inside a block is the owner's) and queues
-// the children that may be opened in turn.  ctl: [0] cursor, [1] overflow flag, [2 + 2 * level] / [3 + 2 * level] counts.
+// the children that may be opened in turn.  Eight lanes per entry, one child each: the (remote) node loads of a block
+// are in flight together.  ctl: [0] cursor, [1] overflow flag, [2 + level] frontier counts.
 __global__ void k_dd_let_level(const DDLetEntry* __restrict__ fin, const int* __restrict__ n_in, DDLetEntry* __restrict__ fout, int* n_out,
                                int fcap, int* cursor, int let_end, int* overflow, const __grid_constant__ DDPeerNodes peers,
-                               WNode* __restrict__ wn, const BvhBox* __restrict__ dom, double theta2) {
+                               WNode* __restrict__ wn, const BvhBox* __restrict__ lvl0, const BvhBox* __restrict__ upper, const __grid_constant__ DDBvh bi, double theta2) {
   const int n = *n_in < fcap ? *n_in : fcap;
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+  const int k = threadIdx.x & 7, lane = threadIdx.x & 31;
+  const unsigned gmask = 0xffu << (lane & 24);
+  const int nsub = (gridDim.x * blockDim.x) >> 3;
+  for (int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; t < n; t += nsub) {
     const DDLetEntry e = fin[t];
-    const int d = atomicAdd(cursor, e.nchild);
-    if (d + e.nchild > let_end) { atomicExch(overflow, 1); continue; }
-    const WNode* src = peers.wn[e.owner] + e.rchild;
-    for (int k = 0; k < e.nchild; ++k) {
-      const WNode w = src[k];
-      wn[d + k] = w;                                             // child index still the owner's: patched when (if) it is opened
-      if (w.nchild > 0 && dd_may_open(w, dom, theta2)) {
+    int d = 0;
+    if (k == 0) d = atomicAdd(cursor, e.nchild);
+    d = __shfl_sync(gmask, d, lane & 24);
+    if (d + e.nchild > let_end) { if (k == 0) atomicExch(overflow, 1); continue; }
+    if (k < e.nchild) {
+      const double2* src = reinterpret_cast<const double2*>(peers.wn[e.owner] + e.rchild + k);
+      const double2 a = src[0], b = src[1], c2 = src[2];
+      double2* dst = reinterpret_cast<double2*>(wn + d + k);
+      dst[0] = a; dst[1] = b; dst[2] = c2;                         // child index still the owner's: patched when (if) it is opened
+      WNode w; w.cx = a.x; w.cy = a.y; w.cz = b.x; w.m = b.y; w.size = c2.x; w.child = __double2loint(c2.y); w.nchild = __double2hiint(c2.y);
+      if (w.nchild > 0 && dd_may_open(w, lvl0, upper, bi, theta2)) {
         const int o = atomicAdd(n_out, 1);
         if (o < fcap) fout[o] = DDLetEntry{d + k, e.owner, w.child, w.nchild}; else atomicExch(overflow, 2);
       }
     }
-    wn[e.slot].child = d;
+    __syncwarp(gmask);
+    if (k == 0) wn[e.slot].child = d;
   }
 }
 // top-region entries whose children live on a peer: decide whether this domain may open them (frontier of level 0)
 __global__ void k_dd_let_seed(int n_cand, const DDLetEntry* __restrict__ cand, DDLetEntry* __restrict__ fout, int* n_out,
-                              const WNode* __restrict__ wn, const BvhBox* __restrict__ dom, double theta2) {
+                              const WNode* __restrict__ wn, const BvhBox* __restrict__ lvl0, const BvhBox* __restrict__ upper, const __grid_constant__ DDBvh bi, double theta2) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_cand) return;
   const DDLetEntry e = cand[t];
-  if (dd_may_open(wn[e.slot], dom, theta2)) fout[atomicAdd(n_out, 1)] = e;
+  if (dd_may_open(wn[e.slot], lvl0, upper, bi, theta2)) fout[atomicAdd(n_out, 1)] = e;
 }
 
 // ---- halo ---------------------------------------------------------------------------------------------------------------
@@ -201,29 +208,23 @@ struct DDPeerGroups { int ng[DD_MAX_RANKS]; int goff[DD_MAX_RANKS + 1]; const in
 // ng[self] = 0) can hold a source or a partner of some own particle: its reach box meets a position box of this
 // domain (x_i inside Box(j), F:443 | V:479) or its position box meets a reach box (x_j inside Box(i), the pair loop's
 // other direction).  A superset is harmless: the walks keep their exact tests.
-__global__ void k_dd_halo_mark(const __grid_constant__ DDPeerGroups pg, const BvhBox* __restrict__ dom, unsigned char* __restrict__ flag) {
+__global__ void k_dd_halo_mark(const __grid_constant__ DDPeerGroups pg, const BvhBox* __restrict__ lvl0, const BvhBox* __restrict__ upper,
+                               const __grid_constant__ DDBvh bi, unsigned char* __restrict__ flag, int* __restrict__ hsize) {
   const int G = blockIdx.x * blockDim.x + threadIdx.x;
+  if (G == pg.goff[DD_MAX_RANKS]) hsize[G] = 0;                  // the scan's total lands here
   if (G >= pg.goff[DD_MAX_RANKS]) return;
   int q = 0;
   while (q + 1 < DD_MAX_RANKS && G >= pg.goff[q + 1]) ++q;
   const BvhBox b = pg.box[q][G - pg.goff[q]];
-  bool hit = false;
-  for (int k = 0; k < DD_BOXES && !hit; ++k) {
-    const BvhBox d = dom[k];
-    if (!(d.plo[0] <= d.phi[0])) continue;
-    hit = box_overlap(d.plo, d.phi, b.rlo, b.rhi) || box_overlap(d.rlo, d.rhi, b.plo, b.phi);
-  }
+  const bool hit = dd_bvh_any(lvl0, upper, bi, [&](const BvhBox& d) {
+    return box_overlap(d.plo, d.phi, b.rlo, b.rhi) || box_overlap(d.rlo, d.rhi, b.plo, b.phi); });
   flag[G] = hit ? 1 : 0;
+  hsize[G] = hit ? pg.groups[q][G - pg.goff[q]].y : 0;           // particles this group adds behind the own ones
 }
-// sizes of the selected groups (for the exclusive scan that places their particles behind the own ones)
-__global__ void k_dd_halo_sizes(int nh, const int* __restrict__ list, const __grid_constant__ DDPeerGroups pg, int* __restrict__ size) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k > nh) return;
-  if (k == nh) { size[k] = 0; return; }
-  const int G = list[k];
-  int q = 0;
-  while (q + 1 < DD_MAX_RANKS && G >= pg.goff[q + 1]) ++q;
-  size[k] = pg.groups[q][G - pg.goff[q]].y;
+// [0] selected groups, [1] their particles, [2] 1 when own + halo exceed the rank's capacity (all-reduced afterwards)
+__global__ void k_dd_halo_check(const int* __restrict__ nsel, const int* __restrict__ total, int n_own, int ng_own, long long cap, int* __restrict__ out3) {
+  out3[0] = *nsel; out3[1] = *total;
+  out3[2] = ((long long)n_own + *total > cap || (long long)ng_own + *nsel > cap) ? 1 : 0;
 }
 // one warp per halo group: copy `nf` double fields (+ optionally the ids) of its particles from the owner's arrays;
 // with write_groups the group table entry [ng_own + k] = (local first, size) is written as well
@@ -240,11 +241,16 @@ __global__ void k_dd_pull(int nh, const int* __restrict__ list, const int* __res
   int q = 0;
   while (q + 1 < DD_MAX_RANKS && G >= pg.goff[q + 1]) ++q;
   const int2 sg = pg.groups[q][G - pg.goff[q]];
-  const int first = a.n_own + poff[k];
+  const int first = a.n_own + poff[G];
   if (a.write_groups && lane == 0) groups[a.ng_own + k] = make_int2(first, sg.y);
   if (lane < sg.y) {
-    for (int f = 0; f < a.nf; ++f) a.dst[f][first + lane] = a.src[q][f][sg.x + lane];
-    if (a.with_id) a.dst_id[first + lane] = a.src_id[q][sg.x + lane];
+    double v[DD_PULL_FIELDS]; int vid = 0;                       // all (remote) loads first: they are in flight together
+#pragma unroll
+    for (int f = 0; f < DD_PULL_FIELDS; ++f) if (f < a.nf) v[f] = a.src[q][f][sg.x + lane];
+    if (a.with_id) vid = a.src_id[q][sg.x + lane];
+#pragma unroll
+    for (int f = 0; f < DD_PULL_FIELDS; ++f) if (f < a.nf) a.dst[f][first + lane] = v[f];
+    if (a.with_id) a.dst_id[first + lane] = vid;
   }
 }
 

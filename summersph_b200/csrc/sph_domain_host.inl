@@ -39,11 +39,23 @@ int dd_barrier(sph_ctx* c) {
   return coll_allreduce(c, c->stream, c->d_flag + 3, 1, NC_INT32, NC_SUM);
 }
 
+// Collective error agreement: a capacity failure on one rank must stop every rank at the same point (a rank that
+// returned alone would leave its peers waiting in the next collective).  Returns SPH_OK only when no rank reported `code`.
+int dd_agree(sph_ctx* c, int code, const char* what) {
+  int mine = code, all[DD_MAX_RANKS] = {0};
+  { int r_ = dd_allgather_host(c, &mine, sizeof(int), all); if (r_) return r_; }
+  int worst = 0, who = -1;
+  for (int q = 0; q < c->n_ranks; ++q) if (all[q] && !worst) { worst = all[q]; who = q; }
+  if (!worst) return SPH_OK;
+  if (!code) c->err = std::string("domain decomposition: rank ") + std::to_string(who) + " stopped in " + what + " (see its error); every rank returns";
+  return worst;
+}
+
 int dd_alloc(sph_ctx* c) {               // private scratch of the decomposition (sizes that do not depend on the particle count)
   if (c->dd_samples) return SPH_OK;
   const int R = c->n_ranks;
   DA(c->dd_samples, (size_t)R * DD_SAMPLES); DA(c->dd_counts, R); DA(c->dd_split, R + 1); DA(c->dd_sendoff, R + 1);
-  DA(c->dd_cells, DD_MAX_CELLS); DA(c->dd_contrib, (size_t)DD_MAX_CELLS * 8); DA(c->dd_dom, DD_BOXES);
+  DA(c->dd_cells, DD_MAX_CELLS); DA(c->dd_contrib, (size_t)DD_MAX_CELLS * 8);
   DA(c->dd_let_ctl, 64); DA(c->dd_create8, 8); DA(c->dd_cand, 2);
   if (!c->d_flag) DA(c->d_flag, 4);
   CK(cudaMemset(c->d_flag, 0, 4 * sizeof(int)));
@@ -117,7 +129,20 @@ int dd_halo(sph_ctx* c) {
   StateArrays s = state_of(c, c->cur);
   // own level-0 boxes (from the current reach) and the domain boxes derived from them
   LAUNCH(k_bvh_leaf, cdiv((int64_t)std::max(ng_own, 1) * 32, T), T, 0, ng_own, c->groups, s.x, s.y, s.z, c->lcx, c->lcy, c->lcz, c->reach, c->bvh);
-  LAUNCH(k_dd_domain_boxes, DD_BOXES, 32, 0, ng_own, c->bvh, c->dd_dom);
+  {   // own-only BVH above them (private): what the halo selection and the LET criterion walk
+    if ((size_t)ng_own / 7 + 64 > c->dd_obvh_cap) { c->dd_obvh_cap = (size_t)c->cap / 7 + 64; DA(c->dd_obvh, c->dd_obvh_cap); }
+    DDBvh& ob = c->dd_ob;
+    int cntl = ng_own, offu = 0, l = 0;
+    ob.off[0] = 0; ob.cnt[0] = cntl;
+    const BvhBox* src = c->bvh;
+    while (cntl > 32) {
+      const int np = cdiv(cntl, SPH_BVH_FAN);
+      LAUNCH(k_bvh_up, cdiv(np, T), T, 0, cntl, src, c->dd_obvh + offu);
+      ob.off[l + 1] = offu; ob.cnt[l + 1] = np;
+      src = c->dd_obvh + offu; offu += np; cntl = np; ++l;
+    }
+    ob.nlev = l + 1;
+  }
   { int r_ = dd_barrier(c); if (r_) return r_; }
   DDPeerGroups pg; const int ngp = dd_fill_peer_groups(c, pg);
   c->dd_pg = pg;
@@ -130,22 +155,28 @@ int dd_halo(sph_ctx* c) {
     if (std::max(b1, b2) + 256 > c->cub_bytes) { c->cub_bytes = std::max(b1, b2) + 256; if (c->cub_tmp) cudaFree(c->cub_tmp); c->cub_tmp = nullptr; if (cudaMalloc(&c->cub_tmp, c->cub_bytes) != cudaSuccess) { c->err = "cudaMalloc(cub temp)"; return SPH_ERR_OOM; } }
   }
   int nh = 0, n_halo = 0;
-  if (ngp > 0) {
-    LAUNCH(k_dd_halo_mark, cdiv(ngp, T), T, 0, pg, c->dd_dom, c->dd_halo_flag);
-    size_t bytes = c->cub_bytes;
-    CK(cub::DeviceSelect::Flagged(c->cub_tmp, bytes, cub::CountingInputIterator<int>(0), c->dd_halo_flag, c->dd_halo_list, c->d_nsel, ngp, c->stream));
-    CK(cudaMemcpyAsync(&nh, c->d_nsel, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  {   // one read-back: selected groups, their particles, and whether ANY rank ran out of room (every rank stops together)
+    int h3[3] = {0, 0, 0};
+    CK(cudaMemsetAsync(c->dd_let_ctl + 60, 0, 3 * sizeof(int), c->stream));
+    if (ngp > 0) {
+      LAUNCH(k_dd_halo_mark, cdiv(ngp + 1, T), T, 0, pg, c->bvh, c->dd_obvh, c->dd_ob, c->dd_halo_flag, c->dd_halo_size);
+      size_t bytes = c->cub_bytes;
+      CK(cub::DeviceSelect::Flagged(c->cub_tmp, bytes, cub::CountingInputIterator<int>(0), c->dd_halo_flag, c->dd_halo_list, c->d_nsel, ngp, c->stream));
+      bytes = c->cub_bytes;
+      CK(cub::DeviceScan::ExclusiveSum(c->cub_tmp, bytes, c->dd_halo_size, c->dd_halo_poff, ngp + 1, c->stream));
+      LAUNCH(k_dd_halo_check, 1, 1, 0, c->d_nsel, c->dd_halo_poff + ngp, n_own, ng_own, (long long)c->cap, c->dd_let_ctl + 60);
+    }
+    { int r_ = coll_allreduce(c, c->stream, c->dd_let_ctl + 62, 1, NC_INT32, NC_MAX); if (r_) return r_; }
+    CK(cudaMemcpyAsync(h3, c->dd_let_ctl + 60, sizeof(h3), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    LAUNCH(k_dd_halo_sizes, cdiv(nh + 1, T), T, 0, nh, c->dd_halo_list, pg, c->dd_halo_size);
-    bytes = c->cub_bytes;
-    CK(cub::DeviceScan::ExclusiveSum(c->cub_tmp, bytes, c->dd_halo_size, c->dd_halo_poff, nh + 1, c->stream));
-    CK(cudaMemcpyAsync(&n_halo, c->dd_halo_poff + nh, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-  }
-  if ((int64_t)n_own + n_halo > c->cap || (int64_t)ng_own + nh > c->cap) {
-    c->err = "domain decomposition: own + halo particles (" + std::to_string(n_own) + " + " + std::to_string(n_halo) + ") exceed the rank's capacity " +
-             std::to_string((long long)c->cap) + " (raise SPH_B200_DOMAIN_SLACK)";
-    return SPH_ERR_OOM;
+    nh = h3[0]; n_halo = h3[1];
+    if (h3[2]) {
+      if ((int64_t)n_own + n_halo > c->cap || (int64_t)ng_own + nh > c->cap)
+        c->err = "domain decomposition: own + halo particles (" + std::to_string(n_own) + " + " + std::to_string(n_halo) + ") exceed the rank's capacity " +
+                 std::to_string((long long)c->cap) + " (raise SPH_B200_DOMAIN_SLACK)";
+      else c->err = "domain decomposition: a peer rank's own + halo particles exceed its capacity (see its error); every rank returns";
+      return SPH_ERR_OOM;
+    }
   }
   c->n_halo = n_halo; c->ng_halo = nh; c->n_groups = ng_own + nh;
   if (nh > 0) {
@@ -174,7 +205,8 @@ int dd_halo(sph_ctx* c) {
     }
     bi.nlev = l + 1;
   }
-  { int r_ = dd_barrier(c); if (r_) return r_; }      // nobody changes what a peer may still be pulling
+  // no trailing barrier: what the peers pull (own-region state, leaf cells, group table, level-0 boxes) is next written by
+  // the kick / the next build, and collectives lie in between (the density pass's "lists void" all-reduce is the first)
   return SPH_OK;
 }
 
@@ -188,7 +220,7 @@ int dd_pull_density_fields(sph_ctx* c) {
     add_slot(DS_RHO, c->rho); add_slot(DS_CS, c->cs); add_slot(DS_POR2, c->por2);
     LAUNCH(k_dd_pull, cdiv((int64_t)c->ng_halo * 32, 256), 256, 0, c->ng_halo, c->dd_halo_list, c->dd_halo_poff, c->dd_pg, a, c->groups);
   }
-  return dd_barrier(c);
+  return SPH_OK;      // rho c P/(Omega rho^2) of the own region are next written by calc_smoothing / the next density pass: the sink all-reduce of run_gravity lies in between
 }
 
 // ---- locally essential tree ----------------------------------------------------------------------------------------------
@@ -203,18 +235,18 @@ int dd_build_let(sph_ctx* c, const std::vector<DDLetEntry>& cand) {
   CK(cudaMemcpyAsync(seed, cand.data(), cand.size() * sizeof(DDLetEntry), cudaMemcpyHostToDevice, c->stream));
   CK(cudaStreamSynchronize(c->stream));               // `cand` is a host vector of the caller
   const double theta2 = c->dp.theta * c->dp.theta;
-  LAUNCH(k_dd_let_seed, cdiv((int)cand.size(), T), T, 0, (int)cand.size(), seed, c->dd_let_f[0], c->dd_let_ctl + 2, c->wnodes, c->dd_dom, theta2);
+  LAUNCH(k_dd_let_seed, cdiv((int)cand.size(), T), T, 0, (int)cand.size(), seed, c->dd_let_f[0], c->dd_let_ctl + 2, c->wnodes, c->bvh, c->dd_obvh, c->dd_ob, theta2);
   DDPeerNodes pn; std::memset(&pn, 0, sizeof(pn));
   for (int q = 0; q < c->n_ranks; ++q) if (q != c->rank) pn.wn[q] = dd_peer<const WNode>(c, DS_WN, q);
   const int levels = SPH_KEY_LEVELS + 3;              // a compressed tree is at most lmax <= 21 branching levels deep
   for (int l = 0; l < levels; ++l)
     LAUNCH(k_dd_let_level, c->n_sm * 4, T, 0, c->dd_let_f[l & 1], c->dd_let_ctl + 2 + l, c->dd_let_f[(l + 1) & 1], c->dd_let_ctl + 3 + l, (int)fcap,
-           c->dd_let_ctl, c->dd_let_end, c->dd_let_ctl + 1, pn, c->wnodes, c->dd_dom, theta2);
+           c->dd_let_ctl, c->dd_let_end, c->dd_let_ctl + 1, pn, c->wnodes, c->bvh, c->dd_obvh, c->dd_ob, theta2);
   int ctl[2] = {0, 0};
   CK(cudaMemcpyAsync(ctl, c->dd_let_ctl, sizeof(ctl), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
-  if (ctl[1]) { c->err = "domain decomposition: locally essential tree exceeds its capacity (raise SPH_B200_DOMAIN_SLACK)"; return SPH_ERR_OOM; }
   c->dd_let_used = ctl[0] - c->dd_let_begin;
+  if (ctl[1]) { c->err = "domain decomposition: locally essential tree exceeds its capacity (raise SPH_B200_DOMAIN_SLACK)"; return SPH_ERR_OOM; }
   return SPH_OK;
 }
 
@@ -250,6 +282,7 @@ int dd_build_tree(sph_ctx* c) {
       if (dk.Current() != c->key[0]) std::swap(c->key[0], c->key[1]);
       if (dv.Current() != c->perm[0]) std::swap(c->perm[0], c->perm[1]);
     }
+    stage_end(c); stage_begin(c, ST_MIGRATE);
     LAUNCH(k_dd_samples, cdiv(DD_SAMPLES, T), T, 0, n, c->key[0], DD_SAMPLES, c->dd_samples + (size_t)c->rank * DD_SAMPLES);
     { int r_ = coll_allgather(c, c->stream, c->dd_samples + (size_t)c->rank * DD_SAMPLES, c->dd_samples, (size_t)DD_SAMPLES * 8); if (r_) return r_; }
     long long cnt_mine = n;
@@ -278,13 +311,18 @@ int dd_build_tree(sph_ctx* c) {
       m.perm[q] = q == c->rank ? c->perm[0] : dd_peer<const int>(c, DS_PERM + all[q].perm_slot, q);
     }
     m.dst_off[R] = acc;
-    if ((int64_t)acc > c->cap) { c->err = "domain decomposition: " + std::to_string(acc) + " particles migrate to this rank, capacity " + std::to_string((long long)c->cap); return SPH_ERR_OOM; }
+    {
+      int bad = 0;
+      if ((int64_t)acc > c->cap) { c->err = "domain decomposition: " + std::to_string(acc) + " particles migrate to this rank, capacity " + std::to_string((long long)c->cap); bad = SPH_ERR_OOM; }
+      { int r_ = dd_agree(c, bad, "the migration"); if (r_) return r_; }
+    }
     for (int f = 0; f < 10; ++f) m.dst[f] = c->st[c->cur ^ 1][f];
     m.dst_id = c->id[c->cur ^ 1]; m.dst_key = c->key[1];
     if (acc > 0) LAUNCH(k_dd_migrate, cdiv(acc, T), T, 0, m);
     { int r_ = dd_barrier(c); if (r_) return r_; }      // every pull has finished: the source buffers may be reused
     c->cur ^= 1; std::swap(c->key[0], c->key[1]);
     c->n = n = acc;
+    stage_end(c); stage_begin(c, ST_SORT);
     if (moved && n > 0) {                               // the incoming segments are sorted runs: order them (and the state) once more
       LAUNCH(k_iota, cdiv(n, T), T, 0, n, c->perm[0]);
       size_t bytes = c->cub_bytes;
@@ -454,10 +492,11 @@ int dd_build_tree(sph_ctx* c) {
   }
   stage_end(c);
   // ---- halo (also computes this domain's boxes and crosses a barrier: the peers' node arrays are final), then the LET
-  stage_begin(c, ST_COMM);
+  stage_begin(c, ST_HALO);
   { int r_ = dd_halo(c); if (r_) return r_; }
-  { int r_ = dd_build_let(c, cand); if (r_) return r_; }
-  { int r_ = dd_barrier(c); if (r_) return r_; }          // nobody rebuilds its node array while a peer still reads it
+  stage_end(c); stage_begin(c, ST_LET);
+  { int r_ = dd_build_let(c, cand); if (r_ && r_ != SPH_ERR_OOM) return r_; r_ = dd_agree(c, r_, "the locally essential tree"); if (r_) return r_; }
+  // (the peers read the local-tree region of this rank's node array only; it is next written by the next build, collectives lie in between)
   stage_end(c);
   c->tree_valid = true; c->pos_moved = false;
   return SPH_OK;
@@ -474,7 +513,7 @@ int dd_refresh_tree(sph_ctx* c) {
     LAUNCH(k_refresh_reach, cdiv(n, T), T, 0, n, s.h, c->level, c->root, c->dp, c->reach);
   }
   stage_end(c);
-  stage_begin(c, ST_COMM);
+  stage_begin(c, ST_HALO);
   { int r_ = dd_halo(c); if (r_) return r_; }
   stage_end(c);
   return SPH_OK;

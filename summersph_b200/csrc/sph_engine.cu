@@ -30,7 +30,7 @@ namespace {
 
 thread_local std::string g_create_error;
 
-enum Stage { ST_KEYS = 0, ST_SORT, ST_TREE, ST_DENSITY, ST_GRAVITY, ST_SPH, ST_INTEGRATE, ST_HITER, ST_CULL, ST_COMM, ST_COUNT };
+enum Stage { ST_KEYS = 0, ST_SORT, ST_TREE, ST_DENSITY, ST_GRAVITY, ST_SPH, ST_INTEGRATE, ST_HITER, ST_CULL, ST_COMM, ST_HALO, ST_LET, ST_MIGRATE, ST_COUNT };   // the last three: domain decomposition only
 
 // x**n in libgcc __powidf2 order (kernel tables, SUMMER_SPH.f90:63-100)
 inline double powi(double x, int n) { double y = (n % 2) ? x : 1.0; while (n >>= 1) { x = x * x; if (n % 2) y *= x; } return y; }
@@ -103,7 +103,7 @@ struct sph_ctx {
   bool dd = false; int64_t n_global = 0; int n_halo = 0, ng_own = 0, ng_halo = 0;
   uint64_t* key_alloc[2] = {}; int* perm_alloc[2] = {};          // the allocations behind key[] / perm[] (which swap)
   uint64_t *dd_samples = nullptr, *dd_split = nullptr; long long* dd_counts = nullptr; int* dd_sendoff = nullptr;
-  DDCell* dd_cells = nullptr; DDContrib* dd_contrib = nullptr; BvhBox* dd_dom = nullptr; int* dd_let_ctl = nullptr; double* dd_create8 = nullptr; unsigned long long* dd_cand = nullptr;
+  DDCell* dd_cells = nullptr; DDContrib* dd_contrib = nullptr; BvhBox* dd_obvh = nullptr; size_t dd_obvh_cap = 0; DDBvh dd_ob; int* dd_let_ctl = nullptr; double* dd_create8 = nullptr; unsigned long long* dd_cand = nullptr;
   DDLetEntry* dd_let_f[2] = {}; int dd_let_fcap = 0, dd_let_begin = 0, dd_let_end = 0, dd_let_used = 0, dd_top_n = 0;
   unsigned char* dd_halo_flag = nullptr; int *dd_halo_list = nullptr, *dd_halo_size = nullptr, *dd_halo_poff = nullptr; size_t dd_halo_cap = 0;
   unsigned long long* dd_acc_key = nullptr; DDAccRec* dd_acc_rec = nullptr;                      // exported: this rank's accretion records
@@ -1046,7 +1046,7 @@ int sph_destroy(sph_ctx* c) {
   F(c->rho); F(c->omega); F(c->prs); F(c->cs); F(c->por2); F(c->ax); F(c->ay); F(c->az); F(c->udot); F(c->adot);
   F(c->node_count); F(c->gsize); F(c->gfirst); F(c->groups); F(c->level); F(c->lcx); F(c->lcy); F(c->lcz); F(c->reach); F(c->bvh); F(c->nodes); F(c->node_part); F(c->parent); F(c->nchild);
   F(c->nl_pool); F(c->nl_head); F(c->nl_ctl); F(c->ggroups); F(c->gbvh); F(c->seg_cnt); F(c->seg_off); F(c->wnodes); F(c->wcount); F(c->wstart); F(c->widx); F(c->grav_spill);
-  F(c->dd_samples); F(c->dd_split); F(c->dd_counts); F(c->dd_sendoff); F(c->dd_cells); F(c->dd_contrib); F(c->dd_dom); F(c->dd_let_ctl); F(c->dd_create8); F(c->dd_cand);
+  F(c->dd_samples); F(c->dd_split); F(c->dd_counts); F(c->dd_sendoff); F(c->dd_cells); F(c->dd_contrib); F(c->dd_obvh); F(c->dd_let_ctl); F(c->dd_create8); F(c->dd_cand);
   F(c->dd_let_f[0]); F(c->dd_let_f[1]); F(c->dd_halo_flag); F(c->dd_halo_list); F(c->dd_halo_size); F(c->dd_halo_poff); F(c->dd_acc_key); F(c->dd_acc_rec);
   F(c->dd_accg_key[0]); F(c->dd_accg_key[1]); F(c->dd_accg_idx[0]); F(c->dd_accg_idx[1]); F(c->dd_accg_rec); F(c->dd_gid); F(c->dd_gpos); F(c->dd_gcnt); F(c->dd_goff); F(c->dd_gstage);
   F(c->cons_partial); F(c->cons_out); F(c->img_table); F(c->sink_spin);
