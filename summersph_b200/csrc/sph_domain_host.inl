@@ -54,11 +54,12 @@ int dd_agree(sph_ctx* c, int code, const char* what) {
 int dd_alloc(sph_ctx* c) {               // private scratch of the decomposition (sizes that do not depend on the particle count)
   if (c->dd_samples) return SPH_OK;
   const int R = c->n_ranks;
-  DA(c->dd_samples, (size_t)R * DD_SAMPLES); DA(c->dd_counts, R); DA(c->dd_split, R + 1); DA(c->dd_sendoff, R + 1);
+  DA(c->dd_samples, (size_t)R * DD_SAMPLES); DA(c->dd_counts, R); DA(c->dd_split, R + 1); DA(c->dd_sendoff, R + 1); DA(c->dd_segkeys, 2 * DD_MAX_RANKS);
   DA(c->dd_cells, DD_MAX_CELLS); DA(c->dd_contrib, (size_t)DD_MAX_CELLS * 8);
   DA(c->dd_let_ctl, 64); DA(c->dd_create8, 8); DA(c->dd_cand, 2);
   if (!c->d_flag) DA(c->d_flag, 4);
   CK(cudaMemset(c->d_flag, 0, 4 * sizeof(int)));
+  CK(cudaFuncSetAttribute(k_dd_splitters, cudaFuncAttributeMaxDynamicSharedMemorySize, DD_MAX_RANKS * DD_SAMPLES * 8));
   return SPH_OK;
 }
 
@@ -224,29 +225,37 @@ int dd_pull_density_fields(sph_ctx* c) {
 }
 
 // ---- locally essential tree ----------------------------------------------------------------------------------------------
+// Runs on the exchange stream, under the density pass (only the gravity walk reads it: run_gravity waits for let_done).
+// Nothing is read back here: an overflow raises `let_flag`, which travels with the sink all-reduce of run_gravity and
+// becomes the sticky device error 5 on EVERY rank, seen at the step's (or sph_evaluate's) own read-back.
+__global__ void k_dd_let_flag(const int* __restrict__ ctl, double* __restrict__ flag, int force) { *flag = (ctl[1] || force) ? 1.0 : 0.0; }
+__global__ void k_dd_let_err(const double* __restrict__ flag, int* err) { if (*flag > 0.0) atomicExch(err, 5); }
+#define LAUNCH_X(kern, grid, block, ...) do { kern<<<(grid), (block), 0, c->xstream>>>(__VA_ARGS__); ++c->launches; } while (0)
 int dd_build_let(sph_ctx* c, const std::vector<DDLetEntry>& cand) {
   const int T = 256;
   const size_t fcap = (size_t)c->dd_let_fcap;
-  CK(cudaMemsetAsync(c->dd_let_ctl, 0, 64 * sizeof(int), c->stream));
-  CK(cudaMemcpyAsync(c->dd_let_ctl, &c->dd_let_begin, sizeof(int), cudaMemcpyHostToDevice, c->stream));        // cursor
-  if (cand.empty()) return SPH_OK;
-  if (cand.size() > fcap) { c->err = "domain decomposition: LET frontier capacity"; return SPH_ERR_OOM; }
-  DDLetEntry* seed = c->dd_let_f[1];
-  CK(cudaMemcpyAsync(seed, cand.data(), cand.size() * sizeof(DDLetEntry), cudaMemcpyHostToDevice, c->stream));
-  CK(cudaStreamSynchronize(c->stream));               // `cand` is a host vector of the caller
-  const double theta2 = c->dp.theta * c->dp.theta;
-  LAUNCH(k_dd_let_seed, cdiv((int)cand.size(), T), T, 0, (int)cand.size(), seed, c->dd_let_f[0], c->dd_let_ctl + 2, c->wnodes, c->bvh, c->dd_obvh, c->dd_ob, theta2);
-  DDPeerNodes pn; std::memset(&pn, 0, sizeof(pn));
-  for (int q = 0; q < c->n_ranks; ++q) if (q != c->rank) pn.wn[q] = dd_peer<const WNode>(c, DS_WN, q);
-  const int levels = SPH_KEY_LEVELS + 3;              // a compressed tree is at most lmax <= 21 branching levels deep
-  for (int l = 0; l < levels; ++l)
-    LAUNCH(k_dd_let_level, c->n_sm * 4, T, 0, c->dd_let_f[l & 1], c->dd_let_ctl + 2 + l, c->dd_let_f[(l + 1) & 1], c->dd_let_ctl + 3 + l, (int)fcap,
-           c->dd_let_ctl, c->dd_let_end, c->dd_let_ctl + 1, pn, c->wnodes, c->bvh, c->dd_obvh, c->dd_ob, theta2);
-  int ctl[2] = {0, 0};
-  CK(cudaMemcpyAsync(ctl, c->dd_let_ctl, sizeof(ctl), cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
-  c->dd_let_used = ctl[0] - c->dd_let_begin;
-  if (ctl[1]) { c->err = "domain decomposition: locally essential tree exceeds its capacity (raise SPH_B200_DOMAIN_SLACK)"; return SPH_ERR_OOM; }
+  if (!c->let_done) CK(cudaEventCreateWithFlags(&c->let_done, cudaEventDisableTiming));
+  CK(cudaEventRecord(c->x_ready, c->stream));
+  CK(cudaStreamWaitEvent(c->xstream, c->x_ready, 0));
+  CK(cudaMemsetAsync(c->dd_let_ctl, 0, 60 * sizeof(int), c->xstream));
+  CK(cudaMemcpyAsync(c->dd_let_ctl, &c->dd_let_begin, sizeof(int), cudaMemcpyHostToDevice, c->xstream));        // cursor
+  const bool too_many = cand.size() > fcap;
+  if (!cand.empty() && !too_many) {
+    c->dd_cand_host = cand;                              // stays alive while the copy is in flight
+    DDLetEntry* seed = c->dd_let_f[1];
+    CK(cudaMemcpyAsync(seed, c->dd_cand_host.data(), cand.size() * sizeof(DDLetEntry), cudaMemcpyHostToDevice, c->xstream));
+    const double theta2 = c->dp.theta * c->dp.theta;
+    LAUNCH_X(k_dd_let_seed, cdiv((int)cand.size(), T), T, (int)cand.size(), seed, c->dd_let_f[0], c->dd_let_ctl + 2, c->wnodes, c->bvh, c->dd_obvh, c->dd_ob, theta2);
+    DDPeerNodes pn; std::memset(&pn, 0, sizeof(pn));
+    for (int q = 0; q < c->n_ranks; ++q) if (q != c->rank) pn.wn[q] = dd_peer<const WNode>(c, DS_WN, q);
+    const int levels = SPH_KEY_LEVELS + 3;              // a compressed tree is at most lmax <= 21 branching levels deep
+    for (int l = 0; l < levels; ++l)
+      LAUNCH_X(k_dd_let_level, c->n_sm * 4, T, c->dd_let_f[l & 1], c->dd_let_ctl + 2 + l, c->dd_let_f[(l + 1) & 1], c->dd_let_ctl + 3 + l, (int)fcap,
+               c->dd_let_ctl, c->dd_let_end, c->dd_let_ctl + 1, pn, c->wnodes, c->bvh, c->dd_obvh, c->dd_ob, theta2);
+  }
+  LAUNCH_X(k_dd_let_flag, 1, 1, c->dd_let_ctl, c->let_flag, too_many ? 1 : 0);
+  CK(cudaEventRecord(c->let_done, c->xstream));
+  c->let_pending = true;
   return SPH_OK;
 }
 
@@ -273,6 +282,7 @@ int dd_build_tree(sph_ctx* c) {
   }
   stage_end(c);
   // ---- local order, splitters, migration
+  RootBox rb; std::vector<DDInfo>& info = c->dd_info;
   stage_begin(c, ST_SORT);
   {
     if (n > 0) {
@@ -288,15 +298,35 @@ int dd_build_tree(sph_ctx* c) {
     long long cnt_mine = n;
     CK(cudaMemcpyAsync(c->dd_counts + c->rank, &cnt_mine, 8, cudaMemcpyHostToDevice, c->stream));
     { int r_ = coll_allgather(c, c->stream, c->dd_counts + c->rank, c->dd_counts, 8); if (r_) return r_; }
-    LAUNCH(k_dd_splitters, 1, 32, 0, R, DD_SAMPLES, c->dd_samples, c->dd_counts, c->dd_split);
-    LAUNCH(k_dd_segments, 1, 32, 0, R, n, c->key[0], c->dd_split, c->dd_sendoff);
-    // every rank's segment table + which of its buffers hold the (unsorted) state, the sorted keys and the permutation
-    struct Seg { int off[DD_MAX_RANKS + 1]; int cur, key_slot, perm_slot; } mine, all[DD_MAX_RANKS];
+    if (R > 1) LAUNCH(k_dd_splitters, R - 1, 256, (size_t)R * DD_SAMPLES * 8, R, DD_SAMPLES, c->dd_samples, c->dd_counts, c->dd_split);
+    LAUNCH(k_dd_segments, 1, 32, 0, R, n, c->key[0], c->dd_split, c->dd_sendoff, c->dd_segkeys);
+    // every rank's segment table (offsets + boundary keys) + which of its buffers hold the (unsorted) state, the sorted keys and the permutation
+    struct Seg { int off[DD_MAX_RANKS + 1]; int cur, key_slot, perm_slot; long long cap; unsigned long long first[DD_MAX_RANKS], last[DD_MAX_RANKS]; } mine, all[DD_MAX_RANKS];
     std::memset(&mine, 0, sizeof(mine));
     CK(cudaMemcpyAsync(mine.off, c->dd_sendoff, sizeof(int) * (R + 1), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(mine.first, c->dd_segkeys, sizeof(unsigned long long) * 2 * DD_MAX_RANKS, cudaMemcpyDeviceToHost, c->stream));      // first[] and last[] are adjacent
+    CK(cudaMemcpyAsync(&rb, c->root, sizeof(rb), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    mine.cur = c->cur; mine.key_slot = c->key[0] == c->key_alloc[0] ? 0 : 1; mine.perm_slot = c->perm[0] == c->perm_alloc[0] ? 0 : 1;
+    mine.cap = c->cap; mine.cur = c->cur; mine.key_slot = c->key[0] == c->key_alloc[0] ? 0 : 1; mine.perm_slot = c->perm[0] == c->perm_alloc[0] ? 0 : 1;
     { int r_ = dd_allgather_host(c, &mine, sizeof(Seg), all); if (r_) return r_; }
+    // what every domain looks like after the migration: size, boundary keys, which state buffer is current
+    info.assign(R, DDInfo());
+    c->n_global = 0;
+    for (int q = 0; q < R; ++q) {
+      DDInfo& I = info[q]; std::memset(&I, 0, sizeof(I));
+      bool q_moved = false; bool any = false;
+      for (int pq = 0; pq < R; ++pq) {
+        const int cnt = all[pq].off[q + 1] - all[pq].off[q];
+        if (cnt <= 0) continue;
+        if (pq != q) q_moved = true;
+        I.n_own += cnt;
+        if (!any || all[pq].first[q] < I.first_key) I.first_key = all[pq].first[q];
+        if (!any || all[pq].last[q] > I.last_key) I.last_key = all[pq].last[q];
+        any = true;
+      }
+      I.cur = all[q].cur ^ 1; if (q_moved && I.n_own > 0) I.cur ^= 1;
+      c->n_global += I.n_own;
+    }
     DDMigrate m; std::memset(&m, 0, sizeof(m));
     m.R = R;
     int acc = 0; bool moved = false;
@@ -311,10 +341,9 @@ int dd_build_tree(sph_ctx* c) {
       m.perm[q] = q == c->rank ? c->perm[0] : dd_peer<const int>(c, DS_PERM + all[q].perm_slot, q);
     }
     m.dst_off[R] = acc;
-    {
-      int bad = 0;
-      if ((int64_t)acc > c->cap) { c->err = "domain decomposition: " + std::to_string(acc) + " particles migrate to this rank, capacity " + std::to_string((long long)c->cap); bad = SPH_ERR_OOM; }
-      { int r_ = dd_agree(c, bad, "the migration"); if (r_) return r_; }
+    for (int q = 0; q < R; ++q) {      // every rank holds every segment table: all ranks find the same overfull rank and stop together
+      long long in = 0; for (int pq = 0; pq < R; ++pq) in += all[pq].off[q + 1] - all[pq].off[q];
+      if (in > all[q].cap) { c->err = "domain decomposition: " + std::to_string(in) + " particles migrate to rank " + std::to_string(q) + ", capacity " + std::to_string(all[q].cap) + " (raise SPH_B200_DOMAIN_SLACK)"; return SPH_ERR_OOM; }
     }
     for (int f = 0; f < 10; ++f) m.dst[f] = c->st[c->cur ^ 1][f];
     m.dst_id = c->id[c->cur ^ 1]; m.dst_key = c->key[1];
@@ -338,21 +367,10 @@ int dd_build_tree(sph_ctx* c) {
     }
   }
   stage_end(c);
-  if (n < 2) { c->err = "domain decomposition: a rank holds fewer than 2 particles"; return SPH_ERR_STATE; }
+  for (int q = 0; q < R; ++q) if (info[q].n_own < 2) { c->err = "domain decomposition: rank " + std::to_string(q) + " holds fewer than 2 particles"; return SPH_ERR_STATE; }      // the same verdict on every rank
   // ---- local octree (leaf levels see the neighbouring domains' boundary keys)
   stage_begin(c, ST_TREE);
   StateArrays s = state_of(c, c->cur);
-  std::vector<DDInfo>& info = c->dd_info;
-  {
-    DDInfo mine; std::memset(&mine, 0, sizeof(mine));
-    mine.n_own = n; mine.cur = c->cur;
-    CK(cudaMemcpyAsync(&mine.first_key, c->key[0], 8, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(&mine.last_key, c->key[0] + (n - 1), 8, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    info.assign(R, DDInfo());
-    { int r_ = dd_allgather_host(c, &mine, sizeof(DDInfo), info.data()); if (r_) return r_; }
-    c->n_global = 0; for (int q = 0; q < R; ++q) c->n_global += info[q].n_own;
-  }
   unsigned long long kprev = 0, knext = 0; int has_prev = 0, has_next = 0;
   for (int q = c->rank - 1; q >= 0; --q) if (info[q].n_own > 0) { kprev = info[q].last_key; has_prev = 1; break; }
   for (int q = c->rank + 1; q < R; ++q) if (info[q].n_own > 0) { knext = info[q].first_key; has_next = 1; break; }
@@ -376,24 +394,42 @@ int dd_build_tree(sph_ctx* c) {
   LAUNCH(k_oct_widx, cdiv(nn, T), T, 0, nn, c->nodes, c->wcount, c->wstart, c->widx);
   CK(cudaMemsetAsync(c->arrive, 0, sizeof(int) * (size_t)nn, c->stream));
   LAUNCH(k_oct_up, cdiv(n, T), T, 0, n, c->off, c->cnt, s.x, s.y, s.z, s.m, s.h, c->level, c->root, c->nodes, c->parent, c->nchild, c->arrive);
+  // ---- walk groups of the own particles (marked here so that their count travels with the top-tree records)
+  CK(cudaMemsetAsync(c->gsize, 0, sizeof(int) * (size_t)n, c->stream));
+  LAUNCH(k_group_mark, cdiv(nn, T), T, 0, nn, c->nodes, c->node_part, c->node_count, c->gsize);
+  bytes = c->cub_bytes;
+  CK(cub::DeviceSelect::Flagged(c->cub_tmp, bytes, cub::CountingInputIterator<int>(0), c->gsize, c->gfirst, c->d_nsel, n, c->stream));
   // ---- top tree: straddling cells, their locally complete children from every rank, the single-rank summation order
   std::vector<DDCell> cells;
   { int r_ = dd_make_cells(c, info, cells); if (r_) return r_; }
   const int ncell = (int)cells.size();
-  std::vector<DDContrib> contrib_all((size_t)R * std::max(ncell, 1) * 8);
-  if (ncell > 0) {
+  if (ncell == 0) { c->err = "domain decomposition: all particles on one rank"; return SPH_ERR_STATE; }
+  std::vector<DDContrib> contrib_all((size_t)R * ncell * 8);
+  int ng = 0;
+  {
     CK(cudaMemcpyAsync(c->dd_cells, cells.data(), sizeof(DDCell) * ncell, cudaMemcpyHostToDevice, c->stream));
     LAUNCH(k_dd_top_contrib, cdiv(ncell * 8, 64), 64, 0, ncell, c->dd_cells, n, c->key[0], c->off, c->cnt, c->node_count, c->nodes, c->wcount, c->wstart, c->dd_contrib, &c->sc->err);
-    std::vector<DDContrib> mine((size_t)ncell * 8);
+    // one read-back and one all-gather carry the records AND the own group count (slot 0's count field of an extra record)
+    const size_t nrec = (size_t)ncell * 8 + 1;
+    std::vector<DDContrib> mine(nrec), all(nrec * R);
     CK(cudaMemcpyAsync(mine.data(), c->dd_contrib, sizeof(DDContrib) * ncell * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(&ng, c->d_nsel, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    { int r_ = dd_allgather_host(c, mine.data(), sizeof(DDContrib) * ncell * 8, contrib_all.data()); if (r_) return r_; }
+    std::memset(&mine[nrec - 1], 0, sizeof(DDContrib)); mine[nrec - 1].count = ng;
+    { int r_ = dd_allgather_host(c, mine.data(), sizeof(DDContrib) * nrec, all.data()); if (r_) return r_; }
+    for (int q = 0; q < R; ++q) {
+      std::memcpy(&contrib_all[(size_t)q * ncell * 8], &all[(size_t)q * nrec], sizeof(DDContrib) * ncell * 8);
+      info[q].ng_own = all[(size_t)q * nrec + nrec - 1].count;
+    }
   }
+  c->ng_own = ng; c->n_groups = ng;
+  LAUNCH(k_group_pack, cdiv(ng, T), T, 0, ng, c->gfirst, c->gsize, c->groups);
+  c->rank_g.assign(R + 1, 0); c->rank_p.assign(R + 1, 0);
+  c->g0 = 0; c->g1 = ng; c->p0 = 0; c->p1 = n;
   // local nodes into the walk layout, behind the top region
   LAUNCH(k_oct_finalize, cdiv(nn, T), T, 0, nn, c->nodes, c->wcount, c->wstart, c->widx, c->wnodes, DD_TOP_CAP);
   std::vector<DDLetEntry> cand;
   {
-    RootBox rb; CK(cudaMemcpyAsync(&rb, c->root, sizeof(rb), cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream));
     // resolve(cell index) -> a reference to the node that stands for the cell in the compressed tree
     struct Ref { int kind; int cell; int owner; DDContrib rec; };      // kind 0: nothing, 1: top node (cell), 2: a rank's complete node
     std::vector<DDTopNode> tn(ncell);
@@ -430,17 +466,13 @@ int dd_build_tree(sph_ctx* c) {
       Ref r; r.kind = 1; r.cell = ci; r.owner = -1; return r;
     };
     c->dd_top_recs.clear();
-    std::vector<WNode> top;
+    std::vector<WNode>& top = c->dd_top_host; top.clear();      // a member: stays alive while the copy below is in flight
     auto make_wnode = [&](double m, double sx, double sy, double sz, double size) {
       WNode w; w.m = m; w.size = size; w.child = 0; w.nchild = 0;
       if (m > 0.0) { w.cx = sx / m; w.cy = sy / m; w.cz = sz / m; } else { w.cx = sx; w.cy = sy; w.cz = sz; }          // k_oct_finalize, F:173-177
       return w;
     };
     auto cell_size = [&](int level) { double sz = rb.size; for (int q = 0; q < level; ++q) sz = sz * 0.5; return sz; };
-    if (ncell == 0) {
-      // one non-empty rank only: its local root is the global root
-      c->err = "domain decomposition: all particles on one rank"; return SPH_ERR_STATE;
-    }
     Ref root = resolve(0);                                              // cells[0] = (level 0, prefix 0): the root cube
     if (root.kind != 1) { c->err = "domain decomposition: the root cell does not branch across ranks"; return SPH_ERR_STATE; }
     // walk layout of the top nodes: root at slot 0, every top node's children in one contiguous block
@@ -468,23 +500,6 @@ int dd_build_tree(sph_ctx* c) {
     if ((int)top.size() > DD_TOP_CAP) { c->err = "domain decomposition: top tree exceeds DD_TOP_CAP"; return SPH_ERR_STATE; }
     c->dd_top_n = (int)top.size();
     CK(cudaMemcpyAsync(c->wnodes, top.data(), sizeof(WNode) * top.size(), cudaMemcpyHostToDevice, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-  }
-  // ---- walk groups of the own particles
-  CK(cudaMemsetAsync(c->gsize, 0, sizeof(int) * (size_t)n, c->stream));
-  LAUNCH(k_group_mark, cdiv(nn, T), T, 0, nn, c->nodes, c->node_part, c->node_count, c->gsize);
-  bytes = c->cub_bytes;
-  CK(cub::DeviceSelect::Flagged(c->cub_tmp, bytes, cub::CountingInputIterator<int>(0), c->gsize, c->gfirst, c->d_nsel, n, c->stream));
-  int ng = 0;
-  CK(cudaMemcpyAsync(&ng, c->d_nsel, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
-  c->ng_own = ng; c->n_groups = ng;
-  LAUNCH(k_group_pack, cdiv(ng, T), T, 0, ng, c->gfirst, c->gsize, c->groups);
-  c->rank_g.assign(R + 1, 0); c->rank_p.assign(R + 1, 0);
-  c->g0 = 0; c->g1 = ng; c->p0 = 0; c->p1 = n;
-  {   // tell the peers how many own groups there are (they read groups / boxes [0, ng_own) of this rank)
-    DDInfo mine = info[c->rank]; mine.ng_own = ng;
-    { int r_ = dd_allgather_host(c, &mine, sizeof(DDInfo), info.data()); if (r_) return r_; }
   }
   {
     const int nst = cdiv(ng, GRAV_SEG), nsk = std::max(c->n_sink, 1);
@@ -495,7 +510,7 @@ int dd_build_tree(sph_ctx* c) {
   stage_begin(c, ST_HALO);
   { int r_ = dd_halo(c); if (r_) return r_; }
   stage_end(c); stage_begin(c, ST_LET);
-  { int r_ = dd_build_let(c, cand); if (r_ && r_ != SPH_ERR_OOM) return r_; r_ = dd_agree(c, r_, "the locally essential tree"); if (r_) return r_; }
+  { int r_ = dd_build_let(c, cand); if (r_) return r_; }
   // (the peers read the local-tree region of this rank's node array only; it is next written by the next build, collectives lie in between)
   stage_end(c);
   c->tree_valid = true; c->pos_moved = false;

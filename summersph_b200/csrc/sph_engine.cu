@@ -102,8 +102,9 @@ struct sph_ctx {
   // ---- Morton-domain decomposition (sph_domain.cuh / sph_domain_host.inl); in this mode n = own particles, cap = own + halo capacity
   bool dd = false; int64_t n_global = 0; int n_halo = 0, ng_own = 0, ng_halo = 0;
   uint64_t* key_alloc[2] = {}; int* perm_alloc[2] = {};          // the allocations behind key[] / perm[] (which swap)
-  uint64_t *dd_samples = nullptr, *dd_split = nullptr; long long* dd_counts = nullptr; int* dd_sendoff = nullptr;
+  uint64_t *dd_samples = nullptr, *dd_split = nullptr; long long* dd_counts = nullptr; int* dd_sendoff = nullptr; uint64_t* dd_segkeys = nullptr; std::vector<WNode> dd_top_host;
   DDCell* dd_cells = nullptr; DDContrib* dd_contrib = nullptr; BvhBox* dd_obvh = nullptr; size_t dd_obvh_cap = 0; DDBvh dd_ob; int* dd_let_ctl = nullptr; double* dd_create8 = nullptr; unsigned long long* dd_cand = nullptr;
+  cudaEvent_t let_done = nullptr; bool let_pending = false; double* let_flag = nullptr; std::vector<DDLetEntry> dd_cand_host;
   DDLetEntry* dd_let_f[2] = {}; int dd_let_fcap = 0, dd_let_begin = 0, dd_let_end = 0, dd_let_used = 0, dd_top_n = 0;
   unsigned char* dd_halo_flag = nullptr; int *dd_halo_list = nullptr, *dd_halo_size = nullptr, *dd_halo_poff = nullptr; size_t dd_halo_cap = 0;
   unsigned long long* dd_acc_key = nullptr; DDAccRec* dd_acc_rec = nullptr;                      // exported: this rank's accretion records
@@ -715,6 +716,7 @@ int run_gravity(sph_ctx* c, int do_grav, int do_sinks) {
       LAUNCH(k_grav_boxes, cdiv((int64_t)ng * 32, 256), 256, 0, ng, c->ggroups, s.x, s.y, s.z, c->gbvh);
       c->grav_groups_valid = true;
     }
+    if (c->let_pending) { CK(cudaStreamWaitEvent(c->stream, c->let_done, 0)); c->let_pending = false; }      // domains: the locally essential tree was pulled under the density pass
     LAUNCH(k_set_int, 1, 1, 0, c->work, 0);
     LAUNCH(k_gravity, grid, GWW * 32, gravity_smem(c, GWW), 0, ng, c->ggroups, c->gbvh, c->dp, c->wnodes, s.x, s.y, s.z, s.h, s.m, c->d_gt,
            c->ax, c->ay, c->az, do_grav, ns, c->S, c->sink_partial, c->ctr, c->work, c->grav_spill, &c->sc->err);
@@ -747,7 +749,13 @@ int run_gravity(sph_ctx* c, int do_grav, int do_sinks) {
     LAUNCH(k_sink_reduce, 1, 256, 0, nst, c->n_sink, c->sink_seg, c->S, do_sinks);
     stage_end(c);
     // domains: the segments are per rank (walk groups differ at domain boundaries), so the ranks' totals are added
-    if (c->dd) { stage_begin(c, ST_COMM); int r_ = allreduce(c, c->S.ax, (size_t)3 * SPH_MAX_SINKS, NC_FLOAT64, NC_SUM); if (r_) return r_; stage_end(c); }
+    if (c->dd) {
+      stage_begin(c, ST_COMM);
+      if (c->let_pending) { CK(cudaStreamWaitEvent(c->stream, c->let_done, 0)); c->let_pending = false; }
+      int r_ = allreduce(c, c->S.ax, (size_t)3 * SPH_MAX_SINKS + 1, NC_FLOAT64, NC_SUM); if (r_) return r_;      // + the LET overflow flags of all ranks
+      LAUNCH(k_dd_let_err, 1, 1, 0, c->let_flag, &c->sc->err);
+      stage_end(c);
+    }
   }
   stage_begin(c, ST_GRAVITY);
   LAUNCH(k_sink_pairs, 1, 32, 0, c->n_sink, c->S, c->dp.G, do_sinks);
@@ -786,6 +794,7 @@ int fetch_counters(sph_ctx* c) {
 
 int check_device_error(sph_ctx* c) {
   if (c->h_sc->err == 2) { c->err = "gravity walk: node stack overflow (GW_SPILL)"; return SPH_ERR_STATE; }
+  if (c->h_sc->err == 5) { c->err = "domain decomposition: the locally essential tree of some rank exceeds its capacity (raise SPH_B200_DOMAIN_SLACK)"; return SPH_ERR_OOM; }
   if (c->h_sc->err == 3) { c->err = "sink table full (SPH_MAX_SINKS): check_sink_creation (V:549-597) could not append a sink"; return SPH_ERR_STATE; }
   if (c->h_sc->err) {
     c->err = "particles share a full 126-bit descent key (closer than root_size/2^42) while max_depth > 42";
@@ -1002,10 +1011,11 @@ int sph_create(const sph_params* p, int32_t device, sph_ctx** out) {
   if ((r = dalloc(c, &c->nl_ctl, 4))) return fail(r);
   cudaMemset(c->nl_ctl, 0, 4 * sizeof(int));
   if ((r = dalloc(c, &c->d_nsel, 1))) return fail(r);
-  if ((r = dalloc(c, &c->sink_buf, (size_t)SPH_MAX_SINKS * 11))) return fail(r);
+  if ((r = dalloc(c, &c->sink_buf, (size_t)SPH_MAX_SINKS * 11 + 8))) return fail(r);      // + the LET overflow flag right behind az (it rides the sink all-reduce)
+  c->let_flag = c->sink_buf + (size_t)SPH_MAX_SINKS * 11;
   { double* b = c->sink_buf; const int M = SPH_MAX_SINKS;
     c->S = SinkArrays{b, b + M, b + 2 * M, b + 3 * M, b + 4 * M, b + 5 * M, b + 6 * M, b + 7 * M, b + 8 * M, b + 9 * M, b + 10 * M}; }
-  cudaMemset(c->sink_buf, 0, (size_t)SPH_MAX_SINKS * 11 * 8);
+  cudaMemset(c->sink_buf, 0, ((size_t)SPH_MAX_SINKS * 11 + 8) * 8);
   c->sink_extras = (p->mode & SPH_FLAG_SINK_MERGE_SPIN) ? 1 : 0;
   if (c->sink_extras) { if ((r = dalloc(c, &c->sink_spin, (size_t)SPH_MAX_SINKS * 3))) return fail(r); cudaMemset(c->sink_spin, 0, (size_t)SPH_MAX_SINKS * 3 * 8); }
   if (cudaMallocHost((void**)&c->h_sc, sizeof(SimScalars)) != cudaSuccess || cudaMallocHost((void**)&c->h_ctr, sizeof(WalkCounters)) != cudaSuccess) { c->err = "cudaMallocHost failed"; return fail(SPH_ERR_OOM); }
@@ -1037,6 +1047,7 @@ int sph_destroy(sph_ctx* c) {
   for (auto st : c->pstream) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
   for (auto ev : c->pevent) cudaEventDestroy(ev);
   if (c->xstream) { cudaStreamSynchronize(c->xstream); cudaStreamDestroy(c->xstream); cudaEventDestroy(c->x_ready); cudaEventDestroy(c->x_done); }
+  if (c->let_done) cudaEventDestroy(c->let_done);
   if (c->d_flag) cudaFree(c->d_flag);
   if (c->d_blob) cudaFree(c->d_blob);
   if (c->comm && c->nccl.CommDestroy) c->nccl.CommDestroy(c->comm);
@@ -1046,7 +1057,7 @@ int sph_destroy(sph_ctx* c) {
   F(c->rho); F(c->omega); F(c->prs); F(c->cs); F(c->por2); F(c->ax); F(c->ay); F(c->az); F(c->udot); F(c->adot);
   F(c->node_count); F(c->gsize); F(c->gfirst); F(c->groups); F(c->level); F(c->lcx); F(c->lcy); F(c->lcz); F(c->reach); F(c->bvh); F(c->nodes); F(c->node_part); F(c->parent); F(c->nchild);
   F(c->nl_pool); F(c->nl_head); F(c->nl_ctl); F(c->ggroups); F(c->gbvh); F(c->seg_cnt); F(c->seg_off); F(c->wnodes); F(c->wcount); F(c->wstart); F(c->widx); F(c->grav_spill);
-  F(c->dd_samples); F(c->dd_split); F(c->dd_counts); F(c->dd_sendoff); F(c->dd_cells); F(c->dd_contrib); F(c->dd_obvh); F(c->dd_let_ctl); F(c->dd_create8); F(c->dd_cand);
+  F(c->dd_samples); F(c->dd_split); F(c->dd_counts); F(c->dd_sendoff); F(c->dd_segkeys); F(c->dd_cells); F(c->dd_contrib); F(c->dd_obvh); F(c->dd_let_ctl); F(c->dd_create8); F(c->dd_cand);
   F(c->dd_let_f[0]); F(c->dd_let_f[1]); F(c->dd_halo_flag); F(c->dd_halo_list); F(c->dd_halo_size); F(c->dd_halo_poff); F(c->dd_acc_key); F(c->dd_acc_rec);
   F(c->dd_accg_key[0]); F(c->dd_accg_key[1]); F(c->dd_accg_idx[0]); F(c->dd_accg_idx[1]); F(c->dd_accg_rec); F(c->dd_gid); F(c->dd_gpos); F(c->dd_gcnt); F(c->dd_goff); F(c->dd_gstage);
   F(c->cons_partial); F(c->cons_out); F(c->img_table); F(c->sink_spin);
@@ -1301,6 +1312,7 @@ int sph_state_hash(sph_ctx* c, uint64_t* hash, double* sums5) {
 int sph_domain_stats(sph_ctx* c, int64_t* out8) {
   if (!c || !out8) return SPH_ERR_ARG;
   out8[0] = c->dd ? 1 : 0; out8[1] = c->n; out8[2] = c->n_halo; out8[3] = c->dd ? c->ng_own : c->n_groups; out8[4] = c->ng_halo;
+  if (c->dd && c->dd_let_ctl) { int cur = 0; cudaStreamSynchronize(c->xstream ? c->xstream : c->stream); cudaMemcpy(&cur, c->dd_let_ctl, sizeof(int), cudaMemcpyDeviceToHost); c->dd_let_used = cur > c->dd_let_begin ? cur - c->dd_let_begin : 0; }
   out8[5] = c->dd_let_used; out8[6] = c->dd_top_n; out8[7] = c->dd ? c->n_global : c->n;
   return SPH_OK;
 }
