@@ -721,12 +721,6 @@ int run_gravity(sph_ctx* c, int do_grav, int do_sinks) {
     LAUNCH(k_gravity, grid, GWW * 32, gravity_smem(c, GWW), 0, ng, c->ggroups, c->gbvh, c->dp, c->wnodes, s.x, s.y, s.z, s.h, s.m, c->d_gt,
            c->ax, c->ay, c->az, do_grav, ns, c->S, c->sink_partial, c->ctr, c->work, c->grav_spill, &c->sc->err);
   }
-#ifdef GW_DEBUG
-  { unsigned long long d[16]; cudaStreamSynchronize(c->stream); cudaMemcpyFromSymbol(d, gw_dbg, sizeof(d)); unsigned long long z[16] = {}; cudaMemcpyToSymbol(gw_dbg, z, sizeof(z));
-    fprintf(stderr, "GWDBG trips %llu popped %llu A %llu O %llu M %llu evals %llu entries %llu lanework %llu spills %llu maxsn %llu mixacc %llu mixopen %llu | T %d RC %d sparse rounds %llu lanework %llu dense entries %llu lanework %llu\n", d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7], d[8], d[9], d[10], d[11], GW_DBG_T, GW_DBG_RC, d[12], d[13], d[14], d[15]);
-    unsigned long long hh[33]; cudaMemcpyFromSymbol(hh, gw_hist, sizeof(hh)); unsigned long long zz[33] = {}; cudaMemcpyToSymbol(gw_hist, zz, sizeof(zz));
-    fprintf(stderr, "GWHIST"); for (int i = 0; i < 33; ++i) fprintf(stderr, " %llu", hh[i]); fprintf(stderr, "\n"); }
-#endif
   // sink side of the gas terms: per-segment folds -> exchange of the rows -> one fixed fold over all segments (rank-count independent)
   {
     const int nst = cdiv(c->dd ? c->g1 : c->n_groups, GRAV_SEG), nsk = std::max(c->n_sink, 1);

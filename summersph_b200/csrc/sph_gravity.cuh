@@ -38,24 +38,6 @@ struct SinkArrays { double *x, *y, *z, *vx, *vy, *vz, *m, *radius, *ax, *ay, *az
 #endif
 #define GW_SPILL 8192       // per-warp overflow entries in global memory (never reached in practice; loud if it is)
 
-#ifdef GW_DEBUG
-#ifndef GW_DBG_T
-#define GW_DBG_T 16
-#endif
-#ifndef GW_DBG_RC
-#define GW_DBG_RC 64
-#endif
-__device__ unsigned long long gw_dbg[16];
-__device__ unsigned long long gw_hist[33];
-#define GWD(i, v) do { if (lane == 0) atomicAdd(&gw_dbg[i], (unsigned long long)(v)); } while (0)
-__global__ void k_gw_dbg_print() {
-  printf("GWDBG trips %llu popped %llu A %llu O %llu M %llu evals %llu entries %llu lanework %llu spills %llu maxsn %llu mixacc %llu mixopen %llu\n",
-         gw_dbg[0], gw_dbg[1], gw_dbg[2], gw_dbg[3], gw_dbg[4], gw_dbg[5], gw_dbg[6], gw_dbg[7], gw_dbg[8], gw_dbg[9], gw_dbg[10], gw_dbg[11]);
-  for (int i = 0; i < 16; ++i) gw_dbg[i] = 0;
-}
-#else
-#define GWD(i, v)
-#endif
 
 struct GravWarpSmem {
   int2     stack[GW_STACK];
@@ -78,6 +60,7 @@ __device__ __forceinline__ double fast_rsqrt(double x) {
 // one list entry against one particle: a -= G M g(dist/h) dir / dist^3                  F:279-281 | F:129-146
 // h2x4 = 4 h^2: dist/h <= 2 is decided on the squares (g(2) = 1 and the table is continuous there, so which side
 // of the branch a borderline pair takes changes the term by rounding only); W = 1 beyond it needs no multiply.
+template <bool NEAR>
 __device__ __forceinline__ void grav_term(const double2 a, const double2 b, const bool on, const double xi, const double yi,
                                           const double zi, const double inv_h, const double h2x4, const double soft, const double* __restrict__ gt,
                                           const int nq, const double dq, const double inv_dq, double& gx, double& gy, double& gz) {
@@ -85,7 +68,7 @@ __device__ __forceinline__ void grav_term(const double2 a, const double2 b, cons
   const double d2 = fma(dx, dx, fma(dy, dy, fma(dz, dz, soft)));
   const double rs = fast_rsqrt(d2);                                          // F:279: M > 0 is checked when the entry is listed; d2 >= soft > 0
   double gm = b.y;
-  if (d2 <= h2x4) gm *= table_lerp1(gt, nq, dq, inv_dq, (d2 * rs) * inv_h);
+  if (NEAR) { if (d2 <= h2x4) gm *= table_lerp1(gt, nq, dq, inv_dq, (d2 * rs) * inv_h); }      // far entries: d2 > 4 h^2 for every particle of the run (decided at listing)
   const double f = gm * (rs * rs * rs);
   if (on) { gx = fma(-f, dx, gx); gy = fma(-f, dy, gy); gz = fma(-f, dz, gz); }
 }
@@ -126,18 +109,23 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
 #pragma unroll
     for (int u = 0; u < GW_ILP; ++u) gx[u] = gy[u] = gz[u] = 0.0;
 
-    auto evaluate_list = [&](int cnt) {
+    // The list is filled from both ends: far entries (no particle of the run lies within 2 h of the node: W = 1, F:138-141,
+    // no softening test at all) from slot 0 upwards, the others from the last slot downwards.
+    auto evaluate_list = [&](int nfar, int nnear) {
       int k = 0;
-#ifdef GW_DEBUG
-      GWD(5, 1); GWD(6, cnt);
-      { unsigned long long w = 0; for (int q = 0; q < cnt; ++q) { int pc = __popc(W.lmask[q]); w += pc; if (lane == 0) { atomicAdd(&gw_hist[pc], 1ull); } } GWD(7, w); }
-#endif
-      for (; k + GW_ILP <= cnt; k += GW_ILP) {          // GW_ILP independent chains per trip
+      for (; k + GW_ILP <= nfar; k += GW_ILP) {          // GW_ILP independent chains per trip
 #pragma unroll
         for (int u = 0; u < GW_ILP; ++u)
-          grav_term(W.lxy[k + u], W.lzg[k + u], (W.lmask[k + u] >> lane) & 1u, xi, yi, zi, inv_h, h2x4, soft, gt, P.nq, P.dq, P.inv_dq, gx[u], gy[u], gz[u]);
+          grav_term<false>(W.lxy[k + u], W.lzg[k + u], (W.lmask[k + u] >> lane) & 1u, xi, yi, zi, inv_h, h2x4, soft, gt, P.nq, P.dq, P.inv_dq, gx[u], gy[u], gz[u]);
       }
-      for (; k < cnt; ++k) grav_term(W.lxy[k], W.lzg[k], (W.lmask[k] >> lane) & 1u, xi, yi, zi, inv_h, h2x4, soft, gt, P.nq, P.dq, P.inv_dq, gx[0], gy[0], gz[0]);
+      for (; k < nfar; ++k) grav_term<false>(W.lxy[k], W.lzg[k], (W.lmask[k] >> lane) & 1u, xi, yi, zi, inv_h, h2x4, soft, gt, P.nq, P.dq, P.inv_dq, gx[0], gy[0], gz[0]);
+      k = GW_LIST - nnear;
+      for (; k + GW_ILP <= GW_LIST; k += GW_ILP) {
+#pragma unroll
+        for (int u = 0; u < GW_ILP; ++u)
+          grav_term<true>(W.lxy[k + u], W.lzg[k + u], (W.lmask[k + u] >> lane) & 1u, xi, yi, zi, inv_h, h2x4, soft, gt, P.nq, P.dq, P.inv_dq, gx[u], gy[u], gz[u]);
+      }
+      for (; k < GW_LIST; ++k) grav_term<true>(W.lxy[k], W.lzg[k], (W.lmask[k] >> lane) & 1u, xi, yi, zi, inv_h, h2x4, soft, gt, P.nq, P.dq, P.inv_dq, gx[0], gy[0], gz[0]);
     };
 
     if (do_grav && tg.y > 0) {               // tg.y == 0: an unused tail entry of the run table
@@ -153,19 +141,13 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
       const float xif = (float)(xi - g0x), yif = (float)(yi - g0y), zif = (float)(zi - g0z);
       const float softf = (float)soft, softf_min = __double2float_rd(soft_min), softf_max = __double2float_ru(soft_max);
       const float th2f = (float)theta2, inv_th2f = (float)inv_theta2;
-      int sn = 1, gsp = 0, ln = 0;
-#ifdef GW_DEBUG
-      int dq_len = 0, dq_ring = 0;
-      auto dq_flush = [&]() { int mx = dq_len, sm = dq_len; for (int o = 16; o > 0; o >>= 1) { mx = max(mx, __shfl_xor_sync(FULL_MASK, mx, o)); sm += __shfl_xor_sync(FULL_MASK, sm, o); }
-                              GWD(12, mx); GWD(13, sm); dq_len = 0; dq_ring = 0; };
-      auto dq_account = [&](unsigned m) { const int pc = __popc(m); if (pc < GW_DBG_T) { dq_len += (m >> lane) & 1u; if (++dq_ring == GW_DBG_RC) dq_flush(); } else { GWD(14, 1); GWD(15, pc); } };
-#endif
+      const float nearf = __double2float_ru(warp_max(live ? h2x4 : 0.0)) * 1.0001f;      // d2 above it: farther than 2 h from every particle of the run
+      int sn = 1, gsp = 0, ln = 0, nn = 0;
       if (lane == 0) W.stack[0] = make_int2(0, (int)livemask);
       __syncwarp();
 
       auto make_room = [&](int need) {       // keep the pushes inside the shared-memory stack
         if (sn + need <= GW_STACK) return;
-        GWD(8, 1);
         __syncwarp();
         if (gsp + sn > GW_SPILL) { if (lane == 0) atomicExch(err_flag, 2); sn = 0; }     // loud: the host returns an error
         for (int e = lane; e < sn; e += 32) myspill[gsp + e] = W.stack[e];
@@ -181,9 +163,6 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
           gsp -= take; sn = take;
           __syncwarp();
         }
-#ifdef GW_DEBUG
-        if (lane == 0) atomicMax(&gw_dbg[9], (unsigned long long)sn);
-#endif
         const int npop = sn < 32 ? sn : 32;
         const bool valid = lane < npop;
         const int2 e = valid ? W.stack[sn - 1 - lane] : make_int2(0, 0);
@@ -192,7 +171,7 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
         // ---- lane = node: classify against the group box
         int cls = 0;                           // 1 all accept, 2 all open, 3 mixed
         double ncx = 0.0, ncy = 0.0, ncz = 0.0, nm = 0.0, nsize = 0.0; int nchild = 0, nnch = 0;
-        float rxf = 0.f, ryf = 0.f, rzf = 0.f, s2f = 0.f;
+        float rxf = 0.f, ryf = 0.f, rzf = 0.f, s2f = 0.f, dmin2 = 0.f;
         if (valid) {
           const double2* p = reinterpret_cast<const double2*>(wn + e.x);
           const double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
@@ -202,7 +181,8 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
           const float axf = fabsf(rxf), ayf = fabsf(ryf), azf = fabsf(rzf);
           const float nx = fmaxf(axf - hxf, 0.f), ny = fmaxf(ayf - hyf, 0.f), nz = fmaxf(azf - hzf, 0.f);
           const float fx = axf + hxf, fy = ayf + hyf, fz = azf + hzf;
-          const float dmin2 = fmaf(nx, nx, fmaf(ny, ny, fmaf(nz, nz, softf_min))), dmax2 = fmaf(fx, fx, fmaf(fy, fy, fmaf(fz, fz, softf_max)));
+          dmin2 = fmaf(nx, nx, fmaf(ny, ny, fmaf(nz, nz, softf_min)));
+          const float dmax2 = fmaf(fx, fx, fmaf(fy, fy, fmaf(fz, fz, softf_max)));
           const float szf = (float)nsize;
           s2f = szf * szf;
           if (nnch == 0 || s2f < th2f * dmin2 * (1.f - 3e-5f)) cls = 1;
@@ -212,7 +192,6 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
         const unsigned emask = (unsigned)e.y;
         const unsigned balM = __ballot_sync(FULL_MASK, cls == 3);
         const int nmix = __popc(balM);
-        GWD(0, 1); GWD(1, npop); GWD(4, nmix);
         if (cls == 3) {
           const int pos = __popc(balM & lt_mask);
           W.mcx[pos] = ncx; W.mcy[pos] = ncy; W.mcz[pos] = ncz; W.msize[pos] = nsize; W.mmask[pos] = emask;
@@ -250,15 +229,13 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
         // ---- lane = node again: accepted (node, lane set) pairs join the interaction list, opened ones push their child block
         n_acc += __popc(acc_mask); n_open += __popc(open_mask);
         const bool ins = acc_mask != 0u && nm > 0.0;                                // F:279: massless nodes add nothing
-        const unsigned balL = __ballot_sync(FULL_MASK, ins);
+        const bool insn = ins && !(dmin2 > nearf);                                  // some particle of the run may be within 2 h of it
+        const unsigned balL = __ballot_sync(FULL_MASK, ins && !insn), balN = __ballot_sync(FULL_MASK, insn);
         if (ins) {
-          const int pos = ln + __popc(balL & lt_mask);
+          const int pos = insn ? GW_LIST - 1 - (nn + __popc(balN & lt_mask)) : ln + __popc(balL & lt_mask);
           W.lxy[pos] = make_double2(ncx, ncy); W.lzg[pos] = make_double2(ncz, P.G * nm); W.lmask[pos] = acc_mask;
         }
-#ifdef GW_DEBUG
-        __syncwarp();
-        for (int q = 0; q < __popc(balL); ++q) dq_account(W.lmask[ln + q]);
-#endif
+        nn += __popc(balN);
         ln += __popc(balL);
         const int nch = open_mask ? nnch : 0;
         int incl = nch;
@@ -268,13 +245,10 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
         for (int k = 0; k < nch; ++k) W.stack[sn + incl - nch + k] = make_int2(nchild + k, (int)open_mask);
         sn += total;
         __syncwarp();
-        if (ln > GW_LIST - 32) { evaluate_list(ln); ln = 0; __syncwarp(); }
+        if (ln + nn > GW_LIST - 32) { evaluate_list(ln, nn); ln = nn = 0; __syncwarp(); }
       }
-      if (ln > 0) evaluate_list(ln);
+      if (ln + nn > 0) evaluate_list(ln, nn);
       __syncwarp();
-#ifdef GW_DEBUG
-      if (dq_ring) dq_flush();
-#endif
     }
 #pragma unroll
     for (int u = 1; u < GW_ILP; ++u) { gx[0] += gx[u]; gy[0] += gy[u]; gz[0] += gz[u]; }
