@@ -116,6 +116,7 @@ program run_sph
   filename = merge('disc_20k_low_vel.txt', 'disc_12000_2.txt    ', variable)     ! V:1181 | F:946
   rc = sph_default_params(merge(SPH_MODE_VARIABLE_H, SPH_MODE_FIXED_H, variable), p)
   ncol = merge(10, 8, variable)
+  if (variable) call read_params_from_file('parameters.txt', p)                  ! V:1182-1184 (the fixed-h program has no parameter file)
 
   ! ---- read_data_from_file (F:594-716): header skipped, first pass counts records, second pass reads
   open(unit=10, file=trim(filename), status='old', action='read', iostat=status)
@@ -186,6 +187,46 @@ program run_sph
   rc = sph_destroy(ctx)
 
 contains
+
+  ! V:854-919: one header line, then rows of `bounding_size max_depth theta gamma eta convergence_criteria max_length
+  ! timestep_scale end_time`; every row is read, the LAST one stands (V:900-918).  A missing or empty file leaves the
+  ! defaults and says so, as the reference does (V:880-893).  theta is stored but, like in the reference (V:1029 passes
+  ! the literal 0.5), it does not reach the opening test: theta_override stays 0.
+  subroutine read_params_from_file(fname, params)
+    character(len=*), intent(in) :: fname
+    type(sph_params), intent(inout) :: params
+    character(len=256) :: hdr
+    integer :: st, nl, k, max_depth
+    real(dp) :: bounding_size, theta, gamma, eta, convergence_criteria, max_length, timestep_scale, end_time
+    nl = 0
+    open(unit=11, file=fname, status='old', action='read', iostat=st)
+    if (st /= 0) then
+      write(*,*) 'Error opening file: ', trim(fname); return
+    end if
+    read(11, '(A)', iostat=st) hdr
+    do
+      read(11, *, iostat=st)
+      if (st /= 0) exit
+      nl = nl + 1
+    end do
+    close(11)
+    if (nl == 0) then
+      write(*,*) 'No data found in file: ', trim(fname); return
+    end if
+    open(unit=11, file=fname, status='old', action='read', iostat=st)
+    read(11, '(A)', iostat=st) hdr
+    do k = 1, nl
+      read(11, *, iostat=st) bounding_size, max_depth, theta, gamma, eta, convergence_criteria, max_length, timestep_scale, end_time
+      if (st /= 0) then
+        write(*,*) 'Error reading line ', k; exit
+      end if
+    end do
+    close(11)
+    params%bounding_size = bounding_size; params%max_depth = int(max_depth, c_int32_t); params%theta = theta
+    params%gamma = gamma; params%eta = eta; params%convergence_criteria = convergence_criteria
+    params%max_length = max_length; params%timestep_scale = timestep_scale; params%end_time = end_time
+    write(*,*) 'Successfully read parameters from', trim(fname), '.'
+  end subroutine read_params_from_file
 
   subroutine make_save(number)                           ! F:719-738 | V:921-942
     integer, intent(in) :: number
