@@ -212,8 +212,7 @@ int dd_halo(sph_ctx* c) {
 }
 
 // after the density pass: the halo particles' rho, c and P/(Omega rho^2) (what the pair loop reads of its sources)
-int dd_pull_density_fields(sph_ctx* c) {
-  { int r_ = dd_barrier(c); if (r_) return r_; }
+int dd_pull_density_fields(sph_ctx* c) {      // called right behind the evaluation's all-reduce: every rank's density pass has finished
   if (c->ng_halo > 0) {
     DDPull a; std::memset(&a, 0, sizeof(a));
     a.nf = 0; a.with_id = 0; a.write_groups = 0; a.ng_own = c->ng_own; a.n_own = (int)c->n;
@@ -229,7 +228,12 @@ int dd_pull_density_fields(sph_ctx* c) {
 // Nothing is read back here: an overflow raises `let_flag`, which travels with the sink all-reduce of run_gravity and
 // becomes the sticky device error 5 on EVERY rank, seen at the step's (or sph_evaluate's) own read-back.
 __global__ void k_dd_let_flag(const int* __restrict__ ctl, double* __restrict__ flag, int force) { *flag = (ctl[1] || force) ? 1.0 : 0.0; }
-__global__ void k_dd_let_err(const double* __restrict__ flag, int* err) { if (*flag > 0.0) atomicExch(err, 5); }
+// flag[0] = LET overflow (set by k_dd_let_flag), flag[1] = this rank's "candidate lists void" (nl_ctl[1]); summed over the ranks
+__global__ void k_dd_flags_pack(const int* __restrict__ nl_ctl, double* __restrict__ flag) { flag[1] = nl_ctl[1] ? 1.0 : 0.0; }
+__global__ void k_dd_flags_apply(const double* __restrict__ flag, int* err, int* __restrict__ nl_ctl) {
+  if (flag[0] > 0.0) atomicExch(err, 5);
+  if (flag[1] > 0.0) nl_ctl[1] = 1;
+}
 #define LAUNCH_X(kern, grid, block, ...) do { kern<<<(grid), (block), 0, c->xstream>>>(__VA_ARGS__); ++c->launches; } while (0)
 int dd_build_let(sph_ctx* c, const std::vector<DDLetEntry>& cand) {
   const int T = 256;

@@ -104,7 +104,7 @@ struct sph_ctx {
   uint64_t* key_alloc[2] = {}; int* perm_alloc[2] = {};          // the allocations behind key[] / perm[] (which swap)
   uint64_t *dd_samples = nullptr, *dd_split = nullptr; long long* dd_counts = nullptr; int* dd_sendoff = nullptr; uint64_t* dd_segkeys = nullptr; std::vector<WNode> dd_top_host;
   DDCell* dd_cells = nullptr; DDContrib* dd_contrib = nullptr; BvhBox* dd_obvh = nullptr; size_t dd_obvh_cap = 0; DDBvh dd_ob; int* dd_let_ctl = nullptr; double* dd_create8 = nullptr; unsigned long long* dd_cand = nullptr;
-  cudaEvent_t let_done = nullptr; bool let_pending = false; double* let_flag = nullptr; std::vector<DDLetEntry> dd_cand_host;
+  bool dd_fields_pending = false; cudaEvent_t let_done = nullptr; bool let_pending = false; double* let_flag = nullptr; std::vector<DDLetEntry> dd_cand_host;
   DDLetEntry* dd_let_f[2] = {}; int dd_let_fcap = 0, dd_let_begin = 0, dd_let_end = 0, dd_let_used = 0, dd_top_n = 0;
   unsigned char* dd_halo_flag = nullptr; int *dd_halo_list = nullptr, *dd_halo_size = nullptr, *dd_halo_poff = nullptr; size_t dd_halo_cap = 0;
   unsigned long long* dd_acc_key = nullptr; DDAccRec* dd_acc_rec = nullptr;                      // exported: this rank's accretion records
@@ -625,9 +625,11 @@ int run_density(sph_ctx* c) {
   LAUNCH(k_density<false>, walk_grid(c, W), W * 32, density_smem(c, W), c->g1, c->groups, c->dp, dens_arrays(c), c->bvh, c->bi, c->d_wt, c->d_dwt,
          s.u, s.h, c->rho, c->omega, c->prs, c->cs, c->por2, c->ctr, c->work, c->exact_counters, nl);
   c->nl_valid = true; c->nl_exact = c->exact_counters;
-  if (c->n_ranks > 1) { int r_ = allreduce(c, c->nl_ctl + 1, 1, 2 /*ncclInt32*/, 2 /*ncclMax*/); if (r_) return r_; }   // a non-finite particle anywhere voids every rank's lists
+  // a non-finite particle anywhere voids every rank's lists.  Domains: the flag rides the one all-reduce of the evaluation (after the gravity walk)
+  if (c->n_ranks > 1 && !c->dd) { int r_ = allreduce(c, c->nl_ctl + 1, 1, 2 /*ncclInt32*/, 2 /*ncclMax*/); if (r_) return r_; }
   stage_end(c);
-  if (c->dd) { stage_begin(c, ST_COMM); int r_ = dd_pull_density_fields(c); if (r_) return r_; stage_end(c); }
+  c->dd_fields_pending = c->dd;        // the halo's rho, c, P/(Omega rho^2) are pulled after that all-reduce (it is also the "every density pass has finished" barrier)
+  if (c->dd) {}
   else if (c->n_ranks > 1) { stage_begin(c, ST_COMM); double* bufs[3] = {c->rho, c->cs, c->por2}; int r_ = allgatherv_begin(c, bufs, 3);   /* what the pair loop reads of its sources (Omega and P stay rank-local until a diagnostic download asks); completes under the gravity walk */ if (r_) return r_; stage_end(c); }
   return SPH_OK;
 }
@@ -746,8 +748,12 @@ int run_gravity(sph_ctx* c, int do_grav, int do_sinks) {
     if (c->dd) {
       stage_begin(c, ST_COMM);
       if (c->let_pending) { CK(cudaStreamWaitEvent(c->stream, c->let_done, 0)); c->let_pending = false; }
-      int r_ = allreduce(c, c->S.ax, (size_t)3 * SPH_MAX_SINKS + 1, NC_FLOAT64, NC_SUM); if (r_) return r_;      // + the LET overflow flags of all ranks
-      LAUNCH(k_dd_let_err, 1, 1, 0, c->let_flag, &c->sc->err);
+      // ONE all-reduce per evaluation: the ranks' sink sums, their LET overflow flags and their "lists void" flags; it is
+      // also the barrier behind which the peers' density fields are final (one sync point per evaluation instead of three)
+      LAUNCH(k_dd_flags_pack, 1, 1, 0, c->nl_ctl, c->let_flag);
+      int r_ = allreduce(c, c->S.ax, (size_t)3 * SPH_MAX_SINKS + 2, NC_FLOAT64, NC_SUM); if (r_) return r_;
+      LAUNCH(k_dd_flags_apply, 1, 1, 0, c->let_flag, &c->sc->err, c->nl_ctl);
+      if (c->dd_fields_pending) { r_ = dd_pull_density_fields(c); if (r_) return r_; c->dd_fields_pending = false; }
       stage_end(c);
     }
   }
