@@ -263,11 +263,12 @@ def main():
     e = engine_for(p, local, rank, world)
     e.ics_disc(n, seed=20251018)                 # generated on the device: every rank its own rows under the decomposition
     cons = {}
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(local)                # every rank samples its own GPU; rank 0's record is the line's "clocks", the others' medians are listed beside it
     want_drift = args.drift and decomp == 0      # sph_conserved walks the single-rank / replicated tree
     ms, stage_acc, launches, clocks, (dt, t) = timed_run(e, n, args.steps, args.warmup, barrier, sampler,
                                                          before=(lambda: cons.update(first=e.conserved())) if want_drift else None)
     per_rank = allgather(ms)
+    per_rank_sm_mhz = allgather(float(clocks["sm_mhz"] or 0.0)) if clocks else None
     per_rank_walk = [v / args.steps for v in allgather(stage_acc.get("density", 0) + stage_acc.get("gravity", 0) + stage_acc.get("sph", 0))]
     per_rank_comm = [v / args.steps for v in allgather(sum(stage_acc.get(k, 0) for k in ("comm", "halo", "let", "migrate")))]
     per_rank_build = [v / args.steps for v in allgather(stage_acc.get("keys", 0) + stage_acc.get("sort", 0) + stage_acc.get("tree", 0))]
@@ -414,6 +415,7 @@ def main():
             "state_hash": f"{state_hash:016x}", "state_sums": state_sums,
         }
         if world > 1:
+            line["per_rank_sm_mhz"] = per_rank_sm_mhz
             line["per_rank_walk_ms_per_step"] = per_rank_walk
             line["per_rank_comm_ms_per_step"] = per_rank_comm
             line["per_rank_build_ms_per_step"] = per_rank_build

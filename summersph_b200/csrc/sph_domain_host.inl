@@ -333,16 +333,20 @@ int dd_build_tree(sph_ctx* c) {
     }
     DDMigrate m; std::memset(&m, 0, sizeof(m));
     m.R = R;
-    int acc = 0; bool moved = false;
-    for (int q = 0; q < R; ++q) {
-      m.dst_off[q] = acc; m.src_off[q] = all[q].off[c->rank];
+    // destination order: the rows this rank keeps first (one sorted run), then the rows arriving from rank 0, 1, ...
+    int acc = 0; bool moved = false; int n_kept = 0;
+    std::vector<int> order; order.push_back(c->rank); for (int q = 0; q < R; ++q) if (q != c->rank) order.push_back(q);
+    for (int slot = 0; slot < R; ++slot) {
+      const int q = order[slot];
+      m.dst_off[slot] = acc; m.src_off[slot] = all[q].off[c->rank];
       const int cnt = all[q].off[c->rank + 1] - all[q].off[c->rank];
       if (q != c->rank && cnt > 0) moved = true;
+      if (q == c->rank) n_kept = cnt;
       acc += cnt;
-      for (int f = 0; f < 10; ++f) m.st[q][f] = q == c->rank ? c->st[c->cur][f] : dd_peer<const double>(c, DS_ST + all[q].cur * 10 + f, q);
-      m.id[q] = q == c->rank ? c->id[c->cur] : dd_peer<const int>(c, DS_ID + all[q].cur, q);
-      m.key[q] = q == c->rank ? c->key[0] : dd_peer<const uint64_t>(c, DS_KEY + all[q].key_slot, q);
-      m.perm[q] = q == c->rank ? c->perm[0] : dd_peer<const int>(c, DS_PERM + all[q].perm_slot, q);
+      for (int f = 0; f < 10; ++f) m.st[slot][f] = q == c->rank ? c->st[c->cur][f] : dd_peer<const double>(c, DS_ST + all[q].cur * 10 + f, q);
+      m.id[slot] = q == c->rank ? c->id[c->cur] : dd_peer<const int>(c, DS_ID + all[q].cur, q);
+      m.key[slot] = q == c->rank ? c->key[0] : dd_peer<const uint64_t>(c, DS_KEY + all[q].key_slot, q);
+      m.perm[slot] = q == c->rank ? c->perm[0] : dd_peer<const int>(c, DS_PERM + all[q].perm_slot, q);
     }
     m.dst_off[R] = acc;
     for (int q = 0; q < R; ++q) {      // every rank holds every segment table: all ranks find the same overfull rank and stop together
@@ -356,17 +360,23 @@ int dd_build_tree(sph_ctx* c) {
     c->cur ^= 1; std::swap(c->key[0], c->key[1]);
     c->n = n = acc;
     stage_end(c); stage_begin(c, ST_SORT);
-    if (moved && n > 0) {                               // the incoming segments are sorted runs: order them (and the state) once more
+    if (moved && n > 0) {      // [kept rows: sorted | arrivals: a few sorted runs]: sort the arrivals, MERGE the two, move the state once more
+      const int nf = n - n_kept;
       LAUNCH(k_iota, cdiv(n, T), T, 0, n, c->perm[0]);
+      cub::DoubleBuffer<uint64_t> dk(c->key[0] + n_kept, c->key[1] + n_kept); cub::DoubleBuffer<int> dv(c->perm[0] + n_kept, c->perm[1] + n_kept);
       size_t bytes = c->cub_bytes;
-      cub::DoubleBuffer<uint64_t> dk(c->key[0], c->key[1]); cub::DoubleBuffer<int> dv(c->perm[0], c->perm[1]);
-      CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp, bytes, dk, dv, n, 0, 63, c->stream));
-      if (dk.Current() != c->key[0]) std::swap(c->key[0], c->key[1]);
-      if (dv.Current() != c->perm[0]) std::swap(c->perm[0], c->perm[1]);
+      CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp, bytes, dk, dv, nf, 0, 63, c->stream));
+      uint64_t* mkey = reinterpret_cast<uint64_t*>(c->acc_key[0]); int* mperm = c->acc_val[0];      // scratch of the cull stage
+      size_t mb = 0;
+      CK(cub::DeviceMerge::MergePairs(nullptr, mb, c->key[0], c->perm[0], n_kept, dk.Current(), dv.Current(), nf, mkey, mperm, cuda::std::less<uint64_t>{}, c->stream));
+      if (mb + 256 > c->cub_bytes) { c->cub_bytes = mb + 256; if (c->cub_tmp) cudaFree(c->cub_tmp); c->cub_tmp = nullptr; if (cudaMalloc(&c->cub_tmp, c->cub_bytes) != cudaSuccess) { c->err = "cudaMalloc(cub temp)"; return SPH_ERR_OOM; } }
+      mb = c->cub_bytes;
+      CK(cub::DeviceMerge::MergePairs(c->cub_tmp, mb, c->key[0], c->perm[0], n_kept, dk.Current(), dv.Current(), nf, mkey, mperm, cuda::std::less<uint64_t>{}, c->stream));
+      CK(cudaMemcpyAsync(c->key[0], mkey, (size_t)n * 8, cudaMemcpyDeviceToDevice, c->stream));
       PermuteArgs pa;
       for (int f = 0; f < 10; ++f) { pa.src[f] = c->st[c->cur][f]; pa.dst[f] = c->st[c->cur ^ 1][f]; }
       pa.id_src = c->id[c->cur]; pa.id_dst = c->id[c->cur ^ 1];
-      LAUNCH(k_permute, cdiv(n, 4 * T), T, 0, n, c->perm[0], pa);
+      LAUNCH(k_permute, cdiv(n, 4 * T), T, 0, n, mperm, pa);
       c->cur ^= 1;
     }
   }

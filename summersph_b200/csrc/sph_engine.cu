@@ -12,6 +12,8 @@
 #include <functional>
 #include <dlfcn.h>
 #include <cub/cub.cuh>
+#include <cub/device/device_merge.cuh>
+#include <cuda/std/functional>
 
 #include "../../include/sph_b200.h"
 #include "sph_common.cuh"
