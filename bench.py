@@ -255,18 +255,33 @@ def main():
         dist.all_gather(out, tv)
         return [float(x.item()) for x in out]
 
-    check = None
-    if world > 1 and not args.no_check:
-        check = multi_gpu_check(p, local, rank, world, dist, torch)
-
     # ---- device-resident throughput ("value") ---------------------------------------------------------
-    e = engine_for(p, local, rank, world)
-    e.ics_disc(n, seed=20251018)                 # generated on the device: every rank its own rows under the decomposition
+    # The domain form stops collectively (same error on every rank from the same call) when a rank runs out of room or the
+    # GPUs cannot map each other's memory; the line is then measured with the replicated form and says so ("fallback").
     cons = {}
     sampler = ClockSampler(local)                # every rank samples its own GPU; rank 0's record is the line's "clocks", the others' medians are listed beside it
-    want_drift = args.drift and decomp == 0      # sph_conserved walks the single-rank / replicated tree
-    ms, stage_acc, launches, clocks, (dt, t) = timed_run(e, n, args.steps, args.warmup, barrier, sampler,
-                                                         before=(lambda: cons.update(first=e.conserved())) if want_drift else None)
+    fallback = None
+    for form in ([decomp, 0] if decomp == 1 else [decomp]):
+        p.decomposition = form
+        e = None; err = None
+        try:
+            check = multi_gpu_check(p, local, rank, world, dist, torch) if (world > 1 and not args.no_check) else None
+            e = engine_for(p, local, rank, world)
+            e.ics_disc(n, seed=20251018)         # generated on the device: every rank its own rows under the decomposition
+            want_drift = args.drift and form == 0      # sph_conserved walks the single-rank / replicated tree
+            ms, stage_acc, launches, clocks, (dt, t) = timed_run(e, n, args.steps, args.warmup, barrier, sampler,
+                                                                 before=(lambda: cons.update(first=e.conserved())) if want_drift else None)
+        except Exception as ex:                  # noqa: BLE001 - reported in the line
+            err = f"{type(ex).__name__}: {ex}"[:300]
+        if allmax(1.0 if err else 0.0) == 0.0:
+            decomp = form
+            break
+        if e is not None:
+            e.close()
+        if form == 0 or decomp == 0:
+            raise SystemExit(f"bench: the engine failed: {err}")
+        fallback = {"from": "Morton-ordered domains", "to": "replicated state", "reason": err or "a peer rank failed"}
+        sampler = ClockSampler(local)
     per_rank = allgather(ms)
     per_rank_sm_mhz = allgather(float(clocks["sm_mhz"] or 0.0)) if clocks else None
     per_rank_walk = [v / args.steps for v in allgather(stage_acc.get("density", 0) + stage_acc.get("gravity", 0) + stage_acc.get("sph", 0))]
@@ -420,6 +435,8 @@ def main():
             line["per_rank_comm_ms_per_step"] = per_rank_comm
             line["per_rank_build_ms_per_step"] = per_rank_build
             line["multi_gpu_check"] = check
+            if fallback:
+                line["fallback"] = fallback
             if dstats_all:
                 line["domain_stats"] = dstats_all
         if drift is not None:
