@@ -235,6 +235,13 @@ int64_t sph_launch_count(sph_ctx* ctx);
 /* Number of walk groups (cell-aligned runs of <= 32 particles) in the most recent tree. */
 int64_t sph_group_count(sph_ctx* ctx);
 
+/* Number of gravity evaluations so far that kept the far-field sums of the evaluation before them and walked only the
+ * near field: evaluation A of a loop body sees the positions, tree and sinks of the previous body's evaluation B
+ * (SUMMER_SPH.f90:894 after :905-912), so the accepted (node, particle) pairs of particle_gravforce_one (:264-290) and
+ * their distances are the same; only the terms within 2 h change with calc_smoothing (Variable.f90:1152).  Same terms as
+ * a full walk, summed in another order.  SPH_B200_NO_FAR_REUSE=1 (environment, read in sph_create) turns it off. */
+int64_t sph_far_reuse_count(sph_ctx* ctx);
+
 /* CUDA-event timer on the context's own stream (bench.py: torch events cannot see this stream). */
 int sph_timer_start(sph_ctx* ctx);
 int sph_timer_stop(sph_ctx* ctx, double* elapsed_ms);

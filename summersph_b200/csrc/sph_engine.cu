@@ -99,6 +99,10 @@ struct sph_ctx {
   std::vector<void*> ipc_opened; int* d_flag = nullptr; void* d_blob = nullptr; size_t blob_cap = 0;
   int g0 = 0, g1 = 0, p0 = 0, p1 = 0;
   double* cons_partial = nullptr; double* cons_out = nullptr;   // sph_conserved: block partials, result slots
+  // far-field reuse of the gravity walk (sph_gravity.cuh): stored far sums, per-particle near / far split, the sinks and counters they were taken with
+  double *far_fx = nullptr, *far_fy = nullptr, *far_fz = nullptr, *far_hc2 = nullptr, *far_sink_a = nullptr; SinkSnap* far_snap = nullptr; unsigned long long* far_ctr = nullptr;
+  bool far_valid = false; int far_reuse = 1; int64_t far_count = 0;
+  int* far_list = nullptr; int* far_cnt = nullptr; unsigned char* far_ovf = nullptr; size_t far_list_runs = 0; int far_slots = 128; bool far_lists = true; int far_n_ovf = 0;   // recorded near pairs: [run][slot][lane]
   double* sink_spin = nullptr; int sink_extras = 0;               // SPH_FLAG_SINK_MERGE_SPIN: spin[3][SPH_MAX_SINKS]; null pointer into the kernels when off
   double* img_table = nullptr;
   // ---- Morton-domain decomposition (sph_domain.cuh / sph_domain_host.inl); in this mode n = own particles, cap = own + halo capacity
@@ -164,6 +168,7 @@ int ensure_capacity(sph_ctx* c, int64_t n) {
   for (int b = 0; b < 2; ++b) { c->key_alloc[b] = c->key[b]; c->perm_alloc[b] = c->perm[b]; }
   DA(c->rho, cap); DA(c->omega, cap); DA(c->prs, cap); DA(c->cs, cap); DA(c->por2, cap);
   DA(c->ax, cap); DA(c->ay, cap); DA(c->az, cap); DA(c->udot, cap); DA(c->adot, cap);
+  DA(c->far_fx, cap); DA(c->far_fy, cap); DA(c->far_fz, cap); DA(c->far_hc2, cap); c->far_valid = false;
   DA(c->level, cap); DA(c->lcx, cap); DA(c->lcy, cap); DA(c->lcz, cap); DA(c->reach, cap);
   DA(c->node_count, 2 * cap); DA(c->gsize, cap); DA(c->gfirst, cap); DA(c->groups, cap);
   DA(c->nodes, 2 * cap); DA(c->node_part, 2 * cap); DA(c->parent, 2 * cap); DA(c->nchild, 2 * cap); DA(c->arrive, 2 * cap);
@@ -466,8 +471,10 @@ int refresh_tree(sph_ctx* c) {
 }
 
 int build_tree(sph_ctx* c) {
-  if (c->dd) return (c->tree_valid && !c->pos_moved && c->tree_reuse) ? dd_refresh_tree(c) : dd_build_tree(c);
-  if (c->tree_valid && !c->pos_moved && c->tree_reuse) return refresh_tree(c);
+  const bool reuse = c->tree_valid && !c->pos_moved && c->tree_reuse;
+  if (!reuse) c->far_valid = false;          // the stored far sums belong to the tree they were taken on
+  if (c->dd) return reuse ? dd_refresh_tree(c) : dd_build_tree(c);
+  if (reuse) return refresh_tree(c);
   bool retry = false;
   int r = build_tree_impl(c, &retry);
   if (r == SPH_OK && retry) {
@@ -694,8 +701,17 @@ int grav_warps(const sph_ctx* c) {     // as many warps (<= GW_WARPS) as the sha
   while (w > 1 && gravity_smem(c, w) > (size_t)c->max_smem) --w;
   return w;
 }
+__global__ void k_ctr_save(const WalkCounters* ctr, unsigned long long* saved) { saved[0] = ctr->grav_opened; saved[1] = ctr->grav_accepted; }
+__global__ void k_ctr_restore(WalkCounters* ctr, const unsigned long long* saved) { ctr->grav_opened += saved[0]; ctr->grav_accepted += saved[1]; }
+
 int run_gravity(sph_ctx* c, int do_grav, int do_sinks) {
   const int GWW = grav_warps(c);
+  // far-field reuse (sph_gravity.cuh): the full walk of a complete evaluation stores its far sums; while they stand
+  // (far_valid: same tree, same sinks, no h beyond its cutoff - decided at the end of step()), the next one walks only the near field
+  const bool far_on = c->far_reuse && do_grav && do_sinks && !c->dp.soft_hi && !c->exact_counters && !c->sink_extras;
+  const bool near_only = far_on && c->far_valid;
+  if (near_only) ++c->far_count;
+  if (!near_only) c->far_valid = false;      // a full walk re-takes the near / far split (and may not store at all)
   stage_begin(c, ST_GRAVITY);
   StateArrays s = state_of(c, c->cur);
   // upper bound of the number of runs in this rank's slice; unused tail entries stay empty (first = 0, count = 0)
@@ -721,10 +737,39 @@ int run_gravity(sph_ctx* c, int do_grav, int do_sinks) {
       c->grav_groups_valid = true;
     }
     if (c->let_pending) { CK(cudaStreamWaitEvent(c->stream, c->let_done, 0)); c->let_pending = false; }      // domains: the locally essential tree was pulled under the density pass
-    LAUNCH(k_set_int, 1, 1, 0, c->work, 0);
-    LAUNCH(k_gravity, grid, GWW * 32, gravity_smem(c, GWW), 0, ng, c->ggroups, c->gbvh, c->dp, c->wnodes, s.x, s.y, s.z, s.h, s.m, c->d_gt,
-           c->ax, c->ay, c->az, do_grav, ns, c->S, c->sink_partial, c->ctr, c->work, c->grav_spill, &c->sc->err);
+    // recorded near pairs: slots x 32 ints per run (16 KB at 128 slots); without the memory the near field is walked
+    if (far_on && c->far_lists && (size_t)ng > c->far_list_runs) {
+      if (c->far_list) { cudaFree(c->far_list); cudaFree(c->far_cnt); cudaFree(c->far_ovf); c->far_list = nullptr; c->far_cnt = nullptr; c->far_ovf = nullptr; }
+      const size_t runs = (size_t)ng + ng / 50 + 64;
+      if (cudaMalloc((void**)&c->far_list, runs * c->far_slots * 32 * sizeof(int)) != cudaSuccess || cudaMalloc((void**)&c->far_cnt, runs * 32 * sizeof(int)) != cudaSuccess ||
+          cudaMalloc((void**)&c->far_ovf, runs) != cudaSuccess) {
+        cudaGetLastError();
+        if (c->far_list) cudaFree(c->far_list); if (c->far_cnt) cudaFree(c->far_cnt); if (c->far_ovf) cudaFree(c->far_ovf);
+        c->far_list = nullptr; c->far_cnt = nullptr; c->far_ovf = nullptr; c->far_list_runs = 0; c->far_lists = false;
+      } else c->far_list_runs = runs;
+    }
+    const bool lists = far_on && c->far_lists && c->far_list != nullptr;
+    const FarField ff{c->far_fx, c->far_fy, c->far_fz, c->far_hc2, far_on ? 1 : 0, lists ? c->far_list : nullptr, c->far_cnt, c->far_ovf, c->far_slots, &c->sc->far_ovf};
+    if (near_only) {
+      if (lists) LAUNCH(k_gravity_near, std::max(1, std::min(cdiv(ng, GN_WARPS), 16 * c->n_sm)), GN_WARPS * 32, gravity_smem(c, 0), ng, c->ggroups, c->dp, c->wnodes, s.x, s.y, s.z, s.h, c->d_gt, c->ax, c->ay, c->az, ff);
+      if (!lists || c->far_n_ovf > 0) {       // runs whose lists overflowed (or all of them without lists): the near-only walk
+        LAUNCH(k_set_int, 1, 1, 0, c->work, 0);
+        LAUNCH(k_gravity<1>, grid, GWW * 32, gravity_smem(c, GWW), 0, ng, c->ggroups, c->gbvh, c->dp, c->wnodes, s.x, s.y, s.z, s.h, s.m, c->d_gt,
+               c->ax, c->ay, c->az, do_grav, ns, c->S, c->sink_partial, c->ctr, c->work, c->grav_spill, &c->sc->err, ff);
+      }
+    } else {
+      LAUNCH(k_set_int, 1, 1, 0, c->work, 0);
+      CK(cudaMemsetAsync(&c->sc->far_ovf, 0, sizeof(int), c->stream));
+      LAUNCH(k_far_hcut, cdiv(c->n, 256), 256, 0, (int)c->n, c->dp, s.h, far_on ? (double)GW_HCUT : 1.0, c->far_hc2);
+      LAUNCH(k_gravity<0>, grid, GWW * 32, gravity_smem(c, GWW), 0, ng, c->ggroups, c->gbvh, c->dp, c->wnodes, s.x, s.y, s.z, s.h, s.m, c->d_gt,
+             c->ax, c->ay, c->az, do_grav, ns, c->S, c->sink_partial, c->ctr, c->work, c->grav_spill, &c->sc->err, ff);
+    }
   }
+#ifdef GW_STATS
+  { unsigned long long d[16]; cudaStreamSynchronize(c->stream); cudaMemcpyFromSymbol(d, gw_stats, sizeof(d)); unsigned long long z[16] = {}; cudaMemcpyToSymbol(gw_stats, z, sizeof(z));
+    fprintf(stderr, "GWSTATS mode %d runs %llu trips %llu pops %llu pruned %llu accept %llu open %llu mixed %llu | far entries %llu (lanes %llu) near entries %llu (lanes %llu) evals %llu\n",
+            near_only ? 1 : 0, d[0], d[10], d[1], d[2], d[3], d[4], d[5], d[6], d[8], d[7], d[9], d[12]); }
+#endif
   // sink side of the gas terms: per-segment folds -> exchange of the rows -> one fixed fold over all segments (rank-count independent)
   {
     const int nst = cdiv(c->dd ? c->g1 : c->n_groups, GRAV_SEG), nsk = std::max(c->n_sink, 1);
@@ -732,10 +777,10 @@ int run_gravity(sph_ctx* c, int do_grav, int do_sinks) {
       c->sink_seg_cap = (size_t)(nst + nst / 8 + 64) * (nsk + 1) * 3;
       DA(c->sink_seg, c->sink_seg_cap); if (!c->dd) c->p2p_stale = true;
     }
-    if (do_sinks && nseg > 0 && c->g1 > c->g0)
+    if (do_sinks && !near_only && nseg > 0 && c->g1 > c->g0)
       LAUNCH(k_sink_seg_fold, cdiv((int64_t)nseg * c->n_sink * 3, 128), 128, 0, nseg, seg0, c->n_sink, c->seg_off, c->sink_partial, c->sink_seg);
     stage_end(c);
-    if (c->n_ranks > 1 && do_sinks && !c->dd) {
+    if (c->n_ranks > 1 && do_sinks && !c->dd && !near_only) {
       stage_begin(c, ST_COMM);
       std::vector<size_t> roff(c->n_ranks + 1);
       for (int r = 0; r <= c->n_ranks; ++r) roff[r] = (size_t)(r == c->n_ranks ? nst : c->rank_g[r] / GRAV_SEG) * c->n_sink * 3;
@@ -744,7 +789,8 @@ int run_gravity(sph_ctx* c, int do_grav, int do_sinks) {
       stage_end(c);
     }
     stage_begin(c, ST_GRAVITY);
-    LAUNCH(k_sink_reduce, 1, 256, 0, nst, c->n_sink, c->sink_seg, c->S, do_sinks);
+    if (near_only) CK(cudaMemsetAsync(c->S.ax, 0, (size_t)SPH_MAX_SINKS * 3 * 8, c->stream));      // domains: zeros into the all-reduce below; the sinks' own sums are the stored ones
+    else LAUNCH(k_sink_reduce, 1, 256, 0, nst, c->n_sink, c->sink_seg, c->S, do_sinks);
     stage_end(c);
     // domains: the segments are per rank (walk groups differ at domain boundaries), so the ranks' totals are added
     if (c->dd) {
@@ -760,7 +806,18 @@ int run_gravity(sph_ctx* c, int do_grav, int do_sinks) {
     }
   }
   stage_begin(c, ST_GRAVITY);
-  LAUNCH(k_sink_pairs, 1, 32, 0, c->n_sink, c->S, c->dp.G, do_sinks);
+  if (near_only) {       // sink accelerations and the walk's counters of the evaluation the far sums were taken in (same sinks, same gas, same accepted sets)
+    CK(cudaMemcpyAsync(c->S.ax, c->far_sink_a, (size_t)SPH_MAX_SINKS * 3 * 8, cudaMemcpyDeviceToDevice, c->stream));
+    LAUNCH(k_ctr_restore, 1, 1, 0, c->ctr, c->far_ctr);
+  } else {
+    LAUNCH(k_sink_pairs, 1, 32, 0, c->n_sink, c->S, c->dp.G, do_sinks);
+    if (far_on) {
+      CK(cudaMemcpyAsync(c->far_sink_a, c->S.ax, (size_t)SPH_MAX_SINKS * 3 * 8, cudaMemcpyDeviceToDevice, c->stream));
+      LAUNCH(k_sink_snapshot, 1, SPH_MAX_SINKS, 0, c->n_sink, c->S, c->far_snap);
+      LAUNCH(k_ctr_save, 1, 1, 0, c->ctr, c->far_ctr);
+      c->far_valid = true;
+    }
+  }
   stage_end(c);
   return SPH_OK;
 }
@@ -895,6 +952,14 @@ int step(sph_ctx* c) {
   CK(cudaMemsetAsync(&c->sc->n_removed, 0, sizeof(int) * 2, c->stream));
   if (n_removed > 0) { if ((r = compact(c))) return r; }
   if (c->dd && n_removed_global > 0) { c->tree_valid = false; c->pos_moved = true; c->n_global -= n_removed_global; }      // every domain rebuilds when any lost a particle
+  // may evaluation A of the next step keep evaluation B's far-field gravity?  Same particles (no removal anywhere), the same
+  // sinks (bitwise), and no h beyond the cutoff its near / far split was taken with; domains agree through one all-reduce
+  const bool far_try = c->far_valid && n_removed == 0 && n_removed_global == 0;
+  CK(cudaMemsetAsync(&c->sc->far_bad, 0, sizeof(int), c->stream));
+  if (far_try) {
+    LAUNCH(k_far_check, cdiv(std::max<int64_t>(c->n, SPH_MAX_SINKS), T), T, 0, (int)c->n, c->dp, state_of(c, c->cur).h, c->far_hc2, c->S, &c->sc->n_sink, c->far_snap, &c->sc->far_bad);
+    if (c->dd) { int r_ = allreduce(c, &c->sc->far_bad, 1, NC_INT32, NC_MAX); if (r_) return r_; }
+  }
   CK(cudaMemcpyAsync(c->h_sc, c->sc, sizeof(SimScalars), cudaMemcpyDeviceToHost, c->stream));
   int nl_host[4] = {0, 0, 0, 0};
   CK(cudaMemcpyAsync(nl_host, c->nl_ctl, sizeof(nl_host), cudaMemcpyDeviceToHost, c->stream));
@@ -905,6 +970,8 @@ int step(sph_ctx* c) {
     CK(cudaMemsetAsync(c->nl_ctl, 0, 4 * sizeof(int), c->stream));
   }
   c->nl_valid = false;
+  c->far_valid = far_try && c->h_sc->far_bad == 0;
+  c->far_n_ovf = c->h_sc->far_ovf;
   c->n_sink = c->h_sc->n_sink;
   stage_end(c);
   return SPH_OK;
@@ -1001,6 +1068,9 @@ int sph_create(const sph_params* p, int32_t device, sph_ctx** out) {
   make_dev_params(c);
   c->tree_reuse = getenv("SPH_B200_NO_TREE_REUSE") ? 0 : 1;
   c->fused_push = getenv("SPH_B200_NO_FUSED_PUSH") ? 0 : 1;     // developer switch: copy-engine exchange after the pair kernel
+  c->far_reuse = getenv("SPH_B200_NO_FAR_REUSE") ? 0 : 1;        // developer switch: every gravity evaluation walks the whole tree
+  c->far_lists = getenv("SPH_B200_NO_FAR_LISTS") ? false : true; // developer switch: the near field is always walked, never read from recorded pairs
+  if (getenv("SPH_B200_FAR_SLOTS")) c->far_slots = std::max(1, atoi(getenv("SPH_B200_FAR_SLOTS")));      // test hook: recorded near pairs per particle (overflowing runs walk)
   c->use_lists = getenv("SPH_B200_NO_LISTS") ? 0 : 1;            // developer switch: the pair loop always walks by itself     // developer switch: rebuild the tree in every evaluation
   int r;
   if ((r = upload_tables(c))) return fail(r);
@@ -1013,6 +1083,9 @@ int sph_create(const sph_params* p, int32_t device, sph_ctx** out) {
   if ((r = dalloc(c, &c->nl_ctl, 4))) return fail(r);
   cudaMemset(c->nl_ctl, 0, 4 * sizeof(int));
   if ((r = dalloc(c, &c->d_nsel, 1))) return fail(r);
+  if ((r = dalloc(c, &c->far_sink_a, (size_t)SPH_MAX_SINKS * 3))) return fail(r);
+  if ((r = dalloc(c, &c->far_snap, 1))) return fail(r);
+  if ((r = dalloc(c, &c->far_ctr, 2))) return fail(r);
   if ((r = dalloc(c, &c->sink_buf, (size_t)SPH_MAX_SINKS * 11 + 8))) return fail(r);      // + the LET overflow flag right behind az (it rides the sink all-reduce)
   c->let_flag = c->sink_buf + (size_t)SPH_MAX_SINKS * 11;
   { double* b = c->sink_buf; const int M = SPH_MAX_SINKS;
@@ -1034,7 +1107,9 @@ int sph_create(const sph_params* p, int32_t device, sph_ctx** out) {
   cudaFuncSetAttribute(k_density<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)density_smem(c, DENS_WARPS));
   cudaFuncSetAttribute(k_force<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)force_smem(c, force_warps(c, true), true));
   cudaFuncSetAttribute(k_force<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)force_smem(c, force_warps(c, false), false));
-  cudaFuncSetAttribute(k_gravity, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gravity_smem(c, grav_warps(c)));
+  cudaFuncSetAttribute(k_gravity<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gravity_smem(c, grav_warps(c)));
+  cudaFuncSetAttribute(k_gravity<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gravity_smem(c, grav_warps(c)));
+  cudaFuncSetAttribute(k_gravity_near, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gravity_smem(c, 0));
   cudaFuncSetAttribute(k_neighbours, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   if (cudaGetLastError() != cudaSuccess) { c->err = "cudaFuncSetAttribute failed (was the library built for this GPU's architecture?)"; return fail(SPH_ERR_CUDA); }
   *out = c;
@@ -1063,6 +1138,7 @@ int sph_destroy(sph_ctx* c) {
   F(c->dd_let_f[0]); F(c->dd_let_f[1]); F(c->dd_halo_flag); F(c->dd_halo_list); F(c->dd_halo_size); F(c->dd_halo_poff); F(c->dd_acc_key); F(c->dd_acc_rec);
   F(c->dd_accg_key[0]); F(c->dd_accg_key[1]); F(c->dd_accg_idx[0]); F(c->dd_accg_idx[1]); F(c->dd_accg_rec); F(c->dd_gid); F(c->dd_gpos); F(c->dd_gcnt); F(c->dd_goff); F(c->dd_gstage);
   F(c->cons_partial); F(c->cons_out); F(c->img_table); F(c->sink_spin);
+  F(c->far_fx); F(c->far_fy); F(c->far_fz); F(c->far_hc2); F(c->far_sink_a); F(c->far_snap); F(c->far_ctr); F(c->far_list); F(c->far_cnt); F(c->far_ovf);
   F(c->arrive); F(c->cnt); F(c->off); F(c->root); F(c->partial); F(c->cub_tmp); F(c->d_wt); F(c->d_dwt); F(c->d_gt);
   F(c->sink_buf); F(c->sink_partial); F(c->sink_seg); F(c->sc); F(c->ctr); F(c->work); F(c->keep); F(c->d_nsel); F(c->pos); F(c->stage_d); F(c->stage_d2);
   if (c->h_sc) cudaFreeHost(c->h_sc);
@@ -1212,6 +1288,7 @@ int sph_evaluate(sph_ctx* c, int32_t mask) {
   int r = evaluate(c, mask); if (r) return r;
   CK(cudaMemcpyAsync(c->h_sc, c->sc, sizeof(SimScalars), cudaMemcpyDeviceToHost, c->stream));
   if ((r = fetch_counters(c))) return r;
+  c->far_n_ovf = c->h_sc->far_ovf;
   stage_collect(c, true);
   CK(cudaGetLastError());
   return check_device_error(c);
@@ -1504,6 +1581,7 @@ int sph_stage_times(sph_ctx* c, double* ms, int32_t n) {
 
 int64_t sph_launch_count(sph_ctx* c) { return c ? c->launches : 0; }
 int64_t sph_group_count(sph_ctx* c) { return c ? c->n_groups : 0; }
+int64_t sph_far_reuse_count(sph_ctx* c) { return c ? c->far_count : 0; }
 
 int sph_timer_start(sph_ctx* c) {
   if (!c) return SPH_ERR_ARG;

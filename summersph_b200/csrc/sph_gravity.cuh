@@ -39,6 +39,13 @@ struct SinkArrays { double *x, *y, *z, *vx, *vy, *vz, *m, *radius, *ax, *ay, *az
 #define GW_SPILL 8192       // per-warp overflow entries in global memory (never reached in practice; loud if it is)
 
 
+#ifdef GW_STATS       // developer build: what the walk does per launch (scripts/build_variant.sh stats -DGW_STATS)
+__device__ unsigned long long gw_stats[16];
+#define GWS(slot, v) do { const unsigned long long v_ = (unsigned long long)(v); if (lane == 0) gws[slot] += v_; } while (0)      // v may hold a warp vote: evaluated by every lane
+#else
+#define GWS(slot, v) do {} while (0)
+#endif
+
 struct GravWarpSmem {
   int2     stack[GW_STACK];
   double2  lxy[GW_LIST], lzg[GW_LIST];     // (cx, cy), (cz, G*M)
@@ -46,6 +53,10 @@ struct GravWarpSmem {
   double   mcx[32], mcy[32], mcz[32], msize[32], mlo[32], mhi[32];   // mixed nodes of the current trip: COM, size, d2 band of the cheap FP64 test
   float4   mf[32];                                                   // the same nodes for the FP32 screen: COM relative to the run's origin, size^2 / theta^2
   unsigned mmask[32];
+  double   nacc[3][32];                                              // full walk: the near sums of the lanes between list evaluations (registers are short there)
+  double   hpar[3][32];                                              // full walk: 1/h, 4 h^2, hc2 of the lanes (only the near entries need them)
+  int      lidx[GW_LIST];                                            // node index of every list entry (recorded with the near pairs)
+  int      ncnt[32];                                                 // full walk: near pairs recorded so far, per lane
 };
 
 // 1/sqrt(x): MUFU seed (~2^-20) + one Halley step (cubic: ~2^-58), x > 0
@@ -60,28 +71,86 @@ __device__ __forceinline__ double fast_rsqrt(double x) {
 // one list entry against one particle: a -= G M g(dist/h) dir / dist^3                  F:279-281 | F:129-146
 // h2x4 = 4 h^2: dist/h <= 2 is decided on the squares (g(2) = 1 and the table is continuous there, so which side
 // of the branch a borderline pair takes changes the term by rounding only); W = 1 beyond it needs no multiply.
-template <bool NEAR>
-__device__ __forceinline__ void grav_term(const double2 a, const double2 b, const bool on, const double xi, const double yi,
-                                          const double zi, const double inv_h, const double h2x4, const double soft, const double* __restrict__ gt,
-                                          const int nq, const double dq, const double inv_dq, double& gx, double& gy, double& gz) {
+// KIND 0: far-list entry (d2 > hc2 for every particle of the run, decided at listing): W = 1, far sum.
+// KIND 1: near-list entry of the full walk: the term joins the near sum when d2 <= hc2, else the far sum.
+// KIND 2: near-only walk: only the terms with d2 <= hc2 (the far sum is the stored one).
+// KIND 3: a recorded near pair (d2 <= hc2 held when the full walk recorded it): near sum, no test.
+template <int KIND>
+__device__ __forceinline__ bool grav_term(const double2 a, const double2 b, const bool on, const double xi, const double yi,
+                                          const double zi, const double inv_h, const double h2x4, const double hc2, const double soft, const double* __restrict__ gt,
+                                          const int nq, const double dq, const double inv_dq, double& gx, double& gy, double& gz,
+                                          double& nx, double& ny, double& nz) {
   const double dx = xi - a.x, dy = yi - a.y, dz = zi - b.x;                  // F:274
   const double d2 = fma(dx, dx, fma(dy, dy, fma(dz, dz, soft)));
   const double rs = fast_rsqrt(d2);                                          // F:279: M > 0 is checked when the entry is listed; d2 >= soft > 0
   double gm = b.y;
-  if (NEAR) { if (d2 <= h2x4) gm *= table_lerp1(gt, nq, dq, inv_dq, (d2 * rs) * inv_h); }      // far entries: d2 > 4 h^2 for every particle of the run (decided at listing)
+  if (KIND != 0) { if (d2 <= h2x4) gm *= table_lerp1(gt, nq, dq, inv_dq, (d2 * rs) * inv_h); }      // far entries: d2 > 4 h^2 for every particle of the run (decided at listing)
   const double f = gm * (rs * rs * rs);
-  if (on) { gx = fma(-f, dx, gx); gy = fma(-f, dy, gy); gz = fma(-f, dz, gz); }
+  if (KIND == 0) { if (on) { gx = fma(-f, dx, gx); gy = fma(-f, dy, gy); gz = fma(-f, dz, gz); } return false; }
+  else {
+    const bool nr = on && (KIND == 3 || d2 <= hc2);
+    if (nr) { nx = fma(-f, dx, nx); ny = fma(-f, dy, ny); nz = fma(-f, dz, nz); }
+    if (KIND == 1) { if (on && !nr) { gx = fma(-f, dx, gx); gy = fma(-f, dy, gy); gz = fma(-f, dz, gz); } }
+    return nr;
+  }
 }
 
+// Far-field reuse.  Evaluation A of a loop body sees the positions, masses, sinks and tree of the previous body's
+// evaluation B (F:894 after F:905-912: the second kick moves nothing), and the reference's opening test does not
+// involve h (soft = 0.001 x the fixed smoothing, F:275), so every accepted (node, particle) pair and its distance are
+// the same; only h changed (calc_smoothing, V:1152), and h enters a term only through g(dist/h) for dist < 2 h
+// (F:138-141).  The full walk (MODE 0) therefore adds the terms with d2 <= hc2 = 4 (GW_HCUT h)^2 and all the others
+// apart, and stores the far sum together with the gas <- sink terms; while the tree, the sinks and "4 h^2 <= hc2 for
+// every particle" stand (checked on the device at the end of every step), the next evaluation is the near-only walk
+// (MODE 1): subtrees whose cell cannot hold a centre of mass within sqrt(max hc2) of the run's box are dropped at
+// classification, the opening decisions on the others are the full walk's own, the near terms are evaluated with the
+// new h and added to the stored far sum.  Same terms as a full walk, summed in another order (rounding level).
+// Only ~10 % of the lane slots of the near entries hold such a term (an entry is near for the run's box, a term for one
+// particle), so the full walk also records, per particle, the node of every term it added to the near sum
+// (list[run][slot][lane], `slots` per lane; ~70 per particle), and the next evaluation is k_gravity_near: lane =
+// particle, one gathered node per trip, every lane slot a needed term, no walk.  A run in which some lane needs more
+// slots is flagged (ovf) and served by the near-only walk instead.
+#ifndef GW_HCUT
+#define GW_HCUT 1.1
+#endif
+struct FarField { double *fx, *fy, *fz; const double* hc2; int store; int* list; int* cnt; unsigned char* ovf; int slots; int* n_ovf; };
+__global__ void k_far_hcut(int n, DevParams P, const double* __restrict__ h, double factor, double* __restrict__ hc2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double hc = factor * (P.variable_h ? h[i] : P.h_fixed);
+  hc2[i] = 4.0 * hc * hc;
+}
+// end of a step: may the next evaluation keep the stored far sums?  bit 0: some h grew beyond its cutoff (or is NaN);
+// bit 1: the sinks are not the ones the far sums were taken with (accretion, creation, cull, merger)
+struct SinkSnap { int n; double x[SPH_MAX_SINKS], y[SPH_MAX_SINKS], z[SPH_MAX_SINKS], m[SPH_MAX_SINKS]; };
+__global__ void k_sink_snapshot(int n_sink, SinkArrays S, SinkSnap* snap) {
+  const int t = threadIdx.x;
+  if (t == 0) snap->n = n_sink;
+  if (t < n_sink) { snap->x[t] = S.x[t]; snap->y[t] = S.y[t]; snap->z[t] = S.z[t]; snap->m[t] = S.m[t]; }
+}
+__global__ void k_far_check(int n, DevParams P, const double* __restrict__ h, const double* __restrict__ hc2, SinkArrays S, const int* __restrict__ n_sink_now,
+                            const SinkSnap* __restrict__ snap, int* __restrict__ far_bad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int bad = 0;
+  if (i < n && P.variable_h) { const double hi = h[i]; if (!(4.0 * hi * hi <= hc2[i])) bad = 1; }
+  if (blockIdx.x == 0 && threadIdx.x < SPH_MAX_SINKS) {
+    const int t = threadIdx.x, ns = *n_sink_now;
+    if (ns != snap->n) bad |= 2;
+    else if (t < ns && !(S.x[t] == snap->x[t] && S.y[t] == snap->y[t] && S.z[t] == snap->z[t] && S.m[t] == snap->m[t])) bad |= 2;
+  }
+  if (bad) atomicOr(far_bad, bad);
+}
 
 // dynamic smem: grav table (nq+1 doubles, padded to even) then one GravWarpSmem per warp
+// MODE 0: full walk; MODE 1: near-only walk on top of the stored far sums (see "Far-field reuse" above)
+template <int MODE>
 __global__ void __launch_bounds__(GW_WARPS * 32, 1)
 k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox* __restrict__ gbox, DevParams P,
           const WNode* __restrict__ wn, const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
           const double* __restrict__ h, const double* __restrict__ m, const double* __restrict__ g_gt,
           double* __restrict__ ax, double* __restrict__ ay, double* __restrict__ az,
           int do_grav, int n_sink, SinkArrays S, double* __restrict__ sink_partial, WalkCounters* ctr, int* work,
-          int2* __restrict__ spill, int* err_flag) {
+          int2* __restrict__ spill, int* err_flag, FarField F) {
   extern __shared__ __align__(16) double gsm[];
   double* gt = gsm;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -92,6 +161,9 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
   const unsigned lt_mask = (1u << lane) - 1u;
   const double theta = P.theta, theta2 = theta * theta, inv_theta2 = 1.0 / theta2;
   unsigned long long n_open = 0, n_acc = 0;
+#ifdef GW_STATS
+  unsigned long long gws[16] = {};
+#endif
 
   for (;;) {
     int chunk = 0;
@@ -104,30 +176,53 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
     const double xi = live ? x[i] : 0.0, yi = live ? y[i] : 0.0, zi = live ? z[i] : 0.0;
     const double hi = live ? (P.variable_h ? h[i] : P.h_fixed) : 1.0;
     const double inv_h = 1.0 / hi, h2x4 = 4.0 * hi * hi;
+    const double hc2 = live ? F.hc2[i] : 0.0;                                // >= h2x4: the near / far split of the sums
     const double soft = P.soft_hi ? 0.001 * hi : 0.001 * P.h_fixed;          // F:275 | V:296 | T:298
     double gx[GW_ILP], gy[GW_ILP], gz[GW_ILP];
 #pragma unroll
     for (int u = 0; u < GW_ILP; ++u) gx[u] = gy[u] = gz[u] = 0.0;
+    double nx = 0.0, ny = 0.0, nz = 0.0;                                     // terms with d2 <= hc2
+    if (MODE == 0) { W.nacc[0][lane] = 0.0; W.nacc[1][lane] = 0.0; W.nacc[2][lane] = 0.0; W.hpar[0][lane] = inv_h; W.hpar[1][lane] = h2x4; W.hpar[2][lane] = hc2; W.ncnt[lane] = 0; }
+    if (MODE == 1 && F.list && !F.ovf[chunk]) continue;                      // near-only walk behind k_gravity_near: only the runs whose lists overflowed
 
     // The list is filled from both ends: far entries (no particle of the run lies within 2 h of the node: W = 1, F:138-141,
     // no softening test at all) from slot 0 upwards, the others from the last slot downwards.
     auto evaluate_list = [&](int nfar, int nnear) {
       int k = 0;
-      for (; k + GW_ILP <= nfar; k += GW_ILP) {          // GW_ILP independent chains per trip
+      if (MODE == 0) {
+        for (; k + GW_ILP <= nfar; k += GW_ILP) {          // GW_ILP independent chains per trip
 #pragma unroll
-        for (int u = 0; u < GW_ILP; ++u)
-          grav_term<false>(W.lxy[k + u], W.lzg[k + u], (W.lmask[k + u] >> lane) & 1u, xi, yi, zi, inv_h, h2x4, soft, gt, P.nq, P.dq, P.inv_dq, gx[u], gy[u], gz[u]);
+          for (int u = 0; u < GW_ILP; ++u)
+            grav_term<0>(W.lxy[k + u], W.lzg[k + u], (W.lmask[k + u] >> lane) & 1u, xi, yi, zi, 0.0, 0.0, 0.0, soft, gt, P.nq, P.dq, P.inv_dq, gx[u], gy[u], gz[u], nx, ny, nz);
+        }
+        for (; k < nfar; ++k) grav_term<0>(W.lxy[k], W.lzg[k], (W.lmask[k] >> lane) & 1u, xi, yi, zi, 0.0, 0.0, 0.0, soft, gt, P.nq, P.dq, P.inv_dq, gx[0], gy[0], gz[0], nx, ny, nz);
+        if (nnear == 0) return;
       }
-      for (; k < nfar; ++k) grav_term<false>(W.lxy[k], W.lzg[k], (W.lmask[k] >> lane) & 1u, xi, yi, zi, inv_h, h2x4, soft, gt, P.nq, P.dq, P.inv_dq, gx[0], gy[0], gz[0]);
+      constexpr int NK = MODE == 0 ? 1 : 2;
+      const double e_inv_h = MODE == 0 ? W.hpar[0][lane] : inv_h, e_h2x4 = MODE == 0 ? W.hpar[1][lane] : h2x4, e_hc2 = MODE == 0 ? W.hpar[2][lane] : hc2;
+      if (MODE == 0) { nx = W.nacc[0][lane]; ny = W.nacc[1][lane]; nz = W.nacc[2][lane]; }
+      const bool rec = MODE == 0 && F.list != nullptr;                       // record the node of every term that joins the near sum
+      int nc = rec ? W.ncnt[lane] : 0;
+      int* const lst = rec ? F.list + ((size_t)chunk * F.slots) * 32 + lane : nullptr;
       k = GW_LIST - nnear;
       for (; k + GW_ILP <= GW_LIST; k += GW_ILP) {
+        bool hit[GW_ILP];
 #pragma unroll
         for (int u = 0; u < GW_ILP; ++u)
-          grav_term<true>(W.lxy[k + u], W.lzg[k + u], (W.lmask[k + u] >> lane) & 1u, xi, yi, zi, inv_h, h2x4, soft, gt, P.nq, P.dq, P.inv_dq, gx[u], gy[u], gz[u]);
+          hit[u] = grav_term<NK>(W.lxy[k + u], W.lzg[k + u], (W.lmask[k + u] >> lane) & 1u, xi, yi, zi, e_inv_h, e_h2x4, e_hc2, soft, gt, P.nq, P.dq, P.inv_dq, gx[u], gy[u], gz[u], nx, ny, nz);
+        if (rec) {
+#pragma unroll
+          for (int u = 0; u < GW_ILP; ++u) if (hit[u]) { if (nc < F.slots) lst[(size_t)nc * 32] = W.lidx[k + u]; ++nc; }
+        }
       }
-      for (; k < GW_LIST; ++k) grav_term<true>(W.lxy[k], W.lzg[k], (W.lmask[k] >> lane) & 1u, xi, yi, zi, inv_h, h2x4, soft, gt, P.nq, P.dq, P.inv_dq, gx[0], gy[0], gz[0]);
+      for (; k < GW_LIST; ++k) {
+        const bool hit = grav_term<NK>(W.lxy[k], W.lzg[k], (W.lmask[k] >> lane) & 1u, xi, yi, zi, e_inv_h, e_h2x4, e_hc2, soft, gt, P.nq, P.dq, P.inv_dq, gx[0], gy[0], gz[0], nx, ny, nz);
+        if (rec && hit) { if (nc < F.slots) lst[(size_t)nc * 32] = W.lidx[k]; ++nc; }
+      }
+      if (MODE == 0) { W.nacc[0][lane] = nx; W.nacc[1][lane] = ny; W.nacc[2][lane] = nz; if (rec) W.ncnt[lane] = nc; }
     };
 
+    GWS(0, 1);
     if (do_grav && tg.y > 0) {               // tg.y == 0: an unused tail entry of the run table
       const BvhBox gb = gbox[chunk];
       const double lo0 = gb.plo[0], lo1 = gb.plo[1], lo2 = gb.plo[2], hi0 = gb.phi[0], hi1 = gb.phi[1], hi2 = gb.phi[2];
@@ -141,7 +236,7 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
       const float xif = (float)(xi - g0x), yif = (float)(yi - g0y), zif = (float)(zi - g0z);
       const float softf = (float)soft, softf_min = __double2float_rd(soft_min), softf_max = __double2float_ru(soft_max);
       const float th2f = (float)theta2, inv_th2f = (float)inv_theta2;
-      const float nearf = __double2float_ru(warp_max(live ? h2x4 : 0.0)) * 1.0001f;      // d2 above it: farther than 2 h from every particle of the run
+      const float nearf = __double2float_ru(warp_max(hc2)) * 1.0001f;      // d2 above it: beyond the near / far split (hence farther than 2 h) for every particle of the run
       int sn = 1, gsp = 0, ln = 0, nn = 0;
       if (lane == 0) W.stack[0] = make_int2(0, (int)livemask);
       __syncwarp();
@@ -188,10 +283,17 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
           if (nnch == 0 || s2f < th2f * dmin2 * (1.f - 3e-5f)) cls = 1;
           else if (s2f > th2f * dmax2 * (1.f + 3e-5f)) cls = 2;
           else cls = 3;
+          if (MODE == 1) {       // every centre of mass of the subtree lies in the node's cell, i.e. within `size` of the node's own per axis
+            const float px = fmaxf(axf - hxf - szf - 2e-6f * (axf + hxf + szf), 0.f), py = fmaxf(ayf - hyf - szf - 2e-6f * (ayf + hyf + szf), 0.f),
+                        pz = fmaxf(azf - hzf - szf - 2e-6f * (azf + hzf + szf), 0.f);
+            if (fmaf(px, px, fmaf(py, py, pz * pz)) > nearf) cls = 0;       // no term of the subtree can be near for any particle of the run
+          }
         }
         const unsigned emask = (unsigned)e.y;
         const unsigned balM = __ballot_sync(FULL_MASK, cls == 3);
         const int nmix = __popc(balM);
+        GWS(1, npop); GWS(2, __popc(__ballot_sync(FULL_MASK, valid && cls == 0))); GWS(3, __popc(__ballot_sync(FULL_MASK, cls == 1)));
+        GWS(4, __popc(__ballot_sync(FULL_MASK, cls == 2))); GWS(5, nmix); GWS(10, 1);
         if (cls == 3) {
           const int pos = __popc(balM & lt_mask);
           W.mcx[pos] = ncx; W.mcy[pos] = ncy; W.mcz[pos] = ncz; W.msize[pos] = nsize; W.mmask[pos] = emask;
@@ -227,16 +329,24 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
           if (lane == L) { acc_mask = balAcc; open_mask = balOpen; }
         }
         // ---- lane = node again: accepted (node, lane set) pairs join the interaction list, opened ones push their child block
-        n_acc += __popc(acc_mask); n_open += __popc(open_mask);
-        const bool ins = acc_mask != 0u && nm > 0.0;                                // F:279: massless nodes add nothing
-        const bool insn = ins && !(dmin2 > nearf);                                  // some particle of the run may be within 2 h of it
-        const unsigned balL = __ballot_sync(FULL_MASK, ins && !insn), balN = __ballot_sync(FULL_MASK, insn);
+        if (MODE == 0) { n_acc += __popc(acc_mask); n_open += __popc(open_mask); }
+        const bool ins0 = acc_mask != 0u && nm > 0.0;                               // F:279: massless nodes add nothing
+        const bool insn = ins0 && !(dmin2 > nearf);                                 // some particle of the run may be within the near / far split of it
+        const bool ins = MODE == 0 ? ins0 : insn;
+        const unsigned balL = MODE == 0 ? __ballot_sync(FULL_MASK, ins && !insn) : 0u, balN = __ballot_sync(FULL_MASK, insn);
         if (ins) {
           const int pos = insn ? GW_LIST - 1 - (nn + __popc(balN & lt_mask)) : ln + __popc(balL & lt_mask);
           W.lxy[pos] = make_double2(ncx, ncy); W.lzg[pos] = make_double2(ncz, P.G * nm); W.lmask[pos] = acc_mask;
+          if (MODE == 0) W.lidx[pos] = e.x;
         }
         nn += __popc(balN);
         ln += __popc(balL);
+        GWS(6, __popc(balL)); GWS(7, __popc(balN));
+#ifdef GW_STATS
+        { int a = (ins && !insn) ? __popc(acc_mask) : 0, b = insn ? __popc(acc_mask) : 0;
+          for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(FULL_MASK, a, o); b += __shfl_xor_sync(FULL_MASK, b, o); }
+          GWS(8, a); GWS(9, b); }
+#endif
         const int nch = open_mask ? nnch : 0;
         int incl = nch;
         for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL_MASK, incl, o); if (lane >= o) incl += t; }
@@ -245,10 +355,14 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
         for (int k = 0; k < nch; ++k) W.stack[sn + incl - nch + k] = make_int2(nchild + k, (int)open_mask);
         sn += total;
         __syncwarp();
-        if (ln + nn > GW_LIST - 32) { evaluate_list(ln, nn); ln = nn = 0; __syncwarp(); }
+        if (ln + nn > GW_LIST - 32) { GWS(12, 1); evaluate_list(ln, nn); ln = nn = 0; __syncwarp(); }
       }
       if (ln + nn > 0) evaluate_list(ln, nn);
       __syncwarp();
+    }
+    if (MODE == 1) {       // stored far sum (tree terms beyond the split + gas <- sink terms) + the near terms at the new h
+      if (live) { ax[i] = F.fx[i] + nx; ay[i] = F.fy[i] + ny; az[i] = F.fz[i] + nz; }
+      continue;
     }
 #pragma unroll
     for (int u = 1; u < GW_ILP; ++u) { gx[0] += gx[u]; gy[0] += gy[u]; gz[0] += gz[u]; }
@@ -271,10 +385,68 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
         o[0] = px; o[1] = py; o[2] = pz;
       }
     }
-    if (live) { ax[i] = gx[0]; ay[i] = gy[0]; az[i] = gz[0]; }
+    if (F.list) {          // near pairs recorded per lane; a lane that needed more slots sends its run to the near-only walk
+      const int nc = W.ncnt[lane];
+      F.cnt[(size_t)chunk * 32 + lane] = nc;
+      const bool over = __any_sync(FULL_MASK, nc > F.slots);
+      if (lane == 0) { F.ovf[chunk] = over ? 1 : 0; if (over) atomicAdd(F.n_ovf, 1); }
+    }
+    if (live) {
+      if (F.store) { F.fx[i] = gx[0]; F.fy[i] = gy[0]; F.fz[i] = gz[0]; }
+      ax[i] = gx[0] + W.nacc[0][lane]; ay[i] = gy[0] + W.nacc[1][lane]; az[i] = gz[0] + W.nacc[2][lane];
+    }
   }
   n_open = (unsigned long long)warp_sum_ll((long long)n_open); n_acc = (unsigned long long)warp_sum_ll((long long)n_acc);
-  if (lane == 0 && do_grav) { atomicAdd(&ctr->grav_opened, n_open); atomicAdd(&ctr->grav_accepted, n_acc); }
+  if (MODE == 0 && lane == 0 && do_grav) { atomicAdd(&ctr->grav_opened, n_open); atomicAdd(&ctr->grav_accepted, n_acc); }
+#ifdef GW_STATS
+  if (lane == 0) for (int k = 0; k < 16; ++k) if (gws[k]) atomicAdd(&gw_stats[k], gws[k]);
+#endif
+}
+
+// The near field from the recorded pairs (see "Far-field reuse"): one warp per run, lane = particle, trip k evaluates
+// the k-th recorded node of every lane (coalesced index load, gathered 32-byte node read) with the current h and adds
+// it in the order the full walk did; the stored far sum completes the acceleration.  dynamic smem: the kernel table.
+#define GN_WARPS 8
+__global__ void __launch_bounds__(GN_WARPS * 32)
+k_gravity_near(int n_runs, const int2* __restrict__ groups, DevParams P, const WNode* __restrict__ wn, const double* __restrict__ x,
+               const double* __restrict__ y, const double* __restrict__ z, const double* __restrict__ h, const double* __restrict__ g_gt,
+               double* __restrict__ ax, double* __restrict__ ay, double* __restrict__ az, FarField F) {
+  extern __shared__ __align__(16) double gsm[];
+  double* gt = gsm;
+  for (int i = threadIdx.x; i <= P.nq; i += blockDim.x) gt[i] = g_gt[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  for (int run = blockIdx.x * GN_WARPS + (threadIdx.x >> 5); run < n_runs; run += gridDim.x * GN_WARPS) {
+    const int2 tg = groups[run];
+    if (tg.y == 0 || F.ovf[run]) continue;
+    const int i = tg.x + lane;
+    const bool live = lane < tg.y;
+    const double xi = live ? x[i] : 0.0, yi = live ? y[i] : 0.0, zi = live ? z[i] : 0.0;
+    const double hi = live ? (P.variable_h ? h[i] : P.h_fixed) : 1.0;
+    const double inv_h = 1.0 / hi, h2x4 = 4.0 * hi * hi, soft = 0.001 * P.h_fixed;          // F:275 (the reuse is off under the (test new) softening)
+    const int cnt = live ? F.cnt[(size_t)run * 32 + lane] : 0;
+    int cmax = cnt;
+    for (int o = 16; o > 0; o >>= 1) cmax = max(cmax, __shfl_xor_sync(FULL_MASK, cmax, o));
+    const int* lst = F.list + ((size_t)run * F.slots) * 32 + lane;
+    double nx = 0.0, ny = 0.0, nz = 0.0, dum = 0.0;
+    int k = 0;
+    for (; k + 2 <= cmax; k += 2) {             // two gathers in flight per lane; the sums stay in recorded order
+      const bool on0 = k < cnt, on1 = k + 1 < cnt;
+      const int j0 = on0 ? lst[(size_t)k * 32] : 0, j1 = on1 ? lst[(size_t)(k + 1) * 32] : 0;
+      const double2* p0 = reinterpret_cast<const double2*>(wn + j0); const double2* p1 = reinterpret_cast<const double2*>(wn + j1);
+      const double2 a0 = __ldg(p0), b0 = __ldg(p0 + 1), a1 = __ldg(p1), b1 = __ldg(p1 + 1);
+      grav_term<3>(a0, make_double2(b0.x, P.G * b0.y), on0, xi, yi, zi, inv_h, h2x4, 0.0, soft, gt, P.nq, P.dq, P.inv_dq, dum, dum, dum, nx, ny, nz);
+      grav_term<3>(a1, make_double2(b1.x, P.G * b1.y), on1, xi, yi, zi, inv_h, h2x4, 0.0, soft, gt, P.nq, P.dq, P.inv_dq, dum, dum, dum, nx, ny, nz);
+    }
+    if (k < cmax) {
+      const bool on0 = k < cnt;
+      const int j0 = on0 ? lst[(size_t)k * 32] : 0;
+      const double2* p0 = reinterpret_cast<const double2*>(wn + j0);
+      const double2 a0 = __ldg(p0), b0 = __ldg(p0 + 1);
+      grav_term<3>(a0, make_double2(b0.x, P.G * b0.y), on0, xi, yi, zi, inv_h, h2x4, 0.0, soft, gt, P.nq, P.dq, P.inv_dq, dum, dum, dum, nx, ny, nz);
+    }
+    if (live) { ax[i] = F.fx[i] + nx; ay[i] = F.fy[i] + ny; az[i] = F.fz[i] + nz; }
+  }
 }
 
 // Gravity walk groups: runs of GRAV_CHUNK_WIDTH Morton-consecutive particles.  The gravity walk tolerates a run that

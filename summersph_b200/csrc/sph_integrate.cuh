@@ -17,6 +17,8 @@ struct SimScalars {
   int    err;             // sticky error flag (key depth)
   int    any_sink_mass;   // any(sinks%mass > 0) F:919
   unsigned long long create_cand;   // (id << 32) | sorted index of the first over-dense particle, ~0 if none
+  int    far_bad;         // end of step: the stored far-field gravity may not be kept (k_far_check)
+  int    far_ovf;         // runs of the last full gravity walk whose recorded near pairs did not fit their slots
 };
 
 struct StateArrays { double *x, *y, *z, *vx, *vy, *vz, *u, *m, *alpha, *h; int* id; };

@@ -66,6 +66,8 @@ def load_library(path=None):
     lib.sph_launch_count.restype = i64
     lib.sph_group_count.argtypes = [vp]
     lib.sph_group_count.restype = i64
+    lib.sph_far_reuse_count.argtypes = [vp]
+    lib.sph_far_reuse_count.restype = i64
     lib.sph_timer_start.argtypes = [vp]
     lib.sph_timer_stop.argtypes = [vp, C.POINTER(dbl)]
     lib.sph_fp64_peak.argtypes = [vp, C.POINTER(dbl)]
@@ -295,3 +297,7 @@ class Engine:
 
     def group_count(self):
         return int(self._l.sph_group_count(self._c))
+
+    def far_reuse_count(self):
+        """Gravity evaluations so far that walked only the near field on top of the stored far sums."""
+        return int(self._l.sph_far_reuse_count(self._c))

@@ -353,10 +353,13 @@ def test_tree_reuse_is_bit_identical(mode, E, monkeypatch):
     """Evaluation A of a step sees the positions of the previous step's evaluation B (F:894 after F:905): the
     engine keeps that tree and only refreshes the reach R = 2h + size/2 with the new h (V:1152).  The state after
     several steps must equal, bit for bit, the state of a context that rebuilds the tree in every evaluation
-    (which is what the oracle-checked tests above establish as the reference's result)."""
+    (which is what the oracle-checked tests above establish as the reference's result).  The far-field reuse of the
+    gravity walk rides on the kept tree and changes the summation order, so it is off in both runs here; it has its
+    own tests below."""
     p = default_params(mode)
     b, s = ics.keplerian_disc(20_000, seed=5)
     out = []
+    monkeypatch.setenv("SPH_B200_NO_FAR_REUSE", "1")
     for no_reuse in (False, True):
         if no_reuse:
             monkeypatch.setenv("SPH_B200_NO_TREE_REUSE", "1")
@@ -375,6 +378,88 @@ def test_tree_reuse_is_bit_identical(mode, E, monkeypatch):
         assert np.array_equal(getattr(b0, k), getattr(b1, k)), k
     for k in ("x", "y", "z", "vx", "vy", "vz", "m"):
         assert np.array_equal(getattr(s0, k), getattr(s1, k)), k
+
+
+FAR_ENVS = {"lists": {}, "walk": {"SPH_B200_NO_FAR_LISTS": "1"}, "overflow": {"SPH_B200_FAR_SLOTS": "48"}, "off": {"SPH_B200_NO_FAR_REUSE": "1"}}
+
+
+@pytest.mark.parametrize("mode", [MODE_FIXED_H, MODE_VARIABLE_H])
+def test_far_field_reuse_matches_full_walk(mode, E, monkeypatch):
+    """Evaluation A of a loop body keeps the far-field gravity sums of the previous body's evaluation B (same positions,
+    tree, sinks; F:894 after F:905-912) and adds only the near field with the new h - from the near pairs the full walk
+    recorded ("lists"), by the near-only walk ("walk"), or both where some run's pairs did not fit their slots
+    ("overflow").  Same terms as the full walk in another order: dt / t equal, state within rounding of a run that walks
+    the whole tree in every evaluation ("off")."""
+    p = default_params(mode)
+    b, s = ics.keplerian_disc(20_000, seed=5)
+    out = {}
+    for name, env in FAR_ENVS.items():
+        for k in ("SPH_B200_NO_FAR_LISTS", "SPH_B200_FAR_SLOTS", "SPH_B200_NO_FAR_REUSE"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        with E(p) as e:
+            e.upload(b, s)
+            dt, t = 0.01, 0.0
+            for _ in range(4):
+                dt, t = e.step(dt, t)
+            e.evaluate()
+            out[name] = (dt, t, e.download(), e.diag(), e.counters(), e.far_reuse_count())
+    dt1, t1, (b1, s1), d1, c1, n1 = out["off"]
+    assert n1 == 0
+    for name in ("lists", "walk", "overflow"):
+        dt0, t0, (b0, s0), d0, c0, n0 = out[name]
+        assert n0 >= 3, name                  # evaluation A of steps 2-4 and the evaluation after the last step; the first
+        if len(b0) == len(b) and mode == MODE_FIXED_H:      # calc_smoothing of a variable-h run may move an IC's h beyond its cutoff
+            assert n0 == 4, name
+        assert (dt0, t0) == (dt1, t1), name
+        for k in GAS_FIELDS:
+            assert relerr(getattr(b0, k), getattr(b1, k)) < 1e-12, (name, k)
+        for k in ("x", "y", "z", "vx", "vy", "vz", "m"):
+            assert relerr(getattr(s0, k), getattr(s1, k)) < 1e-12, (name, k)
+        for k in d0:
+            assert relerr(d0[k], d1[k]) < 1e-12, (name, k)
+        assert c0 == c1, name                 # the near-only evaluation reports the counts of the accepted sets it stands for
+
+
+@pytest.mark.parametrize("mode", [MODE_FIXED_H, MODE_VARIABLE_H])
+def test_far_field_reuse_vs_oracle(mode, E, O):
+    """The near-only evaluation against the oracle's full evaluation of the same state (two sinks, accretion on: steps
+    that remove particles void the stored sums and walk the whole tree)."""
+    p = default_params(mode)
+    b, s = ics.keplerian_disc(10_000, seed=31)
+    with E(p) as e:
+        e.upload(b, s)
+        dt, t = 0.01, 0.0
+        for _ in range(3):
+            dt, t = e.step(dt, t)
+        be, se = e.download()
+        n_before = e.far_reuse_count()
+        e.evaluate()
+        reused = e.far_reuse_count() - n_before
+        o = O(p); o.record_neighbours(True); o.upload(be, se); o.evaluate()
+        do, de = o.diag(), e.diag()
+        for k in do:
+            assert relerr(de[k], do[k]) < TOL, f"{k}: {relerr(de[k], do[k]):.3e}"
+        assert o.counters()["grav_accepted"] == e.counters()["grav_accepted"]
+        # a step that removed nothing leaves the sums standing
+        if e.sizes() == (len(b), len(s)):
+            assert reused == 1
+
+
+def test_far_field_reuse_h_cutoff(E):
+    """A smoothing length that grows beyond the cutoff its near / far split was taken with (1.1 h) voids the stored sums:
+    the next evaluation walks the whole tree.  Forced here by a state whose h is far from converged (eta (m/rho)^(1/3)
+    moves it by much more than 10 % in calc_smoothing)."""
+    p = default_params(MODE_VARIABLE_H)
+    b, s = ics.keplerian_disc(10_000, seed=4)
+    b.h[:] = 0.5 * b.h
+    with E(p) as e:
+        e.upload(b, s)
+        dt, t = e.step(0.01, 0.0)
+        assert e.far_reuse_count() == 0
+        dt, t = e.step(dt, t)            # evaluation A of this step: h doubled since the sums were stored
+        assert e.far_reuse_count() == 0
 
 
 def test_candidate_list_pool_overflow_falls_back(E, monkeypatch):
