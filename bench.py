@@ -183,7 +183,7 @@ def timed_run(e, n, steps, warmup, barrier, sampler=None, before=None):
     barrier()
     if sampler:
         sampler.start()
-    l0 = e.launch_count()
+    l0 = e.launch_count(); f0 = e.far_reuse_count()
     e.timer_start()
     for _ in range(steps):
         dt, t = e.step(dt, t)
@@ -192,6 +192,7 @@ def timed_run(e, n, steps, warmup, barrier, sampler=None, before=None):
     ms = e.timer_stop()
     barrier()
     clocks = sampler.stop() if sampler else None
+    stage_acc["_gravity_near_launches"] = e.far_reuse_count() - f0       # evaluations that kept the stored far sums (k_gravity_near instead of the full walk)
     return ms, stage_acc, e.launch_count() - l0, clocks, (dt, t)
 
 
@@ -271,6 +272,7 @@ def main():
             want_drift = args.drift and form == 0      # sph_conserved walks the single-rank / replicated tree
             ms, stage_acc, launches, clocks, (dt, t) = timed_run(e, n, args.steps, args.warmup, barrier, sampler,
                                                                  before=(lambda: cons.update(first=e.conserved())) if want_drift else None)
+            near_launches = int(stage_acc.pop("_gravity_near_launches", 0))
         except Exception as ex:                  # noqa: BLE001 - reported in the line
             err = f"{type(ex).__name__}: {ex}"[:300]
         if allmax(1.0 if err else 0.0) == 0.0:
@@ -326,6 +328,12 @@ def main():
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
+            if world == 1:       # sph_step_host: the same three operations in one call, copies under the compute
+                so = Sinks.empty(len(hs) + 8)
+                dt2, t2, n_loc, ns2 = e.step_host(views(n_loc), hs, dt2, t2, into=(views(capn), so))
+                hs = Sinks(*[getattr(so, k)[:ns2] for k in ("x", "y", "z", "vx", "vy", "vz", "m", "radius")])
+                moved += n_loc
+                continue
             if decomp:
                 e.upload_local(n, views(n_loc), hs, numbers=num.numpy()[:n_loc])
             else:
@@ -358,6 +366,7 @@ def main():
             e5 = engine_for(p, local, rank, world)
             e5.ics_disc(N_CONFIG5, seed=20251018)
             ms5, st5, _, _, _ = timed_run(e5, N_CONFIG5, 2, 2, barrier)
+            st5.pop("_gravity_near_launches", None)
             ms5 = allmax(ms5)
             h5, sums5 = e5.state_hash()
             config5 = {"workload": f"Keplerian disc {N_CONFIG5} gas + 1 sink (BASELINE configs[4])", "particles": N_CONFIG5, "n_gpus": world, "steps": 2, "warmup": 2,
@@ -373,7 +382,10 @@ def main():
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         per_launch = {"sph": (BYTES_SPH_PER_LAUNCH, "k_force"), "density": (BYTES_DENSITY_PER_LAUNCH, "k_density"), "gravity": (BYTES_GRAVITY_PER_LAUNCH, "k_gravity")}
         dom = max(per_launch, key=lambda k: stage_acc.get(k, 0.0))
-        dom_ms = stage_acc[dom] / (2 * args.steps)           # two launches per step
+        # launches of the dominant kernel in the timed region: two per step, except that a gravity evaluation on the stored
+        # far sums (evaluation A of a step that follows a step without removals) is k_gravity_near, timed apart ("gravity_near")
+        dom_launches = 2 * args.steps - (near_launches if dom == "gravity" else 0)
+        dom_ms = stage_acc[dom] / max(dom_launches, 1)
         achieved = per_launch[dom][0] * (n / world) / (dom_ms * 1e-3) / 1e9       # one rank's launch processes n / world targets
         traffic = None; traffic_note = "no ncu capture at this particle count in profiles/"
         try:
@@ -391,7 +403,8 @@ def main():
             return (c["density_candidates"] * FLOPS["density_candidate"] + c["sph_pairs"] * FLOPS["sph_pair"]
                     + c["grav_opened"] * FLOPS["grav_opened"] + c["grav_accepted"] * FLOPS["grav_accepted"] + n * ns_now * FLOPS["sink_gas"])
         step_flops = 2.0 * flops(counters)
-        step_flops_exec = 2.0 * flops(counters_exec)
+        grav_flops_exec = counters_exec["grav_opened"] * FLOPS["grav_opened"] + counters_exec["grav_accepted"] * FLOPS["grav_accepted"] + n * ns_now * FLOPS["sink_gas"]
+        step_flops_exec = 2.0 * flops(counters_exec) - grav_flops_exec * near_launches / args.steps      # evaluations on the stored far sums execute only the near pairs (not counted)
         dom_flops = {"gravity": counters["grav_opened"] * FLOPS["grav_opened"] + counters["grav_accepted"] * FLOPS["grav_accepted"] + n * ns_now * FLOPS["sink_gas"],
                      "sph": counters["sph_pairs"] * FLOPS["sph_pair"], "density": counters["density_candidates"] * FLOPS["density_candidate"]}[dom]
         dom_tflops = dom_flops / world / (dom_ms * 1e-3) / 1e12
@@ -408,11 +421,15 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "what": ("sph_upload_local + sph_step + sph_download_local per step: every rank moves the rows it owns (pinned host SoA + their numbers)" if decomp else
-                                                 "sph_upload (pinned host SoA) + sph_step + sph_download (ascending number order) per step")},
+                                                 ("sph_step_host per step: upload (pinned host SoA) + one loop body + download (ascending number order) in one call, the copies under the compute" if world == 1 else
+                                                  "sph_upload (pinned host SoA) + sph_step + sph_download (ascending number order) per step"))},
             "gpu_launches": launches,
+            "gravity_far_reuse": {"near_only_evaluations": near_launches, "of": 2 * args.steps,
+                                  "what": "evaluation A of a step sees the positions, tree and sinks of the step before (F:894 after F:905-912): it keeps that evaluation's far-field sums "
+                                          "and re-evaluates the recorded near pairs with the new h (k_gravity_near, stage gravity_near); same terms as a full walk, summed in another order"},
             "roofline": {"bound": "fp64", "kernel": per_launch[dom][1], "achieved": dom_tflops, "peak": fp64_one, "unit": "TFLOP/s", "frac": dom_tflops / fp64_one,
                          "peak_source": "in-library FP64 FMA probe (sph_fp64_peak) run at the end of this process; MEASURED_PEAKS.json holds no FP64 figure",
-                         "launch_ms": dom_ms, "algorithmic_flops_per_launch": dom_flops / world,
+                         "launch_ms": dom_ms, "launches": dom_launches, "algorithmic_flops_per_launch": dom_flops / world,
                          "hbm": {"achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "peak_source": peak_src,
                                  "algorithmic_bytes_per_particle_per_launch": per_launch[dom][0]},
                          "traffic": traffic, "traffic_note": traffic_note,
@@ -420,7 +437,7 @@ def main():
             "fp64": {"achieved_tflops": step_flops / sec / 1e12, "peak_tflops": fp64_peak, "frac": step_flops / sec / 1e12 / fp64_peak,
                      "algorithmic_flops_per_step": step_flops,
                      "executed": {"flops_per_step": step_flops_exec, "achieved_tflops": step_flops_exec / sec / 1e12, "frac": step_flops_exec / sec / 1e12 / fp64_peak,
-                                  "what": "the same per-interaction flop counts on the pairs the timed kernels actually tested (exact-zero pairs are culled before any FP64 work)"},
+                                  "what": "the same per-interaction flop counts on the pairs the timed kernels actually tested (exact-zero pairs are culled before any FP64 work; a gravity evaluation that kept the stored far sums counts as zero)"},
                      "how": "reference-expression flop counts x interaction counters (SURVEY.md 8(d)): 44 per density candidate, 173 per unordered pair, 13 / 35 per opened / accepted node, 20 per sink-gas pair"},
             "hbm_step": {"achieved": BYTES_PER_PARTICLE_STEP * n / sec / 1e9, "peak": hbm_peak * world,
                          "frac": BYTES_PER_PARTICLE_STEP * n / sec / 1e9 / (hbm_peak * world), "unit": "GB/s"},

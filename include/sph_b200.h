@@ -170,6 +170,21 @@ int sph_evaluate(sph_ctx* ctx, int32_t mask);
 int sph_step(sph_ctx* ctx, double* dt_inout, double* t_inout,
              int64_t* n_gas_out, int32_t* n_sink_out);
 
+/* sph_upload + sph_step + sph_download in one call for a host that owns the state between steps (the reference's loop,
+ * SUMMER_SPH.f90:879-929, keeps bodies(:) / sinks(:) on its side), single rank.  The copies run under the compute when the
+ * host arrays are page-locked: x y z go first and the tree build starts on them while the other columns follow in the
+ * order their first readers come (h: leaf cells, m: node sums, u: EOS, v / alpha: pair loop); x y z (final after the
+ * drift, :903) and m leave while evaluation B runs, v u alpha after the second kick (:912), h after calc_smoothing
+ * (Variable.f90:1152).  If the step removed particles every column is sent again, compacted.  Results are bit-identical
+ * to the three separate calls.
+ *   gas_in[10]  = x y z vx vy vz u m alpha h (alpha may be NULL = 0; h may be NULL in fixed-h mode), n_gas rows each
+ *   sink_in[8]  = x y z vx vy vz m radius, n_sink rows each (NULL when n_sink = 0; radius NaN / NULL = params.sink_radius)
+ *   gas_out[10] = where the rows go, ascending `number`, capacity >= n_gas each (entries may be NULL; may alias gas_in)
+ *   sink_out[8] = capacity >= n_sink + 8 each (entries may be NULL) */
+int sph_step_host(sph_ctx* ctx, int64_t n_gas, const double* const* gas_in, int32_t n_sink, const double* const* sink_in,
+                  double* dt_inout, double* t_inout, double* const* gas_out, double* const* sink_out,
+                  int64_t* n_gas_out, int32_t* n_sink_out);
+
 /* Device-resident loop: step until t >= t_stop or max_steps (<=0: unlimited) steps. */
 int sph_run_until(sph_ctx* ctx, double t_stop, int64_t max_steps,
                   double* dt_inout, double* t_inout, int64_t* steps_out,

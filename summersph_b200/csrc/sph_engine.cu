@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <cmath>
+#include <ctime>
 #include <string>
 #include <vector>
 #include <algorithm>
@@ -32,7 +33,7 @@ namespace {
 
 thread_local std::string g_create_error;
 
-enum Stage { ST_KEYS = 0, ST_SORT, ST_TREE, ST_DENSITY, ST_GRAVITY, ST_SPH, ST_INTEGRATE, ST_HITER, ST_CULL, ST_COMM, ST_HALO, ST_LET, ST_MIGRATE, ST_COUNT };   // the last three: domain decomposition only
+enum Stage { ST_KEYS = 0, ST_SORT, ST_TREE, ST_DENSITY, ST_GRAVITY, ST_SPH, ST_INTEGRATE, ST_HITER, ST_CULL, ST_COMM, ST_HALO, ST_LET, ST_MIGRATE, ST_GRAV_NEAR, ST_COUNT };   // halo / let / migrate: domain decomposition only; grav_near: gravity evaluations on the stored far sums
 
 // x**n in libgcc __powidf2 order (kernel tables, SUMMER_SPH.f90:63-100)
 inline double powi(double x, int n) { double y = (n % 2) ? x : 1.0; while (n >>= 1) { x = x * x; if (n % 2) y *= x; } return y; }
@@ -77,6 +78,7 @@ struct sph_ctx {
   SinkArrays S = {}; double* sink_buf = nullptr; double* sink_partial = nullptr; size_t sink_partial_cap = 0;
   double* sink_seg = nullptr; size_t sink_seg_cap = 0;     // [global GRAV_SEG segment][sink][3]: gas terms of the sink accelerations (exchanged between ranks)
   SimScalars* sc = nullptr; SimScalars* h_sc = nullptr;     // device + pinned host mirror
+  int* h_rb = nullptr;                                      // pinned scratch for readback(): 16 ints
   WalkCounters* ctr = nullptr; WalkCounters* h_ctr = nullptr; int* work = nullptr;
   unsigned char* keep = nullptr; unsigned long long* acc_key[2] = {}; int* acc_val[2] = {}; int* d_nsel = nullptr;
   int* pos = nullptr;           // ascending-number position of each sorted particle (downloads)
@@ -101,8 +103,14 @@ struct sph_ctx {
   double* cons_partial = nullptr; double* cons_out = nullptr;   // sph_conserved: block partials, result slots
   // far-field reuse of the gravity walk (sph_gravity.cuh): stored far sums, per-particle near / far split, the sinks and counters they were taken with
   double *far_fx = nullptr, *far_fy = nullptr, *far_fz = nullptr, *far_hc2 = nullptr, *far_sink_a = nullptr; SinkSnap* far_snap = nullptr; unsigned long long* far_ctr = nullptr;
-  bool far_valid = false; int far_reuse = 1; int64_t far_count = 0;
+  bool far_valid = false; int far_reuse = 1; int64_t far_count = 0; bool far_want_store = false; int steps_since_upload = 0; double far_hcut = GW_HCUT;
   int* far_list = nullptr; int* far_cnt = nullptr; unsigned char* far_ovf = nullptr; size_t far_list_runs = 0; int far_slots = 128; bool far_lists = true; int far_n_ovf = 0;   // recorded near pairs: [run][slot][lane]
+  // sph_step_host: copies under the compute.  Late fields = gas columns still on their way from the host when the tree build starts
+  // (they land in st[0] on io_stream; the state re-order permutes them when their first reader is due); early results leave
+  // through staging buffers on io_stream while the step goes on
+  cudaStream_t io_stream = nullptr; cudaEvent_t io_ev_xyz = nullptr, io_ev_out = nullptr, io_ev_done = nullptr, io_ev_field[10] = {};
+  unsigned late_pending = 0; const double* late_src[10] = {}; double* late_dst[10] = {}; const int* late_perm = nullptr; bool late_permuted = false; int late_order[10] = {}; int late_n = 0;
+  double* io_stage[5] = {}; size_t io_stage_cap = 0; bool io_active = false; double* io_out[10] = {}; unsigned io_fetched = 0; bool io_busy = false;
   double* sink_spin = nullptr; int sink_extras = 0;               // SPH_FLAG_SINK_MERGE_SPIN: spin[3][SPH_MAX_SINKS]; null pointer into the kernels when off
   double* img_table = nullptr;
   // ---- Morton-domain decomposition (sph_domain.cuh / sph_domain_host.inl); in this mode n = own particles, cap = own + halo capacity
@@ -422,6 +430,11 @@ int allreduce(sph_ctx* c, void* buf, size_t count, int dtype, int op) {
 }
 
 __global__ void k_set_int(int* p, int v) { *p = v; }
+// A few control words back to the host by a kernel store into page-locked host memory (device-visible under unified
+// addressing): a copy-engine transfer would queue behind the bulk columns sph_step_host has in flight on its own stream
+// (measured: 10 ms per step-end read-back at 16M).  Valid on the host after the stream synchronises.
+__global__ void k_readback(const int* __restrict__ src, int* __restrict__ dst, int nwords) { for (int i = threadIdx.x; i < nwords; i += blockDim.x) dst[i] = src[i]; }
+void readback(sph_ctx* c, void* pinned_dst, const void* dev_src, size_t bytes);
 __global__ void k_iota_from(int n, int first, int* a) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) a[i] = first + i; }
 
 // first walk group of every rank's target slice (n_ranks + 1 entries): contiguous, cut only at multiples of GRAV_SEG
@@ -447,7 +460,29 @@ int compute_slices(sph_ctx* c) {
 // ---------------------------------------------------------------------------------------------------
 // tree
 // ---------------------------------------------------------------------------------------------------
+void readback(sph_ctx* c, void* pinned_dst, const void* dev_src, size_t bytes) { LAUNCH(k_readback, 1, 64, 0, (const int*)dev_src, (int*)pinned_dst, (int)(bytes / 4)); }
 int build_tree_impl(sph_ctx* c, bool* retry_two_word);
+
+// sph_step_host: gas columns that were still in flight when the state was re-ordered.  They arrive in late_order; when a
+// reader of some of them is due, everything queued up to the last one it needs is waited for and re-ordered (one launch).
+int flush_late(sph_ctx* c, unsigned need) {
+  const unsigned m = c->late_pending & need;
+  if (!m) return SPH_OK;
+  int last = -1;
+  for (int k = 0; k < c->late_n; ++k) if ((m >> c->late_order[k]) & 1u) last = k;
+  PermuteArgs pa; std::memset(&pa, 0, sizeof(pa));
+  unsigned done = 0;
+  for (int k = 0; k <= last; ++k) {
+    const int f = c->late_order[k];
+    if (!((c->late_pending >> f) & 1u)) continue;
+    done |= 1u << f; pa.src[f] = c->late_src[f]; pa.dst[f] = c->late_dst[f];
+  }
+  CK(cudaStreamWaitEvent(c->stream, c->io_ev_field[c->late_order[last]], 0));
+  if (c->late_permuted) LAUNCH(k_permute, cdiv(c->n, 4 * 256), 256, 0, (int)c->n, c->late_perm, pa);      // before any re-order they are in place already
+  c->late_pending &= ~done;
+  return SPH_OK;
+}
+enum { LF_H = 1u << 9, LF_M = 1u << 7, LF_U = 1u << 6, LF_ALL = 0x3ffu };
 
 #include "sph_domain_host.inl"
 
@@ -492,6 +527,7 @@ int build_tree_impl(sph_ctx* c, bool* retry_two_word) {
   const int T = 256;
   *retry_two_word = false;
   if (c->two_word && !c->key_lo[0]) { for (int b = 0; b < 2; ++b) DA(c->key_lo[b], c->cap); }
+  if (c->late_pending && c->late_permuted) { int r_ = flush_late(c, LF_ALL); if (r_) return r_; }      // a second re-order (two-word retry) takes complete columns
   stage_begin(c, ST_KEYS);
   {
     StateArrays s = state_of(c, c->cur);
@@ -520,6 +556,10 @@ int build_tree_impl(sph_ctx* c, bool* retry_two_word) {
     PermuteArgs pa;
     for (int f = 0; f < 10; ++f) { pa.src[f] = c->st[c->cur][f]; pa.dst[f] = c->st[c->cur ^ 1][f]; }
     pa.id_src = c->id[c->cur]; pa.id_dst = c->id[c->cur ^ 1];
+    if (c->late_pending) {      // sph_step_host: columns still arriving are re-ordered when their first reader is due (flush_late)
+      for (int f = 0; f < 10; ++f) if ((c->late_pending >> f) & 1u) { c->late_src[f] = pa.src[f]; c->late_dst[f] = pa.dst[f]; pa.src[f] = nullptr; }
+      c->late_perm = c->perm[0]; c->late_permuted = true;
+    }
     LAUNCH(k_permute, cdiv(n, 4 * T), T, 0, n, c->perm[0], pa);
     c->cur ^= 1;
     if (c->two_word) {     // regenerate both key words in the final order from the re-ordered positions
@@ -532,6 +572,7 @@ int build_tree_impl(sph_ctx* c, bool* retry_two_word) {
   {
     StateArrays s = state_of(c, c->cur);
     const uint64_t* klo = c->two_word ? c->key_lo[0] : nullptr;
+    { int r_ = flush_late(c, LF_H); if (r_) return r_; }
     LAUNCH(k_leaf, cdiv(n, T), T, 0, n, c->key[0], klo, s.h, c->root, c->dp, c->level, c->lcx, c->lcy, c->lcz, c->reach, &c->sc->err);
     // octree
     LAUNCH(k_oct_nodes<false>, cdiv(n, T), T, 0, n, c->key[0], klo, c->dp.lmax, c->root, c->cnt, c->off, 0, c->nodes, c->node_part, c->node_count);
@@ -539,10 +580,10 @@ int build_tree_impl(sph_ctx* c, bool* retry_two_word) {
     size_t bytes = c->cub_bytes;
     CK(cub::DeviceScan::ExclusiveSum(c->cub_tmp, bytes, c->cnt, c->off, n + 1, c->stream));
     // node count is needed on the host for launch sizes of the per-node passes
-    int n_int = 0, key_err = 0;
-    CK(cudaMemcpyAsync(&n_int, c->off + n, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(&key_err, &c->sc->err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    readback(c, c->h_rb, c->off + n, sizeof(int));
+    readback(c, c->h_rb + 1, &c->sc->err, sizeof(int));
     CK(cudaStreamSynchronize(c->stream));
+    const int n_int = c->h_rb[0], key_err = c->h_rb[1];
     if (key_err && !c->two_word) {            // a 63-bit key collision: redo this build with two-word keys
       CK(cudaMemsetAsync(&c->sc->err, 0, sizeof(int), c->stream));
       stage_end(c);
@@ -558,6 +599,7 @@ int build_tree_impl(sph_ctx* c, bool* retry_two_word) {
     CK(cudaMemsetAsync(c->widx, 0xff, sizeof(int) * (size_t)nn, c->stream));
     LAUNCH(k_oct_widx, cdiv(nn, T), T, 0, nn, c->nodes, c->wcount, c->wstart, c->widx);
     CK(cudaMemsetAsync(c->arrive, 0, sizeof(int) * (size_t)nn, c->stream));
+    { int r_ = flush_late(c, LF_M | LF_H); if (r_) return r_; }
     LAUNCH(k_oct_up, cdiv(n, T), T, 0, n, c->off, c->cnt, s.x, s.y, s.z, s.m, s.h, c->level, c->root, c->nodes, c->parent, c->nchild, c->arrive);
     LAUNCH(k_oct_finalize, cdiv(nn, T), T, 0, nn, c->nodes, c->wcount, c->wstart, c->widx, c->wnodes);
     // walk groups (cell-aligned buckets) and the implicit 8-ary BVH over them
@@ -565,9 +607,9 @@ int build_tree_impl(sph_ctx* c, bool* retry_two_word) {
     LAUNCH(k_group_mark, cdiv(nn, T), T, 0, nn, c->nodes, c->node_part, c->node_count, c->gsize);
     bytes = c->cub_bytes;
     CK(cub::DeviceSelect::Flagged(c->cub_tmp, bytes, cub::CountingInputIterator<int>(0), c->gsize, c->gfirst, c->d_nsel, n, c->stream));
-    int ng = 0;
-    CK(cudaMemcpyAsync(&ng, c->d_nsel, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    readback(c, c->h_rb, c->d_nsel, sizeof(int));
     CK(cudaStreamSynchronize(c->stream));
+    const int ng = c->h_rb[0];
     c->n_groups = ng;
     if ((size_t)ng + ng / 7 + 64 > c->bvh_cap) { c->bvh_cap = (size_t)(ng + ng / 7 + 64) * 5 / 4; DA(c->bvh, c->bvh_cap); }
     LAUNCH(k_group_pack, cdiv(ng, T), T, 0, ng, c->gfirst, c->gsize, c->groups);
@@ -617,6 +659,7 @@ DensityArrays dens_arrays(sph_ctx* c) {
 
 int run_density(sph_ctx* c) {
   const int W = DENS_WARPS;
+  { int r_ = flush_late(c, LF_U | LF_M | LF_H); if (r_) return r_; }
   stage_begin(c, ST_DENSITY);
   StateArrays s = state_of(c, c->cur);
   // pool of 32-int blocks for the saved candidate lists: about one block (30 sources) per local particle, grown
@@ -655,6 +698,7 @@ int run_hiter(sph_ctx* c) {
   return SPH_OK;
 }
 int run_force(sph_ctx* c) {
+  { int r_ = flush_late(c, LF_ALL); if (r_) return r_; }
   if (c->x_pending) { stage_begin(c, ST_COMM); int r_ = allgatherv_end(c); if (r_) return r_; stage_end(c); }
   stage_begin(c, ST_SPH);
   StateArrays s = state_of(c, c->cur);
@@ -708,11 +752,14 @@ int run_gravity(sph_ctx* c, int do_grav, int do_sinks) {
   const int GWW = grav_warps(c);
   // far-field reuse (sph_gravity.cuh): the full walk of a complete evaluation stores its far sums; while they stand
   // (far_valid: same tree, same sinks, no h beyond its cutoff - decided at the end of step()), the next one walks only the near field
-  const bool far_on = c->far_reuse && do_grav && do_sinks && !c->dp.soft_hi && !c->exact_counters && !c->sink_extras;
-  const bool near_only = far_on && c->far_valid;
+  // Stored only where the next evaluation can use it: by evaluation B of a step whose state stayed on the device since the
+  // step before (a host that uploads before every step never reuses, and should not pay for the records)
+  const bool far_ok = c->far_reuse && do_grav && do_sinks && !c->dp.soft_hi && !c->exact_counters && !c->sink_extras;
+  const bool near_only = far_ok && c->far_valid;
+  const bool far_on = far_ok && !near_only && c->far_want_store;
   if (near_only) ++c->far_count;
   if (!near_only) c->far_valid = false;      // a full walk re-takes the near / far split (and may not store at all)
-  stage_begin(c, ST_GRAVITY);
+  stage_begin(c, near_only ? ST_GRAV_NEAR : ST_GRAVITY);
   StateArrays s = state_of(c, c->cur);
   // upper bound of the number of runs in this rank's slice; unused tail entries stay empty (first = 0, count = 0)
   const int seg0 = c->g0 / GRAV_SEG, nseg = cdiv(c->g1 - c->g0, GRAV_SEG);
@@ -748,7 +795,7 @@ int run_gravity(sph_ctx* c, int do_grav, int do_sinks) {
         c->far_list = nullptr; c->far_cnt = nullptr; c->far_ovf = nullptr; c->far_list_runs = 0; c->far_lists = false;
       } else c->far_list_runs = runs;
     }
-    const bool lists = far_on && c->far_lists && c->far_list != nullptr;
+    const bool lists = (far_on || near_only) && c->far_lists && c->far_list != nullptr;
     const FarField ff{c->far_fx, c->far_fy, c->far_fz, c->far_hc2, far_on ? 1 : 0, lists ? c->far_list : nullptr, c->far_cnt, c->far_ovf, c->far_slots, &c->sc->far_ovf};
     if (near_only) {
       if (lists) LAUNCH(k_gravity_near, std::max(1, std::min(cdiv(ng, GN_WARPS), 16 * c->n_sm)), GN_WARPS * 32, gravity_smem(c, 0), ng, c->ggroups, c->dp, c->wnodes, s.x, s.y, s.z, s.h, c->d_gt, c->ax, c->ay, c->az, ff);
@@ -760,7 +807,7 @@ int run_gravity(sph_ctx* c, int do_grav, int do_sinks) {
     } else {
       LAUNCH(k_set_int, 1, 1, 0, c->work, 0);
       CK(cudaMemsetAsync(&c->sc->far_ovf, 0, sizeof(int), c->stream));
-      LAUNCH(k_far_hcut, cdiv(c->n, 256), 256, 0, (int)c->n, c->dp, s.h, far_on ? (double)GW_HCUT : 1.0, c->far_hc2);
+      LAUNCH(k_far_hcut, cdiv(c->n, 256), 256, 0, (int)c->n, c->dp, s.h, far_on ? c->far_hcut : 1.0, c->far_hc2);
       LAUNCH(k_gravity<0>, grid, GWW * 32, gravity_smem(c, GWW), 0, ng, c->ggroups, c->gbvh, c->dp, c->wnodes, s.x, s.y, s.z, s.h, s.m, c->d_gt,
              c->ax, c->ay, c->az, do_grav, ns, c->S, c->sink_partial, c->ctr, c->work, c->grav_spill, &c->sc->err, ff);
     }
@@ -788,7 +835,7 @@ int run_gravity(sph_ctx* c, int do_grav, int do_sinks) {
       int r_ = allgatherv(c, bufs, 1, roff.data()); if (r_) return r_;
       stage_end(c);
     }
-    stage_begin(c, ST_GRAVITY);
+    stage_begin(c, near_only ? ST_GRAV_NEAR : ST_GRAVITY);
     if (near_only) CK(cudaMemsetAsync(c->S.ax, 0, (size_t)SPH_MAX_SINKS * 3 * 8, c->stream));      // domains: zeros into the all-reduce below; the sinks' own sums are the stored ones
     else LAUNCH(k_sink_reduce, 1, 256, 0, nst, c->n_sink, c->sink_seg, c->S, do_sinks);
     stage_end(c);
@@ -805,7 +852,7 @@ int run_gravity(sph_ctx* c, int do_grav, int do_sinks) {
       stage_end(c);
     }
   }
-  stage_begin(c, ST_GRAVITY);
+  stage_begin(c, near_only ? ST_GRAV_NEAR : ST_GRAVITY);
   if (near_only) {       // sink accelerations and the walk's counters of the evaluation the far sums were taken in (same sinks, same gas, same accepted sets)
     CK(cudaMemcpyAsync(c->S.ax, c->far_sink_a, (size_t)SPH_MAX_SINKS * 3 * 8, cudaMemcpyDeviceToDevice, c->stream));
     LAUNCH(k_ctr_restore, 1, 1, 0, c->ctr, c->far_ctr);
@@ -832,15 +879,16 @@ int evaluate(sph_ctx* c, int mask) {
   CK(cudaMemsetAsync(c->udot, 0, nb, c->stream)); CK(cudaMemsetAsync(c->adot, 0, nb, c->stream));     // F:824
   CK(cudaMemsetAsync(c->ctr, 0, sizeof(WalkCounters), c->stream));
   if (mask & SPH_EVAL_DENSITY) { if ((r = run_density(c))) return r; }
+  if ((r = flush_late(c, LF_M | LF_H))) return r;
   if ((r = run_gravity(c, (mask & SPH_EVAL_GRAVITY) ? 1 : 0, (mask & SPH_EVAL_SINKS) ? 1 : 0))) return r;
   if (mask & SPH_EVAL_SPH) { if ((r = run_force(c))) return r; }
   else if (!c->dd) { double* bufs[3] = {c->ax, c->ay, c->az}; if ((r = allgatherv(c, bufs, 3))) return r; }
-  return SPH_OK;
+  return flush_late(c, LF_ALL);
 }
 
 int fetch_counters(sph_ctx* c) {
   { int r_ = allreduce(c, c->ctr, sizeof(WalkCounters) / 8, NC_UINT64, NC_SUM); if (r_) return r_; }
-  CK(cudaMemcpyAsync(c->h_ctr, c->ctr, sizeof(WalkCounters), cudaMemcpyDeviceToHost, c->stream));
+  readback(c, c->h_ctr, c->ctr, sizeof(WalkCounters));
   CK(cudaStreamSynchronize(c->stream));
   c->counts.n_gas = c->dd ? c->n_global : c->n;
   c->counts.density_candidates = (int64_t)c->h_ctr->dens_cand;
@@ -881,10 +929,36 @@ int compact(sph_ctx* c) {
   return SPH_OK;
 }
 
+// sph_step_host: columns that are final leave while the step goes on.  Scatter into ascending-number order on the compute
+// stream (nothing was removed since the upload of this call: number == id), copies on io_stream.
+int io_fetch(sph_ctx* c, const int* fields, int nf) {
+  if (!c->io_active || c->n != c->n_upload) return SPH_OK;
+  const int n = (int)c->n, T = 256;
+  if (c->io_busy) CK(cudaStreamWaitEvent(c->stream, c->io_ev_done, 0));      // the staging buffers of the batch before
+  int used = 0; int fl[5];
+  for (int k = 0; k < nf && used < 5; ++k) {
+    const int f = fields[k];
+    if (!c->io_out[f]) continue;
+    LAUNCH(k_scatter_d, cdiv(n, T), T, 0, n, c->id[c->cur], c->st[c->cur][f], c->io_stage[used]);
+    fl[used++] = f;
+  }
+  if (!used) return SPH_OK;
+  CK(cudaEventRecord(c->io_ev_out, c->stream));
+  CK(cudaStreamWaitEvent(c->io_stream, c->io_ev_out, 0));
+  for (int k = 0; k < used; ++k) {
+    CK(cudaMemcpyAsync(c->io_out[fl[k]], c->io_stage[k], (size_t)n * 8, cudaMemcpyDeviceToHost, c->io_stream));
+    c->io_fetched |= 1u << fl[k];
+  }
+  CK(cudaEventRecord(c->io_ev_done, c->io_stream));
+  c->io_busy = true;
+  return SPH_OK;
+}
+
 int step(sph_ctx* c) {
   const int T = 256;
   int r;
   int n = (int)c->n;
+  c->far_want_store = false;                                                   // the positions move right after this evaluation
   if ((r = evaluate(c, SPH_EVAL_ALL))) return r;                              // F:894-898
   n = (int)c->n;                                                               // domains: the build may have moved particles between ranks
   stage_begin(c, ST_INTEGRATE);
@@ -892,11 +966,14 @@ int step(sph_ctx* c) {
   c->pos_moved = true;
   LAUNCH(k_kick_sinks<true>, 1, SPH_MAX_SINKS, 0, c->S, c->sc);
   stage_end(c);
+  if (c->io_active) { const int fl[4] = {0, 1, 2, 7}; if ((r = io_fetch(c, fl, 4))) return r; }      // x y z are final after the drift (F:903), m never changes
+  c->far_want_store = c->steps_since_upload >= 1;
   if ((r = evaluate(c, SPH_EVAL_ALL))) return r;                              // F:905-910
   n = (int)c->n;
   stage_begin(c, ST_INTEGRATE);
   LAUNCH(k_kick<false>, cdiv(n, T), T, 0, n, state_of(c, c->cur), rates_of(c), c->sc);      // F:912
   LAUNCH(k_kick_sinks<false>, 1, SPH_MAX_SINKS, 0, c->S, c->sc);
+  if (c->io_active) { const int fl[5] = {3, 4, 5, 6, 8}; if ((r = io_fetch(c, fl, 5))) return r; }  // v u alpha are final after the second kick (F:912)
   {
     int nb = std::max(1, std::min(cdiv(c->p1 - c->p0, T), c->n_partial));
     LAUNCH(k_dt_partial, nb, T, 0, c->p0, c->p1, c->dp, state_of(c, c->cur), rates_of(c), c->cs, c->partial);   // F:916
@@ -925,7 +1002,7 @@ int step(sph_ctx* c) {
   LAUNCH(k_any_sink_mass, 1, 32, 0, c->S, c->sc);                             // F:919
   LAUNCH(k_flags, cdiv(n, T), T, 0, n, c->dp, state_of(c, c->cur), c->key[0], c->two_word ? c->key_lo[0] : nullptr, c->level, c->lcx, c->lcy, c->lcz, c->reach, c->root,
          c->S, c->sc, c->keep, c->acc_key[0], c->acc_val[0], (int)c->cap);
-  CK(cudaMemcpyAsync(c->h_sc, c->sc, sizeof(SimScalars), cudaMemcpyDeviceToHost, c->stream));
+  readback(c, c->h_sc, c->sc, sizeof(SimScalars));
   CK(cudaStreamSynchronize(c->stream));
   if ((r = check_device_error(c))) return r;
   if (c->h_sc->n_accreted > (int)c->cap) {      // k_flags already dropped the particles: never truncate silently
@@ -960,9 +1037,9 @@ int step(sph_ctx* c) {
     LAUNCH(k_far_check, cdiv(std::max<int64_t>(c->n, SPH_MAX_SINKS), T), T, 0, (int)c->n, c->dp, state_of(c, c->cur).h, c->far_hc2, c->S, &c->sc->n_sink, c->far_snap, &c->sc->far_bad);
     if (c->dd) { int r_ = allreduce(c, &c->sc->far_bad, 1, NC_INT32, NC_MAX); if (r_) return r_; }
   }
-  CK(cudaMemcpyAsync(c->h_sc, c->sc, sizeof(SimScalars), cudaMemcpyDeviceToHost, c->stream));
-  int nl_host[4] = {0, 0, 0, 0};
-  CK(cudaMemcpyAsync(nl_host, c->nl_ctl, sizeof(nl_host), cudaMemcpyDeviceToHost, c->stream));
+  readback(c, c->h_sc, c->sc, sizeof(SimScalars));
+  int* const nl_host = c->h_rb + 4;
+  readback(c, nl_host, c->nl_ctl, 4 * sizeof(int));
   CK(cudaStreamSynchronize(c->stream));
   if (nl_host[2]) {                          // the candidate-list pool overflowed in this step: double it for the next one
     const size_t want = c->nl_pool_blocks * 2;
@@ -972,6 +1049,7 @@ int step(sph_ctx* c) {
   c->nl_valid = false;
   c->far_valid = far_try && c->h_sc->far_bad == 0;
   c->far_n_ovf = c->h_sc->far_ovf;
+  ++c->steps_since_upload;
   c->n_sink = c->h_sc->n_sink;
   stage_end(c);
   return SPH_OK;
@@ -1070,6 +1148,7 @@ int sph_create(const sph_params* p, int32_t device, sph_ctx** out) {
   c->fused_push = getenv("SPH_B200_NO_FUSED_PUSH") ? 0 : 1;     // developer switch: copy-engine exchange after the pair kernel
   c->far_reuse = getenv("SPH_B200_NO_FAR_REUSE") ? 0 : 1;        // developer switch: every gravity evaluation walks the whole tree
   c->far_lists = getenv("SPH_B200_NO_FAR_LISTS") ? false : true; // developer switch: the near field is always walked, never read from recorded pairs
+  if (getenv("SPH_B200_FAR_HCUT")) c->far_hcut = std::max(1.0, atof(getenv("SPH_B200_FAR_HCUT")));      // test hook: near / far split at this multiple of h (default GW_HCUT)
   if (getenv("SPH_B200_FAR_SLOTS")) c->far_slots = std::max(1, atoi(getenv("SPH_B200_FAR_SLOTS")));      // test hook: recorded near pairs per particle (overflowing runs walk)
   c->use_lists = getenv("SPH_B200_NO_LISTS") ? 0 : 1;            // developer switch: the pair loop always walks by itself     // developer switch: rebuild the tree in every evaluation
   int r;
@@ -1094,6 +1173,7 @@ int sph_create(const sph_params* p, int32_t device, sph_ctx** out) {
   c->sink_extras = (p->mode & SPH_FLAG_SINK_MERGE_SPIN) ? 1 : 0;
   if (c->sink_extras) { if ((r = dalloc(c, &c->sink_spin, (size_t)SPH_MAX_SINKS * 3))) return fail(r); cudaMemset(c->sink_spin, 0, (size_t)SPH_MAX_SINKS * 3 * 8); }
   if (cudaMallocHost((void**)&c->h_sc, sizeof(SimScalars)) != cudaSuccess || cudaMallocHost((void**)&c->h_ctr, sizeof(WalkCounters)) != cudaSuccess) { c->err = "cudaMallocHost failed"; return fail(SPH_ERR_OOM); }
+  if (cudaMallocHost((void**)&c->h_rb, 16 * sizeof(int)) != cudaSuccess) { c->err = "cudaMallocHost failed"; return fail(SPH_ERR_OOM); }
   std::memset(c->h_sc, 0, sizeof(SimScalars)); c->h_sc->create_cand = ~0ull; c->h_sc->dt = 1.0e-2;
   cudaMemcpy(c->sc, c->h_sc, sizeof(SimScalars), cudaMemcpyHostToDevice);
   cudaMemset(c->ctr, 0, sizeof(WalkCounters));
@@ -1125,6 +1205,8 @@ int sph_destroy(sph_ctx* c) {
   for (auto ev : c->pevent) cudaEventDestroy(ev);
   if (c->xstream) { cudaStreamSynchronize(c->xstream); cudaStreamDestroy(c->xstream); cudaEventDestroy(c->x_ready); cudaEventDestroy(c->x_done); }
   if (c->let_done) cudaEventDestroy(c->let_done);
+  if (c->io_stream) { cudaStreamSynchronize(c->io_stream); cudaStreamDestroy(c->io_stream); cudaEventDestroy(c->io_ev_xyz); cudaEventDestroy(c->io_ev_out); cudaEventDestroy(c->io_ev_done); for (int f = 0; f < 10; ++f) cudaEventDestroy(c->io_ev_field[f]); }
+  for (int k = 0; k < 5; ++k) if (c->io_stage[k]) cudaFree(c->io_stage[k]);
   if (c->d_flag) cudaFree(c->d_flag);
   if (c->d_blob) cudaFree(c->d_blob);
   if (c->comm && c->nccl.CommDestroy) c->nccl.CommDestroy(c->comm);
@@ -1142,6 +1224,7 @@ int sph_destroy(sph_ctx* c) {
   F(c->arrive); F(c->cnt); F(c->off); F(c->root); F(c->partial); F(c->cub_tmp); F(c->d_wt); F(c->d_dwt); F(c->d_gt);
   F(c->sink_buf); F(c->sink_partial); F(c->sink_seg); F(c->sc); F(c->ctr); F(c->work); F(c->keep); F(c->d_nsel); F(c->pos); F(c->stage_d); F(c->stage_d2);
   if (c->h_sc) cudaFreeHost(c->h_sc);
+  if (c->h_rb) cudaFreeHost(c->h_rb);
   if (c->h_ctr) cudaFreeHost(c->h_ctr);
   for (auto& e : c->ev_used) { cudaEventDestroy(e.second.first); cudaEventDestroy(e.second.second); }
   for (auto e : c->ev_pool) cudaEventDestroy(e);
@@ -1192,7 +1275,7 @@ int sph_comm_init_host(sph_ctx* c, int32_t rank, int32_t n_ranks, const char* na
 
 // n_local rows starting at global number id_first out of n_global (single rank / replicated: all of them)
 static int upload_impl(sph_ctx* c, int64_t n_global, int64_t id_first, int64_t n, const double* const* src,
-                       int32_t ns, const double* const* ssrc, const double* srad, bool gas_on_device = false) {
+                       int32_t ns, const double* const* ssrc, const double* srad, bool gas_on_device = false, unsigned late_mask = 0) {
   cudaSetDevice(c->device);
   c->dd = c->n_ranks > 1 && c->p.decomposition == 1;
   int64_t want = n;
@@ -1204,10 +1287,25 @@ static int upload_impl(sph_ctx* c, int64_t n_global, int64_t id_first, int64_t n
   int r = ensure_capacity(c, want); if (r) return r;
   c->n_halo = 0; c->ng_halo = 0; c->dd_info.clear();
   c->n = n; c->n_upload = n_global; c->n_global = n_global; c->cur = 0; c->tree_valid = false; c->pos_moved = true;
+  c->far_valid = false; c->steps_since_upload = 0;
+  c->late_pending = 0; c->late_permuted = false; c->late_n = 0;
   for (int f = 0; f < 10 && !gas_on_device; ++f) {
+    if (src[f] && ((late_mask >> f) & 1u)) continue;       // follows on io_stream behind x y z (below)
     if (src[f]) { if (n > 0) CK(cudaMemcpyAsync(c->st[0][f], src[f], (size_t)n * 8, cudaMemcpyHostToDevice, c->stream)); }
     else if (f == 8) CK(cudaMemsetAsync(c->st[0][f], 0, (size_t)std::max<int64_t>(n, 1) * 8, c->stream));            // alpha := 0, F:681
     else { std::vector<double> hv((size_t)std::max<int64_t>(n, 1), c->p.h_fixed); CK(cudaMemcpyAsync(c->st[0][f], hv.data(), hv.size() * 8, cudaMemcpyHostToDevice, c->stream)); CK(cudaStreamSynchronize(c->stream)); }
+  }
+  if (late_mask && n > 0) {      // sph_step_host: the other columns in the order their readers come (h: leaf cells, m: node sums, u: EOS, then v, alpha)
+    CK(cudaEventRecord(c->io_ev_xyz, c->stream));
+    CK(cudaStreamWaitEvent(c->io_stream, c->io_ev_xyz, 0));
+    const int order[7] = {9, 7, 6, 3, 4, 5, 8};
+    for (int k = 0; k < 7; ++k) {
+      const int f = order[k];
+      if (!src[f] || !((late_mask >> f) & 1u)) continue;
+      CK(cudaMemcpyAsync(c->st[0][f], src[f], (size_t)n * 8, cudaMemcpyHostToDevice, c->io_stream));
+      CK(cudaEventRecord(c->io_ev_field[f], c->io_stream));
+      c->late_order[c->late_n++] = f; c->late_pending |= 1u << f;
+    }
   }
   if (n > 0) LAUNCH(k_iota_from, cdiv(n, 256), 256, 0, (int)n, (int)id_first, c->id[0]);
   // sinks (dummy zero sink if none: F:698-707)
@@ -1285,6 +1383,7 @@ int sph_evaluate(sph_ctx* c, int32_t mask) {
   if (!c) return SPH_ERR_ARG;
   if (c->n <= 0) { c->err = "no particles uploaded"; return SPH_ERR_STATE; }
   cudaSetDevice(c->device);
+  c->far_want_store = c->steps_since_upload >= 1;
   int r = evaluate(c, mask); if (r) return r;
   CK(cudaMemcpyAsync(c->h_sc, c->sc, sizeof(SimScalars), cudaMemcpyDeviceToHost, c->stream));
   if ((r = fetch_counters(c))) return r;
@@ -1307,6 +1406,65 @@ int sph_step(sph_ctx* c, double* dt, double* t, int64_t* n_out, int32_t* ns_out)
   CK(cudaGetLastError());
   *dt = c->h_sc->dt; *t = c->h_sc->t;
   if (n_out) *n_out = c->dd ? c->n_global : c->n;
+  if (ns_out) *ns_out = c->n_sink;
+  return SPH_OK;
+}
+
+// upload + one loop body + download with the copies under the compute (single rank)
+int sph_step_host(sph_ctx* c, int64_t n, const double* const* gas_in, int32_t ns, const double* const* sink_in,
+                  double* dt, double* t, double* const* gas_out, double* const* sink_out, int64_t* n_out, int32_t* ns_out) {
+  if (!c || !gas_in || !dt || !t) return SPH_ERR_ARG;
+  if (c->n_ranks > 1) { c->err = "sph_step_host is single-rank: ranks of a multi-GPU run move their rows with sph_upload_local / sph_step / sph_download_local"; return SPH_ERR_ARG; }
+  if (n < 2 || n > 0x0fffffff * (int64_t)SPH_CHUNK) { c->err = "bad particle count"; return SPH_ERR_ARG; }
+  for (int f = 0; f < 8; ++f) if (!gas_in[f]) { c->err = "bad particle arrays"; return SPH_ERR_ARG; }
+  if (ns < 0 || ns > SPH_MAX_SINKS - 8 || (ns > 0 && !sink_in)) { c->err = "bad sink arrays"; return SPH_ERR_ARG; }
+  if (c->dp.variable_h && !gas_in[9]) { c->err = "variable-h mode needs the smoothing-length column"; return SPH_ERR_ARG; }
+  cudaSetDevice(c->device);
+  if (!c->io_stream) {
+    if (cudaStreamCreateWithFlags(&c->io_stream, cudaStreamNonBlocking) != cudaSuccess) { c->err = "stream create failed"; return SPH_ERR_CUDA; }
+    cudaEventCreateWithFlags(&c->io_ev_xyz, cudaEventDisableTiming); cudaEventCreateWithFlags(&c->io_ev_out, cudaEventDisableTiming); cudaEventCreateWithFlags(&c->io_ev_done, cudaEventDisableTiming);
+    for (int f = 0; f < 10; ++f) cudaEventCreateWithFlags(&c->io_ev_field[f], cudaEventDisableTiming);
+  }
+  const double* src[10]; for (int f = 0; f < 10; ++f) src[f] = gas_in[f];
+  if (!c->dp.variable_h) src[9] = nullptr;                                     // F ignores column 10
+  // developer switches: SPH_B200_IO_NO_LATE (all columns before the build), SPH_B200_IO_NO_EARLY (all results after the step), SPH_B200_IO_TRACE (host time line on stderr)
+  const bool io_trace = getenv("SPH_B200_IO_TRACE") != nullptr, io_no_late = getenv("SPH_B200_IO_NO_LATE") != nullptr, io_no_early = getenv("SPH_B200_IO_NO_EARLY") != nullptr;
+  auto now_ms = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
+  const double tr0 = now_ms();
+  const double* ssrc[7] = {}; const double* srad = nullptr;
+  if (ns > 0) { for (int k = 0; k < 7; ++k) ssrc[k] = sink_in[k]; srad = sink_in[7]; }
+  int r = upload_impl(c, n, 0, n, src, ns, ssrc, srad, false, io_no_late ? 0u : 0x3f8u /* everything but x y z arrives while the build runs */);
+  if (r) return r;
+  const double tr1 = now_ms();
+  if ((size_t)c->cap > c->io_stage_cap) { for (int k = 0; k < 5; ++k) DA(c->io_stage[k], c->cap); c->io_stage_cap = (size_t)c->cap; }
+  for (int f = 0; f < 10; ++f) c->io_out[f] = gas_out ? gas_out[f] : nullptr;
+  c->io_active = gas_out != nullptr && !io_no_early; c->io_fetched = 0; c->io_busy = false;
+  c->h_sc->dt = *dt; c->h_sc->t = *t;
+  CK(cudaMemcpyAsync(c->sc, c->h_sc, 2 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  r = step(c);
+  c->io_active = false;
+  if (r) { cudaStreamSynchronize(c->io_stream); c->late_pending = 0; return r; }
+  if ((r = fetch_counters(c))) return r;
+  c->counts.h_iterations = (int64_t)c->h_ctr->h_iters;
+  stage_collect(c, true);
+  const double tr2 = now_ms();
+  if (gas_out && c->n > 0) {
+    unsigned have = c->io_fetched;
+    if (c->n != c->n_upload) { CK(cudaStreamSynchronize(c->io_stream)); have = 0; }      // rows were removed after the early columns left: all of them again, compacted
+    if ((r = compute_pos(c))) return r;
+    for (int f = 0; f < 10; ++f) if (!((have >> f) & 1u)) { if ((r = fetch_ordered(c, c->st[c->cur][f], gas_out[f]))) return r; }
+  }
+  if (sink_out) {
+    const double* ss[8] = {c->S.x, c->S.y, c->S.z, c->S.vx, c->S.vy, c->S.vz, c->S.m, c->S.radius};
+    for (int k = 0; k < 8; ++k) if ((r = fetch_sink(c, ss[k], sink_out[k]))) return r;
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  const double tr3 = now_ms();
+  CK(cudaStreamSynchronize(c->io_stream));
+  CK(cudaGetLastError());
+  if (io_trace) fprintf(stderr, "sph_step_host: upload %.2f ms, step %.2f ms, last columns %.2f ms, early columns still in flight %.2f ms\n", tr1 - tr0, tr2 - tr1, tr3 - tr2, now_ms() - tr3);
+  *dt = c->h_sc->dt; *t = c->h_sc->t;
+  if (n_out) *n_out = c->n;
   if (ns_out) *ns_out = c->n_sink;
   return SPH_OK;
 }

@@ -105,12 +105,14 @@ __global__ void k_permute(int n, const int* __restrict__ perm, PermuteArgs a) {
   for (int k = 0; k < 4; ++k) { const int i = base + k * blockDim.x; ok[k] = i < n; p[k] = ok[k] ? perm[i] : 0; }
 #pragma unroll
   for (int f = 0; f < 10; ++f) {
+    if (a.src[f] == nullptr) continue;          // a field that is permuted by a later launch (sph_step_host: still on its way from the host)
     double v[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) v[k] = a.src[f][p[k]];
 #pragma unroll
     for (int k = 0; k < 4; ++k) if (ok[k]) a.dst[f][base + k * blockDim.x] = v[k];
   }
+  if (a.id_src == nullptr) return;
   int w[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) w[k] = a.id_src[p[k]];

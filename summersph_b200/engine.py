@@ -9,13 +9,13 @@ import os
 import numpy as np
 
 from ._abi import SphParams, SphCounts, EVAL_ALL, ERRORS, CONSERVED, conserved_dict
-from .state import Bodies, Sinks
+from .state import Bodies, Sinks, GAS_FIELDS
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SPH_B200_LIB") or os.path.join(_HERE, "libsph_b200.so")   # override: developer experiments only
 _LIB = None
 
-STAGES = ("keys", "sort", "tree", "density", "gravity", "sph", "integrate", "h_iter", "cull", "comm", "halo", "let", "migrate")
+STAGES = ("keys", "sort", "tree", "density", "gravity", "sph", "integrate", "h_iter", "cull", "comm", "halo", "let", "migrate", "gravity_near")
 
 
 class SphError(RuntimeError):
@@ -53,6 +53,7 @@ def load_library(path=None):
     lib.sph_ics_disc.argtypes = [vp, i64, C.c_uint64] + [dbl] * 8
     lib.sph_evaluate.argtypes = [vp, i32]
     lib.sph_step.argtypes = [vp, C.POINTER(dbl), C.POINTER(dbl), C.POINTER(i64), C.POINTER(i32)]
+    lib.sph_step_host.argtypes = [vp, i64, vp, i32, vp, C.POINTER(dbl), C.POINTER(dbl), vp, vp, C.POINTER(i64), C.POINTER(i32)]
     lib.sph_run_until.argtypes = [vp, dbl, i64, C.POINTER(dbl), C.POINTER(dbl), C.POINTER(i64), C.POINTER(i64), C.POINTER(i32)]
     lib.sph_sizes.argtypes = [vp, C.POINTER(i64), C.POINTER(i32)]
     lib.sph_download.argtypes = [vp] + [vp] * 18
@@ -196,6 +197,21 @@ class Engine:
         cdt, ct, n, ns = C.c_double(dt), C.c_double(t), C.c_int64(), C.c_int32()
         self._ck(self._l.sph_step(self._c, C.byref(cdt), C.byref(ct), C.byref(n), C.byref(ns)))
         return cdt.value, ct.value
+
+    def step_host(self, b: Bodies, s: Sinks, dt, t, into=None):
+        """`sph_step_host`: upload (b, s), one loop body, download - one call, the copies run under the compute (pinned
+        host arrays for the overlap).  `into` = (Bodies, Sinks) with room for len(b) rows and len(s) + 8 sinks (may be
+        the input arrays); returns (dt, t, n_gas, n_sink): the first n_gas / n_sink rows of `into` hold the result."""
+        if into is None:
+            into = (Bodies.empty(len(b)), Sinks.empty(len(s) + 8))
+        ob, os_ = into
+        gin = (C.c_void_p * 10)(*[_p(getattr(b, k)) for k in GAS_FIELDS])
+        sin = (C.c_void_p * 8)(*[_p(getattr(s, k)) for k in ("x", "y", "z", "vx", "vy", "vz", "m", "radius")])
+        gout = (C.c_void_p * 10)(*[_p(getattr(ob, k)) for k in GAS_FIELDS])
+        sout = (C.c_void_p * 8)(*[_p(getattr(os_, k)) for k in ("x", "y", "z", "vx", "vy", "vz", "m", "radius")])
+        cdt, ct, n, ns = C.c_double(dt), C.c_double(t), C.c_int64(), C.c_int32()
+        self._ck(self._l.sph_step_host(self._c, len(b), gin, len(s), sin, C.byref(cdt), C.byref(ct), gout, sout, C.byref(n), C.byref(ns)))
+        return cdt.value, ct.value, n.value, ns.value
 
     def run_until(self, t_stop, dt, t, max_steps=0):
         cdt, ct, steps, n, ns = C.c_double(dt), C.c_double(t), C.c_int64(), C.c_int64(), C.c_int32()

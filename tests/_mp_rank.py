@@ -16,6 +16,10 @@ import numpy as np  # noqa: E402
 
 def case(mode, n=60_000, decomposition=0):
     from summersph_b200 import default_params, ics
+    if os.environ.get("SPH_TEST_QUIET"):    # nothing is removed: evaluation A keeps evaluation B's far-field gravity (sph_far_reuse_count > 0)
+        p = default_params(mode, decomposition=decomposition)
+        b, s = ics.keplerian_disc(n, seed=12)
+        return p, b, s
     p = default_params(mode, bounding_size=95.0, decomposition=decomposition)
     b, s = ics.keplerian_disc(n, seed=12)
     s.radius[:] = 12.0                      # accretion + bounds removals exercised too
@@ -46,11 +50,11 @@ def main():
         bb, ss = e.download()
         d = e.diag()
         c = e.counters()
-        extra = {}
+        extra = {"far_reuse": np.array([e.far_reuse_count()])}
         if len(sys.argv) > 11 and sys.argv[11] == "tree":      # one more evaluation on the end state with exact counters: tree + neighbour sets
             e.set_exact_counters(True); e.evaluate(); e.set_exact_counters(False)
             tr = e.tree(); cnt, hsh, _, _ = e.neighbours(with_list=False)
-            extra = {"t_" + k: v for k, v in tr.items()}
+            extra.update({"t_" + k: v for k, v in tr.items()})
             extra.update({"n_count": cnt, "n_hash": hsh})
             d2 = e.diag(); extra.update({"e_" + k: v for k, v in d2.items()})
             c2 = e.counters(); extra["e_counters"] = np.array([c2[k] for k in sorted(c2)], dtype=np.int64)

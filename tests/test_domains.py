@@ -71,6 +71,19 @@ def test_domains_three_steps(mode, world, reference, tmp_path):
         compare(res[r], reference[(mode, 3)], f"world {world} rank {r} steps", 1e-10, 1e-10)
 
 
+@pytest.mark.parametrize("world", [2, 3])
+def test_domains_far_reuse(world, built_engine, tmp_path):
+    """A case that removes nothing, four loop bodies: every domain keeps evaluation B's far-field gravity for the next
+    evaluation A (the ranks agree on it through one all-reduce; the sinks' own sums are the stored ones)."""
+    env = {"SPH_TEST_QUIET": "1"}
+    ref = run_ranks(tmp_path, "ddq1", 1, "host", MODE_VARIABLE_H, steps=4, env_extra=env, n=30_000, extra="tree")[0]
+    res = run_ranks(tmp_path, f"ddq{world}", world, "host", MODE_VARIABLE_H, steps=4, env_extra=env, n=30_000, domains=1, extra="tree")
+    assert int(ref["far_reuse"][0]) >= 2
+    for r in range(world):
+        assert int(res[r]["far_reuse"][0]) == int(ref["far_reuse"][0]), (r, res[r]["far_reuse"], ref["far_reuse"])
+        compare(res[r], ref, f"quiet world {world} rank {r}", 1e-10, 1e-10)
+
+
 @pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
 def test_domains_nccl_two_gpus(reference, tmp_path):
     res = run_ranks(tmp_path, "ddn2", 2, "nccl", MODE_VARIABLE_H, steps=3, domains=1, extra="tree")

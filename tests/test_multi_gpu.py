@@ -78,6 +78,18 @@ def single_rank(tmp_path_factory, built_engine):
     return {m: run_ranks(d, f"one{m}", 1, "host", m)[0] for m in (MODE_VARIABLE_H, MODE_FIXED_H)}
 
 
+def test_replicated_far_reuse_bit_identical(built_engine, tmp_path):
+    """A case that removes nothing: evaluation A of steps 2.. keeps evaluation B's far-field gravity and adds the recorded
+    near pairs.  The gravity runs - and with them the recorded pairs and their order - are the same for any rank count,
+    so the replicated form stays bit-identical to one rank."""
+    env = {"SPH_TEST_QUIET": "1"}
+    ref = run_ranks(tmp_path, "q1", 1, "host", MODE_VARIABLE_H, steps=4, env_extra=env, n=30_000)[0]
+    assert int(ref["far_reuse"][0]) >= 2
+    res = run_ranks(tmp_path, "q2", 2, "host", MODE_VARIABLE_H, steps=4, env_extra=env, n=30_000)
+    for r in range(2):
+        assert_identical(res[r], ref, f"quiet rank {r}")
+
+
 @pytest.mark.parametrize("mode", [MODE_VARIABLE_H, MODE_FIXED_H])
 @pytest.mark.parametrize("world,env", [(2, {}), (3, {}), (2, {"SPH_B200_NO_FUSED_PUSH": "1"})])
 def test_process_per_rank_shared_gpu_bit_identical(mode, world, env, single_rank, tmp_path):
