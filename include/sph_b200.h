@@ -257,6 +257,16 @@ int64_t sph_group_count(sph_ctx* ctx);
  * a full walk, summed in another order.  SPH_B200_NO_FAR_REUSE=1 (environment, read in sph_create) turns it off. */
 int64_t sph_far_reuse_count(sph_ctx* ctx);
 
+/* A host that owns the state between steps (upload, loop body, download - the reference's own loop keeps bodies(:) /
+ * sinks(:) on the host side, SUMMER_SPH.f90:879-929) hands back exactly what it was given.  sph_upload / sph_step_host
+ * therefore compare the incoming x y z m h and sinks bitwise, on the device, with the state the context holds (rows by
+ * `number`); when they are the same - and the resident state came out of a step that removed nothing - the tree, the walk
+ * groups and the stored far-field sums still stand and only v u alpha are taken over.  Any difference (one bit, one row,
+ * the row count, a sink) makes the upload a new state.  sph_resident_hits counts the uploads that were recognised;
+ * sph_set_resident_check(ctx, 0) turns the comparison off (SPH_B200_NO_RESIDENT_CHECK=1 does the same at sph_create). */
+int64_t sph_resident_hits(sph_ctx* ctx);
+int sph_set_resident_check(sph_ctx* ctx, int32_t on);
+
 /* CUDA-event timer on the context's own stream (bench.py: torch events cannot see this stream). */
 int sph_timer_start(sph_ctx* ctx);
 int sph_timer_stop(sph_ctx* ctx, double* elapsed_ms);

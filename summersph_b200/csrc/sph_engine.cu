@@ -79,6 +79,7 @@ struct sph_ctx {
   double* sink_seg = nullptr; size_t sink_seg_cap = 0;     // [global GRAV_SEG segment][sink][3]: gas terms of the sink accelerations (exchanged between ranks)
   SimScalars* sc = nullptr; SimScalars* h_sc = nullptr;     // device + pinned host mirror
   int* h_rb = nullptr;                                      // pinned scratch for readback(): 16 ints
+  int resident_check = 1; int64_t resident_hits = 0; int* d_same = nullptr; double* sink_land = nullptr;      // upload_impl: "is this the state I hold?"
   WalkCounters* ctr = nullptr; WalkCounters* h_ctr = nullptr; int* work = nullptr;
   unsigned char* keep = nullptr; unsigned long long* acc_key[2] = {}; int* acc_val[2] = {}; int* d_nsel = nullptr;
   int* pos = nullptr;           // ascending-number position of each sorted particle (downloads)
@@ -1164,6 +1165,9 @@ int sph_create(const sph_params* p, int32_t device, sph_ctx** out) {
   if ((r = dalloc(c, &c->d_nsel, 1))) return fail(r);
   if ((r = dalloc(c, &c->far_sink_a, (size_t)SPH_MAX_SINKS * 3))) return fail(r);
   if ((r = dalloc(c, &c->far_snap, 1))) return fail(r);
+  if ((r = dalloc(c, &c->d_same, 1))) return fail(r);
+  if ((r = dalloc(c, &c->sink_land, (size_t)SPH_MAX_SINKS * 8))) return fail(r);
+  c->resident_check = getenv("SPH_B200_NO_RESIDENT_CHECK") ? 0 : 1;      // developer switch: every upload is a new state
   if ((r = dalloc(c, &c->far_ctr, 2))) return fail(r);
   if ((r = dalloc(c, &c->sink_buf, (size_t)SPH_MAX_SINKS * 11 + 8))) return fail(r);      // + the LET overflow flag right behind az (it rides the sink all-reduce)
   c->let_flag = c->sink_buf + (size_t)SPH_MAX_SINKS * 11;
@@ -1220,7 +1224,7 @@ int sph_destroy(sph_ctx* c) {
   F(c->dd_let_f[0]); F(c->dd_let_f[1]); F(c->dd_halo_flag); F(c->dd_halo_list); F(c->dd_halo_size); F(c->dd_halo_poff); F(c->dd_acc_key); F(c->dd_acc_rec);
   F(c->dd_accg_key[0]); F(c->dd_accg_key[1]); F(c->dd_accg_idx[0]); F(c->dd_accg_idx[1]); F(c->dd_accg_rec); F(c->dd_gid); F(c->dd_gpos); F(c->dd_gcnt); F(c->dd_goff); F(c->dd_gstage);
   F(c->cons_partial); F(c->cons_out); F(c->img_table); F(c->sink_spin);
-  F(c->far_fx); F(c->far_fy); F(c->far_fz); F(c->far_hc2); F(c->far_sink_a); F(c->far_snap); F(c->far_ctr); F(c->far_list); F(c->far_cnt); F(c->far_ovf);
+  F(c->far_fx); F(c->far_fy); F(c->far_fz); F(c->far_hc2); F(c->far_sink_a); F(c->far_snap); F(c->far_ctr); F(c->far_list); F(c->far_cnt); F(c->far_ovf); F(c->d_same); F(c->sink_land);
   F(c->arrive); F(c->cnt); F(c->off); F(c->root); F(c->partial); F(c->cub_tmp); F(c->d_wt); F(c->d_dwt); F(c->d_gt);
   F(c->sink_buf); F(c->sink_partial); F(c->sink_seg); F(c->sc); F(c->ctr); F(c->work); F(c->keep); F(c->d_nsel); F(c->pos); F(c->stage_d); F(c->stage_d2);
   if (c->h_sc) cudaFreeHost(c->h_sc);
@@ -1274,6 +1278,29 @@ int sph_comm_init_host(sph_ctx* c, int32_t rank, int32_t n_ranks, const char* na
 }
 
 // n_local rows starting at global number id_first out of n_global (single rank / replicated: all of them)
+// Is the state the host hands over the one this context holds?  A host that keeps bodies(:) / sinks(:) on its side and
+// passes them through every step (upload, loop body, download) sends back exactly what it was given.  The geometry columns
+// (x y z m h) land in the idle half of the double buffer and are compared bitwise, row `number` against the resident row
+// carrying that number, the sinks likewise; when they are the same, the tree, the walk groups, the stored far-field
+// sums and their recorded pairs still stand (they are functions of exactly these values), and only the other columns
+// (v u alpha) are gathered into the resident order.  Anything else is a new state.
+struct SameCols { const double* a[5]; const double* b[5]; int nf; };
+__global__ void k_same_state(int n, const int* __restrict__ id, SameCols C, int* __restrict__ differ) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool d = false;
+  if (i < n) {
+    const int j = id[i];
+    for (int f = 0; f < C.nf; ++f) d |= __double_as_longlong(C.a[f][i]) != __double_as_longlong(C.b[f][j]);
+  }
+  if (__any_sync(FULL_MASK, d) && (threadIdx.x & 31) == 0) atomicOr(differ, 1);
+}
+__global__ void k_same_sinks(int ns, const double* __restrict__ resident, const double* __restrict__ landed, int* __restrict__ differ) {
+  const int t = threadIdx.x;      // 8 arrays (x y z vx vy vz m radius) of SPH_MAX_SINKS
+  bool d = false;
+  for (int k = 0; k < 8; ++k) if (t < ns) d |= __double_as_longlong(resident[k * SPH_MAX_SINKS + t]) != __double_as_longlong(landed[k * SPH_MAX_SINKS + t]);
+  if (d) atomicOr(differ, 1);
+}
+
 static int upload_impl(sph_ctx* c, int64_t n_global, int64_t id_first, int64_t n, const double* const* src,
                        int32_t ns, const double* const* ssrc, const double* srad, bool gas_on_device = false, unsigned late_mask = 0) {
   cudaSetDevice(c->device);
@@ -1284,16 +1311,25 @@ static int upload_impl(sph_ctx* c, int64_t n_global, int64_t id_first, int64_t n
     want = std::max<int64_t>(n, (int64_t)((double)(n_global / c->n_ranks) * (1.0 + slack)) + 65536);
   }
   if (c->dd && !c->dd_acc_key) c->cap = 0;        // the exported arrays of the decomposition are sized in ensure_capacity
+  // the resident state is a candidate when it came out of a step of this context with every row of its upload still there
+  const bool try_same = c->resident_check && c->n_ranks == 1 && !gas_on_device && !c->sink_extras && c->tree_valid && !c->pos_moved && c->steps_since_upload >= 1 &&
+                        n > 0 && c->n == n && c->n_upload == n && n_global == n && id_first == 0 && n <= c->cap && (ns > 0 ? ns : 1) == c->n_sink &&
+                        src[0] && src[1] && src[2] && src[3] && src[4] && src[5] && src[6] && src[7] && (src[9] || !c->dp.variable_h);
   int r = ensure_capacity(c, want); if (r) return r;
-  c->n_halo = 0; c->ng_halo = 0; c->dd_info.clear();
-  c->n = n; c->n_upload = n_global; c->n_global = n_global; c->cur = 0; c->tree_valid = false; c->pos_moved = true;
-  c->far_valid = false; c->steps_since_upload = 0;
+  const int L = try_same ? (c->cur ^ 1) : 0;      // where the columns land
+  // sinks as the context would hold them (dummy zero sink if none: F:698-707)
+  std::vector<double> hb((size_t)SPH_MAX_SINKS * 11, 0.0);
+  const int M = SPH_MAX_SINKS;
+  for (int k = 0; k < 7; ++k) for (int q = 0; q < ns; ++q) hb[(size_t)k * M + q] = ssrc[k] ? ssrc[k][q] : 0.0;
+  for (int q = 0; q < ns; ++q) hb[(size_t)7 * M + q] = (srad && srad[q] == srad[q]) ? srad[q] : c->p.sink_radius;
   c->late_pending = 0; c->late_permuted = false; c->late_n = 0;
+  const unsigned geometry = try_same ? ((1u << 0) | (1u << 1) | (1u << 2) | (1u << 7) | (1u << 9)) : 0x7u;      // columns the compute stream waits for
+  if (late_mask) late_mask &= ~geometry;
   for (int f = 0; f < 10 && !gas_on_device; ++f) {
-    if (src[f] && ((late_mask >> f) & 1u)) continue;       // follows on io_stream behind x y z (below)
-    if (src[f]) { if (n > 0) CK(cudaMemcpyAsync(c->st[0][f], src[f], (size_t)n * 8, cudaMemcpyHostToDevice, c->stream)); }
-    else if (f == 8) CK(cudaMemsetAsync(c->st[0][f], 0, (size_t)std::max<int64_t>(n, 1) * 8, c->stream));            // alpha := 0, F:681
-    else { std::vector<double> hv((size_t)std::max<int64_t>(n, 1), c->p.h_fixed); CK(cudaMemcpyAsync(c->st[0][f], hv.data(), hv.size() * 8, cudaMemcpyHostToDevice, c->stream)); CK(cudaStreamSynchronize(c->stream)); }
+    if (src[f] && ((late_mask >> f) & 1u)) continue;       // follows on io_stream behind the first columns (below)
+    if (src[f]) { if (n > 0) CK(cudaMemcpyAsync(c->st[L][f], src[f], (size_t)n * 8, cudaMemcpyHostToDevice, c->stream)); }
+    else if (f == 8) CK(cudaMemsetAsync(c->st[L][f], 0, (size_t)std::max<int64_t>(n, 1) * 8, c->stream));            // alpha := 0, F:681
+    else if (!try_same) { std::vector<double> hv((size_t)std::max<int64_t>(n, 1), c->p.h_fixed); CK(cudaMemcpyAsync(c->st[L][f], hv.data(), hv.size() * 8, cudaMemcpyHostToDevice, c->stream)); CK(cudaStreamSynchronize(c->stream)); }
   }
   if (late_mask && n > 0) {      // sph_step_host: the other columns in the order their readers come (h: leaf cells, m: node sums, u: EOS, then v, alpha)
     CK(cudaEventRecord(c->io_ev_xyz, c->stream));
@@ -1302,17 +1338,48 @@ static int upload_impl(sph_ctx* c, int64_t n_global, int64_t id_first, int64_t n
     for (int k = 0; k < 7; ++k) {
       const int f = order[k];
       if (!src[f] || !((late_mask >> f) & 1u)) continue;
-      CK(cudaMemcpyAsync(c->st[0][f], src[f], (size_t)n * 8, cudaMemcpyHostToDevice, c->io_stream));
+      CK(cudaMemcpyAsync(c->st[L][f], src[f], (size_t)n * 8, cudaMemcpyHostToDevice, c->io_stream));
       CK(cudaEventRecord(c->io_ev_field[f], c->io_stream));
       c->late_order[c->late_n++] = f; c->late_pending |= 1u << f;
     }
   }
-  if (n > 0) LAUNCH(k_iota_from, cdiv(n, 256), 256, 0, (int)n, (int)id_first, c->id[0]);
-  // sinks (dummy zero sink if none: F:698-707)
-  std::vector<double> hb((size_t)SPH_MAX_SINKS * 11, 0.0);
-  const int M = SPH_MAX_SINKS;
-  for (int k = 0; k < 7; ++k) for (int q = 0; q < ns; ++q) hb[(size_t)k * M + q] = ssrc[k] ? ssrc[k][q] : 0.0;
-  for (int q = 0; q < ns; ++q) hb[(size_t)7 * M + q] = (srad && srad[q] == srad[q]) ? srad[q] : c->p.sink_radius;
+  if (try_same) {
+    const int cur = c->cur;
+    SameCols C; C.nf = 0;
+    const int cols[5] = {0, 1, 2, 7, 9};
+    for (int k = 0; k < 5; ++k) { const int f = cols[k]; if (f == 9 && !c->dp.variable_h) continue; C.a[C.nf] = c->st[cur][f]; C.b[C.nf] = c->st[L][f]; ++C.nf; }
+    double* landed = c->sink_land;
+    CK(cudaMemcpyAsync(landed, hb.data(), (size_t)8 * M * 8, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemsetAsync(c->d_same, 0, sizeof(int), c->stream));
+    LAUNCH(k_same_state, cdiv(n, 256), 256, 0, (int)n, c->id[cur], C, c->d_same);
+    LAUNCH(k_same_sinks, 1, SPH_MAX_SINKS, 0, c->n_sink, c->sink_buf, landed, c->d_same);
+    readback(c, c->h_rb + 8, c->d_same, sizeof(int));
+    CK(cudaStreamSynchronize(c->stream));
+    if (c->h_rb[8] == 0) {      // the resident state, handed back: keep it and everything derived from its geometry; v u alpha into the resident order
+      ++c->resident_hits;
+      c->nl_valid = false;
+      PermuteArgs pa; std::memset(&pa, 0, sizeof(pa));
+      const int rest[5] = {6, 3, 4, 5, 8};
+      bool now = false;
+      for (int k = 0; k < 5; ++k) {
+        const int f = rest[k];
+        if ((c->late_pending >> f) & 1u) { c->late_src[f] = c->st[L][f]; c->late_dst[f] = c->st[cur][f]; }      // flush_late gathers it when its first reader is due
+        else { pa.src[f] = c->st[L][f]; pa.dst[f] = c->st[cur][f]; now = true; }
+      }
+      c->late_perm = c->id[cur]; c->late_permuted = true;
+      if (now) LAUNCH(k_permute, cdiv(n, 4 * 256), 256, 0, (int)n, c->id[cur], pa);
+      c->h_sc->n_sink = c->n_sink; c->h_sc->n_removed = 0; c->h_sc->n_accreted = 0; c->h_sc->err = 0; c->h_sc->create_cand = ~0ull;
+      CK(cudaMemcpyAsync(c->sc, c->h_sc, sizeof(SimScalars), cudaMemcpyHostToDevice, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      return SPH_OK;
+    }
+    if (!c->dp.variable_h) { std::vector<double> hv((size_t)n, c->p.h_fixed); CK(cudaMemcpyAsync(c->st[L][9], hv.data(), hv.size() * 8, cudaMemcpyHostToDevice, c->stream)); CK(cudaStreamSynchronize(c->stream)); }
+  }
+  // a new state
+  c->n_halo = 0; c->ng_halo = 0; c->dd_info.clear();
+  c->n = n; c->n_upload = n_global; c->n_global = n_global; c->cur = L; c->tree_valid = false; c->pos_moved = true;
+  c->far_valid = false; c->steps_since_upload = 0;
+  if (n > 0) LAUNCH(k_iota_from, cdiv(n, 256), 256, 0, (int)n, (int)id_first, c->id[L]);
   c->n_sink = ns > 0 ? ns : 1;
   CK(cudaMemcpyAsync(c->sink_buf, hb.data(), hb.size() * 8, cudaMemcpyHostToDevice, c->stream));
   if (c->sink_spin) CK(cudaMemsetAsync(c->sink_spin, 0, (size_t)SPH_MAX_SINKS * 3 * 8, c->stream));   // F:695 spin = 0
@@ -1740,6 +1807,8 @@ int sph_stage_times(sph_ctx* c, double* ms, int32_t n) {
 int64_t sph_launch_count(sph_ctx* c) { return c ? c->launches : 0; }
 int64_t sph_group_count(sph_ctx* c) { return c ? c->n_groups : 0; }
 int64_t sph_far_reuse_count(sph_ctx* c) { return c ? c->far_count : 0; }
+int64_t sph_resident_hits(sph_ctx* c) { return c ? c->resident_hits : 0; }
+int sph_set_resident_check(sph_ctx* c, int32_t on) { if (!c) return SPH_ERR_ARG; c->resident_check = on ? 1 : 0; return SPH_OK; }
 
 int sph_timer_start(sph_ctx* c) {
   if (!c) return SPH_ERR_ARG;

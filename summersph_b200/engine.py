@@ -69,6 +69,9 @@ def load_library(path=None):
     lib.sph_group_count.restype = i64
     lib.sph_far_reuse_count.argtypes = [vp]
     lib.sph_far_reuse_count.restype = i64
+    lib.sph_resident_hits.argtypes = [vp]
+    lib.sph_resident_hits.restype = i64
+    lib.sph_set_resident_check.argtypes = [vp, i32]
     lib.sph_timer_start.argtypes = [vp]
     lib.sph_timer_stop.argtypes = [vp, C.POINTER(dbl)]
     lib.sph_fp64_peak.argtypes = [vp, C.POINTER(dbl)]
@@ -313,6 +316,13 @@ class Engine:
 
     def group_count(self):
         return int(self._l.sph_group_count(self._c))
+
+    def resident_hits(self):
+        """Uploads so far that were recognised as the state the context already holds (`sph_resident_hits`)."""
+        return int(self._l.sph_resident_hits(self._c))
+
+    def set_resident_check(self, on=True):
+        self._ck(self._l.sph_set_resident_check(self._c, 1 if on else 0))
 
     def far_reuse_count(self):
         """Gravity evaluations so far that walked only the near field on top of the stored far sums."""

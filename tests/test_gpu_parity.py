@@ -499,6 +499,73 @@ def test_step_host_equals_upload_step_download(mode, removals, E):
             assert len(b1) < len(b)
 
 
+@pytest.mark.parametrize("mode", [MODE_VARIABLE_H, MODE_FIXED_H])
+def test_resident_upload_is_recognised(mode, E):
+    """A host that passes the state through every step (upload, step, download) hands back what it was given: the context
+    recognises it (bitwise comparison of x y z m h + sinks on the device), keeps its tree and stored far-field sums and
+    ends up - bit for bit - where a context that was never re-uploaded ends up.  Both host flows: three calls, one call."""
+    p = default_params(mode)
+    b, s = ics.keplerian_disc(20_000, seed=15)
+    steps = 4
+    with E(p) as e0:
+        e0.upload(b, s)
+        dt, t = 0.01, 0.0
+        for _ in range(steps):
+            dt, t = e0.step(dt, t)
+        ref_b, ref_s = e0.download(); ref = (dt, t, e0.far_reuse_count())
+    assert len(ref_b) == len(b)
+    for flow in ("three calls", "one call"):
+        with E(p) as e:
+            bb, ss = b.copy(), s
+            dt, t = 0.01, 0.0
+            for k in range(steps):
+                if flow == "three calls":
+                    e.upload(bb, ss); dt, t = e.step(dt, t); bb, ss = e.download()
+                else:
+                    ob, os_ = Bodies.empty(len(bb)), Sinks.empty(len(ss) + 8)
+                    dt, t, n2, ns2 = e.step_host(bb, ss, dt, t, into=(ob, os_))
+                    bb = ob; ss = Sinks(*[getattr(os_, f)[:ns2].copy() for f in ("x", "y", "z", "vx", "vy", "vz", "m", "radius")])
+            assert e.resident_hits() == steps - 1, flow
+            assert (dt, t, e.far_reuse_count()) == ref, flow
+            for f in GAS_FIELDS:
+                assert np.array_equal(getattr(bb, f), getattr(ref_b, f)), (flow, f)
+            for f in ("x", "y", "z", "vx", "vy", "vz", "m"):
+                assert np.array_equal(getattr(ss, f), getattr(ref_s, f)), (flow, f)
+
+
+def test_resident_upload_changed_state(E):
+    """Same geometry, other velocities: recognised, the new v u alpha are taken over (result within rounding of a cold
+    upload of the same rows, which walks the whole tree).  One position changed by one ulp: the comparison fails and the
+    upload is a new state (bit-identical to the cold upload)."""
+    p = default_params(MODE_VARIABLE_H)
+    b, s = ics.keplerian_disc(20_000, seed=16)
+    with E(p) as e:
+        e.upload(b, s)
+        dt, t = 0.01, 0.0
+        for _ in range(2):
+            dt, t = e.step(dt, t)
+        b1, s1 = e.download()                   # the context holds this state, out of a step
+        for change in ("velocity", "position"):
+            b2 = b1.copy()
+            if change == "velocity":
+                b2.vx[::7] *= 1.01; b2.u[::5] *= 0.99
+            else:
+                b2.x[123] = np.nextafter(b2.x[123], np.inf)
+            h0 = e.resident_hits()
+            e.upload(b2, s1); dta, ta = e.step(dt, t); ba, sa = e.download()
+            assert e.resident_hits() - h0 == (1 if change == "velocity" else 0), change
+            with E(p) as cold:
+                cold.set_resident_check(False)
+                cold.upload(b2, s1); dtc, tc = cold.step(dt, t); bc, sc_ = cold.download()
+            assert (dta, ta) == (dtc, tc), change
+            for f in GAS_FIELDS:
+                if change == "velocity":
+                    assert relerr(getattr(ba, f), getattr(bc, f)) < 1e-12, (change, f)
+                else:
+                    assert np.array_equal(getattr(ba, f), getattr(bc, f)), (change, f)
+            b1, s1, dt, t = ba, sa, dta, ta     # again a state the context holds, out of a step
+
+
 def test_candidate_list_pool_overflow_falls_back(E, monkeypatch):
     """The density pass saves the pair loop's candidate lists in a pool of blocks.  A pool that is too small voids
     the lists on the device: the walking pair kernel runs instead and the host doubles the pool for the next
