@@ -1285,11 +1285,14 @@ int sph_comm_init_host(sph_ctx* c, int32_t rank, int32_t n_ranks, const char* na
 // sums and their recorded pairs still stand (they are functions of exactly these values), and only the other columns
 // (v u alpha) are gathered into the resident order.  Anything else is a new state.
 struct SameCols { const double* a[5]; const double* b[5]; int nf; };
-__global__ void k_same_state(int n, const int* __restrict__ id, SameCols C, int* __restrict__ differ) {
+// number == nullptr: the host's row j is the particle numbered j (single rank, nothing ever removed).  Otherwise the host's
+// rows come with their numbers in the order sph_download_local gave them (domains): row i against resident row i.
+__global__ void k_same_state(int n, const int* __restrict__ id, const int* __restrict__ number, SameCols C, int* __restrict__ differ) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   bool d = false;
   if (i < n) {
-    const int j = id[i];
+    const int j = number ? i : id[i];
+    if (number) d = number[i] != id[i];
     for (int f = 0; f < C.nf; ++f) d |= __double_as_longlong(C.a[f][i]) != __double_as_longlong(C.b[f][j]);
   }
   if (__any_sync(FULL_MASK, d) && (threadIdx.x & 31) == 0) atomicOr(differ, 1);
@@ -1302,8 +1305,9 @@ __global__ void k_same_sinks(int ns, const double* __restrict__ resident, const 
 }
 
 static int upload_impl(sph_ctx* c, int64_t n_global, int64_t id_first, int64_t n, const double* const* src,
-                       int32_t ns, const double* const* ssrc, const double* srad, bool gas_on_device = false, unsigned late_mask = 0) {
+                       int32_t ns, const double* const* ssrc, const double* srad, bool gas_on_device = false, unsigned late_mask = 0, const int32_t* number = nullptr) {
   cudaSetDevice(c->device);
+  const bool was_dd = c->dd;
   c->dd = c->n_ranks > 1 && c->p.decomposition == 1;
   int64_t want = n;
   if (c->dd) {      // own share + halo + migration slack; every exported array is sized once here (the peers map them once)
@@ -1312,10 +1316,16 @@ static int upload_impl(sph_ctx* c, int64_t n_global, int64_t id_first, int64_t n
   }
   if (c->dd && !c->dd_acc_key) c->cap = 0;        // the exported arrays of the decomposition are sized in ensure_capacity
   // the resident state is a candidate when it came out of a step of this context with every row of its upload still there
-  const bool try_same = c->resident_check && c->n_ranks == 1 && !gas_on_device && !c->sink_extras && c->tree_valid && !c->pos_moved && c->steps_since_upload >= 1 &&
-                        n > 0 && c->n == n && c->n_upload == n && n_global == n && id_first == 0 && n <= c->cap && (ns > 0 ? ns : 1) == c->n_sink &&
-                        src[0] && src[1] && src[2] && src[3] && src[4] && src[5] && src[6] && src[7] && (src[9] || !c->dp.variable_h);
-  int r = ensure_capacity(c, want); if (r) return r;
+  // Domains: every rank hands back its own rows with their numbers, in the order sph_download_local gave them; the ranks
+  // agree through one all-reduce (a rank that cannot even try votes "different"), so they all keep or all replace.
+  const bool cols_ok = src[0] && src[1] && src[2] && src[3] && src[4] && src[5] && src[6] && src[7] && (src[9] || !c->dp.variable_h);
+  const bool try_any = c->resident_check && !gas_on_device && !c->sink_extras && c->tree_valid && !c->pos_moved && c->steps_since_upload >= 1 &&
+                       (c->n_ranks == 1 || (c->dd && was_dd));      // the same on every rank of a communicator
+  const bool local_ok = try_any && n > 0 && c->n == n && n <= c->cap && want <= c->cap && (ns > 0 ? ns : 1) == c->n_sink && cols_ok &&
+                        (c->dd ? (number != nullptr && n_global == c->n_global) : (c->n_upload == n && n_global == n && id_first == 0));
+  const bool try_same = try_any && (local_ok || c->dd);
+  int r = SPH_OK;
+  if (!try_same) { r = ensure_capacity(c, want); if (r) return r; }
   const int L = try_same ? (c->cur ^ 1) : 0;      // where the columns land
   // sinks as the context would hold them (dummy zero sink if none: F:698-707)
   std::vector<double> hb((size_t)SPH_MAX_SINKS * 11, 0.0);
@@ -1325,13 +1335,14 @@ static int upload_impl(sph_ctx* c, int64_t n_global, int64_t id_first, int64_t n
   c->late_pending = 0; c->late_permuted = false; c->late_n = 0;
   const unsigned geometry = try_same ? ((1u << 0) | (1u << 1) | (1u << 2) | (1u << 7) | (1u << 9)) : 0x7u;      // columns the compute stream waits for
   if (late_mask) late_mask &= ~geometry;
-  for (int f = 0; f < 10 && !gas_on_device; ++f) {
+  const bool land = !try_same || local_ok;         // domains: a rank that cannot try only votes (its columns go the plain way afterwards)
+  for (int f = 0; f < 10 && !gas_on_device && land; ++f) {
     if (src[f] && ((late_mask >> f) & 1u)) continue;       // follows on io_stream behind the first columns (below)
     if (src[f]) { if (n > 0) CK(cudaMemcpyAsync(c->st[L][f], src[f], (size_t)n * 8, cudaMemcpyHostToDevice, c->stream)); }
     else if (f == 8) CK(cudaMemsetAsync(c->st[L][f], 0, (size_t)std::max<int64_t>(n, 1) * 8, c->stream));            // alpha := 0, F:681
     else if (!try_same) { std::vector<double> hv((size_t)std::max<int64_t>(n, 1), c->p.h_fixed); CK(cudaMemcpyAsync(c->st[L][f], hv.data(), hv.size() * 8, cudaMemcpyHostToDevice, c->stream)); CK(cudaStreamSynchronize(c->stream)); }
   }
-  if (late_mask && n > 0) {      // sph_step_host: the other columns in the order their readers come (h: leaf cells, m: node sums, u: EOS, then v, alpha)
+  if (late_mask && n > 0 && land) {      // sph_step_host: the other columns in the order their readers come (h: leaf cells, m: node sums, u: EOS, then v, alpha)
     CK(cudaEventRecord(c->io_ev_xyz, c->stream));
     CK(cudaStreamWaitEvent(c->io_stream, c->io_ev_xyz, 0));
     const int order[7] = {9, 7, 6, 3, 4, 5, 8};
@@ -1351,10 +1362,20 @@ static int upload_impl(sph_ctx* c, int64_t n_global, int64_t id_first, int64_t n
     double* landed = c->sink_land;
     CK(cudaMemcpyAsync(landed, hb.data(), (size_t)8 * M * 8, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemsetAsync(c->d_same, 0, sizeof(int), c->stream));
-    LAUNCH(k_same_state, cdiv(n, 256), 256, 0, (int)n, c->id[cur], C, c->d_same);
-    LAUNCH(k_same_sinks, 1, SPH_MAX_SINKS, 0, c->n_sink, c->sink_buf, landed, c->d_same);
+    if (local_ok) {
+      const int* d_number = nullptr;
+      if (c->dd) { CK(cudaMemcpyAsync(c->pos, number, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream)); d_number = c->pos; }
+      LAUNCH(k_same_state, cdiv(n, 256), 256, 0, (int)n, c->id[cur], d_number, C, c->d_same);
+      LAUNCH(k_same_sinks, 1, SPH_MAX_SINKS, 0, c->n_sink, c->sink_buf, landed, c->d_same);
+    } else LAUNCH(k_set_int, 1, 1, 0, c->d_same, 1);
+    if (c->dd) { r = allreduce(c, c->d_same, 1, NC_INT32, NC_MAX); if (r) return r; }
     readback(c, c->h_rb + 8, c->d_same, sizeof(int));
     CK(cudaStreamSynchronize(c->stream));
+    if (c->h_rb[8] != 0 && !local_ok) {      // domains, and this rank could not even try (row count, capacity): the plain path from the start
+      r = ensure_capacity(c, want); if (r) return r;
+      c->tree_valid = false;                 // no second attempt
+      return upload_impl(c, n_global, id_first, n, src, ns, ssrc, srad, gas_on_device, late_mask, number);
+    }
     if (c->h_rb[8] == 0) {      // the resident state, handed back: keep it and everything derived from its geometry; v u alpha into the resident order
       ++c->resident_hits;
       c->nl_valid = false;
@@ -1363,7 +1384,8 @@ static int upload_impl(sph_ctx* c, int64_t n_global, int64_t id_first, int64_t n
       bool now = false;
       for (int k = 0; k < 5; ++k) {
         const int f = rest[k];
-        if ((c->late_pending >> f) & 1u) { c->late_src[f] = c->st[L][f]; c->late_dst[f] = c->st[cur][f]; }      // flush_late gathers it when its first reader is due
+        if (c->dd) CK(cudaMemcpyAsync(c->st[cur][f], c->st[L][f], (size_t)n * 8, cudaMemcpyDeviceToDevice, c->stream));      // rows came in resident order
+        else if ((c->late_pending >> f) & 1u) { c->late_src[f] = c->st[L][f]; c->late_dst[f] = c->st[cur][f]; }      // flush_late gathers it when its first reader is due
         else { pa.src[f] = c->st[L][f]; pa.dst[f] = c->st[cur][f]; now = true; }
       }
       c->late_perm = c->id[cur]; c->late_permuted = true;
@@ -1380,6 +1402,7 @@ static int upload_impl(sph_ctx* c, int64_t n_global, int64_t id_first, int64_t n
   c->n = n; c->n_upload = n_global; c->n_global = n_global; c->cur = L; c->tree_valid = false; c->pos_moved = true;
   c->far_valid = false; c->steps_since_upload = 0;
   if (n > 0) LAUNCH(k_iota_from, cdiv(n, 256), 256, 0, (int)n, (int)id_first, c->id[L]);
+  if (number && n > 0) CK(cudaMemcpyAsync(c->id[L], number, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
   c->n_sink = ns > 0 ? ns : 1;
   CK(cudaMemcpyAsync(c->sink_buf, hb.data(), hb.size() * 8, cudaMemcpyHostToDevice, c->stream));
   if (c->sink_spin) CK(cudaMemsetAsync(c->sink_spin, 0, (size_t)SPH_MAX_SINKS * 3 * 8, c->stream));   // F:695 spin = 0
@@ -1441,9 +1464,7 @@ int sph_upload_local(sph_ctx* c, int64_t n_global, int64_t id_first, const int32
   if (c->dp.variable_h && !h && n_local > 0) { c->err = "variable-h mode needs the smoothing-length column"; return SPH_ERR_ARG; }
   const double* src[10] = {x, y, z, vx, vy, vz, u, m, alpha, c->dp.variable_h ? h : nullptr};
   const double* ssrc[7] = {sx, sy, sz, svx, svy, svz, sm};
-  int r = upload_impl(c, n_global, id_first, n_local, src, ns, ssrc, srad); if (r) return r;
-  if (number && n_local > 0) { CK(cudaMemcpyAsync(c->id[0], number, (size_t)n_local * 4, cudaMemcpyHostToDevice, c->stream)); CK(cudaStreamSynchronize(c->stream)); }
-  return SPH_OK;
+  return upload_impl(c, n_global, id_first, n_local, src, ns, ssrc, srad, false, 0, number);
 }
 
 int sph_evaluate(sph_ctx* c, int32_t mask) {

@@ -45,12 +45,18 @@ def main():
         else:
             e.upload(b, s)
         dt, t = 0.01, 0.0
-        for _ in range(steps):
+        for k in range(steps):
+            if k > 0 and os.environ.get("SPH_TEST_ROUNDTRIP"):      # the host takes the state and hands it back before every step
+                if domains:
+                    numbers, bl = e.download_local(); sl = e.sinks_only()
+                    e.upload_local(n, bl, sl, numbers=numbers)
+                else:
+                    bl, sl = e.download(); e.upload(bl, sl)
             dt, t = e.step(dt, t)
         bb, ss = e.download()
         d = e.diag()
         c = e.counters()
-        extra = {"far_reuse": np.array([e.far_reuse_count()])}
+        extra = {"far_reuse": np.array([e.far_reuse_count()]), "resident_hits": np.array([e.resident_hits()])}
         if len(sys.argv) > 11 and sys.argv[11] == "tree":      # one more evaluation on the end state with exact counters: tree + neighbour sets
             e.set_exact_counters(True); e.evaluate(); e.set_exact_counters(False)
             tr = e.tree(); cnt, hsh, _, _ = e.neighbours(with_list=False)

@@ -84,6 +84,24 @@ def test_domains_far_reuse(world, built_engine, tmp_path):
         compare(res[r], ref, f"quiet world {world} rank {r}", 1e-10, 1e-10)
 
 
+@pytest.mark.parametrize("world", [2, 3])
+def test_domains_recognise_handed_back_state(world, built_engine, tmp_path):
+    """Every rank downloads its rows (sph_download_local) and hands them back (sph_upload_local) before every step: the
+    ranks recognise the state they hold (one all-reduce of the comparison flags) and end up bit for bit where the same
+    domains end up without the round trips."""
+    env = {"SPH_TEST_QUIET": "1"}
+    ref = run_ranks(tmp_path, f"ddr{world}", world, "host", MODE_VARIABLE_H, steps=4, env_extra=env, n=30_000, domains=1)
+    env2 = dict(env, SPH_TEST_ROUNDTRIP="1")
+    res = run_ranks(tmp_path, f"ddt{world}", world, "host", MODE_VARIABLE_H, steps=4, env_extra=env2, n=30_000, domains=1)
+    for r in range(world):
+        assert int(res[r]["resident_hits"][0]) == 3 and int(ref[r]["resident_hits"][0]) == 0, (r, res[r]["resident_hits"])
+        for k in ref[r]:
+            if k == "resident_hits":
+                continue
+            a, b = res[r][k], ref[r][k]
+            assert a.shape == b.shape and np.array_equal(a, b, equal_nan=True), (r, k)
+
+
 @pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
 def test_domains_nccl_two_gpus(reference, tmp_path):
     res = run_ranks(tmp_path, "ddn2", 2, "nccl", MODE_VARIABLE_H, steps=3, domains=1, extra="tree")
