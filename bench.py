@@ -408,7 +408,7 @@ def main():
         achieved = per_launch[dom][0] * (n / world) / (dom_ms * 1e-3) / 1e9       # one rank's launch processes n / world targets
         traffic = None; traffic_note = "no ncu capture at this particle count in profiles/"
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r2b_traffic.json")))
             if int(tr["particles"]) == n and world == 1:
                 traffic = tr["dram_bytes_per_launch"][per_launch[dom][1]]; traffic_note = tr.get("note", "")
         except Exception:

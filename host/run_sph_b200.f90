@@ -59,6 +59,19 @@ module sph_b200_c
       integer(c_int64_t), intent(out) :: n_gas
       integer(c_int32_t), intent(out) :: n_sink
     end function
+    ! upload + one loop body + download in one call (include/sph_b200.h: sph_step_host); gas_in / gas_out = 10 column
+    ! pointers (x y z vx vy vz u m alpha h), sink_in / sink_out = 8 (x y z vx vy vz m radius)
+    integer(c_int) function sph_step_host(ctx, n_gas, gas_in, n_sink, sink_in, dt, t, gas_out, sink_out, n_gas_out, n_sink_out) &
+        bind(C, name="sph_step_host")
+      import :: c_int, c_int32_t, c_int64_t, c_double, c_ptr
+      type(c_ptr), value :: ctx
+      integer(c_int64_t), value :: n_gas
+      type(c_ptr), intent(in) :: gas_in(10), sink_in(8), gas_out(10), sink_out(8)
+      integer(c_int32_t), value :: n_sink
+      real(c_double), intent(inout) :: dt, t
+      integer(c_int64_t), intent(out) :: n_gas_out
+      integer(c_int32_t), intent(out) :: n_sink_out
+    end function
     integer(c_int) function sph_sizes(ctx, n_gas, n_sink) bind(C, name="sph_sizes")
       import :: c_int, c_int32_t, c_int64_t, c_ptr
       type(c_ptr), value :: ctx
