@@ -102,8 +102,8 @@ struct sph_ctx {
   std::vector<void*> ipc_opened; int* d_flag = nullptr; void* d_blob = nullptr; size_t blob_cap = 0;
   int g0 = 0, g1 = 0, p0 = 0, p1 = 0;
   double* cons_partial = nullptr; double* cons_out = nullptr;   // sph_conserved: block partials, result slots
-  // far-field reuse of the gravity walk (sph_gravity.cuh): stored far sums, per-particle near / far split, the sinks and counters they were taken with
-  double *far_fx = nullptr, *far_fy = nullptr, *far_fz = nullptr, *far_hc2 = nullptr, *far_sink_a = nullptr; SinkSnap* far_snap = nullptr; unsigned long long* far_ctr = nullptr;
+  // far-field reuse of the gravity walk (sph_gravity.cuh): stored far sums of the tree terms, per-particle near / far split, the walk's counters
+  double *far_fx = nullptr, *far_fy = nullptr, *far_fz = nullptr, *far_hc2 = nullptr; unsigned long long* far_ctr = nullptr;
   bool far_valid = false; int far_reuse = 1; int64_t far_count = 0; bool far_want_store = false; int steps_since_upload = 0; double far_hcut = GW_HCUT;
   int* far_list = nullptr; int* far_cnt = nullptr; unsigned char* far_ovf = nullptr; size_t far_list_runs = 0; int far_slots = 128; bool far_lists = true; int far_n_ovf = 0;   // recorded near pairs: [run][slot][lane]
   // sph_step_host: copies under the compute.  Late fields = gas columns still on their way from the host when the tree build starts
@@ -751,11 +751,11 @@ __global__ void k_ctr_restore(WalkCounters* ctr, const unsigned long long* saved
 
 int run_gravity(sph_ctx* c, int do_grav, int do_sinks) {
   const int GWW = grav_warps(c);
-  // far-field reuse (sph_gravity.cuh): the full walk of a complete evaluation stores its far sums; while they stand
-  // (far_valid: same tree, same sinks, no h beyond its cutoff - decided at the end of step()), the next one walks only the near field
+  // far-field reuse (sph_gravity.cuh): the full walk stores the far sums of its tree terms; while they stand (far_valid: same
+  // tree, no h beyond its cutoff - decided at the end of step()), the next evaluation adds only the near field and the sinks
   // Stored only where the next evaluation can use it: by evaluation B of a step whose state stayed on the device since the
   // step before (a host that uploads before every step never reuses, and should not pay for the records)
-  const bool far_ok = c->far_reuse && do_grav && do_sinks && !c->dp.soft_hi && !c->exact_counters && !c->sink_extras;
+  const bool far_ok = c->far_reuse && do_grav && !c->dp.soft_hi && !c->exact_counters;
   const bool near_only = far_ok && c->far_valid;
   const bool far_on = far_ok && !near_only && c->far_want_store;
   if (near_only) ++c->far_count;
@@ -799,7 +799,7 @@ int run_gravity(sph_ctx* c, int do_grav, int do_sinks) {
     const bool lists = (far_on || near_only) && c->far_lists && c->far_list != nullptr;
     const FarField ff{c->far_fx, c->far_fy, c->far_fz, c->far_hc2, far_on ? 1 : 0, lists ? c->far_list : nullptr, c->far_cnt, c->far_ovf, c->far_slots, &c->sc->far_ovf};
     if (near_only) {
-      if (lists) LAUNCH(k_gravity_near, std::max(1, std::min(cdiv(ng, GN_WARPS), 16 * c->n_sm)), GN_WARPS * 32, gravity_smem(c, 0), ng, c->ggroups, c->dp, c->wnodes, s.x, s.y, s.z, s.h, c->d_gt, c->ax, c->ay, c->az, ff);
+      if (lists) LAUNCH(k_gravity_near, std::max(1, std::min(cdiv(ng, GN_WARPS), 16 * c->n_sm)), GN_WARPS * 32, gravity_smem(c, 0), ng, c->ggroups, c->dp, c->wnodes, s.x, s.y, s.z, s.h, s.m, c->d_gt, c->ax, c->ay, c->az, ns, c->S, c->sink_partial, ff);
       if (!lists || c->far_n_ovf > 0) {       // runs whose lists overflowed (or all of them without lists): the near-only walk
         LAUNCH(k_set_int, 1, 1, 0, c->work, 0);
         LAUNCH(k_gravity<1>, grid, GWW * 32, gravity_smem(c, GWW), 0, ng, c->ggroups, c->gbvh, c->dp, c->wnodes, s.x, s.y, s.z, s.h, s.m, c->d_gt,
@@ -825,10 +825,10 @@ int run_gravity(sph_ctx* c, int do_grav, int do_sinks) {
       c->sink_seg_cap = (size_t)(nst + nst / 8 + 64) * (nsk + 1) * 3;
       DA(c->sink_seg, c->sink_seg_cap); if (!c->dd) c->p2p_stale = true;
     }
-    if (do_sinks && !near_only && nseg > 0 && c->g1 > c->g0)
+    if (do_sinks && nseg > 0 && c->g1 > c->g0)
       LAUNCH(k_sink_seg_fold, cdiv((int64_t)nseg * c->n_sink * 3, 128), 128, 0, nseg, seg0, c->n_sink, c->seg_off, c->sink_partial, c->sink_seg);
     stage_end(c);
-    if (c->n_ranks > 1 && do_sinks && !c->dd && !near_only) {
+    if (c->n_ranks > 1 && do_sinks && !c->dd) {
       stage_begin(c, ST_COMM);
       std::vector<size_t> roff(c->n_ranks + 1);
       for (int r = 0; r <= c->n_ranks; ++r) roff[r] = (size_t)(r == c->n_ranks ? nst : c->rank_g[r] / GRAV_SEG) * c->n_sink * 3;
@@ -837,8 +837,7 @@ int run_gravity(sph_ctx* c, int do_grav, int do_sinks) {
       stage_end(c);
     }
     stage_begin(c, near_only ? ST_GRAV_NEAR : ST_GRAVITY);
-    if (near_only) CK(cudaMemsetAsync(c->S.ax, 0, (size_t)SPH_MAX_SINKS * 3 * 8, c->stream));      // domains: zeros into the all-reduce below; the sinks' own sums are the stored ones
-    else LAUNCH(k_sink_reduce, 1, 256, 0, nst, c->n_sink, c->sink_seg, c->S, do_sinks);
+    LAUNCH(k_sink_reduce, 1, 256, 0, nst, c->n_sink, c->sink_seg, c->S, do_sinks);
     stage_end(c);
     // domains: the segments are per rank (walk groups differ at domain boundaries), so the ranks' totals are added
     if (c->dd) {
@@ -854,18 +853,9 @@ int run_gravity(sph_ctx* c, int do_grav, int do_sinks) {
     }
   }
   stage_begin(c, near_only ? ST_GRAV_NEAR : ST_GRAVITY);
-  if (near_only) {       // sink accelerations and the walk's counters of the evaluation the far sums were taken in (same sinks, same gas, same accepted sets)
-    CK(cudaMemcpyAsync(c->S.ax, c->far_sink_a, (size_t)SPH_MAX_SINKS * 3 * 8, cudaMemcpyDeviceToDevice, c->stream));
-    LAUNCH(k_ctr_restore, 1, 1, 0, c->ctr, c->far_ctr);
-  } else {
-    LAUNCH(k_sink_pairs, 1, 32, 0, c->n_sink, c->S, c->dp.G, do_sinks);
-    if (far_on) {
-      CK(cudaMemcpyAsync(c->far_sink_a, c->S.ax, (size_t)SPH_MAX_SINKS * 3 * 8, cudaMemcpyDeviceToDevice, c->stream));
-      LAUNCH(k_sink_snapshot, 1, SPH_MAX_SINKS, 0, c->n_sink, c->S, c->far_snap);
-      LAUNCH(k_ctr_save, 1, 1, 0, c->ctr, c->far_ctr);
-      c->far_valid = true;
-    }
-  }
+  LAUNCH(k_sink_pairs, 1, 32, 0, c->n_sink, c->S, c->dp.G, do_sinks);
+  if (near_only) LAUNCH(k_ctr_restore, 1, 1, 0, c->ctr, c->far_ctr);      // the walk's counters of the evaluation the far sums were taken in (same accepted sets)
+  else if (far_on) { LAUNCH(k_ctr_save, 1, 1, 0, c->ctr, c->far_ctr); c->far_valid = true; }
   stage_end(c);
   return SPH_OK;
 }
@@ -1030,12 +1020,12 @@ int step(sph_ctx* c) {
   CK(cudaMemsetAsync(&c->sc->n_removed, 0, sizeof(int) * 2, c->stream));
   if (n_removed > 0) { if ((r = compact(c))) return r; }
   if (c->dd && n_removed_global > 0) { c->tree_valid = false; c->pos_moved = true; c->n_global -= n_removed_global; }      // every domain rebuilds when any lost a particle
-  // may evaluation A of the next step keep evaluation B's far-field gravity?  Same particles (no removal anywhere), the same
-  // sinks (bitwise), and no h beyond the cutoff its near / far split was taken with; domains agree through one all-reduce
+  // may evaluation A of the next step keep evaluation B's far-field gravity?  Same particles (no removal anywhere) and no h
+  // beyond the cutoff its near / far split was taken with; domains agree through one all-reduce
   const bool far_try = c->far_valid && n_removed == 0 && n_removed_global == 0;
   CK(cudaMemsetAsync(&c->sc->far_bad, 0, sizeof(int), c->stream));
   if (far_try) {
-    LAUNCH(k_far_check, cdiv(std::max<int64_t>(c->n, SPH_MAX_SINKS), T), T, 0, (int)c->n, c->dp, state_of(c, c->cur).h, c->far_hc2, c->S, &c->sc->n_sink, c->far_snap, &c->sc->far_bad);
+    LAUNCH(k_far_check, cdiv(c->n, T), T, 0, (int)c->n, c->dp, state_of(c, c->cur).h, c->far_hc2, &c->sc->far_bad);
     if (c->dd) { int r_ = allreduce(c, &c->sc->far_bad, 1, NC_INT32, NC_MAX); if (r_) return r_; }
   }
   readback(c, c->h_sc, c->sc, sizeof(SimScalars));
@@ -1163,8 +1153,6 @@ int sph_create(const sph_params* p, int32_t device, sph_ctx** out) {
   if ((r = dalloc(c, &c->nl_ctl, 4))) return fail(r);
   cudaMemset(c->nl_ctl, 0, 4 * sizeof(int));
   if ((r = dalloc(c, &c->d_nsel, 1))) return fail(r);
-  if ((r = dalloc(c, &c->far_sink_a, (size_t)SPH_MAX_SINKS * 3))) return fail(r);
-  if ((r = dalloc(c, &c->far_snap, 1))) return fail(r);
   if ((r = dalloc(c, &c->d_same, 1))) return fail(r);
   if ((r = dalloc(c, &c->sink_land, (size_t)SPH_MAX_SINKS * 8))) return fail(r);
   c->resident_check = getenv("SPH_B200_NO_RESIDENT_CHECK") ? 0 : 1;      // developer switch: every upload is a new state
@@ -1224,7 +1212,7 @@ int sph_destroy(sph_ctx* c) {
   F(c->dd_let_f[0]); F(c->dd_let_f[1]); F(c->dd_halo_flag); F(c->dd_halo_list); F(c->dd_halo_size); F(c->dd_halo_poff); F(c->dd_acc_key); F(c->dd_acc_rec);
   F(c->dd_accg_key[0]); F(c->dd_accg_key[1]); F(c->dd_accg_idx[0]); F(c->dd_accg_idx[1]); F(c->dd_accg_rec); F(c->dd_gid); F(c->dd_gpos); F(c->dd_gcnt); F(c->dd_goff); F(c->dd_gstage);
   F(c->cons_partial); F(c->cons_out); F(c->img_table); F(c->sink_spin);
-  F(c->far_fx); F(c->far_fy); F(c->far_fz); F(c->far_hc2); F(c->far_sink_a); F(c->far_snap); F(c->far_ctr); F(c->far_list); F(c->far_cnt); F(c->far_ovf); F(c->d_same); F(c->sink_land);
+  F(c->far_fx); F(c->far_fy); F(c->far_fz); F(c->far_hc2); F(c->far_ctr); F(c->far_list); F(c->far_cnt); F(c->far_ovf); F(c->d_same); F(c->sink_land);
   F(c->arrive); F(c->cnt); F(c->off); F(c->root); F(c->partial); F(c->cub_tmp); F(c->d_wt); F(c->d_dwt); F(c->d_gt);
   F(c->sink_buf); F(c->sink_partial); F(c->sink_seg); F(c->sc); F(c->ctr); F(c->work); F(c->keep); F(c->d_nsel); F(c->pos); F(c->stage_d); F(c->stage_d2);
   if (c->h_sc) cudaFreeHost(c->h_sc);

@@ -100,8 +100,9 @@ __device__ __forceinline__ bool grav_term(const double2 a, const double2 b, cons
 // involve h (soft = 0.001 x the fixed smoothing, F:275), so every accepted (node, particle) pair and its distance are
 // the same; only h changed (calc_smoothing, V:1152), and h enters a term only through g(dist/h) for dist < 2 h
 // (F:138-141).  The full walk (MODE 0) therefore adds the terms with d2 <= hc2 = 4 (GW_HCUT h)^2 and all the others
-// apart, and stores the far sum together with the gas <- sink terms; while the tree, the sinks and "4 h^2 <= hc2 for
-// every particle" stand (checked on the device at the end of every step), the next evaluation is the near-only walk
+// apart, and stores the far sum of the tree terms (the direct sink terms are taken anew in every evaluation: sinks move,
+// grow and, with a mass that is not a power of two, shift by an ulp in every accretion pass, F:497-501); while the tree and
+// "4 h^2 <= hc2 for every particle" stand (checked on the device at the end of every step), the next evaluation is the near-only walk
 // (MODE 1): subtrees whose cell cannot hold a centre of mass within sqrt(max hc2) of the run's box are dropped at
 // classification, the opening decisions on the others are the full walk's own, the near terms are evaluated with the
 // new h and added to the stored far sum.  Same terms as a full walk, summed in another order (rounding level).
@@ -120,25 +121,33 @@ __global__ void k_far_hcut(int n, DevParams P, const double* __restrict__ h, dou
   const double hc = factor * (P.variable_h ? h[i] : P.h_fixed);
   hc2[i] = 4.0 * hc * hc;
 }
-// end of a step: may the next evaluation keep the stored far sums?  bit 0: some h grew beyond its cutoff (or is NaN);
-// bit 1: the sinks are not the ones the far sums were taken with (accretion, creation, cull, merger)
-struct SinkSnap { int n; double x[SPH_MAX_SINKS], y[SPH_MAX_SINKS], z[SPH_MAX_SINKS], m[SPH_MAX_SINKS]; };
-__global__ void k_sink_snapshot(int n_sink, SinkArrays S, SinkSnap* snap) {
-  const int t = threadIdx.x;
-  if (t == 0) snap->n = n_sink;
-  if (t < n_sink) { snap->x[t] = S.x[t]; snap->y[t] = S.y[t]; snap->z[t] = S.z[t]; snap->m[t] = S.m[t]; }
-}
-__global__ void k_far_check(int n, DevParams P, const double* __restrict__ h, const double* __restrict__ hc2, SinkArrays S, const int* __restrict__ n_sink_now,
-                            const SinkSnap* __restrict__ snap, int* __restrict__ far_bad) {
+// end of a step: may the next evaluation keep the stored far sums?  Not when some h grew beyond its cutoff (or is NaN)
+__global__ void k_far_check(int n, DevParams P, const double* __restrict__ h, const double* __restrict__ hc2, int* __restrict__ far_bad) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  int bad = 0;
-  if (i < n && P.variable_h) { const double hi = h[i]; if (!(4.0 * hi * hi <= hc2[i])) bad = 1; }
-  if (blockIdx.x == 0 && threadIdx.x < SPH_MAX_SINKS) {
-    const int t = threadIdx.x, ns = *n_sink_now;
-    if (ns != snap->n) bad |= 2;
-    else if (t < ns && !(S.x[t] == snap->x[t] && S.y[t] == snap->y[t] && S.z[t] == snap->z[t] && S.m[t] == snap->m[t])) bad |= 2;
+  bool bad = false;
+  if (i < n && P.variable_h) { const double hi = h[i]; bad = !(4.0 * hi * hi <= hc2[i]); }
+  if (__any_sync(FULL_MASK, bad) && (threadIdx.x & 31) == 0) atomicOr(far_bad, 1);
+}
+
+// direct sink <-> gas (unsoftened) F:567-576 for the 32 particles of one run: the gas side goes into (gx, gy, gz), the
+// sink side into the run's slot of sink_partial (one warp sum per sink, no block barrier)
+__device__ __forceinline__ void sink_terms(const DevParams& P, const SinkArrays& S, int n_sink, bool live, double xi, double yi, double zi, double mi,
+                                           double& gx, double& gy, double& gz, double* __restrict__ run_partial) {
+  const int lane = threadIdx.x & 31;
+  for (int s = 0; s < n_sink; ++s) {
+    const double vx_ = xi - S.x[s], vy_ = yi - S.y[s], vz_ = zi - S.z[s];
+    const double dr = sqrt(vx_ * vx_ + vy_ * vy_ + vz_ * vz_);
+    const double d3 = dr * dr * dr;
+    double wx = P.G * vx_ / d3, wy = P.G * vy_ / d3, wz = P.G * vz_ / d3;    // F:572
+    const double ms = S.m[s];
+    double px = 0.0, py = 0.0, pz = 0.0;
+    if (live) {
+      gx -= ms * wx; gy -= ms * wy; gz -= ms * wz;                             // F:574
+      px = mi * wx; py = mi * wy; pz = mi * wz;                               // F:573
+    }
+    px = warp_sum(px); py = warp_sum(py); pz = warp_sum(pz);
+    if (lane == 0) { double* o = run_partial + (size_t)s * 3; o[0] = px; o[1] = py; o[2] = pz; }
   }
-  if (bad) atomicOr(far_bad, bad);
 }
 
 // dynamic smem: grav table (nq+1 doubles, padded to even) then one GravWarpSmem per warp
@@ -360,30 +369,15 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
       if (ln + nn > 0) evaluate_list(ln, nn);
       __syncwarp();
     }
-    if (MODE == 1) {       // stored far sum (tree terms beyond the split + gas <- sink terms) + the near terms at the new h
-      if (live) { ax[i] = F.fx[i] + nx; ay[i] = F.fy[i] + ny; az[i] = F.fz[i] + nz; }
-      continue;
-    }
 #pragma unroll
     for (int u = 1; u < GW_ILP; ++u) { gx[0] += gx[u]; gy[0] += gy[u]; gz[0] += gz[u]; }
-    // direct sink <-> gas (unsoftened) F:567-576; per-group partial sums of the sink side (no block barrier)
-    for (int s = 0; s < n_sink; ++s) {
-      const double vx_ = xi - S.x[s], vy_ = yi - S.y[s], vz_ = zi - S.z[s];
-      const double dr = sqrt(vx_ * vx_ + vy_ * vy_ + vz_ * vz_);
-      const double d3 = dr * dr * dr;
-      double wx = P.G * vx_ / d3, wy = P.G * vy_ / d3, wz = P.G * vz_ / d3;    // F:572
-      const double ms = S.m[s];
-      double px = 0.0, py = 0.0, pz = 0.0;
-      if (live) {
-        gx[0] -= ms * wx; gy[0] -= ms * wy; gz[0] -= ms * wz;                   // F:574
-        const double mi = m[i];
-        px = mi * wx; py = mi * wy; pz = mi * wz;                               // F:573
-      }
-      px = warp_sum(px); py = warp_sum(py); pz = warp_sum(pz);
-      if (lane == 0) {
-        double* o = sink_partial + ((size_t)(chunk - g_begin) * n_sink + s) * 3;
-        o[0] = px; o[1] = py; o[2] = pz;
-      }
+    if (MODE == 1) { gx[0] = live ? F.fx[i] : 0.0; gy[0] = live ? F.fy[i] : 0.0; gz[0] = live ? F.fz[i] : 0.0; }      // the stored far sum of the tree terms
+    else if (F.store && live) { F.fx[i] = gx[0]; F.fy[i] = gy[0]; F.fz[i] = gz[0]; }
+    // the sinks are not part of the stored sums: their terms are taken with the sinks as they are now, in every evaluation
+    sink_terms(P, S, n_sink, live, xi, yi, zi, live ? m[i] : 0.0, gx[0], gy[0], gz[0], sink_partial + (size_t)(chunk - g_begin) * n_sink * 3);
+    if (MODE == 1) {
+      if (live) { ax[i] = gx[0] + nx; ay[i] = gy[0] + ny; az[i] = gz[0] + nz; }
+      continue;
     }
     if (F.list) {          // near pairs recorded per lane; a lane that needed more slots sends its run to the near-only walk
       const int nc = W.ncnt[lane];
@@ -391,10 +385,7 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
       const bool over = __any_sync(FULL_MASK, nc > F.slots);
       if (lane == 0) { F.ovf[chunk] = over ? 1 : 0; if (over) atomicAdd(F.n_ovf, 1); }
     }
-    if (live) {
-      if (F.store) { F.fx[i] = gx[0]; F.fy[i] = gy[0]; F.fz[i] = gz[0]; }
-      ax[i] = gx[0] + W.nacc[0][lane]; ay[i] = gy[0] + W.nacc[1][lane]; az[i] = gz[0] + W.nacc[2][lane];
-    }
+    if (live) { ax[i] = gx[0] + W.nacc[0][lane]; ay[i] = gy[0] + W.nacc[1][lane]; az[i] = gz[0] + W.nacc[2][lane]; }
   }
   n_open = (unsigned long long)warp_sum_ll((long long)n_open); n_acc = (unsigned long long)warp_sum_ll((long long)n_acc);
   if (MODE == 0 && lane == 0 && do_grav) { atomicAdd(&ctr->grav_opened, n_open); atomicAdd(&ctr->grav_accepted, n_acc); }
@@ -409,8 +400,8 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
 #define GN_WARPS 8
 __global__ void __launch_bounds__(GN_WARPS * 32)
 k_gravity_near(int n_runs, const int2* __restrict__ groups, DevParams P, const WNode* __restrict__ wn, const double* __restrict__ x,
-               const double* __restrict__ y, const double* __restrict__ z, const double* __restrict__ h, const double* __restrict__ g_gt,
-               double* __restrict__ ax, double* __restrict__ ay, double* __restrict__ az, FarField F) {
+               const double* __restrict__ y, const double* __restrict__ z, const double* __restrict__ h, const double* __restrict__ m, const double* __restrict__ g_gt,
+               double* __restrict__ ax, double* __restrict__ ay, double* __restrict__ az, int n_sink, SinkArrays S, double* __restrict__ sink_partial, FarField F) {
   extern __shared__ __align__(16) double gsm[];
   double* gt = gsm;
   for (int i = threadIdx.x; i <= P.nq; i += blockDim.x) gt[i] = g_gt[i];
@@ -445,7 +436,9 @@ k_gravity_near(int n_runs, const int2* __restrict__ groups, DevParams P, const W
       const double2 a0 = __ldg(p0), b0 = __ldg(p0 + 1);
       grav_term<3>(a0, make_double2(b0.x, P.G * b0.y), on0, xi, yi, zi, inv_h, h2x4, 0.0, soft, gt, P.nq, P.dq, P.inv_dq, dum, dum, dum, nx, ny, nz);
     }
-    if (live) { ax[i] = F.fx[i] + nx; ay[i] = F.fy[i] + ny; az[i] = F.fz[i] + nz; }
+    double gx = live ? F.fx[i] : 0.0, gy = live ? F.fy[i] : 0.0, gz = live ? F.fz[i] : 0.0;      // far tree terms, then the sinks as they are now, then the near terms: the full walk's order
+    sink_terms(P, S, n_sink, live, xi, yi, zi, live ? m[i] : 0.0, gx, gy, gz, sink_partial + (size_t)run * n_sink * 3);
+    if (live) { ax[i] = gx + nx; ay[i] = gy + ny; az[i] = gz + nz; }
   }
 }
 

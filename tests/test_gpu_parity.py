@@ -447,6 +447,27 @@ def test_far_field_reuse_vs_oracle(mode, E, O):
             assert reused == 1
 
 
+def test_far_field_reuse_with_moving_sinks(E, O, monkeypatch):
+    """Three sinks off the origin with masses that are not powers of two, moving, tiny accretion radii (nothing is
+    removed): `initiate_sink_accretion` rewrites every sink position as (m x + 0) / m in every pass (F:497-501), so the
+    sinks change from step to step.  The stored far sums hold tree terms only - the sink terms are taken anew in every
+    evaluation - so the reuse stands, and the run follows the oracle."""
+    p = default_params(MODE_VARIABLE_H)
+    b, _ = ics.keplerian_disc(10_000, seed=23)
+    s = Sinks([0.3, 41.0, -37.0], [-0.2, 3.0, 11.0], [0.01, 0.4, -0.3], [0.01, -0.4, 0.9], [0.02, 5.9, -5.1], [0.0, 0.01, 0.02],
+              [0.7, 0.013, 0.021], [0.05, 0.05, 0.05])
+    o = O(p); o.upload(b, s)
+    with E(p) as e:
+        e.upload(b, s)
+        dto = dte = 0.01; to = te = 0.0
+        for _ in range(4):
+            dto, to = o.step(dto, to); dte, te = e.step(dte, te)
+            assert dto == dte and to == te and o.sizes() == e.sizes()
+        assert e.sizes() == (len(b), 3)
+        assert e.far_reuse_count() == 2            # evaluation A of steps 3 and 4
+        compare_state(o, e)
+
+
 def test_far_field_reuse_h_cutoff(E, monkeypatch):
     """A smoothing length that grows beyond the cutoff its near / far split was taken with voids the stored sums: the
     next evaluation walks the whole tree.  Forced here with a cutoff of 1.000001 h (test hook; default 1.1 h): every
