@@ -808,9 +808,13 @@ int run_gravity(sph_ctx* c, int do_grav, int do_sinks) {
     } else {
       LAUNCH(k_set_int, 1, 1, 0, c->work, 0);
       CK(cudaMemsetAsync(&c->sc->far_ovf, 0, sizeof(int), c->stream));
-      LAUNCH(k_far_hcut, cdiv(c->n, 256), 256, 0, (int)c->n, c->dp, s.h, far_on ? c->far_hcut : 1.0, c->far_hc2);
-      LAUNCH(k_gravity<0>, grid, GWW * 32, gravity_smem(c, GWW), 0, ng, c->ggroups, c->gbvh, c->dp, c->wnodes, s.x, s.y, s.z, s.h, s.m, c->d_gt,
-             c->ax, c->ay, c->az, do_grav, ns, c->S, c->sink_partial, c->ctr, c->work, c->grav_spill, &c->sc->err, ff);
+      if (far_on) {
+        LAUNCH(k_far_hcut, cdiv(c->n, 256), 256, 0, (int)c->n, c->dp, s.h, c->far_hcut, c->far_hc2);
+        LAUNCH(k_gravity<0>, grid, GWW * 32, gravity_smem(c, GWW), 0, ng, c->ggroups, c->gbvh, c->dp, c->wnodes, s.x, s.y, s.z, s.h, s.m, c->d_gt,
+               c->ax, c->ay, c->az, do_grav, ns, c->S, c->sink_partial, c->ctr, c->work, c->grav_spill, &c->sc->err, ff);
+      } else      // nothing to store (first step on a new state, exact counters, reuse switched off): the plain walk, one sum per particle
+        LAUNCH(k_gravity<2>, grid, GWW * 32, gravity_smem(c, GWW), 0, ng, c->ggroups, c->gbvh, c->dp, c->wnodes, s.x, s.y, s.z, s.h, s.m, c->d_gt,
+               c->ax, c->ay, c->az, do_grav, ns, c->S, c->sink_partial, c->ctr, c->work, c->grav_spill, &c->sc->err, ff);
     }
   }
 #ifdef GW_STATS
@@ -1181,6 +1185,7 @@ int sph_create(const sph_params* p, int32_t device, sph_ctx** out) {
   cudaFuncSetAttribute(k_force<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)force_smem(c, force_warps(c, false), false));
   cudaFuncSetAttribute(k_gravity<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gravity_smem(c, grav_warps(c)));
   cudaFuncSetAttribute(k_gravity<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gravity_smem(c, grav_warps(c)));
+  cudaFuncSetAttribute(k_gravity<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gravity_smem(c, grav_warps(c)));
   cudaFuncSetAttribute(k_gravity_near, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gravity_smem(c, 0));
   cudaFuncSetAttribute(k_neighbours, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   if (cudaGetLastError() != cudaSuccess) { c->err = "cudaFuncSetAttribute failed (was the library built for this GPU's architecture?)"; return fail(SPH_ERR_CUDA); }

@@ -75,6 +75,7 @@ __device__ __forceinline__ double fast_rsqrt(double x) {
 // KIND 1: near-list entry of the full walk: the term joins the near sum when d2 <= hc2, else the far sum.
 // KIND 2: near-only walk: only the terms with d2 <= hc2 (the far sum is the stored one).
 // KIND 3: a recorded near pair (d2 <= hc2 held when the full walk recorded it): near sum, no test.
+// KIND 4: near-list entry of a full walk that stores nothing: one sum, like KIND 0 but with the softening test.
 template <int KIND>
 __device__ __forceinline__ bool grav_term(const double2 a, const double2 b, const bool on, const double xi, const double yi,
                                           const double zi, const double inv_h, const double h2x4, const double hc2, const double soft, const double* __restrict__ gt,
@@ -86,7 +87,7 @@ __device__ __forceinline__ bool grav_term(const double2 a, const double2 b, cons
   double gm = b.y;
   if (KIND != 0) { if (d2 <= h2x4) gm *= table_lerp1(gt, nq, dq, inv_dq, (d2 * rs) * inv_h); }      // far entries: d2 > 4 h^2 for every particle of the run (decided at listing)
   const double f = gm * (rs * rs * rs);
-  if (KIND == 0) { if (on) { gx = fma(-f, dx, gx); gy = fma(-f, dy, gy); gz = fma(-f, dz, gz); } return false; }
+  if (KIND == 0 || KIND == 4) { if (on) { gx = fma(-f, dx, gx); gy = fma(-f, dy, gy); gz = fma(-f, dz, gz); } return false; }
   else {
     const bool nr = on && (KIND == 3 || d2 <= hc2);
     if (nr) { nx = fma(-f, dx, nx); ny = fma(-f, dy, ny); nz = fma(-f, dz, nz); }
@@ -151,7 +152,8 @@ __device__ __forceinline__ void sink_terms(const DevParams& P, const SinkArrays&
 }
 
 // dynamic smem: grav table (nq+1 doubles, padded to even) then one GravWarpSmem per warp
-// MODE 0: full walk; MODE 1: near-only walk on top of the stored far sums (see "Far-field reuse" above)
+// MODE 0: full walk that stores the far sums and records the near pairs; MODE 1: near-only walk on top of the stored far
+// sums (see "Far-field reuse" above); MODE 2: full walk that stores nothing (no near / far split: one sum per particle)
 template <int MODE>
 __global__ void __launch_bounds__(GW_WARPS * 32, 1)
 k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox* __restrict__ gbox, DevParams P,
@@ -185,20 +187,22 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
     const double xi = live ? x[i] : 0.0, yi = live ? y[i] : 0.0, zi = live ? z[i] : 0.0;
     const double hi = live ? (P.variable_h ? h[i] : P.h_fixed) : 1.0;
     const double inv_h = 1.0 / hi, h2x4 = 4.0 * hi * hi;
-    const double hc2 = live ? F.hc2[i] : 0.0;                                // >= h2x4: the near / far split of the sums
+    constexpr bool FULL = MODE != 1, SPLIT = MODE == 0;
+    const double hc2 = MODE == 2 ? (live ? h2x4 : 0.0) : (live ? F.hc2[i] : 0.0);      // >= h2x4: the near / far split of the sums
     const double soft = P.soft_hi ? 0.001 * hi : 0.001 * P.h_fixed;          // F:275 | V:296 | T:298
     double gx[GW_ILP], gy[GW_ILP], gz[GW_ILP];
 #pragma unroll
     for (int u = 0; u < GW_ILP; ++u) gx[u] = gy[u] = gz[u] = 0.0;
     double nx = 0.0, ny = 0.0, nz = 0.0;                                     // terms with d2 <= hc2
-    if (MODE == 0) { W.nacc[0][lane] = 0.0; W.nacc[1][lane] = 0.0; W.nacc[2][lane] = 0.0; W.hpar[0][lane] = inv_h; W.hpar[1][lane] = h2x4; W.hpar[2][lane] = hc2; W.ncnt[lane] = 0; }
+    if (FULL) { W.hpar[0][lane] = inv_h; W.hpar[1][lane] = h2x4; }
+    if (SPLIT) { W.nacc[0][lane] = 0.0; W.nacc[1][lane] = 0.0; W.nacc[2][lane] = 0.0; W.hpar[2][lane] = hc2; W.ncnt[lane] = 0; }
     if (MODE == 1 && F.list && !F.ovf[chunk]) continue;                      // near-only walk behind k_gravity_near: only the runs whose lists overflowed
 
     // The list is filled from both ends: far entries (no particle of the run lies within 2 h of the node: W = 1, F:138-141,
     // no softening test at all) from slot 0 upwards, the others from the last slot downwards.
     auto evaluate_list = [&](int nfar, int nnear) {
       int k = 0;
-      if (MODE == 0) {
+      if (FULL) {
         for (; k + GW_ILP <= nfar; k += GW_ILP) {          // GW_ILP independent chains per trip
 #pragma unroll
           for (int u = 0; u < GW_ILP; ++u)
@@ -207,10 +211,10 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
         for (; k < nfar; ++k) grav_term<0>(W.lxy[k], W.lzg[k], (W.lmask[k] >> lane) & 1u, xi, yi, zi, 0.0, 0.0, 0.0, soft, gt, P.nq, P.dq, P.inv_dq, gx[0], gy[0], gz[0], nx, ny, nz);
         if (nnear == 0) return;
       }
-      constexpr int NK = MODE == 0 ? 1 : 2;
-      const double e_inv_h = MODE == 0 ? W.hpar[0][lane] : inv_h, e_h2x4 = MODE == 0 ? W.hpar[1][lane] : h2x4, e_hc2 = MODE == 0 ? W.hpar[2][lane] : hc2;
-      if (MODE == 0) { nx = W.nacc[0][lane]; ny = W.nacc[1][lane]; nz = W.nacc[2][lane]; }
-      const bool rec = MODE == 0 && F.list != nullptr;                       // record the node of every term that joins the near sum
+      constexpr int NK = MODE == 0 ? 1 : MODE == 1 ? 2 : 4;
+      const double e_inv_h = FULL ? W.hpar[0][lane] : inv_h, e_h2x4 = FULL ? W.hpar[1][lane] : h2x4, e_hc2 = SPLIT ? W.hpar[2][lane] : hc2;
+      if (SPLIT) { nx = W.nacc[0][lane]; ny = W.nacc[1][lane]; nz = W.nacc[2][lane]; }
+      const bool rec = SPLIT && F.list != nullptr;                           // record the node of every term that joins the near sum
       int nc = rec ? W.ncnt[lane] : 0;
       int* const lst = rec ? F.list + ((size_t)chunk * F.slots) * 32 + lane : nullptr;
       k = GW_LIST - nnear;
@@ -228,7 +232,7 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
         const bool hit = grav_term<NK>(W.lxy[k], W.lzg[k], (W.lmask[k] >> lane) & 1u, xi, yi, zi, e_inv_h, e_h2x4, e_hc2, soft, gt, P.nq, P.dq, P.inv_dq, gx[0], gy[0], gz[0], nx, ny, nz);
         if (rec && hit) { if (nc < F.slots) lst[(size_t)nc * 32] = W.lidx[k]; ++nc; }
       }
-      if (MODE == 0) { W.nacc[0][lane] = nx; W.nacc[1][lane] = ny; W.nacc[2][lane] = nz; if (rec) W.ncnt[lane] = nc; }
+      if (SPLIT) { W.nacc[0][lane] = nx; W.nacc[1][lane] = ny; W.nacc[2][lane] = nz; if (rec) W.ncnt[lane] = nc; }
     };
 
     GWS(0, 1);
@@ -338,15 +342,15 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
           if (lane == L) { acc_mask = balAcc; open_mask = balOpen; }
         }
         // ---- lane = node again: accepted (node, lane set) pairs join the interaction list, opened ones push their child block
-        if (MODE == 0) { n_acc += __popc(acc_mask); n_open += __popc(open_mask); }
+        if (FULL) { n_acc += __popc(acc_mask); n_open += __popc(open_mask); }
         const bool ins0 = acc_mask != 0u && nm > 0.0;                               // F:279: massless nodes add nothing
         const bool insn = ins0 && !(dmin2 > nearf);                                 // some particle of the run may be within the near / far split of it
-        const bool ins = MODE == 0 ? ins0 : insn;
-        const unsigned balL = MODE == 0 ? __ballot_sync(FULL_MASK, ins && !insn) : 0u, balN = __ballot_sync(FULL_MASK, insn);
+        const bool ins = FULL ? ins0 : insn;
+        const unsigned balL = FULL ? __ballot_sync(FULL_MASK, ins && !insn) : 0u, balN = __ballot_sync(FULL_MASK, insn);
         if (ins) {
           const int pos = insn ? GW_LIST - 1 - (nn + __popc(balN & lt_mask)) : ln + __popc(balL & lt_mask);
           W.lxy[pos] = make_double2(ncx, ncy); W.lzg[pos] = make_double2(ncz, P.G * nm); W.lmask[pos] = acc_mask;
-          if (MODE == 0) W.lidx[pos] = e.x;
+          if (SPLIT) W.lidx[pos] = e.x;
         }
         nn += __popc(balN);
         ln += __popc(balL);
@@ -372,23 +376,26 @@ k_gravity(int g_begin, int g_end, const int2* __restrict__ groups, const BvhBox*
 #pragma unroll
     for (int u = 1; u < GW_ILP; ++u) { gx[0] += gx[u]; gy[0] += gy[u]; gz[0] += gz[u]; }
     if (MODE == 1) { gx[0] = live ? F.fx[i] : 0.0; gy[0] = live ? F.fy[i] : 0.0; gz[0] = live ? F.fz[i] : 0.0; }      // the stored far sum of the tree terms
-    else if (F.store && live) { F.fx[i] = gx[0]; F.fy[i] = gy[0]; F.fz[i] = gz[0]; }
+    else if (SPLIT && F.store && live) { F.fx[i] = gx[0]; F.fy[i] = gy[0]; F.fz[i] = gz[0]; }
     // the sinks are not part of the stored sums: their terms are taken with the sinks as they are now, in every evaluation
     sink_terms(P, S, n_sink, live, xi, yi, zi, live ? m[i] : 0.0, gx[0], gy[0], gz[0], sink_partial + (size_t)(chunk - g_begin) * n_sink * 3);
     if (MODE == 1) {
       if (live) { ax[i] = gx[0] + nx; ay[i] = gy[0] + ny; az[i] = gz[0] + nz; }
       continue;
     }
-    if (F.list) {          // near pairs recorded per lane; a lane that needed more slots sends its run to the near-only walk
+    if (SPLIT && F.list) {          // near pairs recorded per lane; a lane that needed more slots sends its run to the near-only walk
       const int nc = W.ncnt[lane];
       F.cnt[(size_t)chunk * 32 + lane] = nc;
       const bool over = __any_sync(FULL_MASK, nc > F.slots);
       if (lane == 0) { F.ovf[chunk] = over ? 1 : 0; if (over) atomicAdd(F.n_ovf, 1); }
     }
-    if (live) { ax[i] = gx[0] + W.nacc[0][lane]; ay[i] = gy[0] + W.nacc[1][lane]; az[i] = gz[0] + W.nacc[2][lane]; }
+    if (live) {
+      if (SPLIT) { ax[i] = gx[0] + W.nacc[0][lane]; ay[i] = gy[0] + W.nacc[1][lane]; az[i] = gz[0] + W.nacc[2][lane]; }
+      else { ax[i] = gx[0]; ay[i] = gy[0]; az[i] = gz[0]; }
+    }
   }
   n_open = (unsigned long long)warp_sum_ll((long long)n_open); n_acc = (unsigned long long)warp_sum_ll((long long)n_acc);
-  if (MODE == 0 && lane == 0 && do_grav) { atomicAdd(&ctr->grav_opened, n_open); atomicAdd(&ctr->grav_accepted, n_acc); }
+  if (MODE != 1 && lane == 0 && do_grav) { atomicAdd(&ctr->grav_opened, n_open); atomicAdd(&ctr->grav_accepted, n_acc); }
 #ifdef GW_STATS
   if (lane == 0) for (int k = 0; k < 16; ++k) if (gws[k]) atomicAdd(&gw_stats[k], gws[k]);
 #endif
