@@ -520,6 +520,24 @@ def test_step_host_equals_upload_step_download(mode, removals, E):
             assert len(b1) < len(b)
 
 
+def test_step_host_two_word_keys(E):
+    """Pairs closer than root_size/2^21: the first tree build of the call finds a 63-bit key collision and repeats itself
+    with two-word keys - while the late columns of sph_step_host are still on their way (they are re-ordered before the
+    second build).  Bit-identical to the three separate calls."""
+    p = default_params(MODE_VARIABLE_H)
+    b, s = ics.keplerian_disc(5_000, seed=31)
+    for a_, c_, eps in ((10, 11, 3e-7), (200, 201, 5e-9), (3000, 3001, 2e-10)):
+        b.x[c_] = b.x[a_] + eps; b.y[c_] = b.y[a_] - 0.5 * eps; b.z[c_] = b.z[a_] + 0.25 * eps
+    with E(p) as e1, E(p) as e2:
+        e1.upload(b, s); dt1, t1 = e1.step(0.01, 0.0); b1, s1 = e1.download()
+        ob, os_ = Bodies.empty(len(b)), Sinks.empty(len(s) + 8)
+        dt2, t2, n2, ns2 = e2.step_host(b, s, 0.01, 0.0, into=(ob, os_))
+        assert (dt1, t1, len(b1), len(s1)) == (dt2, t2, n2, ns2)
+        for f in GAS_FIELDS:
+            assert np.array_equal(getattr(b1, f), getattr(ob, f)[:n2]), f
+        assert np.max(e2.tree()["level"]) > 21
+
+
 @pytest.mark.parametrize("mode", [MODE_VARIABLE_H, MODE_FIXED_H])
 def test_resident_upload_is_recognised(mode, E):
     """A host that passes the state through every step (upload, step, download) hands back what it was given: the context
