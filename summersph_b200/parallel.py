@@ -1,10 +1,12 @@
-"""Multi-GPU plumbing: one process (or thread) per GPU, NCCL communicator owned by the engine.
+"""Multi-GPU plumbing: one process per GPU, the communicator (NCCL, or host shared memory for tests) owned by the engine.
 
-Design: the particle set is replicated on every rank (64M particles need ~26 GB of
-the 180 GB), the tree is built redundantly, and the expensive target work — density, gravity, SPH pair
-forces, h iteration — is sharded by contiguous Morton slices of walk groups; results travel with an
-all-gather-v over NVLink, the sink sums and the dt minimum with all-reduces.  Every rank therefore holds
-bit-identical state after each step, and an N-rank run is bit-identical to the 1-rank run.
+Two forms, chosen by `params.decomposition`:
+  1 - Morton-ordered domains: every rank owns a contiguous range of the global descent-key order plus a halo; top tree by
+      all-gather, locally essential tree pulled from the peers, migration at every tree build; results equal the
+      single-rank run to rounding (order, keys, leaf cells, neighbour sets and counters bit for bit).  `bench.py --gpus N`.
+  0 - replicated state: every rank holds all particles and builds the whole tree, the target work is sharded by
+      contiguous Morton slices of walk groups (`slice_bounds`), results travel by peer-memory pushes; bit-identical to
+      the single-rank run.
 """
 
 
